@@ -1,0 +1,226 @@
+"""ctypes front-end of the parity oracle (oracle/drone2d_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package never imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libdrone2d_oracle.so")
+MAX_TARGETS = 8
+TRAJ_CAP = 2048
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("dt", C.c_double), ("map_scale", C.c_double), ("map_w", C.c_double), ("map_h", C.c_double),
+        ("agent_radius", C.c_double), ("drone_max_acc", C.c_double), ("drone_radius", C.c_double),
+        ("drone_max_yaw_speed", C.c_double), ("view_depth", C.c_double), ("view_range", C.c_double),
+        ("max_flight_time", C.c_double), ("var_cam", C.c_double), ("drone_max_speed", C.c_double),
+        ("planner", C.c_int32), ("n_rays", C.c_int32), ("gw", C.c_int32), ("gh", C.c_int32), ("local", C.c_int32),
+        ("n_u", C.c_int32), ("n_samp", C.c_int32), ("n_way", C.c_int32), ("pad0", C.c_int32),
+        ("u_space", C.c_double * 64),
+        ("t_samp", C.c_double * 32), ("t_samp2", C.c_double * 32),
+        ("t_way", C.c_double * 64), ("t_way2", C.c_double * 64), ("t_way_x2", C.c_double * 64),
+        ("n_yaw", C.c_int32), ("pad1", C.c_int32),
+        ("v_yaw_space", C.c_double * 16),
+        ("ox_cos_thresh", C.c_double),
+    ]
+
+
+_P = C.POINTER
+
+
+class Env(C.Structure):
+    _fields_ = [
+        ("p", Params), ("n", C.c_int32), ("pad", C.c_int32),
+        ("apos", _P(C.c_double)), ("apref", _P(C.c_double)), ("arad", _P(C.c_double)),
+        ("gt", _P(C.c_uint8)), ("belief", _P(C.c_uint8)), ("hit", _P(C.c_int8)),
+        ("x", C.c_double), ("y", C.c_double), ("yaw", C.c_double), ("vx", C.c_double), ("vy", C.c_double),
+        ("steps", C.c_int32), ("state_machine", C.c_int32), ("fail_count", C.c_int32),
+        ("target_cursor", C.c_int32), ("n_targets", C.c_int32),
+        ("collision", C.c_int32), ("dead_lock", C.c_int32), ("freezing", C.c_int32), ("done", C.c_int32),
+        ("replan", C.c_int32), ("plan_ok", C.c_int32), ("planned", C.c_int32), ("newly_tracked", C.c_int32),
+        ("targets", (C.c_double * 2) * MAX_TARGETS), ("target", C.c_double * 4),
+        ("tracked_agent", C.c_int64),
+        ("trk_active", _P(C.c_uint8)), ("trk_mu", _P(C.c_double)), ("trk_sigma", _P(C.c_double)),
+        ("trk_radius", _P(C.c_double)), ("trk_ts", _P(C.c_int64)),
+        ("buf_count", C.c_int64), ("buf_ts", C.c_int64),
+        ("traj_len", C.c_int32), ("traj_head", C.c_int32),
+        ("traj_pos", _P(C.c_double)), ("traj_vel", _P(C.c_double)),
+        ("local_map", _P(C.c_uint8)), ("yaw_obs", C.c_float), ("pad2", C.c_int32),
+        ("ox_last", _P(C.c_double)), ("ox_swep", _P(C.c_double)),
+        ("n_samples", C.c_int64),
+    ]
+
+
+_lib = None
+
+
+def build(force=False):
+    if force or not os.path.isfile(_LIB_PATH) or \
+            os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "drone2d_oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libdrone2d_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.d2do_create.restype = _P(Env)
+        L.d2do_create.argtypes = [_P(Params), C.c_int]
+        L.d2do_destroy.argtypes = [_P(Env)]
+        for name in ("d2do_agents_step", "d2do_trackers_update", "d2do_local_map"):
+            getattr(L, name).argtypes = [_P(Env)]
+            getattr(L, name).restype = None
+        for name in ("d2do_cast_rays", "d2do_replan_check", "d2do_plan", "d2do_is_collide"):
+            getattr(L, name).argtypes = [_P(Env)]
+            getattr(L, name).restype = C.c_int
+        L.d2do_step.argtypes = [_P(Env), C.c_double]
+        L.d2do_step.restype = C.c_int
+        L.d2do_oxford_plan.argtypes = [_P(Env)]
+        L.d2do_oxford_plan.restype = C.c_double
+        L.d2do_run_many.argtypes = [_P(_P(Env)), C.c_int, C.c_int, _P(C.c_double)]
+        L.d2do_run_many.restype = C.c_int64
+        L.d2do_sizeof_params.restype = C.c_size_t
+        L.d2do_sizeof_env.restype = C.c_size_t
+        assert L.d2do_sizeof_params() == C.sizeof(Params), (L.d2do_sizeof_params(), C.sizeof(Params))
+        assert L.d2do_sizeof_env() == C.sizeof(Env), (L.d2do_sizeof_env(), C.sizeof(Env))
+        _lib = L
+    return _lib
+
+
+def oxford_cos_threshold(view_range_deg):
+    """c* = min{c : np.arccos(c) <= radians(view_range/2)}, bisection over doubles with the ARRAY
+    np.arccos (the SIMD loop Oxford.get_view_map runs, yaw_planner.py:78)."""
+    import math
+    ang = math.radians(view_range_deg / 2)
+
+    def ok(c):
+        return bool(np.arccos(np.array([c, c, c, c, c, c, c, c, c]))[0] <= ang)
+
+    lo, hi = -1.0, 1.0  # ok(hi) True, ok(lo) False unless the wedge is the full circle
+    if ok(lo):
+        return -1.0
+    while True:
+        mid = lo + (hi - lo) / 2
+        if mid == lo or mid == hi:
+            break
+        if ok(mid):
+            hi = mid
+        else:
+            lo = mid
+    return hi
+
+
+def make_params(dt=0.1, map_scale=10, map_size=(500, 500), agent_radius=10, drone_max_acceleration=40,
+                drone_radius=10, drone_max_yaw_speed=80, drone_view_depth=80, drone_view_range=90,
+                max_flight_time=80, var_cam=0, drone_max_speed=40, planner="NoMove", strip_width=10, **_ignored):
+    """Builds the C params block with the reference's own numpy expressions for the lookup tables
+    (traj_planner.py:98-104,180,212; yaw_planner.py:65; utils.py:587)."""
+    import math
+    p = Params()
+    p.dt, p.map_scale, p.map_w, p.map_h = dt, map_scale, map_size[0], map_size[1]
+    p.agent_radius, p.drone_max_acc, p.drone_radius = agent_radius, drone_max_acceleration, drone_radius
+    p.drone_max_yaw_speed, p.view_depth, p.view_range = drone_max_yaw_speed, drone_view_depth, drone_view_range
+    p.max_flight_time, p.var_cam, p.drone_max_speed = max_flight_time, var_cam, drone_max_speed
+    p.planner = {"NoMove": 0, "Primitive": 1}[planner]
+    p.n_rays = math.ceil(map_size[0] / strip_width)
+    p.gw, p.gh = map_size[0] // map_scale, map_size[1] // map_scale
+    p.local = 4 * (drone_view_depth // map_scale) + 1
+    if drone_max_speed <= 40:
+        u = np.arange(-drone_max_acceleration, drone_max_acceleration, 0.4 * drone_max_speed - 5)
+    else:
+        u = np.arange(-drone_max_acceleration, drone_max_acceleration, 4)
+    pdt = 2
+    sample_num = drone_max_speed * pdt // map_scale
+    ts = np.arange(0, pdt, pdt / sample_num)
+    tw = np.arange(pdt, 0, -dt)
+    assert len(u) <= 64 and len(ts) <= 32 and len(tw) <= 64
+    p.n_u, p.n_samp, p.n_way = len(u), len(ts), len(tw)
+    for i, v in enumerate(u):
+        p.u_space[i] = float(v)
+    for i, t in enumerate(ts):
+        p.t_samp[i] = float(t)
+        p.t_samp2[i] = float(t ** 2)      # numpy-scalar power == libm pow(t, 2.0)
+    for i, t in enumerate(tw):
+        p.t_way[i] = float(t)
+        p.t_way2[i] = float(t ** 2)
+        p.t_way_x2[i] = float(2 * t)
+    vy = np.arange(-drone_max_yaw_speed, drone_max_yaw_speed, drone_max_yaw_speed / 3)
+    p.n_yaw = len(vy)
+    for i, v in enumerate(vy):
+        p.v_yaw_space[i] = float(v)
+    p.ox_cos_thresh = oxford_cos_threshold(drone_view_range)
+    return p
+
+
+class OracleEnv(object):
+    """One CPU env.  World state is supplied by the caller (arrays from the reference or from the product's
+    host-side world generator); numpy views alias the C arrays."""
+
+    def __init__(self, params, agent_pos, agent_pref, agent_radius, gt_grid, tracker_radius=None,
+                 drone=(50.0, 50.0, 270.0), targets=((50, 460),)):
+        L = lib()
+        self.n = int(len(agent_radius))
+        self._params = params
+        self._ptr = L.d2do_create(C.byref(params), self.n)
+        self.c = self._ptr.contents
+        n = max(self.n, 1)
+        cells = params.gw * params.gh
+        as_arr = np.ctypeslib.as_array
+        self.apos = as_arr(self.c.apos, (n, 2))
+        self.apref = as_arr(self.c.apref, (n, 2))
+        self.arad = as_arr(self.c.arad, (n,))
+        self.gt = as_arr(self.c.gt, (params.gw, params.gh))
+        self.belief = as_arr(self.c.belief, (params.gw, params.gh))
+        self.hit = as_arr(self.c.hit, (n,))
+        self.trk_active = as_arr(self.c.trk_active, (n,))
+        self.trk_mu = as_arr(self.c.trk_mu, (n, 4))
+        self.trk_sigma = as_arr(self.c.trk_sigma, (n, 16))
+        self.trk_radius = as_arr(self.c.trk_radius, (n,))
+        self.trk_ts = as_arr(self.c.trk_ts, (n,))
+        self.traj_pos = as_arr(self.c.traj_pos, (TRAJ_CAP, 2))
+        self.traj_vel = as_arr(self.c.traj_vel, (TRAJ_CAP, 2))
+        self.local_map = as_arr(self.c.local_map, (params.local, params.local))
+        self.ox_last = as_arr(self.c.ox_last, (params.gw, params.gh))
+        if self.n:
+            self.apos[:self.n] = np.asarray(agent_pos, dtype=np.float64).reshape(self.n, 2)
+            self.apref[:self.n] = np.asarray(agent_pref, dtype=np.float64).reshape(self.n, 2)
+            self.arad[:self.n] = np.asarray(agent_radius, dtype=np.float64)
+            if tracker_radius is not None:
+                self.trk_radius[:self.n] = np.asarray(tracker_radius, dtype=np.float64)
+        self.gt[:] = np.asarray(gt_grid, dtype=np.uint8)
+        self.c.x, self.c.y, self.c.yaw = float(drone[0]), float(drone[1]), float(drone[2])
+        self.c.n_targets = len(targets)
+        for i, t in enumerate(targets):
+            self.c.targets[i][0], self.c.targets[i][1] = float(t[0]), float(t[1])
+        # Planner.__init__ traj_planner.py:22: target = [drone.x, drone.y, 0, 0]
+        self.c.target[0], self.c.target[1] = float(drone[0]), float(drone[1])
+
+    def step(self, a):
+        return bool(lib().d2do_step(self._ptr, float(a)))
+
+    def oxford_plan(self):
+        return float(lib().d2do_oxford_plan(self._ptr))
+
+    def trajectory(self):
+        h, l = self.c.traj_head, self.c.traj_len
+        return self.traj_pos[h:h + l].copy(), self.traj_vel[h:h + l].copy()
+
+    def close(self):
+        if self._ptr is not None:
+            lib().d2do_destroy(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
