@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s (and rays/s) of the batched drone2d hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5] [--envs B]
+
+A "step" is one pass of Drone2DEnv2.step over one batch of synthetic (seeded) environments.  Default workload is
+BASELINE.json configs[1]: empty_map.npy, 4096 envs per GPU, 10 agents, perception + dynamics (NoMove planner,
+Kalman trackers on as in the reference).  For N > 1 launch with torchrun (one rank per GPU, weak scaling: every
+rank steps its own 4096 envs; the only collective is one NCCL all-reduce of the episode statistics).
+
+Prints ONE JSON line (rank 0).  `value`: whole-job env-steps/s with inputs resident in HBM (per-step CUDA events,
+L2 flushed between steps, flush untimed).  `e2e`: the same metric through d2d_step_host with pinned HOST buffers
+(actions H2D + observation D2H inside the timed region).  `roofline`: algorithmic bytes (SURVEY.md §8d:
+2406 + 104*N per env-step) / measured kernel time vs the measured HBM copy peak.  `cpu_baseline`: the oracle port
+of the reference path (oracle/drone2d_oracle.c) on the host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+CONFIGS = {
+    # BASELINE.json configs[1..4] (SURVEY.md §8d parameters)
+    2: dict(name="configs[1]: empty_map.npy, 4096 envs/GPU, 10 agents, perception+dynamics (NoMove)", envs=4096,
+            params=dict(planner="NoMove", static_map="maps/empty_map.npy", agent_number=10, agent_radius=15,
+                        agent_max_speed=20, map_id=1)),
+    3: dict(name="configs[2]: random_map_0.npy, 65536 envs/GPU, 20 agents radius 15", envs=65536,
+            params=dict(planner="NoMove", static_map="maps/random_map_0.npy", agent_number=20, agent_radius=15,
+                        agent_max_speed=40, map_id=1)),
+    4: dict(name="configs[3]: obstacle_map.npy, 65536 envs/GPU, 10 agents speed 20", envs=65536,
+            params=dict(planner="NoMove", static_map="maps/obstacle_map.npy", agent_number=10, agent_radius=10,
+                        agent_max_speed=20, map_id=1)),
+    5: dict(name="configs[4]: shaped_obstacle_map.npy, 131072 envs/GPU, 50 agents", envs=131072,
+            params=dict(planner="NoMove", static_map="maps/shaped_obstacle_map.npy", agent_number=50, agent_radius=10,
+                        agent_max_speed=40, map_id=1)),
+}
+METRIC = "env-steps/sec"
+N_RAYS = 50
+
+
+def _gen_chunk(args):
+    from gym_drone2d_activeperception_b200 import Params, generate_worlds
+    pk, seeds = args
+    return generate_worlds(Params(debug=False, **pk), seeds)
+
+
+def make_worlds(pk, seeds, unique=None):
+    """Host-side world generation (seeded, the reference's own procedure).  `unique` caps the number of distinct
+    worlds (tiled to the batch) to bound set-up time for the very large configs; the default keeps every env unique."""
+    import multiprocessing as mp
+    seeds = np.asarray(seeds)
+    B = len(seeds)
+    gen = seeds if unique is None or unique >= B else seeds[:unique]
+    nproc = max(1, min(len(os.sched_getaffinity(0)), 32, len(gen) // 64))
+    chunks = np.array_split(gen, nproc)
+    if nproc > 1:
+        with mp.get_context("fork").Pool(nproc) as pool:
+            parts = pool.map(_gen_chunk, [(pk, c) for c in chunks])
+    else:
+        parts = [_gen_chunk((pk, gen))]
+    w = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    if len(gen) < B:
+        reps = (B + len(gen) - 1) // len(gen)
+        w = {k: np.concatenate([v] * reps)[:B] for k, v in w.items()}
+    return w
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(n_agents):
+    return 2406 + 104 * n_agents          # SURVEY.md §8(d); tracker traffic deliberately NOT counted
+
+
+def cpu_port_run(pk, n_envs, steps, threads, seed0=1):
+    """Times the oracle port of the reference path on the host: n_envs envs x steps steps over `threads` threads
+    (ctypes releases the GIL).  Returns env-steps/s."""
+    import ctypes as C
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    from gym_drone2d_activeperception_b200 import Params
+    p = Params(debug=False, **pk)
+    worlds = make_worlds(pk, seed0 + np.arange(n_envs))
+    op = oracle.make_params(dt=p.dt, map_scale=p.map_scale, map_size=p.map_size, agent_radius=p.agent_radius,
+                            drone_max_acceleration=p.drone_max_acceleration, drone_radius=p.drone_radius,
+                            drone_max_yaw_speed=p.drone_max_yaw_speed, drone_view_depth=p.drone_view_depth,
+                            drone_view_range=p.drone_view_range, max_flight_time=p.max_flight_time, var_cam=p.var_cam,
+                            drone_max_speed=p.drone_max_speed, planner=p.planner)
+    envs = [oracle.OracleEnv(op, worlds["agent_pos"][i], worlds["agent_pref"][i], worlds["agent_radius"][i],
+                             worlds["gt_grid"][i], worlds["tracker_radius"][i], drone=worlds["drone_pose"][i],
+                             targets=p.target_list) for i in range(n_envs)]
+    L = oracle.lib()
+    table = np.arange(-80, 80, 80 / 3) / 80
+    rng = np.random.RandomState(0)
+    slices = np.array_split(np.arange(n_envs), threads)
+
+    def run_slice(idx, nsteps):
+        arr = (C.POINTER(oracle.Env) * len(idx))(*[envs[i]._ptr for i in idx])
+        acts = np.ascontiguousarray(table[rng.randint(0, 6, (len(idx), nsteps))])
+        L.d2do_run_many(arr, len(idx), nsteps, acts.ctypes.data_as(C.POINTER(C.c_double)))
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda s: run_slice(s, 2), slices))            # warm-up
+        t0 = time.perf_counter()
+        list(ex.map(lambda s: run_slice(s, steps), slices))
+        dt = time.perf_counter() - t0
+    for e in envs:
+        e.close()
+    return n_envs * steps / dt, dt
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python reference cannot
+    travel to the GPU box), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    cores = len(os.sched_getaffinity(0))
+    n_envs = max(cores * 8, 256)
+    steps_per = 25
+    vals = []
+    t_all = time.perf_counter()
+    for it in range(args.warmup + args.steps):
+        v, dt = cpu_port_run(cfg["params"], n_envs, steps_per, cores, seed0=1 + it)
+        if it >= args.warmup:
+            vals.append((n_envs * steps_per, dt))
+        if time.perf_counter() - t_all > 240 and len(vals) >= 1:
+            break
+    tot_steps = sum(v[0] for v in vals)
+    tot_t = sum(v[1] for v in vals)
+    value = tot_steps / tot_t
+    sample = "%d envs x %d steps per bench step, %d bench steps, %d threads" % (n_envs, steps_per, len(vals), cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(vals)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "rays_per_env_step": N_RAYS},
+            "rays_per_sec": value * N_RAYS,
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the config's)")
+    ap.add_argument("--envs-per-block", type=int, default=0)
+    ap.add_argument("--unique-worlds", type=int, default=0, help="cap distinct generated worlds (0 = all unique up to 8192)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps (reported in config)")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, cfg)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    B = args.envs or cfg["envs"]
+    pk = cfg["params"]
+    unique = args.unique_worlds or min(B, 8192)
+    # worlds are generated before CUDA is touched (fork-based pool)
+    seeds = pk["map_id"] + rank * B + np.arange(B)
+    t0 = time.perf_counter()
+    worlds = make_worlds(pk, seeds, unique=unique)
+    t_world = time.perf_counter() - t0
+
+    import torch
+    import torch.distributed as dist
+    from gym_drone2d_activeperception_b200 import Params
+    from gym_drone2d_activeperception_b200.vec_env import Drone2DVecEnv
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    p = Params(debug=False, **pk)
+    env = Drone2DVecEnv(p, B, seeds=seeds, worlds=worlds, device=dev, auto_reset=True, trackers=True,
+                        envs_per_block=args.envs_per_block)
+    N = env.num_agents
+    K, W = args.steps, args.warmup
+    table = torch.as_tensor(np.arange(-80, 80, 80 / 3) / 80, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    actions = table[torch.randint(0, 6, (K + W, B), device=dev, generator=gen)].contiguous()
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: per-step CUDA events on the launch stream, L2 flushed (untimed) between steps
+    for t in range(W):
+        env.step(actions[t])
+    barrier()
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    sampler.start()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    l0 = env.launch_count()
+    wall0 = time.perf_counter()
+    for t in range(K):
+        if flush is not None:
+            flush.fill_(t & 0xFF)
+        ev0[t].record()
+        env.step(actions[W + t])
+        ev1[t].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = env.launch_count() - l0
+    step_ms = np.array([a.elapsed_time(b) for a, b in zip(ev0, ev1)])
+    total_ms = float(step_ms.sum())
+    # ---- end to end through the C ABI with pinned host buffers
+    a_host = actions[W:].cpu().pin_memory()
+    lm_host = torch.empty((B, 1, 33, 33), dtype=torch.uint8).pin_memory()
+    yaw_host = torch.empty((B,), dtype=torch.float32).pin_memory()
+    done_host = torch.empty((B,), dtype=torch.uint8).pin_memory()
+    Ke = min(K, 100)
+    for t in range(3):
+        env.step_host(a_host[t], lm_host, yaw_host, done_host)
+    barrier()
+    te0 = time.perf_counter()
+    for t in range(Ke):
+        env.step_host(a_host[t], lm_host, yaw_host, done_host)
+    barrier()
+    e2e_s = time.perf_counter() - te0
+    clocks = sampler.stop()
+
+    # max over ranks (device time), whole-job throughput
+    tt = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms_max, e2e_ms_max = float(tt[0]), float(tt[1])
+    # the one collective of the path: all-reduce of the episode statistics
+    stats = torch.as_tensor(env.stats(), device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    value = world * B * K / (total_ms_max * 1e-3)
+    e2e = world * B * Ke / (e2e_ms_max * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kern_ms = float(np.mean(step_ms))
+        bytes_launch = algorithmic_bytes(N) * B
+        achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_config%d.json" % args.config)
+        if os.path.isfile(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "envs_per_gpu": B, "agents_per_env": N, "rays_per_env_step": N_RAYS,
+                       "planner": pk["planner"], "trackers": True, "auto_reset": True,
+                       "unique_worlds_per_gpu": int(unique), "world_gen_s": round(t_world, 2),
+                       "l2": "no flush (state stays L2-resident)" if flush is None else
+                             "flushed between timed steps (256 MiB fill, untimed; per-step CUDA events summed)",
+                       "envs_per_block": env.cfg.envs_per_block, "parallelism": "env-sharded x%d" % world},
+            "rays_per_sec": value * N_RAYS,
+            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": B * 8,
+                    "d2h_bytes_per_step": B * (1089 + 4 + 1), "steps": Ke},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "bytes_per_env_step": algorithmic_bytes(N),
+                         "kernel": "d2d_step_fused_kernel", "kernel_ms": kern_ms,
+                         "step_ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())]},
+            "wall_s_timed_region": wall,
+            "episode_stats": {n: int(v) for n, v in zip(
+                ["env_steps", "episodes", "success", "static_collision", "dynamic_collision", "freezing", "dead_lock"],
+                stats.tolist()[:7])},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            import oracle
+            oracle.build()
+            cores = len(os.sched_getaffinity(0))
+            n_envs, steps_c = max(cores * 8, 256), 50
+            v, dt = cpu_port_run(pk, n_envs, steps_c, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                    "sample": "%d envs x %d steps of the same workload (%.1f s)" % (n_envs, steps_c, dt)}
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

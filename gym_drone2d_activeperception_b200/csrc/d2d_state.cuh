@@ -1,0 +1,63 @@
+// d2d_state.cuh -- device-side view of one handle's arena (passed by value to every kernel).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "../../include/drone2d.h"
+
+// state_machine values (utils.py:24-29)
+#define SM_WAIT_FOR_GOAL 0
+#define SM_GOAL_REACHED 1
+#define SM_PLANNING 2
+#define SM_EXECUTING 3
+
+#define D2D_GT_ROW_BYTES 400   // 50 rows x uint64 per env (bit j of row i == ground truth cell (i,j) == OCCUPIED)
+#define D2D_GRID 50            // cells per side (map_size // map_scale); the reference's maps are 50x50
+#define D2D_CELLS 2500
+#define D2D_LOCAL 33
+#define D2D_LOCAL_CELLS 1089
+
+struct DevTables {   // lookup tables in global memory (read through the read-only path)
+    double u_space[D2D_MAX_U];
+    double t_samp[D2D_MAX_SAMP], t_samp2[D2D_MAX_SAMP];
+    double t_way[D2D_MAX_WAY], t_way2[D2D_MAX_WAY], t_way_x2[D2D_MAX_WAY];
+    double v_yaw_space[D2D_MAX_YAW];
+};
+
+struct DevP {
+    int B, N, NP, HW;            // envs, agents, padded agents, hit words per env
+    int n_rays, planner, trackers, auto_reset, n_targets;
+    int n_u, n_samp, n_way, n_yaw;
+    double dt, scale, inv_scale, map_w, map_h, agent_radius, max_acc, drone_r, max_yaw_speed;
+    double depth2, fov, max_steps, var_cam, max_speed, cull_reach, ox_cos_thresh;
+    double targets[D2D_MAX_TARGETS][2];
+    // agents [B][NP] (env-major)
+    double2 *apos, *apref, *apos0, *apref0;
+    double *arad, *trk_radius0;
+    uint64_t *gt_rows;           // [B][50]
+    uint8_t *belief;             // [B][D2D_BELIEF_STRIDE]
+    // drone + env bookkeeping [B]
+    double *drone_x, *drone_y, *drone_yaw, *drone_vx, *drone_vy, *pose0;  // pose0: [3][B]
+    double *target_x, *target_y;
+    int *steps, *state_machine, *fail_count, *target_cursor;
+    uint8_t *collision, *dead_lock, *freezing, *done, *pending_reset;
+    // observation
+    uint8_t *local_map;          // [B][1][33][33]
+    float *yaw_obs;              // [B][1]
+    float *reward;               // [B] zeros (drone_v2.py:257)
+    int8_t *hit;                 // [B][NP]
+    // trackers [B][NP]
+    uint8_t *trk_active;
+    double *trk_mu, *trk_sigma, *trk_radius;   // [B][NP][4], [B][NP][16], [B][NP]
+    int *trk_ts;
+    int *buf_count, *buf_ts, *tracked_agent;   // [B]
+    // trajectory as A* segments
+    double *traj_coeff;          // [B][D2D_MAX_SEGMENTS][6]
+    int *traj_nseg, *traj_cursor;  // remaining waypoints = nseg*n_way - cursor
+    uint8_t *need_plan, *plan_ok, *replan;
+    // Oxford
+    double *ox_last;             // [B][2500]
+    unsigned long long *stats;   // [D2D_NUM_STATS]
+    unsigned char *plan_ws;      // A* workspaces (Primitive planner)
+    int *plan_list;              // [B+4] compacted list of envs that need a plan; [B] = count
+    const DevTables *tab;
+};

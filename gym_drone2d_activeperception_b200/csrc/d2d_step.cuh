@@ -1,0 +1,582 @@
+// d2d_step.cuh -- the per-step kernels (sm_100a).
+//
+// Work decomposition.  One thread block owns E consecutive environments and walks them through the phases of
+// Drone2DEnv2.step (envs/drone_v2.py:152-257) in the reference's order, separated by __syncthreads():
+//
+//   P0  env leaders load the drone/bookkeeping scalars (lazy auto-reset from the snapshot if the env was done);
+//       one thread issues TMA bulk copies (cp.async.bulk -> UBLKCP) of each env's belief grid (2560 B) and
+//       ground-truth row bitmap (400 B) from HBM into shared memory, completion on an mbarrier.
+//   P1  one work item per (env, agent): Agent.step (utils.py:472-493), write back, keep (x, y, r^2) in shared
+//       memory, broad-phase cull against the drone's view reach, drone-vs-agent collision test.
+//   P2  one work item per (env, ray): Raycast.castRay (utils.py:620-713) with the reference's exact stepping
+//       arithmetic against the shared-memory bitmap and the culled discs; newly seen belief cells are written
+//       to shared memory AND to HBM (only cells whose value changes: ~3 byte stores per env-step).
+//   P3  one work item per (env, agent): hit mask out, Kalman tracker update (utils.py:242-275).
+//   P4  env leaders: planner bookkeeping, step_pos / step_yaw, static collision probes, flags, done, statistics.
+//   P5  the block writes its E*1089-byte slice of the local-map observation with coalesced 32-bit stores,
+//       gathering from the shared-memory belief grids (Drone2D.get_local_map, utils.py:780-784).
+//
+// Work items are packed across environment boundaries (item -> (env, k) by division), so lanes stay busy for any
+// ray / agent count; everything an environment shares between its threads lives in shared memory.
+#pragma once
+#include "d2d_state.cuh"
+#include "d2d_math.cuh"
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t d2d_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void d2d_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(d2d_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void d2d_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(d2d_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void d2d_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     d2d_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(d2d_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void d2d_mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    const uint32_t addr = d2d_smem_u32(bar);
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// ------------------------------------------------------------------------------------------ shared-memory context
+struct EnvS {
+    double px, py, yaw, vx, vy, tgx, tgy;
+    int steps, sm, fail, tcur;
+    int bufc, bufts, tracked;
+    int valid, reset, ncull, coll_agent;
+    int arch_cnt, arch_ts, act_cnt, act_ts, newly;
+    int done_now, nseg, cursor, ix, iy, pad;
+};
+
+struct BlockCtx {
+    uint8_t *belief;     // [E][D2D_BELIEF_STRIDE]
+    uint64_t *gt;        // [E][50]
+    double *sx, *sy, *sr2;  // [E][NP]
+    uint16_t *cull;      // [E][NP]
+    uint32_t *hitw;      // [E][HW]
+    EnvS *S;             // [E]
+    uint64_t *mbar;
+    int *misc;           // [4] block-level scratch
+};
+
+__host__ __device__ inline size_t d2d_step_smem_bytes(int E, int NP, int HW) {
+    size_t b = (size_t)E * D2D_BELIEF_STRIDE + (size_t)E * D2D_GT_ROW_BYTES;
+    b += (size_t)E * NP * 8 * 3;
+    b += ((size_t)E * NP * 2 + 15) / 16 * 16;
+    b += ((size_t)E * HW * 4 + 15) / 16 * 16;
+    b += (size_t)E * sizeof(EnvS);
+    b += 16 + 16;
+    return b;
+}
+
+__device__ __forceinline__ BlockCtx d2d_carve(unsigned char *base, int E, int NP, int HW) {
+    BlockCtx c;
+    size_t o = 0;
+    c.belief = base; o += (size_t)E * D2D_BELIEF_STRIDE;
+    c.gt = (uint64_t *)(base + o); o += (size_t)E * D2D_GT_ROW_BYTES;
+    c.sx = (double *)(base + o); o += (size_t)E * NP * 8;
+    c.sy = (double *)(base + o); o += (size_t)E * NP * 8;
+    c.sr2 = (double *)(base + o); o += (size_t)E * NP * 8;
+    c.cull = (uint16_t *)(base + o); o += ((size_t)E * NP * 2 + 15) / 16 * 16;
+    c.hitw = (uint32_t *)(base + o); o += ((size_t)E * HW * 4 + 15) / 16 * 16;
+    c.S = (EnvS *)(base + o); o += (size_t)E * sizeof(EnvS);
+    c.mbar = (uint64_t *)(base + o); o += 16;
+    c.misc = (int *)(base + o);
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------ P0: scalars + bulk loads
+__device__ __forceinline__ void d2d_load_env_scalars(const DevP &P, EnvS &s, int e) {
+    s.valid = e < P.B;
+    s.ncull = 0; s.coll_agent = 0; s.arch_cnt = 0; s.arch_ts = 0; s.act_cnt = 0; s.act_ts = 0; s.newly = 0;
+    s.done_now = 0; s.reset = 0;
+    if (!s.valid) return;
+    const bool rs = P.pending_reset[e] || (P.auto_reset && P.done[e]);
+    s.reset = rs;
+    if (rs) {   // Drone2DEnv2.__init__ (drone_v2.py:88-117): drone at init pose, zero velocity, WAIT_FOR_GOAL
+        s.px = P.pose0[e]; s.py = P.pose0[P.B + e]; s.yaw = P.pose0[2 * P.B + e];
+        s.vx = 0; s.vy = 0; s.tgx = s.px; s.tgy = s.py;   // Planner.__init__ traj_planner.py:22
+        s.steps = 0; s.sm = SM_WAIT_FOR_GOAL; s.fail = 0; s.tcur = 0;
+        s.bufc = 0; s.bufts = 0; s.tracked = 0; s.nseg = 0; s.cursor = 0;
+        P.pending_reset[e] = 0;
+    } else {
+        s.px = P.drone_x[e]; s.py = P.drone_y[e]; s.yaw = P.drone_yaw[e];
+        s.vx = P.drone_vx[e]; s.vy = P.drone_vy[e]; s.tgx = P.target_x[e]; s.tgy = P.target_y[e];
+        s.steps = P.steps[e]; s.sm = P.state_machine[e]; s.fail = P.fail_count[e]; s.tcur = P.target_cursor[e];
+        s.bufc = P.buf_count[e]; s.bufts = P.buf_ts[e]; s.tracked = P.tracked_agent[e];
+        s.nseg = P.traj_nseg[e]; s.cursor = P.traj_cursor[e];
+    }
+}
+
+__device__ __forceinline__ void d2d_store_env_scalars(const DevP &P, const EnvS &s, int e) {
+    P.drone_x[e] = s.px; P.drone_y[e] = s.py; P.drone_yaw[e] = s.yaw; P.drone_vx[e] = s.vx; P.drone_vy[e] = s.vy;
+    P.target_x[e] = s.tgx; P.target_y[e] = s.tgy;
+    P.steps[e] = s.steps; P.state_machine[e] = s.sm; P.fail_count[e] = s.fail; P.target_cursor[e] = s.tcur;
+    P.buf_count[e] = s.bufc; P.buf_ts[e] = s.bufts; P.tracked_agent[e] = s.tracked;
+    P.traj_nseg[e] = s.nseg; P.traj_cursor[e] = s.cursor;
+}
+
+// issue the bulk copies for the block (thread 0) -- belief only for envs that are not being reset
+__device__ __forceinline__ void d2d_issue_bulk(const DevP &P, const BlockCtx &c, int env0, int E, bool want_belief) {
+    uint32_t bytes = 0;
+    for (int i = 0; i < E; i++) {
+        if (!c.S[i].valid) continue;
+        bytes += D2D_GT_ROW_BYTES;
+        if (want_belief && !c.S[i].reset) bytes += D2D_BELIEF_STRIDE;
+    }
+    d2d_mbar_expect_tx(c.mbar, bytes);
+    for (int i = 0; i < E; i++) {
+        if (!c.S[i].valid) continue;
+        const size_t e = (size_t)(env0 + i);
+        d2d_bulk_g2s(c.gt + (size_t)i * D2D_GRID, P.gt_rows + e * D2D_GRID, D2D_GT_ROW_BYTES, c.mbar);
+        if (want_belief && !c.S[i].reset)
+            d2d_bulk_g2s(c.belief + (size_t)i * D2D_BELIEF_STRIDE, P.belief + e * D2D_BELIEF_STRIDE, D2D_BELIEF_STRIDE, c.mbar);
+    }
+}
+
+// envs being reset: zero belief in shared memory and HBM; restore the Oxford policy state
+__device__ __forceinline__ void d2d_reset_arrays(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
+    const int W = D2D_BELIEF_STRIDE / 4;
+    for (int w = tid; w < E * W; w += T) {
+        const int i = w / W, o = w - i * W;
+        if (!c.S[i].valid || !c.S[i].reset) continue;
+        ((uint32_t *)(c.belief + (size_t)i * D2D_BELIEF_STRIDE))[o] = 0u;
+        ((uint32_t *)(P.belief + (size_t)(env0 + i) * D2D_BELIEF_STRIDE))[o] = 0u;
+    }
+    if (P.ox_last) {
+        for (int w = tid; w < E * D2D_CELLS; w += T) {
+            const int i = w / D2D_CELLS, o = w - i * D2D_CELLS;
+            if (!c.S[i].valid || !c.S[i].reset) continue;
+            P.ox_last[(size_t)(env0 + i) * D2D_CELLS + o] = 5.0;   // yaw_planner.py:49
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ P1: Agent.step
+template <bool COLLIDE_HERE>
+__device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
+    const double C6 = 0.8660254037844387, S6 = 0.49999999999999994;   // math.cos(pi/6), math.sin(pi/6) (glibc)
+    const int N = P.N, NP = P.NP;
+    for (int w = tid; w < E * N; w += T) {
+        const int i = w / N, k = w - i * N;
+        EnvS &s = c.S[i];
+        if (!s.valid) continue;
+        const size_t g = (size_t)(env0 + i) * NP + k;
+        double2 pos, pref;
+        if (s.reset) { pos = P.apos0[g]; pref = P.apref0[g]; }
+        else { pos = P.apos[g]; pref = P.apref[g]; }
+        const double r = P.arad[g];
+        // drone_v2.py:178  velocity IS pref_velocity (same ndarray)
+        double vx = pref.x, vy = pref.y;
+        const double nx = pos.x + vx * P.dt, ny = pos.y + vy * P.dt;
+        bool rebound = false;
+        if (d2d_norm2(vx, vy) <= 5.0) {   // utils.py:476-477: rotation by 30 deg rebinds pref_velocity
+            const double qx = D2D_FMA(C6, pref.x, -S6 * pref.y);
+            const double qy = D2D_FMA(S6, pref.x, C6 * pref.y);
+            pref.x = qx; pref.y = qy;
+            rebound = true;
+        }
+        const double edge = P.scale;
+        if (nx < edge + r) pref.x = fabs(pref.x);
+        else if (nx > P.map_w - edge - r) pref.x = -fabs(pref.x);
+        if (ny < edge + r) pref.y = fabs(pref.y);
+        else if (ny > P.map_h - edge - r) pref.y = -fabs(pref.y);
+        if (!rebound) { vx = pref.x; vy = pref.y; }
+        pos.x = pos.x + vx * P.dt;
+        pos.y = pos.y + vy * P.dt;
+        P.apos[g] = pos;
+        P.apref[g] = pref;
+        const int q = i * NP + k;
+        c.sx[q] = pos.x; c.sy[q] = pos.y; c.sr2[q] = r * r;
+        // broad phase: a ray sample is never farther than depth + 9*sqrt(2) from the drone
+        const double ddx = pos.x - s.px, ddy = pos.y - s.py;
+        const double reach = r + P.cull_reach;
+        if (ddx * ddx + ddy * ddy <= reach * reach) {
+            const int slot = atomicAdd(&s.ncull, 1);
+            c.cull[i * NP + slot] = (uint16_t)k;
+        }
+        if (COLLIDE_HERE) {   // Drone2D.is_collide utils.py:773-776 (drone does not move under NoMove)
+            if (d2d_norm2(ddx, ddy) < r + P.drone_r) atomicOr(&s.coll_agent, 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ P2: Raycast.castRay
+__device__ __forceinline__ void d2d_mark(uint8_t *bel_s, uint8_t *bel_g, int cell, uint8_t v) {
+    if (bel_s[cell] != v) {   // monotone + idempotent: every writer of a cell writes the same value
+        bel_s[cell] = v;
+        bel_g[cell] = v;
+    }
+}
+
+__device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, int ray, uint8_t *bel_s, uint8_t *bel_g,
+                                             const uint64_t *gt, const double *sx, const double *sy, const double *sr2,
+                                             const uint16_t *cull, uint32_t *hitw) {
+    const double fov = P.fov;
+    const double ray_angle = -fov / 2 + fov / (double)P.n_rays * (double)ray;   // utils.py:594
+    const double player_angle = D2D_TWO_PI - s.yaw * D2D_DEG2RAD;
+    double a = player_angle + ray_angle;                                         // utils.py:626
+    a = copysign(d2d_pymod(fabs(a), D2D_TWO_PI), a);                             // utils.py:612-618
+    if (a < 0) a += D2D_TWO_PI;
+    const bool faced_right = (a < 90.0 * D2D_DEG2RAD) || (a > 270.0 * D2D_DEG2RAD);
+    const bool faced_up = a > D2D_PI;
+    double slope = d2d_tan(a);
+    const double step = P.scale - 1.0;
+    double xs, ys;
+    if (fabs(slope) > 1.0) {
+        slope = 1.0 / slope;
+        ys = faced_up ? -step : step;
+        xs = ys * slope;
+    } else {
+        xs = faced_right ? step : -step;
+        ys = xs * slope;
+    }
+    double x = s.px, y = s.py;
+    const int nc = s.ncull;
+    while (0.0 < x && x < P.map_w && 0.0 < y && y < P.map_h) {
+        const int ci = d2d_cell(x, P.scale, P.inv_scale), cj = d2d_cell(y, P.scale, P.inv_scale);
+        bool any = false;
+        for (int q = 0; q < nc; q++) {
+            const int k = cull[q];
+            const double ex = sx[k] - x, ey = sy[k] - y;
+            if (ex * ex + ey * ey <= sr2[k]) {
+                atomicOr(&hitw[k >> 5], 1u << (k & 31));
+                any = true;
+            }
+        }
+        if (any) break;
+        const bool wall = (gt[ci] >> cj) & 1ull;
+        const double fx = x - s.px, fy = y - s.py;
+        const double dist = fx * fx + fy * fy;
+        const int cell = ci * D2D_GRID + cj;
+        if (wall || dist >= P.depth2) {
+            if (wall) d2d_mark(bel_s, bel_g, cell, 1);
+            break;
+        }
+        d2d_mark(bel_s, bel_g, cell, 2);
+        x = x + xs;
+        y = y + ys;
+    }
+}
+
+__device__ __forceinline__ void d2d_phase_rays(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
+    const int R = P.n_rays, NP = P.NP;
+    for (int w = tid; w < E * R; w += T) {
+        const int i = w / R, ray = w - i * R;
+        const EnvS &s = c.S[i];
+        if (!s.valid) continue;
+        d2d_cast_ray(P, s, ray, c.belief + (size_t)i * D2D_BELIEF_STRIDE, P.belief + (size_t)(env0 + i) * D2D_BELIEF_STRIDE,
+                     c.gt + (size_t)i * D2D_GRID, c.sx + i * NP, c.sy + i * NP, c.sr2 + i * NP, c.cull + i * NP,
+                     c.hitw + i * P.HW);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ P3: hit mask + trackers
+__device__ __forceinline__ void d2d_tracker_update(const DevP &P, EnvS &s, size_t g, bool measured, double z0, double z1) {
+    // KalmanFilter.update utils.py:242-275; F = I + 0.1*shift, H = [I 0], Sigma_z = var_cam*I, Sigma_x = q*I
+    const double q = (P.var_cam != 0.0) ? 0.1 : 0.001;
+    double *mu = P.trk_mu + g * 4, *Sg = P.trk_sigma + g * 16;
+    bool active = s.reset ? false : (P.trk_active[g] != 0);
+    int ts = s.reset ? 1 : P.trk_ts[g];
+    if (s.reset) {   // fresh KalmanFilter(params) + drone_v2.py:46 radius
+        P.trk_radius[g] = P.trk_radius0[g];
+        P.trk_active[g] = 0;
+        P.trk_ts[g] = 1;
+    }
+    if (!active && !measured) return;
+    double m[4], S[16];
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) m[i] = mu[i];
+#pragma unroll
+        for (int i = 0; i < 16; i++) S[i] = Sg[i];
+        // predict utils.py:225-233
+        m[0] = m[0] + 0.1 * m[2];
+        m[1] = m[1] + 0.1 * m[3];
+        double Tm[16];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            Tm[j] = S[j] + 0.1 * S[8 + j];
+            Tm[4 + j] = S[4 + j] + 0.1 * S[12 + j];
+            Tm[8 + j] = S[8 + j];
+            Tm[12 + j] = S[12 + j];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            S[4 * i + 0] = Tm[4 * i + 0] + 0.1 * Tm[4 * i + 2];
+            S[4 * i + 1] = Tm[4 * i + 1] + 0.1 * Tm[4 * i + 3];
+            S[4 * i + 2] = Tm[4 * i + 2];
+            S[4 * i + 3] = Tm[4 * i + 3];
+        }
+        S[0] += q; S[5] += q; S[10] += q; S[15] += q;
+        ts += 1;
+        const double lo = 10.0 + P.agent_radius;
+        if (S[0] >= 150.0 || !(lo < m[0] && m[0] < P.map_w - 10.0 - P.agent_radius) ||
+            !(lo < m[1] && m[1] < P.map_h - 10.0 - P.agent_radius)) {
+            // utils.py:235-239: archive a copy, re-initialise (inactive, default radius)
+            atomicAdd(&s.arch_cnt, 1);
+            atomicAdd(&s.arch_ts, ts);
+            active = false;
+            P.trk_radius[g] = P.agent_radius;
+            m[0] = m[1] = m[2] = m[3] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) S[i] = 0.0;
+            S[0] = 1.0; S[5] = 1.0; S[10] = 10.0; S[15] = 10.0;
+            ts = 1;
+        }
+        if (measured) {   // utils.py:249-260
+            const double rz = P.var_cam;
+            const double s00 = rz + S[0], s01 = S[1], s10 = S[4], s11 = rz + S[5];
+            const double det = s00 * s11 - s01 * s10;
+            const double i00 = s11 / det, i01 = -s01 / det, i10 = -s10 / det, i11 = s00 / det;
+            double K[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                K[2 * i] = S[4 * i] * i00 + S[4 * i + 1] * i10;
+                K[2 * i + 1] = S[4 * i] * i01 + S[4 * i + 1] * i11;
+            }
+            const double r0 = z0 - m[0], r1 = z1 - m[1];
+            double Sn[16];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    // (I - K H) Sigma : row i = Sigma[i] - K[i][0]*Sigma[0] - K[i][1]*Sigma[1]
+                    double acc = 0.0;
+#pragma unroll
+                    for (int qq = 0; qq < 4; qq++) {
+                        const double aiq = (i == qq ? 1.0 : 0.0) - (qq < 2 ? K[2 * i + qq] : 0.0);
+                        acc += aiq * S[4 * qq + j];
+                    }
+                    Sn[4 * i + j] = acc;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) m[i] = m[i] + (K[2 * i] * r0 + K[2 * i + 1] * r1);
+#pragma unroll
+            for (int i = 0; i < 16; i++) S[i] = Sn[i];
+        }
+    } else {   // first sighting utils.py:263-273
+        m[0] = z0; m[1] = z1; m[2] = 0.0; m[3] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) S[i] = 0.0;
+        S[0] = 1.0; S[5] = 1.0; S[10] = 10.0; S[15] = 10.0;
+        ts = 1;
+        active = true;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) mu[i] = m[i];
+#pragma unroll
+    for (int i = 0; i < 16; i++) Sg[i] = S[i];
+    P.trk_active[g] = active ? 1 : 0;
+    P.trk_ts[g] = ts;
+    if (active) {
+        atomicAdd(&s.act_cnt, 1);
+        atomicAdd(&s.act_ts, ts);
+    }
+}
+
+__device__ __forceinline__ void d2d_phase_trackers(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
+    const int N = P.N, NP = P.NP;
+    for (int w = tid; w < E * N; w += T) {
+        const int i = w / N, k = w - i * N;
+        EnvS &s = c.S[i];
+        if (!s.valid) continue;
+        const size_t g = (size_t)(env0 + i) * NP + k;
+        const bool hit = (c.hitw[i * P.HW + (k >> 5)] >> (k & 31)) & 1u;
+        P.hit[g] = hit ? 1 : 0;
+        if (P.trackers) {
+            const bool was_active = s.reset ? false : (P.trk_active[g] != 0);
+            if (hit && !was_active) atomicAdd(&s.newly, 1);   // utils.py:606-607
+            if (was_active || hit || s.reset) {
+                d2d_tracker_update(P, s, g, hit, c.sx[i * NP + k], c.sy[i * NP + k]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ P4: leaders
+__device__ __forceinline__ int d2d_gt_probe(const DevP &P, const uint64_t *gt, double x, double y) {
+    if (x >= P.map_w || x < 0 || y >= P.map_h || y < 0) return 1;   // utils.py:546-547
+    const int ci = d2d_cell(x, P.scale, P.inv_scale), cj = d2d_cell(y, P.scale, P.inv_scale);
+    return (int)((gt[ci] >> cj) & 1ull);
+}
+
+// first half of Drone2DEnv2.step (drone_v2.py:153-163): counters, state machine, next target
+__device__ __forceinline__ void d2d_leader_begin(const DevP &P, EnvS &s) {
+    s.steps += 1;
+    if (s.sm == SM_GOAL_REACHED) s.sm = SM_WAIT_FOR_GOAL;
+    if (s.sm == SM_WAIT_FOR_GOAL) {
+        if (s.tcur < P.n_targets) {
+            s.tgx = P.targets[s.tcur][0];
+            s.tgy = P.targets[s.tcur][1];
+            s.tcur += 1;
+        }
+        s.sm = SM_PLANNING;
+    }
+}
+
+// second half (drone_v2.py:196-235) after the planner verdict `success`
+__device__ __forceinline__ void d2d_leader_finish(const DevP &P, EnvS &s, const uint64_t *gt, int e, double action,
+                                                  bool success) {
+    if (!success) {   // Drone2D.brake utils.py:755-762
+        const double nv = d2d_norm2(s.vx, s.vy);
+        if (nv <= P.max_acc * P.dt) { s.vx = 0.0; s.vy = 0.0; }
+        else {
+            s.vx = s.vx - s.vx / nv * P.max_acc * P.dt;
+            s.vy = s.vy - s.vy / nv * P.max_acc * P.dt;
+            s.px += s.vx * P.dt;
+            s.py += s.vy * P.dt;
+        }
+        s.sm = SM_PLANNING;
+        s.fail += 1;
+    } else {
+        s.sm = SM_EXECUTING;
+        s.fail = 0;
+    }
+    // step_pos utils.py:733-739: pop one waypoint
+    const int remaining = s.nseg * P.n_way - s.cursor;
+    if (remaining > 0) {
+        const int seg = s.cursor / P.n_way, ws = s.cursor - seg * P.n_way;
+        const int ti = P.n_way - 1 - ws;
+        const double *cf = P.traj_coeff + ((size_t)e * D2D_MAX_SEGMENTS + seg) * 6;
+        const double t = P.tab->t_way[ti], t2 = P.tab->t_way2[ti], tt = P.tab->t_way_x2[ti];
+        // np.array([1,t,t**2]) @ coeff.T on the reference image: fma(t2, h, p + t*v); then np.around, then round()
+        s.px = rint(D2D_FMA(t2, cf[2], cf[0] + t * cf[1]));
+        s.py = rint(D2D_FMA(t2, cf[5], cf[3] + t * cf[4]));
+        s.vx = cf[1] + tt * cf[2];
+        s.vy = cf[4] + tt * cf[5];
+        s.cursor += 1;
+        if (s.cursor == s.nseg * P.n_way) { s.nseg = 0; s.cursor = 0; }
+    }
+    // step_yaw utils.py:741-743
+    s.yaw = d2d_pymod(s.yaw + (action * P.max_yaw_speed) * P.dt, 360.0);
+}
+
+__device__ __forceinline__ void d2d_leader_flags(const DevP &P, EnvS &s, const uint64_t *gt, int e) {
+    // is_collide utils.py:764-778
+    int col = 0;
+    const double r = P.drone_r;
+    if (d2d_gt_probe(P, gt, s.px - r, s.py) || d2d_gt_probe(P, gt, s.px, s.py) || d2d_gt_probe(P, gt, s.px + r, s.py) ||
+        d2d_gt_probe(P, gt, s.px, s.py - r) || d2d_gt_probe(P, gt, s.px, s.py + r))
+        col = 1;
+    else if (s.coll_agent) col = 2;
+    int dead = 0, frz = 0;
+    if (col == 0) {   // drone_v2.py:222-225
+        if (d2d_norm2(s.px - s.tgx, s.py - s.tgy) <= 10.0) s.sm = SM_GOAL_REACHED;
+        dead = (s.fail >= 10 && d2d_norm2(s.vx, s.vy) == 0.0) ? 1 : 0;
+        frz = ((double)s.steps >= P.max_steps && !dead) ? 1 : 0;
+    }
+    const int done = (col != 0 || dead || frz || (s.sm == SM_GOAL_REACHED && s.tcur >= P.n_targets)) ? 1 : 0;
+    // tracker bookkeeping: archived this step (utils.py:238, drone_v2.py:187) + still-active ones at done (:232-235)
+    s.bufc += s.arch_cnt; s.bufts += s.arch_ts; s.tracked += s.newly;
+    if (done) { s.bufc += s.act_cnt; s.bufts += s.act_ts; }
+    s.done_now = done;
+    s.ix = d2d_cell(s.px, P.scale, P.inv_scale); s.iy = d2d_cell(s.py, P.scale, P.inv_scale);
+    P.collision[e] = (uint8_t)col; P.dead_lock[e] = (uint8_t)dead; P.freezing[e] = (uint8_t)frz; P.done[e] = (uint8_t)done;
+    P.yaw_obs[e] = (float)s.yaw;
+    if (done) {
+        atomicAdd(&P.stats[D2D_STAT_EPISODES], 1ull);
+        if (s.sm == SM_GOAL_REACHED) atomicAdd(&P.stats[D2D_STAT_SUCCESS], 1ull);
+        if (col == 1) atomicAdd(&P.stats[D2D_STAT_STATIC_COLLISION], 1ull);
+        if (col == 2) atomicAdd(&P.stats[D2D_STAT_DYNAMIC_COLLISION], 1ull);
+        if (frz) atomicAdd(&P.stats[D2D_STAT_FREEZING], 1ull);
+        if (dead) atomicAdd(&P.stats[D2D_STAT_DEAD_LOCK], 1ull);
+        atomicAdd(&P.stats[D2D_STAT_FLIGHT_STEPS], (unsigned long long)s.steps);
+        atomicAdd(&P.stats[D2D_STAT_AGENTS_TRACKED], (unsigned long long)s.bufc);
+        atomicAdd(&P.stats[D2D_STAT_TRACKED_STEPS], (unsigned long long)s.bufts);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ P5: observation
+// Drone2D.get_local_map utils.py:780-784: zero-padded 33x33 window centred on the drone's cell.  The block's E envs
+// occupy E*1089 contiguous bytes of the observation tensor; E is a multiple of 4, so the slice is 4-byte aligned.
+__device__ __forceinline__ void d2d_phase_obs(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
+    uint32_t *out = (uint32_t *)(P.local_map + (size_t)env0 * D2D_LOCAL_CELLS);
+    const int words = E * D2D_LOCAL_CELLS / 4;
+    for (int w = tid; w < words; w += T) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int o = w * 4 + b;
+            const int i = o / D2D_LOCAL_CELLS, r = o - i * D2D_LOCAL_CELLS;
+            const EnvS &s = c.S[i];
+            uint32_t cellv = 0;
+            if (s.valid) {
+                const int u = r / D2D_LOCAL, vv = r - u * D2D_LOCAL;
+                const int gi = s.ix - 16 + u, gj = s.iy - 16 + vv;
+                if (gi >= 0 && gi < D2D_GRID && gj >= 0 && gj < D2D_GRID)
+                    cellv = c.belief[(size_t)i * D2D_BELIEF_STRIDE + gi * D2D_GRID + gj];
+            }
+            v |= cellv << (8 * b);
+        }
+        out[w] = v;
+    }
+}
+
+// explored-cell count of envs that finished this step (experiment.py:90 "Grid discovered")
+__device__ __forceinline__ void d2d_phase_done_stats(const DevP &P, const BlockCtx &c, int E, int tid, int T) {
+    int cnt = 0;
+    for (int w = tid; w < E * D2D_CELLS; w += T) {
+        const int i = w / D2D_CELLS, o = w - i * D2D_CELLS;
+        if (c.S[i].valid && c.S[i].done_now && c.belief[(size_t)i * D2D_BELIEF_STRIDE + o] != 0) cnt++;
+    }
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+    if ((tid & 31) == 0 && cnt) atomicAdd(&P.stats[D2D_STAT_GRID_DISCOVERED], (unsigned long long)cnt);
+}
+
+// ------------------------------------------------------------------------------------------ fused step (NoMove planner)
+// Whole Drone2DEnv2.step in one launch when the planner is NoMove (traj_planner.py:68-76): the drone never moves,
+// so the drone-vs-agent test can run with the agent phase and no planner kernel is needed.
+template <int E>
+__global__ void __launch_bounds__((E * 50 + 31) / 32 * 32) d2d_step_fused_kernel(const DevP P, const double *__restrict__ actions) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const BlockCtx c = d2d_carve(smem, E, P.NP, P.HW);
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int env0 = blockIdx.x * E;
+
+    if (tid < E) d2d_load_env_scalars(P, c.S[tid], env0 + tid);
+    for (int w = tid; w < E * P.HW; w += T) c.hitw[w] = 0u;
+    if (tid == 0) { d2d_mbar_init(c.mbar, 1); c.misc[0] = 0; }
+    __syncthreads();
+    if (tid == 0) d2d_issue_bulk(P, c, env0, E, true);
+    d2d_reset_arrays(P, c, env0, E, tid, T);
+    d2d_phase_agents<true>(P, c, env0, E, tid, T);
+    if (tid < E && c.S[tid].valid) d2d_leader_begin(P, c.S[tid]);
+    __syncthreads();
+    d2d_mbar_wait(c.mbar, 0);
+    d2d_phase_rays(P, c, env0, E, tid, T);
+    __syncthreads();
+    d2d_phase_trackers(P, c, env0, E, tid, T);
+    __syncthreads();
+    if (tid < E && c.S[tid].valid) {
+        EnvS &s = c.S[tid];
+        const int e = env0 + tid;
+        // NoMove.plan traj_planner.py:70-73 / NoMove.replan_check :75-76
+        s.tgx = -1.0; s.tgy = -1.0;
+        P.replan[e] = 0; P.plan_ok[e] = 1; P.need_plan[e] = 0;
+        d2d_leader_finish(P, s, c.gt + (size_t)tid * D2D_GRID, e, actions[e], true);
+        d2d_leader_flags(P, s, c.gt + (size_t)tid * D2D_GRID, e);
+        d2d_store_env_scalars(P, s, e);
+        if (s.done_now) c.misc[0] = 1;
+    }
+    if (tid == 0) {
+        int nv = 0;
+        for (int i = 0; i < E; i++) nv += c.S[i].valid;
+        atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], (unsigned long long)nv);
+    }
+    __syncthreads();
+    d2d_phase_obs(P, c, env0, E, tid, T);
+    if (c.misc[0]) d2d_phase_done_stats(P, c, E, tid, T);
+}

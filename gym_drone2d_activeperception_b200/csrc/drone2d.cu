@@ -1,0 +1,448 @@
+// drone2d.cu -- C-ABI implementation of libdrone2d.so (see include/drone2d.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3 --shared -Xcompiler -fPIC
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <initializer_list>
+
+#include "d2d_state.cuh"
+#include "d2d_math.cuh"
+#include "d2d_step.cuh"
+#include "d2d_plan.cuh"
+
+// ------------------------------------------------------------------------------------------ handle
+struct BufDesc {
+    std::string name;
+    size_t offset, nbytes;
+    int dtype, ndim;
+    int64_t shape[4], strides[4];
+};
+
+struct d2d_handle {
+    d2d_config cfg;
+    DevP P;
+    int B, Bpad, N, NP, HW, E, T;
+    unsigned char *arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<BufDesc> bufs;
+    double *stage_actions = nullptr;     // device staging for d2d_step_host
+    int64_t launches = 0;
+    bool world_set = false;
+    std::string err;
+    size_t smem_step = 0, smem_post = 0;
+    int plan_threads = 64;
+};
+
+static thread_local std::string g_create_err;
+
+static size_t dtype_size(int dt) {
+    switch (dt) {
+        case D2D_U8: case D2D_I8: return 1;
+        case D2D_I32: case D2D_F32: return 4;
+        default: return 8;
+    }
+}
+
+#define CUDA_TRY(h, call)                                                                          \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                         \
+            return D2D_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+// registers a buffer of `count` rows x inner dims; returns offset
+static size_t add_buf(d2d_handle *h, size_t &cursor, const char *name, int dtype, int ndim,
+                      std::initializer_list<int64_t> shape, std::initializer_list<int64_t> strides, size_t alloc_elems) {
+    BufDesc b;
+    b.name = name; b.dtype = dtype; b.ndim = ndim;
+    for (int i = 0; i < 4; i++) { b.shape[i] = i < ndim ? shape.begin()[i] : 1; b.strides[i] = i < ndim ? strides.begin()[i] : 1; }
+    cursor = (cursor + 255) / 256 * 256;
+    b.offset = cursor;
+    b.nbytes = alloc_elems * dtype_size(dtype);
+    cursor += b.nbytes;
+    h->bufs.push_back(b);
+    return b.offset;
+}
+
+extern "C" int d2d_version(void) { return D2D_VERSION; }
+
+extern "C" const char *d2d_last_error(const d2d_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int64_t d2d_launch_count(const d2d_handle *h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------ reset kernel
+// Eager reset (Drone2DEnv2.reset -> __init__, drone_v2.py:259-261, 69-117) of masked envs from the snapshot.
+__global__ void d2d_reset_kernel(const DevP P, const uint8_t *__restrict__ mask) {
+    const int e = blockIdx.x;
+    if (e >= P.B) return;
+    if (mask && !mask[e]) return;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const size_t base = (size_t)e * P.NP;
+    for (int k = tid; k < P.N; k += T) {
+        P.apos[base + k] = P.apos0[base + k];
+        P.apref[base + k] = P.apref0[base + k];
+        P.hit[base + k] = 0;
+        P.trk_active[base + k] = 0;
+        P.trk_radius[base + k] = P.trk_radius0[base + k];
+        P.trk_ts[base + k] = 1;
+        double *mu = P.trk_mu + (base + k) * 4, *S = P.trk_sigma + (base + k) * 16;
+        for (int i = 0; i < 4; i++) mu[i] = 0.0;
+        for (int i = 0; i < 16; i++) S[i] = 0.0;
+        S[0] = 1.0; S[5] = 1.0; S[10] = 10.0; S[15] = 10.0;
+    }
+    uint32_t *bel = (uint32_t *)(P.belief + (size_t)e * D2D_BELIEF_STRIDE);
+    for (int w = tid; w < D2D_BELIEF_STRIDE / 4; w += T) bel[w] = 0u;
+    for (int w = tid; w < D2D_LOCAL_CELLS; w += T) P.local_map[(size_t)e * D2D_LOCAL_CELLS + w] = 0;
+    if (P.ox_last)
+        for (int w = tid; w < D2D_CELLS; w += T) P.ox_last[(size_t)e * D2D_CELLS + w] = 5.0;
+    if (tid == 0) {
+        const double x = P.pose0[e], y = P.pose0[P.B + e], yaw = P.pose0[2 * P.B + e];
+        P.drone_x[e] = x; P.drone_y[e] = y; P.drone_yaw[e] = yaw; P.drone_vx[e] = 0; P.drone_vy[e] = 0;
+        P.target_x[e] = x; P.target_y[e] = y;
+        P.steps[e] = 0; P.state_machine[e] = SM_WAIT_FOR_GOAL; P.fail_count[e] = 0; P.target_cursor[e] = 0;
+        P.collision[e] = 0; P.dead_lock[e] = 0; P.freezing[e] = 0; P.done[e] = 0; P.pending_reset[e] = 0;
+        P.buf_count[e] = 0; P.buf_ts[e] = 0; P.tracked_agent[e] = 0;
+        P.traj_nseg[e] = 0; P.traj_cursor[e] = 0; P.need_plan[e] = 0; P.plan_ok[e] = 1; P.replan[e] = 0;
+        P.yaw_obs[e] = (float)yaw;
+    }
+}
+
+__global__ void d2d_set_pose_kernel(const DevP P, const double *__restrict__ pose) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P.B) return;
+    P.drone_x[e] = pose[3 * e]; P.drone_y[e] = pose[3 * e + 1]; P.drone_yaw[e] = pose[3 * e + 2];
+}
+
+// ------------------------------------------------------------------------------------------ create / destroy
+extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
+    if (!cfg || !out) { g_create_err = "null argument"; return D2D_ERR_INVALID; }
+    if (cfg->struct_size != (int32_t)sizeof(d2d_config)) { g_create_err = "d2d_config size mismatch (ABI)"; return D2D_ERR_INVALID; }
+    if (cfg->num_envs <= 0 || cfg->num_agents < 0 || cfg->num_agents > 4000) { g_create_err = "bad num_envs / num_agents"; return D2D_ERR_INVALID; }
+    if ((int)(cfg->map_w / cfg->map_scale) != D2D_GRID || (int)(cfg->map_h / cfg->map_scale) != D2D_GRID) {
+        g_create_err = "only 50x50-cell maps are supported (map_size // map_scale == 50)"; return D2D_ERR_INVALID;
+    }
+    if (4 * (int)(cfg->drone_view_depth / cfg->map_scale) + 1 != D2D_LOCAL) {
+        g_create_err = "only drone_view_depth // map_scale == 8 (33x33 local map) is supported"; return D2D_ERR_INVALID;
+    }
+    if (cfg->n_rays <= 0 || cfg->n_rays > 1024 || cfg->n_targets < 1 || cfg->n_targets > D2D_MAX_TARGETS ||
+        cfg->n_u > D2D_MAX_U || cfg->n_samp > D2D_MAX_SAMP || cfg->n_way > D2D_MAX_WAY || cfg->n_yaw > D2D_MAX_YAW) {
+        g_create_err = "table size out of range"; return D2D_ERR_INVALID;
+    }
+    if (cfg->var_cam != 0.0) { g_create_err = "var_cam != 0 (noisy measurements) is not implemented"; return D2D_ERR_INVALID; }
+    d2d_handle *h = new d2d_handle();
+    h->cfg = *cfg;
+    cudaError_t ce = cudaSetDevice(cfg->device);
+    if (ce != cudaSuccess) { g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(ce); delete h; return D2D_ERR_CUDA; }
+    const int B = cfg->num_envs, N = cfg->num_agents;
+    const int Bpad = (B + 15) / 16 * 16;
+    const int NP = (N > 0 ? N : 1);
+    h->B = B; h->Bpad = Bpad; h->N = N; h->NP = NP; h->HW = (NP + 31) / 32;
+    // envs per block / threads: E*n_rays ray items per block, one per thread when it fits
+    int E = cfg->envs_per_block;
+    if (E != 4 && E != 8 && E != 16) E = 8;
+    while (E > 4 && (size_t)E * cfg->n_rays > 1024) E /= 2;   // keep >= 1 thread per ray when possible
+    h->E = E;
+    int T = (E * cfg->n_rays + 31) / 32 * 32;
+    const int maxT = (E * 50 + 31) / 32 * 32;   // launch bound of the instantiation (see d2d_step_fused_kernel)
+    if (T > maxT) T = maxT;
+    if (T < 64) T = 64;
+    h->T = T;
+
+    size_t cur = 0;
+    DevP &P = h->P;
+    memset(&P, 0, sizeof(P));
+    const int64_t sB = Bpad;
+#define SHP(...) {__VA_ARGS__}
+    size_t o_apos = add_buf(h, cur, "agent_pos", D2D_F64, 3, SHP(B, N, 2), SHP(NP * 2, 2, 1), (size_t)sB * NP * 2);
+    size_t o_apref = add_buf(h, cur, "agent_pref", D2D_F64, 3, SHP(B, N, 2), SHP(NP * 2, 2, 1), (size_t)sB * NP * 2);
+    size_t o_apos0 = add_buf(h, cur, "agent_pos0", D2D_F64, 3, SHP(B, N, 2), SHP(NP * 2, 2, 1), (size_t)sB * NP * 2);
+    size_t o_apref0 = add_buf(h, cur, "agent_pref0", D2D_F64, 3, SHP(B, N, 2), SHP(NP * 2, 2, 1), (size_t)sB * NP * 2);
+    size_t o_arad = add_buf(h, cur, "agent_radius", D2D_F64, 2, SHP(B, N), SHP(NP, 1), (size_t)sB * NP);
+    size_t o_trad0 = add_buf(h, cur, "tracker_radius0", D2D_F64, 2, SHP(B, N), SHP(NP, 1), (size_t)sB * NP);
+    size_t o_gt = add_buf(h, cur, "gt_rows", D2D_I64, 2, SHP(B, D2D_GRID), SHP(D2D_GRID, 1), (size_t)sB * D2D_GRID);
+    size_t o_bel = add_buf(h, cur, "belief", D2D_U8, 3, SHP(B, D2D_GRID, D2D_GRID), SHP(D2D_BELIEF_STRIDE, D2D_GRID, 1),
+                           (size_t)sB * D2D_BELIEF_STRIDE);
+    size_t o_dx = add_buf(h, cur, "drone_x", D2D_F64, 1, SHP(B), SHP(1), sB);
+    size_t o_dy = add_buf(h, cur, "drone_y", D2D_F64, 1, SHP(B), SHP(1), sB);
+    size_t o_dyaw = add_buf(h, cur, "drone_yaw", D2D_F64, 1, SHP(B), SHP(1), sB);
+    size_t o_dvx = add_buf(h, cur, "drone_vx", D2D_F64, 1, SHP(B), SHP(1), sB);
+    size_t o_dvy = add_buf(h, cur, "drone_vy", D2D_F64, 1, SHP(B), SHP(1), sB);
+    size_t o_pose0 = add_buf(h, cur, "drone_pose0", D2D_F64, 2, SHP(3, B), SHP(B, 1), (size_t)3 * sB);
+    size_t o_tx = add_buf(h, cur, "target_x", D2D_F64, 1, SHP(B), SHP(1), sB);
+    size_t o_ty = add_buf(h, cur, "target_y", D2D_F64, 1, SHP(B), SHP(1), sB);
+    size_t o_steps = add_buf(h, cur, "steps", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_sm = add_buf(h, cur, "state_machine", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_fail = add_buf(h, cur, "fail_count", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_tcur = add_buf(h, cur, "target_cursor", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_col = add_buf(h, cur, "collision_flag", D2D_U8, 1, SHP(B), SHP(1), sB);
+    size_t o_dead = add_buf(h, cur, "dead_lock_flag", D2D_U8, 1, SHP(B), SHP(1), sB);
+    size_t o_frz = add_buf(h, cur, "freezing_flag", D2D_U8, 1, SHP(B), SHP(1), sB);
+    size_t o_done = add_buf(h, cur, "done", D2D_U8, 1, SHP(B), SHP(1), sB);
+    size_t o_pend = add_buf(h, cur, "pending_reset", D2D_U8, 1, SHP(B), SHP(1), sB);
+    size_t o_lm = add_buf(h, cur, "local_map", D2D_U8, 4, SHP(B, 1, D2D_LOCAL, D2D_LOCAL),
+                          SHP(D2D_LOCAL_CELLS, D2D_LOCAL_CELLS, D2D_LOCAL, 1), (size_t)sB * D2D_LOCAL_CELLS);
+    size_t o_yawo = add_buf(h, cur, "yaw_angle", D2D_F32, 2, SHP(B, 1), SHP(1, 1), sB);
+    size_t o_rew = add_buf(h, cur, "reward", D2D_F32, 1, SHP(B), SHP(1), sB);
+    size_t o_hit = add_buf(h, cur, "hit", D2D_I8, 2, SHP(B, N), SHP(NP, 1), (size_t)sB * NP);
+    size_t o_tact = add_buf(h, cur, "tracker_active", D2D_U8, 2, SHP(B, N), SHP(NP, 1), (size_t)sB * NP);
+    size_t o_tmu = add_buf(h, cur, "tracker_mu", D2D_F64, 3, SHP(B, N, 4), SHP(NP * 4, 4, 1), (size_t)sB * NP * 4);
+    size_t o_tsg = add_buf(h, cur, "tracker_sigma", D2D_F64, 4, SHP(B, N, 4, 4), SHP(NP * 16, 16, 4, 1), (size_t)sB * NP * 16);
+    size_t o_trad = add_buf(h, cur, "tracker_radius", D2D_F64, 2, SHP(B, N), SHP(NP, 1), (size_t)sB * NP);
+    size_t o_tts = add_buf(h, cur, "tracker_ts", D2D_I32, 2, SHP(B, N), SHP(NP, 1), (size_t)sB * NP);
+    size_t o_bufc = add_buf(h, cur, "tracker_buffer_count", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_bufts = add_buf(h, cur, "tracker_buffer_ts", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_trk = add_buf(h, cur, "tracked_agent", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_coef = add_buf(h, cur, "traj_coeff", D2D_F64, 3, SHP(B, D2D_MAX_SEGMENTS, 6), SHP(D2D_MAX_SEGMENTS * 6, 6, 1),
+                            cfg->planner == D2D_PLANNER_PRIMITIVE ? (size_t)sB * D2D_MAX_SEGMENTS * 6 : 16);
+    size_t o_nseg = add_buf(h, cur, "traj_nseg", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_curs = add_buf(h, cur, "traj_cursor", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_need = add_buf(h, cur, "need_plan", D2D_U8, 1, SHP(B), SHP(1), sB);
+    size_t o_pok = add_buf(h, cur, "plan_ok", D2D_U8, 1, SHP(B), SHP(1), sB);
+    size_t o_rep = add_buf(h, cur, "replan", D2D_U8, 1, SHP(B), SHP(1), sB);
+    size_t o_ox = add_buf(h, cur, "oxford_last_time_observed", D2D_F64, 3, SHP(B, D2D_GRID, D2D_GRID),
+                          SHP(D2D_CELLS, D2D_GRID, 1), cfg->oxford ? (size_t)sB * D2D_CELLS : 16);
+    size_t o_stats = add_buf(h, cur, "stats", D2D_I64, 1, SHP(D2D_NUM_STATS), SHP(1), D2D_NUM_STATS);
+    size_t o_tab = add_buf(h, cur, "tables", D2D_U8, 1, SHP((int64_t)sizeof(DevTables)), SHP(1), sizeof(DevTables));
+    size_t o_stage = add_buf(h, cur, "actions_staging", D2D_F64, 1, SHP(B), SHP(1), sB);
+    size_t o_plan_ws = 0;
+    size_t plan_ws_bytes = 0;
+    if (cfg->planner == D2D_PLANNER_PRIMITIVE) {
+        plan_ws_bytes = d2d_plan_workspace_bytes(cfg->n_u) * (size_t)D2D_PLAN_SLOTS;
+        o_plan_ws = add_buf(h, cur, "plan_workspace", D2D_U8, 1, SHP((int64_t)plan_ws_bytes), SHP(1), plan_ws_bytes);
+    }
+    size_t o_plan_list = add_buf(h, cur, "plan_list", D2D_I32, 1, SHP(B + 4), SHP(1), sB + 4);
+#undef SHP
+    h->arena_bytes = (cur + 255) / 256 * 256;
+    ce = cudaMalloc((void **)&h->arena, h->arena_bytes);
+    if (ce != cudaSuccess) {
+        g_create_err = std::string("cudaMalloc arena (") + std::to_string(h->arena_bytes) + " B): " + cudaGetErrorString(ce);
+        delete h; return D2D_ERR_NOMEM;
+    }
+    ce = cudaMemset(h->arena, 0, h->arena_bytes);
+    if (ce != cudaSuccess) { g_create_err = std::string("cudaMemset: ") + cudaGetErrorString(ce); cudaFree(h->arena); delete h; return D2D_ERR_CUDA; }
+
+    unsigned char *A = h->arena;
+    P.B = B; P.N = N; P.NP = NP; P.HW = h->HW;
+    P.n_rays = cfg->n_rays; P.planner = cfg->planner; P.trackers = cfg->trackers; P.auto_reset = cfg->auto_reset;
+    P.n_targets = cfg->n_targets; P.n_u = cfg->n_u; P.n_samp = cfg->n_samp; P.n_way = cfg->n_way; P.n_yaw = cfg->n_yaw;
+    P.dt = cfg->dt; P.scale = cfg->map_scale; P.inv_scale = 1.0 / cfg->map_scale; P.map_w = cfg->map_w; P.map_h = cfg->map_h;
+    P.agent_radius = cfg->agent_radius; P.max_acc = cfg->drone_max_acceleration; P.drone_r = cfg->drone_radius;
+    P.max_yaw_speed = cfg->drone_max_yaw_speed; P.depth2 = cfg->drone_view_depth * cfg->drone_view_depth;
+    P.fov = cfg->drone_view_range * D2D_DEG2RAD;                 // radians(drone.yaw_range), utils.py:575
+    P.max_steps = cfg->max_flight_time / cfg->dt;                // drone_v2.py:89
+    P.var_cam = cfg->var_cam; P.max_speed = cfg->drone_max_speed;
+    // a sample is evaluated only if the previous one was closer than depth: reach = depth + step*sqrt(2) (+ slack)
+    P.cull_reach = cfg->drone_view_depth + (cfg->map_scale - 1.0) * 1.4142135623730951 + 1e-3;
+    P.ox_cos_thresh = cfg->ox_cos_thresh;
+    memcpy(P.targets, cfg->targets, sizeof(P.targets));
+    P.apos = (double2 *)(A + o_apos); P.apref = (double2 *)(A + o_apref);
+    P.apos0 = (double2 *)(A + o_apos0); P.apref0 = (double2 *)(A + o_apref0);
+    P.arad = (double *)(A + o_arad); P.trk_radius0 = (double *)(A + o_trad0);
+    P.gt_rows = (uint64_t *)(A + o_gt); P.belief = A + o_bel;
+    P.drone_x = (double *)(A + o_dx); P.drone_y = (double *)(A + o_dy); P.drone_yaw = (double *)(A + o_dyaw);
+    P.drone_vx = (double *)(A + o_dvx); P.drone_vy = (double *)(A + o_dvy); P.pose0 = (double *)(A + o_pose0);
+    P.target_x = (double *)(A + o_tx); P.target_y = (double *)(A + o_ty);
+    P.steps = (int *)(A + o_steps); P.state_machine = (int *)(A + o_sm); P.fail_count = (int *)(A + o_fail);
+    P.target_cursor = (int *)(A + o_tcur);
+    P.collision = A + o_col; P.dead_lock = A + o_dead; P.freezing = A + o_frz; P.done = A + o_done; P.pending_reset = A + o_pend;
+    P.local_map = A + o_lm; P.yaw_obs = (float *)(A + o_yawo); P.reward = (float *)(A + o_rew); P.hit = (int8_t *)(A + o_hit);
+    P.trk_active = A + o_tact; P.trk_mu = (double *)(A + o_tmu); P.trk_sigma = (double *)(A + o_tsg);
+    P.trk_radius = (double *)(A + o_trad); P.trk_ts = (int *)(A + o_tts);
+    P.buf_count = (int *)(A + o_bufc); P.buf_ts = (int *)(A + o_bufts); P.tracked_agent = (int *)(A + o_trk);
+    P.traj_coeff = (double *)(A + o_coef); P.traj_nseg = (int *)(A + o_nseg); P.traj_cursor = (int *)(A + o_curs);
+    P.need_plan = A + o_need; P.plan_ok = A + o_pok; P.replan = A + o_rep;
+    P.ox_last = cfg->oxford ? (double *)(A + o_ox) : nullptr;
+    P.stats = (unsigned long long *)(A + o_stats);
+    P.tab = (const DevTables *)(A + o_tab);
+    P.plan_ws = cfg->planner == D2D_PLANNER_PRIMITIVE ? (A + o_plan_ws) : nullptr;
+    P.plan_list = (int *)(A + o_plan_list);
+    h->stage_actions = (double *)(A + o_stage);
+
+    DevTables tab;
+    memset(&tab, 0, sizeof(tab));
+    memcpy(tab.u_space, cfg->u_space, sizeof(tab.u_space));
+    memcpy(tab.t_samp, cfg->t_samp, sizeof(tab.t_samp)); memcpy(tab.t_samp2, cfg->t_samp2, sizeof(tab.t_samp2));
+    memcpy(tab.t_way, cfg->t_way, sizeof(tab.t_way)); memcpy(tab.t_way2, cfg->t_way2, sizeof(tab.t_way2));
+    memcpy(tab.t_way_x2, cfg->t_way_x2, sizeof(tab.t_way_x2));
+    memcpy(tab.v_yaw_space, cfg->v_yaw_space, sizeof(tab.v_yaw_space));
+    ce = cudaMemcpy(A + o_tab, &tab, sizeof(tab), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { g_create_err = std::string("cudaMemcpy tables: ") + cudaGetErrorString(ce); cudaFree(h->arena); delete h; return D2D_ERR_CUDA; }
+
+    h->smem_step = d2d_step_smem_bytes(E, NP, h->HW);
+    if (h->smem_step > 227 * 1024) {
+        g_create_err = "shared memory per block exceeds 227 KB (too many agents per env for this envs_per_block)";
+        cudaFree(h->arena); delete h; return D2D_ERR_INVALID;
+    }
+    *out = h;
+    return D2D_OK;
+}
+
+extern "C" int d2d_destroy(d2d_handle *h) {
+    if (!h) return D2D_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->arena) cudaFree(h->arena);
+    delete h;
+    return D2D_OK;
+}
+
+extern "C" int d2d_get_buffer(d2d_handle *h, const char *name, d2d_buffer_info *out) {
+    if (!h || !name || !out) return D2D_ERR_INVALID;
+    for (const BufDesc &b : h->bufs) {
+        if (b.name == name) {
+            out->dev_ptr = h->arena + b.offset; out->nbytes = (int64_t)b.nbytes; out->dtype = b.dtype; out->ndim = b.ndim;
+            for (int i = 0; i < 4; i++) { out->shape[i] = b.shape[i]; out->strides[i] = b.strides[i]; }
+            return D2D_OK;
+        }
+    }
+    h->err = std::string("unknown buffer: ") + name;
+    return D2D_ERR_INVALID;
+}
+
+// ------------------------------------------------------------------------------------------ world upload
+extern "C" int d2d_set_world(d2d_handle *h, int32_t first_env, int32_t count, const double *agent_pos,
+                             const double *agent_pref, const double *agent_radius, const double *tracker_radius,
+                             const uint8_t *gt_grid, const double *drone_pose) {
+    if (!h) return D2D_ERR_INVALID;
+    if (first_env < 0 || count <= 0 || first_env + count > h->B || !gt_grid || !drone_pose ||
+        (h->N > 0 && (!agent_pos || !agent_pref || !agent_radius || !tracker_radius))) {
+        h->err = "d2d_set_world: bad range or null array"; return D2D_ERR_INVALID;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const DevP &P = h->P;
+    const int N = h->N, NP = h->NP;
+    const size_t e0 = (size_t)first_env;
+    if (N > 0) {   // NP == N, rows are dense
+        CUDA_TRY(h, cudaMemcpy(P.apos0 + e0 * NP, agent_pos, (size_t)count * N * 16, cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(P.apref0 + e0 * NP, agent_pref, (size_t)count * N * 16, cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(P.arad + e0 * NP, agent_radius, (size_t)count * N * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(P.trk_radius0 + e0 * NP, tracker_radius, (size_t)count * N * 8, cudaMemcpyHostToDevice));
+    }
+    std::vector<uint64_t> rows((size_t)count * D2D_GRID);
+    for (int c = 0; c < count; c++)
+        for (int i = 0; i < D2D_GRID; i++) {
+            uint64_t bits = 0;
+            for (int j = 0; j < D2D_GRID; j++)
+                if (gt_grid[((size_t)c * D2D_GRID + i) * D2D_GRID + j] == 1) bits |= (1ull << j);
+            rows[(size_t)c * D2D_GRID + i] = bits;
+        }
+    CUDA_TRY(h, cudaMemcpy(P.gt_rows + e0 * D2D_GRID, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice));
+    std::vector<double> col((size_t)count);
+    for (int f = 0; f < 3; f++) {
+        for (int c = 0; c < count; c++) col[c] = drone_pose[3 * (size_t)c + f];
+        CUDA_TRY(h, cudaMemcpy(P.pose0 + (size_t)f * P.B + e0, col.data(), (size_t)count * 8, cudaMemcpyHostToDevice));
+    }
+    // reset exactly those envs
+    std::vector<uint8_t> mask((size_t)h->B, 0);
+    for (int c = 0; c < count; c++) mask[e0 + c] = 1;
+    uint8_t *dmask = nullptr;
+    CUDA_TRY(h, cudaMalloc((void **)&dmask, (size_t)h->B));
+    cudaError_t ce = cudaMemcpy(dmask, mask.data(), (size_t)h->B, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+        d2d_reset_kernel<<<h->B, 128>>>(P, dmask);
+        h->launches++;
+        ce = cudaDeviceSynchronize();
+    }
+    cudaFree(dmask);
+    if (ce != cudaSuccess) { h->err = std::string("d2d_set_world reset: ") + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
+    h->world_set = true;
+    return D2D_OK;
+}
+
+extern "C" int d2d_reset(d2d_handle *h, const uint8_t *mask_dev, void *stream) {
+    if (!h) return D2D_ERR_INVALID;
+    if (!h->world_set) { h->err = "d2d_reset before d2d_set_world"; return D2D_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    d2d_reset_kernel<<<h->B, 128, 0, (cudaStream_t)stream>>>(h->P, mask_dev);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return D2D_OK;
+}
+
+extern "C" int d2d_set_drone_pose(d2d_handle *h, const double *pose_host, void *stream) {
+    if (!h || !pose_host) return D2D_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    double *tmp = nullptr;
+    CUDA_TRY(h, cudaMalloc((void **)&tmp, (size_t)h->B * 24));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce = cudaMemcpyAsync(tmp, pose_host, (size_t)h->B * 24, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) {
+        d2d_set_pose_kernel<<<(h->B + 255) / 256, 256, 0, st>>>(h->P, tmp);
+        h->launches++;
+        ce = cudaStreamSynchronize(st);
+    }
+    cudaFree(tmp);
+    if (ce != cudaSuccess) { h->err = std::string("d2d_set_drone_pose: ") + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
+    return D2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------ step
+template <int E>
+static int launch_fused(d2d_handle *h, const double *actions, cudaStream_t st) {
+    static bool attr_done[64] = {false};
+    const int dev = h->cfg.device;
+    if (!attr_done[dev & 63]) {
+        cudaError_t ce = cudaFuncSetAttribute(d2d_step_fused_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
+        attr_done[dev & 63] = true;
+    }
+    const int grid = (h->B + E - 1) / E;
+    d2d_step_fused_kernel<E><<<grid, h->T, h->smem_step, st>>>(h->P, actions);
+    h->launches++;
+    return D2D_OK;
+}
+
+static int step_primitive(d2d_handle *h, const double *actions, cudaStream_t st);
+
+extern "C" int d2d_step(d2d_handle *h, const double *actions_dev, void *stream) {
+    if (!h || !actions_dev) return D2D_ERR_INVALID;
+    if (!h->world_set) { h->err = "d2d_step before d2d_set_world"; return D2D_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (h->cfg.planner == D2D_PLANNER_NOMOVE) {
+        switch (h->E) {
+            case 4: rc = launch_fused<4>(h, actions_dev, st); break;
+            case 16: rc = launch_fused<16>(h, actions_dev, st); break;
+            default: rc = launch_fused<8>(h, actions_dev, st); break;
+        }
+    } else {
+        rc = step_primitive(h, actions_dev, st);
+    }
+    if (rc != D2D_OK) return rc;
+    CUDA_TRY(h, cudaGetLastError());
+    return D2D_OK;
+}
+
+extern "C" int d2d_step_host(d2d_handle *h, const double *actions_host, uint8_t *local_map_host, float *yaw_host,
+                             uint8_t *done_host, void *stream) {
+    if (!h || !actions_host) return D2D_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaMemcpyAsync(h->stage_actions, actions_host, (size_t)h->B * 8, cudaMemcpyHostToDevice, st));
+    int rc = d2d_step(h, h->stage_actions, stream);
+    if (rc != D2D_OK) return rc;
+    if (local_map_host)
+        CUDA_TRY(h, cudaMemcpyAsync(local_map_host, h->P.local_map, (size_t)h->B * D2D_LOCAL_CELLS, cudaMemcpyDeviceToHost, st));
+    if (yaw_host) CUDA_TRY(h, cudaMemcpyAsync(yaw_host, h->P.yaw_obs, (size_t)h->B * 4, cudaMemcpyDeviceToHost, st));
+    if (done_host) CUDA_TRY(h, cudaMemcpyAsync(done_host, h->P.done, (size_t)h->B, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return D2D_OK;
+}
+
+extern "C" int d2d_stats(d2d_handle *h, int64_t *out_host, int32_t reset, void *stream) {
+    if (!h || !out_host) return D2D_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaMemcpyAsync(out_host, h->P.stats, D2D_NUM_STATS * 8, cudaMemcpyDeviceToHost, st));
+    if (reset) CUDA_TRY(h, cudaMemsetAsync(h->P.stats, 0, D2D_NUM_STATS * 8, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return D2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------ Primitive planner path + Oxford
+#include "d2d_plan_host.inl"

@@ -1,0 +1,152 @@
+/*
+ * drone2d.h -- C ABI of libdrone2d.so: the B200-native batched replacement for the per-step hot path of
+ * smoggy-P/gym-Drone2D-ActivePerception.
+ *
+ * The reference has no FFI layer; its boundary for this path is the gym 0.21 Env protocol of
+ * `Drone2DEnv2` (envs/drone_v2.py:69 __init__, :152 step, :259 reset) plus the `env.info` dict its callers
+ * read (experiment.py:69-101, yaw_planner.py:81-127).  Each entry point below names the reference interface
+ * it replaces.  All functions return 0 on success or a negative d2d_status; no C++ exception crosses the
+ * ABI; d2d_last_error() gives the message.  A handle is bound to one CUDA device and is not thread-safe;
+ * distinct handles (one per GPU / process) are independent.  All work is enqueued on the caller's stream
+ * (a `cudaStream_t` passed as void*, NULL = legacy default stream); only the *_host variants and d2d_stats
+ * synchronise that stream.
+ *
+ * Memory: the library owns one device arena per handle (SoA state for `num_envs` environments, laid out
+ * env-major so one thread block streams the state of its environments with coalesced / bulk copies).
+ * d2d_get_buffer() exposes every state and observation array as a raw device pointer + shape/strides so the
+ * host language can wrap them zero-copy (the Python host wraps them as torch tensors).
+ */
+#ifndef DRONE2D_H
+#define DRONE2D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D2D_VERSION 100          /* 0.1.0 */
+#define D2D_MAX_TARGETS 8
+#define D2D_MAX_U 64
+#define D2D_MAX_SAMP 32
+#define D2D_MAX_WAY 64
+#define D2D_MAX_YAW 16
+#define D2D_MAX_SEGMENTS 100     /* Primitive.plan stops after 99 expansions (traj_planner.py:149) */
+#define D2D_BELIEF_STRIDE 2560   /* bytes per env of the belief grid buffer (50*50 used, 128-B aligned rows) */
+#define D2D_NUM_STATS 16
+
+typedef enum d2d_status {
+    D2D_OK = 0,
+    D2D_ERR_INVALID = -1,        /* bad argument / unsupported configuration */
+    D2D_ERR_CUDA = -2,           /* a CUDA runtime call failed (see d2d_last_error) */
+    D2D_ERR_NOMEM = -3,
+    D2D_ERR_STATE = -4           /* call sequence error, e.g. step before set_world */
+} d2d_status;
+
+typedef enum d2d_planner { D2D_PLANNER_NOMOVE = 0, D2D_PLANNER_PRIMITIVE = 1 } d2d_planner;
+
+typedef enum d2d_dtype { D2D_U8 = 0, D2D_I8 = 1, D2D_I32 = 2, D2D_I64 = 3, D2D_F32 = 4, D2D_F64 = 5 } d2d_dtype;
+
+/* indices into the statistics vector (episode totals, experiment.py:76-101 CSV columns) */
+enum {
+    D2D_STAT_ENV_STEPS = 0, D2D_STAT_EPISODES, D2D_STAT_SUCCESS, D2D_STAT_STATIC_COLLISION,
+    D2D_STAT_DYNAMIC_COLLISION, D2D_STAT_FREEZING, D2D_STAT_DEAD_LOCK, D2D_STAT_FLIGHT_STEPS,
+    D2D_STAT_GRID_DISCOVERED, D2D_STAT_AGENTS_TRACKED, D2D_STAT_TRACKED_STEPS, D2D_STAT_PLANS,
+    D2D_STAT_PLAN_FAILURES, D2D_STAT_REPLANS
+};
+
+/* Mirrors the reference `Params` object (utils.py:65-106) plus the batch shape.  The lookup tables are the
+ * reference's own numpy expressions, evaluated by the host (traj_planner.py:98-104,180,212; yaw_planner.py:65)
+ * so that np.arange's element values are reproduced exactly. */
+typedef struct d2d_config {
+    int32_t struct_size;             /* sizeof(d2d_config), ABI check */
+    int32_t device;                  /* CUDA device ordinal */
+    int32_t num_envs;                /* B */
+    int32_t num_agents;              /* N = agent_number + nnz(static_map) (drone_v2.py:28-66) */
+    int32_t planner;                 /* d2d_planner */
+    int32_t trackers;                /* 1: run the Kalman trackers (utils.py:242-275) every step, as the reference does */
+    int32_t auto_reset;              /* 1: an env that reported done is re-initialised at the start of its next step */
+    int32_t oxford;                  /* 1: allocate the Oxford gaze-policy state (yaw_planner.py:49-50) */
+    int32_t envs_per_block;          /* 0 = library default; tuning knob (4, 8 or 16) */
+    int32_t n_rays;                  /* ceil(map_size[0] / strip_width), utils.py:587 */
+    int32_t n_targets;
+    int32_t n_u, n_samp, n_way, n_yaw;
+    int32_t reserved0;
+    double dt, map_scale, map_w, map_h;
+    double agent_radius;             /* params.agent_radius */
+    double drone_max_acceleration, drone_radius, drone_max_yaw_speed;
+    double drone_view_depth, drone_view_range, max_flight_time, var_cam, drone_max_speed;
+    double ox_cos_thresh;            /* min{c : np.arccos(c) <= radians(view_range/2)} (host bisection) */
+    double targets[D2D_MAX_TARGETS][2];
+    double u_space[D2D_MAX_U];
+    double t_samp[D2D_MAX_SAMP], t_samp2[D2D_MAX_SAMP];
+    double t_way[D2D_MAX_WAY], t_way2[D2D_MAX_WAY], t_way_x2[D2D_MAX_WAY];
+    double v_yaw_space[D2D_MAX_YAW];
+} d2d_config;
+
+typedef struct d2d_handle d2d_handle;
+
+typedef struct d2d_buffer_info {
+    void *dev_ptr;
+    int64_t nbytes;
+    int32_t dtype;                   /* d2d_dtype */
+    int32_t ndim;
+    int64_t shape[4];
+    int64_t strides[4];              /* in elements */
+} d2d_buffer_info;
+
+int d2d_version(void);
+const char *d2d_last_error(const d2d_handle *h);   /* h may be NULL: error of the last failed d2d_create */
+
+/* Replaces Drone2DEnv2.__init__ (drone_v2.py:69-149) minus world generation: allocates the arena. */
+int d2d_create(const d2d_config *cfg, d2d_handle **out);
+int d2d_destroy(d2d_handle *h);
+
+/* Replaces the state produced by init_obstacles_random_size + OccupancyGridMap.init_obstacles
+ * (drone_v2.py:12-66, utils.py:508-525) for envs [first_env, first_env+count): HOST arrays, env-major.
+ *   agent_pos, agent_pref : [count][N][2] f64     agent_radius, tracker_radius : [count][N] f64
+ *   gt_grid : [count][gw][gh] u8 ground-truth grid (only cells == 1 are occupancy; utils.py:666,770)
+ *   drone_pose : [count][3] f64 (x, y, yaw degrees)
+ * Stores the data as the per-env reset snapshot and resets those envs (reset() == __init__, drone_v2.py:259). */
+int d2d_set_world(d2d_handle *h, int32_t first_env, int32_t count, const double *agent_pos, const double *agent_pref,
+                  const double *agent_radius, const double *tracker_radius, const uint8_t *gt_grid,
+                  const double *drone_pose);
+
+/* Replaces Drone2DEnv2.reset() (drone_v2.py:259-261) for every env whose mask byte is non-zero
+ * (mask_dev == NULL: all).  mask_dev is a DEVICE pointer to num_envs bytes. */
+int d2d_reset(d2d_handle *h, const uint8_t *mask_dev, void *stream);
+
+/* Replaces Drone2DEnv2.step(a) (drone_v2.py:152-257) for all envs.  actions_dev: DEVICE [num_envs] f64 in [-1, 1].
+ * Results land in the buffers "local_map", "yaw_angle", "done", "collision_flag", ... (d2d_get_buffer). */
+int d2d_step(d2d_handle *h, const double *actions_dev, void *stream);
+
+/* Same step with HOST buffers (the call an FFI user makes): copies actions host->device, steps, copies the
+ * observation back and synchronises.  Any output pointer may be NULL.
+ *   local_map_host [num_envs][1][L][L] u8, yaw_host [num_envs] f32, done_host [num_envs] u8 */
+int d2d_step_host(d2d_handle *h, const double *actions_host, uint8_t *local_map_host, float *yaw_host,
+                  uint8_t *done_host, void *stream);
+
+/* Replaces Oxford.plan(env.info) (yaw_planner.py:81-127) for all envs: writes the chosen action per env to
+ * actions_out_dev (DEVICE [num_envs] f64) and advances the policy state.  Requires cfg.oxford = 1. */
+int d2d_plan_oxford(d2d_handle *h, double *actions_out_dev, void *stream);
+
+/* Replaces direct writes to env.drone.x / .y / .yaw by the metric scripts
+ * (script/difficulty_calculator/glob_survivability_calculator.py:36-37).  pose_host: [num_envs][3] f64 HOST. */
+int d2d_set_drone_pose(d2d_handle *h, const double *pose_host, void *stream);
+
+/* Named views of the arena (see DESIGN.md "Data layout"): "local_map", "yaw_angle", "done", "belief", "agent_pos",
+ * "agent_pref", "agent_radius", "hit", "drone_x", ... Returns D2D_ERR_INVALID for an unknown name. */
+int d2d_get_buffer(d2d_handle *h, const char *name, d2d_buffer_info *out);
+
+/* Episode statistics accumulated on the device since the last call with reset != 0; copies D2D_NUM_STATS int64
+ * counters to out_host (synchronises the stream).  The multi-GPU host all-reduces this vector (NCCL). */
+int d2d_stats(d2d_handle *h, int64_t *out_host, int32_t reset, void *stream);
+
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
+int64_t d2d_launch_count(const d2d_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRONE2D_H */

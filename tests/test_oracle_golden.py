@@ -1,0 +1,78 @@
+"""The C restatement (oracle/drone2d_oracle.c) against the committed outputs of the reference (tests/golden)."""
+import numpy as np
+import pytest
+
+import util
+
+
+def _run_against_golden(g, use_oxford):
+    import oracle
+    p = util.params_from_golden(g)
+    e = util.oracle_env_from_world(p, util.world_from_golden(g), 0)
+    n = int(g["n_agents"])
+    T = len(g["done"])
+    has_trk = "trk_active" in g
+    first_done = T
+    plan_i = 0
+    for t in range(T):
+        if use_oxford:
+            a = e.oxford_plan()
+            assert a == g["action"][t], ("action", t)
+            assert np.array_equal(e.ox_last, g["ox_last"][t]), ("oxford last_time_observed", t)
+        a = float(g["action"][t])
+        d = e.step(a)
+        assert np.array_equal(e.belief, g["belief"][t]), ("belief", t)
+        assert np.array_equal(e.hit[:n], g["hit"][t]), ("hit", t)
+        assert e.c.collision == g["collision"][t] and d == bool(g["done"][t]), ("collision/done", t)
+        assert e.c.dead_lock == g["dead_lock"][t] and e.c.freezing == g["freezing"][t], ("flags", t)
+        assert e.c.state_machine == g["state_machine"][t] and e.c.fail_count == g["fail_count"][t], ("sm", t)
+        assert np.array_equal(e.local_map, g["local_map"][t]), ("local_map", t)
+        assert np.float32(e.c.yaw_obs) == g["yaw_obs"][t]
+        assert (e.c.x, e.c.y, e.c.yaw) == tuple(g["drone"][t]), ("drone", t)
+        assert (e.c.vx, e.c.vy) == tuple(g["drone_vel"][t]), ("vel", t)
+        assert np.array_equal(e.apos[:n], g["agent_pos"][t]) and np.array_equal(e.apref[:n], g["agent_pref"][t]), ("agents", t)
+        assert e.c.newly_tracked == g["newly"][t]
+        if has_trk:
+            act = g["trk_active"][t]
+            assert np.array_equal(e.trk_active[:n].astype(bool), act), ("trk_active", t)
+            assert np.array_equal(e.trk_ts[:n], g["trk_ts"][t]) and np.array_equal(e.trk_radius[:n], g["trk_radius"][t])
+            if act.any():
+                assert util.rel_err(e.trk_mu[:n][act], g["trk_mu"][t][act]) < 1e-9
+                assert util.rel_err(e.trk_sigma[:n][act], g["trk_sigma"][t][act]) < 1e-9
+            if t <= first_done:
+                assert (e.c.buf_count, e.c.buf_ts) == (g["buf_count"][t], g["buf_ts"][t]), ("tracker_buffer", t)
+        if "traj_len" in g:
+            assert e.c.traj_len == g["traj_len"][t] and bool(e.c.replan) == bool(g["replan"][t])
+            assert bool(e.c.plan_ok) == bool(g["plan_ok"][t])
+            if g["planned"][t] and g["plan_ok"][t]:
+                pos, vel = e.trajectory()
+                assert np.array_equal(pos, g["plan%d_pos" % plan_i][1:]), ("plan positions", t)
+                assert np.array_equal(vel, g["plan%d_vel" % plan_i][1:]), ("plan velocities", t)
+                plan_i += 1
+        if d and first_done == T:
+            first_done = t
+    e.close()
+
+
+@pytest.mark.parametrize("path", util.golden_files("nomove_"), ids=lambda p: p.split("/")[-1][:-4])
+def test_oracle_matches_reference_nomove(path):
+    _run_against_golden(util.load_golden(path), use_oxford=False)
+
+
+@pytest.mark.parametrize("path", util.golden_files("episode_"), ids=lambda p: p.split("/")[-1][:-4])
+def test_oracle_matches_reference_full_episode(path):
+    """Primitive A* planner + Kalman trackers + Oxford gaze, whole episodes (config 1 of BASELINE.json among them)."""
+    _run_against_golden(util.load_golden(path), use_oxford=True)
+
+
+def test_config1_known_answer():
+    """SURVEY.md §4 known answer for `main.py --gaze_method Oxford --planner Primitive ... --map_id 1`."""
+    import hashlib
+    g = util.load_golden([p for p in util.golden_files("episode_cfg1")][0])
+    assert len(g["done"]) == 210 and g["done"][-1] and g["state_machine"][-1] == 1
+    assert tuple(g["drone"][-1][:2]) == (42.0, 455.0)
+    h = hashlib.sha256()
+    for b, l in zip(g["belief"], g["local_map"]):
+        h.update(b.tobytes())
+        h.update(l.tobytes())
+    assert h.hexdigest() == "4ef16f046fe2bf8fe88fef5b8ad757be6d5504f2a618b061542716b256941abd"

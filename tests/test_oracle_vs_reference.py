@@ -1,0 +1,46 @@
+"""Live cross-check of the oracle against the UNMODIFIED reference (only where /root/reference is mounted)."""
+import numpy as np
+import pytest
+
+import util
+
+ref_runner = pytest.importorskip("ref_runner")
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not ref_runner.reference_available(), reason="reference checkout not present")]
+
+
+def _compare(steps, policy=None, set_pose=None, **kw):
+    from gym_drone2d_activeperception_b200.params import Params
+    acts = util.action_table().tolist()
+    r = ref_runner.run_episode(steps, actions=acts, policy=policy, set_pose=set_pose, stop_on_done=policy is not None,
+                               record_oxford=policy == "Oxford", **kw)
+    P = r["params"]
+    p = Params(debug=False, **{k: P[k] for k in util.PARAM_KEYS if k in P}, init_pos=P["init_position"],
+               target_list=P["target_list"])
+    world = dict(agent_pos=r["agent_pos0"], agent_pref=r["agent_pref0"], agent_radius=r["agent_radius"],
+                 tracker_radius=r["tracker_radius"], gt_grid=r["gt_grid"], drone_pose=r["drone0"])
+    e = util.oracle_env_from_world(p, world)
+    n = r["n_agents"]
+    for t in range(len(r["done"])):
+        if policy == "Oxford":
+            assert e.oxford_plan() == r["action"][t]
+            assert np.array_equal(e.ox_last, r["ox_last"][t])
+        d = e.step(float(r["action"][t]))
+        assert np.array_equal(e.belief, r["belief"][t]) and np.array_equal(e.hit[:n], r["hit"][t]), t
+        assert (e.c.collision, d) == (r["collision"][t], bool(r["done"][t])), t
+        assert (e.c.x, e.c.y, e.c.yaw, e.c.vx, e.c.vy) == (*r["drone"][t], *r["drone_vel"][t]), t
+        assert np.array_equal(e.apos[:n], r["agent_pos"][t]), t
+        assert np.array_equal(e.local_map, r["local_map"][t]), t
+        assert e.c.traj_len == r["traj_len"][t] and e.c.state_machine == r["state_machine"][t], t
+        assert np.array_equal(e.trk_active[:n].astype(bool), r["trk_active"][t]), t
+    e.close()
+
+
+@pytest.mark.parametrize("seed", [3, 11])
+@pytest.mark.parametrize("smap", ["maps/empty_map.npy", "maps/obstacle_map.npy"])
+def test_nomove_live(seed, smap):
+    _compare(40, planner="NoMove", map_id=seed, static_map=smap, set_pose=(200.5 + seed, 260.25, 77.0))
+
+
+def test_full_episode_live():
+    _compare(400, policy="Oxford", planner="Primitive", map_id=6, agent_number=12)
