@@ -117,6 +117,7 @@ __device__ __forceinline__ void d2d_load_env_scalars(const DevP &P, EnvS &s, int
         s.bufc = P.buf_count[e]; s.bufts = P.buf_ts[e]; s.tracked = P.tracked_agent[e];
         s.nseg = P.traj_nseg[e]; s.cursor = P.traj_cursor[e];
     }
+    s.ix = d2d_cell(s.px, P.scale, P.inv_scale); s.iy = d2d_cell(s.py, P.scale, P.inv_scale);
 }
 
 __device__ __forceinline__ void d2d_store_env_scalars(const DevP &P, const EnvS &s, int e) {
@@ -147,6 +148,7 @@ __device__ __forceinline__ void d2d_issue_bulk(const DevP &P, const BlockCtx &c,
 
 // envs being reset: zero belief in shared memory and HBM; restore the Oxford policy state
 __device__ __forceinline__ void d2d_reset_arrays(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
+    if (!c.misc[1]) return;   // block-uniform: no env of this block is being reset (the common case)
     const int W = D2D_BELIEF_STRIDE / 4;
     for (int w = tid; w < E * W; w += T) {
         const int i = w / W, o = w - i * W;
@@ -244,8 +246,11 @@ __device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, int r
     }
     double x = s.px, y = s.py;
     const int nc = s.ncull;
+    // int(x // scale) tracked incrementally: |step| < scale, so a sample moves at most one cell per axis, and
+    // x in [scale*ci, scale*(ci+1)) is exactly CPython's floor (multiples of the scale are exact doubles).
+    int ci = s.ix, cj = s.iy;
+    double xlo = P.scale * (double)ci, xhi = xlo + P.scale, ylo = P.scale * (double)cj, yhi = ylo + P.scale;
     while (0.0 < x && x < P.map_w && 0.0 < y && y < P.map_h) {
-        const int ci = d2d_cell(x, P.scale, P.inv_scale), cj = d2d_cell(y, P.scale, P.inv_scale);
         bool any = false;
         for (int q = 0; q < nc; q++) {
             const int k = cull[q];
@@ -267,6 +272,10 @@ __device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, int r
         d2d_mark(bel_s, bel_g, cell, 2);
         x = x + xs;
         y = y + ys;
+        if (x >= xhi) { ci += 1; xlo = xhi; xhi += P.scale; }
+        else if (x < xlo) { ci -= 1; xhi = xlo; xlo -= P.scale; }
+        if (y >= yhi) { cj += 1; ylo = yhi; yhi += P.scale; }
+        else if (y < ylo) { cj -= 1; yhi = ylo; ylo -= P.scale; }
     }
 }
 
@@ -301,23 +310,18 @@ __device__ __forceinline__ void d2d_tracker_update(const DevP &P, EnvS &s, size_
         for (int i = 0; i < 4; i++) m[i] = mu[i];
 #pragma unroll
         for (int i = 0; i < 16; i++) S[i] = Sg[i];
-        // predict utils.py:225-233
+        // predict utils.py:225-233, in place: Sigma <- F Sigma F^T + Q with F = I + 0.1*[[0,I],[0,0]]
         m[0] = m[0] + 0.1 * m[2];
         m[1] = m[1] + 0.1 * m[3];
-        double Tm[16];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            Tm[j] = S[j] + 0.1 * S[8 + j];
-            Tm[4 + j] = S[4 + j] + 0.1 * S[12 + j];
-            Tm[8 + j] = S[8 + j];
-            Tm[12 + j] = S[12 + j];
+        for (int j = 0; j < 4; j++) {   // rows 0,1 += 0.1 * rows 2,3   (F Sigma)
+            S[j] = S[j] + 0.1 * S[8 + j];
+            S[4 + j] = S[4 + j] + 0.1 * S[12 + j];
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            S[4 * i + 0] = Tm[4 * i + 0] + 0.1 * Tm[4 * i + 2];
-            S[4 * i + 1] = Tm[4 * i + 1] + 0.1 * Tm[4 * i + 3];
-            S[4 * i + 2] = Tm[4 * i + 2];
-            S[4 * i + 3] = Tm[4 * i + 3];
+        for (int i = 0; i < 4; i++) {   // cols 0,1 += 0.1 * cols 2,3   ((F Sigma) F^T)
+            S[4 * i + 0] = S[4 * i + 0] + 0.1 * S[4 * i + 2];
+            S[4 * i + 1] = S[4 * i + 1] + 0.1 * S[4 * i + 3];
         }
         S[0] += q; S[5] += q; S[10] += q; S[15] += q;
         ts += 1;
@@ -340,32 +344,27 @@ __device__ __forceinline__ void d2d_tracker_update(const DevP &P, EnvS &s, size_
             const double s00 = rz + S[0], s01 = S[1], s10 = S[4], s11 = rz + S[5];
             const double det = s00 * s11 - s01 * s10;
             const double i00 = s11 / det, i01 = -s01 / det, i10 = -s10 / det, i11 = s00 / det;
-            double K[8];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                K[2 * i] = S[4 * i] * i00 + S[4 * i + 1] * i10;
-                K[2 * i + 1] = S[4 * i] * i01 + S[4 * i + 1] * i11;
-            }
             const double r0 = z0 - m[0], r1 = z1 - m[1];
-            double Sn[16];
+            // rows 3, 2 first (they need the ORIGINAL rows 0 and 1), then rows 0 and 1 together
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 3; i >= 2; i--) {
+                const double k0 = S[4 * i] * i00 + S[4 * i + 1] * i10, k1 = S[4 * i] * i01 + S[4 * i + 1] * i11;
+                m[i] = m[i] + (k0 * r0 + k1 * r1);
+#pragma unroll
+                for (int j = 0; j < 4; j++) S[4 * i + j] = ((-k0) * S[j] + (-k1) * S[4 + j]) + S[4 * i + j];
+            }
+            {
+                const double k00 = S[0] * i00 + S[1] * i10, k01 = S[0] * i01 + S[1] * i11;
+                const double k10 = S[4] * i00 + S[5] * i10, k11 = S[4] * i01 + S[5] * i11;
+                m[0] = m[0] + (k00 * r0 + k01 * r1);
+                m[1] = m[1] + (k10 * r0 + k11 * r1);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    // (I - K H) Sigma : row i = Sigma[i] - K[i][0]*Sigma[0] - K[i][1]*Sigma[1]
-                    double acc = 0.0;
-#pragma unroll
-                    for (int qq = 0; qq < 4; qq++) {
-                        const double aiq = (i == qq ? 1.0 : 0.0) - (qq < 2 ? K[2 * i + qq] : 0.0);
-                        acc += aiq * S[4 * qq + j];
-                    }
-                    Sn[4 * i + j] = acc;
+                    const double a0 = S[j], a1 = S[4 + j];
+                    S[j] = (1.0 - k00) * a0 + (-k01) * a1;
+                    S[4 + j] = (-k10) * a0 + (1.0 - k11) * a1;
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 4; i++) m[i] = m[i] + (K[2 * i] * r0 + K[2 * i + 1] * r1);
-#pragma unroll
-            for (int i = 0; i < 16; i++) S[i] = Sn[i];
         }
     } else {   // first sighting utils.py:263-273
         m[0] = z0; m[1] = z1; m[2] = 0.0; m[3] = 0.0;
@@ -506,20 +505,33 @@ __device__ __forceinline__ void d2d_phase_obs(const DevP &P, const BlockCtx &c, 
     uint32_t *out = (uint32_t *)(P.local_map + (size_t)env0 * D2D_LOCAL_CELLS);
     const int words = E * D2D_LOCAL_CELLS / 4;
     for (int w = tid; w < words; w += T) {
+        const int o = w * 4;
+        int i = o / D2D_LOCAL_CELLS;
+        const int r = o - i * D2D_LOCAL_CELLS;
+        int u = r / D2D_LOCAL, vv = r - u * D2D_LOCAL;
+        int bi = c.S[i].ix - 16, bj = c.S[i].iy - 16;
+        bool valid = c.S[i].valid != 0;
+        const uint8_t *bel = c.belief + (size_t)i * D2D_BELIEF_STRIDE;
         uint32_t v = 0;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            const int o = w * 4 + b;
-            const int i = o / D2D_LOCAL_CELLS, r = o - i * D2D_LOCAL_CELLS;
-            const EnvS &s = c.S[i];
+            const int gi = bi + u, gj = bj + vv;
             uint32_t cellv = 0;
-            if (s.valid) {
-                const int u = r / D2D_LOCAL, vv = r - u * D2D_LOCAL;
-                const int gi = s.ix - 16 + u, gj = s.iy - 16 + vv;
-                if (gi >= 0 && gi < D2D_GRID && gj >= 0 && gj < D2D_GRID)
-                    cellv = c.belief[(size_t)i * D2D_BELIEF_STRIDE + gi * D2D_GRID + gj];
-            }
+            if (valid && (unsigned)gi < (unsigned)D2D_GRID && (unsigned)gj < (unsigned)D2D_GRID)
+                cellv = bel[gi * D2D_GRID + gj];
             v |= cellv << (8 * b);
+            if (++vv == D2D_LOCAL) {
+                vv = 0;
+                if (++u == D2D_LOCAL) {   // next env of the block
+                    u = 0;
+                    if (++i < E) {
+                        bi = c.S[i].ix - 16; bj = c.S[i].iy - 16; valid = c.S[i].valid != 0;
+                        bel = c.belief + (size_t)i * D2D_BELIEF_STRIDE;
+                    } else {
+                        valid = false;
+                    }
+                }
+            }
         }
         out[w] = v;
     }
@@ -540,15 +552,19 @@ __device__ __forceinline__ void d2d_phase_done_stats(const DevP &P, const BlockC
 // Whole Drone2DEnv2.step in one launch when the planner is NoMove (traj_planner.py:68-76): the drone never moves,
 // so the drone-vs-agent test can run with the agent phase and no planner kernel is needed.
 template <int E>
-__global__ void __launch_bounds__((E * 50 + 31) / 32 * 32) d2d_step_fused_kernel(const DevP P, const double *__restrict__ actions) {
+__global__ void __launch_bounds__((E * 50 + 31) / 32 * 32, (E == 4 ? 4 : (E == 8 ? 2 : 1))) d2d_step_fused_kernel(const DevP P, const double *__restrict__ actions) {
     extern __shared__ __align__(128) unsigned char smem[];
     const BlockCtx c = d2d_carve(smem, E, P.NP, P.HW);
     const int tid = threadIdx.x, T = blockDim.x;
     const int env0 = blockIdx.x * E;
 
-    if (tid < E) d2d_load_env_scalars(P, c.S[tid], env0 + tid);
+    if (tid == 0) { d2d_mbar_init(c.mbar, 1); c.misc[0] = 0; c.misc[1] = 0; }
     for (int w = tid; w < E * P.HW; w += T) c.hitw[w] = 0u;
-    if (tid == 0) { d2d_mbar_init(c.mbar, 1); c.misc[0] = 0; }
+    __syncthreads();
+    if (tid < E) {
+        d2d_load_env_scalars(P, c.S[tid], env0 + tid);
+        if (c.S[tid].reset) c.misc[1] = 1;
+    }
     __syncthreads();
     if (tid == 0) d2d_issue_bulk(P, c, env0, E, true);
     d2d_reset_arrays(P, c, env0, E, tid, T);
