@@ -1,5 +1,559 @@
-// d2d_plan.cuh -- Primitive planner kernels (placeholder until the A* kernel lands)
+// d2d_plan.cuh -- kernels for the Primitive planner path and the Oxford gaze policy (sm_100a).
+//
+// With planner == Primitive one env step is three launches (the planner verdict sits in the middle of
+// Drone2DEnv2.step, drone_v2.py:194-204, and an A* search is ~1000x longer than the rest of the step, so it gets
+// its own kernel over a compacted list of the envs that actually need a plan):
+//
+//   d2d_step_pre_kernel   P0-P3 of the fused kernel (agents, rays, trackers) + Primitive.replan_check
+//                         (traj_planner.py:220-233) + compaction of the envs whose trajectory is empty
+//   d2d_plan_kernel       Primitive.plan (traj_planner.py:125-218): one thread block per planning env, A* over
+//                         motion primitives with the reference's insertion-ordered-dict tie breaking
+//   d2d_step_post_kernel  brake / step_pos / step_yaw / is_collide / flags / done / observation
+//
+// d2d_oxford_kernel is Oxford.plan (yaw_planner.py:81-127), one block per env.
 #pragma once
 #include "d2d_state.cuh"
-#define D2D_PLAN_SLOTS 1
-__host__ __device__ inline size_t d2d_plan_workspace_bytes(int n_u) { return 16; }
+#include "d2d_math.cuh"
+#include "d2d_step.cuh"
+
+#define D2D_PLAN_SLOTS 296          // concurrent A* workspaces (2 per SM)
+#define D2D_PLAN_THREADS 128
+#define D2D_HASH_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+// ------------------------------------------------------------------------------------------ shared helpers
+// waypoint `a` (absolute index) of the stored trajectory: segment a / n_way, sample time t_way[n_way-1 - a % n_way]
+// (the reference builds each segment with t = arange(2, 0, -dt) and reverses the whole list, traj_planner.py:212-217)
+__device__ __forceinline__ void d2d_waypoint_pos(const DevP &P, int e, int a, double &x, double &y) {
+    const int seg = a / P.n_way, ws = a - seg * P.n_way, ti = P.n_way - 1 - ws;
+    const double *cf = P.traj_coeff + ((size_t)e * D2D_MAX_SEGMENTS + seg) * 6;
+    const double t = P.tab->t_way[ti], t2 = P.tab->t_way2[ti];
+    x = rint(D2D_FMA(t2, cf[2], cf[0] + t * cf[1]));
+    y = rint(D2D_FMA(t2, cf[5], cf[3] + t * cf[4]));
+}
+
+// OccupancyGridMap.get_grid on a belief grid in shared memory (utils.py:545-548)
+__device__ __forceinline__ int d2d_belief_probe(const DevP &P, const uint8_t *bel, double x, double y) {
+    if (x >= P.map_w || x < 0 || y >= P.map_h || y < 0) return 1;
+    return bel[d2d_cell(x, P.scale, P.inv_scale) * D2D_GRID + d2d_cell(y, P.scale, P.inv_scale)];
+}
+
+// Planner.is_free (traj_planner.py:28-59); trk = active trackers as [mu0, mu1, mu2, mu3, radius]
+__device__ __forceinline__ bool d2d_is_free(const DevP &P, const uint8_t *bel, double px, double py, double t,
+                                            const double *trk, int nact) {
+    if (px != px || py != py) return false;
+    const double sd = P.drone_r + 10.0;
+    if (d2d_belief_probe(P, bel, px - sd, py) == 1) return false;
+    if (d2d_belief_probe(P, bel, px, py) == 1) return false;
+    if (d2d_belief_probe(P, bel, px + sd, py) == 1) return false;
+    if (d2d_belief_probe(P, bel, px, py - sd) == 1) return false;
+    if (d2d_belief_probe(P, bel, px, py + sd) == 1) return false;
+    for (int k = 0; k < nact; k++) {
+        const double *m = trk + 5 * k;
+        const double ex = m[0] + t * m[2], ey = m[1] + t * m[3];   // estimate_pos utils.py:220-223
+        if (d2d_norm2(px - ex, py - ey) <= P.drone_r + m[4] + 5.0 + P.var_cam) return false;
+    }
+    return true;
+}
+
+// gathers the env's active trackers into shared memory; returns via *nact (block must sync afterwards)
+__device__ __forceinline__ void d2d_gather_trackers(const DevP &P, int e, double *trk, int *nact, int tid, int T) {
+    for (int k = tid; k < P.N; k += T) {
+        const size_t g = (size_t)e * P.NP + k;
+        if (P.trk_active[g]) {
+            const int slot = atomicAdd(nact, 1);
+            const double *mu = P.trk_mu + g * 4;
+            double *d = trk + 5 * slot;
+            d[0] = mu[0]; d[1] = mu[1]; d[2] = mu[2]; d[3] = mu[3]; d[4] = P.trk_radius[g];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ pre kernel
+__host__ __device__ inline size_t d2d_pre_smem_bytes(int E, int NP, int HW) {
+    return d2d_step_smem_bytes(E, NP, HW) + (size_t)E * NP * 5 * 8 + (size_t)E * 16;
+}
+
+template <int E>
+__global__ void __launch_bounds__((E * 50 + 31) / 32 * 32, (E == 4 ? 4 : (E == 8 ? 2 : 1)))
+d2d_step_pre_kernel(const DevP P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const BlockCtx c = d2d_carve(smem, E, P.NP, P.HW);
+    double *trk = (double *)(smem + d2d_step_smem_bytes(E, P.NP, P.HW));   // [E][NP][5]
+    int *nact = (int *)(trk + (size_t)E * P.NP * 5);                        // [E]
+    int *rep = nact + E;                                                    // [E] replan flags
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int env0 = blockIdx.x * E;
+
+    if (tid == 0) { d2d_mbar_init(c.mbar, 1); c.misc[0] = 0; c.misc[1] = 0; }
+    for (int w = tid; w < E * P.HW; w += T) c.hitw[w] = 0u;
+    if (tid < E) { nact[tid] = 0; rep[tid] = 0; }
+    __syncthreads();
+    if (tid < E) {
+        d2d_load_env_scalars(P, c.S[tid], env0 + tid);
+        if (c.S[tid].reset) c.misc[1] = 1;
+    }
+    __syncthreads();
+    if (tid == 0) d2d_issue_bulk(P, c, env0, E, true);
+    d2d_reset_arrays(P, c, env0, E, tid, T);
+    d2d_phase_agents<false>(P, c, env0, E, tid, T);
+    if (tid < E && c.S[tid].valid) d2d_leader_begin(P, c.S[tid]);
+    __syncthreads();
+    d2d_mbar_wait(c.mbar, 0);
+    d2d_phase_rays(P, c, env0, E, tid, T);
+    __syncthreads();
+    d2d_phase_trackers(P, c, env0, E, tid, T);
+    __syncthreads();
+    // ---- Primitive.replan_check (traj_planner.py:220-233)
+    for (int i = 0; i < E; i++)
+        if (c.S[i].valid) d2d_gather_trackers(P, env0 + i, trk + (size_t)i * P.NP * 5, &nact[i], tid, T);
+    __syncthreads();
+    for (int i = 0; i < E; i++) {
+        const EnvS &s = c.S[i];
+        if (!s.valid) continue;
+        const int len = s.nseg * P.n_way - s.cursor;
+        const uint8_t *bel = c.belief + (size_t)i * D2D_BELIEF_STRIDE;
+        const double *tk = trk + (size_t)i * P.NP * 5;
+        const int na = nact[i];
+        bool hit = false;
+        for (int w = tid; w < len && !hit; w += T) {
+            double x, y;
+            d2d_waypoint_pos(P, env0 + i, s.cursor + w, x, y);
+            const double ti = (double)w * P.dt;
+            // static overlap: swep_map is uint8 (zeros_like of the belief grid), so i*dt is truncated (:222-224,230)
+            const int ci = d2d_cell(x, P.scale, P.inv_scale), cj = d2d_cell(y, P.scale, P.inv_scale);
+            if ((unsigned)ci < (unsigned)D2D_GRID && (unsigned)cj < (unsigned)D2D_GRID) {
+                if (bel[ci * D2D_GRID + cj] == 1 && (uint8_t)ti > 0) hit = true;
+            }
+            for (int k = 0; k < na && !hit; k++) {
+                const double *m = tk + 5 * k;
+                const double ex = m[0] + ti * m[2], ey = m[1] + ti * m[3];
+                if (d2d_norm2(ex - x, ey - y) <= P.drone_r + m[4]) hit = true;   // :225-229
+            }
+        }
+        if (hit) rep[i] = 1;
+    }
+    __syncthreads();
+    if (tid < E && c.S[tid].valid) {
+        EnvS &s = c.S[tid];
+        const int e = env0 + tid;
+        if (rep[tid]) { s.nseg = 0; s.cursor = 0; atomicAdd(&P.stats[D2D_STAT_REPLANS], 1ull); }   // trajectory.clear()
+        const int need = (s.nseg * P.n_way - s.cursor) == 0;
+        P.replan[e] = (uint8_t)rep[tid];
+        P.need_plan[e] = (uint8_t)need;
+        P.plan_ok[e] = 1;
+        if (need) {
+            const int slot = atomicAdd(&P.plan_list[P.B], 1);
+            P.plan_list[slot] = e;
+        }
+        // tracker bookkeeping of this step; the still-active totals travel to the post kernel
+        s.bufc += s.arch_cnt; s.bufts += s.arch_ts; s.tracked += s.newly;
+        P.tmp_act_cnt[e] = s.act_cnt; P.tmp_act_ts[e] = s.act_ts;
+        d2d_store_env_scalars(P, s, e);
+        P.done[e] = 0;   // consumed by the lazy reset above; the post kernel writes this step's verdict
+    }
+}
+
+// ------------------------------------------------------------------------------------------ A* workspace
+struct PlanWs {
+    double *px, *py, *vx, *vy, *cost, *total, *open_total;
+    int *parent, *itr, *act;
+    unsigned long long *hkeys;
+    int *hvals;
+    int cap, hcap;
+};
+
+__host__ __device__ inline int d2d_plan_cap(int n_u) { return 99 * n_u * n_u + 8; }
+__host__ __device__ inline int d2d_plan_hcap(int n_u) {
+    int need = 2 * d2d_plan_cap(n_u), h = 1024;
+    while (h < need) h <<= 1;
+    return h;
+}
+__host__ __device__ inline size_t d2d_plan_workspace_bytes(int n_u) {
+    const size_t cap = (size_t)d2d_plan_cap(n_u), hcap = (size_t)d2d_plan_hcap(n_u);
+    size_t b = cap * 8 * 7 + cap * 4 * 3 + hcap * 8 + hcap * 4;
+    return (b + 255) / 256 * 256;
+}
+__device__ __forceinline__ PlanWs d2d_plan_carve(unsigned char *base, int n_u) {
+    PlanWs w;
+    w.cap = d2d_plan_cap(n_u); w.hcap = d2d_plan_hcap(n_u);
+    double *d = (double *)base;
+    w.px = d; w.py = d + w.cap; w.vx = d + 2 * (size_t)w.cap; w.vy = d + 3 * (size_t)w.cap;
+    w.cost = d + 4 * (size_t)w.cap; w.total = d + 5 * (size_t)w.cap; w.open_total = d + 6 * (size_t)w.cap;
+    w.hkeys = (unsigned long long *)(d + 7 * (size_t)w.cap);
+    int *ip = (int *)(w.hkeys + w.hcap);
+    w.hvals = ip; ip += w.hcap;
+    w.parent = ip; w.itr = ip + w.cap; w.act = ip + 2 * (size_t)w.cap;
+    return w;
+}
+
+// Primitive_Node.get_index (traj_planner.py:92-93): (round(px)//10, round(py)//10, round(vx), round(vy))
+__device__ __forceinline__ long long d2d_floordiv10(long long a) {
+    long long q = a / 10;
+    if ((a % 10 != 0) && (a < 0)) q -= 1;
+    return q;
+}
+__device__ __forceinline__ unsigned long long d2d_node_key(double px, double py, double vx, double vy) {
+    const long long a = d2d_floordiv10((long long)rint(px)), b = d2d_floordiv10((long long)rint(py));
+    const long long c = (long long)rint(vx), d = (long long)rint(vy);
+    return ((unsigned long long)(unsigned short)(short)a << 48) | ((unsigned long long)(unsigned short)(short)b << 32) |
+           ((unsigned long long)(unsigned short)(short)c << 16) | (unsigned long long)(unsigned short)(short)d;
+}
+__device__ __forceinline__ int d2d_hash_slot0(unsigned long long k, int hcap) {
+    return (int)(((k * 0x9E3779B97F4A7C15ull) >> 40) & (unsigned long long)(hcap - 1));
+}
+// returns slot; *existed tells whether the key was already present
+__device__ __forceinline__ int d2d_hash_find_or_insert(const PlanWs &w, unsigned long long key, bool *existed) {
+    int s = d2d_hash_slot0(key, w.hcap);
+    for (;;) {
+        const unsigned long long cur = w.hkeys[s];
+        if (cur == key) { *existed = true; return s; }
+        if (cur == D2D_HASH_EMPTY) {
+            const unsigned long long old = atomicCAS(&w.hkeys[s], D2D_HASH_EMPTY, key);
+            if (old == D2D_HASH_EMPTY) { *existed = false; return s; }
+            if (old == key) { *existed = true; return s; }
+        }
+        s = (s + 1) & (w.hcap - 1);
+    }
+}
+
+// total_cost of a node (traj_planner.py:88)
+__device__ __forceinline__ double d2d_node_total(double cost, double px, double py, double vx, double vy, double tx,
+                                                 double ty) {
+    return cost + 0.5 * d2d_norm2(px - tx, py - ty) + 0.1 * d2d_norm2(vx, vy);
+}
+
+// ------------------------------------------------------------------------------------------ A* kernel
+// One block per planning env (persistent over the compacted list).  Node storage is SoA in an HBM workspace
+// (stays in L2); the belief grid and the active trackers are staged in shared memory.
+__global__ void __launch_bounds__(D2D_PLAN_THREADS) d2d_plan_kernel(const DevP P) {
+    extern __shared__ __align__(16) unsigned char psm[];
+    uint8_t *bel = psm;                                         // [2560]
+    double *trk = (double *)(psm + D2D_BELIEF_STRIDE);          // [NP][5]
+    double *red_v = trk + (size_t)P.NP * 5;                     // [4] warp partials
+    int *red_i = (int *)(red_v + 4);                            // [4]
+    int *sh = red_i + 4;                                        // [8] cur, n_nodes, n_open, status, nact, chunk_new
+    int *wsum = sh + 8;                                         // [4] warp prefix
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int count = min(P.plan_list[P.B], P.B);
+    const PlanWs w = d2d_plan_carve(P.plan_ws + (size_t)blockIdx.x * d2d_plan_workspace_bytes(P.n_u), P.n_u);
+    const int nu = P.n_u, nprim = nu * nu;
+
+    for (int li = blockIdx.x; li < count; li += gridDim.x) {
+        const int e = P.plan_list[li];
+        __syncthreads();
+        // stage belief + trackers, clear the hash table
+        for (int o = tid; o < D2D_BELIEF_STRIDE / 4; o += T)
+            ((uint32_t *)bel)[o] = ((const uint32_t *)(P.belief + (size_t)e * D2D_BELIEF_STRIDE))[o];
+        for (int o = tid; o < w.hcap; o += T) { w.hkeys[o] = D2D_HASH_EMPTY; w.hvals[o] = -1; }
+        if (tid == 0) sh[4] = 0;
+        __syncthreads();
+        d2d_gather_trackers(P, e, trk, &sh[4], tid, T);
+        const double tx = P.target_x[e], ty = P.target_y[e];
+        if (tid == 0) {   // start node (traj_planner.py:136-146)
+            const double x = P.drone_x[e], y = P.drone_y[e], vx = P.drone_vx[e], vy = P.drone_vy[e];
+            w.px[0] = x; w.py[0] = y; w.vx[0] = vx; w.vy[0] = vy; w.cost[0] = 0.0;
+            const double tot = d2d_node_total(0.0, x, y, vx, vy, tx, ty);
+            w.total[0] = tot; w.open_total[0] = tot; w.parent[0] = -1; w.itr[0] = 0; w.act[0] = 0;
+            bool ex;
+            const int s = d2d_hash_find_or_insert(w, d2d_node_key(x, y, vx, vy), &ex);
+            w.hvals[s] = 0;
+            sh[1] = 1; sh[2] = 1; sh[3] = 0;
+        }
+        __syncthreads();
+        const int nact = sh[4];
+        int goal = -1;
+        bool success = false;
+        for (int itr = 1;; itr++) {
+            const int n_nodes = sh[1];
+            if (sh[2] == 0 || itr >= 100) break;                 // traj_planner.py:149
+            // ---- first minimal total_cost in insertion order (min() over a dict, :155-158)
+            double bv = INFINITY;
+            int bi = 0x7fffffff;
+            for (int i = tid; i < n_nodes; i += T) {
+                const double v = w.open_total[i];
+                if (v < bv) { bv = v; bi = i; }
+            }
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+                if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { red_v[wid] = bv; red_i[wid] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int q = 1; q < (T >> 5); q++)
+                    if (red_v[q] < bv || (red_v[q] == bv && red_i[q] < bi)) { bv = red_v[q]; bi = red_i[q]; }
+                sh[0] = bi;
+            }
+            __syncthreads();
+            const int cur = sh[0];
+            if (cur == 0x7fffffff) break;                        // only non-finite costs left (cannot happen)
+            const double cpx = w.px[cur], cpy = w.py[cur], cvx = w.vx[cur], cvy = w.vy[cur], ccost = w.cost[cur];
+            const int citr = w.itr[cur];
+            if (d2d_norm2(cpx - tx, cpy - ty) <= 10.0) { goal = cur; success = true; break; }   // :160
+            __syncthreads();
+            if (tid == 0) { w.open_total[cur] = INFINITY; sh[2] -= 1; }     // open -> closed (:167-170)
+            __syncthreads();
+            // ---- expand in (x_acc, y_acc) loop order, T primitives at a time (:174-195)
+            for (int base = 0; base < nprim; base += T) {
+                const int pidx = base + tid;
+                bool ok = pidx < nprim;
+                double xa = 0, ya = 0, nvx = 0, nvy = 0;
+                if (ok) {
+                    xa = P.tab->u_space[pidx / nu];
+                    ya = P.tab->u_space[pidx - (pidx / nu) * nu];
+                    nvx = 1.0 * cvx + 4.0 * (xa / 2.0);
+                    nvy = 1.0 * cvy + 4.0 * (ya / 2.0);
+                    ok = d2d_norm2(nvx, nvy) < P.max_speed;      // :176
+                }
+                if (ok) {
+                    const double hx = xa / 2.0, hy = ya / 2.0;
+                    for (int sI = 0; sI < P.n_samp; sI++) {      // :180-185
+                        const double t = P.tab->t_samp[sI], t2 = P.tab->t_samp2[sI];
+                        const double qx = rint(D2D_FMA(t2, hx, 1.0 * cpx + t * cvx));
+                        const double qy = rint(D2D_FMA(t2, hy, 1.0 * cpy + t * cvy));
+                        if (!d2d_is_free(P, bel, qx, qy, t + (double)(citr * 2), trk, nact)) { ok = false; break; }
+                    }
+                }
+                double spx = 0, spy = 0, scost = 0;
+                int slot = -1, exist_idx = -1;
+                bool is_new = false;
+                if (ok) {
+                    spx = rint((1.0 * cpx + 2.0 * cvx) + 4.0 * (xa / 2.0));   // :188
+                    spy = rint((1.0 * cpy + 2.0 * cvy) + 4.0 * (ya / 2.0));
+                    scost = ccost + (xa * xa + ya * ya) / 100.0 + 10.0;      // :190
+                    bool existed;
+                    slot = d2d_hash_find_or_insert(w, d2d_node_key(spx, spy, nvx, nvy), &existed);
+                    if (existed) exist_idx = w.hvals[slot];
+                    else is_new = true;
+                }
+                // ordered slot assignment for the new nodes of this chunk (insertion order == primitive order)
+                const unsigned bal = __ballot_sync(0xffffffffu, is_new);
+                const int wrank = __popc(bal & ((1u << lane) - 1u));
+                if (lane == 0) wsum[wid] = __popc(bal);
+                __syncthreads();
+                int before = 0, tot_new = 0;
+                for (int q = 0; q < (T >> 5); q++) {
+                    if (q < wid) before += wsum[q];
+                    tot_new += wsum[q];
+                }
+                const int nn = sh[1];
+                int idx = -1;
+                if (is_new) { idx = nn + before + wrank; w.hvals[slot] = idx; }
+                else if (ok && exist_idx >= 0) {
+                    // in closed_set -> skip; in open_set -> replace if cheaper, keeping the dict slot (:197-206)
+                    if (w.open_total[exist_idx] != INFINITY && w.cost[exist_idx] > scost) idx = exist_idx;
+                }
+                if (idx >= 0 && idx < w.cap) {
+                    const double tot = d2d_node_total(scost, spx, spy, nvx, nvy, tx, ty);
+                    w.px[idx] = spx; w.py[idx] = spy; w.vx[idx] = nvx; w.vy[idx] = nvy; w.cost[idx] = scost;
+                    w.total[idx] = tot; w.open_total[idx] = tot; w.parent[idx] = cur; w.itr[idx] = citr + 1;
+                    w.act[idx] = pidx;
+                }
+                __syncthreads();
+                if (tid == 0) { sh[1] = nn + tot_new; sh[2] += tot_new; }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+        // ---- result: segments from the start outwards (the reference walks parents and reverses, :208-217)
+        if (tid == 0) {
+            atomicAdd(&P.stats[D2D_STAT_PLANS], 1ull);
+            if (success) {
+                int depth = 0;
+                for (int c2 = goal; c2 != 0; c2 = w.parent[c2]) depth++;
+                int seg = depth;
+                for (int c2 = goal; c2 != 0; c2 = w.parent[c2]) {
+                    seg--;
+                    const int par = w.parent[c2], pidx = w.act[c2];
+                    double *cf = P.traj_coeff + ((size_t)e * D2D_MAX_SEGMENTS + seg) * 6;
+                    cf[0] = w.px[par]; cf[1] = w.vx[par]; cf[2] = P.tab->u_space[pidx / nu] / 2.0;
+                    cf[3] = w.py[par]; cf[4] = w.vy[par]; cf[5] = P.tab->u_space[pidx - (pidx / nu) * nu] / 2.0;
+                }
+                P.traj_nseg[e] = depth; P.traj_cursor[e] = 0; P.plan_ok[e] = 1;
+            } else {
+                P.traj_nseg[e] = 0; P.traj_cursor[e] = 0; P.plan_ok[e] = 0;
+                atomicAdd(&P.stats[D2D_STAT_PLAN_FAILURES], 1ull);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ post kernel
+template <int E>
+__global__ void __launch_bounds__(256) d2d_step_post_kernel(const DevP P, const double *__restrict__ actions) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const BlockCtx c = d2d_carve(smem, E, 1, 1);
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int env0 = blockIdx.x * E;
+    if (tid == 0) { d2d_mbar_init(c.mbar, 1); c.misc[0] = 0; c.misc[1] = 0; }
+    __syncthreads();
+    if (tid < E) {
+        EnvS &s = c.S[tid];
+        const int e = env0 + tid;
+        s.valid = e < P.B;
+        s.reset = 0; s.coll_agent = 0; s.done_now = 0;
+        if (s.valid) {
+            s.px = P.drone_x[e]; s.py = P.drone_y[e]; s.yaw = P.drone_yaw[e];
+            s.vx = P.drone_vx[e]; s.vy = P.drone_vy[e]; s.tgx = P.target_x[e]; s.tgy = P.target_y[e];
+            s.steps = P.steps[e]; s.sm = P.state_machine[e]; s.fail = P.fail_count[e]; s.tcur = P.target_cursor[e];
+            s.bufc = P.buf_count[e]; s.bufts = P.buf_ts[e]; s.tracked = P.tracked_agent[e];
+            s.nseg = P.traj_nseg[e]; s.cursor = P.traj_cursor[e];
+            s.arch_cnt = 0; s.arch_ts = 0; s.newly = 0;      // already applied by the pre kernel
+            s.act_cnt = P.tmp_act_cnt[e]; s.act_ts = P.tmp_act_ts[e];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) d2d_issue_bulk(P, c, env0, E, true);
+    if (tid < E && c.S[tid].valid) {
+        const int e = env0 + tid;
+        const bool success = P.need_plan[e] ? (P.plan_ok[e] != 0) : true;
+        d2d_leader_finish(P, c.S[tid], nullptr, e, actions[e], success);
+    }
+    __syncthreads();
+    // Drone2D.is_collide, dynamic part (utils.py:773-776) against the drone's NEW position
+    for (int w = tid; w < E * P.N; w += T) {
+        const int i = w / P.N, k = w - i * P.N;
+        EnvS &s = c.S[i];
+        if (!s.valid) continue;
+        const size_t g = (size_t)(env0 + i) * P.NP + k;
+        const double2 pos = P.apos[g];
+        if (d2d_norm2(pos.x - s.px, pos.y - s.py) < P.arad[g] + P.drone_r) atomicOr(&s.coll_agent, 1);
+    }
+    d2d_mbar_wait(c.mbar, 0);
+    __syncthreads();
+    if (tid < E && c.S[tid].valid) {
+        EnvS &s = c.S[tid];
+        const int e = env0 + tid;
+        d2d_leader_flags(P, s, c.gt + (size_t)tid * D2D_GRID, e);
+        d2d_store_env_scalars(P, s, e);
+        if (s.done_now) c.misc[0] = 1;
+    }
+    if (tid == 0) {
+        int nv = 0;
+        for (int i = 0; i < E; i++) nv += c.S[i].valid;
+        atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], (unsigned long long)nv);
+        if (blockIdx.x == 0) P.plan_list[P.B] = 0;   // reset the compaction counter for the next step
+    }
+    __syncthreads();
+    d2d_phase_obs(P, c, env0, E, tid, T);
+    if (c.misc[0]) d2d_phase_done_stats(P, c, E, tid, T);
+}
+
+// ------------------------------------------------------------------------------------------ Oxford gaze policy
+// Oxford.plan (yaw_planner.py:81-127), one block per env.  np.sum over the 50x50 product array is reproduced in
+// NumPy's pairwise order: the host supplies the leaf blocks (offset, length <= 128) of the recursion for n = 2500 and
+// the post-order combine program; each leaf is summed by one thread with NumPy's 8-accumulator loop.
+#define D2D_OX_MAX_LEAVES 64
+struct OxProgram {
+    int n_leaves, n_ops;
+    int leaf_off[D2D_OX_MAX_LEAVES], leaf_len[D2D_OX_MAX_LEAVES];
+    int ops[2 * D2D_OX_MAX_LEAVES];     // post-order: >= 0 push leaf, -1 add top two
+};
+
+__device__ __forceinline__ double d2d_np_leaf_sum(const double *a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; i++) r += a[i];
+        return r;
+    }
+    double r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+        r0 += a[i]; r1 += a[i + 1]; r2 += a[i + 2]; r3 += a[i + 3];
+        r4 += a[i + 4]; r5 += a[i + 5]; r6 += a[i + 6]; r7 += a[i + 7];
+    }
+    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; i++) res += a[i];
+    return res;
+}
+
+__device__ __forceinline__ bool d2d_ox_visible(const DevP &P, int cell, double dx, double dy, double cs, double msn) {
+    const int i = cell / D2D_GRID, j = cell - i * D2D_GRID;
+    const double x = (double)i * P.scale, y = (double)j * P.scale;
+    const double ex = dx - x, ey = dy - y;
+    const double d2 = ex * ex + ey * ey;
+    if (d2 <= 0.0) return true;
+    const double cc = ((x - dx) * cs + (y - dy) * msn) / D2D_SQRT(d2);
+    // np.arccos(cc) <= view_angle  <=>  cc >= c*;  arccos(cc > 1) is NaN -> False (yaw_planner.py:78)
+    return cc >= P.ox_cos_thresh && cc <= 1.0 && d2 <= P.depth2;
+}
+
+__global__ void __launch_bounds__(256) d2d_oxford_kernel(const DevP P, const OxProgram *__restrict__ prog,
+                                                         double *__restrict__ actions_out) {
+    __shared__ double reward[D2D_CELLS];
+    __shared__ double prod[D2D_CELLS];
+    int *swep_i = (int *)prod;          // only needed while the reward map is built, before prod is used
+    __shared__ double leaf[D2D_OX_MAX_LEAVES];
+    __shared__ double score[D2D_MAX_YAW];
+    __shared__ double cs_s[D2D_MAX_YAW + 1], sn_s[D2D_MAX_YAW + 1];
+    const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    if (e >= P.B) return;
+    // an env that reported done and will be re-initialised by its next step is seen by the policy as freshly reset
+    // (the reference builds a new env + policy per episode, experiment.py:27-34)
+    const bool fresh = P.pending_reset[e] || (P.auto_reset && P.done[e]);
+    const double dx = fresh ? P.pose0[e] : P.drone_x[e], dy = fresh ? P.pose0[P.B + e] : P.drone_y[e];
+    const double yaw = fresh ? P.pose0[2 * P.B + e] : P.drone_yaw[e];
+    const int len = fresh ? 0 : P.traj_nseg[e] * P.n_way - P.traj_cursor[e], cursor = fresh ? 0 : P.traj_cursor[e];
+    for (int c = tid; c < D2D_CELLS; c += T) swep_i[c] = -1;
+    if (tid <= P.n_yaw) {
+        // candidate yaws: Drone2D(..., yaw_i) stores yaw_i % 360 (utils.py:718); entry n_yaw is the current pose
+        const double y = (tid < P.n_yaw) ? d2d_pymod(yaw + P.tab->v_yaw_space[tid] * P.dt, 360.0) : yaw;
+        double sn, cs;
+        d2d_sincos(y * D2D_DEG2RAD, &sn, &cs);
+        cs_s[tid] = cs; sn_s[tid] = -sn;    // vec_yaw = [cos, -sin] (yaw_planner.py:72)
+    }
+    __syncthreads();
+    // swep_map[cell] = i*dt with later waypoints overwriting earlier ones -> keep the largest i (:87-89)
+    double wx = 0, wy = 0;
+    for (int w = tid; w < len; w += T) {
+        double x, y;
+        d2d_waypoint_pos(P, e, cursor + w, x, y);
+        const int ci = d2d_cell(x, P.scale, P.inv_scale), cj = d2d_cell(y, P.scale, P.inv_scale);
+        if ((unsigned)ci < (unsigned)D2D_GRID && (unsigned)cj < (unsigned)D2D_GRID) atomicMax(&swep_i[ci * D2D_GRID + cj], w);
+    }
+    if (len > 0) d2d_waypoint_pos(P, e, cursor, wx, wy);
+    __syncthreads();
+    double *last = P.ox_last + (size_t)e * D2D_CELLS;
+    for (int c = tid; c < D2D_CELLS; c += T) {
+        const bool vis = d2d_ox_visible(P, c, dx, dy, cs_s[P.n_yaw], sn_s[P.n_yaw]);
+        const double lt = vis ? 0.0 : (fresh ? 5.0 : last[c]) + 1.0 * P.dt;   // :95-97 (init 5.0, :49)
+        last[c] = lt;
+        const double sw = swep_i[c] >= 0 ? (double)swep_i[c] * P.dt : 0.0;
+        double r;
+        if (sw > 0.0 && sw <= 3.0 && lt >= 0.5) r = 1000000.0;       // :108-110
+        else if (sw > 3.0 && lt >= 0.5) r = 1000.0;
+        else r = (lt > 1.0) ? 1.0 : lt;
+        reward[c] = r;
+    }
+    __syncthreads();
+    if (len == 0) {                                                  // :117-118
+        if (tid == 0) { actions_out[e] = 0.0; if (fresh) P.ox_fresh[e] = 1; }
+        return;
+    }
+    for (int k = 0; k < P.n_yaw; k++) {
+        for (int c = tid; c < D2D_CELLS; c += T)
+            prod[c] = d2d_ox_visible(P, c, wx, wy, cs_s[k], sn_s[k]) ? reward[c] : 0.0;
+        __syncthreads();
+        if (tid < prog->n_leaves) leaf[tid] = d2d_np_leaf_sum(prod + prog->leaf_off[tid], prog->leaf_len[tid]);
+        __syncthreads();
+        if (tid == 0) {
+            double st[16];
+            int sp = 0;
+            for (int o = 0; o < prog->n_ops; o++) {
+                const int op = prog->ops[o];
+                if (op >= 0) st[sp++] = leaf[op];
+                else { sp--; st[sp - 1] = st[sp - 1] + st[sp]; }
+            }
+            score[k] = 0.0 + st[0];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double max_reward = 0.0;
+        int best = 0;
+        for (int k = 0; k < P.n_yaw; k++)
+            if (max_reward < score[k]) { best = k; max_reward = score[k]; }   // strict <, first maximum (:123-125)
+        actions_out[e] = P.tab->v_yaw_space[best] / P.max_yaw_speed;
+    }
+}

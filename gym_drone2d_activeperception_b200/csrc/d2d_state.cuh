@@ -54,6 +54,8 @@ struct DevP {
     double *traj_coeff;          // [B][D2D_MAX_SEGMENTS][6]
     int *traj_nseg, *traj_cursor;  // remaining waypoints = nseg*n_way - cursor
     uint8_t *need_plan, *plan_ok, *replan;
+    int *tmp_act_cnt, *tmp_act_ts;   // still-active tracker totals, pre kernel -> post kernel
+    uint8_t *ox_fresh;           // Oxford state already re-initialised for a pending reset
     // Oxford
     double *ox_last;             // [B][2500]
     unsigned long long *stats;   // [D2D_NUM_STATS]

@@ -56,7 +56,7 @@ struct EnvS {
     int bufc, bufts, tracked;
     int valid, reset, ncull, coll_agent;
     int arch_cnt, arch_ts, act_cnt, act_ts, newly;
-    int done_now, nseg, cursor, ix, iy, pad;
+    int done_now, nseg, cursor, ix, iy, ox_fresh;
 };
 
 struct BlockCtx {
@@ -104,6 +104,8 @@ __device__ __forceinline__ void d2d_load_env_scalars(const DevP &P, EnvS &s, int
     if (!s.valid) return;
     const bool rs = P.pending_reset[e] || (P.auto_reset && P.done[e]);
     s.reset = rs;
+    s.ox_fresh = P.ox_fresh[e];
+    P.ox_fresh[e] = 0;
     if (rs) {   // Drone2DEnv2.__init__ (drone_v2.py:88-117): drone at init pose, zero velocity, WAIT_FOR_GOAL
         s.px = P.pose0[e]; s.py = P.pose0[P.B + e]; s.yaw = P.pose0[2 * P.B + e];
         s.vx = 0; s.vy = 0; s.tgx = s.px; s.tgy = s.py;   // Planner.__init__ traj_planner.py:22
@@ -159,7 +161,7 @@ __device__ __forceinline__ void d2d_reset_arrays(const DevP &P, const BlockCtx &
     if (P.ox_last) {
         for (int w = tid; w < E * D2D_CELLS; w += T) {
             const int i = w / D2D_CELLS, o = w - i * D2D_CELLS;
-            if (!c.S[i].valid || !c.S[i].reset) continue;
+            if (!c.S[i].valid || !c.S[i].reset || c.S[i].ox_fresh) continue;
             P.ox_last[(size_t)(env0 + i) * D2D_CELLS + o] = 5.0;   // yaw_planner.py:49
         }
     }

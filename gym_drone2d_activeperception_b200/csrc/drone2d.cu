@@ -34,6 +34,8 @@ struct d2d_handle {
     std::string err;
     size_t smem_step = 0, smem_post = 0;
     int plan_threads = 64;
+    OxProgram *ox_prog = nullptr;
+    size_t smem_pre = 0, smem_plan = 0;
 };
 
 static thread_local std::string g_create_err;
@@ -109,6 +111,7 @@ __global__ void d2d_reset_kernel(const DevP P, const uint8_t *__restrict__ mask)
         P.buf_count[e] = 0; P.buf_ts[e] = 0; P.tracked_agent[e] = 0;
         P.traj_nseg[e] = 0; P.traj_cursor[e] = 0; P.need_plan[e] = 0; P.plan_ok[e] = 1; P.replan[e] = 0;
         P.yaw_obs[e] = (float)yaw;
+        P.ox_fresh[e] = 0; P.tmp_act_cnt[e] = 0; P.tmp_act_ts[e] = 0;
     }
 }
 
@@ -116,6 +119,25 @@ __global__ void d2d_set_pose_kernel(const DevP P, const double *__restrict__ pos
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= P.B) return;
     P.drone_x[e] = pose[3 * e]; P.drone_y[e] = pose[3 * e + 1]; P.drone_yaw[e] = pose[3 * e + 2];
+}
+
+// NumPy pairwise-sum recursion for a contiguous run of n doubles -> leaf blocks + post-order combine program
+static void ox_rec(OxProgram *p, int off, int n) {
+    if (n <= 128) {
+        const int id = p->n_leaves++;
+        p->leaf_off[id] = off; p->leaf_len[id] = n;
+        p->ops[p->n_ops++] = id;
+        return;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    ox_rec(p, off, n2);
+    ox_rec(p, off + n2, n - n2);
+    p->ops[p->n_ops++] = -1;
+}
+static void build_ox_program(OxProgram *p, int n) {
+    memset(p, 0, sizeof(*p));
+    ox_rec(p, 0, n);
 }
 
 // ------------------------------------------------------------------------------------------ create / destroy
@@ -204,6 +226,10 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     size_t o_need = add_buf(h, cur, "need_plan", D2D_U8, 1, SHP(B), SHP(1), sB);
     size_t o_pok = add_buf(h, cur, "plan_ok", D2D_U8, 1, SHP(B), SHP(1), sB);
     size_t o_rep = add_buf(h, cur, "replan", D2D_U8, 1, SHP(B), SHP(1), sB);
+    size_t o_tac = add_buf(h, cur, "tmp_active_count", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_tat = add_buf(h, cur, "tmp_active_ts", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_oxf = add_buf(h, cur, "oxford_fresh", D2D_U8, 1, SHP(B), SHP(1), sB);
+    size_t o_oxp = add_buf(h, cur, "oxford_program", D2D_U8, 1, SHP((int64_t)sizeof(OxProgram)), SHP(1), sizeof(OxProgram));
     size_t o_ox = add_buf(h, cur, "oxford_last_time_observed", D2D_F64, 3, SHP(B, D2D_GRID, D2D_GRID),
                           SHP(D2D_CELLS, D2D_GRID, 1), cfg->oxford ? (size_t)sB * D2D_CELLS : 16);
     size_t o_stats = add_buf(h, cur, "stats", D2D_I64, 1, SHP(D2D_NUM_STATS), SHP(1), D2D_NUM_STATS);
@@ -257,6 +283,8 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.traj_coeff = (double *)(A + o_coef); P.traj_nseg = (int *)(A + o_nseg); P.traj_cursor = (int *)(A + o_curs);
     P.need_plan = A + o_need; P.plan_ok = A + o_pok; P.replan = A + o_rep;
     P.ox_last = cfg->oxford ? (double *)(A + o_ox) : nullptr;
+    P.tmp_act_cnt = (int *)(A + o_tac); P.tmp_act_ts = (int *)(A + o_tat); P.ox_fresh = A + o_oxf;
+    h->ox_prog = (OxProgram *)(A + o_oxp);
     P.stats = (unsigned long long *)(A + o_stats);
     P.tab = (const DevTables *)(A + o_tab);
     P.plan_ws = cfg->planner == D2D_PLANNER_PRIMITIVE ? (A + o_plan_ws) : nullptr;
@@ -273,6 +301,18 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     ce = cudaMemcpy(A + o_tab, &tab, sizeof(tab), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { g_create_err = std::string("cudaMemcpy tables: ") + cudaGetErrorString(ce); cudaFree(h->arena); delete h; return D2D_ERR_CUDA; }
 
+    {
+        OxProgram prog;
+        build_ox_program(&prog, D2D_CELLS);
+        ce = cudaMemcpy(A + o_oxp, &prog, sizeof(prog), cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) { g_create_err = std::string("cudaMemcpy oxford program: ") + cudaGetErrorString(ce); cudaFree(h->arena); delete h; return D2D_ERR_CUDA; }
+    }
+    h->smem_pre = d2d_pre_smem_bytes(E, NP, h->HW);
+    h->smem_plan = D2D_BELIEF_STRIDE + (size_t)NP * 5 * 8 + 4 * 8 + 4 * 4 + 8 * 4 + 4 * 4 + 64;
+    if (cfg->planner == D2D_PLANNER_PRIMITIVE && h->smem_pre > 227 * 1024) {
+        g_create_err = "shared memory per block exceeds 227 KB (Primitive path; lower envs_per_block)";
+        cudaFree(h->arena); delete h; return D2D_ERR_INVALID;
+    }
     h->smem_step = d2d_step_smem_bytes(E, NP, h->HW);
     if (h->smem_step > 227 * 1024) {
         g_create_err = "shared memory per block exceeds 227 KB (too many agents per env for this envs_per_block)";

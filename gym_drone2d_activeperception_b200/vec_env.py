@@ -285,3 +285,36 @@ class Drone2DVecEnv(object):
             self.close()
         except Exception:
             pass
+
+
+def trajectory_waypoints(cfg, coeff, nseg, cursor):
+    """Host-side expansion of one env's stored A* segments into the reference's waypoint lists
+    (Trajectory2D.positions / .velocities, traj_planner.py:208-217) from `cursor` on.
+    coeff: [D2D_MAX_SEGMENTS, 6] array, nseg / cursor ints.  Returns (positions [L,2], velocities [L,2])."""
+    import ctypes as _C  # noqa: F401
+    n_way = cfg.n_way
+    pos, vel = [], []
+    for a in range(int(cursor), int(nseg) * n_way):
+        seg, ws = divmod(a, n_way)
+        ti = n_way - 1 - ws
+        t, t2, tt = cfg.t_way[ti], cfg.t_way2[ti], cfg.t_way_x2[ti]
+        c = coeff[seg]
+        # np.array([1, t, t**2]) @ coeff.T on the reference image == fma(t2, h, p + t*v); np.around
+        px = np.rint(_fma(t2, c[2], c[0] + t * c[1]))
+        py = np.rint(_fma(t2, c[5], c[3] + t * c[4]))
+        pos.append((px, py))
+        vel.append((c[1] + tt * c[2], c[4] + tt * c[5]))
+    return np.array(pos, dtype=np.float64).reshape(-1, 2), np.array(vel, dtype=np.float64).reshape(-1, 2)
+
+
+_libm = None
+
+
+def _fma(a, b, c):
+    global _libm
+    if _libm is None:
+        import ctypes.util
+        _libm = C.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        _libm.fma.restype = C.c_double
+        _libm.fma.argtypes = [C.c_double] * 3
+    return _libm.fma(float(a), float(b), float(c))

@@ -1,0 +1,116 @@
+"""Parity of the Primitive planner path (replan check, A*, brake / step_pos) and the Oxford gaze kernel."""
+import numpy as np
+import pytest
+
+import util
+from test_gpu_parity import _env, _host, _cmp_env_to_oracle, RTOL
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _traj(env, h, i):
+    from gym_drone2d_activeperception_b200.vec_env import trajectory_waypoints
+    coeff = env.buffer("traj_coeff")[i].cpu().numpy()
+    return trajectory_waypoints(env.cfg, coeff, h["traj_nseg"][i], h["traj_cursor"][i])
+
+
+@pytest.mark.parametrize("path", util.golden_files("episode_"), ids=lambda p: p.split("/")[-1][:-4])
+def test_cuda_matches_reference_golden_episode(path):
+    """Whole episodes of the reference (Primitive + Kalman trackers + Oxford): actions chosen on the device must equal
+    the reference's, and every recorded field must match step by step."""
+    g = util.load_golden(path)
+    p = util.params_from_golden(g)
+    n = int(g["n_agents"])
+    B = 3
+    env = _env(p, B, util.world_from_golden(g, B), auto_reset=False, oxford=True)
+    T = len(g["done"])
+    plan_i = 0
+    for t in range(T):
+        a = env.plan_oxford()
+        torch.cuda.synchronize()
+        ah = a.cpu().numpy()
+        assert ah[0] == g["action"][t] and ah[B - 1] == g["action"][t], ("oxford action", t, ah, g["action"][t])
+        ox = env.buffer("oxford_last_time_observed").cpu().numpy()
+        assert np.array_equal(ox[0], g["ox_last"][t]), ("oxford last_time_observed_map", t)
+        env.step(a)
+        h = _host(env)
+        for i in (0, B - 1):
+            assert np.array_equal(h["belief"][i], g["belief"][t]), ("belief", t)
+            assert np.array_equal(h["hit"][i, :n], g["hit"][t]), ("hit", t)
+            assert h["collision_flag"][i] == g["collision"][t] and bool(h["done"][i]) == bool(g["done"][t]), ("done", t)
+            assert h["dead_lock_flag"][i] == g["dead_lock"][t] and h["freezing_flag"][i] == g["freezing"][t]
+            assert h["state_machine"][i] == g["state_machine"][t] and h["fail_count"][i] == g["fail_count"][t], ("sm", t)
+            assert np.array_equal(h["local_map"][i, 0], g["local_map"][t]), ("local_map", t)
+            assert h["yaw_angle"][i, 0] == g["yaw_obs"][t]
+            assert util.rel_err([h["drone_x"][i], h["drone_y"][i], h["drone_yaw"][i]], g["drone"][t]) <= RTOL, ("drone", t)
+            assert util.rel_err([h["drone_vx"][i], h["drone_vy"][i]], g["drone_vel"][t]) <= RTOL, ("vel", t)
+            assert h["traj_nseg"][i] * 20 - h["traj_cursor"][i] == g["traj_len"][t], ("traj_len", t)
+            assert bool(h["replan"][i]) == bool(g["replan"][t]) and bool(h["plan_ok"][i]) == bool(g["plan_ok"][t]), ("plan", t)
+            act = g["trk_active"][t]
+            assert np.array_equal(h["tracker_active"][i, :n].astype(bool), act), ("trk_active", t)
+            if act.any():
+                assert util.rel_err(h["tracker_mu"][i, :n][act], g["trk_mu"][t][act]) <= RTOL
+            assert (h["tracker_buffer_count"][i], h["tracker_buffer_ts"][i]) == (g["buf_count"][t], g["buf_ts"][t])
+        if g["planned"][t] and g["plan_ok"][t]:
+            pos, vel = _traj(env, h, 0)
+            assert np.array_equal(pos, g["plan%d_pos" % plan_i][1:]), ("plan positions", t)
+            assert util.rel_err(vel, g["plan%d_vel" % plan_i][1:]) <= RTOL, ("plan velocities", t)
+            plan_i += 1
+    assert plan_i == len(g["plan_steps"])
+    st = env.stats()
+    assert st[1] == B                                    # every copy finished exactly one episode
+    env.close()
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(static_map="maps/empty_map.npy", agent_number=10, agent_radius=15, agent_max_speed=20, drone_max_speed=40, B=24, steps=260),
+    dict(static_map="maps/obstacle_map.npy", agent_number=10, agent_radius=10, agent_max_speed=20, drone_max_speed=40, B=16, steps=200),
+    dict(static_map="maps/empty_map.npy", agent_number=30, agent_radius=10, agent_max_speed=40, drone_max_speed=20, B=12, steps=200),
+], ids=["cfg1_like", "cfg4_obstacle", "speed20_crowded"])
+def test_cuda_matches_oracle_primitive_oxford_with_auto_reset(cfg):
+    """Seeded batch, Primitive planner + Oxford policy on the device vs the oracle, with auto-reset: when an episode
+    ends the oracle env and its policy state are rebuilt from the same world (what the reference's reset() does)."""
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200.world import generate_worlds
+    B, steps = cfg["B"], cfg["steps"]
+    p = Params(debug=False, planner="Primitive", gaze_method="Oxford", map_id=500, static_map=cfg["static_map"],
+               agent_number=cfg["agent_number"], agent_radius=cfg["agent_radius"], agent_max_speed=cfg["agent_max_speed"],
+               drone_max_speed=cfg["drone_max_speed"])
+    worlds = generate_worlds(p, 500 + np.arange(B))
+    env = _env(p, B, worlds, auto_reset=True, oxford=True, envs_per_block=4)
+    n = env.num_agents
+    oracles = [util.oracle_env_from_world(p, worlds, i) for i in range(B)]
+    episodes = 0
+    for t in range(steps):
+        a = env.plan_oxford()
+        acts = np.zeros(B)
+        for i in range(B):
+            if oracles[i].c.done:
+                oracles[i].close()
+                oracles[i] = util.oracle_env_from_world(p, worlds, i)
+                episodes += 1
+            acts[i] = oracles[i].oxford_plan()
+        torch.cuda.synchronize()
+        ah = a.cpu().numpy()
+        assert np.array_equal(ah, acts), ("oxford actions", t, np.nonzero(ah != acts))
+        env.step(a)
+        for i in range(B):
+            oracles[i].step(acts[i])
+        h = _host(env)
+        ox = env.buffer("oxford_last_time_observed").cpu().numpy()
+        for i, e in enumerate(oracles):
+            _cmp_env_to_oracle(h, i, e, n, t, "primitive")
+            assert h["traj_nseg"][i] * 20 - h["traj_cursor"][i] == e.c.traj_len, ("traj_len", t, i)
+            assert bool(h["replan"][i]) == bool(e.c.replan) and bool(h["plan_ok"][i]) == bool(e.c.plan_ok), ("plan", t, i)
+            assert np.array_equal(ox[i], e.ox_last), ("ox_last", t, i)
+            if e.c.planned and e.c.plan_ok:
+                pos, vel = _traj(env, h, i)
+                opos, ovel = e.trajectory()
+                assert np.array_equal(pos, opos) and util.rel_err(vel, ovel) <= RTOL, ("trajectory", t, i)
+    assert episodes > 0
+    st = env.stats()
+    assert st[11] > 0 and st[1] >= episodes
+    for e in oracles:
+        e.close()
+    env.close()
