@@ -508,32 +508,27 @@ __device__ __forceinline__ void d2d_phase_obs(const DevP &P, const BlockCtx &c, 
     const int words = E * D2D_LOCAL_CELLS / 4;
     for (int w = tid; w < words; w += T) {
         const int o = w * 4;
-        int i = o / D2D_LOCAL_CELLS;
-        const int r = o - i * D2D_LOCAL_CELLS;
-        int u = r / D2D_LOCAL, vv = r - u * D2D_LOCAL;
-        int bi = c.S[i].ix - 16, bj = c.S[i].iy - 16;
-        bool valid = c.S[i].valid != 0;
-        const uint8_t *bel = c.belief + (size_t)i * D2D_BELIEF_STRIDE;
+        const int i0 = o / D2D_LOCAL_CELLS;
+        const int r = o - i0 * D2D_LOCAL_CELLS;
+        const int u0 = r / D2D_LOCAL, v0 = r - u0 * D2D_LOCAL;
         uint32_t v = 0;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            const int gi = bi + u, gj = bj + vv;
-            uint32_t cellv = 0;
-            if (valid && (unsigned)gi < (unsigned)D2D_GRID && (unsigned)gj < (unsigned)D2D_GRID)
-                cellv = bel[gi * D2D_GRID + gj];
-            v |= cellv << (8 * b);
-            if (++vv == D2D_LOCAL) {
-                vv = 0;
-                if (++u == D2D_LOCAL) {   // next env of the block
-                    u = 0;
-                    if (++i < E) {
-                        bi = c.S[i].ix - 16; bj = c.S[i].iy - 16; valid = c.S[i].valid != 0;
-                        bel = c.belief + (size_t)i * D2D_BELIEF_STRIDE;
-                    } else {
-                        valid = false;
-                    }
-                }
+            // byte b of the word: (env, row, col) derived independently (a word may straddle a row or an env)
+            int vb = v0 + b, ub = u0, ib = i0;
+            if (vb >= D2D_LOCAL) {
+                vb -= D2D_LOCAL;
+                ub += 1;
+                if (ub >= D2D_LOCAL) { ub = 0; ib += 1; }
             }
+            uint32_t cellv = 0;
+            if (ib < E) {
+                const EnvS &s = c.S[ib];
+                const int gi = s.ix - 16 + ub, gj = s.iy - 16 + vb;
+                if (s.valid && (unsigned)gi < (unsigned)D2D_GRID && (unsigned)gj < (unsigned)D2D_GRID)
+                    cellv = c.belief[(size_t)ib * D2D_BELIEF_STRIDE + gi * D2D_GRID + gj];
+            }
+            v |= cellv << (8 * b);
         }
         out[w] = v;
     }

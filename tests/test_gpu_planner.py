@@ -64,9 +64,9 @@ def test_cuda_matches_reference_golden_episode(path):
 
 
 @pytest.mark.parametrize("cfg", [
-    dict(static_map="maps/empty_map.npy", agent_number=10, agent_radius=15, agent_max_speed=20, drone_max_speed=40, B=24, steps=260),
-    dict(static_map="maps/obstacle_map.npy", agent_number=10, agent_radius=10, agent_max_speed=20, drone_max_speed=40, B=16, steps=200),
-    dict(static_map="maps/empty_map.npy", agent_number=30, agent_radius=10, agent_max_speed=40, drone_max_speed=20, B=12, steps=200),
+    dict(static_map="maps/empty_map.npy", agent_number=10, agent_radius=15, agent_max_speed=20, drone_max_speed=40, B=23, steps=260),
+    dict(static_map="maps/obstacle_map.npy", agent_number=10, agent_radius=10, agent_max_speed=20, drone_max_speed=40, B=14, steps=200),
+    dict(static_map="maps/empty_map.npy", agent_number=30, agent_radius=10, agent_max_speed=40, drone_max_speed=20, B=9, steps=200),
 ], ids=["cfg1_like", "cfg4_obstacle", "speed20_crowded"])
 def test_cuda_matches_oracle_primitive_oxford_with_auto_reset(cfg):
     """Seeded batch, Primitive planner + Oxford policy on the device vs the oracle, with auto-reset: when an episode
