@@ -205,8 +205,17 @@ def main():
     ap.add_argument("--unique-worlds", type=int, default=0, help="cap distinct generated worlds (0 = all unique up to 8192)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps (reported in config)")
+    ap.add_argument("--planner", default=None, choices=["NoMove", "Primitive"], help="override the config's planner")
+    ap.add_argument("--gaze", default="scripted", choices=["scripted", "Oxford"],
+                    help="scripted: random actions from the Oxford action set; Oxford: d2d_plan_oxford every step")
     args = ap.parse_args()
-    cfg = CONFIGS[args.config]
+    cfg = dict(CONFIGS[args.config])
+    if args.planner:
+        cfg["params"] = dict(cfg["params"], planner=args.planner)
+        cfg["name"] += " [planner=%s]" % args.planner
+    if args.gaze == "Oxford":
+        cfg["params"] = dict(cfg["params"], gaze_method="Oxford")
+        cfg["name"] += " [gaze=Oxford on device]"
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
@@ -235,8 +244,16 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     p = Params(debug=False, **pk)
-    env = Drone2DVecEnv(p, B, seeds=seeds, worlds=worlds, device=dev, auto_reset=True, trackers=True,
+    use_ox = args.gaze == "Oxford"
+    env = Drone2DVecEnv(p, B, seeds=seeds, worlds=worlds, device=dev, auto_reset=True, trackers=True, oxford=use_ox,
                         envs_per_block=args.envs_per_block)
+    ox_out = torch.empty(B, dtype=torch.float64, device=dev)
+
+    def do_step(a):
+        if use_ox:
+            env.step(env.plan_oxford(ox_out))
+        else:
+            env.step(a)
     N = env.num_agents
     K, W = args.steps, args.warmup
     table = torch.as_tensor(np.arange(-80, 80, 80 / 3) / 80, device=dev)
@@ -252,7 +269,7 @@ def main():
 
     # ---- device-resident timing: per-step CUDA events on the launch stream, L2 flushed (untimed) between steps
     for t in range(W):
-        env.step(actions[t])
+        do_step(actions[t])
     barrier()
     sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
                            int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
@@ -265,7 +282,7 @@ def main():
         if flush is not None:
             flush.fill_(t & 0xFF)
         ev0[t].record()
-        env.step(actions[W + t])
+        do_step(actions[W + t])
         ev1[t].record()
     barrier()
     wall = time.perf_counter() - wall0
@@ -317,7 +334,7 @@ def main():
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["name"], "envs_per_gpu": B, "agents_per_env": N, "rays_per_env_step": N_RAYS,
-                       "planner": pk["planner"], "trackers": True, "auto_reset": True,
+                       "planner": cfg["params"]["planner"], "gaze": args.gaze, "trackers": True, "auto_reset": True,
                        "unique_worlds_per_gpu": int(unique), "world_gen_s": round(t_world, 2),
                        "l2": "no flush (state stays L2-resident)" if flush is None else
                              "flushed between timed steps (256 MiB fill, untimed; per-step CUDA events summed)",
@@ -333,8 +350,9 @@ def main():
                          "step_ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())]},
             "wall_s_timed_region": wall,
             "episode_stats": {n: int(v) for n, v in zip(
-                ["env_steps", "episodes", "success", "static_collision", "dynamic_collision", "freezing", "dead_lock"],
-                stats.tolist()[:7])},
+                ["env_steps", "episodes", "success", "static_collision", "dynamic_collision", "freezing", "dead_lock",
+                 "flight_steps", "grid_discovered", "agents_tracked", "tracked_steps", "plans", "plan_failures", "replans"],
+                stats.tolist()[:14])},
         }
         if not args.no_cpu_baseline and world == 1:
             import oracle
