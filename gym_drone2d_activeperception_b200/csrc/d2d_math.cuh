@@ -47,9 +47,15 @@ D2D_HD int d2d_cell(double x, double scale, double inv_scale) {
     return k;
 }
 
-// Python `x % w` for w > 0 (float_rem): fmod then sign fix-up.
+// Python `x % w` for w > 0 (float_rem): fmod then sign fix-up.  fmod is exact, and for |x| < 2w it is |x| or |x| - w
+// (an exact subtraction, Sterbenz), so the library fmod is only needed outside that range.
+D2D_HD double d2d_fmod_pos(double ax, double w) {   // fmod(ax, w) for ax >= 0, w > 0
+    if (ax < w) return ax;
+    if (ax < 2.0 * w) return ax - w;
+    return fmod(ax, w);
+}
 D2D_HD double d2d_pymod(double x, double w) {
-    double m = fmod(x, w);
+    double m = (x < 0) ? -d2d_fmod_pos(-x, w) : d2d_fmod_pos(x, w);
     if (m != 0.0) {
         if (m < 0) m += w;
     } else {
@@ -113,12 +119,15 @@ D2D_HD d2d_dd dd_mul_d(d2d_dd a, double b) {
     p.l += a.l * b;
     return dd_fast_two_sum(p.h, p.l);
 }
+// a / b to ~2^-100: one IEEE division for the reciprocal, then long division with multiplications (each correction
+// term only needs ~2^-50 relative accuracy because it is 2^-52 of the result).
 D2D_HD d2d_dd dd_div(d2d_dd a, d2d_dd b) {
-    double q1 = a.h / b.h;
+    const double inv = 1.0 / b.h;
+    const double q1 = a.h * inv;
     d2d_dd r = dd_add(a, dd_neg(dd_mul_d(b, q1)));
-    double q2 = r.h / b.h;
+    const double q2 = r.h * inv;
     r = dd_add(r, dd_neg(dd_mul_d(b, q2)));
-    double q3 = r.h / b.h;
+    const double q3 = r.h * inv;
     d2d_dd q = dd_fast_two_sum(q1, q2);
     return dd_add_d(q, q3);
 }
@@ -184,25 +193,19 @@ D2D_HD double d2d_tan(double a) {
     if (j > 25) j = 25;
     d2d_dd d = dd_add_d(r, -(double)j * 0.03125);
     d2d_dd t = d2d_tan_small(d);
-    d2d_dd num, den;
-    if (j == 0) {
-        num = t;
-        den.h = 1.0;
-        den.l = 0.0;
-    } else {
-        d2d_dd T;
-        T.h = D2D_TAN_TAB[j][0];
-        T.l = D2D_TAN_TAB[j][1];
-        num = dd_add(T, t);
-        den = dd_add_d(dd_neg(dd_mul(T, t)), 1.0);
-    }
-    d2d_dd res;
-    if (quad & 1) {
-        res = dd_div(den, num);   // tan(r + pi/2) = -1/tan(r)
-        res = dd_neg(res);
-    } else {
-        res = dd_div(num, den);
-    }
+    // branch-free: every lane of a warp runs the same instruction stream (tan(0) = 0 makes j == 0 a no-op), and the
+    // quadrant only swaps the operands of the single double-double division: tan(r + pi/2) = -1/tan(r)
+    d2d_dd T;
+    T.h = D2D_TAN_TAB[j][0];
+    T.l = D2D_TAN_TAB[j][1];
+    d2d_dd num = dd_add(T, t);
+    d2d_dd den = dd_add_d(dd_neg(dd_mul(T, t)), 1.0);
+    const bool odd = (quad & 1) != 0;
+    d2d_dd a_, b_;
+    a_.h = odd ? den.h : num.h; a_.l = odd ? den.l : num.l;
+    b_.h = odd ? num.h : den.h; b_.l = odd ? num.l : den.l;
+    d2d_dd res = dd_div(a_, b_);
+    if (odd) res = dd_neg(res);
     double v = res.h + res.l;
     return neg ? -v : v;
 }

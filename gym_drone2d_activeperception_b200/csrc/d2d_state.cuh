@@ -27,7 +27,9 @@ struct DevP {
     int B, N, NP, HW;            // envs, agents, padded agents, hit words per env
     int n_rays, planner, trackers, auto_reset, n_targets;
     int n_u, n_samp, n_way, n_yaw;
+    int m_far;                   // first ray sample index at which the view-depth test can fire
     double dt, scale, inv_scale, map_w, map_h, agent_radius, max_acc, drone_r, max_yaw_speed;
+    double ray_a0, ray_da;       // -FOV/2 and FOV/n_rays (utils.py:594)
     double depth2, fov, max_steps, var_cam, max_speed, cull_reach, ox_cos_thresh;
     double targets[D2D_MAX_TARGETS][2];
     // agents [B][NP] (env-major)
@@ -56,6 +58,7 @@ struct DevP {
     uint8_t *need_plan, *plan_ok, *replan;
     int *tmp_act_cnt, *tmp_act_ts;   // still-active tracker totals, pre kernel -> post kernel
     uint8_t *ox_fresh;           // Oxford state already re-initialised for a pending reset
+    int *obs_ix, *obs_iy;        // drone cell for which the local_map tensor content is currently valid
     // Oxford
     double *ox_last;             // [B][2500]
     unsigned long long *stats;   // [D2D_NUM_STATS]

@@ -98,28 +98,40 @@ __device__ __forceinline__ BlockCtx d2d_carve(unsigned char *base, int E, int NP
 
 // ------------------------------------------------------------------------------------------ P0: scalars + bulk loads
 __device__ __forceinline__ void d2d_load_env_scalars(const DevP &P, EnvS &s, int e) {
-    s.valid = e < P.B;
-    s.ncull = 0; s.coll_agent = 0; s.arch_cnt = 0; s.arch_ts = 0; s.act_cnt = 0; s.act_ts = 0; s.newly = 0;
-    s.done_now = 0; s.reset = 0;
-    if (!s.valid) return;
-    const bool rs = P.pending_reset[e] || (P.auto_reset && P.done[e]);
-    s.reset = rs;
-    s.ox_fresh = P.ox_fresh[e];
-    P.ox_fresh[e] = 0;
-    if (rs) {   // Drone2DEnv2.__init__ (drone_v2.py:88-117): drone at init pose, zero velocity, WAIT_FOR_GOAL
-        s.px = P.pose0[e]; s.py = P.pose0[P.B + e]; s.yaw = P.pose0[2 * P.B + e];
-        s.vx = 0; s.vy = 0; s.tgx = s.px; s.tgy = s.py;   // Planner.__init__ traj_planner.py:22
-        s.steps = 0; s.sm = SM_WAIT_FOR_GOAL; s.fail = 0; s.tcur = 0;
-        s.bufc = 0; s.bufts = 0; s.tracked = 0; s.nseg = 0; s.cursor = 0;
-        P.pending_reset[e] = 0;
-    } else {
-        s.px = P.drone_x[e]; s.py = P.drone_y[e]; s.yaw = P.drone_yaw[e];
-        s.vx = P.drone_vx[e]; s.vy = P.drone_vy[e]; s.tgx = P.target_x[e]; s.tgy = P.target_y[e];
-        s.steps = P.steps[e]; s.sm = P.state_machine[e]; s.fail = P.fail_count[e]; s.tcur = P.target_cursor[e];
-        s.bufc = P.buf_count[e]; s.bufts = P.buf_ts[e]; s.tracked = P.tracked_agent[e];
-        s.nseg = P.traj_nseg[e]; s.cursor = P.traj_cursor[e];
+    // All global loads are issued into registers BEFORE anything is written to shared memory: the compiler cannot
+    // prove that the EnvS reference does not alias the global arrays, so interleaved load/store pairs would
+    // serialise ~20 DRAM round trips.
+    if (e >= P.B) {
+        s.valid = 0; s.reset = 0; s.done_now = 0; s.ncull = 0; s.coll_agent = 0;
+        return;
     }
-    s.ix = d2d_cell(s.px, P.scale, P.inv_scale); s.iy = d2d_cell(s.py, P.scale, P.inv_scale);
+    const bool pend = P.pending_reset[e] != 0, was_done = P.done[e] != 0;
+    const int oxf = P.ox_fresh[e];
+    const double p0x = P.pose0[e], p0y = P.pose0[P.B + e], p0yaw = P.pose0[2 * P.B + e];
+    const double gx = P.drone_x[e], gy = P.drone_y[e], gyaw = P.drone_yaw[e], gvx = P.drone_vx[e], gvy = P.drone_vy[e];
+    const double gtx = P.target_x[e], gty = P.target_y[e];
+    const int gsteps = P.steps[e], gsm = P.state_machine[e], gfail = P.fail_count[e], gtcur = P.target_cursor[e];
+    const int gbufc = P.buf_count[e], gbufts = P.buf_ts[e], gtracked = P.tracked_agent[e];
+    const int gnseg = P.traj_nseg[e], gcursor = P.traj_cursor[e];
+    const bool rs = pend || (P.auto_reset && was_done);
+    double px, py, yaw, vx, vy, tgx, tgy;
+    int steps, sm, fail, tcur, bufc, bufts, tracked, nseg, cursor;
+    if (rs) {   // Drone2DEnv2.__init__ (drone_v2.py:88-117): drone at init pose, zero velocity, WAIT_FOR_GOAL
+        px = p0x; py = p0y; yaw = p0yaw; vx = 0; vy = 0; tgx = p0x; tgy = p0y;   // Planner.__init__ traj_planner.py:22
+        steps = 0; sm = SM_WAIT_FOR_GOAL; fail = 0; tcur = 0; bufc = 0; bufts = 0; tracked = 0; nseg = 0; cursor = 0;
+    } else {
+        px = gx; py = gy; yaw = gyaw; vx = gvx; vy = gvy; tgx = gtx; tgy = gty;
+        steps = gsteps; sm = gsm; fail = gfail; tcur = gtcur; bufc = gbufc; bufts = gbufts; tracked = gtracked;
+        nseg = gnseg; cursor = gcursor;
+    }
+    const int ix = d2d_cell(px, P.scale, P.inv_scale), iy = d2d_cell(py, P.scale, P.inv_scale);
+    s.valid = 1; s.reset = rs; s.ox_fresh = oxf;
+    s.ncull = 0; s.coll_agent = 0; s.arch_cnt = 0; s.arch_ts = 0; s.act_cnt = 0; s.act_ts = 0; s.newly = 0; s.done_now = 0;
+    s.px = px; s.py = py; s.yaw = yaw; s.vx = vx; s.vy = vy; s.tgx = tgx; s.tgy = tgy;
+    s.steps = steps; s.sm = sm; s.fail = fail; s.tcur = tcur; s.bufc = bufc; s.bufts = bufts; s.tracked = tracked;
+    s.nseg = nseg; s.cursor = cursor; s.ix = ix; s.iy = iy;
+    if (pend) P.pending_reset[e] = 0;
+    if (oxf) P.ox_fresh[e] = 0;
 }
 
 __device__ __forceinline__ void d2d_store_env_scalars(const DevP &P, const EnvS &s, int e) {
@@ -217,25 +229,39 @@ __device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &
 }
 
 // ------------------------------------------------------------------------------------------ P2: Raycast.castRay
-__device__ __forceinline__ void d2d_mark(uint8_t *bel_s, uint8_t *bel_g, int cell, uint8_t v) {
-    if (bel_s[cell] != v) {   // monotone + idempotent: every writer of a cell writes the same value
-        bel_s[cell] = v;
-        bel_g[cell] = v;
+struct RayOut {
+    uint8_t *bel_s, *bel_g;   // belief grid in shared memory / HBM
+    uint8_t *obs;             // env's local_map slice when it can be patched in place (window unchanged), else null
+    int wi, wj;               // window origin cell (ix-16, iy-16)
+};
+
+__device__ __forceinline__ void d2d_mark(const RayOut &o, int ci, int cj, uint8_t v) {
+    const int cell = ci * D2D_GRID + cj;
+    if (o.bel_s[cell] != v) {   // monotone + idempotent: every writer of a cell writes the same value
+        o.bel_s[cell] = v;
+        o.bel_g[cell] = v;
+        if (o.obs) {            // the cell is always inside the 33x33 window (view reach < 16 cells)
+            const int u = ci - o.wi, w = cj - o.wj;
+            if ((unsigned)u < (unsigned)D2D_LOCAL && (unsigned)w < (unsigned)D2D_LOCAL) o.obs[u * D2D_LOCAL + w] = v;
+        }
     }
 }
 
-__device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, int ray, uint8_t *bel_s, uint8_t *bel_g,
+// wrapped ray angle, utils.py:594, 626, 612-618
+__device__ __forceinline__ double d2d_ray_angle(const DevP &P, double yaw, int ray) {
+    const double ray_angle = P.ray_a0 + P.ray_da * (double)ray;
+    const double player_angle = D2D_TWO_PI - yaw * D2D_DEG2RAD;
+    double a = player_angle + ray_angle;
+    a = copysign(d2d_pymod(fabs(a), D2D_TWO_PI), a);
+    if (a < 0) a += D2D_TWO_PI;
+    return a;
+}
+
+__device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, double a, double slope, const RayOut &o,
                                              const uint64_t *gt, const double *sx, const double *sy, const double *sr2,
                                              const uint16_t *cull, uint32_t *hitw) {
-    const double fov = P.fov;
-    const double ray_angle = -fov / 2 + fov / (double)P.n_rays * (double)ray;   // utils.py:594
-    const double player_angle = D2D_TWO_PI - s.yaw * D2D_DEG2RAD;
-    double a = player_angle + ray_angle;                                         // utils.py:626
-    a = copysign(d2d_pymod(fabs(a), D2D_TWO_PI), a);                             // utils.py:612-618
-    if (a < 0) a += D2D_TWO_PI;
     const bool faced_right = (a < 90.0 * D2D_DEG2RAD) || (a > 270.0 * D2D_DEG2RAD);
     const bool faced_up = a > D2D_PI;
-    double slope = d2d_tan(a);
     const double step = P.scale - 1.0;
     double xs, ys;
     if (fabs(slope) > 1.0) {
@@ -248,36 +274,67 @@ __device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, int r
     }
     double x = s.px, y = s.py;
     const int nc = s.ncull;
+    // Per-ray prefilter (conservative): a culled disc can only contain a sample of this ray if its centre lies within
+    // r (+slack) of the ray's line.  |cross((c - p), d)| <= (r + slack) * |d|, compared squared.  Most rays have no
+    // candidate and skip the per-sample disc loop entirely; the decision itself stays the sampled test below.
+    bool cand = false;
+    {
+        const double dd2 = xs * xs + ys * ys;
+        for (int q = 0; q < nc; q++) {
+            const int k = cull[q];
+            const double cx = sx[k] - x, cy = sy[k] - y;
+            const double cr = cx * ys - cy * xs;
+            const double rr = sr2[k] * 1.000001 + 1e-3;          // (r + slack)^2 upper bound
+            if (cr * cr <= rr * dd2) cand = true;
+        }
+    }
     // int(x // scale) tracked incrementally: |step| < scale, so a sample moves at most one cell per axis, and
     // x in [scale*ci, scale*(ci+1)) is exactly CPython's floor (multiples of the scale are exact doubles).
     int ci = s.ix, cj = s.iy;
-    double xlo = P.scale * (double)ci, xhi = xlo + P.scale, ylo = P.scale * (double)cj, yhi = ylo + P.scale;
-    while (0.0 < x && x < P.map_w && 0.0 < y && y < P.map_h) {
+    // a ray moves monotonically along each axis, so only the boundary ahead can be crossed: xb / yb is the next
+    // boundary in the direction of travel (upper bound of the cell when stepping up, lower bound when stepping down)
+    const bool xup = xs > 0.0, yup = ys > 0.0;
+    const int sxi = xup ? 1 : -1, syi = yup ? 1 : -1;
+    const double sxd = xup ? P.scale : -P.scale, syd = yup ? P.scale : -P.scale;
+    double xb = P.scale * (double)(ci + (xup ? 1 : 0)), yb = P.scale * (double)(cj + (yup ? 1 : 0));
+    // sample m lies at most m * step * sqrt(2) from the drone: while that bound is below the view depth the
+    // `dist >= depth^2` test (utils.py:668) cannot fire and is skipped (P.m_far, margin >> accumulated rounding).
+    int m = 0;
+    for (;;) {
+        // loop condition utils.py:654: 0 < x < W and 0 < y < H; interior cells satisfy it by construction
+        if ((unsigned)(ci - 1) >= (unsigned)(D2D_GRID - 2) || (unsigned)(cj - 1) >= (unsigned)(D2D_GRID - 2)) {
+            if (!(0.0 < x && x < P.map_w && 0.0 < y && y < P.map_h)) break;
+        }
         bool any = false;
-        for (int q = 0; q < nc; q++) {
-            const int k = cull[q];
-            const double ex = sx[k] - x, ey = sy[k] - y;
-            if (ex * ex + ey * ey <= sr2[k]) {
-                atomicOr(&hitw[k >> 5], 1u << (k & 31));
-                any = true;
+        if (cand) {
+            for (int q = 0; q < nc; q++) {
+                const int k = cull[q];
+                const double ex = sx[k] - x, ey = sy[k] - y;
+                if (ex * ex + ey * ey <= sr2[k]) {
+                    atomicOr(&hitw[k >> 5], 1u << (k & 31));
+                    any = true;
+                }
             }
         }
         if (any) break;
         const bool wall = (gt[ci] >> cj) & 1ull;
-        const double fx = x - s.px, fy = y - s.py;
-        const double dist = fx * fx + fy * fy;
-        const int cell = ci * D2D_GRID + cj;
-        if (wall || dist >= P.depth2) {
-            if (wall) d2d_mark(bel_s, bel_g, cell, 1);
+        bool far = false;
+        if (m >= P.m_far) {
+            const double fx = x - s.px, fy = y - s.py;
+            far = (fx * fx + fy * fy) >= P.depth2;
+        }
+        if (wall || far) {
+            if (wall) d2d_mark(o, ci, cj, 1);
             break;
         }
-        d2d_mark(bel_s, bel_g, cell, 2);
+        d2d_mark(o, ci, cj, 2);
         x = x + xs;
         y = y + ys;
-        if (x >= xhi) { ci += 1; xlo = xhi; xhi += P.scale; }
-        else if (x < xlo) { ci -= 1; xhi = xlo; xlo -= P.scale; }
-        if (y >= yhi) { cj += 1; ylo = yhi; yhi += P.scale; }
-        else if (y < ylo) { cj -= 1; yhi = ylo; ylo -= P.scale; }
+        m += 1;
+        const bool cx = xup ? (x >= xb) : (x < xb);
+        const bool cy = yup ? (y >= yb) : (y < yb);
+        if (cx) { ci += sxi; xb += sxd; }
+        if (cy) { cj += syi; yb += syd; }
     }
 }
 
@@ -287,9 +344,27 @@ __device__ __forceinline__ void d2d_phase_rays(const DevP &P, const BlockCtx &c,
         const int i = w / R, ray = w - i * R;
         const EnvS &s = c.S[i];
         if (!s.valid) continue;
-        d2d_cast_ray(P, s, ray, c.belief + (size_t)i * D2D_BELIEF_STRIDE, P.belief + (size_t)(env0 + i) * D2D_BELIEF_STRIDE,
-                     c.gt + (size_t)i * D2D_GRID, c.sx + i * NP, c.sy + i * NP, c.sr2 + i * NP, c.cull + i * NP,
-                     c.hitw + i * P.HW);
+        RayOut o;
+        o.bel_s = c.belief + (size_t)i * D2D_BELIEF_STRIDE;
+        o.bel_g = P.belief + (size_t)(env0 + i) * D2D_BELIEF_STRIDE;
+        o.obs = nullptr; o.wi = 0; o.wj = 0;
+        const double a = d2d_ray_angle(P, s.yaw, ray);
+        d2d_cast_ray(P, s, a, d2d_tan(a), o, c.gt + (size_t)i * D2D_GRID, c.sx + i * NP, c.sy + i * NP, c.sr2 + i * NP,
+                     c.cull + i * NP, c.hitw + i * P.HW);
+    }
+}
+
+// one env per warp: lane handles rays `lane` and `lane + 32` (+64, ...); the two tangent evaluations of a pair are
+// independent straight-line code, which gives the scheduler two dependency chains to interleave
+__device__ __forceinline__ void d2d_phase_rays_warp(const DevP &P, const BlockCtx &c, const RayOut &o, int lane) {
+    const EnvS &s = c.S[0];
+    const int R = P.n_rays;
+    for (int r0 = lane; r0 < R; r0 += 64) {
+        const int r1 = r0 + 32;
+        const double a0 = d2d_ray_angle(P, s.yaw, r0), a1 = d2d_ray_angle(P, s.yaw, r1);
+        const double t0 = d2d_tan(a0), t1 = d2d_tan(a1);
+        d2d_cast_ray(P, s, a0, t0, o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
+        if (r1 < R) d2d_cast_ray(P, s, a1, t1, o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
     }
 }
 
@@ -465,13 +540,21 @@ __device__ __forceinline__ void d2d_leader_finish(const DevP &P, EnvS &s, const 
     s.yaw = d2d_pymod(s.yaw + (action * P.max_yaw_speed) * P.dt, 360.0);
 }
 
-__device__ __forceinline__ void d2d_leader_flags(const DevP &P, EnvS &s, const uint64_t *gt, int e) {
+// the five static probes of Drone2D.is_collide (utils.py:766-771); q = 0..4
+__device__ __forceinline__ int d2d_static_probe(const DevP &P, const uint64_t *gt, double px, double py, int q) {
+    const double r = P.drone_r;
+    const double ox = (q == 0) ? -r : ((q == 2) ? r : 0.0), oy = (q == 3) ? -r : ((q == 4) ? r : 0.0);
+    return d2d_gt_probe(P, gt, px + ox, py + oy);
+}
+
+__device__ __forceinline__ void d2d_leader_flags(const DevP &P, EnvS &s, const uint64_t *gt, int e, int static_hit = -1) {
     // is_collide utils.py:764-778
     int col = 0;
-    const double r = P.drone_r;
-    if (d2d_gt_probe(P, gt, s.px - r, s.py) || d2d_gt_probe(P, gt, s.px, s.py) || d2d_gt_probe(P, gt, s.px + r, s.py) ||
-        d2d_gt_probe(P, gt, s.px, s.py - r) || d2d_gt_probe(P, gt, s.px, s.py + r))
-        col = 1;
+    if (static_hit < 0) {
+        static_hit = 0;
+        for (int q = 0; q < 5; q++) static_hit |= d2d_static_probe(P, gt, s.px, s.py, q);
+    }
+    if (static_hit) col = 1;
     else if (s.coll_agent) col = 2;
     int dead = 0, frz = 0;
     if (col == 0) {   // drone_v2.py:222-225
@@ -592,4 +675,130 @@ __global__ void __launch_bounds__((E * 50 + 31) / 32 * 32, (E == 4 ? 4 : (E == 8
     __syncthreads();
     d2d_phase_obs(P, c, env0, E, tid, T);
     if (c.misc[0]) d2d_phase_done_stats(P, c, E, tid, T);
+}
+
+
+// =============================================================================================================
+// Warp-per-environment variant.  Same phase functions, but every warp owns ONE env (E = 1, T = 32) with a private
+// shared-memory slice and its own mbarrier, so the phases are separated by __syncwarp() instead of block barriers:
+// warps of a block never wait for each other (the block-wide version spent ~44 % of its stall samples in
+// __syncthreads because the agent / tracker / leader phases have few work items).
+// =============================================================================================================
+__host__ __device__ inline size_t d2d_warp_slice_bytes(int NP, int HW, int extra) {
+    size_t b = d2d_step_smem_bytes(1, NP, HW) + (size_t)extra;
+    return (b + 127) / 128 * 128;
+}
+
+// observation of ONE env written by one warp: bytes [1089*e, 1089*e + 1089) of the tensor; the unaligned head / tail
+// (1089 = 1 mod 4) go out as byte stores, the middle as coalesced 32-bit stores.
+__device__ __forceinline__ uint32_t d2d_obs_cell(const uint8_t *bel, int ix, int iy, int k) {
+    const int u = k / D2D_LOCAL, v = k - u * D2D_LOCAL;
+    const int gi = ix - 16 + u, gj = iy - 16 + v;
+    if ((unsigned)gi < (unsigned)D2D_GRID && (unsigned)gj < (unsigned)D2D_GRID) return bel[gi * D2D_GRID + gj];
+    return 0u;
+}
+
+// 4 consecutive window bytes of row u starting at column v (bytes past column 32 are garbage, masked by the caller);
+// window byte (u, v) = belief[ix-16+u][iy-16+v], zero outside the 50x50 grid (np.pad, utils.py:783).
+__device__ __forceinline__ uint32_t d2d_win4(const uint8_t *bel, int ix, int iy, int u, int v) {
+    const int gi = ix - 16 + u;
+    if ((unsigned)gi >= (unsigned)D2D_GRID) return 0u;
+    const int gj = iy - 16 + v;
+    const int a = gi * D2D_GRID + gj;                 // byte address, may leave [0, 2500) by < 20 on masked bytes
+    const int al = a & ~3;
+    const uint32_t lo = (al >= 0) ? *(const uint32_t *)(bel + al) : 0u;
+    const uint32_t hi = (al + 4 >= 0 && al + 4 < D2D_BELIEF_STRIDE) ? *(const uint32_t *)(bel + al + 4) : 0u;
+    uint32_t w = __funnelshift_r(lo, hi, (a & 3) * 8);
+    if ((unsigned)gj > (unsigned)(D2D_GRID - 4)) {     // some of the 4 columns fall outside [0, 50)
+        uint32_t m = 0u;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if ((unsigned)(gj + b) < (unsigned)D2D_GRID) m |= 0xFFu << (8 * b);
+        w &= m;
+    }
+    return w;
+}
+
+__device__ __forceinline__ uint32_t d2d_obs_word(const uint8_t *bel, int ix, int iy, int k0) {
+    // env-relative bytes k0..k0+3 of the row-major 33x33 window (k0 + 3 < 1089)
+    const int u0 = k0 / D2D_LOCAL, v0 = k0 - u0 * D2D_LOCAL;
+    uint32_t w = d2d_win4(bel, ix, iy, u0, v0);
+    if (v0 > D2D_LOCAL - 4) {                          // the word wraps into the next row
+        const int n1 = D2D_LOCAL - v0;                 // bytes taken from row u0 (1..3)
+        const uint32_t w2 = d2d_win4(bel, ix, iy, u0 + 1, 0);
+        w = (w & ((1u << (8 * n1)) - 1u)) | (w2 << (8 * n1));
+    }
+    return w;
+}
+
+__device__ __forceinline__ void d2d_obs_env_warp(const DevP &P, const uint8_t *bel, int ix, int iy, int e, int lane) {
+    // bytes [1089*e, 1089*e + 1089) of the observation tensor: unaligned head / tail (1089 = 1 mod 4) as byte stores,
+    // the middle as coalesced 32-bit stores assembled with funnel shifts from aligned shared-memory words.
+    uint8_t *out = P.local_map + (size_t)e * D2D_LOCAL_CELLS;
+    const int head = (4 - (e & 3)) & 3;                 // arena buffers are 256-B aligned
+    const int nwords = (D2D_LOCAL_CELLS - head) >> 2;
+    const int tail0 = head + 4 * nwords;
+    if (lane < head) out[lane] = (uint8_t)d2d_obs_cell(bel, ix, iy, lane);
+    if (lane < D2D_LOCAL_CELLS - tail0) out[tail0 + lane] = (uint8_t)d2d_obs_cell(bel, ix, iy, tail0 + lane);
+    uint32_t *ow = (uint32_t *)(out + head);
+    for (int j = lane; j < nwords; j += 32) ow[j] = d2d_obs_word(bel, ix, iy, head + 4 * j);
+}
+
+template <int WPB, int MINB>
+__global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(const DevP P,
+                                                                             const double *__restrict__ actions) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int e = blockIdx.x * WPB + wid;
+    if (e >= P.B) return;                                            // warp-uniform
+    const BlockCtx c = d2d_carve(smem + (size_t)wid * d2d_warp_slice_bytes(P.NP, P.HW, 0), 1, P.NP, P.HW);
+    EnvS &s = c.S[0];
+
+    if (lane == 0) {
+        d2d_mbar_init(c.mbar, 1);
+        c.misc[0] = 0;
+        d2d_load_env_scalars(P, s, e);
+        c.misc[1] = s.reset;
+    }
+    for (int w = lane; w < P.HW; w += 32) c.hitw[w] = 0u;
+    __syncwarp();
+    if (lane == 0) d2d_issue_bulk(P, c, e, 1, true);
+    d2d_reset_arrays(P, c, e, 1, lane, 32);
+    d2d_phase_agents<true>(P, c, e, 1, lane, 32);
+    if (lane == 0) d2d_leader_begin(P, s);
+    // NoMove: the drone cell cannot change during the step, so if the observation tensor already holds this window it
+    // is patched in place by the rays (only cells whose value changes) instead of being rewritten
+    const int oix = P.obs_ix[e], oiy = P.obs_iy[e];
+    __syncwarp();
+    const bool patch = !s.reset && oix == s.ix && oiy == s.iy;
+    RayOut ro;
+    ro.bel_s = c.belief; ro.bel_g = P.belief + (size_t)e * D2D_BELIEF_STRIDE;
+    ro.obs = patch ? P.local_map + (size_t)e * D2D_LOCAL_CELLS : nullptr;
+    ro.wi = s.ix - 16; ro.wj = s.iy - 16;
+    d2d_mbar_wait(c.mbar, 0);
+    d2d_phase_rays_warp(P, c, ro, lane);
+    __syncwarp();
+    d2d_phase_trackers(P, c, e, 1, lane, 32);
+    const int shit = __any_sync(0xffffffffu, lane < 5 ? d2d_static_probe(P, c.gt, s.px, s.py, lane) : 0);
+    __syncwarp();
+    if (lane == 0) {
+        // NoMove.plan traj_planner.py:70-73 / NoMove.replan_check :75-76
+        s.tgx = -1.0; s.tgy = -1.0;
+        P.replan[e] = 0; P.plan_ok[e] = 1; P.need_plan[e] = 0;
+        d2d_leader_finish(P, s, c.gt, e, actions[e], true);
+        d2d_leader_flags(P, s, c.gt, e, shit);
+        d2d_store_env_scalars(P, s, e);
+        atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], 1ull);
+    }
+    __syncwarp();
+    if (!patch || s.ix != oix || s.iy != oiy) {
+        d2d_obs_env_warp(P, c.belief, s.ix, s.iy, e, lane);
+        if (lane == 0) { P.obs_ix[e] = s.ix; P.obs_iy[e] = s.iy; }
+    }
+    if (s.done_now) {
+        int cnt = 0;
+        for (int o = lane; o < D2D_CELLS; o += 32) cnt += (c.belief[o] != 0);
+        for (int off = 16; off > 0; off >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+        if (lane == 0 && cnt) atomicAdd(&P.stats[D2D_STAT_GRID_DISCOVERED], (unsigned long long)cnt);
+    }
 }

@@ -112,6 +112,8 @@ __global__ void d2d_reset_kernel(const DevP P, const uint8_t *__restrict__ mask)
         P.traj_nseg[e] = 0; P.traj_cursor[e] = 0; P.need_plan[e] = 0; P.plan_ok[e] = 1; P.replan[e] = 0;
         P.yaw_obs[e] = (float)yaw;
         P.ox_fresh[e] = 0; P.tmp_act_cnt[e] = 0; P.tmp_act_ts[e] = 0;
+        // local_map was zeroed above, which IS the window of an all-unexplored belief grid at the initial cell
+        P.obs_ix[e] = d2d_cell(x, P.scale, P.inv_scale); P.obs_iy[e] = d2d_cell(y, P.scale, P.inv_scale);
     }
 }
 
@@ -119,6 +121,7 @@ __global__ void d2d_set_pose_kernel(const DevP P, const double *__restrict__ pos
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= P.B) return;
     P.drone_x[e] = pose[3 * e]; P.drone_y[e] = pose[3 * e + 1]; P.drone_yaw[e] = pose[3 * e + 2];
+    P.obs_ix[e] = -1000000; P.obs_iy[e] = -1000000;   // the observation window must be rebuilt
 }
 
 // NumPy pairwise-sum recursion for a contiguous run of n doubles -> leaf blocks + post-order combine program
@@ -229,6 +232,8 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     size_t o_tac = add_buf(h, cur, "tmp_active_count", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_tat = add_buf(h, cur, "tmp_active_ts", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_oxf = add_buf(h, cur, "oxford_fresh", D2D_U8, 1, SHP(B), SHP(1), sB);
+    size_t o_obx = add_buf(h, cur, "obs_ix", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_oby = add_buf(h, cur, "obs_iy", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_oxp = add_buf(h, cur, "oxford_program", D2D_U8, 1, SHP((int64_t)sizeof(OxProgram)), SHP(1), sizeof(OxProgram));
     size_t o_ox = add_buf(h, cur, "oxford_last_time_observed", D2D_F64, 3, SHP(B, D2D_GRID, D2D_GRID),
                           SHP(D2D_CELLS, D2D_GRID, 1), cfg->oxford ? (size_t)sB * D2D_CELLS : 16);
@@ -264,7 +269,14 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.var_cam = cfg->var_cam; P.max_speed = cfg->drone_max_speed;
     // a sample is evaluated only if the previous one was closer than depth: reach = depth + step*sqrt(2) (+ slack)
     P.cull_reach = cfg->drone_view_depth + (cfg->map_scale - 1.0) * 1.4142135623730951 + 1e-3;
+    P.ray_a0 = -P.fov / 2; P.ray_da = P.fov / (double)cfg->n_rays;
     P.ox_cos_thresh = cfg->ox_cos_thresh;
+    {   // sample m is at most m*(scale-1)*sqrt(2) from the drone; skip the depth test while that is < 0.99*depth
+        const double lmax = (cfg->map_scale - 1.0) * 1.4142135623730951;
+        int m = 0;
+        while ((double)(m + 1) * lmax < 0.99 * cfg->drone_view_depth) m++;
+        P.m_far = m + 1;                     // samples 0..m are provably inside the view depth
+    }
     memcpy(P.targets, cfg->targets, sizeof(P.targets));
     P.apos = (double2 *)(A + o_apos); P.apref = (double2 *)(A + o_apref);
     P.apos0 = (double2 *)(A + o_apos0); P.apref0 = (double2 *)(A + o_apref0);
@@ -284,6 +296,7 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.need_plan = A + o_need; P.plan_ok = A + o_pok; P.replan = A + o_rep;
     P.ox_last = cfg->oxford ? (double *)(A + o_ox) : nullptr;
     P.tmp_act_cnt = (int *)(A + o_tac); P.tmp_act_ts = (int *)(A + o_tat); P.ox_fresh = A + o_oxf;
+    P.obs_ix = (int *)(A + o_obx); P.obs_iy = (int *)(A + o_oby);
     h->ox_prog = (OxProgram *)(A + o_oxp);
     P.stats = (unsigned long long *)(A + o_stats);
     P.tab = (const DevTables *)(A + o_tab);
@@ -436,6 +449,22 @@ static int launch_fused(d2d_handle *h, const double *actions, cudaStream_t st) {
     return D2D_OK;
 }
 
+template <int WPB, int MINB>
+static int launch_fused_warp(d2d_handle *h, const double *actions, cudaStream_t st) {
+    static bool attr_done[64] = {false};
+    const int dev = h->cfg.device;
+    const size_t smem = (size_t)WPB * d2d_warp_slice_bytes(h->NP, h->HW, 0);
+    if (smem > 227 * 1024) { h->err = "warp-per-env kernel: shared memory per block exceeds 227 KB"; return D2D_ERR_INVALID; }
+    if (!attr_done[dev & 63]) {
+        cudaError_t ce = cudaFuncSetAttribute(d2d_step_fused_warp_kernel<WPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
+        attr_done[dev & 63] = true;
+    }
+    d2d_step_fused_warp_kernel<WPB, MINB><<<(h->B + WPB - 1) / WPB, WPB * 32, smem, st>>>(h->P, actions);
+    h->launches++;
+    return D2D_OK;
+}
+
 static int step_primitive(d2d_handle *h, const double *actions, cudaStream_t st);
 
 extern "C" int d2d_step(d2d_handle *h, const double *actions_dev, void *stream) {
@@ -444,7 +473,22 @@ extern "C" int d2d_step(d2d_handle *h, const double *actions_dev, void *stream) 
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if (h->cfg.planner == D2D_PLANNER_NOMOVE) {
+    const int epb = h->cfg.envs_per_block;
+    if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb <= 0) {
+        rc = launch_fused_warp<4, 7>(h, actions_dev, st);       // default: one warp per env, 72 registers
+    } else if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb == 1) {
+        rc = launch_fused_warp<2, 14>(h, actions_dev, st);
+    } else if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb == 2) {
+        rc = launch_fused_warp<7, 4>(h, actions_dev, st);
+    } else if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb == 32) {     // tuning variants: register caps
+        rc = launch_fused_warp<4, 8>(h, actions_dev, st);       // 64 registers, 32 warps/SM
+    } else if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb == 33) {
+        rc = launch_fused_warp<4, 9>(h, actions_dev, st);       // 56 registers, 36 warps/SM
+    } else if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb == 34) {
+        rc = launch_fused_warp<4, 10>(h, actions_dev, st);      // 48 registers, 40 warps/SM
+    } else if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb == 35) {
+        rc = launch_fused_warp<4, 6>(h, actions_dev, st);       // 80 registers, 24 warps/SM
+    } else if (h->cfg.planner == D2D_PLANNER_NOMOVE) {
         switch (h->E) {
             case 4: rc = launch_fused<4>(h, actions_dev, st); break;
             case 16: rc = launch_fused<16>(h, actions_dev, st); break;
