@@ -223,41 +223,112 @@ __device__ __forceinline__ double d2d_node_total(double cost, double px, double 
 }
 
 // ------------------------------------------------------------------------------------------ A* kernel
-// One block per planning env (persistent over the compacted list).  Node storage is SoA in an HBM workspace
-// (stays in L2); the belief grid and the active trackers are staged in shared memory.
-__global__ void __launch_bounds__(D2D_PLAN_THREADS) d2d_plan_kernel(const DevP P) {
+// One block per planning env (persistent over the compacted list).  Per-search hot state lives in shared memory when
+// it fits (8x8 primitives: open-set totals 51 KB + 32-bit-key hash 48 KB, two blocks per SM): the argmin over the open set, the dict
+// lookups and the replace-if-cheaper test never leave the SM.  Cold node fields (position, velocity, parent, action)
+// are SoA in an HBM workspace that stays L2-resident.  Collision checks are spread over (primitive, sample) pairs.
+#define D2D_PLAN_SMEM_NODES 6400       // >= 99 * 64 + 8
+#define D2D_PLAN_SMEM_HASH 8192
+#define D2D_HASH32_EMPTY 0xFFFFFFFFu
+
+struct PlanHot {                        // pointers into shared memory (fast path) or the HBM workspace (fallback)
+    double *open_total;                 // +inf once the node is closed
+    double *cost;
+    uint32_t *hkeys32; uint16_t *hvals16;          // fast path
+    unsigned long long *hkeys64; int *hvals32;     // fallback
+    int hcap;
+    bool fast;
+};
+
+__host__ __device__ inline size_t d2d_plan_smem_bytes(int NP, int n_u, int n_samp) {
+    size_t b = D2D_BELIEF_STRIDE + (size_t)NP * 5 * 8 + 256 + (size_t)n_u * n_u;   // belief, trackers, scratch, prim_ok
+    if (d2d_plan_cap(n_u) <= D2D_PLAN_SMEM_NODES)
+        b += (size_t)D2D_PLAN_SMEM_NODES * 8 + (size_t)D2D_PLAN_SMEM_HASH * 6;
+    return (b + 15) / 16 * 16;
+}
+
+// packs (round(px)//10, round(py)//10, round(vx), round(vy)) into 28 bits; valid for |v| < 64 and cells in [-32, 95]
+__device__ __forceinline__ uint32_t d2d_node_key32(double px, double py, double vx, double vy) {
+    const int a = (int)d2d_floordiv10((long long)rint(px)) + 32, b = (int)d2d_floordiv10((long long)rint(py)) + 32;
+    const int c = (int)rint(vx) + 64, d = (int)rint(vy) + 64;
+    return ((uint32_t)(a & 127) << 21) | ((uint32_t)(b & 127) << 14) | ((uint32_t)(c & 127) << 7) | (uint32_t)(d & 127);
+}
+
+// dict lookup / insert; returns the node index stored for the key (>= 0) or -1 after inserting a fresh slot (*slot)
+__device__ __forceinline__ int d2d_plan_find_or_insert(const PlanHot &h, const PlanWs &w, double px, double py, double vx,
+                                                       double vy, int *slot) {
+    if (h.fast) {
+        const uint32_t key = d2d_node_key32(px, py, vx, vy);
+        int s = (int)((key * 2654435761u) >> 19) & (h.hcap - 1);
+        for (;;) {
+            const uint32_t cur = h.hkeys32[s];
+            if (cur == key) { *slot = s; return h.hvals16[s]; }
+            if (cur == D2D_HASH32_EMPTY) {
+                const uint32_t old = atomicCAS(&h.hkeys32[s], D2D_HASH32_EMPTY, key);
+                if (old == D2D_HASH32_EMPTY) { *slot = s; return -1; }
+                if (old == key) { *slot = s; return h.hvals16[s]; }
+            }
+            s = (s + 1) & (h.hcap - 1);
+        }
+    } else {
+        bool existed;
+        const int s = d2d_hash_find_or_insert(w, d2d_node_key(px, py, vx, vy), &existed);
+        *slot = s;
+        return existed ? w.hvals[s] : -1;
+    }
+}
+
+#define D2D_PLAN_THREADS2 256
+__global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP P) {
     extern __shared__ __align__(16) unsigned char psm[];
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = T >> 5;
+    const int nu = P.n_u, nprim = nu * nu, nsamp = P.n_samp;
     uint8_t *bel = psm;                                         // [2560]
     double *trk = (double *)(psm + D2D_BELIEF_STRIDE);          // [NP][5]
-    double *red_v = trk + (size_t)P.NP * 5;                     // [4] warp partials
-    int *red_i = (int *)(red_v + 4);                            // [4]
-    int *sh = red_i + 4;                                        // [8] cur, n_nodes, n_open, status, nact, chunk_new
-    int *wsum = sh + 8;                                         // [4] warp prefix
-    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5;
-    const int count = min(P.plan_list[P.B], P.B);
+    double *red_v = trk + (size_t)P.NP * 5;                     // [8] warp partials
+    int *red_i = (int *)(red_v + 8);                            // [8]
+    int *sh = red_i + 8;                                        // [8] cur, n_nodes, n_open, -, nact
+    int *wsum = sh + 8;                                         // [8] warp prefix
+    uint8_t *prim_ok = (uint8_t *)(wsum + 8);                   // [nprim]
     const PlanWs w = d2d_plan_carve(P.plan_ws + (size_t)blockIdx.x * d2d_plan_workspace_bytes(P.n_u), P.n_u);
-    const int nu = P.n_u, nprim = nu * nu;
+    PlanHot h;
+    h.fast = d2d_plan_cap(nu) <= D2D_PLAN_SMEM_NODES && P.max_speed < 60.0;
+    if (h.fast) {
+        unsigned char *q = psm + ((size_t)D2D_BELIEF_STRIDE + (size_t)P.NP * 40 + 256 + nprim + 15) / 16 * 16;
+        h.open_total = (double *)q; q += (size_t)D2D_PLAN_SMEM_NODES * 8;
+        h.cost = w.cost;                                        // only read on dict hits: stays in the L2-resident workspace
+        h.hkeys32 = (uint32_t *)q; q += (size_t)D2D_PLAN_SMEM_HASH * 4;
+        h.hvals16 = (uint16_t *)q;
+        h.hkeys64 = nullptr; h.hvals32 = nullptr; h.hcap = D2D_PLAN_SMEM_HASH;
+    } else {
+        h.open_total = w.open_total; h.cost = w.cost; h.hkeys32 = nullptr; h.hvals16 = nullptr;
+        h.hkeys64 = w.hkeys; h.hvals32 = w.hvals; h.hcap = w.hcap;
+    }
+    const int count = min(P.plan_list[P.B], P.B);
 
     for (int li = blockIdx.x; li < count; li += gridDim.x) {
         const int e = P.plan_list[li];
         __syncthreads();
-        // stage belief + trackers, clear the hash table
         for (int o = tid; o < D2D_BELIEF_STRIDE / 4; o += T)
             ((uint32_t *)bel)[o] = ((const uint32_t *)(P.belief + (size_t)e * D2D_BELIEF_STRIDE))[o];
-        for (int o = tid; o < w.hcap; o += T) { w.hkeys[o] = D2D_HASH_EMPTY; w.hvals[o] = -1; }
+        if (h.fast) {
+            for (int o = tid; o < h.hcap; o += T) h.hkeys32[o] = D2D_HASH32_EMPTY;
+        } else {
+            for (int o = tid; o < w.hcap; o += T) { w.hkeys[o] = D2D_HASH_EMPTY; w.hvals[o] = -1; }
+        }
         if (tid == 0) sh[4] = 0;
         __syncthreads();
         d2d_gather_trackers(P, e, trk, &sh[4], tid, T);
         const double tx = P.target_x[e], ty = P.target_y[e];
         if (tid == 0) {   // start node (traj_planner.py:136-146)
             const double x = P.drone_x[e], y = P.drone_y[e], vx = P.drone_vx[e], vy = P.drone_vy[e];
-            w.px[0] = x; w.py[0] = y; w.vx[0] = vx; w.vy[0] = vy; w.cost[0] = 0.0;
-            const double tot = d2d_node_total(0.0, x, y, vx, vy, tx, ty);
-            w.total[0] = tot; w.open_total[0] = tot; w.parent[0] = -1; w.itr[0] = 0; w.act[0] = 0;
-            bool ex;
-            const int s = d2d_hash_find_or_insert(w, d2d_node_key(x, y, vx, vy), &ex);
-            w.hvals[s] = 0;
-            sh[1] = 1; sh[2] = 1; sh[3] = 0;
+            w.px[0] = x; w.py[0] = y; w.vx[0] = vx; w.vy[0] = vy; h.cost[0] = 0.0;
+            h.open_total[0] = d2d_node_total(0.0, x, y, vx, vy, tx, ty);
+            w.parent[0] = -1; w.itr[0] = 0; w.act[0] = 0;
+            int slot;
+            d2d_plan_find_or_insert(h, w, x, y, vx, vy, &slot);
+            if (h.fast) h.hvals16[slot] = 0; else w.hvals[slot] = 0;
+            sh[1] = 1; sh[2] = 1;
         }
         __syncthreads();
         const int nact = sh[4];
@@ -270,7 +341,7 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS) d2d_plan_kernel(const DevP P
             double bv = INFINITY;
             int bi = 0x7fffffff;
             for (int i = tid; i < n_nodes; i += T) {
-                const double v = w.open_total[i];
+                const double v = h.open_total[i];
                 if (v < bv) { bv = v; bi = i; }
             }
             for (int off = 16; off > 0; off >>= 1) {
@@ -281,51 +352,53 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS) d2d_plan_kernel(const DevP P
             if (lane == 0) { red_v[wid] = bv; red_i[wid] = bi; }
             __syncthreads();
             if (tid == 0) {
-                for (int q = 1; q < (T >> 5); q++)
+                for (int q = 1; q < NW; q++)
                     if (red_v[q] < bv || (red_v[q] == bv && red_i[q] < bi)) { bv = red_v[q]; bi = red_i[q]; }
                 sh[0] = bi;
+                if (bi != 0x7fffffff) { h.open_total[bi] = INFINITY; sh[2] -= 1; }   // open -> closed (:167-170)
             }
+            for (int q = tid; q < nprim; q += T) prim_ok[q] = 1;
             __syncthreads();
             const int cur = sh[0];
             if (cur == 0x7fffffff) break;                        // only non-finite costs left (cannot happen)
-            const double cpx = w.px[cur], cpy = w.py[cur], cvx = w.vx[cur], cvy = w.vy[cur], ccost = w.cost[cur];
+            const double cpx = w.px[cur], cpy = w.py[cur], cvx = w.vx[cur], cvy = w.vy[cur], ccost = h.cost[cur];
             const int citr = w.itr[cur];
-            if (d2d_norm2(cpx - tx, cpy - ty) <= 10.0) { goal = cur; success = true; break; }   // :160
+            if (d2d_norm2(cpx - tx, cpy - ty) <= 10.0) {         // :160 (the node stays in the open set in the reference,
+                goal = cur; success = true; break;               //       which no longer matters once the search ends)
+            }
+            // ---- collision checks of all (primitive, sample) pairs (:174-185)
+            for (int q = tid; q < nprim * nsamp; q += T) {
+                const int pidx = q / nsamp, sI = q - pidx * nsamp;
+                const int ia = pidx / nu, ib = pidx - ia * nu;
+                const double xa = P.tab->u_space[ia], ya = P.tab->u_space[ib];
+                const double nvx = 1.0 * cvx + 4.0 * (xa / 2.0), nvy = 1.0 * cvy + 4.0 * (ya / 2.0);
+                bool ok = d2d_norm2(nvx, nvy) < P.max_speed;     // :176
+                if (ok && prim_ok[pidx]) {
+                    const double t = P.tab->t_samp[sI], t2 = P.tab->t_samp2[sI];
+                    const double qx = rint(D2D_FMA(t2, xa / 2.0, 1.0 * cpx + t * cvx));
+                    const double qy = rint(D2D_FMA(t2, ya / 2.0, 1.0 * cpy + t * cvy));
+                    ok = d2d_is_free(P, bel, qx, qy, t + (double)(citr * 2), trk, nact);
+                }
+                if (!ok) prim_ok[pidx] = 0;
+            }
             __syncthreads();
-            if (tid == 0) { w.open_total[cur] = INFINITY; sh[2] -= 1; }     // open -> closed (:167-170)
-            __syncthreads();
-            // ---- expand in (x_acc, y_acc) loop order, T primitives at a time (:174-195)
+            // ---- successors in (x_acc, y_acc) loop order, T primitives at a time (:187-206)
             for (int base = 0; base < nprim; base += T) {
                 const int pidx = base + tid;
-                bool ok = pidx < nprim;
-                double xa = 0, ya = 0, nvx = 0, nvy = 0;
+                const bool ok = pidx < nprim && prim_ok[pidx];
+                double xa = 0, ya = 0, nvx = 0, nvy = 0, spx = 0, spy = 0, scost = 0;
+                int slot = -1, exist_idx = -1;
+                bool is_new = false;
                 if (ok) {
                     xa = P.tab->u_space[pidx / nu];
                     ya = P.tab->u_space[pidx - (pidx / nu) * nu];
                     nvx = 1.0 * cvx + 4.0 * (xa / 2.0);
                     nvy = 1.0 * cvy + 4.0 * (ya / 2.0);
-                    ok = d2d_norm2(nvx, nvy) < P.max_speed;      // :176
-                }
-                if (ok) {
-                    const double hx = xa / 2.0, hy = ya / 2.0;
-                    for (int sI = 0; sI < P.n_samp; sI++) {      // :180-185
-                        const double t = P.tab->t_samp[sI], t2 = P.tab->t_samp2[sI];
-                        const double qx = rint(D2D_FMA(t2, hx, 1.0 * cpx + t * cvx));
-                        const double qy = rint(D2D_FMA(t2, hy, 1.0 * cpy + t * cvy));
-                        if (!d2d_is_free(P, bel, qx, qy, t + (double)(citr * 2), trk, nact)) { ok = false; break; }
-                    }
-                }
-                double spx = 0, spy = 0, scost = 0;
-                int slot = -1, exist_idx = -1;
-                bool is_new = false;
-                if (ok) {
                     spx = rint((1.0 * cpx + 2.0 * cvx) + 4.0 * (xa / 2.0));   // :188
                     spy = rint((1.0 * cpy + 2.0 * cvy) + 4.0 * (ya / 2.0));
                     scost = ccost + (xa * xa + ya * ya) / 100.0 + 10.0;      // :190
-                    bool existed;
-                    slot = d2d_hash_find_or_insert(w, d2d_node_key(spx, spy, nvx, nvy), &existed);
-                    if (existed) exist_idx = w.hvals[slot];
-                    else is_new = true;
+                    exist_idx = d2d_plan_find_or_insert(h, w, spx, spy, nvx, nvy, &slot);
+                    is_new = exist_idx < 0;
                 }
                 // ordered slot assignment for the new nodes of this chunk (insertion order == primitive order)
                 const unsigned bal = __ballot_sync(0xffffffffu, is_new);
@@ -333,22 +406,23 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS) d2d_plan_kernel(const DevP P
                 if (lane == 0) wsum[wid] = __popc(bal);
                 __syncthreads();
                 int before = 0, tot_new = 0;
-                for (int q = 0; q < (T >> 5); q++) {
+                for (int q = 0; q < NW; q++) {
                     if (q < wid) before += wsum[q];
                     tot_new += wsum[q];
                 }
                 const int nn = sh[1];
                 int idx = -1;
-                if (is_new) { idx = nn + before + wrank; w.hvals[slot] = idx; }
-                else if (ok && exist_idx >= 0) {
+                if (is_new) {
+                    idx = nn + before + wrank;
+                    if (h.fast) h.hvals16[slot] = (uint16_t)idx; else w.hvals[slot] = idx;
+                } else if (ok) {
                     // in closed_set -> skip; in open_set -> replace if cheaper, keeping the dict slot (:197-206)
-                    if (w.open_total[exist_idx] != INFINITY && w.cost[exist_idx] > scost) idx = exist_idx;
+                    if (h.open_total[exist_idx] != INFINITY && h.cost[exist_idx] > scost) idx = exist_idx;
                 }
                 if (idx >= 0 && idx < w.cap) {
-                    const double tot = d2d_node_total(scost, spx, spy, nvx, nvy, tx, ty);
-                    w.px[idx] = spx; w.py[idx] = spy; w.vx[idx] = nvx; w.vy[idx] = nvy; w.cost[idx] = scost;
-                    w.total[idx] = tot; w.open_total[idx] = tot; w.parent[idx] = cur; w.itr[idx] = citr + 1;
-                    w.act[idx] = pidx;
+                    w.px[idx] = spx; w.py[idx] = spy; w.vx[idx] = nvx; w.vy[idx] = nvy; h.cost[idx] = scost;
+                    h.open_total[idx] = d2d_node_total(scost, spx, spy, nvx, nvy, tx, ty);
+                    w.parent[idx] = cur; w.itr[idx] = citr + 1; w.act[idx] = pidx;
                 }
                 __syncthreads();
                 if (tid == 0) { sh[1] = nn + tot_new; sh[2] += tot_new; }
@@ -468,23 +542,50 @@ __device__ __forceinline__ double d2d_np_leaf_sum(const double *a, int n) {
     return res;
 }
 
+// exact decision of `np.arccos(cc) <= view_angle` with cc = num / den (yaw_planner.py:78): cc >= c* and cc <= 1
+// (arccos of cc > 1 is NaN -> False).  The IEEE division is only performed when num is within a few ulps of the two
+// decision boundaries c* * den and den; everywhere else the comparison of the products decides (margins 8e-16 relative
+// cover the rounding of the division and of the products).
+__device__ __forceinline__ bool d2d_ox_wedge(double num, double den, double cstar) {
+    const double t = cstar * den;
+    const double slack = 8e-16;
+    if (num > t + fabs(t) * slack && num < den - den * slack) return true;
+    if (num < t - fabs(t) * slack) return false;
+    const double cc = num / den;
+    return cc >= cstar && cc <= 1.0;
+}
+
 __device__ __forceinline__ bool d2d_ox_visible(const DevP &P, int cell, double dx, double dy, double cs, double msn) {
     const int i = cell / D2D_GRID, j = cell - i * D2D_GRID;
     const double x = (double)i * P.scale, y = (double)j * P.scale;
     const double ex = dx - x, ey = dy - y;
     const double d2 = ex * ex + ey * ey;
     if (d2 <= 0.0) return true;
-    const double cc = ((x - dx) * cs + (y - dy) * msn) / D2D_SQRT(d2);
-    // np.arccos(cc) <= view_angle  <=>  cc >= c*;  arccos(cc > 1) is NaN -> False (yaw_planner.py:78)
-    return cc >= P.ox_cos_thresh && cc <= 1.0 && d2 <= P.depth2;
+    if (!(d2 <= P.depth2)) return false;
+    return d2d_ox_wedge((x - dx) * cs + (y - dy) * msn, D2D_SQRT(d2), P.ox_cos_thresh);
 }
 
-__global__ void __launch_bounds__(256) d2d_oxford_kernel(const DevP P, const OxProgram *__restrict__ prog,
-                                                         double *__restrict__ actions_out) {
-    __shared__ double reward[D2D_CELLS];
-    __shared__ double prod[D2D_CELLS];
-    int *swep_i = (int *)prod;          // only needed while the reward map is built, before prod is used
-    __shared__ double leaf[D2D_OX_MAX_LEAVES];
+// Only cells whose corner lies within the view depth of the pose can be visible: rows/cols [lo, hi] of the grid.
+__device__ __forceinline__ void d2d_ox_window(const DevP &P, double dx, int &lo, int &hi) {
+    const double depth = D2D_SQRT(P.depth2);
+    lo = (int)floor((dx - depth) * P.inv_scale) - 1;
+    hi = (int)floor((dx + depth) * P.inv_scale) + 1;
+    if (lo < 0) lo = 0;
+    if (hi > D2D_GRID - 1) hi = D2D_GRID - 1;
+}
+
+#define D2D_OX_ROWS 21          // window rows (2 * depth / scale + slack) handled per pose
+#define D2D_OX_THREADS 256
+__host__ __device__ inline size_t d2d_oxford_smem_bytes(int n_yaw) {
+    return (size_t)n_yaw * D2D_OX_ROWS * D2D_GRID * 8 + (size_t)D2D_CELLS * 4 + (size_t)n_yaw * D2D_OX_MAX_LEAVES * 8 + 256;
+}
+
+__global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P, const OxProgram *__restrict__ prog,
+                                                                    double *__restrict__ actions_out) {
+    extern __shared__ __align__(16) unsigned char oxsm[];
+    double *prod = (double *)oxsm;                                         // [n_yaw][D2D_OX_ROWS * 50] candidate products
+    int *swep_i = (int *)(prod + (size_t)P.n_yaw * D2D_OX_ROWS * D2D_GRID);   // [2500] last waypoint index per cell
+    double *leaf = (double *)(swep_i + D2D_CELLS);                          // [n_yaw][D2D_OX_MAX_LEAVES]
     __shared__ double score[D2D_MAX_YAW];
     __shared__ double cs_s[D2D_MAX_YAW + 1], sn_s[D2D_MAX_YAW + 1];
     const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
@@ -495,10 +596,11 @@ __global__ void __launch_bounds__(256) d2d_oxford_kernel(const DevP P, const OxP
     const double dx = fresh ? P.pose0[e] : P.drone_x[e], dy = fresh ? P.pose0[P.B + e] : P.drone_y[e];
     const double yaw = fresh ? P.pose0[2 * P.B + e] : P.drone_yaw[e];
     const int len = fresh ? 0 : P.traj_nseg[e] * P.n_way - P.traj_cursor[e], cursor = fresh ? 0 : P.traj_cursor[e];
+    const int ny = P.n_yaw;
     for (int c = tid; c < D2D_CELLS; c += T) swep_i[c] = -1;
-    if (tid <= P.n_yaw) {
+    if (tid <= ny) {
         // candidate yaws: Drone2D(..., yaw_i) stores yaw_i % 360 (utils.py:718); entry n_yaw is the current pose
-        const double y = (tid < P.n_yaw) ? d2d_pymod(yaw + P.tab->v_yaw_space[tid] * P.dt, 360.0) : yaw;
+        const double y = (tid < ny) ? d2d_pymod(yaw + P.tab->v_yaw_space[tid] * P.dt, 360.0) : yaw;
         double sn, cs;
         d2d_sincos(y * D2D_DEG2RAD, &sn, &cs);
         cs_s[tid] = cs; sn_s[tid] = -sn;    // vec_yaw = [cos, -sin] (yaw_planner.py:72)
@@ -513,46 +615,101 @@ __global__ void __launch_bounds__(256) d2d_oxford_kernel(const DevP P, const OxP
         if ((unsigned)ci < (unsigned)D2D_GRID && (unsigned)cj < (unsigned)D2D_GRID) atomicMax(&swep_i[ci * D2D_GRID + cj], w);
     }
     if (len > 0) d2d_waypoint_pos(P, e, cursor, wx, wy);
-    __syncthreads();
+    // ---- last_time_observed update (:95-97): visible cells (only possible inside the pose's window) -> 0, others += dt
+    int i0, i1, j0, j1;
+    d2d_ox_window(P, dx, i0, i1);
+    d2d_ox_window(P, dy, j0, j1);
     double *last = P.ox_last + (size_t)e * D2D_CELLS;
     for (int c = tid; c < D2D_CELLS; c += T) {
-        const bool vis = d2d_ox_visible(P, c, dx, dy, cs_s[P.n_yaw], sn_s[P.n_yaw]);
-        const double lt = vis ? 0.0 : (fresh ? 5.0 : last[c]) + 1.0 * P.dt;   // :95-97 (init 5.0, :49)
-        last[c] = lt;
-        const double sw = swep_i[c] >= 0 ? (double)swep_i[c] * P.dt : 0.0;
-        double r;
-        if (sw > 0.0 && sw <= 3.0 && lt >= 0.5) r = 1000000.0;       // :108-110
-        else if (sw > 3.0 && lt >= 0.5) r = 1000.0;
-        else r = (lt > 1.0) ? 1.0 : lt;
-        reward[c] = r;
+        const int i = c / D2D_GRID, j = c - i * D2D_GRID;
+        bool vis = false;
+        if (i >= i0 && i <= i1 && j >= j0 && j <= j1) vis = d2d_ox_visible(P, c, dx, dy, cs_s[ny], sn_s[ny]);
+        last[c] = vis ? 0.0 : (fresh ? 5.0 : last[c]) + 1.0 * P.dt;          // init 5.0 (:49)
     }
-    __syncthreads();
     if (len == 0) {                                                  // :117-118
         if (tid == 0) { actions_out[e] = 0.0; if (fresh) P.ox_fresh[e] = 1; }
         return;
     }
-    for (int k = 0; k < P.n_yaw; k++) {
-        for (int c = tid; c < D2D_CELLS; c += T)
-            prod[c] = d2d_ox_visible(P, c, wx, wy, cs_s[k], sn_s[k]) ? reward[c] : 0.0;
-        __syncthreads();
-        if (tid < prog->n_leaves) leaf[tid] = d2d_np_leaf_sum(prod + prog->leaf_off[tid], prog->leaf_len[tid]);
-        __syncthreads();
-        if (tid == 0) {
-            double st[16];
-            int sp = 0;
-            for (int o = 0; o < prog->n_ops; o++) {
-                const int op = prog->ops[o];
-                if (op >= 0) st[sp++] = leaf[op];
-                else { sp--; st[sp - 1] = st[sp - 1] + st[sp]; }
+    __syncthreads();
+    // ---- candidate scores (:120-125): np.sum(view_k * reward) over the 50x50 grid.  view_k is zero outside the
+    // window of the first waypoint, so only rows [r0, r1] are materialised; every other element of the product array
+    // is +0.0 and contributes nothing to NumPy's pairwise sum (x + 0.0 == x), whose tree order is kept.
+    int r0, r1, q0, q1;
+    d2d_ox_window(P, wx, r0, r1);
+    d2d_ox_window(P, wy, q0, q1);
+    if (r1 - r0 + 1 > D2D_OX_ROWS) r1 = r0 + D2D_OX_ROWS - 1;       // cannot happen for depth <= 9 cells
+    const int nrow = r1 - r0 + 1, span = nrow * D2D_GRID, base = r0 * D2D_GRID;
+    for (int o = tid; o < span; o += T) {
+        const int c = base + o;
+        const int i = c / D2D_GRID, j = c - i * D2D_GRID;
+        bool inwin = (j >= q0 && j <= q1);
+        double r = 0.0, num_x = 0.0, num_y = 0.0, den = 1.0;
+        bool zero_d = false;
+        if (inwin) {
+            const double x = (double)i * P.scale, y = (double)j * P.scale;
+            const double ex = wx - x, ey = wy - y;
+            const double d2 = ex * ex + ey * ey;
+            zero_d = d2 <= 0.0;
+            inwin = zero_d || d2 <= P.depth2;
+            if (inwin) {
+                const double lt = last[c];
+                const double sw = swep_i[c] >= 0 ? (double)swep_i[c] * P.dt : 0.0;
+                if (sw > 0.0 && sw <= 3.0 && lt >= 0.5) r = 1000000.0;       // :108-110
+                else if (sw > 3.0 && lt >= 0.5) r = 1000.0;
+                else r = (lt > 1.0) ? 1.0 : lt;
+                num_x = x - wx; num_y = y - wy; den = D2D_SQRT(d2);
             }
-            score[k] = 0.0 + st[0];
         }
-        __syncthreads();
+        for (int k = 0; k < ny; k++) {
+            bool vis = false;
+            if (inwin) vis = zero_d || d2d_ox_wedge(num_x * cs_s[k] + num_y * sn_s[k], den, P.ox_cos_thresh);
+            prod[(size_t)k * (D2D_OX_ROWS * D2D_GRID) + o] = vis ? r : 0.0;
+        }
     }
+    __syncthreads();
+    // leaves of NumPy's pairwise recursion that intersect [base, base + span); a leaf outside sums to +0.0
+    const int nl = prog->n_leaves;
+    for (int q = tid; q < ny * nl; q += T) {
+        const int k = q / nl, l = q - k * nl;
+        const int off = prog->leaf_off[l], n = prog->leaf_len[l];
+        double v = 0.0;
+        if (off + n > base && off < base + span) {
+            // elements of the leaf outside the materialised rows are zeros: build the 8-accumulator sum in NumPy's order
+            const double *a = prod + (size_t)k * (D2D_OX_ROWS * D2D_GRID) - base;     // a[c] valid for c in [base, base+span)
+            const int lo = base, hi = base + span;
+            if (n < 8) {
+                for (int i = 0; i < n; i++) { const int c = off + i; v += (c >= lo && c < hi) ? a[c] : 0.0; }
+            } else {
+                double r8[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { const int c = off + u; r8[u] = (c >= lo && c < hi) ? a[c] : 0.0; }
+                int i;
+                for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const int c = off + i + u; r8[u] += (c >= lo && c < hi) ? a[c] : 0.0; }
+                }
+                v = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+                for (; i < n; i++) { const int c = off + i; v += (c >= lo && c < hi) ? a[c] : 0.0; }
+            }
+        }
+        leaf[k * D2D_OX_MAX_LEAVES + l] = v;
+    }
+    __syncthreads();
+    if (tid < ny) {
+        double st[16];
+        int sp = 0;
+        for (int o = 0; o < prog->n_ops; o++) {
+            const int op = prog->ops[o];
+            if (op >= 0) st[sp++] = leaf[tid * D2D_OX_MAX_LEAVES + op];
+            else { sp--; st[sp - 1] = st[sp - 1] + st[sp]; }
+        }
+        score[tid] = 0.0 + st[0];
+    }
+    __syncthreads();
     if (tid == 0) {
         double max_reward = 0.0;
         int best = 0;
-        for (int k = 0; k < P.n_yaw; k++)
+        for (int k = 0; k < ny; k++)
             if (max_reward < score[k]) { best = k; max_reward = score[k]; }   // strict <, first maximum (:123-125)
         actions_out[e] = P.tab->v_yaw_space[best] / P.max_yaw_speed;
     }

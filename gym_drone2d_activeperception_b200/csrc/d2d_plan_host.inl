@@ -26,12 +26,12 @@ static int step_primitive(d2d_handle *h, const double *actions, cudaStream_t st)
         static bool attr_done[64] = {false};
         const int dev = h->cfg.device;
         if (!attr_done[dev & 63]) {
-            cudaError_t ce = cudaFuncSetAttribute(d2d_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            cudaError_t ce = cudaFuncSetAttribute(d2d_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (ce != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute(plan): ") + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
             attr_done[dev & 63] = true;
         }
         const int grid = h->B < D2D_PLAN_SLOTS ? h->B : D2D_PLAN_SLOTS;
-        d2d_plan_kernel<<<grid, D2D_PLAN_THREADS, h->smem_plan, st>>>(h->P);
+        d2d_plan_kernel<<<grid, D2D_PLAN_THREADS2, h->smem_plan, st>>>(h->P);
         h->launches++;
     }
     {
@@ -47,7 +47,15 @@ extern "C" int d2d_plan_oxford(d2d_handle *h, double *actions_out_dev, void *str
     if (!h->cfg.oxford) { h->err = "d2d_plan_oxford: handle was created with oxford = 0"; return D2D_ERR_STATE; }
     if (!h->world_set) { h->err = "d2d_plan_oxford before d2d_set_world"; return D2D_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    d2d_oxford_kernel<<<h->B, 256, 0, (cudaStream_t)stream>>>(h->P, h->ox_prog, actions_out_dev);
+    {
+        static bool attr_done[64] = {false};
+        const int dev = h->cfg.device;
+        if (!attr_done[dev & 63]) {
+            CUDA_TRY(h, cudaFuncSetAttribute(d2d_oxford_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_done[dev & 63] = true;
+        }
+    }
+    d2d_oxford_kernel<<<h->B, D2D_OX_THREADS, d2d_oxford_smem_bytes(h->cfg.n_yaw), (cudaStream_t)stream>>>(h->P, h->ox_prog, actions_out_dev);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return D2D_OK;

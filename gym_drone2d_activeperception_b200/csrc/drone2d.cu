@@ -321,7 +321,7 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
         if (ce != cudaSuccess) { g_create_err = std::string("cudaMemcpy oxford program: ") + cudaGetErrorString(ce); cudaFree(h->arena); delete h; return D2D_ERR_CUDA; }
     }
     h->smem_pre = d2d_pre_smem_bytes(E, NP, h->HW);
-    h->smem_plan = D2D_BELIEF_STRIDE + (size_t)NP * 5 * 8 + 4 * 8 + 4 * 4 + 8 * 4 + 4 * 4 + 64;
+    h->smem_plan = d2d_plan_smem_bytes(NP, cfg->n_u, cfg->n_samp);
     if (cfg->planner == D2D_PLANNER_PRIMITIVE && h->smem_pre > 227 * 1024) {
         g_create_err = "shared memory per block exceeds 227 KB (Primitive path; lower envs_per_block)";
         cudaFree(h->arena); delete h; return D2D_ERR_INVALID;
