@@ -191,3 +191,67 @@ def test_step_host_buffers_and_explicit_reset():
     assert int(obs["local_map"].sum()) == 0 and float(obs["yaw_angle"][0, 0]) == 270.0
     assert int(env.buffer("steps").sum()) == 0 and int(env.buffer("belief").sum()) == 0
     env.close()
+
+
+@pytest.mark.parametrize("case", [
+    dict(name="no_agents", kw=dict(agent_number=0), B=6, steps=40),
+    dict(name="pillars", kw=dict(agent_number=6, pillar_number=4, agent_radius=10, agent_max_speed=40), B=10, steps=60),
+    dict(name="wide_fov_dense_rays", kw=dict(agent_number=8, drone_view_range=180), B=6, steps=40, strip_width=5),
+    dict(name="full_circle_250_rays", kw=dict(agent_number=8, drone_view_range=360), B=5, steps=30, strip_width=2),
+    dict(name="random_radius", kw=dict(agent_number=12, agent_radius=-1, agent_max_speed=60), B=9, steps=60),
+    dict(name="many_agents_radius5", kw=dict(agent_number=64, agent_radius=5, agent_max_speed=30), B=5, steps=40),
+], ids=lambda c: c["name"])
+def test_cuda_matches_oracle_edge_configs(case):
+    """Edge configurations of the reference's Params: empty agent list, static pillars (per-env ground truth),
+    wider FOV and denser ray fans (BASELINE config 5 sweeps strip_width 10/5/2 and view_range 90/180/360),
+    `agent_radius == -1` (uniform 5..15 radii, drone_v2.py:31), crowded worlds."""
+    import oracle
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200.world import generate_worlds
+    B, steps = case["B"], case["steps"]
+    sw = case.get("strip_width", 10)
+    p = Params(debug=False, planner="NoMove", map_id=900, **case["kw"])
+    worlds = generate_worlds(p, 900 + np.arange(B))
+    env = _env(p, B, worlds, auto_reset=False, strip_width=sw)
+    n = env.num_agents
+    rng = np.random.RandomState(11)
+    poses = worlds["drone_pose"].copy()
+    poses[1:, 0] = rng.uniform(15, 485, B - 1)
+    poses[1:, 1] = rng.uniform(15, 485, B - 1)
+    poses[1:, 2] = rng.uniform(0, 360, B - 1)
+    env.set_drone_pose(poses)
+    op = util.oracle_params(p)
+    op.n_rays = int(np.ceil(p.map_size[0] / sw))
+    oracles = [oracle.OracleEnv(op, worlds["agent_pos"][i], worlds["agent_pref"][i], worlds["agent_radius"][i],
+                                worlds["gt_grid"][i], worlds["tracker_radius"][i], drone=poses[i], targets=p.target_list)
+               for i in range(B)]
+    table = util.action_table()
+    for t in range(steps):
+        acts = table[rng.randint(0, 6, B)]
+        env.step(torch.as_tensor(acts, device="cuda:0"))
+        for i, e in enumerate(oracles):
+            e.step(float(acts[i]))
+        h = _host(env)
+        for i, e in enumerate(oracles):
+            _cmp_env_to_oracle(h, i, e, n, t, case["name"])
+    for e in oracles:
+        e.close()
+    env.close()
+
+
+def test_error_paths_are_loud():
+    """Unsupported configurations and misuse raise instead of silently falling back."""
+    from gym_drone2d_activeperception_b200 import _native
+    from gym_drone2d_activeperception_b200.params import Params
+    with pytest.raises(_native.Drone2DNativeError):
+        _env(Params(debug=False, planner="NoMove", var_cam=1), 4, None)
+    with pytest.raises(ValueError):
+        _env(Params(debug=False, planner="MPC"), 4, None)
+    with pytest.raises(ValueError):
+        _env(Params(debug=False, planner="NoMove", motion_profile="RVO"), 4, None)
+    env = _env(Params(debug=False, planner="NoMove", agent_number=3), 4, None, oxford=False)
+    with pytest.raises(_native.Drone2DNativeError):
+        env.plan_oxford()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(3, dtype=torch.float64, device="cuda:0"))
+    env.close()

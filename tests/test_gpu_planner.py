@@ -114,3 +114,32 @@ def test_cuda_matches_oracle_primitive_oxford_with_auto_reset(cfg):
     for e in oracles:
         e.close()
     env.close()
+
+
+def test_primitive_multiple_targets_and_no_agents():
+    """target_list with two goals (state machine GOAL_REACHED -> WAIT_FOR_GOAL -> PLANNING, drone_v2.py:156-163) and an
+    empty agent list; scripted gaze; oracle comparison until the episode ends."""
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200.world import generate_worlds
+    B = 5
+    p = Params(debug=False, planner="Primitive", map_id=70, agent_number=0, target_list=[[200, 120], [60, 300]])
+    worlds = generate_worlds(p, 70 + np.arange(B))
+    env = _env(p, B, worlds, auto_reset=False, oxford=False)
+    oracles = [util.oracle_env_from_world(p, worlds, i) for i in range(B)]
+    table = util.action_table()
+    rng = np.random.RandomState(5)
+    done_at = None
+    for t in range(400):
+        acts = table[rng.randint(0, 6, B)]
+        env.step(torch.as_tensor(acts, device="cuda:0"))
+        for i, e in enumerate(oracles):
+            e.step(float(acts[i]))
+        h = _host(env)
+        for i, e in enumerate(oracles):
+            _cmp_env_to_oracle(h, i, e, 0, t, "targets", trackers=False)
+            assert h["traj_nseg"][i] * 20 - h["traj_cursor"][i] == e.c.traj_len
+        if oracles[0].c.done:
+            done_at = t
+            break
+    assert done_at is not None and oracles[0].c.state_machine == 1 and oracles[0].c.target_cursor == 2
+    env.close()
