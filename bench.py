@@ -227,7 +227,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     B = args.envs or cfg["envs"]
     pk = cfg["params"]
-    unique = args.unique_worlds or min(B, 8192)
+    unique = args.unique_worlds or min(B, 16384)
     # worlds are generated before CUDA is touched (fork-based pool)
     seeds = pk["map_id"] + rank * B + np.arange(B)
     t0 = time.perf_counter()

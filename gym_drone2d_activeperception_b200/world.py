@@ -59,24 +59,38 @@ def generate_world(params, seed, static_map=None):
     # random disc agents (drone_v2.py:28-47)
     pos, pref, rad, trk_rad = [], [], [], []
     n_rand = params.agent_number
+    P_arr = np.empty((max(n_rand, 1), 2), dtype=np.float64)     # accepted positions / radii for the vectorised check
+    R_arr = np.empty(max(n_rand, 1), dtype=np.float64)
+    headings = [-params.agent_max_speed * np.array([np.cos(2 * np.pi * k / n_rand), np.sin(2 * np.pi * k / n_rand)])
+                for k in range(n_rand)]
     while len(pos) < n_rand:
         p = np.array((rnd.uniform(20, W - 20), rnd.uniform(20, H - 20)))
         r = rnd.uniform(5, 15) if params.agent_radius == -1 else rnd.uniform(params.agent_radius - 2,
                                                                                   params.agent_radius + 2)
         k = len(pos)
-        pv = -params.agent_max_speed * np.array([np.cos(2 * np.pi * k / n_rand), np.sin(2 * np.pi * k / n_rand)])
         free = True
-        for q, rq in zip(pos, rad):
-            if norm(q - p) <= rq + r:
+        if k:
+            # norm(q - p) <= rq + r for every accepted agent (drone_v2.py:36-38).  Decided by a vectorised distance;
+            # only pairs within 1e-12 relative of the threshold are re-evaluated with np.linalg.norm itself.
+            d = P_arr[:k] - p
+            approx = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])
+            thr = R_arr[:k] + r
+            if (approx <= thr * (1 - 1e-12)).any():
                 free = False
+            else:
+                for j in np.nonzero(np.abs(approx - thr) <= thr * 1e-12)[0].tolist():
+                    if norm(P_arr[j] - p) <= R_arr[j] + r:
+                        free = False
         for ob in obstacles:
             if norm(np.array([ob[0], ob[1]]) - p) <= ob[2] + r + 10:
                 free = False
         if norm(p - drone_xy) <= params.drone_radius + 70:
             free = False
         if free:
+            P_arr[k] = p
+            R_arr[k] = r
             pos.append(p)
-            pref.append(pv)
+            pref.append(headings[k])
             rad.append(r)
             trk_rad.append(r)           # drone_v2.py:46
 
@@ -86,17 +100,23 @@ def generate_world(params, seed, static_map=None):
     direction = nrs.rand(100) * 2 * np.pi          # same stream as 100 sequential np.random.rand() calls
     vels = np.stack([vel * np.cos(direction), vel * np.sin(direction)], axis=1)
     xs, ys = np.nonzero(smap)                      # row-major order == the reference's nested x, y loops
-    for x, y in zip(xs.tolist(), ys.tolist()):
-        pos.append(np.array([5 + x * 10, 5 + y * 10], dtype=np.float64))
-        pref.append(vels[int(smap[x][y])].copy())
-        rad.append(5.0)
-        trk_rad.append(float(params.agent_radius))  # KalmanFilter.__init__ default, utils.py:184
-
-    n = len(pos)
-    agent_pos = np.array(pos, dtype=np.float64).reshape(n, 2)
-    agent_pref = np.array(pref, dtype=np.float64).reshape(n, 2)
-    agent_radius = np.array(rad, dtype=np.float64).reshape(n)
-    tracker_radius = np.array(trk_rad, dtype=np.float64).reshape(n)
+    n_rnd, n_map = len(pos), len(xs)
+    n = n_rnd + n_map
+    agent_pos = np.empty((n, 2), dtype=np.float64)
+    agent_pref = np.empty((n, 2), dtype=np.float64)
+    agent_radius = np.empty(n, dtype=np.float64)
+    tracker_radius = np.empty(n, dtype=np.float64)
+    if n_rnd:
+        agent_pos[:n_rnd] = np.array(pos, dtype=np.float64).reshape(n_rnd, 2)
+        agent_pref[:n_rnd] = np.array(pref, dtype=np.float64).reshape(n_rnd, 2)
+        agent_radius[:n_rnd] = rad
+        tracker_radius[:n_rnd] = trk_rad
+    if n_map:
+        agent_pos[n_rnd:, 0] = 5 + xs * 10         # int64 cell centres (become float after the first step)
+        agent_pos[n_rnd:, 1] = 5 + ys * 10
+        agent_pref[n_rnd:] = vels[smap[xs, ys].astype(np.int64)]
+        agent_radius[n_rnd:] = 5.0
+        tracker_radius[n_rnd:] = float(params.agent_radius)   # KalmanFilter.__init__ default, utils.py:184
 
     # ground truth grid (utils.py:495-525).  Only cells == 1 matter downstream (utils.py:666,770).  NB: a cell
     # whose CENTRE lies inside an agent disc is overwritten with DYNAMIC_OCCUPIED even if it was a border / pillar
@@ -113,18 +133,18 @@ def generate_world(params, seed, static_map=None):
             for j in range(max(0, int((ob[1] - ob[2]) // scale) - 1), min(gh, int((ob[1] + ob[2]) // scale) + 2)):
                 if norm(np.array([scale * (i + 0.5), scale * (j + 0.5)]) - np.array([ob[0], ob[1]])) <= ob[2]:
                     gt[i, j] = 1
-    occ_i, occ_j = np.nonzero(gt == 1)
-    if n:
-        for i, j in zip(occ_i.tolist(), occ_j.tolist()):
-            cx, cy = scale * (i + 0.5), scale * (j + 0.5)
-            # cheap reject, then the reference's scalar expression (`**2` is libm pow there, utils.py:523)
-            near = np.nonzero((np.abs(agent_pos[:, 0] - cx) <= agent_radius + 1) &
-                              (np.abs(agent_pos[:, 1] - cy) <= agent_radius + 1))[0]
-            for k in near.tolist():
-                ax, ay, r = float(agent_pos[k, 0]), float(agent_pos[k, 1]), float(agent_radius[k])
-                if (cx - ax) ** 2 + (cy - ay) ** 2 <= r ** 2:
-                    gt[i, j] = 2
-                    break
+    occ = np.argwhere(gt == 1)
+    if n and len(occ):
+        cxs, cys = scale * (occ[:, 0] + 0.5), scale * (occ[:, 1] + 0.5)
+        # cheap vectorised reject, then the reference's scalar expression on the few candidate pairs
+        # (`**2` on Python floats / NumPy scalars is libm pow there, utils.py:523)
+        near = (np.abs(agent_pos[None, :, 0] - cxs[:, None]) <= agent_radius[None, :] + 1) & \
+               (np.abs(agent_pos[None, :, 1] - cys[:, None]) <= agent_radius[None, :] + 1)
+        for m, k in np.argwhere(near).tolist():
+            cx, cy = float(cxs[m]), float(cys[m])
+            ax, ay, r = float(agent_pos[k, 0]), float(agent_pos[k, 1]), float(agent_radius[k])
+            if (cx - ax) ** 2 + (cy - ay) ** 2 <= r ** 2:
+                gt[occ[m, 0], occ[m, 1]] = 2
     yaw0 = -90 % 360                                # Drone2D(init_yaw=-90): yaw = init_yaw % 360 (utils.py:718)
     return dict(agent_pos=agent_pos, agent_pref=agent_pref, agent_radius=agent_radius, tracker_radius=tracker_radius,
                 gt_grid=gt, drone_pose=np.array([float(dx), float(dy), float(yaw0)]),

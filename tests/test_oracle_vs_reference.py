@@ -44,3 +44,23 @@ def test_nomove_live(seed, smap):
 
 def test_full_episode_live():
     _compare(400, policy="Oxford", planner="Primitive", map_id=6, agent_number=12)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(static_map="maps/empty_map.npy", agent_number=10, agent_radius=15, agent_max_speed=20),
+    dict(static_map="maps/obstacle_map.npy", agent_number=10, agent_radius=10, agent_max_speed=20),
+    dict(static_map="maps/random_map_0.npy", agent_number=20, agent_radius=15, agent_max_speed=40),
+    dict(static_map="maps/shaped_obstacle_map.npy", agent_number=50, agent_radius=10, agent_max_speed=40),
+    dict(static_map="maps/empty_map.npy", agent_number=12, agent_radius=-1, agent_max_speed=30, pillar_number=3),
+], ids=["empty", "obstacle", "random0", "shaped50", "pillars_randradius"])
+def test_world_generation_live(kw):
+    """Host world generator (product code) vs the reference's __init__ on many seeds."""
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200.world import generate_world
+    for seed in range(200, 212):
+        env, params = ref_runner.make_env(planner="NoMove", map_id=seed, **kw)
+        ws = ref_runner.world_snapshot(env)
+        w = generate_world(Params(debug=False, planner="NoMove", map_id=seed, **kw), seed)
+        assert np.array_equal(w["agent_pos"], ws["agent_pos0"]) and np.array_equal(w["agent_pref"], ws["agent_pref0"])
+        assert np.array_equal(w["agent_radius"], ws["agent_radius"]) and np.array_equal(w["tracker_radius"], ws["tracker_radius"])
+        assert np.array_equal(w["gt_grid"] == 1, ws["gt_grid"] == 1), seed
