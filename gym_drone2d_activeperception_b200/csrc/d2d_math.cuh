@@ -19,8 +19,10 @@
 
 #if defined(__CUDACC__)
 #define D2D_HD __host__ __device__ __forceinline__
+#define D2D_HD_NOINLINE __host__ __device__ __noinline__     // one shared copy: keeps the kernels inside the I-cache
 #else
 #define D2D_HD static inline
+#define D2D_HD_NOINLINE static
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -49,10 +51,11 @@ D2D_HD int d2d_cell(double x, double scale, double inv_scale) {
 
 // Python `x % w` for w > 0 (float_rem): fmod then sign fix-up.  fmod is exact, and for |x| < 2w it is |x| or |x| - w
 // (an exact subtraction, Sterbenz), so the library fmod is only needed outside that range.
+D2D_HD_NOINLINE double d2d_fmod_slow(double ax, double w) { return fmod(ax, w); }
 D2D_HD double d2d_fmod_pos(double ax, double w) {   // fmod(ax, w) for ax >= 0, w > 0
     if (ax < w) return ax;
     if (ax < 2.0 * w) return ax - w;
-    return fmod(ax, w);
+    return d2d_fmod_slow(ax, w);
 }
 D2D_HD double d2d_pymod(double x, double w) {
     double m = (x < 0) ? -d2d_fmod_pos(-x, w) : d2d_fmod_pos(x, w);
@@ -64,7 +67,8 @@ D2D_HD double d2d_pymod(double x, double w) {
     return m;
 }
 
-D2D_HD double d2d_norm2(double x, double y) { return D2D_SQRT(D2D_FMA(y, y, x * x)); }
+D2D_HD double d2d_sqrt(double v) { return D2D_SQRT(v); }
+D2D_HD double d2d_norm2(double x, double y) { return d2d_sqrt(D2D_FMA(y, y, x * x)); }
 
 // ------------------------------------------------------------------------------------------------ double-double
 struct d2d_dd {
@@ -235,7 +239,7 @@ D2D_HD void d2d_sincos_small(d2d_dd d, d2d_dd *s, d2d_dd *c) {
 }
 
 // sin(a), cos(a) for |a| < 1e5, each rounded to nearest from a double-double
-D2D_HD void d2d_sincos(double a, double *sn, double *cs) {
+D2D_HD_NOINLINE void d2d_sincos(double a, double *sn, double *cs) {
     int quad;
     d2d_dd r = d2d_rem_pio2(a, &quad);
     const bool neg = r.h < 0;

@@ -57,6 +57,7 @@ __device__ __forceinline__ bool d2d_is_free(const DevP &P, const uint8_t *bel, d
 
 // gathers the env's active trackers into shared memory; returns via *nact (block must sync afterwards)
 __device__ __forceinline__ void d2d_gather_trackers(const DevP &P, int e, double *trk, int *nact, int tid, int T) {
+#pragma unroll 1
     for (int k = tid; k < P.N; k += T) {
         const size_t g = (size_t)e * P.NP + k;
         if (P.trk_active[g]) {
@@ -150,6 +151,170 @@ d2d_step_pre_kernel(const DevP P) {
         P.tmp_act_cnt[e] = s.act_cnt; P.tmp_act_ts[e] = s.act_ts;
         d2d_store_env_scalars(P, s, e);
         P.done[e] = 0;   // consumed by the lazy reset above; the post kernel writes this step's verdict
+    }
+}
+
+// ------------------------------------------------------------------------------------------ warp-per-env Primitive step
+// One warp per env.  Everything up to the planner verdict runs as in the fused kernel; an env whose trajectory is
+// still valid (the vast majority) then finishes its step right here -- step_pos / step_yaw / is_collide / flags /
+// observation -- with the belief grid still in shared memory.  Only envs that need a plan are deferred: they are
+// appended to the compacted list for d2d_plan_kernel and completed by d2d_step_post_list_kernel.
+// The cells changed by this step's rays are recorded, so when the drone's cell (the window origin) is unchanged the
+// observation tensor is patched instead of rewritten.
+__host__ __device__ inline size_t d2d_prim_warp_extra(int NP) { return (size_t)NP * 5 * 8 + D2D_CHG_CAP * 4 + 32; }
+
+__device__ D2D_COLD void d2d_finish_env_warp(const DevP &P, const BlockCtx &c, EnvS &s, int e, int lane,
+                                                    double action, bool success, bool agents_in_smem, int nchg,
+                                                    const uint32_t *chg, bool allow_patch) {
+    if (lane == 0) d2d_leader_finish(P, s, c.gt, e, action, success);
+    __syncwarp();
+    // Drone2D.is_collide (utils.py:764-778) against the drone's NEW position
+    bool hit = false;
+#pragma unroll 1
+    for (int k = lane; k < P.N; k += 32) {
+        const size_t g = (size_t)e * P.NP + k;
+        double ax, ay;
+        if (agents_in_smem) { ax = c.sx[k]; ay = c.sy[k]; }
+        else { const double2 q = P.apos[g]; ax = q.x; ay = q.y; }
+        if (d2d_norm2(ax - s.px, ay - s.py) < P.arad[g] + P.drone_r) hit = true;
+    }
+    const bool any_hit = __any_sync(0xffffffffu, hit);
+    const int shit = __any_sync(0xffffffffu, lane < 5 ? d2d_static_probe(P, c.gt, s.px, s.py, lane) : 0);
+    const int oix = P.obs_ix[e], oiy = P.obs_iy[e];
+    if (lane == 0) {
+        s.coll_agent = any_hit ? 1 : 0;
+        d2d_leader_flags(P, s, c.gt, e, shit);
+        d2d_store_env_scalars(P, s, e);
+        atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], 1ull);
+    }
+    __syncwarp();
+    if (allow_patch && !s.reset && oix == s.ix && oiy == s.iy && nchg <= D2D_CHG_CAP) {
+        uint8_t *out = P.local_map + (size_t)e * D2D_LOCAL_CELLS;
+#pragma unroll 1
+        for (int q = lane; q < nchg; q += 32) {
+            const int cell = (int)(chg[q] & 0xFFFFu), v = (int)(chg[q] >> 16);
+            const int u = cell / D2D_GRID - (s.ix - 16), w = cell % D2D_GRID - (s.iy - 16);
+            if ((unsigned)u < (unsigned)D2D_LOCAL && (unsigned)w < (unsigned)D2D_LOCAL) out[u * D2D_LOCAL + w] = (uint8_t)v;
+        }
+    } else {
+        d2d_obs_env_warp(P, c.belief, s.ix, s.iy, e, lane);
+        if (lane == 0) { P.obs_ix[e] = s.ix; P.obs_iy[e] = s.iy; }
+    }
+    if (s.done_now) {
+        int cnt = 0;
+#pragma unroll 1
+        for (int o = lane; o < D2D_CELLS; o += 32) cnt += (c.belief[o] != 0);
+        for (int off = 16; off > 0; off >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+        if (lane == 0 && cnt) atomicAdd(&P.stats[D2D_STAT_GRID_DISCOVERED], (unsigned long long)cnt);
+    }
+}
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(const DevP P,
+                                                                               const double *__restrict__ actions) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int e = blockIdx.x * WPB + wid;
+    if (e >= P.B) return;
+    unsigned char *slice = smem + (size_t)wid * d2d_warp_slice_bytes(P.NP, P.HW, d2d_prim_warp_extra(P.NP));
+    const BlockCtx c = d2d_carve(slice, 1, P.NP, P.HW);
+    double *trk = (double *)(slice + d2d_step_smem_bytes(1, P.NP, P.HW));   // [NP][5]
+    uint32_t *chg = (uint32_t *)(trk + (size_t)P.NP * 5);                  // [D2D_CHG_CAP]
+    int *cnt = (int *)(chg + D2D_CHG_CAP);                                 // [0] nact, [1] nchg
+    EnvS &s = c.S[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.plan_list[P.B + 1 + ((P.step_parity + 1) & 1)] = 0;   // next step's counter
+
+    if (lane == 0) {
+        d2d_mbar_init(c.mbar, 1);
+        c.misc[0] = 0;
+        d2d_load_env_scalars(P, s, e);
+        c.misc[1] = s.reset;
+        cnt[0] = 0; cnt[1] = 0;
+    }
+#pragma unroll 1
+    for (int w = lane; w < P.HW; w += 32) c.hitw[w] = 0u;
+    __syncwarp();
+    if (lane == 0) d2d_issue_bulk(P, c, e, 1, true);
+    d2d_reset_arrays(P, c, e, 1, lane, 32);
+    d2d_phase_agents<false>(P, c, e, 1, lane, 32);
+    if (lane == 0) d2d_leader_begin(P, s);
+    __syncwarp();
+    RayOut ro;
+    ro.bel_s = c.belief; ro.bel_g = P.belief + (size_t)e * D2D_BELIEF_STRIDE;
+    ro.obs = nullptr; ro.wi = 0; ro.wj = 0; ro.chg = chg; ro.nchg = &cnt[1];
+    d2d_mbar_wait(c.mbar, 0);
+    d2d_phase_rays_warp<false>(P, c, ro, lane);
+    __syncwarp();
+    d2d_phase_trackers(P, c, e, 1, lane, 32);
+    __syncwarp();
+    // ---- Primitive.replan_check (traj_planner.py:220-233)
+    d2d_gather_trackers(P, e, trk, &cnt[0], lane, 32);
+    __syncwarp();
+    const int na = cnt[0];
+    const int len = s.nseg * P.n_way - s.cursor;
+    bool hit = false;
+#pragma unroll 1
+    for (int w = lane; w < len && !hit; w += 32) {
+        double x, y;
+        d2d_waypoint_pos(P, e, s.cursor + w, x, y);
+        const double ti = (double)w * P.dt;
+        const int ci = d2d_cell(x, P.scale, P.inv_scale), cj = d2d_cell(y, P.scale, P.inv_scale);
+        if ((unsigned)ci < (unsigned)D2D_GRID && (unsigned)cj < (unsigned)D2D_GRID)
+            if (c.belief[ci * D2D_GRID + cj] == 1 && (uint8_t)ti > 0) hit = true;        // uint8 swep_map (:222-224,230)
+#pragma unroll 1
+        for (int k = 0; k < na && !hit; k++) {
+            const double *m = trk + 5 * k;
+            const double ex = m[0] + ti * m[2], ey = m[1] + ti * m[3];
+            if (d2d_norm2(ex - x, ey - y) <= P.drone_r + m[4]) hit = true;               // :225-229
+        }
+    }
+    const bool rep = __any_sync(0xffffffffu, hit);
+    __syncwarp();
+    if (lane == 0) {
+        if (rep) { s.nseg = 0; s.cursor = 0; atomicAdd(&P.stats[D2D_STAT_REPLANS], 1ull); }   // trajectory.clear()
+        s.bufc += s.arch_cnt; s.bufts += s.arch_ts; s.tracked += s.newly;
+        s.arch_cnt = 0; s.arch_ts = 0; s.newly = 0;
+        P.replan[e] = rep ? 1 : 0;
+        P.plan_ok[e] = 1;
+    }
+    __syncwarp();
+    const bool need = (s.nseg * P.n_way - s.cursor) == 0;
+    if (!need) {
+        if (lane == 0) P.need_plan[e] = 0;
+        d2d_finish_env_warp(P, c, s, e, lane, actions[e], true, true, cnt[1], chg, true);
+    } else if (lane == 0) {
+        P.need_plan[e] = 1;
+        const int slot = atomicAdd(&P.plan_list[P.B + 1 + (P.step_parity & 1)], 1);
+        P.plan_list[slot] = e;
+        P.tmp_act_cnt[e] = s.act_cnt; P.tmp_act_ts[e] = s.act_ts;
+        d2d_store_env_scalars(P, s, e);
+        P.done[e] = 0;
+    }
+}
+
+// completes the step of the envs that went through d2d_plan_kernel (one warp per list entry, grid-stride)
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) d2d_step_post_list_kernel(const DevP P, const double *__restrict__ actions) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int count = min(P.plan_list[P.B + 1 + (P.step_parity & 1)], P.B);
+    const BlockCtx c = d2d_carve(smem + (size_t)wid * d2d_warp_slice_bytes(1, 1, 0), 1, 1, 1);
+    EnvS &s = c.S[0];
+    uint32_t phase = 0;
+    if (lane == 0) d2d_mbar_init(c.mbar, 1);
+    __syncwarp();
+    for (int li = blockIdx.x * WPB + wid; li < count; li += gridDim.x * WPB) {
+        const int e = P.plan_list[li];
+        if (lane == 0) {
+            d2d_load_env_scalars(P, s, e);       // done == 0 and pending_reset == 0 here: plain reload
+            s.act_cnt = P.tmp_act_cnt[e]; s.act_ts = P.tmp_act_ts[e];
+        }
+        __syncwarp();
+        if (lane == 0) d2d_issue_bulk(P, c, e, 1, true);
+        d2d_mbar_wait(c.mbar, phase);
+        phase ^= 1u;
+        d2d_finish_env_warp(P, c, s, e, lane, actions[e], P.plan_ok[e] != 0, false, 0, nullptr, false);
+        __syncwarp();
     }
 }
 
@@ -304,7 +469,7 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
         h.open_total = w.open_total; h.cost = w.cost; h.hkeys32 = nullptr; h.hvals16 = nullptr;
         h.hkeys64 = w.hkeys; h.hvals32 = w.hvals; h.hcap = w.hcap;
     }
-    const int count = min(P.plan_list[P.B], P.B);
+    const int count = min(P.plan_list[P.B + (P.use_parity ? 1 + (P.step_parity & 1) : 0)], P.B);
 
     for (int li = blockIdx.x; li < count; li += gridDim.x) {
         const int e = P.plan_list[li];
@@ -575,20 +740,27 @@ __device__ __forceinline__ void d2d_ox_window(const DevP &P, double dx, int &lo,
 }
 
 #define D2D_OX_ROWS 21          // window rows (2 * depth / scale + slack) handled per pose
-#define D2D_OX_THREADS 256
-__host__ __device__ inline size_t d2d_oxford_smem_bytes(int n_yaw) {
-    return (size_t)n_yaw * D2D_OX_ROWS * D2D_GRID * 8 + (size_t)D2D_CELLS * 4 + (size_t)n_yaw * D2D_OX_MAX_LEAVES * 8 + 256;
-}
+#define D2D_OX_SPAN (D2D_OX_ROWS * D2D_GRID + 2 * 128)   // materialised flattened range, extended to whole leaves
+#define D2D_OX_WORDS ((D2D_OX_SPAN + 31) / 32)
+#define D2D_OX_THREADS 128
 
+// Oxford.plan (yaw_planner.py:81-127), one block per env.
+//  1. swep_map from the remaining waypoints (largest waypoint index per cell, later assignments win, :87-89)
+//  2. last_time_observed update over all 2500 cells (:95-97); only cells inside the pose's depth window can be visible
+//  3. candidate scores np.sum(view_k * reward) (:120-125): view_k vanishes outside the depth window of the first
+//     waypoint, so the reward map is materialised only for the flattened range of rows that window touches (extended to
+//     whole leaves of NumPy's pairwise recursion) and each candidate keeps a visibility BITMASK over that range.  Leaf
+//     sums run in NumPy's order -- 8 strided accumulators (one lane each), combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
+//     then the tail -- and leaves outside the range are exactly +0.0 (x + 0.0 == x, so skipping them changes nothing).
 __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P, const OxProgram *__restrict__ prog,
                                                                     double *__restrict__ actions_out) {
-    extern __shared__ __align__(16) unsigned char oxsm[];
-    double *prod = (double *)oxsm;                                         // [n_yaw][D2D_OX_ROWS * 50] candidate products
-    int *swep_i = (int *)(prod + (size_t)P.n_yaw * D2D_OX_ROWS * D2D_GRID);   // [2500] last waypoint index per cell
-    double *leaf = (double *)(swep_i + D2D_CELLS);                          // [n_yaw][D2D_OX_MAX_LEAVES]
+    __shared__ double reward[D2D_OX_SPAN];
+    __shared__ uint32_t vmask[D2D_MAX_YAW][D2D_OX_WORDS];
+    __shared__ int swep_w[D2D_OX_SPAN];                 // largest waypoint index per cell of the range (-1: none)
+    __shared__ double leaf[D2D_MAX_YAW][D2D_OX_MAX_LEAVES];
     __shared__ double score[D2D_MAX_YAW];
     __shared__ double cs_s[D2D_MAX_YAW + 1], sn_s[D2D_MAX_YAW + 1];
-    const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
     if (e >= P.B) return;
     // an env that reported done and will be re-initialised by its next step is seen by the policy as freshly reset
     // (the reference builds a new env + policy per episode, experiment.py:27-34)
@@ -597,7 +769,6 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
     const double yaw = fresh ? P.pose0[2 * P.B + e] : P.drone_yaw[e];
     const int len = fresh ? 0 : P.traj_nseg[e] * P.n_way - P.traj_cursor[e], cursor = fresh ? 0 : P.traj_cursor[e];
     const int ny = P.n_yaw;
-    for (int c = tid; c < D2D_CELLS; c += T) swep_i[c] = -1;
     if (tid <= ny) {
         // candidate yaws: Drone2D(..., yaw_i) stores yaw_i % 360 (utils.py:718); entry n_yaw is the current pose
         const double y = (tid < ny) ? d2d_pymod(yaw + P.tab->v_yaw_space[tid] * P.dt, 360.0) : yaw;
@@ -605,94 +776,148 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         d2d_sincos(y * D2D_DEG2RAD, &sn, &cs);
         cs_s[tid] = cs; sn_s[tid] = -sn;    // vec_yaw = [cos, -sin] (yaw_planner.py:72)
     }
-    __syncthreads();
-    // swep_map[cell] = i*dt with later waypoints overwriting earlier ones -> keep the largest i (:87-89)
+    // range of the flattened grid that can carry non-zero products: rows of the first waypoint's depth window,
+    // extended to whole leaves
+    __shared__ int lrange[2];
     double wx = 0, wy = 0;
+    int r0 = 0, r1 = -1, q0 = 0, q1 = -1, lo = 0, hi = 0, l0 = 0, l1 = -1;
+    if (len > 0) {
+        d2d_waypoint_pos(P, e, cursor, wx, wy);
+        d2d_ox_window(P, wx, r0, r1);
+        d2d_ox_window(P, wy, q0, q1);
+        if (r1 - r0 + 1 > D2D_OX_ROWS) r1 = r0 + D2D_OX_ROWS - 1;       // cannot happen for depth <= 9 cells
+        if (tid < prog->n_leaves) {
+            const int b0 = r0 * D2D_GRID, b1 = (r1 + 1) * D2D_GRID - 1;
+            const int off = prog->leaf_off[tid], n = prog->leaf_len[tid];
+            if (b0 >= off && b0 < off + n) lrange[0] = tid;
+            if (b1 >= off && b1 < off + n) lrange[1] = tid;
+        }
+    }
+    __syncthreads();
+    if (len > 0) {
+        l0 = lrange[0]; l1 = lrange[1];
+        lo = prog->leaf_off[l0];
+        hi = prog->leaf_off[l1] + prog->leaf_len[l1];
+        for (int o = tid; o < hi - lo; o += T) swep_w[o] = -1;
+    }
+    __syncthreads();
     for (int w = tid; w < len; w += T) {
         double x, y;
         d2d_waypoint_pos(P, e, cursor + w, x, y);
         const int ci = d2d_cell(x, P.scale, P.inv_scale), cj = d2d_cell(y, P.scale, P.inv_scale);
-        if ((unsigned)ci < (unsigned)D2D_GRID && (unsigned)cj < (unsigned)D2D_GRID) atomicMax(&swep_i[ci * D2D_GRID + cj], w);
+        if ((unsigned)ci < (unsigned)D2D_GRID && (unsigned)cj < (unsigned)D2D_GRID) {
+            const int c = ci * D2D_GRID + cj;
+            if (c >= lo && c < hi) atomicMax(&swep_w[c - lo], w);
+        }
     }
-    if (len > 0) d2d_waypoint_pos(P, e, cursor, wx, wy);
     // ---- last_time_observed update (:95-97): visible cells (only possible inside the pose's window) -> 0, others += dt
     int i0, i1, j0, j1;
     d2d_ox_window(P, dx, i0, i1);
     d2d_ox_window(P, dy, j0, j1);
     double *last = P.ox_last + (size_t)e * D2D_CELLS;
-    for (int c = tid; c < D2D_CELLS; c += T) {
-        const int i = c / D2D_GRID, j = c - i * D2D_GRID;
-        bool vis = false;
-        if (i >= i0 && i <= i1 && j >= j0 && j <= j1) vis = d2d_ox_visible(P, c, dx, dy, cs_s[ny], sn_s[ny]);
-        last[c] = vis ? 0.0 : (fresh ? 5.0 : last[c]) + 1.0 * P.dt;          // init 5.0 (:49)
+    {
+        // pass A: every cell ages by dt (all loads first: one DRAM round trip instead of NL dependent ones)
+        constexpr int NL = (D2D_CELLS + D2D_OX_THREADS - 1) / D2D_OX_THREADS;
+        double lv[NL];
+#pragma unroll
+        for (int q = 0; q < NL; q++) {
+            const int c = tid + q * D2D_OX_THREADS;
+            lv[q] = (c < D2D_CELLS && !fresh) ? last[c] : 5.0;               // init 5.0 (:49)
+        }
+#pragma unroll
+        for (int q = 0; q < NL; q++) {
+            const int c = tid + q * D2D_OX_THREADS;
+            if (c < D2D_CELLS) last[c] = lv[q] + 1.0 * P.dt;
+        }
+        __syncthreads();
+        // pass B: the (few) visible cells, all inside the pose's depth window, are reset to 0
+        const int wi = i1 - i0 + 1, wj = j1 - j0 + 1;
+#pragma unroll 1
+        for (int q = tid; q < wi * wj; q += T) {
+            const int i = i0 + q / wj, j = j0 + q % wj;
+            const int c = i * D2D_GRID + j;
+            if (d2d_ox_visible(P, c, dx, dy, cs_s[ny], sn_s[ny])) last[c] = 0.0;
+        }
     }
     if (len == 0) {                                                  // :117-118
         if (tid == 0) { actions_out[e] = 0.0; if (fresh) P.ox_fresh[e] = 1; }
         return;
     }
     __syncthreads();
-    // ---- candidate scores (:120-125): np.sum(view_k * reward) over the 50x50 grid.  view_k is zero outside the
-    // window of the first waypoint, so only rows [r0, r1] are materialised; every other element of the product array
-    // is +0.0 and contributes nothing to NumPy's pairwise sum (x + 0.0 == x), whose tree order is kept.
-    int r0, r1, q0, q1;
-    d2d_ox_window(P, wx, r0, r1);
-    d2d_ox_window(P, wy, q0, q1);
-    if (r1 - r0 + 1 > D2D_OX_ROWS) r1 = r0 + D2D_OX_ROWS - 1;       // cannot happen for depth <= 9 cells
-    const int nrow = r1 - r0 + 1, span = nrow * D2D_GRID, base = r0 * D2D_GRID;
-    for (int o = tid; o < span; o += T) {
-        const int c = base + o;
-        const int i = c / D2D_GRID, j = c - i * D2D_GRID;
-        bool inwin = (j >= q0 && j <= q1);
-        double r = 0.0, num_x = 0.0, num_y = 0.0, den = 1.0;
-        bool zero_d = false;
-        if (inwin) {
-            const double x = (double)i * P.scale, y = (double)j * P.scale;
-            const double ex = wx - x, ey = wy - y;
-            const double d2 = ex * ex + ey * ey;
-            zero_d = d2 <= 0.0;
-            inwin = zero_d || d2 <= P.depth2;
-            if (inwin) {
-                const double lt = last[c];
-                const double sw = swep_i[c] >= 0 ? (double)swep_i[c] * P.dt : 0.0;
-                if (sw > 0.0 && sw <= 3.0 && lt >= 0.5) r = 1000000.0;       // :108-110
-                else if (sw > 3.0 && lt >= 0.5) r = 1000.0;
-                else r = (lt > 1.0) ? 1.0 : lt;
-                num_x = x - wx; num_y = y - wy; den = D2D_SQRT(d2);
+    // ---- reward (:108-110) and per-candidate visibility over [lo, hi)
+    const int span = hi - lo;
+#pragma unroll 1
+    for (int ob = 0; ob < span; ob += T) {          // whole warps stay converged for the ballots
+        const int o = ob + tid, c = lo + o;
+        bool inwin = false, zero_d = false;
+        double num_x = 0.0, num_y = 0.0, den = 1.0;
+        if (o < span) {
+            const int i = c / D2D_GRID, j = c - i * D2D_GRID;
+            if (i >= r0 && i <= r1 && j >= q0 && j <= q1) {
+                const double x = (double)i * P.scale, y = (double)j * P.scale;
+                const double ex = wx - x, ey = wy - y;
+                const double d2 = ex * ex + ey * ey;
+                zero_d = d2 <= 0.0;
+                inwin = zero_d || d2 <= P.depth2;
+                if (inwin) {
+                    const double lt = last[c];
+                    const double sw = swep_w[o] >= 0 ? (double)swep_w[o] * P.dt : 0.0;
+                    double r;
+                    if (sw > 0.0 && sw <= 3.0 && lt >= 0.5) r = 1000000.0;
+                    else if (sw > 3.0 && lt >= 0.5) r = 1000.0;
+                    else r = (lt > 1.0) ? 1.0 : lt;
+                    reward[o] = r;
+                    num_x = x - wx; num_y = y - wy; den = D2D_SQRT(d2);
+                }
             }
         }
+        const bool warp_any = __any_sync(0xffffffffu, inwin);
+#pragma unroll 1
         for (int k = 0; k < ny; k++) {
-            bool vis = false;
-            if (inwin) vis = zero_d || d2d_ox_wedge(num_x * cs_s[k] + num_y * sn_s[k], den, P.ox_cos_thresh);
-            prod[(size_t)k * (D2D_OX_ROWS * D2D_GRID) + o] = vis ? r : 0.0;
+            unsigned bal = 0u;
+            if (warp_any) {
+                bool vis = false;
+                if (inwin) vis = zero_d || d2d_ox_wedge(num_x * cs_s[k] + num_y * sn_s[k], den, P.ox_cos_thresh);
+                bal = __ballot_sync(0xffffffffu, vis);
+            }
+            if (lane == 0 && (ob + tid) < span + 31) vmask[k][(ob + tid) >> 5] = bal;
         }
     }
     __syncthreads();
-    // leaves of NumPy's pairwise recursion that intersect [base, base + span); a leaf outside sums to +0.0
-    const int nl = prog->n_leaves;
-    for (int q = tid; q < ny * nl; q += T) {
-        const int k = q / nl, l = q - k * nl;
+    // ---- leaf sums: task = (candidate, leaf, accumulator lane u in 0..7)
+    const int nleaf = l1 - l0 + 1;
+#pragma unroll 1
+    for (int qb = 0; qb < ny * nleaf * 8; qb += T) {
+        const int q = qb + tid;
+        const bool act = q < ny * nleaf * 8;
+        const int u = q & 7, kl = q >> 3;
+        const int k = act ? kl / nleaf : 0, l = l0 + (act ? kl - k * nleaf : 0);
         const int off = prog->leaf_off[l], n = prog->leaf_len[l];
-        double v = 0.0;
-        if (off + n > base && off < base + span) {
-            // elements of the leaf outside the materialised rows are zeros: build the 8-accumulator sum in NumPy's order
-            const double *a = prod + (size_t)k * (D2D_OX_ROWS * D2D_GRID) - base;     // a[c] valid for c in [base, base+span)
-            const int lo = base, hi = base + span;
+        double r = 0.0;
+        if (act) {
             if (n < 8) {
-                for (int i = 0; i < n; i++) { const int c = off + i; v += (c >= lo && c < hi) ? a[c] : 0.0; }
+                if (u == 0)
+                    for (int i = 0; i < n; i++) { const int o = off + i - lo; r += ((vmask[k][o >> 5] >> (o & 31)) & 1u) ? reward[o] : 0.0; }
             } else {
-                double r8[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) { const int c = off + u; r8[u] = (c >= lo && c < hi) ? a[c] : 0.0; }
-                int i;
-                for (i = 8; i < n - (n % 8); i += 8) {
-#pragma unroll
-                    for (int u = 0; u < 8; u++) { const int c = off + i + u; r8[u] += (c >= lo && c < hi) ? a[c] : 0.0; }
+                { const int o = off + u - lo; r = ((vmask[k][o >> 5] >> (o & 31)) & 1u) ? reward[o] : 0.0; }
+                for (int i = 8; i < n - (n % 8); i += 8) {
+                    const int o = off + i + u - lo;
+                    if ((vmask[k][o >> 5] >> (o & 31)) & 1u) r += reward[o];      // adding +0.0 is the identity
                 }
-                v = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
-                for (; i < n; i++) { const int c = off + i; v += (c >= lo && c < hi) ? a[c] : 0.0; }
             }
         }
-        leaf[k * D2D_OX_MAX_LEAVES + l] = v;
+        // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) across the 8 lanes of the group
+        double t = r + __shfl_down_sync(0xffffffffu, r, 1);      // lanes 0,2,4,6 hold pair sums
+        double t2 = t + __shfl_down_sync(0xffffffffu, t, 2);     // lanes 0,4 hold quad sums
+        double res = t2 + __shfl_down_sync(0xffffffffu, t2, 4);  // lane 0 holds the block sum
+        if (act && u == 0) {
+            if (n >= 8) {
+                for (int i = n - (n % 8); i < n; i++) { const int o = off + i - lo; res += ((vmask[k][o >> 5] >> (o & 31)) & 1u) ? reward[o] : 0.0; }
+            } else {
+                res = r;
+            }
+            leaf[k][l] = res;
+        }
     }
     __syncthreads();
     if (tid < ny) {
@@ -700,7 +925,7 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         int sp = 0;
         for (int o = 0; o < prog->n_ops; o++) {
             const int op = prog->ops[o];
-            if (op >= 0) st[sp++] = leaf[tid * D2D_OX_MAX_LEAVES + op];
+            if (op >= 0) st[sp++] = (op >= l0 && op <= l1) ? leaf[tid][op] : 0.0;
             else { sp--; st[sp - 1] = st[sp - 1] + st[sp]; }
         }
         score[tid] = 0.0 + st[0];

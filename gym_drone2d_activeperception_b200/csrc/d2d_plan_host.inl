@@ -14,7 +14,33 @@ static int launch_pre(d2d_handle *h, cudaStream_t st) {
     return D2D_OK;
 }
 
+template <int WPB>
+static int launch_prim_warp(d2d_handle *h, const double *actions, cudaStream_t st) {
+    static bool attr_done[64] = {false};
+    const int dev = h->cfg.device;
+    const size_t smem = (size_t)WPB * d2d_warp_slice_bytes(h->NP, h->HW, d2d_prim_warp_extra(h->NP));
+    if (smem > 227 * 1024) { h->err = "warp-per-env Primitive kernel: shared memory per block exceeds 227 KB"; return D2D_ERR_INVALID; }
+    if (!attr_done[dev & 63]) {
+        cudaError_t ce = cudaFuncSetAttribute(d2d_step_prim_warp_kernel<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(d2d_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
+        attr_done[dev & 63] = true;
+    }
+    h->P.use_parity = 1;
+    h->P.step_parity = (int)(h->step_count & 1);
+    h->step_count++;
+    d2d_step_prim_warp_kernel<WPB><<<(h->B + WPB - 1) / WPB, WPB * 32, smem, st>>>(h->P, actions);
+    const int pgrid = h->B < D2D_PLAN_SLOTS ? h->B : D2D_PLAN_SLOTS;
+    d2d_plan_kernel<<<pgrid, D2D_PLAN_THREADS2, h->smem_plan, st>>>(h->P);
+    const int lgrid = (h->B + 3) / 4 < 148 * 4 ? (h->B + 3) / 4 : 148 * 4;
+    d2d_step_post_list_kernel<4><<<lgrid, 128, 4 * d2d_warp_slice_bytes(1, 1, 0), st>>>(h->P, actions);
+    h->launches += 3;
+    return D2D_OK;
+}
+
 static int step_primitive(d2d_handle *h, const double *actions, cudaStream_t st) {
+    if (h->cfg.envs_per_block <= 0) return launch_prim_warp<4>(h, actions, st);   // default: one warp per env
+    h->P.use_parity = 0;
     int rc;
     switch (h->E) {
         case 4: rc = launch_pre<4>(h, st); break;
@@ -47,15 +73,7 @@ extern "C" int d2d_plan_oxford(d2d_handle *h, double *actions_out_dev, void *str
     if (!h->cfg.oxford) { h->err = "d2d_plan_oxford: handle was created with oxford = 0"; return D2D_ERR_STATE; }
     if (!h->world_set) { h->err = "d2d_plan_oxford before d2d_set_world"; return D2D_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    {
-        static bool attr_done[64] = {false};
-        const int dev = h->cfg.device;
-        if (!attr_done[dev & 63]) {
-            CUDA_TRY(h, cudaFuncSetAttribute(d2d_oxford_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done[dev & 63] = true;
-        }
-    }
-    d2d_oxford_kernel<<<h->B, D2D_OX_THREADS, d2d_oxford_smem_bytes(h->cfg.n_yaw), (cudaStream_t)stream>>>(h->P, h->ox_prog, actions_out_dev);
+    d2d_oxford_kernel<<<h->B, D2D_OX_THREADS, 0, (cudaStream_t)stream>>>(h->P, h->ox_prog, actions_out_dev);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return D2D_OK;

@@ -22,6 +22,13 @@
 #include "d2d_state.cuh"
 #include "d2d_math.cuh"
 
+// big, once-per-env-step helpers: inlined by default; -DD2D_COLD_NOINLINE=1 keeps one shared copy of each
+#if defined(D2D_COLD_NOINLINE) && D2D_COLD_NOINLINE
+#define D2D_COLD __noinline__
+#else
+#define D2D_COLD __forceinline__
+#endif
+
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t d2d_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void d2d_mbar_init(uint64_t *bar, uint32_t count) {
@@ -97,7 +104,7 @@ __device__ __forceinline__ BlockCtx d2d_carve(unsigned char *base, int E, int NP
 }
 
 // ------------------------------------------------------------------------------------------ P0: scalars + bulk loads
-__device__ __forceinline__ void d2d_load_env_scalars(const DevP &P, EnvS &s, int e) {
+__device__ D2D_COLD void d2d_load_env_scalars(const DevP &P, EnvS &s, int e) {
     // All global loads are issued into registers BEFORE anything is written to shared memory: the compiler cannot
     // prove that the EnvS reference does not alias the global arrays, so interleaved load/store pairs would
     // serialise ~20 DRAM round trips.
@@ -134,7 +141,7 @@ __device__ __forceinline__ void d2d_load_env_scalars(const DevP &P, EnvS &s, int
     if (oxf) P.ox_fresh[e] = 0;
 }
 
-__device__ __forceinline__ void d2d_store_env_scalars(const DevP &P, const EnvS &s, int e) {
+__device__ D2D_COLD void d2d_store_env_scalars(const DevP &P, const EnvS &s, int e) {
     P.drone_x[e] = s.px; P.drone_y[e] = s.py; P.drone_yaw[e] = s.yaw; P.drone_vx[e] = s.vx; P.drone_vy[e] = s.vy;
     P.target_x[e] = s.tgx; P.target_y[e] = s.tgy;
     P.steps[e] = s.steps; P.state_machine[e] = s.sm; P.fail_count[e] = s.fail; P.target_cursor[e] = s.tcur;
@@ -161,9 +168,10 @@ __device__ __forceinline__ void d2d_issue_bulk(const DevP &P, const BlockCtx &c,
 }
 
 // envs being reset: zero belief in shared memory and HBM; restore the Oxford policy state
-__device__ __forceinline__ void d2d_reset_arrays(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
+__device__ D2D_COLD void d2d_reset_arrays(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
     if (!c.misc[1]) return;   // block-uniform: no env of this block is being reset (the common case)
     const int W = D2D_BELIEF_STRIDE / 4;
+#pragma unroll 1
     for (int w = tid; w < E * W; w += T) {
         const int i = w / W, o = w - i * W;
         if (!c.S[i].valid || !c.S[i].reset) continue;
@@ -171,6 +179,7 @@ __device__ __forceinline__ void d2d_reset_arrays(const DevP &P, const BlockCtx &
         ((uint32_t *)(P.belief + (size_t)(env0 + i) * D2D_BELIEF_STRIDE))[o] = 0u;
     }
     if (P.ox_last) {
+#pragma unroll 1
         for (int w = tid; w < E * D2D_CELLS; w += T) {
             const int i = w / D2D_CELLS, o = w - i * D2D_CELLS;
             if (!c.S[i].valid || !c.S[i].reset || c.S[i].ox_fresh) continue;
@@ -184,6 +193,7 @@ template <bool COLLIDE_HERE>
 __device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
     const double C6 = 0.8660254037844387, S6 = 0.49999999999999994;   // math.cos(pi/6), math.sin(pi/6) (glibc)
     const int N = P.N, NP = P.NP;
+#pragma unroll 1
     for (int w = tid; w < E * N; w += T) {
         const int i = w / N, k = w - i * N;
         EnvS &s = c.S[i];
@@ -233,7 +243,10 @@ struct RayOut {
     uint8_t *bel_s, *bel_g;   // belief grid in shared memory / HBM
     uint8_t *obs;             // env's local_map slice when it can be patched in place (window unchanged), else null
     int wi, wj;               // window origin cell (ix-16, iy-16)
+    uint32_t *chg;            // optional shared-memory list of changed cells (cell | value << 16), null if unused
+    int *nchg;                // its counter (entries beyond the capacity are counted but not stored)
 };
+#define D2D_CHG_CAP 64
 
 __device__ __forceinline__ void d2d_mark(const RayOut &o, int ci, int cj, uint8_t v) {
     const int cell = ci * D2D_GRID + cj;
@@ -243,6 +256,10 @@ __device__ __forceinline__ void d2d_mark(const RayOut &o, int ci, int cj, uint8_
         if (o.obs) {            // the cell is always inside the 33x33 window (view reach < 16 cells)
             const int u = ci - o.wi, w = cj - o.wj;
             if ((unsigned)u < (unsigned)D2D_LOCAL && (unsigned)w < (unsigned)D2D_LOCAL) o.obs[u * D2D_LOCAL + w] = v;
+        }
+        if (o.chg) {
+            const int slot = atomicAdd(o.nchg, 1);
+            if (slot < D2D_CHG_CAP) o.chg[slot] = (uint32_t)cell | ((uint32_t)v << 16);
         }
     }
 }
@@ -280,6 +297,7 @@ __device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, doubl
     bool cand = false;
     {
         const double dd2 = xs * xs + ys * ys;
+#pragma unroll 1
         for (int q = 0; q < nc; q++) {
             const int k = cull[q];
             const double cx = sx[k] - x, cy = sy[k] - y;
@@ -307,6 +325,7 @@ __device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, doubl
         }
         bool any = false;
         if (cand) {
+#pragma unroll 1
             for (int q = 0; q < nc; q++) {
                 const int k = cull[q];
                 const double ex = sx[k] - x, ey = sy[k] - y;
@@ -347,7 +366,7 @@ __device__ __forceinline__ void d2d_phase_rays(const DevP &P, const BlockCtx &c,
         RayOut o;
         o.bel_s = c.belief + (size_t)i * D2D_BELIEF_STRIDE;
         o.bel_g = P.belief + (size_t)(env0 + i) * D2D_BELIEF_STRIDE;
-        o.obs = nullptr; o.wi = 0; o.wj = 0;
+        o.obs = nullptr; o.wi = 0; o.wj = 0; o.chg = nullptr; o.nchg = nullptr;
         const double a = d2d_ray_angle(P, s.yaw, ray);
         d2d_cast_ray(P, s, a, d2d_tan(a), o, c.gt + (size_t)i * D2D_GRID, c.sx + i * NP, c.sy + i * NP, c.sr2 + i * NP,
                      c.cull + i * NP, c.hitw + i * P.HW);
@@ -356,20 +375,33 @@ __device__ __forceinline__ void d2d_phase_rays(const DevP &P, const BlockCtx &c,
 
 // one env per warp: lane handles rays `lane` and `lane + 32` (+64, ...); the two tangent evaluations of a pair are
 // independent straight-line code, which gives the scheduler two dependency chains to interleave
+// one env per warp.  ILP2: lane handles rays `lane` and `lane + 32` with the two tangent evaluations as independent
+// straight-line code (two dependency chains for the scheduler; best when all warps run in phase, i.e. one wave).
+// Otherwise a single copy of the ray body (half the code: best when many waves de-phase the warps and the
+// instruction cache becomes the limiter).
+template <bool ILP2>
 __device__ __forceinline__ void d2d_phase_rays_warp(const DevP &P, const BlockCtx &c, const RayOut &o, int lane) {
     const EnvS &s = c.S[0];
     const int R = P.n_rays;
-    for (int r0 = lane; r0 < R; r0 += 64) {
-        const int r1 = r0 + 32;
-        const double a0 = d2d_ray_angle(P, s.yaw, r0), a1 = d2d_ray_angle(P, s.yaw, r1);
-        const double t0 = d2d_tan(a0), t1 = d2d_tan(a1);
-        d2d_cast_ray(P, s, a0, t0, o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
-        if (r1 < R) d2d_cast_ray(P, s, a1, t1, o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
+    if (ILP2) {
+        for (int r0 = lane; r0 < R; r0 += 64) {
+            const int r1 = r0 + 32;
+            const double a0 = d2d_ray_angle(P, s.yaw, r0), a1 = d2d_ray_angle(P, s.yaw, r1);
+            const double t0 = d2d_tan(a0), t1 = d2d_tan(a1);
+            d2d_cast_ray(P, s, a0, t0, o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
+            if (r1 < R) d2d_cast_ray(P, s, a1, t1, o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
+        }
+    } else {
+#pragma unroll 1
+        for (int ray = lane; ray < R; ray += 32) {
+            const double a = d2d_ray_angle(P, s.yaw, ray);
+            d2d_cast_ray(P, s, a, d2d_tan(a), o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------ P3: hit mask + trackers
-__device__ __forceinline__ void d2d_tracker_update(const DevP &P, EnvS &s, size_t g, bool measured, double z0, double z1) {
+__device__ D2D_COLD void d2d_tracker_update(const DevP &P, EnvS &s, size_t g, bool measured, double z0, double z1) {
     // KalmanFilter.update utils.py:242-275; F = I + 0.1*shift, H = [I 0], Sigma_z = var_cam*I, Sigma_x = q*I
     const double q = (P.var_cam != 0.0) ? 0.1 : 0.001;
     double *mu = P.trk_mu + g * 4, *Sg = P.trk_sigma + g * 16;
@@ -420,7 +452,8 @@ __device__ __forceinline__ void d2d_tracker_update(const DevP &P, EnvS &s, size_
             const double rz = P.var_cam;
             const double s00 = rz + S[0], s01 = S[1], s10 = S[4], s11 = rz + S[5];
             const double det = s00 * s11 - s01 * s10;
-            const double i00 = s11 / det, i01 = -s01 / det, i10 = -s10 / det, i11 = s00 / det;
+            const double idet = 1.0 / det;       // np.linalg.inv of the 2x2 innovation covariance (tolerance 1e-9, not bit-exact)
+            const double i00 = s11 * idet, i01 = -s01 * idet, i10 = -s10 * idet, i11 = s00 * idet;
             const double r0 = z0 - m[0], r1 = z1 - m[1];
             // rows 3, 2 first (they need the ORIGINAL rows 0 and 1), then rows 0 and 1 together
 #pragma unroll
@@ -465,6 +498,7 @@ __device__ __forceinline__ void d2d_tracker_update(const DevP &P, EnvS &s, size_
 
 __device__ __forceinline__ void d2d_phase_trackers(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
     const int N = P.N, NP = P.NP;
+#pragma unroll 1
     for (int w = tid; w < E * N; w += T) {
         const int i = w / N, k = w - i * N;
         EnvS &s = c.S[i];
@@ -504,7 +538,7 @@ __device__ __forceinline__ void d2d_leader_begin(const DevP &P, EnvS &s) {
 }
 
 // second half (drone_v2.py:196-235) after the planner verdict `success`
-__device__ __forceinline__ void d2d_leader_finish(const DevP &P, EnvS &s, const uint64_t *gt, int e, double action,
+__device__ D2D_COLD void d2d_leader_finish(const DevP &P, EnvS &s, const uint64_t *gt, int e, double action,
                                                   bool success) {
     if (!success) {   // Drone2D.brake utils.py:755-762
         const double nv = d2d_norm2(s.vx, s.vy);
@@ -547,7 +581,7 @@ __device__ __forceinline__ int d2d_static_probe(const DevP &P, const uint64_t *g
     return d2d_gt_probe(P, gt, px + ox, py + oy);
 }
 
-__device__ __forceinline__ void d2d_leader_flags(const DevP &P, EnvS &s, const uint64_t *gt, int e, int static_hit = -1) {
+__device__ D2D_COLD void d2d_leader_flags(const DevP &P, EnvS &s, const uint64_t *gt, int e, int static_hit = -1) {
     // is_collide utils.py:764-778
     int col = 0;
     if (static_hit < 0) {
@@ -731,7 +765,7 @@ __device__ __forceinline__ uint32_t d2d_obs_word(const uint8_t *bel, int ix, int
     return w;
 }
 
-__device__ __forceinline__ void d2d_obs_env_warp(const DevP &P, const uint8_t *bel, int ix, int iy, int e, int lane) {
+__device__ D2D_COLD void d2d_obs_env_warp(const DevP &P, const uint8_t *bel, int ix, int iy, int e, int lane) {
     // bytes [1089*e, 1089*e + 1089) of the observation tensor: unaligned head / tail (1089 = 1 mod 4) as byte stores,
     // the middle as coalesced 32-bit stores assembled with funnel shifts from aligned shared-memory words.
     uint8_t *out = P.local_map + (size_t)e * D2D_LOCAL_CELLS;
@@ -741,10 +775,11 @@ __device__ __forceinline__ void d2d_obs_env_warp(const DevP &P, const uint8_t *b
     if (lane < head) out[lane] = (uint8_t)d2d_obs_cell(bel, ix, iy, lane);
     if (lane < D2D_LOCAL_CELLS - tail0) out[tail0 + lane] = (uint8_t)d2d_obs_cell(bel, ix, iy, tail0 + lane);
     uint32_t *ow = (uint32_t *)(out + head);
+#pragma unroll 1
     for (int j = lane; j < nwords; j += 32) ow[j] = d2d_obs_word(bel, ix, iy, head + 4 * j);
 }
 
-template <int WPB, int MINB>
+template <int WPB, int MINB, bool ILP2>
 __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(const DevP P,
                                                                              const double *__restrict__ actions) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -760,6 +795,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
         d2d_load_env_scalars(P, s, e);
         c.misc[1] = s.reset;
     }
+#pragma unroll 1
     for (int w = lane; w < P.HW; w += 32) c.hitw[w] = 0u;
     __syncwarp();
     if (lane == 0) d2d_issue_bulk(P, c, e, 1, true);
@@ -774,9 +810,9 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     RayOut ro;
     ro.bel_s = c.belief; ro.bel_g = P.belief + (size_t)e * D2D_BELIEF_STRIDE;
     ro.obs = patch ? P.local_map + (size_t)e * D2D_LOCAL_CELLS : nullptr;
-    ro.wi = s.ix - 16; ro.wj = s.iy - 16;
+    ro.wi = s.ix - 16; ro.wj = s.iy - 16; ro.chg = nullptr; ro.nchg = nullptr;
     d2d_mbar_wait(c.mbar, 0);
-    d2d_phase_rays_warp(P, c, ro, lane);
+    d2d_phase_rays_warp<ILP2>(P, c, ro, lane);
     __syncwarp();
     d2d_phase_trackers(P, c, e, 1, lane, 32);
     const int shit = __any_sync(0xffffffffu, lane < 5 ? d2d_static_probe(P, c.gt, s.px, s.py, lane) : 0);
@@ -797,6 +833,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     }
     if (s.done_now) {
         int cnt = 0;
+#pragma unroll 1
         for (int o = lane; o < D2D_CELLS; o += 32) cnt += (c.belief[o] != 0);
         for (int off = 16; off > 0; off >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, off);
         if (lane == 0 && cnt) atomicAdd(&P.stats[D2D_STAT_GRID_DISCOVERED], (unsigned long long)cnt);

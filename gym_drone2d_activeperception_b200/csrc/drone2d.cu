@@ -30,6 +30,7 @@ struct d2d_handle {
     std::vector<BufDesc> bufs;
     double *stage_actions = nullptr;     // device staging for d2d_step_host
     int64_t launches = 0;
+    int64_t step_count = 0;
     bool world_set = false;
     std::string err;
     size_t smem_step = 0, smem_post = 0;
@@ -449,18 +450,18 @@ static int launch_fused(d2d_handle *h, const double *actions, cudaStream_t st) {
     return D2D_OK;
 }
 
-template <int WPB, int MINB>
+template <int WPB, int MINB, bool ILP2>
 static int launch_fused_warp(d2d_handle *h, const double *actions, cudaStream_t st) {
     static bool attr_done[64] = {false};
     const int dev = h->cfg.device;
     const size_t smem = (size_t)WPB * d2d_warp_slice_bytes(h->NP, h->HW, 0);
     if (smem > 227 * 1024) { h->err = "warp-per-env kernel: shared memory per block exceeds 227 KB"; return D2D_ERR_INVALID; }
     if (!attr_done[dev & 63]) {
-        cudaError_t ce = cudaFuncSetAttribute(d2d_step_fused_warp_kernel<WPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t ce = cudaFuncSetAttribute(d2d_step_fused_warp_kernel<WPB, MINB, ILP2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (ce != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
         attr_done[dev & 63] = true;
     }
-    d2d_step_fused_warp_kernel<WPB, MINB><<<(h->B + WPB - 1) / WPB, WPB * 32, smem, st>>>(h->P, actions);
+    d2d_step_fused_warp_kernel<WPB, MINB, ILP2><<<(h->B + WPB - 1) / WPB, WPB * 32, smem, st>>>(h->P, actions);
     h->launches++;
     return D2D_OK;
 }
@@ -475,19 +476,15 @@ extern "C" int d2d_step(d2d_handle *h, const double *actions_dev, void *stream) 
     int rc;
     const int epb = h->cfg.envs_per_block;
     if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb <= 0) {
-        rc = launch_fused_warp<4, 7>(h, actions_dev, st);       // default: one warp per env, 72 registers
+        // default: one warp per env, single copy of the ray body (smallest code: the kernel is instruction-cache
+        // sensitive once several waves de-phase the warps; measured equal to the 2-rays-per-lane variant at one wave)
+        rc = launch_fused_warp<4, 7, false>(h, actions_dev, st);
     } else if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb == 1) {
-        rc = launch_fused_warp<2, 14>(h, actions_dev, st);
+        rc = launch_fused_warp<4, 7, true>(h, actions_dev, st);
     } else if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb == 2) {
-        rc = launch_fused_warp<7, 4>(h, actions_dev, st);
-    } else if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb == 32) {     // tuning variants: register caps
-        rc = launch_fused_warp<4, 8>(h, actions_dev, st);       // 64 registers, 32 warps/SM
-    } else if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb == 33) {
-        rc = launch_fused_warp<4, 9>(h, actions_dev, st);       // 56 registers, 36 warps/SM
-    } else if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb == 34) {
-        rc = launch_fused_warp<4, 10>(h, actions_dev, st);      // 48 registers, 40 warps/SM
-    } else if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb == 35) {
-        rc = launch_fused_warp<4, 6>(h, actions_dev, st);       // 80 registers, 24 warps/SM
+        rc = launch_fused_warp<4, 7, false>(h, actions_dev, st);
+    } else if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb == 3) {
+        rc = launch_fused_warp<7, 4, true>(h, actions_dev, st);
     } else if (h->cfg.planner == D2D_PLANNER_NOMOVE) {
         switch (h->E) {
             case 4: rc = launch_fused<4>(h, actions_dev, st); break;
