@@ -51,3 +51,32 @@ def test_facade_info_and_pose_write():
     env.drone.x = 123.5                    # scripts write the pose directly (glob_survivability_calculator.py:36-37)
     assert env.drone.x == 123.5
     env.close()
+
+
+def test_global_survivability_matches_oracle():
+    """metrics.global_survivability vs the oracle run the way glob_survivability_calculator.py:30-41 runs the reference."""
+    import oracle
+    from gym_drone2d_activeperception_b200 import Params, generate_worlds
+    from gym_drone2d_activeperception_b200.metrics import global_survivability, survivability_positions, mean_survival_time
+    p = Params(debug=False, planner="NoMove", gaze_method="NoControl", agent_number=20, agent_radius=15, agent_max_speed=40)
+    seeds = [4, 9]
+    T = 6
+    got = global_survivability(p, seeds, T=T)
+    xs, ys = survivability_positions(p)
+    assert got.shape == (2, 8, 8, 60) and xs[0] == 20 and xs[-1] == 440
+    worlds = generate_worlds(p, seeds)
+    op = util.oracle_params(p)
+    for wi in range(2):
+        for a, x in enumerate(xs[::3]):
+            for b, y in enumerate(ys[::3]):
+                e = oracle.OracleEnv(op, worlds["agent_pos"][wi], worlds["agent_pref"][wi], worlds["agent_radius"][wi],
+                                     worlds["gt_grid"][wi], worlds["tracker_radius"][wi], drone=(x, y, 270.0),
+                                     targets=p.target_list)
+                ref = []
+                for t in range(60):
+                    e.c.x, e.c.y = float(x), float(y)
+                    e.step(0.0)
+                    ref.append(1 if e.c.collision == 2 else 0)
+                assert np.array_equal(got[wi, a * 3, b * 3], np.array(ref, dtype=np.uint8)), (wi, x, y)
+                e.close()
+    assert got.sum() > 0 and mean_survival_time(got).shape == (2, 8, 8)
