@@ -744,14 +744,17 @@ __device__ __forceinline__ void d2d_ox_window(const DevP &P, double dx, int &lo,
 #define D2D_OX_WORDS ((D2D_OX_SPAN + 31) / 32)
 #define D2D_OX_THREADS 128
 
-// Oxford.plan (yaw_planner.py:81-127), one block per env.
-//  1. swep_map from the remaining waypoints (largest waypoint index per cell, later assignments win, :87-89)
-//  2. last_time_observed update over all 2500 cells (:95-97); only cells inside the pose's depth window can be visible
-//  3. candidate scores np.sum(view_k * reward) (:120-125): view_k vanishes outside the depth window of the first
-//     waypoint, so the reward map is materialised only for the flattened range of rows that window touches (extended to
-//     whole leaves of NumPy's pairwise recursion) and each candidate keeps a visibility BITMASK over that range.  Leaf
-//     sums run in NumPy's order -- 8 strided accumulators (one lane each), combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
-//     then the tail -- and leaves outside the range are exactly +0.0 (x + 0.0 == x, so skipping them changes nothing).
+// Oxford.plan (yaw_planner.py:81-127), one block (4 warps) per env.
+//  A. warp 0: sin/cos of the 6 candidate yaws + current yaw, first waypoint, leaf range, clears; warps 1-3 meanwhile age
+//     every cell of last_time_observed by dt (:95-97, loads batched).
+//  B. swep_map from the remaining waypoints (largest waypoint index per cell: later assignments win, :87-89); cells of
+//     the pose's depth window that are visible are reset to 0 (only those can be visible).
+//  C. candidate scores np.sum(view_k * reward) (:120-125): view_k vanishes outside the depth window of the first
+//     waypoint, so reward (:108-110) is materialised only on the flattened range of rows that window touches (extended
+//     to whole leaves of NumPy's pairwise recursion) and each candidate gets a visibility BITMASK over that range.
+//  D. leaf sums in NumPy's order -- 8 strided accumulators (one lane each; a lane only visits the set bits of its
+//     residue class), combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail; leaves outside the range are exactly
+//     +0.0 (x + 0.0 == x) -- then the recursion's post-order combine and the strict-< argmax.
 __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P, const OxProgram *__restrict__ prog,
                                                                     double *__restrict__ actions_out) {
     __shared__ double reward[D2D_OX_SPAN];
@@ -760,7 +763,9 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
     __shared__ double leaf[D2D_MAX_YAW][D2D_OX_MAX_LEAVES];
     __shared__ double score[D2D_MAX_YAW];
     __shared__ double cs_s[D2D_MAX_YAW + 1], sn_s[D2D_MAX_YAW + 1];
-    const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+    __shared__ double wpt[2];
+    __shared__ int geo[12];                             // r0 r1 q0 q1 lo hi l0 l1 i0 i1 j0 j1
+    const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5;
     if (e >= P.B) return;
     // an env that reported done and will be re-initialised by its next step is seen by the policy as freshly reset
     // (the reference builds a new env + policy per episode, experiment.py:27-34)
@@ -769,68 +774,64 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
     const double yaw = fresh ? P.pose0[2 * P.B + e] : P.drone_yaw[e];
     const int len = fresh ? 0 : P.traj_nseg[e] * P.n_way - P.traj_cursor[e], cursor = fresh ? 0 : P.traj_cursor[e];
     const int ny = P.n_yaw;
-    if (tid <= ny) {
-        // candidate yaws: Drone2D(..., yaw_i) stores yaw_i % 360 (utils.py:718); entry n_yaw is the current pose
-        const double y = (tid < ny) ? d2d_pymod(yaw + P.tab->v_yaw_space[tid] * P.dt, 360.0) : yaw;
-        double sn, cs;
-        d2d_sincos(y * D2D_DEG2RAD, &sn, &cs);
-        cs_s[tid] = cs; sn_s[tid] = -sn;    // vec_yaw = [cos, -sin] (yaw_planner.py:72)
-    }
-    // range of the flattened grid that can carry non-zero products: rows of the first waypoint's depth window,
-    // extended to whole leaves
-    __shared__ int lrange[2];
-    double wx = 0, wy = 0;
-    int r0 = 0, r1 = -1, q0 = 0, q1 = -1, lo = 0, hi = 0, l0 = 0, l1 = -1;
-    if (len > 0) {
-        d2d_waypoint_pos(P, e, cursor, wx, wy);
-        d2d_ox_window(P, wx, r0, r1);
-        d2d_ox_window(P, wy, q0, q1);
-        if (r1 - r0 + 1 > D2D_OX_ROWS) r1 = r0 + D2D_OX_ROWS - 1;       // cannot happen for depth <= 9 cells
-        if (tid < prog->n_leaves) {
-            const int b0 = r0 * D2D_GRID, b1 = (r1 + 1) * D2D_GRID - 1;
-            const int off = prog->leaf_off[tid], n = prog->leaf_len[tid];
-            if (b0 >= off && b0 < off + n) lrange[0] = tid;
-            if (b1 >= off && b1 < off + n) lrange[1] = tid;
-        }
-    }
-    __syncthreads();
-    if (len > 0) {
-        l0 = lrange[0]; l1 = lrange[1];
-        lo = prog->leaf_off[l0];
-        hi = prog->leaf_off[l1] + prog->leaf_len[l1];
-        for (int o = tid; o < hi - lo; o += T) swep_w[o] = -1;
-    }
-    __syncthreads();
-    for (int w = tid; w < len; w += T) {
-        double x, y;
-        d2d_waypoint_pos(P, e, cursor + w, x, y);
-        const int ci = d2d_cell(x, P.scale, P.inv_scale), cj = d2d_cell(y, P.scale, P.inv_scale);
-        if ((unsigned)ci < (unsigned)D2D_GRID && (unsigned)cj < (unsigned)D2D_GRID) {
-            const int c = ci * D2D_GRID + cj;
-            if (c >= lo && c < hi) atomicMax(&swep_w[c - lo], w);
-        }
-    }
-    // ---- last_time_observed update (:95-97): visible cells (only possible inside the pose's window) -> 0, others += dt
-    int i0, i1, j0, j1;
-    d2d_ox_window(P, dx, i0, i1);
-    d2d_ox_window(P, dy, j0, j1);
     double *last = P.ox_last + (size_t)e * D2D_CELLS;
-    {
-        // pass A: every cell ages by dt (all loads first: one DRAM round trip instead of NL dependent ones)
-        constexpr int NL = (D2D_CELLS + D2D_OX_THREADS - 1) / D2D_OX_THREADS;
+
+    // ---- A
+    if (wid == 0) {
+        if (lane <= ny) {
+            // candidate yaws: Drone2D(..., yaw_i) stores yaw_i % 360 (utils.py:718); entry n_yaw is the current pose
+            const double y = (lane < ny) ? d2d_pymod(yaw + P.tab->v_yaw_space[lane] * P.dt, 360.0) : yaw;
+            double sn, cs;
+            d2d_sincos(y * D2D_DEG2RAD, &sn, &cs);
+            cs_s[lane] = cs; sn_s[lane] = -sn;    // vec_yaw = [cos, -sin] (yaw_planner.py:72)
+        }
+        int r0 = 0, r1 = -1, q0 = 0, q1 = -1, i0, i1, j0, j1;
+        d2d_ox_window(P, dx, i0, i1);
+        d2d_ox_window(P, dy, j0, j1);
+        double wx = 0, wy = 0;
+        if (len > 0) {
+            d2d_waypoint_pos(P, e, cursor, wx, wy);
+            d2d_ox_window(P, wx, r0, r1);
+            d2d_ox_window(P, wy, q0, q1);
+            if (r1 - r0 + 1 > D2D_OX_ROWS) r1 = r0 + D2D_OX_ROWS - 1;       // cannot happen for depth <= 9 cells
+            if (lane < prog->n_leaves) {
+                const int b0 = r0 * D2D_GRID, b1 = (r1 + 1) * D2D_GRID - 1;
+                const int off = prog->leaf_off[lane], n = prog->leaf_len[lane];
+                if (b0 >= off && b0 < off + n) { geo[6] = lane; geo[4] = off; }
+                if (b1 >= off && b1 < off + n) { geo[7] = lane; geo[5] = off + n; }
+            }
+        }
+        if (lane == 0) {
+            geo[0] = r0; geo[1] = r1; geo[2] = q0; geo[3] = q1; geo[8] = i0; geo[9] = i1; geo[10] = j0; geo[11] = j1;
+            wpt[0] = wx; wpt[1] = wy;
+        }
+#pragma unroll 1
+        for (int o = lane; o < D2D_MAX_YAW * D2D_OX_WORDS; o += 32) (&vmask[0][0])[o] = 0u;
+    } else {
+        // every cell ages by dt; all loads first: one DRAM round trip instead of NL dependent ones
+        constexpr int TA = D2D_OX_THREADS - 32, NL = (D2D_CELLS + TA - 1) / TA;
+        const int ta = tid - 32;
         double lv[NL];
 #pragma unroll
         for (int q = 0; q < NL; q++) {
-            const int c = tid + q * D2D_OX_THREADS;
+            const int c = ta + q * TA;
             lv[q] = (c < D2D_CELLS && !fresh) ? last[c] : 5.0;               // init 5.0 (:49)
         }
 #pragma unroll
         for (int q = 0; q < NL; q++) {
-            const int c = tid + q * D2D_OX_THREADS;
+            const int c = ta + q * TA;
             if (c < D2D_CELLS) last[c] = lv[q] + 1.0 * P.dt;
         }
-        __syncthreads();
-        // pass B: the (few) visible cells, all inside the pose's depth window, are reset to 0
+    }
+    __syncthreads();
+    const int r0 = geo[0], r1 = geo[1], q0 = geo[2], q1 = geo[3], lo = geo[4], hi = geo[5], l0 = geo[6], l1 = geo[7];
+    const int i0 = geo[8], i1 = geo[9], j0 = geo[10], j1 = geo[11];
+    const double wx = wpt[0], wy = wpt[1];
+    const int span = (len > 0) ? hi - lo : 0;
+    // ---- B
+#pragma unroll 1
+    for (int o = tid; o < span; o += T) swep_w[o] = -1;
+    {
         const int wi = i1 - i0 + 1, wj = j1 - j0 + 1;
 #pragma unroll 1
         for (int q = tid; q < wi * wj; q += T) {
@@ -844,47 +845,46 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         return;
     }
     __syncthreads();
-    // ---- reward (:108-110) and per-candidate visibility over [lo, hi)
-    const int span = hi - lo;
 #pragma unroll 1
-    for (int ob = 0; ob < span; ob += T) {          // whole warps stay converged for the ballots
-        const int o = ob + tid, c = lo + o;
-        bool inwin = false, zero_d = false;
-        double num_x = 0.0, num_y = 0.0, den = 1.0;
-        if (o < span) {
-            const int i = c / D2D_GRID, j = c - i * D2D_GRID;
-            if (i >= r0 && i <= r1 && j >= q0 && j <= q1) {
-                const double x = (double)i * P.scale, y = (double)j * P.scale;
-                const double ex = wx - x, ey = wy - y;
-                const double d2 = ex * ex + ey * ey;
-                zero_d = d2 <= 0.0;
-                inwin = zero_d || d2 <= P.depth2;
-                if (inwin) {
-                    const double lt = last[c];
-                    const double sw = swep_w[o] >= 0 ? (double)swep_w[o] * P.dt : 0.0;
-                    double r;
-                    if (sw > 0.0 && sw <= 3.0 && lt >= 0.5) r = 1000000.0;
-                    else if (sw > 3.0 && lt >= 0.5) r = 1000.0;
-                    else r = (lt > 1.0) ? 1.0 : lt;
-                    reward[o] = r;
-                    num_x = x - wx; num_y = y - wy; den = D2D_SQRT(d2);
-                }
-            }
-        }
-        const bool warp_any = __any_sync(0xffffffffu, inwin);
-#pragma unroll 1
-        for (int k = 0; k < ny; k++) {
-            unsigned bal = 0u;
-            if (warp_any) {
-                bool vis = false;
-                if (inwin) vis = zero_d || d2d_ox_wedge(num_x * cs_s[k] + num_y * sn_s[k], den, P.ox_cos_thresh);
-                bal = __ballot_sync(0xffffffffu, vis);
-            }
-            if (lane == 0 && (ob + tid) < span + 31) vmask[k][(ob + tid) >> 5] = bal;
+    for (int w = tid; w < len; w += T) {
+        double x, y;
+        d2d_waypoint_pos(P, e, cursor + w, x, y);
+        const int ci = d2d_cell(x, P.scale, P.inv_scale), cj = d2d_cell(y, P.scale, P.inv_scale);
+        if ((unsigned)ci < (unsigned)D2D_GRID && (unsigned)cj < (unsigned)D2D_GRID) {
+            const int c = ci * D2D_GRID + cj;
+            if (c >= lo && c < hi) atomicMax(&swep_w[c - lo], w);
         }
     }
     __syncthreads();
-    // ---- leaf sums: task = (candidate, leaf, accumulator lane u in 0..7)
+    // ---- C: window cells of the first waypoint only
+    {
+        const int wr = r1 - r0 + 1, wq = q1 - q0 + 1;
+#pragma unroll 1
+        for (int q = tid; q < wr * wq; q += T) {
+            const int i = r0 + q / wq, j = q0 + q % wq;
+            const int c = i * D2D_GRID + j, o = c - lo;
+            const double x = (double)i * P.scale, y = (double)j * P.scale;
+            const double ex = wx - x, ey = wy - y;
+            const double d2 = ex * ex + ey * ey;
+            const bool zero_d = d2 <= 0.0;
+            if (!(zero_d || d2 <= P.depth2)) continue;
+            const double lt = last[c];
+            const double sw = swep_w[o] >= 0 ? (double)swep_w[o] * P.dt : 0.0;
+            double r;
+            if (sw > 0.0 && sw <= 3.0 && lt >= 0.5) r = 1000000.0;           // :108-110
+            else if (sw > 3.0 && lt >= 0.5) r = 1000.0;
+            else r = (lt > 1.0) ? 1.0 : lt;
+            reward[o] = r;
+            const double num_x = x - wx, num_y = y - wy, den = D2D_SQRT(d2);
+#pragma unroll 1
+            for (int k = 0; k < ny; k++) {
+                const bool vis = zero_d || d2d_ox_wedge(num_x * cs_s[k] + num_y * sn_s[k], den, P.ox_cos_thresh);
+                if (vis) atomicOr(&vmask[k][o >> 5], 1u << (o & 31));
+            }
+        }
+    }
+    __syncthreads();
+    // ---- D: leaf sums: task = (candidate, leaf, accumulator lane u in 0..7)
     const int nleaf = l1 - l0 + 1;
 #pragma unroll 1
     for (int qb = 0; qb < ny * nleaf * 8; qb += T) {
@@ -893,16 +893,24 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         const int u = q & 7, kl = q >> 3;
         const int k = act ? kl / nleaf : 0, l = l0 + (act ? kl - k * nleaf : 0);
         const int off = prog->leaf_off[l], n = prog->leaf_len[l];
+        const int nb = n - (n % 8);                     // elements covered by the 8 accumulators
         double r = 0.0;
-        if (act) {
-            if (n < 8) {
-                if (u == 0)
-                    for (int i = 0; i < n; i++) { const int o = off + i - lo; r += ((vmask[k][o >> 5] >> (o & 31)) & 1u) ? reward[o] : 0.0; }
-            } else {
-                { const int o = off + u - lo; r = ((vmask[k][o >> 5] >> (o & 31)) & 1u) ? reward[o] : 0.0; }
-                for (int i = 8; i < n - (n % 8); i += 8) {
-                    const int o = off + i + u - lo;
-                    if ((vmask[k][o >> 5] >> (o & 31)) & 1u) r += reward[o];      // adding +0.0 is the identity
+        if (act && n >= 8) {
+            // accumulator u sums elements off+u, off+8+u, ... in ascending order; zeros are skipped (x + 0.0 == x):
+            // walk the words of the leaf and visit only set bits whose leaf-relative index is = u (mod 8)
+            const int o0 = off - lo, o1 = o0 + nb;
+            const uint32_t cls = 0x01010101u << ((u + o0) & 7);   // bit positions b with (32w + b - o0) = u (mod 8)
+            bool first = true;
+#pragma unroll 1
+            for (int w = o0 >> 5; w <= (o1 - 1) >> 5; w++) {
+                uint32_t m = vmask[k][w] & cls;
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int o = (w << 5) + b;
+                    if (o < o0 || o >= o1) continue;
+                    if (first) { r = reward[o]; first = false; }     // r[j] = a[j] then += : same value as 0.0 + a
+                    else r += reward[o];
                 }
             }
         }
@@ -911,10 +919,10 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         double t2 = t + __shfl_down_sync(0xffffffffu, t, 2);     // lanes 0,4 hold quad sums
         double res = t2 + __shfl_down_sync(0xffffffffu, t2, 4);  // lane 0 holds the block sum
         if (act && u == 0) {
-            if (n >= 8) {
-                for (int i = n - (n % 8); i < n; i++) { const int o = off + i - lo; res += ((vmask[k][o >> 5] >> (o & 31)) & 1u) ? reward[o] : 0.0; }
-            } else {
-                res = r;
+            if (n < 8) res = 0.0;
+            for (int i = (n < 8 ? 0 : nb); i < n; i++) {          // tail (or the whole leaf when n < 8), sequential
+                const int o = off + i - lo;
+                if ((vmask[k][o >> 5] >> (o & 31)) & 1u) res += reward[o];
             }
             leaf[k][l] = res;
         }
