@@ -222,7 +222,10 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     uint32_t *chg = (uint32_t *)(trk + (size_t)P.NP * 5);                  // [D2D_CHG_CAP]
     int *cnt = (int *)(chg + D2D_CHG_CAP);                                 // [0] nact, [1] nchg
     EnvS &s = c.S[0];
-    if (blockIdx.x == 0 && threadIdx.x == 0) P.plan_list[P.B + 1 + ((P.step_parity + 1) & 1)] = 0;   // next step's counter
+    // plan-list counters are double buffered by a step parity that lives in DEVICE memory (plan_list[B+3], advanced by
+    // the post kernel), so a captured CUDA graph replays correctly; [B+4] publishes this step's parity to the later kernels
+    const int par = P.plan_list[P.B + 3] & 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { P.plan_list[P.B + 4] = par; P.plan_list[P.B + 1 + (par ^ 1)] = 0; }
 
     if (lane == 0) {
         d2d_mbar_init(c.mbar, 1);
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
         d2d_finish_env_warp(P, c, s, e, lane, actions[e], true, true, cnt[1], chg, true);
     } else if (lane == 0) {
         P.need_plan[e] = 1;
-        const int slot = atomicAdd(&P.plan_list[P.B + 1 + (P.step_parity & 1)], 1);
+        const int slot = atomicAdd(&P.plan_list[P.B + 1 + par], 1);
         P.plan_list[slot] = e;
         P.tmp_act_cnt[e] = s.act_cnt; P.tmp_act_ts[e] = s.act_ts;
         d2d_store_env_scalars(P, s, e);
@@ -297,7 +300,9 @@ template <int WPB>
 __global__ void __launch_bounds__(WPB * 32) d2d_step_post_list_kernel(const DevP P, const double *__restrict__ actions) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int count = min(P.plan_list[P.B + 1 + (P.step_parity & 1)], P.B);
+    const int par = P.plan_list[P.B + 4];
+    const int count = min(P.plan_list[P.B + 1 + par], P.B);
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.plan_list[P.B + 3] += 1;     // next step uses the other counter
     const BlockCtx c = d2d_carve(smem + (size_t)wid * d2d_warp_slice_bytes(1, 1, 0), 1, 1, 1);
     EnvS &s = c.S[0];
     uint32_t phase = 0;
@@ -469,7 +474,7 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
         h.open_total = w.open_total; h.cost = w.cost; h.hkeys32 = nullptr; h.hvals16 = nullptr;
         h.hkeys64 = w.hkeys; h.hvals32 = w.hvals; h.hcap = w.hcap;
     }
-    const int count = min(P.plan_list[P.B + (P.use_parity ? 1 + (P.step_parity & 1) : 0)], P.B);
+    const int count = min(P.plan_list[P.B + (P.use_parity ? 1 + P.plan_list[P.B + 4] : 0)], P.B);
 
     for (int li = blockIdx.x; li < count; li += gridDim.x) {
         const int e = P.plan_list[li];

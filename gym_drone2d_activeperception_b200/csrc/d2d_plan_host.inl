@@ -27,8 +27,6 @@ static int launch_prim_warp(d2d_handle *h, const double *actions, cudaStream_t s
         attr_done[dev & 63] = true;
     }
     h->P.use_parity = 1;
-    h->P.step_parity = (int)(h->step_count & 1);
-    h->step_count++;
     d2d_step_prim_warp_kernel<WPB><<<(h->B + WPB - 1) / WPB, WPB * 32, smem, st>>>(h->P, actions);
     const int pgrid = h->B < D2D_PLAN_SLOTS ? h->B : D2D_PLAN_SLOTS;
     d2d_plan_kernel<<<pgrid, D2D_PLAN_THREADS2, h->smem_plan, st>>>(h->P);

@@ -27,7 +27,7 @@ struct DevP {
     int B, N, NP, HW;            // envs, agents, padded agents, hit words per env
     int n_rays, planner, trackers, auto_reset, n_targets;
     int n_u, n_samp, n_way, n_yaw;
-    int step_parity, use_parity; // plan-list counter double buffering (warp-per-env Primitive path)
+    int step_parity, use_parity; // use_parity: warp-per-env Primitive path (parity itself lives in plan_list[B+3])
     int m_far;                   // first ray sample index at which the view-depth test can fire
     double dt, scale, inv_scale, map_w, map_h, agent_radius, max_acc, drone_r, max_yaw_speed;
     double ray_a0, ray_da;       // -FOV/2 and FOV/n_rays (utils.py:594)
@@ -64,6 +64,7 @@ struct DevP {
     double *ox_last;             // [B][2500]
     unsigned long long *stats;   // [D2D_NUM_STATS]
     unsigned char *plan_ws;      // A* workspaces (Primitive planner)
-    int *plan_list;              // [B+4] compacted list of envs that need a plan; [B] = count (block path), [B+1+parity] (warp path)
+    int *plan_list;              // [B+8]: compacted list of envs that need a plan; [B] count (block path); [B+1], [B+2]
+                                 // double-buffered counts, [B+3] step counter, [B+4] this step's parity (warp path)
     const DevTables *tab;
 };

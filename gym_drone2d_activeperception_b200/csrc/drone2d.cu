@@ -247,7 +247,7 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
         plan_ws_bytes = d2d_plan_workspace_bytes(cfg->n_u) * (size_t)D2D_PLAN_SLOTS;
         o_plan_ws = add_buf(h, cur, "plan_workspace", D2D_U8, 1, SHP((int64_t)plan_ws_bytes), SHP(1), plan_ws_bytes);
     }
-    size_t o_plan_list = add_buf(h, cur, "plan_list", D2D_I32, 1, SHP(B + 4), SHP(1), sB + 4);
+    size_t o_plan_list = add_buf(h, cur, "plan_list", D2D_I32, 1, SHP(B + 8), SHP(1), sB + 8);
 #undef SHP
     h->arena_bytes = (cur + 255) / 256 * 256;
     ce = cudaMalloc((void **)&h->arena, h->arena_bytes);

@@ -143,3 +143,79 @@ def test_primitive_multiple_targets_and_no_agents():
             break
     assert done_at is not None and oracles[0].c.state_machine == 1 and oracles[0].c.target_cursor == 2
     env.close()
+
+
+def test_primitive_crowded_random_map():
+    """Primitive + Oxford on random_map_0 (142 agents per env: 20 discs + 122 moving map cells), vs the oracle."""
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200.world import generate_worlds
+    B, steps = 6, 80
+    p = Params(debug=False, planner="Primitive", gaze_method="Oxford", map_id=20, static_map="maps/random_map_0.npy",
+               agent_number=20, agent_radius=15, agent_max_speed=40)
+    worlds = generate_worlds(p, 20 + np.arange(B))
+    env = _env(p, B, worlds, auto_reset=True, oxford=True)
+    n = env.num_agents
+    assert n == 142
+    oracles = [util.oracle_env_from_world(p, worlds, i) for i in range(B)]
+    for t in range(steps):
+        a = env.plan_oxford()
+        acts = np.zeros(B)
+        for i in range(B):
+            if oracles[i].c.done:
+                oracles[i].close()
+                oracles[i] = util.oracle_env_from_world(p, worlds, i)
+            acts[i] = oracles[i].oxford_plan()
+        torch.cuda.synchronize()
+        assert np.array_equal(a.cpu().numpy(), acts), ("oxford actions", t)
+        env.step(a)
+        for i in range(B):
+            oracles[i].step(acts[i])
+        h = _host(env)
+        for i, e in enumerate(oracles):
+            _cmp_env_to_oracle(h, i, e, n, t, "crowded")
+            assert h["traj_nseg"][i] * 20 - h["traj_cursor"][i] == e.c.traj_len
+    env.close()
+
+
+@pytest.mark.parametrize("planner", ["NoMove", "Primitive"])
+def test_cuda_graph_capture_replays_steps(planner):
+    """d2d_step / d2d_plan_oxford only enqueue kernels on the caller's stream, so a step loop can be captured in a
+    CUDA graph (after one eager warm-up step) and must reproduce the eager results."""
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200.world import generate_worlds
+    B = 64
+    p = Params(debug=False, planner=planner, gaze_method="Oxford", map_id=11, agent_number=10, agent_radius=15,
+               agent_max_speed=20)
+    worlds = generate_worlds(p, 11 + np.arange(B))
+    ox = planner == "Primitive"
+    eager = _env(p, B, worlds, auto_reset=True, oxford=ox)
+    graphed = _env(p, B, worlds, auto_reset=True, oxford=ox)
+    acts = torch.full((B,), 1.0 / 3, dtype=torch.float64, device="cuda:0")
+    static_a = torch.empty(B, dtype=torch.float64, device="cuda:0")
+
+    def one(env):
+        if ox:
+            env.plan_oxford(static_a)
+            env.step(static_a)
+        else:
+            env.step(acts)
+
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        one(eager)
+        one(graphed)                       # warm-up (sets kernel attributes) outside the capture
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(5):
+            one(graphed)
+    for _ in range(4):
+        g.replay()
+    for _ in range(20):
+        one(eager)
+    torch.cuda.synchronize()
+    for name in ("belief", "local_map", "drone_x", "drone_yaw", "agent_pos", "done", "steps", "tracker_mu"):
+        assert torch.equal(eager.buffer(name), graphed.buffer(name)), name
+    eager.close()
+    graphed.close()
