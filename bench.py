@@ -207,6 +207,8 @@ def main():
     ap.add_argument("--unique-worlds", type=int, default=0, help="cap distinct generated worlds (0 = all unique up to 8192)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps (reported in config)")
+    ap.add_argument("--strip-width", type=int, default=10, help="ray strip width: rays = ceil(500 / strip_width) (config 5 sweep: 10/5/2)")
+    ap.add_argument("--view-range", type=int, default=0, help="drone_view_range in degrees (config 5 sweep: 90/180/360)")
     ap.add_argument("--planner", default=None, choices=["NoMove", "Primitive"], help="override the config's planner")
     ap.add_argument("--gaze", default="scripted", choices=["scripted", "Oxford"],
                     help="scripted: random actions from the Oxford action set; Oxford: d2d_plan_oxford every step")
@@ -215,6 +217,11 @@ def main():
     if args.planner:
         cfg["params"] = dict(cfg["params"], planner=args.planner)
         cfg["name"] += " [planner=%s]" % args.planner
+    if args.view_range:
+        cfg["params"] = dict(cfg["params"], drone_view_range=args.view_range)
+        cfg["name"] += " [view_range=%d]" % args.view_range
+    if args.strip_width != 10:
+        cfg["name"] += " [strip_width=%d]" % args.strip_width
     if args.gaze == "Oxford":
         cfg["params"] = dict(cfg["params"], gaze_method="Oxford")
         cfg["name"] += " [gaze=Oxford on device]"
@@ -248,7 +255,8 @@ def main():
     p = Params(debug=False, **pk)
     use_ox = args.gaze == "Oxford"
     env = Drone2DVecEnv(p, B, seeds=seeds, worlds=worlds, device=dev, auto_reset=True, trackers=True, oxford=use_ox,
-                        envs_per_block=args.envs_per_block)
+                        envs_per_block=args.envs_per_block, strip_width=args.strip_width)
+    n_rays = int(env.cfg.n_rays)
     ox_out = torch.empty(B, dtype=torch.float64, device=dev)
 
     def do_step(a):
@@ -348,13 +356,13 @@ def main():
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["name"], "envs_per_gpu": B, "agents_per_env": N, "rays_per_env_step": N_RAYS,
+            "config": {"workload": cfg["name"], "envs_per_gpu": B, "agents_per_env": N, "rays_per_env_step": n_rays,
                        "planner": cfg["params"]["planner"], "gaze": args.gaze, "trackers": True, "auto_reset": True,
                        "unique_worlds_per_gpu": int(unique), "world_gen_s": round(t_world, 2),
                        "l2": "no flush (state stays L2-resident)" if flush is None else
                              "flushed between timed steps (256 MiB fill, untimed; per-step CUDA events summed)",
                        "envs_per_block": env.cfg.envs_per_block, "parallelism": "env-sharded x%d" % world},
-            "rays_per_sec": value * N_RAYS,
+            "rays_per_sec": value * n_rays,
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": B * 8,
                     "d2h_bytes_per_step": B * (1089 + 4 + 1), "steps": Ke},
             "gpu_launches": int(launches),

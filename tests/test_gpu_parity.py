@@ -255,3 +255,45 @@ def test_error_paths_are_loud():
     with pytest.raises(ValueError):
         env.step(torch.zeros(3, dtype=torch.float64, device="cuda:0"))
     env.close()
+
+
+def test_trackers_disabled_and_primitive_step_host():
+    """cfg.trackers = 0 skips the Kalman filters only (perception, flags and observation unchanged); the host-buffer
+    entry point drives the Primitive path as well."""
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200.world import generate_worlds
+    B = 10
+    p = Params(debug=False, planner="NoMove", map_id=60, agent_number=10, agent_radius=15, agent_max_speed=20)
+    worlds = generate_worlds(p, 60 + np.arange(B))
+    env = _env(p, B, worlds, auto_reset=False, trackers=False)
+    oracles = [util.oracle_env_from_world(p, worlds, i) for i in range(B)]
+    for t in range(40):
+        env.step(torch.full((B,), -1.0 / 3, dtype=torch.float64, device="cuda:0"))
+        for e in oracles:
+            e.step(-1.0 / 3)
+        torch.cuda.synchronize()
+        bel, hit = env.buffer("belief").cpu().numpy(), env.buffer("hit").cpu().numpy()
+        lm, dn = env.buffer("local_map").cpu().numpy(), env.buffer("done").cpu().numpy()
+        for i, e in enumerate(oracles):
+            assert np.array_equal(bel[i], e.belief) and np.array_equal(hit[i], e.hit) and int(dn[i]) == e.c.done, (t, i)
+            assert np.array_equal(lm[i, 0], e.local_map)
+    assert int(env.buffer("tracker_active").sum()) == 0
+    env.close()
+
+    pp = Params(debug=False, planner="Primitive", map_id=61, agent_number=8, agent_radius=15, agent_max_speed=20)
+    w2 = generate_worlds(pp, 61 + np.arange(B))
+    env = _env(pp, B, w2, auto_reset=False, oxford=False)
+    oracles = [util.oracle_env_from_world(pp, w2, i) for i in range(B)]
+    acts = torch.full((B,), 2.0 / 3, dtype=torch.float64).pin_memory()
+    lm = torch.empty((B, 1, 33, 33), dtype=torch.uint8).pin_memory()
+    yaw = torch.empty((B,), dtype=torch.float32).pin_memory()
+    dn = torch.empty((B,), dtype=torch.uint8).pin_memory()
+    for t in range(60):
+        env.step_host(acts, lm, yaw, dn)
+        for i, e in enumerate(oracles):
+            if e.c.done:
+                continue
+            e.step(2.0 / 3)
+            assert np.array_equal(lm[i, 0].numpy(), e.local_map) and int(dn[i]) == e.c.done, (t, i)
+            assert float(yaw[i]) == float(np.float32(e.c.yaw_obs))
+    env.close()
