@@ -392,6 +392,46 @@ __device__ __forceinline__ double d2d_node_total(double cost, double px, double 
     return cost + 0.5 * d2d_norm2(px - tx, py - ty) + 0.1 * d2d_norm2(vx, vy);
 }
 
+// ------------------------------------------------------------------------------------------ A* fast collision test
+// largest double T with sqrt_rn(T) <= R: then `np.linalg.norm(d) <= R`  <=>  fma(dy,dy,dx*dx) <= T  exactly
+// (sqrt is correctly rounded and monotone), which removes the square root from the per-sample tracker test.
+__device__ __forceinline__ double d2d_sq_threshold(double R) {
+    if (!(R >= 0.0)) return -1.0;
+    double c = R * R;
+    for (int it = 0; it < 8 && d2d_sqrt(c) > R; it++) c = __longlong_as_double(__double_as_longlong(c) - 1);
+    for (int it = 0; it < 8; it++) {
+        const double up = __longlong_as_double(__double_as_longlong(c) + 1);
+        if (d2d_sqrt(up) <= R) c = up; else break;
+    }
+    return c;
+}
+
+// Planner.is_free (traj_planner.py:28-59) for the A* samples, whose coordinates are integer-valued doubles
+// (np.around, traj_planner.py:181): cells by integer arithmetic.  trk = [mu0, mu1, mu2, mu3, radius, T] per tracker.
+__device__ __forceinline__ int d2d_belief_probe_int(const uint8_t *bel, int x, int y, int w, int h) {
+    if (x >= w || x < 0 || y >= h || y < 0) return 1;            // utils.py:546-547
+    return bel[(x / 10) * D2D_GRID + (y / 10)];
+}
+__device__ __forceinline__ bool d2d_is_free_int(const DevP &P, const uint8_t *bel, double px, double py, double t,
+                                                const double *trk6, int nact) {
+    if (px != px || py != py) return false;
+    if (!(fabs(px) < 1e6 && fabs(py) < 1e6)) return false;       // far outside the map: every probe returns OCCUPIED
+    const int x = (int)px, y = (int)py, sd = (int)(P.drone_r + 10.0), w = (int)P.map_w, h = (int)P.map_h;
+    if (d2d_belief_probe_int(bel, x - sd, y, w, h) == 1) return false;
+    if (d2d_belief_probe_int(bel, x, y, w, h) == 1) return false;
+    if (d2d_belief_probe_int(bel, x + sd, y, w, h) == 1) return false;
+    if (d2d_belief_probe_int(bel, x, y - sd, w, h) == 1) return false;
+    if (d2d_belief_probe_int(bel, x, y + sd, w, h) == 1) return false;
+#pragma unroll 1
+    for (int k = 0; k < nact; k++) {
+        const double *m = trk6 + 6 * k;
+        const double ex = m[0] + t * m[2], ey = m[1] + t * m[3];   // estimate_pos utils.py:220-223
+        const double ddx = px - ex, ddy = py - ey;
+        if (D2D_FMA(ddy, ddy, ddx * ddx) <= m[5]) return false;    // norm(...) <= drone_r + radius + 5 + var_cam
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------ A* kernel
 // One block per planning env (persistent over the compacted list).  Per-search hot state lives in shared memory when
 // it fits (8x8 primitives: open-set totals 51 KB + 32-bit-key hash 48 KB, two blocks per SM): the argmin over the open set, the dict
@@ -411,7 +451,7 @@ struct PlanHot {                        // pointers into shared memory (fast pat
 };
 
 __host__ __device__ inline size_t d2d_plan_smem_bytes(int NP, int n_u, int n_samp) {
-    size_t b = D2D_BELIEF_STRIDE + (size_t)NP * 5 * 8 + 256 + (size_t)n_u * n_u;   // belief, trackers, scratch, prim_ok
+    size_t b = D2D_BELIEF_STRIDE + (size_t)NP * 6 * 8 + 256 + (size_t)n_u * n_u;   // belief, trackers, scratch, prim_ok
     if (d2d_plan_cap(n_u) <= D2D_PLAN_SMEM_NODES)
         b += (size_t)D2D_PLAN_SMEM_NODES * 8 + (size_t)D2D_PLAN_SMEM_HASH * 6;
     return (b + 15) / 16 * 16;
@@ -454,8 +494,8 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = T >> 5;
     const int nu = P.n_u, nprim = nu * nu, nsamp = P.n_samp;
     uint8_t *bel = psm;                                         // [2560]
-    double *trk = (double *)(psm + D2D_BELIEF_STRIDE);          // [NP][5]
-    double *red_v = trk + (size_t)P.NP * 5;                     // [8] warp partials
+    double *trk = (double *)(psm + D2D_BELIEF_STRIDE);          // [NP][6]
+    double *red_v = trk + (size_t)P.NP * 6;                     // [8] warp partials
     int *red_i = (int *)(red_v + 8);                            // [8]
     int *sh = red_i + 8;                                        // [8] cur, n_nodes, n_open, -, nact
     int *wsum = sh + 8;                                         // [8] warp prefix
@@ -464,7 +504,7 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
     PlanHot h;
     h.fast = d2d_plan_cap(nu) <= D2D_PLAN_SMEM_NODES && P.max_speed < 60.0;
     if (h.fast) {
-        unsigned char *q = psm + ((size_t)D2D_BELIEF_STRIDE + (size_t)P.NP * 40 + 256 + nprim + 15) / 16 * 16;
+        unsigned char *q = psm + ((size_t)D2D_BELIEF_STRIDE + (size_t)P.NP * 48 + 256 + nprim + 15) / 16 * 16;
         h.open_total = (double *)q; q += (size_t)D2D_PLAN_SMEM_NODES * 8;
         h.cost = w.cost;                                        // only read on dict hits: stays in the L2-resident workspace
         h.hkeys32 = (uint32_t *)q; q += (size_t)D2D_PLAN_SMEM_HASH * 4;
@@ -488,7 +528,18 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
         }
         if (tid == 0) sh[4] = 0;
         __syncthreads();
-        d2d_gather_trackers(P, e, trk, &sh[4], tid, T);
+#pragma unroll 1
+        for (int k = tid; k < P.N; k += T) {        // active trackers + the exact squared clearance threshold
+            const size_t g = (size_t)e * P.NP + k;
+            if (P.trk_active[g]) {
+                const int slot = atomicAdd(&sh[4], 1);
+                const double *mu = P.trk_mu + g * 4;
+                double *d = trk + 6 * slot;
+                const double rad = P.trk_radius[g];
+                d[0] = mu[0]; d[1] = mu[1]; d[2] = mu[2]; d[3] = mu[3]; d[4] = rad;
+                d[5] = d2d_sq_threshold(P.drone_r + rad + 5.0 + P.var_cam);
+            }
+        }
         const double tx = P.target_x[e], ty = P.target_y[e];
         if (tid == 0) {   // start node (traj_planner.py:136-146)
             const double x = P.drone_x[e], y = P.drone_y[e], vx = P.drone_vx[e], vy = P.drone_vy[e];
@@ -547,7 +598,7 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
                     const double t = P.tab->t_samp[sI], t2 = P.tab->t_samp2[sI];
                     const double qx = rint(D2D_FMA(t2, xa / 2.0, 1.0 * cpx + t * cvx));
                     const double qy = rint(D2D_FMA(t2, ya / 2.0, 1.0 * cpy + t * cvy));
-                    ok = d2d_is_free(P, bel, qx, qy, t + (double)(citr * 2), trk, nact);
+                    ok = d2d_is_free_int(P, bel, qx, qy, t + (double)(citr * 2), trk, nact);
                 }
                 if (!ok) prim_ok[pidx] = 0;
             }
