@@ -555,9 +555,29 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
         const int nact = sh[4];
         int goal = -1;
         bool success = false;
+        // loop-invariant per-thread work items: up to two (primitive, sample) pairs and one successor primitive
+        const int nitems = nprim * nsamp;
+        const bool two_items = nitems <= 2 * T;
+        int it_p[2] = {0, 0};
+        double it_xh[2] = {0, 0}, it_yh[2] = {0, 0}, it_t[2] = {0, 0}, it_t2[2] = {0, 0};
+        bool it_ok[2] = {false, false};
+        if (two_items) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int q = tid + j * T;
+                if (q < nitems) {
+                    const int pidx = q / nsamp, sI = q - pidx * nsamp, ia = pidx / nu, ib = pidx - ia * nu;
+                    it_ok[j] = true; it_p[j] = pidx;
+                    it_xh[j] = P.tab->u_space[ia] / 2.0; it_yh[j] = P.tab->u_space[ib] / 2.0;
+                    it_t[j] = P.tab->t_samp[sI]; it_t2[j] = P.tab->t_samp2[sI];
+                }
+            }
+        }
+        // norm([nvx, nvy]) < max_speed  <=>  fma(nvy, nvy, nvx*nvx) <= speed_thr   (exact, no sqrt per item)
+        const double speed_thr = d2d_sq_threshold(__longlong_as_double(__double_as_longlong(P.max_speed) - 1));
+        int n_nodes = 1, n_open = 1;                     // replicated in every thread (all take the same decisions)
         for (int itr = 1;; itr++) {
-            const int n_nodes = sh[1];
-            if (sh[2] == 0 || itr >= 100) break;                 // traj_planner.py:149
+            if (n_open == 0 || itr >= 100) break;                // traj_planner.py:149
             // ---- first minimal total_cost in insertion order (min() over a dict, :155-158)
             double bv = INFINITY;
             int bi = 0x7fffffff;
@@ -571,48 +591,61 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
                 if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
             }
             if (lane == 0) { red_v[wid] = bv; red_i[wid] = bi; }
-            __syncthreads();
-            if (tid == 0) {
-                for (int q = 1; q < NW; q++)
-                    if (red_v[q] < bv || (red_v[q] == bv && red_i[q] < bi)) { bv = red_v[q]; bi = red_i[q]; }
-                sh[0] = bi;
-                if (bi != 0x7fffffff) { h.open_total[bi] = INFINITY; sh[2] -= 1; }   // open -> closed (:167-170)
-            }
             for (int q = tid; q < nprim; q += T) prim_ok[q] = 1;
             __syncthreads();
-            const int cur = sh[0];
+            bv = red_v[0]; bi = red_i[0];
+            for (int q = 1; q < NW; q++)
+                if (red_v[q] < bv || (red_v[q] == bv && red_i[q] < bi)) { bv = red_v[q]; bi = red_i[q]; }
+            const int cur = bi;
             if (cur == 0x7fffffff) break;                        // only non-finite costs left (cannot happen)
             const double cpx = w.px[cur], cpy = w.py[cur], cvx = w.vx[cur], cvy = w.vy[cur], ccost = h.cost[cur];
             const int citr = w.itr[cur];
-            if (d2d_norm2(cpx - tx, cpy - ty) <= 10.0) {         // :160 (the node stays in the open set in the reference,
-                goal = cur; success = true; break;               //       which no longer matters once the search ends)
+            if (d2d_norm2(cpx - tx, cpy - ty) <= 10.0) {         // :160
+                goal = cur; success = true; break;
             }
+            if (tid == 0) h.open_total[cur] = INFINITY;          // open -> closed (:167-170); visible after the next sync
+            n_open -= 1;
             // ---- collision checks of all (primitive, sample) pairs (:174-185)
-            for (int q = tid; q < nprim * nsamp; q += T) {
-                const int pidx = q / nsamp, sI = q - pidx * nsamp;
-                const int ia = pidx / nu, ib = pidx - ia * nu;
-                const double xa = P.tab->u_space[ia], ya = P.tab->u_space[ib];
-                const double nvx = 1.0 * cvx + 4.0 * (xa / 2.0), nvy = 1.0 * cvy + 4.0 * (ya / 2.0);
-                bool ok = d2d_norm2(nvx, nvy) < P.max_speed;     // :176
-                if (ok && prim_ok[pidx]) {
-                    const double t = P.tab->t_samp[sI], t2 = P.tab->t_samp2[sI];
-                    const double qx = rint(D2D_FMA(t2, xa / 2.0, 1.0 * cpx + t * cvx));
-                    const double qy = rint(D2D_FMA(t2, ya / 2.0, 1.0 * cpy + t * cvy));
-                    ok = d2d_is_free_int(P, bel, qx, qy, t + (double)(citr * 2), trk, nact);
+            const double gt0 = (double)(citr * 2);
+            if (two_items) {
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    if (!it_ok[j]) continue;
+                    const double nvx = 1.0 * cvx + 4.0 * it_xh[j], nvy = 1.0 * cvy + 4.0 * it_yh[j];
+                    bool ok = D2D_FMA(nvy, nvy, nvx * nvx) <= speed_thr;     // :176
+                    if (ok && prim_ok[it_p[j]]) {
+                        const double qx = rint(D2D_FMA(it_t2[j], it_xh[j], 1.0 * cpx + it_t[j] * cvx));
+                        const double qy = rint(D2D_FMA(it_t2[j], it_yh[j], 1.0 * cpy + it_t[j] * cvy));
+                        ok = d2d_is_free_int(P, bel, qx, qy, it_t[j] + gt0, trk, nact);
+                    }
+                    if (!ok) prim_ok[it_p[j]] = 0;
                 }
-                if (!ok) prim_ok[pidx] = 0;
+            } else {
+                for (int q = tid; q < nitems; q += T) {
+                    const int pidx = q / nsamp, sI = q - pidx * nsamp;
+                    const int ia = pidx / nu, ib = pidx - ia * nu;
+                    const double xh = P.tab->u_space[ia] / 2.0, yh = P.tab->u_space[ib] / 2.0;
+                    const double nvx = 1.0 * cvx + 4.0 * xh, nvy = 1.0 * cvy + 4.0 * yh;
+                    bool ok = D2D_FMA(nvy, nvy, nvx * nvx) <= speed_thr;
+                    if (ok && prim_ok[pidx]) {
+                        const double t = P.tab->t_samp[sI], t2 = P.tab->t_samp2[sI];
+                        const double qx = rint(D2D_FMA(t2, xh, 1.0 * cpx + t * cvx));
+                        const double qy = rint(D2D_FMA(t2, yh, 1.0 * cpy + t * cvy));
+                        ok = d2d_is_free_int(P, bel, qx, qy, t + gt0, trk, nact);
+                    }
+                    if (!ok) prim_ok[pidx] = 0;
+                }
             }
             __syncthreads();
             // ---- successors in (x_acc, y_acc) loop order, T primitives at a time (:187-206)
             for (int base = 0; base < nprim; base += T) {
                 const int pidx = base + tid;
                 const bool ok = pidx < nprim && prim_ok[pidx];
-                double xa = 0, ya = 0, nvx = 0, nvy = 0, spx = 0, spy = 0, scost = 0;
+                double nvx = 0, nvy = 0, spx = 0, spy = 0, scost = 0;
                 int slot = -1, exist_idx = -1;
                 bool is_new = false;
                 if (ok) {
-                    xa = P.tab->u_space[pidx / nu];
-                    ya = P.tab->u_space[pidx - (pidx / nu) * nu];
+                    const double xa = P.tab->u_space[pidx / nu], ya = P.tab->u_space[pidx - (pidx / nu) * nu];
                     nvx = 1.0 * cvx + 4.0 * (xa / 2.0);
                     nvy = 1.0 * cvy + 4.0 * (ya / 2.0);
                     spx = rint((1.0 * cpx + 2.0 * cvx) + 4.0 * (xa / 2.0));   // :188
@@ -631,10 +664,9 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
                     if (q < wid) before += wsum[q];
                     tot_new += wsum[q];
                 }
-                const int nn = sh[1];
                 int idx = -1;
                 if (is_new) {
-                    idx = nn + before + wrank;
+                    idx = n_nodes + before + wrank;
                     if (h.fast) h.hvals16[slot] = (uint16_t)idx; else w.hvals[slot] = idx;
                 } else if (ok) {
                     // in closed_set -> skip; in open_set -> replace if cheaper, keeping the dict slot (:197-206)
@@ -645,9 +677,8 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
                     h.open_total[idx] = d2d_node_total(scost, spx, spy, nvx, nvy, tx, ty);
                     w.parent[idx] = cur; w.itr[idx] = citr + 1; w.act[idx] = pidx;
                 }
-                __syncthreads();
-                if (tid == 0) { sh[1] = nn + tot_new; sh[2] += tot_new; }
-                __syncthreads();
+                n_nodes += tot_new; n_open += tot_new;
+                __syncthreads();      // new nodes / wsum reuse visible before the next chunk or the next argmin
             }
         }
         __syncthreads();
