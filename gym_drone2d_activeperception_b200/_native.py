@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(HERE, "libdrone2d.so")
 
 MAX_TARGETS, MAX_U, MAX_SAMP, MAX_WAY, MAX_YAW = 8, 64, 32, 64, 16
 NUM_STATS = 16
+GAZE = {"NoControl": 0, "Rotating": 1, "LookAhead": 2, "LookGoal": 3}
 BELIEF_STRIDE = 2560
 STAT_NAMES = ["env_steps", "episodes", "success", "static_collision", "dynamic_collision", "freezing", "dead_lock",
               "flight_steps", "grid_discovered", "agents_tracked", "tracked_steps", "plans", "plan_failures", "replans",
@@ -39,7 +40,7 @@ class D2DBufferInfo(C.Structure):
 
 
 EXPORTS = ["d2d_version", "d2d_last_error", "d2d_create", "d2d_destroy", "d2d_set_world", "d2d_reset", "d2d_step",
-           "d2d_step_host", "d2d_plan_oxford", "d2d_set_drone_pose", "d2d_get_buffer", "d2d_stats",
+           "d2d_step_host", "d2d_plan_oxford", "d2d_plan_gaze", "d2d_set_drone_pose", "d2d_get_buffer", "d2d_stats",
            "d2d_launch_count"]
 
 _lib = None
@@ -70,6 +71,7 @@ def load():
     L.d2d_step.argtypes = [vp, vp, vp]
     L.d2d_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.d2d_plan_oxford.argtypes = [vp, vp, vp]
+    L.d2d_plan_gaze.argtypes = [vp, C.c_int32, vp, vp]
     L.d2d_set_drone_pose.argtypes = [vp, vp, vp]
     L.d2d_get_buffer.argtypes = [vp, C.c_char_p, C.POINTER(D2DBufferInfo)]
     L.d2d_stats.argtypes = [vp, vp, C.c_int32, vp]

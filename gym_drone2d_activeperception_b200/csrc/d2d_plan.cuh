@@ -1034,3 +1034,56 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         actions_out[e] = P.tab->v_yaw_space[best] / P.max_yaw_speed;
     }
 }
+
+
+// ------------------------------------------------------------------------------------------ scalar gaze policies
+// NoControl / Rotating / LookAhead / LookGoal (yaw_planner.py:10-39, 136-142, 225-255), one warp per env.
+// atan2 is CUDA's (<= 2 ulp; glibc's differs at the ulp level): actions are held to 1e-12, not bit-exact, unless they
+// saturate at +-1 (the common case).
+__device__ __forceinline__ double d2d_turn_towards(const DevP &P, double target_yaw, double yaw) {
+    const double m = P.max_yaw_speed;
+    double v = (target_yaw - yaw) / P.dt;
+    v = v < m ? v : m;
+    v = v > -m ? v : -m;
+    if (!(fabs(target_yaw - yaw) < 180.0)) v = -v;
+    return v / m;
+}
+
+__global__ void __launch_bounds__(128) d2d_gaze_kernel(const DevP P, int policy, double *__restrict__ actions_out) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= P.B) return;
+    const double RAD2DEG = 180.0 / D2D_PI;      // CPython math.degrees
+    // an env that reported done and will be re-initialised by its next step is seen as freshly reset
+    const bool fresh = P.pending_reset[e] || (P.auto_reset && P.done[e]);
+    double a = 0.0;
+    if (policy == D2D_GAZE_ROTATING) a = 1.0;
+    else if (policy == D2D_GAZE_LOOKAHEAD) {
+        const double vx = fresh ? 0.0 : P.drone_vx[e], vy = fresh ? 0.0 : P.drone_vy[e];
+        if (!(vy == 0.0 && vx == 0.0)) {
+            const double ty = d2d_pymod(atan2(-vy, vx) * RAD2DEG, 360.0);
+            a = d2d_turn_towards(P, ty, P.drone_yaw[e]);
+        }
+    } else if (policy == D2D_GAZE_LOOKGOAL) {
+        const int cursor = P.traj_cursor[e];
+        const int len = fresh ? 0 : P.traj_nseg[e] * P.n_way - cursor;
+        if (len > 0) {
+            const uint8_t *bel = P.belief + (size_t)e * D2D_BELIEF_STRIDE;
+            int first = len;                       // first waypoint lying in an UNEXPLORED belief cell
+#pragma unroll 1
+            for (int w = lane; w < len && w < first; w += 32) {
+                double x, y;
+                d2d_waypoint_pos(P, e, cursor + w, x, y);
+                const bool inb = !(x >= P.map_w || x < 0 || y >= P.map_h || y < 0);
+                if (inb && bel[d2d_cell(x, P.scale, P.inv_scale) * D2D_GRID + d2d_cell(y, P.scale, P.inv_scale)] == 0)
+                    first = w;
+            }
+            for (int off = 16; off > 0; off >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, off));
+            double xl, yl;
+            d2d_waypoint_pos(P, e, cursor + (first < len ? first : len - 1), xl, yl);
+            const double ty = d2d_pymod(atan2(-(yl - P.drone_y[e]), xl - P.drone_x[e]) * RAD2DEG, 360.0);
+            a = d2d_turn_towards(P, ty, P.drone_yaw[e]);
+        }
+    }
+    if (lane == 0) actions_out[e] = a;
+}

@@ -76,3 +76,14 @@ extern "C" int d2d_plan_oxford(d2d_handle *h, double *actions_out_dev, void *str
     CUDA_TRY(h, cudaGetLastError());
     return D2D_OK;
 }
+
+extern "C" int d2d_plan_gaze(d2d_handle *h, int32_t policy, double *actions_out_dev, void *stream) {
+    if (!h || !actions_out_dev) return D2D_ERR_INVALID;
+    if (policy < D2D_GAZE_NOCONTROL || policy > D2D_GAZE_LOOKGOAL) { h->err = "d2d_plan_gaze: unknown policy"; return D2D_ERR_INVALID; }
+    if (!h->world_set) { h->err = "d2d_plan_gaze before d2d_set_world"; return D2D_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    d2d_gaze_kernel<<<(h->B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(h->P, policy, actions_out_dev);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return D2D_OK;
+}

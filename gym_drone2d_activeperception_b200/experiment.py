@@ -57,15 +57,17 @@ class Experiment(object):
 
 
 def run_batched(params, num_envs, steps, device="cuda:0", seeds=None):
-    """Plays `steps` env-steps of `num_envs` seeded envs (auto-reset on) with the params' gaze method evaluated on the
-    device (Oxford) or scripted (anything else -> NoControl's 0 action).  Returns the statistics dict."""
+    """Plays `steps` env-steps of `num_envs` seeded envs (auto-reset on) with the params' gaze method (Oxford, LookAhead,
+    LookGoal, Rotating, NoControl) evaluated on the device.  Returns the statistics dict."""
     import torch
     from .vec_env import Drone2DVecEnv
-    use_ox = params.gaze_method == "Oxford"
-    env = Drone2DVecEnv(params, num_envs, seeds=seeds, device=device, auto_reset=True, oxford=use_ox)
-    zero = torch.zeros(num_envs, dtype=torch.float64, device=env.device)
+    if params.gaze_method == "NoControl":
+        params.drone_view_range = 360                            # experiment.py:28-29
+    env = Drone2DVecEnv(params, num_envs, seeds=seeds, device=device, auto_reset=True,
+                        oxford=params.gaze_method == "Oxford")
+    out = torch.empty(num_envs, dtype=torch.float64, device=env.device)
     for _ in range(steps):
-        env.step(env.plan_oxford() if use_ox else zero)
+        env.step(env.plan_gaze(params.gaze_method, out))
     st = env.stats()
     env.close()
     return dict(zip(_native.STAT_NAMES, [int(v) for v in st]))

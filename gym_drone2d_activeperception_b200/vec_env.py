@@ -264,6 +264,17 @@ class Drone2DVecEnv(object):
         self._check(self._lib.d2d_plan_oxford(self._h, C.c_void_p(out.data_ptr()), self._stream()), "d2d_plan_oxford")
         return out
 
+    def plan_gaze(self, policy, out=None):
+        """NoControl / Rotating / LookAhead / LookGoal .plan for every env (yaw_planner.py), on the device.
+        policy: name or d2d_gaze value.  'Oxford' is routed to plan_oxford()."""
+        if policy == "Oxford":
+            return self.plan_oxford(out)
+        code = _native.GAZE[policy] if isinstance(policy, str) else int(policy)
+        if out is None:
+            out = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+        self._check(self._lib.d2d_plan_gaze(self._h, code, C.c_void_p(out.data_ptr()), self._stream()), "d2d_plan_gaze")
+        return out
+
     def stats(self, reset=False):
         """Episode statistics accumulated on device (int64 [16], names in _native.STAT_NAMES)."""
         out = np.zeros(_native.NUM_STATS, dtype=np.int64)

@@ -46,6 +46,9 @@ typedef enum d2d_status {
 
 typedef enum d2d_planner { D2D_PLANNER_NOMOVE = 0, D2D_PLANNER_PRIMITIVE = 1 } d2d_planner;
 
+/* scalar gaze policies of yaw_planner.py that d2d_plan_gaze evaluates for every env */
+typedef enum d2d_gaze { D2D_GAZE_NOCONTROL = 0, D2D_GAZE_ROTATING = 1, D2D_GAZE_LOOKAHEAD = 2, D2D_GAZE_LOOKGOAL = 3 } d2d_gaze;
+
 typedef enum d2d_dtype { D2D_U8 = 0, D2D_I8 = 1, D2D_I32 = 2, D2D_I64 = 3, D2D_F32 = 4, D2D_F64 = 5 } d2d_dtype;
 
 /* indices into the statistics vector (episode totals, experiment.py:76-101 CSV columns) */
@@ -130,6 +133,10 @@ int d2d_step_host(d2d_handle *h, const double *actions_host, uint8_t *local_map_
 /* Replaces Oxford.plan(env.info) (yaw_planner.py:81-127) for all envs: writes the chosen action per env to
  * actions_out_dev (DEVICE [num_envs] f64) and advances the policy state.  Requires cfg.oxford = 1. */
 int d2d_plan_oxford(d2d_handle *h, double *actions_out_dev, void *stream);
+
+/* Replaces NoControl / Rotating / LookAhead / LookGoal .plan(env.info) (yaw_planner.py:10-39, 136-142, 225-255) for all envs:
+ * writes the action per env to actions_out_dev (DEVICE [num_envs] f64).  `policy` is a d2d_gaze value. */
+int d2d_plan_gaze(d2d_handle *h, int32_t policy, double *actions_out_dev, void *stream);
 
 /* Replaces direct writes to env.drone.x / .y / .yaw by the metric scripts
  * (script/difficulty_calculator/glob_survivability_calculator.py:36-37).  pose_host: [num_envs][3] f64 HOST. */

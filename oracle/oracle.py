@@ -86,6 +86,8 @@ def lib():
         L.d2do_step.restype = C.c_int
         L.d2do_oxford_plan.argtypes = [_P(Env)]
         L.d2do_oxford_plan.restype = C.c_double
+        L.d2do_policy_plan.argtypes = [_P(Env), C.c_int]
+        L.d2do_policy_plan.restype = C.c_double
         L.d2do_run_many.argtypes = [_P(_P(Env)), C.c_int, C.c_int, _P(C.c_double)]
         L.d2do_run_many.restype = C.c_int64
         L.d2do_sizeof_params.restype = C.c_size_t
@@ -209,6 +211,10 @@ class OracleEnv(object):
 
     def oxford_plan(self):
         return float(lib().d2do_oxford_plan(self._ptr))
+
+    def policy_plan(self, kind):
+        """kind: 0 NoControl, 1 Rotating, 2 LookAhead, 3 LookGoal (yaw_planner.py)"""
+        return float(lib().d2do_policy_plan(self._ptr, int(kind)))
 
     def trajectory(self):
         h, l = self.c.traj_head, self.c.traj_len

@@ -104,8 +104,8 @@ def run_episode(steps, actions=None, policy=None, set_pose=None, stop_on_done=Fa
     n = len(env.agents)
 
     pol = None
-    if policy == "Oxford":
-        pol = ref_yaw.Oxford
+    if policy is not None:
+        pol = getattr(ref_yaw, policy)      # class object used as the instance, as experiment.py:33-34 does
         pol.__init__(pol, params)
 
     # observe castRays' measurement list without touching the reference source
@@ -153,7 +153,7 @@ def run_episode(steps, actions=None, policy=None, set_pose=None, stop_on_done=Fa
         for t in range(steps):
             if pol is not None:
                 a = pol.plan(pol, env.info)
-                if record_oxford:
+                if record_oxford and policy == "Oxford":
                     rec["ox_last"].append(pol.last_time_observed_map.copy())
             else:
                 a = actions[t % len(actions)]

@@ -219,3 +219,39 @@ def test_cuda_graph_capture_replays_steps(planner):
         assert torch.equal(eager.buffer(name), graphed.buffer(name)), name
     eager.close()
     graphed.close()
+
+
+@pytest.mark.parametrize("policy,kind", [("LookAhead", 2), ("LookGoal", 3), ("Rotating", 1), ("NoControl", 0)])
+def test_scalar_gaze_policies_on_device(policy, kind):
+    """d2d_plan_gaze vs the oracle's restatement of yaw_planner.py.  atan2 on the device is CUDA's (not glibc's), so
+    unsaturated actions are held to 1e-12 and the oracle is driven with the DEVICE's actions (state compared as usual)."""
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200.world import generate_worlds
+    B, steps = 12, 150
+    p = Params(debug=False, planner="Primitive", gaze_method=policy, map_id=800, agent_number=8, agent_radius=15,
+               agent_max_speed=20)
+    worlds = generate_worlds(p, 800 + np.arange(B))
+    env = _env(p, B, worlds, auto_reset=True, oxford=False)
+    n = env.num_agents
+    oracles = [util.oracle_env_from_world(p, worlds, i) for i in range(B)]
+    unsat = 0
+    for t in range(steps):
+        a = env.plan_gaze(policy)
+        torch.cuda.synchronize()
+        ah = a.cpu().numpy()
+        for i in range(B):
+            if oracles[i].c.done:
+                oracles[i].close()
+                oracles[i] = util.oracle_env_from_world(p, worlds, i)
+            ref = oracles[i].policy_plan(kind)
+            assert abs(ah[i] - ref) <= 1e-12 * max(1.0, abs(ref)), (policy, t, i, ah[i], ref)
+            unsat += int(abs(ref) not in (0.0, 1.0))
+        env.step(a)
+        for i in range(B):
+            oracles[i].step(float(ah[i]))
+        h = _host(env)
+        for i, e in enumerate(oracles):
+            _cmp_env_to_oracle(h, i, e, n, t, policy)
+    if policy in ("LookAhead", "LookGoal"):
+        assert unsat > 0
+    env.close()

@@ -64,3 +64,23 @@ def test_world_generation_live(kw):
         assert np.array_equal(w["agent_pos"], ws["agent_pos0"]) and np.array_equal(w["agent_pref"], ws["agent_pref0"])
         assert np.array_equal(w["agent_radius"], ws["agent_radius"]) and np.array_equal(w["tracker_radius"], ws["tracker_radius"])
         assert np.array_equal(w["gt_grid"] == 1, ws["gt_grid"] == 1), seed
+
+
+@pytest.mark.parametrize("policy,kind", [("LookAhead", 2), ("LookGoal", 3), ("Rotating", 1), ("NoControl", 0)])
+def test_scalar_gaze_policies_live(policy, kind):
+    """Oracle restatement of the scalar gaze policies (yaw_planner.py:10-39, 136-142, 225-255) vs the reference."""
+    from gym_drone2d_activeperception_b200.params import Params
+    kw = dict(planner="Primitive", map_id=7, agent_number=8, agent_radius=15, agent_max_speed=20, gaze_method=policy)
+    r = ref_runner.run_episode(150, policy=policy, stop_on_done=True, **kw)
+    P = r["params"]
+    p = Params(debug=False, **{k: P[k] for k in util.PARAM_KEYS if k in P}, init_pos=P["init_position"],
+               target_list=P["target_list"])
+    world = dict(agent_pos=r["agent_pos0"], agent_pref=r["agent_pref0"], agent_radius=r["agent_radius"],
+                 tracker_radius=r["tracker_radius"], gt_grid=r["gt_grid"], drone_pose=r["drone0"])
+    e = util.oracle_env_from_world(p, world)
+    for t in range(len(r["done"])):
+        a = e.policy_plan(kind)
+        assert a == r["action"][t], (policy, t, a, r["action"][t])
+        e.step(a)
+        assert np.array_equal(e.belief, r["belief"][t]) and (e.c.x, e.c.y, e.c.yaw) == tuple(r["drone"][t]), t
+    e.close()
