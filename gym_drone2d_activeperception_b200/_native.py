@@ -39,7 +39,7 @@ class D2DBufferInfo(C.Structure):
                 ("shape", C.c_int64 * 4), ("strides", C.c_int64 * 4)]
 
 
-EXPORTS = ["d2d_version", "d2d_last_error", "d2d_create", "d2d_destroy", "d2d_set_world", "d2d_reset", "d2d_step",
+EXPORTS = ["d2d_version", "d2d_last_error", "d2d_create", "d2d_destroy", "d2d_set_world", "d2d_set_rng", "d2d_reset", "d2d_step",
            "d2d_step_host", "d2d_plan_oxford", "d2d_plan_gaze", "d2d_set_drone_pose", "d2d_get_buffer", "d2d_stats",
            "d2d_launch_count"]
 
@@ -67,6 +67,7 @@ def load():
     L.d2d_create.argtypes = [C.POINTER(D2DConfig), C.POINTER(vp)]
     L.d2d_destroy.argtypes = [vp]
     L.d2d_set_world.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.d2d_set_rng.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
     L.d2d_reset.argtypes = [vp, vp, vp]
     L.d2d_step.argtypes = [vp, vp, vp]
     L.d2d_step_host.argtypes = [vp, vp, vp, vp, vp, vp]

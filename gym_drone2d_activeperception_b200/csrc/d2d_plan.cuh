@@ -248,6 +248,10 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     d2d_mbar_wait(c.mbar, 0);
     d2d_phase_rays_warp<false>(P, c, ro, lane);
     __syncwarp();
+    if (P.var_cam != 0.0) {
+        if (lane == 0) d2d_measure_env(P, c, e);
+        __syncwarp();
+    }
     d2d_phase_trackers(P, c, e, 1, lane, 32);
     __syncwarp();
     // ---- Primitive.replan_check (traj_planner.py:220-233)

@@ -60,6 +60,10 @@ struct DevP {
     int *tmp_act_cnt, *tmp_act_ts;   // still-active tracker totals, pre kernel -> post kernel
     uint8_t *ox_fresh;           // Oxford state already re-initialised for a pending reset
     int *obs_ix, *obs_iy;        // drone cell for which the local_map tensor content is currently valid
+    // legacy np.random stream per env (MT19937 + cached gaussian), consumed by noisy measurements (var_cam != 0)
+    uint32_t *rng_key, *rng_key0;   // [B][624] current / reset snapshot
+    int *rng_pos, *rng_pos0, *rng_has, *rng_has0;
+    double *rng_gauss, *rng_gauss0;
     // Oxford
     double *ox_last;             // [B][2500]
     unsigned long long *stats;   // [D2D_NUM_STATS]

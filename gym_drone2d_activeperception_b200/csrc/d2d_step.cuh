@@ -70,6 +70,7 @@ struct BlockCtx {
     uint8_t *belief;     // [E][D2D_BELIEF_STRIDE]
     uint64_t *gt;        // [E][50]
     double *sx, *sy, *sr2;  // [E][NP]
+    double *mx, *my;        // [E][NP] measurements handed to the trackers (== sx, sy when var_cam == 0)
     uint16_t *cull;      // [E][NP]
     uint32_t *hitw;      // [E][HW]
     EnvS *S;             // [E]
@@ -79,7 +80,7 @@ struct BlockCtx {
 
 __host__ __device__ inline size_t d2d_step_smem_bytes(int E, int NP, int HW) {
     size_t b = (size_t)E * D2D_BELIEF_STRIDE + (size_t)E * D2D_GT_ROW_BYTES;
-    b += (size_t)E * NP * 8 * 3;
+    b += (size_t)E * NP * 8 * 5;
     b += ((size_t)E * NP * 2 + 15) / 16 * 16;
     b += ((size_t)E * HW * 4 + 15) / 16 * 16;
     b += (size_t)E * sizeof(EnvS);
@@ -95,6 +96,8 @@ __device__ __forceinline__ BlockCtx d2d_carve(unsigned char *base, int E, int NP
     c.sx = (double *)(base + o); o += (size_t)E * NP * 8;
     c.sy = (double *)(base + o); o += (size_t)E * NP * 8;
     c.sr2 = (double *)(base + o); o += (size_t)E * NP * 8;
+    c.mx = (double *)(base + o); o += (size_t)E * NP * 8;
+    c.my = (double *)(base + o); o += (size_t)E * NP * 8;
     c.cull = (uint16_t *)(base + o); o += ((size_t)E * NP * 2 + 15) / 16 * 16;
     c.hitw = (uint32_t *)(base + o); o += ((size_t)E * HW * 4 + 15) / 16 * 16;
     c.S = (EnvS *)(base + o); o += (size_t)E * sizeof(EnvS);
@@ -177,6 +180,16 @@ __device__ D2D_COLD void d2d_reset_arrays(const DevP &P, const BlockCtx &c, int 
         if (!c.S[i].valid || !c.S[i].reset) continue;
         ((uint32_t *)(c.belief + (size_t)i * D2D_BELIEF_STRIDE))[o] = 0u;
         ((uint32_t *)(P.belief + (size_t)(env0 + i) * D2D_BELIEF_STRIDE))[o] = 0u;
+    }
+    if (P.rng_key) {   // reset() re-seeds np.random with map_id (drone_v2.py:80): restore the post-init stream state
+#pragma unroll 1
+        for (int w = tid; w < E * 624; w += T) {
+            const int i = w / 624, o = w - i * 624;
+            if (!c.S[i].valid || !c.S[i].reset) continue;
+            const size_t g = (size_t)(env0 + i) * 624 + o;
+            P.rng_key[g] = P.rng_key0[g];
+            if (o == 0) { const int e2 = env0 + i; P.rng_pos[e2] = P.rng_pos0[e2]; P.rng_has[e2] = P.rng_has0[e2]; P.rng_gauss[e2] = P.rng_gauss0[e2]; }
+        }
     }
     if (P.ox_last) {
 #pragma unroll 1
@@ -400,6 +413,63 @@ __device__ __forceinline__ void d2d_phase_rays_warp(const DevP &P, const BlockCt
     }
 }
 
+// ------------------------------------------------------------------------------------------ noisy measurements
+// NumPy legacy RandomState (MT19937 + polar gaussian with a cached second value), one stream per env, continued from the
+// state left by world generation (drone_v2.py:80, 54).  utils.py:605 draws randn(2) for every in-view agent in index
+// order, so lane 0 walks the hit mask sequentially.
+struct D2DRng {
+    uint32_t *key;      // [624] in HBM
+    int pos, has;
+    double gauss;
+};
+__device__ __noinline__ void d2d_mt_regen(uint32_t *mt) {
+    const uint32_t UP = 0x80000000u, LO = 0x7fffffffu, MA = 0x9908b0dfu;
+    int kk;
+    uint32_t y;
+#pragma unroll 1
+    for (kk = 0; kk < 624 - 397; kk++) { y = (mt[kk] & UP) | (mt[kk + 1] & LO); mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? MA : 0u); }
+#pragma unroll 1
+    for (; kk < 623; kk++) { y = (mt[kk] & UP) | (mt[kk + 1] & LO); mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? MA : 0u); }
+    y = (mt[623] & UP) | (mt[0] & LO); mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? MA : 0u);
+}
+__device__ __forceinline__ uint32_t d2d_mt_next32(D2DRng &r) {
+    if (r.pos == 624) { d2d_mt_regen(r.key); r.pos = 0; }
+    uint32_t y = r.key[r.pos++];
+    y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+    return y;
+}
+__device__ __forceinline__ double d2d_mt_next_double(D2DRng &r) {
+    const int a = (int)(d2d_mt_next32(r) >> 5), b = (int)(d2d_mt_next32(r) >> 6);
+    return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+}
+__device__ __noinline__ double d2d_legacy_gauss(D2DRng &r) {
+    if (r.has) { const double t = r.gauss; r.has = 0; r.gauss = 0.0; return t; }
+    double f, x1, x2, r2;
+    do {
+        x1 = 2.0 * d2d_mt_next_double(r) - 1.0;
+        x2 = 2.0 * d2d_mt_next_double(r) - 1.0;
+        r2 = x1 * x1 + x2 * x2;
+    } while (r2 >= 1.0 || r2 == 0.0);
+    f = D2D_SQRT(-2.0 * log(r2) / r2);        // device log: <= 1 ulp from glibc's (continuous tolerance 1e-9)
+    r.gauss = f * x1; r.has = 1;
+    return f * x2;
+}
+// measurement = position + sigma * randn(2) for every hit agent of ONE env (warp path; called by lane 0)
+__device__ __forceinline__ void d2d_measure_env(const DevP &P, const BlockCtx &c, int e) {
+    D2DRng r;
+    r.key = P.rng_key + (size_t)e * 624; r.pos = P.rng_pos[e]; r.has = P.rng_has[e]; r.gauss = P.rng_gauss[e];
+    bool used = false;
+#pragma unroll 1
+    for (int k = 0; k < P.N; k++) {
+        if (!((c.hitw[k >> 5] >> (k & 31)) & 1u)) continue;
+        const double g0 = d2d_legacy_gauss(r), g1 = d2d_legacy_gauss(r);
+        c.mx[k] = c.sx[k] + P.var_cam * g0;
+        c.my[k] = c.sy[k] + P.var_cam * g1;
+        used = true;
+    }
+    if (used) { P.rng_pos[e] = r.pos; P.rng_has[e] = r.has; P.rng_gauss[e] = r.gauss; }
+}
+
 // ------------------------------------------------------------------------------------------ P3: hit mask + trackers
 __device__ D2D_COLD void d2d_tracker_update(const DevP &P, EnvS &s, size_t g, bool measured, double z0, double z1) {
     // KalmanFilter.update utils.py:242-275; F = I + 0.1*shift, H = [I 0], Sigma_z = var_cam*I, Sigma_x = q*I
@@ -510,7 +580,9 @@ __device__ __forceinline__ void d2d_phase_trackers(const DevP &P, const BlockCtx
             const bool was_active = s.reset ? false : (P.trk_active[g] != 0);
             if (hit && !was_active) atomicAdd(&s.newly, 1);   // utils.py:606-607
             if (was_active || hit || s.reset) {
-                d2d_tracker_update(P, s, g, hit, c.sx[i * NP + k], c.sy[i * NP + k]);
+                const bool noisy = P.var_cam != 0.0;
+                d2d_tracker_update(P, s, g, hit, noisy ? c.mx[i * NP + k] : c.sx[i * NP + k],
+                                   noisy ? c.my[i * NP + k] : c.sy[i * NP + k]);
             }
         }
     }
@@ -814,6 +886,10 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     d2d_mbar_wait(c.mbar, 0);
     d2d_phase_rays_warp<ILP2>(P, c, ro, lane);
     __syncwarp();
+    if (P.var_cam != 0.0) {
+        if (lane == 0) d2d_measure_env(P, c, e);
+        __syncwarp();
+    }
     d2d_phase_trackers(P, c, e, 1, lane, 32);
     const int shit = __any_sync(0xffffffffu, lane < 5 ? d2d_static_probe(P, c.gt, s.px, s.py, lane) : 0);
     __syncwarp();

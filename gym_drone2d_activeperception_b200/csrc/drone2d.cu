@@ -32,6 +32,7 @@ struct d2d_handle {
     int64_t launches = 0;
     int64_t step_count = 0;
     bool world_set = false;
+    bool rng_set = false;
     std::string err;
     size_t smem_step = 0, smem_post = 0;
     int plan_threads = 64;
@@ -103,6 +104,8 @@ __global__ void d2d_reset_kernel(const DevP P, const uint8_t *__restrict__ mask)
     for (int w = tid; w < D2D_LOCAL_CELLS; w += T) P.local_map[(size_t)e * D2D_LOCAL_CELLS + w] = 0;
     if (P.ox_last)
         for (int w = tid; w < D2D_CELLS; w += T) P.ox_last[(size_t)e * D2D_CELLS + w] = 5.0;
+    if (P.rng_key)
+        for (int w = tid; w < 624; w += T) P.rng_key[(size_t)e * 624 + w] = P.rng_key0[(size_t)e * 624 + w];
     if (tid == 0) {
         const double x = P.pose0[e], y = P.pose0[P.B + e], yaw = P.pose0[2 * P.B + e];
         P.drone_x[e] = x; P.drone_y[e] = y; P.drone_yaw[e] = yaw; P.drone_vx[e] = 0; P.drone_vy[e] = 0;
@@ -113,6 +116,7 @@ __global__ void d2d_reset_kernel(const DevP P, const uint8_t *__restrict__ mask)
         P.traj_nseg[e] = 0; P.traj_cursor[e] = 0; P.need_plan[e] = 0; P.plan_ok[e] = 1; P.replan[e] = 0;
         P.yaw_obs[e] = (float)yaw;
         P.ox_fresh[e] = 0; P.tmp_act_cnt[e] = 0; P.tmp_act_ts[e] = 0;
+        P.rng_pos[e] = P.rng_pos0[e]; P.rng_has[e] = P.rng_has0[e]; P.rng_gauss[e] = P.rng_gauss0[e];
         // local_map was zeroed above, which IS the window of an all-unexplored belief grid at the initial cell
         P.obs_ix[e] = d2d_cell(x, P.scale, P.inv_scale); P.obs_iy[e] = d2d_cell(y, P.scale, P.inv_scale);
     }
@@ -159,7 +163,10 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
         cfg->n_u > D2D_MAX_U || cfg->n_samp > D2D_MAX_SAMP || cfg->n_way > D2D_MAX_WAY || cfg->n_yaw > D2D_MAX_YAW) {
         g_create_err = "table size out of range"; return D2D_ERR_INVALID;
     }
-    if (cfg->var_cam != 0.0) { g_create_err = "var_cam != 0 (noisy measurements) is not implemented"; return D2D_ERR_INVALID; }
+    if (cfg->var_cam != 0.0 && cfg->envs_per_block > 0) {
+        g_create_err = "var_cam != 0 (noisy measurements) is only implemented on the default warp-per-env kernels (envs_per_block = 0)";
+        return D2D_ERR_INVALID;
+    }
     d2d_handle *h = new d2d_handle();
     h->cfg = *cfg;
     cudaError_t ce = cudaSetDevice(cfg->device);
@@ -233,6 +240,11 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     size_t o_tac = add_buf(h, cur, "tmp_active_count", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_tat = add_buf(h, cur, "tmp_active_ts", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_oxf = add_buf(h, cur, "oxford_fresh", D2D_U8, 1, SHP(B), SHP(1), sB);
+    const bool noisy = cfg->var_cam != 0.0;
+    size_t o_rk = add_buf(h, cur, "rng_key", D2D_I32, 2, SHP(B, 624), SHP(624, 1), noisy ? (size_t)sB * 624 : 16);
+    size_t o_rk0 = add_buf(h, cur, "rng_key0", D2D_I32, 2, SHP(B, 624), SHP(624, 1), noisy ? (size_t)sB * 624 : 16);
+    size_t o_rp = add_buf(h, cur, "rng_pos", D2D_I32, 2, SHP(4, B), SHP(B, 1), (size_t)4 * sB);      // pos, pos0, has, has0
+    size_t o_rg = add_buf(h, cur, "rng_gauss", D2D_F64, 2, SHP(2, B), SHP(B, 1), (size_t)2 * sB);     // gauss, gauss0
     size_t o_obx = add_buf(h, cur, "obs_ix", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_oby = add_buf(h, cur, "obs_iy", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_oxp = add_buf(h, cur, "oxford_program", D2D_U8, 1, SHP((int64_t)sizeof(OxProgram)), SHP(1), sizeof(OxProgram));
@@ -298,6 +310,9 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.ox_last = cfg->oxford ? (double *)(A + o_ox) : nullptr;
     P.tmp_act_cnt = (int *)(A + o_tac); P.tmp_act_ts = (int *)(A + o_tat); P.ox_fresh = A + o_oxf;
     P.obs_ix = (int *)(A + o_obx); P.obs_iy = (int *)(A + o_oby);
+    P.rng_key = noisy ? (uint32_t *)(A + o_rk) : nullptr; P.rng_key0 = noisy ? (uint32_t *)(A + o_rk0) : nullptr;
+    P.rng_pos = (int *)(A + o_rp); P.rng_pos0 = P.rng_pos + sB; P.rng_has = P.rng_pos + 2 * sB; P.rng_has0 = P.rng_pos + 3 * sB;
+    P.rng_gauss = (double *)(A + o_rg); P.rng_gauss0 = P.rng_gauss + sB;
     h->ox_prog = (OxProgram *)(A + o_oxp);
     P.stats = (unsigned long long *)(A + o_stats);
     P.tab = (const DevTables *)(A + o_tab);
@@ -407,6 +422,28 @@ extern "C" int d2d_set_world(d2d_handle *h, int32_t first_env, int32_t count, co
     return D2D_OK;
 }
 
+extern "C" int d2d_set_rng(d2d_handle *h, int32_t first_env, int32_t count, const uint32_t *key, const int32_t *pos,
+                           const int32_t *has_gauss, const double *gauss) {
+    if (!h || !key || !pos || !has_gauss || !gauss || first_env < 0 || count <= 0 || first_env + count > h->B) {
+        if (h) h->err = "d2d_set_rng: bad argument";
+        return D2D_ERR_INVALID;
+    }
+    if (h->cfg.var_cam == 0.0) return D2D_OK;     // the stream has no observable effect without measurement noise
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const DevP &P = h->P;
+    const size_t e0 = (size_t)first_env, n = (size_t)count;
+    CUDA_TRY(h, cudaMemcpy(P.rng_key0 + e0 * 624, key, n * 624 * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(P.rng_key + e0 * 624, key, n * 624 * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(P.rng_pos0 + e0, pos, n * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(P.rng_pos + e0, pos, n * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(P.rng_has0 + e0, has_gauss, n * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(P.rng_has + e0, has_gauss, n * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(P.rng_gauss0 + e0, gauss, n * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(P.rng_gauss + e0, gauss, n * 8, cudaMemcpyHostToDevice));
+    h->rng_set = true;
+    return D2D_OK;
+}
+
 extern "C" int d2d_reset(d2d_handle *h, const uint8_t *mask_dev, void *stream) {
     if (!h) return D2D_ERR_INVALID;
     if (!h->world_set) { h->err = "d2d_reset before d2d_set_world"; return D2D_ERR_STATE; }
@@ -471,6 +508,7 @@ static int step_primitive(d2d_handle *h, const double *actions, cudaStream_t st)
 extern "C" int d2d_step(d2d_handle *h, const double *actions_dev, void *stream) {
     if (!h || !actions_dev) return D2D_ERR_INVALID;
     if (!h->world_set) { h->err = "d2d_step before d2d_set_world"; return D2D_ERR_STATE; }
+    if (h->cfg.var_cam != 0.0 && !h->rng_set) { h->err = "var_cam != 0: d2d_set_rng must provide the np.random stream state"; return D2D_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc;

@@ -177,6 +177,10 @@ class Drone2DVecEnv(object):
         keep = [p(w["agent_pos"], np.float64), p(w["agent_pref"], np.float64), p(w["agent_radius"], np.float64),
                 p(w["tracker_radius"], np.float64), p(w["gt_grid"], np.uint8), p(w["drone_pose"], np.float64)]
         self._check(self._lib.d2d_set_world(self._h, first_env, count, *[k[1] for k in keep]), "d2d_set_world")
+        if "rng_key" in w:      # legacy np.random stream state (only consumed when var_cam != 0)
+            rk = [p(w["rng_key"], np.uint32), p(w["rng_pos"], np.int32), p(w["rng_has_gauss"], np.int32),
+                  p(w["rng_gauss"], np.float64)]
+            self._check(self._lib.d2d_set_rng(self._h, first_env, count, *[k[1] for k in rk]), "d2d_set_rng")
 
     def buffer(self, name):
         """Torch tensor aliasing the named arena buffer."""

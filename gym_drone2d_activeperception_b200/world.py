@@ -146,7 +146,10 @@ def generate_world(params, seed, static_map=None):
             if (cx - ax) ** 2 + (cy - ay) ** 2 <= r ** 2:
                 gt[occ[m, 0], occ[m, 1]] = 2
     yaw0 = -90 % 360                                # Drone2D(init_yaw=-90): yaw = init_yaw % 360 (utils.py:718)
-    return dict(agent_pos=agent_pos, agent_pref=agent_pref, agent_radius=agent_radius, tracker_radius=tracker_radius,
+    st = nrs.get_state()                            # legacy np.random stream after the 100 heading draws (utils.py:605 continues it)
+    return dict(rng_key=np.asarray(st[1], dtype=np.uint32).copy(), rng_pos=np.int32(st[2]), rng_has_gauss=np.int32(st[3]),
+                rng_gauss=np.float64(st[4]),
+                agent_pos=agent_pos, agent_pref=agent_pref, agent_radius=agent_radius, tracker_radius=tracker_radius,
                 gt_grid=gt, drone_pose=np.array([float(dx), float(dy), float(yaw0)]),
                 obstacles=np.array(obstacles, dtype=np.float64).reshape(len(obstacles), 3))
 
@@ -156,4 +159,6 @@ def generate_worlds(params, seeds, static_map=None):
     smap = load_static_map(params.static_map if static_map is None else static_map)
     ws = [generate_world(params, int(s), smap) for s in seeds]
     keys = ("agent_pos", "agent_pref", "agent_radius", "tracker_radius", "gt_grid", "drone_pose")
+    if getattr(params, "var_cam", 0) != 0:
+        keys = keys + ("rng_key", "rng_pos", "rng_has_gauss", "rng_gauss")
     return {k: np.ascontiguousarray(np.stack([w[k] for w in ws])) for k in keys}

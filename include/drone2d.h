@@ -116,6 +116,13 @@ int d2d_set_world(d2d_handle *h, int32_t first_env, int32_t count, const double 
                   const double *agent_radius, const double *tracker_radius, const uint8_t *gt_grid,
                   const double *drone_pose);
 
+/* State of the reference's global legacy `np.random` stream right after world generation (np.random.seed(map_id),
+ * drone_v2.py:80, then the 100 heading draws, :54), as returned by RandomState.get_state(): key [count][624] u32, pos,
+ * has_gauss, cached_gaussian per env (HOST).  Needed only when var_cam != 0: the per-step measurement noise
+ * `sigma * np.random.randn(2)` (utils.py:605) continues this stream; reset() restores it. */
+int d2d_set_rng(d2d_handle *h, int32_t first_env, int32_t count, const uint32_t *key, const int32_t *pos,
+                const int32_t *has_gauss, const double *gauss);
+
 /* Replaces Drone2DEnv2.reset() (drone_v2.py:259-261) for every env whose mask byte is non-zero
  * (mask_dev == NULL: all).  mask_dev is a DEVICE pointer to num_envs bytes. */
 int d2d_reset(d2d_handle *h, const uint8_t *mask_dev, void *stream);

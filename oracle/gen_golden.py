@@ -63,7 +63,8 @@ def save(name, r, keys, extra=None):
     print("%-40s %8.1f KB  steps=%d N=%d" % (name, os.path.getsize(path) / 1024, len(r["done"]), r["n_agents"]))
 
 
-WORLD = ["agent_pos0", "agent_pref0", "agent_radius", "tracker_radius", "gt_grid", "drone0"]
+WORLD = ["agent_pos0", "agent_pref0", "agent_radius", "tracker_radius", "gt_grid", "drone0",
+         "rng_key", "rng_pos", "rng_has_gauss", "rng_gauss"]
 STEP_CORE = ["action", "agent_pos", "agent_pref", "belief", "hit", "newly", "collision", "done", "dead_lock",
              "freezing", "state_machine", "fail_count", "drone", "drone_vel", "local_map", "yaw_obs", "target"]
 TRACK = ["trk_active", "trk_mu", "trk_sigma", "trk_radius", "trk_ts", "buf_count", "buf_ts", "tracked_agent"]
@@ -71,6 +72,7 @@ PLAN = ["traj_len", "replan", "plan_ok", "planned"]
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else ""      # optional substring filter: regenerate matching fixtures only
     os.makedirs(OUT, exist_ok=True)
     acts = rr.oxford_action_set()
     # --- perception + dynamics (NoMove), the four shipped maps (BASELINE.json configs 2-5 worlds)
@@ -84,8 +86,12 @@ def main():
         ("nomove_random0_s5", dict(map_id=5, static_map="maps/random_map_0.npy", agent_number=20, agent_radius=15,
                                    agent_max_speed=40), 30, (300.5, 200.25, 200.0), False),
         ("nomove_slow_agents_s4", dict(map_id=4, agent_max_speed=4, agent_number=6), 80, (250.0, 250.0, 0.0), True),
+        # measurement noise: sigma * np.random.randn(2) per in-view agent continues the seeded legacy stream (utils.py:605)
+        ("nomove_noise_s3", dict(map_id=3, agent_number=12, var_cam=1), 120, (250.0, 250.0, 0.0), True),
     ]
     for name, kw, steps, pose, trk in cases:
+        if only not in name:
+            continue
         r = rr.run_episode(steps, actions=acts, set_pose=pose, planner="NoMove", **kw)
         save(name, r, WORLD + STEP_CORE + (TRACK if trk else []))
     # --- full loop: Primitive planner + Oxford gaze (BASELINE.json config 1 and variants)
@@ -94,8 +100,11 @@ def main():
         ("episode_s2", dict(map_id=2)),
         ("episode_speed20_s4", dict(map_id=4, drone_max_speed=20, agent_number=30)),
         ("episode_obstacle_s0", dict(map_id=0, static_map="maps/obstacle_map.npy", agent_radius=10)),
+        ("episode_noise_s6", dict(map_id=6, agent_number=12, var_cam=1)),
     ]
     for name, kw in eps:
+        if only not in name:
+            continue
         r = rr.run_episode(800, policy="Oxford", planner="Primitive", stop_on_done=True, record_oxford=True, **kw)
         save(name, r, WORLD + STEP_CORE + TRACK + PLAN + ["ox_last"])
 

@@ -55,6 +55,8 @@ class Env(C.Structure):
         ("local_map", _P(C.c_uint8)), ("yaw_obs", C.c_float), ("pad2", C.c_int32),
         ("ox_last", _P(C.c_double)), ("ox_swep", _P(C.c_double)),
         ("n_samples", C.c_int64),
+        ("rng_key", C.c_uint32 * 624), ("rng_pos", C.c_int32), ("rng_has_gauss", C.c_int32), ("rng_gauss", C.c_double),
+        ("meas", _P(C.c_double)),
     ]
 
 
@@ -205,6 +207,12 @@ class OracleEnv(object):
             self.c.targets[i][0], self.c.targets[i][1] = float(t[0]), float(t[1])
         # Planner.__init__ traj_planner.py:22: target = [drone.x, drone.y, 0, 0]
         self.c.target[0], self.c.target[1] = float(drone[0]), float(drone[1])
+
+    def set_rng(self, key, pos, has_gauss, gauss):
+        """legacy np.random state right after world generation (RandomState.get_state()); needed when var_cam != 0"""
+        for i, v in enumerate(np.asarray(key, dtype=np.uint32).tolist()):
+            self.c.rng_key[i] = v
+        self.c.rng_pos, self.c.rng_has_gauss, self.c.rng_gauss = int(pos), int(has_gauss), float(gauss)
 
     def step(self, a):
         return bool(lib().d2do_step(self._ptr, float(a)))

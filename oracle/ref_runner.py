@@ -101,6 +101,11 @@ def run_episode(steps, actions=None, policy=None, set_pose=None, stop_on_done=Fa
         if len(set_pose) > 2:
             env.drone.yaw = set_pose[2]
     world = world_snapshot(env)
+    st = np.random.get_state()           # the reference uses the GLOBAL legacy stream (drone_v2.py:80, utils.py:605)
+    world["rng_key"] = np.asarray(st[1], dtype=np.uint32).copy()
+    world["rng_pos"] = np.array(int(st[2]))
+    world["rng_has_gauss"] = np.array(int(st[3]))
+    world["rng_gauss"] = np.array(float(st[4]))
     n = len(env.agents)
 
     pol = None

@@ -243,8 +243,16 @@ def test_error_paths_are_loud():
     """Unsupported configurations and misuse raise instead of silently falling back."""
     from gym_drone2d_activeperception_b200 import _native
     from gym_drone2d_activeperception_b200.params import Params
+    with pytest.raises(_native.Drone2DNativeError):      # noisy measurements exist only on the default warp-per-env kernels
+        _env(Params(debug=False, planner="NoMove", var_cam=1), 4, None, envs_per_block=8)
+    noisy = _env(Params(debug=False, planner="NoMove", var_cam=1, agent_number=3), 4, None)
+    w = {k: v for k, v in __import__("gym_drone2d_activeperception_b200").generate_worlds(noisy.params, [0, 1, 2, 3]).items()
+         if not k.startswith("rng_")}
+    noisy2 = _env(Params(debug=False, planner="NoMove", var_cam=1, agent_number=3), 4, w)      # worlds without the RNG state
     with pytest.raises(_native.Drone2DNativeError):
-        _env(Params(debug=False, planner="NoMove", var_cam=1), 4, None)
+        noisy2.step(torch.zeros(4, dtype=torch.float64, device="cuda:0"))
+    noisy.close()
+    noisy2.close()
     with pytest.raises(ValueError):
         _env(Params(debug=False, planner="MPC"), 4, None)
     with pytest.raises(ValueError):

@@ -255,3 +255,38 @@ def test_scalar_gaze_policies_on_device(policy, kind):
     if policy in ("LookAhead", "LookGoal"):
         assert unsat > 0
     env.close()
+
+
+def test_measurement_noise_with_auto_reset():
+    """var_cam = 1: noisy measurements drawn from the per-env legacy np.random stream on the device (restored at reset)
+    vs the oracle; Primitive planner + Oxford, auto-reset."""
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200.world import generate_worlds
+    B, steps = 16, 220
+    p = Params(debug=False, planner="Primitive", gaze_method="Oxford", map_id=40, agent_number=14, agent_radius=15,
+               agent_max_speed=20, var_cam=1)
+    worlds = generate_worlds(p, 40 + np.arange(B))
+    assert "rng_key" in worlds and worlds["rng_key"].shape == (B, 624)
+    env = _env(p, B, worlds, auto_reset=True, oxford=True)
+    n = env.num_agents
+    oracles = [util.oracle_env_from_world(p, worlds, i) for i in range(B)]
+    resets = 0
+    for t in range(steps):
+        a = env.plan_oxford()
+        acts = np.zeros(B)
+        for i in range(B):
+            if oracles[i].c.done:
+                oracles[i].close()
+                oracles[i] = util.oracle_env_from_world(p, worlds, i)
+                resets += 1
+            acts[i] = oracles[i].oxford_plan()
+        torch.cuda.synchronize()
+        assert np.array_equal(a.cpu().numpy(), acts), ("oxford actions", t)
+        env.step(a)
+        for i in range(B):
+            oracles[i].step(acts[i])
+        h = _host(env)
+        for i, e in enumerate(oracles):
+            _cmp_env_to_oracle(h, i, e, n, t, "noise")
+    assert resets > 0 and int(env.buffer("tracker_active").sum()) >= 0
+    env.close()

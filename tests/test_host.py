@@ -24,6 +24,9 @@ def test_world_generation_matches_reference(path):
     assert np.array_equal(w["tracker_radius"], g["tracker_radius"])
     assert np.array_equal(w["gt_grid"] == 1, g["gt_grid"] == 1)
     assert w["drone_pose"][2] == 270.0
+    if "rng_key" in g:      # legacy np.random stream state after world generation (consumed by noisy measurements)
+        assert np.array_equal(w["rng_key"], g["rng_key"]) and int(w["rng_pos"]) == int(g["rng_pos"])
+        assert int(w["rng_has_gauss"]) == int(g["rng_has_gauss"]) and float(w["rng_gauss"]) == float(g["rng_gauss"])
 
 
 def test_border_cell_overridden_by_agent_disc():

@@ -47,14 +47,19 @@ def oracle_env_from_world(p, world, i=None, drone=None):
     """world: dict of arrays (one env, or batched with index i)."""
     import oracle
     w = {k: (v[i] if i is not None else v) for k, v in world.items()}
-    return oracle.OracleEnv(oracle_params(p), w["agent_pos"], w["agent_pref"], w["agent_radius"], w["gt_grid"],
-                            w["tracker_radius"], drone=(w["drone_pose"] if drone is None else drone),
-                            targets=p.target_list)
+    e = oracle.OracleEnv(oracle_params(p), w["agent_pos"], w["agent_pref"], w["agent_radius"], w["gt_grid"],
+                         w["tracker_radius"], drone=(w["drone_pose"] if drone is None else drone),
+                         targets=p.target_list)
+    if "rng_key" in w:
+        e.set_rng(w["rng_key"], w["rng_pos"], w["rng_has_gauss"], w["rng_gauss"])
+    return e
 
 
 def world_from_golden(g, copies=1):
     w = dict(agent_pos=g["agent_pos0"], agent_pref=g["agent_pref0"], agent_radius=g["agent_radius"],
              tracker_radius=g["tracker_radius"], gt_grid=g["gt_grid"], drone_pose=g["drone0"])
+    if "rng_key" in g and g["params"].get("var_cam", 0) != 0:
+        w.update(rng_key=g["rng_key"], rng_pos=g["rng_pos"], rng_has_gauss=g["rng_has_gauss"], rng_gauss=g["rng_gauss"])
     return {k: np.ascontiguousarray(np.stack([v] * copies)) for k, v in w.items()}
 
 
