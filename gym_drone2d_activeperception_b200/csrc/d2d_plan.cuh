@@ -835,9 +835,29 @@ __device__ __forceinline__ void d2d_ox_window(const DevP &P, double dx, int &lo,
 #define D2D_OX_WORDS ((D2D_OX_SPAN + 31) / 32)
 #define D2D_OX_THREADS 128
 
+// last_time_observed of a cell after policy call n (yaw_planner.py:95-97): 0 if visible at call n, else the += dt
+// sequence continued from 0.0 (last seen at call s) or from the initial 5.0 (never seen), read from the exact table
+__device__ __forceinline__ double d2d_ox_last_value(const DevP &P, int s, int n) {
+    if (s == n && n > 0) return 0.0;
+    int k = (s > 0) ? n - s : n;
+    const double *tab = P.ox_tab + (s > 0 ? 0 : D2D_OX_TAB);
+    if (k < D2D_OX_TAB) return tab[k];
+    double v = tab[D2D_OX_TAB - 1];
+    for (int q = D2D_OX_TAB - 1; q < k; q++) v = v + 1.0 * P.dt;       // beyond the table: continue the exact sequence
+    return v;
+}
+
+__global__ void d2d_oxford_export_kernel(const DevP P, double *__restrict__ out) {
+    const int e = blockIdx.x;
+    if (e >= P.B) return;
+    const int n = P.ox_calls[e];
+    const uint16_t *seen = P.ox_seen + (size_t)e * D2D_OX_SEEN_STRIDE;
+    for (int c = threadIdx.x; c < D2D_CELLS; c += blockDim.x) out[(size_t)e * D2D_CELLS + c] = d2d_ox_last_value(P, seen[c], n);
+}
+
 // Oxford.plan (yaw_planner.py:81-127), one block (4 warps) per env.
-//  A. warp 0: sin/cos of the 6 candidate yaws + current yaw, first waypoint, leaf range, clears; warps 1-3 meanwhile age
-//     every cell of last_time_observed by dt (:95-97, loads batched).
+//  A. warp 0: sin/cos of the 6 candidate yaws + current yaw, first waypoint, leaf range, clears.  last_time_observed is
+//     kept compact (call index of the last sighting per cell), so no per-call ageing pass over the 2500 cells exists.
 //  B. swep_map from the remaining waypoints (largest waypoint index per cell: later assignments win, :87-89); cells of
 //     the pose's depth window that are visible are reset to 0 (only those can be visible).
 //  C. candidate scores np.sum(view_k * reward) (:120-125): view_k vanishes outside the depth window of the first
@@ -865,7 +885,8 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
     const double yaw = fresh ? P.pose0[2 * P.B + e] : P.drone_yaw[e];
     const int len = fresh ? 0 : P.traj_nseg[e] * P.n_way - P.traj_cursor[e], cursor = fresh ? 0 : P.traj_cursor[e];
     const int ny = P.n_yaw;
-    double *last = P.ox_last + (size_t)e * D2D_CELLS;
+    uint16_t *seen = P.ox_seen + (size_t)e * D2D_OX_SEEN_STRIDE;
+    const int ncall = (fresh ? 0 : P.ox_calls[e]) + 1;          // index of this policy call within the episode
 
     // ---- A
     if (wid == 0) {
@@ -898,21 +919,10 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         }
 #pragma unroll 1
         for (int o = lane; o < D2D_MAX_YAW * D2D_OX_WORDS; o += 32) (&vmask[0][0])[o] = 0u;
-    } else {
-        // every cell ages by dt; all loads first: one DRAM round trip instead of NL dependent ones
-        constexpr int TA = D2D_OX_THREADS - 32, NL = (D2D_CELLS + TA - 1) / TA;
-        const int ta = tid - 32;
-        double lv[NL];
-#pragma unroll
-        for (int q = 0; q < NL; q++) {
-            const int c = ta + q * TA;
-            lv[q] = (c < D2D_CELLS && !fresh) ? last[c] : 5.0;               // init 5.0 (:49)
-        }
-#pragma unroll
-        for (int q = 0; q < NL; q++) {
-            const int c = ta + q * TA;
-            if (c < D2D_CELLS) last[c] = lv[q] + 1.0 * P.dt;
-        }
+    } else if (fresh) {
+        // first call of a new episode: nothing has been seen yet
+#pragma unroll 1
+        for (int o = tid - 32; o < D2D_OX_SEEN_STRIDE / 2; o += D2D_OX_THREADS - 32) ((uint32_t *)seen)[o] = 0u;
     }
     __syncthreads();
     const int r0 = geo[0], r1 = geo[1], q0 = geo[2], q1 = geo[3], lo = geo[4], hi = geo[5], l0 = geo[6], l1 = geo[7];
@@ -928,11 +938,11 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         for (int q = tid; q < wi * wj; q += T) {
             const int i = i0 + q / wj, j = j0 + q % wj;
             const int c = i * D2D_GRID + j;
-            if (d2d_ox_visible(P, c, dx, dy, cs_s[ny], sn_s[ny])) last[c] = 0.0;
+            if (d2d_ox_visible(P, c, dx, dy, cs_s[ny], sn_s[ny])) seen[c] = (uint16_t)ncall;
         }
     }
     if (len == 0) {                                                  // :117-118
-        if (tid == 0) { actions_out[e] = 0.0; if (fresh) P.ox_fresh[e] = 1; }
+        if (tid == 0) { actions_out[e] = 0.0; P.ox_calls[e] = ncall; if (fresh) P.ox_fresh[e] = 1; }
         return;
     }
     __syncthreads();
@@ -959,7 +969,7 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
             const double d2 = ex * ex + ey * ey;
             const bool zero_d = d2 <= 0.0;
             if (!(zero_d || d2 <= P.depth2)) continue;
-            const double lt = last[c];
+            const double lt = d2d_ox_last_value(P, seen[c], ncall);
             const double sw = swep_w[o] >= 0 ? (double)swep_w[o] * P.dt : 0.0;
             double r;
             if (sw > 0.0 && sw <= 3.0 && lt >= 0.5) r = 1000000.0;           // :108-110
@@ -1036,6 +1046,7 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         for (int k = 0; k < ny; k++)
             if (max_reward < score[k]) { best = k; max_reward = score[k]; }   // strict <, first maximum (:123-125)
         actions_out[e] = P.tab->v_yaw_space[best] / P.max_yaw_speed;
+        P.ox_calls[e] = ncall;
     }
 }
 

@@ -15,6 +15,8 @@
 #define D2D_CELLS 2500
 #define D2D_LOCAL 33
 #define D2D_LOCAL_CELLS 1089
+#define D2D_OX_TAB 4096        // table length of the last_time_observed accumulation sequences
+#define D2D_OX_SEEN_STRIDE 2560
 
 struct DevTables {   // lookup tables in global memory (read through the read-only path)
     double u_space[D2D_MAX_U];
@@ -65,7 +67,12 @@ struct DevP {
     int *rng_pos, *rng_pos0, *rng_has, *rng_has0;
     double *rng_gauss, *rng_gauss0;
     // Oxford
-    double *ox_last;             // [B][2500]
+    // Oxford policy state (yaw_planner.py:49): last_time_observed kept COMPACT -- per cell the index of the policy call at
+    // which it was last visible (0 = never); the exact accumulated double is ox_tab[base][calls since] (the += dt sequence)
+    uint16_t *ox_seen;           // [B][2560] (2500 used)
+    int *ox_calls;               // [B] policy calls since reset
+    const double *ox_tab;        // [2][D2D_OX_TAB] : from 0.0 (seen) and from 5.0 (never seen)
+    double *ox_last;             // [B][2500] materialised on demand by d2d_oxford_export_kernel (may be null)
     unsigned long long *stats;   // [D2D_NUM_STATS]
     unsigned char *plan_ws;      // A* workspaces (Primitive planner)
     int *plan_list;              // [B+8]: compacted list of envs that need a plan; [B] count (block path); [B+1], [B+2]

@@ -191,12 +191,14 @@ __device__ D2D_COLD void d2d_reset_arrays(const DevP &P, const BlockCtx &c, int 
             if (o == 0) { const int e2 = env0 + i; P.rng_pos[e2] = P.rng_pos0[e2]; P.rng_has[e2] = P.rng_has0[e2]; P.rng_gauss[e2] = P.rng_gauss0[e2]; }
         }
     }
-    if (P.ox_last) {
+    if (P.ox_seen) {   // Oxford.__init__ (yaw_planner.py:49): every cell "last observed 5.0 s ago" == never seen, 0 calls
+        const int W = D2D_OX_SEEN_STRIDE / 2;
 #pragma unroll 1
-        for (int w = tid; w < E * D2D_CELLS; w += T) {
-            const int i = w / D2D_CELLS, o = w - i * D2D_CELLS;
+        for (int w = tid; w < E * W; w += T) {
+            const int i = w / W, o = w - i * W;
             if (!c.S[i].valid || !c.S[i].reset || c.S[i].ox_fresh) continue;
-            P.ox_last[(size_t)(env0 + i) * D2D_CELLS + o] = 5.0;   // yaw_planner.py:49
+            ((uint32_t *)(P.ox_seen + (size_t)(env0 + i) * D2D_OX_SEEN_STRIDE))[o] = 0u;
+            if (o == 0) P.ox_calls[env0 + i] = 0;
         }
     }
 }

@@ -37,6 +37,7 @@ struct d2d_handle {
     size_t smem_step = 0, smem_post = 0;
     int plan_threads = 64;
     OxProgram *ox_prog = nullptr;
+    double *ox_export = nullptr;          // lazily allocated [B][2500] view of last_time_observed
     size_t smem_pre = 0, smem_plan = 0;
 };
 
@@ -102,8 +103,8 @@ __global__ void d2d_reset_kernel(const DevP P, const uint8_t *__restrict__ mask)
     uint32_t *bel = (uint32_t *)(P.belief + (size_t)e * D2D_BELIEF_STRIDE);
     for (int w = tid; w < D2D_BELIEF_STRIDE / 4; w += T) bel[w] = 0u;
     for (int w = tid; w < D2D_LOCAL_CELLS; w += T) P.local_map[(size_t)e * D2D_LOCAL_CELLS + w] = 0;
-    if (P.ox_last)
-        for (int w = tid; w < D2D_CELLS; w += T) P.ox_last[(size_t)e * D2D_CELLS + w] = 5.0;
+    if (P.ox_seen)
+        for (int w = tid; w < D2D_OX_SEEN_STRIDE / 2; w += T) ((uint32_t *)(P.ox_seen + (size_t)e * D2D_OX_SEEN_STRIDE))[w] = 0u;
     if (P.rng_key)
         for (int w = tid; w < 624; w += T) P.rng_key[(size_t)e * 624 + w] = P.rng_key0[(size_t)e * 624 + w];
     if (tid == 0) {
@@ -115,7 +116,7 @@ __global__ void d2d_reset_kernel(const DevP P, const uint8_t *__restrict__ mask)
         P.buf_count[e] = 0; P.buf_ts[e] = 0; P.tracked_agent[e] = 0;
         P.traj_nseg[e] = 0; P.traj_cursor[e] = 0; P.need_plan[e] = 0; P.plan_ok[e] = 1; P.replan[e] = 0;
         P.yaw_obs[e] = (float)yaw;
-        P.ox_fresh[e] = 0; P.tmp_act_cnt[e] = 0; P.tmp_act_ts[e] = 0;
+        P.ox_fresh[e] = 0; P.tmp_act_cnt[e] = 0; P.tmp_act_ts[e] = 0; P.ox_calls[e] = 0;
         P.rng_pos[e] = P.rng_pos0[e]; P.rng_has[e] = P.rng_has0[e]; P.rng_gauss[e] = P.rng_gauss0[e];
         // local_map was zeroed above, which IS the window of an all-unexplored belief grid at the initial cell
         P.obs_ix[e] = d2d_cell(x, P.scale, P.inv_scale); P.obs_iy[e] = d2d_cell(y, P.scale, P.inv_scale);
@@ -248,8 +249,10 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     size_t o_obx = add_buf(h, cur, "obs_ix", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_oby = add_buf(h, cur, "obs_iy", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_oxp = add_buf(h, cur, "oxford_program", D2D_U8, 1, SHP((int64_t)sizeof(OxProgram)), SHP(1), sizeof(OxProgram));
-    size_t o_ox = add_buf(h, cur, "oxford_last_time_observed", D2D_F64, 3, SHP(B, D2D_GRID, D2D_GRID),
-                          SHP(D2D_CELLS, D2D_GRID, 1), cfg->oxford ? (size_t)sB * D2D_CELLS : 16);
+    size_t o_oxs = add_buf(h, cur, "oxford_seen_call", D2D_I32, 1, SHP(1), SHP(1),
+                           cfg->oxford ? (size_t)sB * D2D_OX_SEEN_STRIDE / 2 : 4);          // uint16 [B][2560]
+    size_t o_oxc = add_buf(h, cur, "oxford_calls", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_oxt = add_buf(h, cur, "oxford_tables", D2D_F64, 2, SHP(2, D2D_OX_TAB), SHP(D2D_OX_TAB, 1), 2 * D2D_OX_TAB);
     size_t o_stats = add_buf(h, cur, "stats", D2D_I64, 1, SHP(D2D_NUM_STATS), SHP(1), D2D_NUM_STATS);
     size_t o_tab = add_buf(h, cur, "tables", D2D_U8, 1, SHP((int64_t)sizeof(DevTables)), SHP(1), sizeof(DevTables));
     size_t o_stage = add_buf(h, cur, "actions_staging", D2D_F64, 1, SHP(B), SHP(1), sB);
@@ -307,7 +310,8 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.buf_count = (int *)(A + o_bufc); P.buf_ts = (int *)(A + o_bufts); P.tracked_agent = (int *)(A + o_trk);
     P.traj_coeff = (double *)(A + o_coef); P.traj_nseg = (int *)(A + o_nseg); P.traj_cursor = (int *)(A + o_curs);
     P.need_plan = A + o_need; P.plan_ok = A + o_pok; P.replan = A + o_rep;
-    P.ox_last = cfg->oxford ? (double *)(A + o_ox) : nullptr;
+    P.ox_seen = cfg->oxford ? (uint16_t *)(A + o_oxs) : nullptr;
+    P.ox_calls = (int *)(A + o_oxc); P.ox_tab = (const double *)(A + o_oxt); P.ox_last = nullptr;
     P.tmp_act_cnt = (int *)(A + o_tac); P.tmp_act_ts = (int *)(A + o_tat); P.ox_fresh = A + o_oxf;
     P.obs_ix = (int *)(A + o_obx); P.obs_iy = (int *)(A + o_oby);
     P.rng_key = noisy ? (uint32_t *)(A + o_rk) : nullptr; P.rng_key0 = noisy ? (uint32_t *)(A + o_rk0) : nullptr;
@@ -330,6 +334,13 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     ce = cudaMemcpy(A + o_tab, &tab, sizeof(tab), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { g_create_err = std::string("cudaMemcpy tables: ") + cudaGetErrorString(ce); cudaFree(h->arena); delete h; return D2D_ERR_CUDA; }
 
+    {   // exact value of last_time_observed after k consecutive `+= dt` from 0.0 (cell seen) and from 5.0 (never seen)
+        std::vector<double> t(2 * D2D_OX_TAB);
+        double v0 = 0.0, v5 = 5.0;
+        for (int k = 0; k < D2D_OX_TAB; k++) { t[k] = v0; t[D2D_OX_TAB + k] = v5; v0 = v0 + 1.0 * cfg->dt; v5 = v5 + 1.0 * cfg->dt; }
+        ce = cudaMemcpy(A + o_oxt, t.data(), t.size() * 8, cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) { g_create_err = std::string("cudaMemcpy oxford tables: ") + cudaGetErrorString(ce); cudaFree(h->arena); delete h; return D2D_ERR_CUDA; }
+    }
     {
         OxProgram prog;
         build_ox_program(&prog, D2D_CELLS);
@@ -355,12 +366,28 @@ extern "C" int d2d_destroy(d2d_handle *h) {
     if (!h) return D2D_OK;
     cudaSetDevice(h->cfg.device);
     if (h->arena) cudaFree(h->arena);
+    if (h->ox_export) cudaFree(h->ox_export);
     delete h;
     return D2D_OK;
 }
 
 extern "C" int d2d_get_buffer(d2d_handle *h, const char *name, d2d_buffer_info *out) {
     if (!h || !name || !out) return D2D_ERR_INVALID;
+    if (std::string(name) == "oxford_last_time_observed") {
+        // Oxford.last_time_observed_map (yaw_planner.py:49,95-97) as float64 [B,50,50]: expanded from the compact state by a
+        // kernel on the legacy default stream, then synchronised (debug / test accessor, not part of the hot path)
+        if (!h->cfg.oxford) { h->err = "oxford_last_time_observed: handle was created with oxford = 0"; return D2D_ERR_STATE; }
+        CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+        if (!h->ox_export) CUDA_TRY(h, cudaMalloc((void **)&h->ox_export, (size_t)h->B * D2D_CELLS * 8));
+        CUDA_TRY(h, cudaDeviceSynchronize());
+        d2d_oxford_export_kernel<<<h->B, 256>>>(h->P, h->ox_export);
+        h->launches++;
+        CUDA_TRY(h, cudaDeviceSynchronize());
+        out->dev_ptr = h->ox_export; out->nbytes = (int64_t)h->B * D2D_CELLS * 8; out->dtype = D2D_F64; out->ndim = 3;
+        out->shape[0] = h->B; out->shape[1] = D2D_GRID; out->shape[2] = D2D_GRID; out->shape[3] = 1;
+        out->strides[0] = D2D_CELLS; out->strides[1] = D2D_GRID; out->strides[2] = 1; out->strides[3] = 1;
+        return D2D_OK;
+    }
     for (const BufDesc &b : h->bufs) {
         if (b.name == name) {
             out->dev_ptr = h->arena + b.offset; out->nbytes = (int64_t)b.nbytes; out->dtype = b.dtype; out->ndim = b.ndim;

@@ -184,7 +184,9 @@ class Drone2DVecEnv(object):
 
     def buffer(self, name):
         """Torch tensor aliasing the named arena buffer."""
-        t = self._views.get(name) if hasattr(self, "_views") else None
+        # "oxford_last_time_observed" is materialised from the compact policy state on every request (never cached)
+        cacheable = name != "oxford_last_time_observed"
+        t = self._views.get(name) if (cacheable and hasattr(self, "_views")) else None
         if t is not None:
             return t
         info = _native.D2DBufferInfo()
@@ -197,7 +199,7 @@ class Drone2DVecEnv(object):
         else:
             view = _DevView(info.dev_ptr, shape, strides, typestr, torch.empty((), dtype=tdt).element_size())
             t = torch.as_tensor(view, device=self.device)
-        if hasattr(self, "_views"):
+        if cacheable and hasattr(self, "_views"):
             self._views[name] = t
         return t
 
