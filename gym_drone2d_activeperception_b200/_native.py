@@ -12,7 +12,7 @@ GAZE = {"NoControl": 0, "Rotating": 1, "LookAhead": 2, "LookGoal": 3}
 BELIEF_STRIDE = 2560
 STAT_NAMES = ["env_steps", "episodes", "success", "static_collision", "dynamic_collision", "freezing", "dead_lock",
               "flight_steps", "grid_discovered", "agents_tracked", "tracked_steps", "plans", "plan_failures", "replans",
-              "reserved14", "reserved15"]
+              "mirror_bytes", "reserved15"]
 
 
 class D2DConfig(C.Structure):
@@ -40,7 +40,7 @@ class D2DBufferInfo(C.Structure):
 
 
 EXPORTS = ["d2d_version", "d2d_last_error", "d2d_create", "d2d_destroy", "d2d_set_world", "d2d_set_rng", "d2d_reset", "d2d_step",
-           "d2d_step_host", "d2d_plan_oxford", "d2d_plan_gaze", "d2d_set_drone_pose", "d2d_get_buffer", "d2d_stats",
+           "d2d_step_host", "d2d_bind_host_mirror", "d2d_plan_oxford", "d2d_plan_gaze", "d2d_set_drone_pose", "d2d_get_buffer", "d2d_stats",
            "d2d_launch_count"]
 
 _lib = None
@@ -71,6 +71,7 @@ def load():
     L.d2d_reset.argtypes = [vp, vp, vp]
     L.d2d_step.argtypes = [vp, vp, vp]
     L.d2d_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.d2d_bind_host_mirror.argtypes = [vp, vp, vp, vp]
     L.d2d_plan_oxford.argtypes = [vp, vp, vp]
     L.d2d_plan_gaze.argtypes = [vp, C.c_int32, vp, vp]
     L.d2d_set_drone_pose.argtypes = [vp, vp, vp]

@@ -190,12 +190,17 @@ __device__ D2D_COLD void d2d_finish_env_warp(const DevP &P, const BlockCtx &c, E
     __syncwarp();
     if (allow_patch && !s.reset && oix == s.ix && oiy == s.iy && nchg <= D2D_CHG_CAP) {
         uint8_t *out = P.local_map + (size_t)e * D2D_LOCAL_CELLS;
+        uint8_t *out_m = P.lm_mirror ? P.lm_mirror + (size_t)e * D2D_LOCAL_CELLS : nullptr;
 #pragma unroll 1
         for (int q = lane; q < nchg; q += 32) {
             const int cell = (int)(chg[q] & 0xFFFFu), v = (int)(chg[q] >> 16);
             const int u = cell / D2D_GRID - (s.ix - 16), w = cell % D2D_GRID - (s.iy - 16);
-            if ((unsigned)u < (unsigned)D2D_LOCAL && (unsigned)w < (unsigned)D2D_LOCAL) out[u * D2D_LOCAL + w] = (uint8_t)v;
+            if ((unsigned)u < (unsigned)D2D_LOCAL && (unsigned)w < (unsigned)D2D_LOCAL) {
+                out[u * D2D_LOCAL + w] = (uint8_t)v;
+                if (out_m) out_m[u * D2D_LOCAL + w] = (uint8_t)v;
+            }
         }
+        if (out_m && lane == 0 && nchg) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)nchg);
     } else {
         d2d_obs_env_warp(P, c.belief, s.ix, s.iy, e, lane);
         if (lane == 0) { P.obs_ix[e] = s.ix; P.obs_iy[e] = s.iy; }
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     __syncwarp();
     RayOut ro;
     ro.bel_s = c.belief; ro.bel_g = P.belief + (size_t)e * D2D_BELIEF_STRIDE;
-    ro.obs = nullptr; ro.wi = 0; ro.wj = 0; ro.chg = chg; ro.nchg = &cnt[1];
+    ro.obs = nullptr; ro.obs_m = nullptr; ro.wi = 0; ro.wj = 0; ro.chg = chg; ro.nchg = &cnt[1];
     d2d_mbar_wait(c.mbar, 0);
     d2d_phase_rays_warp<false>(P, c, ro, lane);
     __syncwarp();

@@ -17,6 +17,7 @@
 #define D2D_LOCAL_CELLS 1089
 #define D2D_OX_TAB 4096        // table length of the last_time_observed accumulation sequences
 #define D2D_OX_SEEN_STRIDE 2560
+#define D2D_MIRCNT_OFF 2552    // int counter in the zero padding behind the 2500 belief bytes of a shared-memory belief copy
 
 struct DevTables {   // lookup tables in global memory (read through the read-only path)
     double u_space[D2D_MAX_U];
@@ -48,6 +49,14 @@ struct DevP {
     // observation
     uint8_t *local_map;          // [B][1][33][33]
     float *yaw_obs;              // [B][1]
+    // optional zero-copy HOST mirror of the observation (d2d_bind_host_mirror): device-visible addresses of pinned host
+    // buffers; every store to local_map / yaw_obs / done is repeated there, so d2d_step_host has nothing to copy back
+    uint8_t *lm_mirror;          // [B][1][33][33] or null
+    float *yaw_mirror;           // [B] or null
+    uint8_t *done_mirror;        // [B] or null
+#ifdef D2D_WARP_PROF
+    unsigned long long *prof;    // [B][6]: 4 globaltimer stamps, smid, warpid of the fused warp kernel (tools/warp_prof.py builds with -DD2D_WARP_PROF)
+#endif
     float *reward;               // [B] zeros (drone_v2.py:257)
     int8_t *hit;                 // [B][NP]
     // trackers [B][NP]

@@ -257,6 +257,7 @@ __device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &
 struct RayOut {
     uint8_t *bel_s, *bel_g;   // belief grid in shared memory / HBM
     uint8_t *obs;             // env's local_map slice when it can be patched in place (window unchanged), else null
+    uint8_t *obs_m;           // same slice of the host mirror (null if none); only read when obs != null
     int wi, wj;               // window origin cell (ix-16, iy-16)
     uint32_t *chg;            // optional shared-memory list of changed cells (cell | value << 16), null if unused
     int *nchg;                // its counter (entries beyond the capacity are counted but not stored)
@@ -270,7 +271,13 @@ __device__ __forceinline__ void d2d_mark(const RayOut &o, int ci, int cj, uint8_
         o.bel_g[cell] = v;
         if (o.obs) {            // the cell is always inside the 33x33 window (view reach < 16 cells)
             const int u = ci - o.wi, w = cj - o.wj;
-            if ((unsigned)u < (unsigned)D2D_LOCAL && (unsigned)w < (unsigned)D2D_LOCAL) o.obs[u * D2D_LOCAL + w] = v;
+            if ((unsigned)u < (unsigned)D2D_LOCAL && (unsigned)w < (unsigned)D2D_LOCAL) {
+                o.obs[u * D2D_LOCAL + w] = v;
+                if (o.obs_m) {      // one byte over PCIe; counted in the padding word behind the shared belief grid
+                    o.obs_m[u * D2D_LOCAL + w] = v;
+                    atomicAdd((int *)(o.bel_s + D2D_MIRCNT_OFF), 1);
+                }
+            }
         }
         if (o.chg) {
             const int slot = atomicAdd(o.nchg, 1);
@@ -308,18 +315,32 @@ __device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, doubl
     const int nc = s.ncull;
     // Per-ray prefilter (conservative): a culled disc can only contain a sample of this ray if its centre lies within
     // r (+slack) of the ray's line.  |cross((c - p), d)| <= (r + slack) * |d|, compared squared.  Most rays have no
-    // candidate and skip the per-sample disc loop entirely; the decision itself stays the sampled test below.
-    bool cand = false;
+    // candidate and skip the per-sample disc loop entirely.  For the others the candidates are kept as a bit mask over
+    // the culled list (entries >= 32 are not filtered) together with the window of sample indices that can lie inside
+    // any candidate disc: sample m sits at p + m*d (+ ~1e-12 of accumulated rounding), so it is inside disc (c, r) only
+    // if |m - t| <= r / |d| with t = (c - p).d / |d|^2 -- evaluated in fp32 with a 0.05-sample margin, five orders of
+    // magnitude above the fp32 error.  The decision itself stays the reference's sampled point-in-disc test below.
+    uint32_t cmask = 0u;
+    int mlo = 0x7fff, mhi = -1;
     {
         const double dd2 = xs * xs + ys * ys;
+        const float inv_dd2 = 1.0f / (float)dd2;
+        const int ncm = nc < 32 ? nc : 32;
 #pragma unroll 1
-        for (int q = 0; q < nc; q++) {
+        for (int q = 0; q < ncm; q++) {
             const int k = cull[q];
             const double cx = sx[k] - x, cy = sy[k] - y;
             const double cr = cx * ys - cy * xs;
             const double rr = sr2[k] * 1.000001 + 1e-3;          // (r + slack)^2 upper bound
-            if (cr * cr <= rr * dd2) cand = true;
+            if (cr * cr <= rr * dd2) {
+                cmask |= 1u << q;
+                const float t = (float)(cx * xs + cy * ys) * inv_dd2;
+                const float hw = sqrtf((float)rr * inv_dd2) + 0.05f;
+                mlo = min(mlo, (int)ceilf(t - hw));
+                mhi = max(mhi, (int)floorf(t + hw));
+            }
         }
+        if (nc > 32) { mlo = 0; mhi = 0x7fff; }                  // unfiltered tail of a very long culled list
     }
     // int(x // scale) tracked incrementally: |step| < scale, so a sample moves at most one cell per axis, and
     // x in [scale*ci, scale*(ci+1)) is exactly CPython's floor (multiples of the scale are exact doubles).
@@ -339,9 +360,20 @@ __device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, doubl
             if (!(0.0 < x && x < P.map_w && 0.0 < y && y < P.map_h)) break;
         }
         bool any = false;
-        if (cand) {
+        if (m >= mlo && m <= mhi) {
+            uint32_t mm = cmask;
+            while (mm) {
+                const int q = __ffs(mm) - 1;
+                mm &= mm - 1u;
+                const int k = cull[q];
+                const double ex = sx[k] - x, ey = sy[k] - y;
+                if (ex * ex + ey * ey <= sr2[k]) {
+                    atomicOr(&hitw[k >> 5], 1u << (k & 31));
+                    any = true;
+                }
+            }
 #pragma unroll 1
-            for (int q = 0; q < nc; q++) {
+            for (int q = 32; q < nc; q++) {
                 const int k = cull[q];
                 const double ex = sx[k] - x, ey = sy[k] - y;
                 if (ex * ex + ey * ey <= sr2[k]) {
@@ -381,7 +413,7 @@ __device__ __forceinline__ void d2d_phase_rays(const DevP &P, const BlockCtx &c,
         RayOut o;
         o.bel_s = c.belief + (size_t)i * D2D_BELIEF_STRIDE;
         o.bel_g = P.belief + (size_t)(env0 + i) * D2D_BELIEF_STRIDE;
-        o.obs = nullptr; o.wi = 0; o.wj = 0; o.chg = nullptr; o.nchg = nullptr;
+        o.obs = nullptr; o.obs_m = nullptr; o.wi = 0; o.wj = 0; o.chg = nullptr; o.nchg = nullptr;
         const double a = d2d_ray_angle(P, s.yaw, ray);
         d2d_cast_ray(P, s, a, d2d_tan(a), o, c.gt + (size_t)i * D2D_GRID, c.sx + i * NP, c.sy + i * NP, c.sr2 + i * NP,
                      c.cull + i * NP, c.hitw + i * P.HW);
@@ -678,6 +710,8 @@ __device__ D2D_COLD void d2d_leader_flags(const DevP &P, EnvS &s, const uint64_t
     s.ix = d2d_cell(s.px, P.scale, P.inv_scale); s.iy = d2d_cell(s.py, P.scale, P.inv_scale);
     P.collision[e] = (uint8_t)col; P.dead_lock[e] = (uint8_t)dead; P.freezing[e] = (uint8_t)frz; P.done[e] = (uint8_t)done;
     P.yaw_obs[e] = (float)s.yaw;
+    if (P.yaw_mirror) P.yaw_mirror[e] = (float)s.yaw;
+    if (P.done_mirror) P.done_mirror[e] = (uint8_t)done;
     if (done) {
         atomicAdd(&P.stats[D2D_STAT_EPISODES], 1ull);
         if (s.sm == SM_GOAL_REACHED) atomicAdd(&P.stats[D2D_STAT_SUCCESS], 1ull);
@@ -696,6 +730,7 @@ __device__ D2D_COLD void d2d_leader_flags(const DevP &P, EnvS &s, const uint64_t
 // occupy E*1089 contiguous bytes of the observation tensor; E is a multiple of 4, so the slice is 4-byte aligned.
 __device__ __forceinline__ void d2d_phase_obs(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
     uint32_t *out = (uint32_t *)(P.local_map + (size_t)env0 * D2D_LOCAL_CELLS);
+    uint32_t *out_m = P.lm_mirror ? (uint32_t *)(P.lm_mirror + (size_t)env0 * D2D_LOCAL_CELLS) : nullptr;
     const int words = E * D2D_LOCAL_CELLS / 4;
     for (int w = tid; w < words; w += T) {
         const int o = w * 4;
@@ -722,6 +757,15 @@ __device__ __forceinline__ void d2d_phase_obs(const DevP &P, const BlockCtx &c, 
             v |= cellv << (8 * b);
         }
         out[w] = v;
+        if (out_m) {                                   // the host buffer ends at byte B*1089: no store may cross it
+            const size_t g = (size_t)env0 * D2D_LOCAL_CELLS + (size_t)o, end = (size_t)P.B * D2D_LOCAL_CELLS;
+            if (g + 4 <= end) out_m[w] = v;
+            else for (int b = 0; b < 4; b++) if (g + b < end) ((uint8_t *)out_m)[o + b] = (uint8_t)(v >> (8 * b));
+        }
+    }
+    if (out_m && tid == 0) {
+        const int nv = min(E, P.B - env0);
+        atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)(nv > 0 ? nv : 0) * D2D_LOCAL_CELLS);
     }
 }
 
@@ -846,12 +890,42 @@ __device__ D2D_COLD void d2d_obs_env_warp(const DevP &P, const uint8_t *bel, int
     const int head = (4 - (e & 3)) & 3;                 // arena buffers are 256-B aligned
     const int nwords = (D2D_LOCAL_CELLS - head) >> 2;
     const int tail0 = head + 4 * nwords;
-    if (lane < head) out[lane] = (uint8_t)d2d_obs_cell(bel, ix, iy, lane);
-    if (lane < D2D_LOCAL_CELLS - tail0) out[tail0 + lane] = (uint8_t)d2d_obs_cell(bel, ix, iy, tail0 + lane);
+    uint8_t *out_m = P.lm_mirror ? P.lm_mirror + (size_t)e * D2D_LOCAL_CELLS : nullptr;   // base 4-byte aligned (checked at bind)
+    if (lane < head) {
+        const uint8_t v = (uint8_t)d2d_obs_cell(bel, ix, iy, lane);
+        out[lane] = v;
+        if (out_m) out_m[lane] = v;
+    }
+    if (lane < D2D_LOCAL_CELLS - tail0) {
+        const uint8_t v = (uint8_t)d2d_obs_cell(bel, ix, iy, tail0 + lane);
+        out[tail0 + lane] = v;
+        if (out_m) out_m[tail0 + lane] = v;
+    }
     uint32_t *ow = (uint32_t *)(out + head);
+    uint32_t *ow_m = out_m ? (uint32_t *)(out_m + head) : nullptr;
 #pragma unroll 1
-    for (int j = lane; j < nwords; j += 32) ow[j] = d2d_obs_word(bel, ix, iy, head + 4 * j);
+    for (int j = lane; j < nwords; j += 32) {
+        const uint32_t v = d2d_obs_word(bel, ix, iy, head + 4 * j);
+        ow[j] = v;
+        if (ow_m) ow_m[j] = v;
+    }
+    if (out_m && lane == 0) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)D2D_LOCAL_CELLS);
 }
+
+#ifdef D2D_WARP_PROF
+__device__ __forceinline__ void d2d_prof_stamp(const DevP &P, int e, int k, int lane) {
+    if (lane == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); P.prof[(size_t)e * 6 + k] = t;
+        if (k == 0) {
+            unsigned sm, wi; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); asm volatile("mov.u32 %0, %%warpid;" : "=r"(wi));
+            P.prof[(size_t)e * 6 + 4] = sm; P.prof[(size_t)e * 6 + 5] = wi;
+        }
+    }
+}
+#define D2D_PROF(k) d2d_prof_stamp(P, e, k, lane)
+#else
+#define D2D_PROF(k)
+#endif
 
 template <int WPB, int MINB, bool ILP2>
 __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(const DevP P,
@@ -862,6 +936,8 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     if (e >= P.B) return;                                            // warp-uniform
     const BlockCtx c = d2d_carve(smem + (size_t)wid * d2d_warp_slice_bytes(P.NP, P.HW, 0), 1, P.NP, P.HW);
     EnvS &s = c.S[0];
+    D2D_PROF(0);
+    const int oix = P.obs_ix[e], oiy = P.obs_iy[e];                  // issued first: overlaps the scalar loads below
 
     if (lane == 0) {
         d2d_mbar_init(c.mbar, 1);
@@ -878,16 +954,18 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     if (lane == 0) d2d_leader_begin(P, s);
     // NoMove: the drone cell cannot change during the step, so if the observation tensor already holds this window it
     // is patched in place by the rays (only cells whose value changes) instead of being rewritten
-    const int oix = P.obs_ix[e], oiy = P.obs_iy[e];
     __syncwarp();
     const bool patch = !s.reset && oix == s.ix && oiy == s.iy;
     RayOut ro;
     ro.bel_s = c.belief; ro.bel_g = P.belief + (size_t)e * D2D_BELIEF_STRIDE;
     ro.obs = patch ? P.local_map + (size_t)e * D2D_LOCAL_CELLS : nullptr;
+    ro.obs_m = P.lm_mirror ? P.lm_mirror + (size_t)e * D2D_LOCAL_CELLS : nullptr;
     ro.wi = s.ix - 16; ro.wj = s.iy - 16; ro.chg = nullptr; ro.nchg = nullptr;
     d2d_mbar_wait(c.mbar, 0);
+    D2D_PROF(1);
     d2d_phase_rays_warp<ILP2>(P, c, ro, lane);
     __syncwarp();
+    D2D_PROF(2);
     if (P.var_cam != 0.0) {
         if (lane == 0) d2d_measure_env(P, c, e);
         __syncwarp();
@@ -903,6 +981,10 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
         d2d_leader_flags(P, s, c.gt, e, shit);
         d2d_store_env_scalars(P, s, e);
         atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], 1ull);
+        if (patch && P.lm_mirror) {
+            const int nb = *(const int *)(c.belief + D2D_MIRCNT_OFF);
+            if (nb) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)nb);
+        }
     }
     __syncwarp();
     if (!patch || s.ix != oix || s.iy != oiy) {
@@ -916,4 +998,5 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
         for (int off = 16; off > 0; off >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, off);
         if (lane == 0 && cnt) atomicAdd(&P.stats[D2D_STAT_GRID_DISCOVERED], (unsigned long long)cnt);
     }
+    D2D_PROF(3);
 }

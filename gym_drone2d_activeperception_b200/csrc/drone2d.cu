@@ -38,6 +38,10 @@ struct d2d_handle {
     int plan_threads = 64;
     OxProgram *ox_prog = nullptr;
     double *ox_export = nullptr;          // lazily allocated [B][2500] view of last_time_observed
+    // zero-copy observation mirror (d2d_bind_host_mirror): host addresses as bound; *_stale: the host copy must be
+    // refreshed by a full device->host copy at the next d2d_step_host (after bind / eager reset)
+    uint8_t *mir_lm = nullptr; float *mir_yaw = nullptr; uint8_t *mir_done = nullptr;
+    bool mir_stale = true;
     size_t smem_pre = 0, smem_plan = 0;
 };
 
@@ -312,6 +316,10 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.need_plan = A + o_need; P.plan_ok = A + o_pok; P.replan = A + o_rep;
     P.ox_seen = cfg->oxford ? (uint16_t *)(A + o_oxs) : nullptr;
     P.ox_calls = (int *)(A + o_oxc); P.ox_tab = (const double *)(A + o_oxt); P.ox_last = nullptr;
+    P.lm_mirror = nullptr; P.yaw_mirror = nullptr; P.done_mirror = nullptr;
+#ifdef D2D_WARP_PROF
+    cudaMalloc((void **)&P.prof, (size_t)B * 48); cudaMemset(P.prof, 0, (size_t)B * 48);
+#endif
     P.tmp_act_cnt = (int *)(A + o_tac); P.tmp_act_ts = (int *)(A + o_tat); P.ox_fresh = A + o_oxf;
     P.obs_ix = (int *)(A + o_obx); P.obs_iy = (int *)(A + o_oby);
     P.rng_key = noisy ? (uint32_t *)(A + o_rk) : nullptr; P.rng_key0 = noisy ? (uint32_t *)(A + o_rk0) : nullptr;
@@ -388,6 +396,14 @@ extern "C" int d2d_get_buffer(d2d_handle *h, const char *name, d2d_buffer_info *
         out->strides[0] = D2D_CELLS; out->strides[1] = D2D_GRID; out->strides[2] = 1; out->strides[3] = 1;
         return D2D_OK;
     }
+#ifdef D2D_WARP_PROF
+    if (std::string(name) == "warp_prof") {
+        out->dev_ptr = h->P.prof; out->nbytes = (int64_t)h->B * 48; out->dtype = D2D_I64; out->ndim = 2;
+        out->shape[0] = h->B; out->shape[1] = 6; out->shape[2] = 1; out->shape[3] = 1;
+        out->strides[0] = 6; out->strides[1] = 1; out->strides[2] = 1; out->strides[3] = 1;
+        return D2D_OK;
+    }
+#endif
     for (const BufDesc &b : h->bufs) {
         if (b.name == name) {
             out->dev_ptr = h->arena + b.offset; out->nbytes = (int64_t)b.nbytes; out->dtype = b.dtype; out->ndim = b.ndim;
@@ -446,6 +462,7 @@ extern "C" int d2d_set_world(d2d_handle *h, int32_t first_env, int32_t count, co
     cudaFree(dmask);
     if (ce != cudaSuccess) { h->err = std::string("d2d_set_world reset: ") + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
     h->world_set = true;
+    h->mir_stale = true;
     return D2D_OK;
 }
 
@@ -478,6 +495,36 @@ extern "C" int d2d_reset(d2d_handle *h, const uint8_t *mask_dev, void *stream) {
     d2d_reset_kernel<<<h->B, 128, 0, (cudaStream_t)stream>>>(h->P, mask_dev);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
+    h->mir_stale = true;          // the eager reset rewrites the device observation only
+    return D2D_OK;
+}
+
+// pinned (page-locked, mapped) host pointer -> the address kernels can store through; null on failure
+static void *mirror_dev_ptr(d2d_handle *h, void *host, const char *what) {
+    cudaPointerAttributes at;
+    cudaError_t ce = cudaPointerGetAttributes(&at, host);
+    if (ce != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+        cudaGetLastError();
+        h->err = std::string("d2d_bind_host_mirror: ") + what + " is not pinned host memory (cudaHostAlloc / cudaHostRegister)";
+        return nullptr;
+    }
+    return at.devicePointer;
+}
+
+extern "C" int d2d_bind_host_mirror(d2d_handle *h, uint8_t *local_map_host, float *yaw_host, uint8_t *done_host) {
+    if (!h) return D2D_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaDeviceSynchronize());             // no kernel may still be storing through the old mirror
+    void *dl = nullptr, *dy = nullptr, *dd = nullptr;
+    if (local_map_host) {
+        if (((uintptr_t)local_map_host & 3) != 0) { h->err = "d2d_bind_host_mirror: local_map_host must be 4-byte aligned"; return D2D_ERR_INVALID; }
+        if (!(dl = mirror_dev_ptr(h, local_map_host, "local_map_host"))) return D2D_ERR_INVALID;
+    }
+    if (yaw_host && !(dy = mirror_dev_ptr(h, yaw_host, "yaw_host"))) return D2D_ERR_INVALID;
+    if (done_host && !(dd = mirror_dev_ptr(h, done_host, "done_host"))) return D2D_ERR_INVALID;
+    h->P.lm_mirror = (uint8_t *)dl; h->P.yaw_mirror = (float *)dy; h->P.done_mirror = (uint8_t *)dd;
+    h->mir_lm = local_map_host; h->mir_yaw = yaw_host; h->mir_done = done_host;
+    h->mir_stale = true;
     return D2D_OK;
 }
 
@@ -572,11 +619,20 @@ extern "C" int d2d_step_host(d2d_handle *h, const double *actions_host, uint8_t 
     CUDA_TRY(h, cudaMemcpyAsync(h->stage_actions, actions_host, (size_t)h->B * 8, cudaMemcpyHostToDevice, st));
     int rc = d2d_step(h, h->stage_actions, stream);
     if (rc != D2D_OK) return rc;
-    if (local_map_host)
+    // a buffer bound as the zero-copy mirror was already written by the step kernels (only the bytes that changed);
+    // anything else -- or a mirror that missed an eager reset -- is copied back in full
+    const bool fresh = !h->mir_stale;
+    if (local_map_host && !(fresh && local_map_host == h->mir_lm))
         CUDA_TRY(h, cudaMemcpyAsync(local_map_host, h->P.local_map, (size_t)h->B * D2D_LOCAL_CELLS, cudaMemcpyDeviceToHost, st));
-    if (yaw_host) CUDA_TRY(h, cudaMemcpyAsync(yaw_host, h->P.yaw_obs, (size_t)h->B * 4, cudaMemcpyDeviceToHost, st));
-    if (done_host) CUDA_TRY(h, cudaMemcpyAsync(done_host, h->P.done, (size_t)h->B, cudaMemcpyDeviceToHost, st));
+    if (yaw_host && !(fresh && yaw_host == h->mir_yaw))
+        CUDA_TRY(h, cudaMemcpyAsync(yaw_host, h->P.yaw_obs, (size_t)h->B * 4, cudaMemcpyDeviceToHost, st));
+    if (done_host && !(fresh && done_host == h->mir_done))
+        CUDA_TRY(h, cudaMemcpyAsync(done_host, h->P.done, (size_t)h->B, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
+    // the full copies above also refreshed whichever mirrors were passed; a bound mirror that was NOT passed stays stale
+    if (h->mir_stale && (!h->mir_lm || local_map_host == h->mir_lm) && (!h->mir_yaw || yaw_host == h->mir_yaw) &&
+        (!h->mir_done || done_host == h->mir_done))
+        h->mir_stale = false;
     return D2D_OK;
 }
 

@@ -239,6 +239,19 @@ class Drone2DVecEnv(object):
         self._check(self._lib.d2d_step_host(self._h, ptr(actions_host), ptr(local_map_host), ptr(yaw_host),
                                             ptr(done_host), self._stream()), "d2d_step_host")
 
+    def bind_host_mirror(self, local_map_host=None, yaw_host=None, done_host=None):
+        """Zero-copy observation mirror (d2d_bind_host_mirror): the step kernels repeat every observation store into these
+        PINNED host tensors, so `step_host` called with the same tensors copies nothing back -- only the cells a step
+        changes cross PCIe.  The tensors are persistent state (read-only for the caller); all None unbinds."""
+        for x in (local_map_host, yaw_host, done_host):
+            if x is not None and not (torch.is_tensor(x) and x.is_pinned() and x.is_contiguous()):
+                raise ValueError("bind_host_mirror needs contiguous pinned torch tensors (tensor.pin_memory())")
+        def ptr(x):
+            return None if x is None else C.c_void_p(x.data_ptr())
+        self._check(self._lib.d2d_bind_host_mirror(self._h, ptr(local_map_host), ptr(yaw_host), ptr(done_host)),
+                    "d2d_bind_host_mirror")
+        self._mirror = (local_map_host, yaw_host, done_host)      # keep the buffers alive while bound
+
     @property
     def info(self):
         """Batched counterpart of `env.info` (drone_v2.py:238-250): tensors aliasing device state."""

@@ -56,7 +56,8 @@ enum {
     D2D_STAT_ENV_STEPS = 0, D2D_STAT_EPISODES, D2D_STAT_SUCCESS, D2D_STAT_STATIC_COLLISION,
     D2D_STAT_DYNAMIC_COLLISION, D2D_STAT_FREEZING, D2D_STAT_DEAD_LOCK, D2D_STAT_FLIGHT_STEPS,
     D2D_STAT_GRID_DISCOVERED, D2D_STAT_AGENTS_TRACKED, D2D_STAT_TRACKED_STEPS, D2D_STAT_PLANS,
-    D2D_STAT_PLAN_FAILURES, D2D_STAT_REPLANS
+    D2D_STAT_PLAN_FAILURES, D2D_STAT_REPLANS,
+    D2D_STAT_MIRROR_BYTES        /* local_map bytes stored into the host mirror (d2d_bind_host_mirror) */
 };
 
 /* Mirrors the reference `Params` object (utils.py:65-106) plus the batch shape.  The lookup tables are the
@@ -136,6 +137,17 @@ int d2d_step(d2d_handle *h, const double *actions_dev, void *stream);
  *   local_map_host [num_envs][1][L][L] u8, yaw_host [num_envs] f32, done_host [num_envs] u8 */
 int d2d_step_host(d2d_handle *h, const double *actions_host, uint8_t *local_map_host, float *yaw_host,
                   uint8_t *done_host, void *stream);
+
+/* Zero-copy observation mirror for d2d_step_host.  The reference hands its caller a NEW observation dict every step
+ * (drone_v2.py:251-255); over PCIe that is 1089 B per env per step although a step changes only a few cells of the
+ * window.  After this call the step kernels repeat every store to "local_map" / "yaw_angle" / "done" into the given
+ * PINNED host buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory; device-mapped, local_map_host 4-byte
+ * aligned), so a d2d_step_host call that is passed the same pointers copies nothing back: only changed cells (or a whole
+ * window when the drone's cell changed / the env was reset) cross the bus.  The buffers are persistent state: the
+ * caller may read them between steps but must not modify them, and must keep them alive until they are unbound
+ * (all NULL) or the handle is destroyed.  Any pointer may be NULL (that output is then copied as before).  The first
+ * d2d_step_host after a bind, d2d_reset or d2d_set_world refreshes the mirror with one full copy. */
+int d2d_bind_host_mirror(d2d_handle *h, uint8_t *local_map_host, float *yaw_host, uint8_t *done_host);
 
 /* Replaces Oxford.plan(env.info) (yaw_planner.py:81-127) for all envs: writes the chosen action per env to
  * actions_out_dev (DEVICE [num_envs] f64) and advances the policy state.  Requires cfg.oxford = 1. */

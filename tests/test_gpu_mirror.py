@@ -1,0 +1,98 @@
+"""Zero-copy host mirror of the observation (d2d_bind_host_mirror): the pinned host buffers must hold exactly what the
+device tensors hold after every d2d_step_host, on every kernel path (fused NoMove with in-place patching, Primitive with
+moving windows, block-per-E-envs kernels), across auto-resets, eager resets, pose writes and re-binds."""
+import numpy as np
+import pytest
+
+import util
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _env(p, B, worlds, **kw):
+    from gym_drone2d_activeperception_b200.vec_env import Drone2DVecEnv
+    return Drone2DVecEnv(p, B, worlds=worlds, seeds=None if worlds is not None else 7 + np.arange(B), device="cuda:0", **kw)
+
+
+def _pinned(B):
+    return (torch.full((B, 1, 33, 33), 77, dtype=torch.uint8).pin_memory(),
+            torch.full((B,), -1.0, dtype=torch.float32).pin_memory(),
+            torch.full((B,), 9, dtype=torch.uint8).pin_memory())
+
+
+def _check(env, lm, yaw, dn, tag):
+    assert torch.equal(lm, env.buffer("local_map").cpu()), ("local_map", tag)
+    assert torch.equal(yaw, env.buffer("yaw_angle").cpu()[:, 0]), ("yaw", tag)
+    assert torch.equal(dn, env.buffer("done").cpu()), ("done", tag)
+
+
+@pytest.mark.parametrize("planner,epb,B,steps", [("NoMove", 0, 37, 260), ("NoMove", 8, 21, 60), ("Primitive", 0, 23, 160),
+                                                  ("Primitive", 8, 9, 60)])
+def test_mirror_tracks_device_observation(planner, epb, B, steps):
+    from gym_drone2d_activeperception_b200.params import Params
+    p = Params(debug=False, planner=planner, map_id=7, agent_number=10, agent_radius=15, agent_max_speed=40)
+    env = _env(p, B, None, auto_reset=True, oxford=False, envs_per_block=epb)
+    lm, yaw, dn = _pinned(B)
+    env.bind_host_mirror(lm, yaw, dn)
+    table = torch.as_tensor(util.action_table())
+    g = torch.Generator().manual_seed(3)
+    acts = table[torch.randint(0, 6, (steps, B), generator=g)].contiguous().pin_memory()
+    resets = 0
+    for t in range(steps):
+        env.step_host(acts[t], lm, yaw, dn)
+        _check(env, lm, yaw, dn, t)
+        resets += int(dn.sum())
+        if t == steps // 2:                       # eager reset of some envs: the mirror is refreshed by the next call
+            mask = torch.zeros(B, dtype=torch.uint8, device="cuda:0")
+            mask[::3] = 1
+            env.reset(mask)
+        if t == steps // 2 + 5:                   # pose write: the window is rebuilt, into the mirror too
+            pose = np.stack([np.full(B, 250.0), np.full(B, 250.0), np.full(B, 45.0)], 1)
+            env.set_drone_pose(pose)
+    assert resets > 0, "the run must cross at least one auto-reset"
+    mb = env.stats()[14]
+    assert mb > 0
+    if planner == "NoMove" and epb == 0:          # patched in place: far less than one window per env-step
+        assert mb < 0.2 * B * steps * 1089
+    env.close()
+
+
+def test_mirror_partial_rebind_and_unbind():
+    from gym_drone2d_activeperception_b200.params import Params
+    B = 12
+    p = Params(debug=False, planner="NoMove", map_id=11, agent_number=10, agent_radius=15, agent_max_speed=20)
+    env = _env(p, B, None, auto_reset=True, oxford=False)
+    lm, yaw, dn = _pinned(B)
+    acts = torch.full((B,), 1.0 / 3, dtype=torch.float64).pin_memory()
+    env.bind_host_mirror(lm, None, None)          # only the window is mirrored; yaw / done are copied as before
+    for t in range(10):
+        env.step_host(acts, lm, yaw, dn)
+        _check(env, lm, yaw, dn, ("partial", t))
+    lm2, yaw2, dn2 = _pinned(B)                   # other buffers than the bound ones: plain full copies
+    env.step_host(acts, lm2, yaw2, dn2)
+    _check(env, lm2, yaw2, dn2, "unbound buffers")
+    _check(env, lm, yaw2, dn2, "bound mirror kept in sync by the kernels")
+    env.bind_host_mirror(lm2, yaw2, dn2)          # re-bind
+    for t in range(10):
+        env.step_host(acts, lm2, yaw2, dn2)
+        _check(env, lm2, yaw2, dn2, ("rebound", t))
+    env.bind_host_mirror(None, None, None)
+    snap = lm2.clone()
+    env.step(torch.full((B,), 1.0, dtype=torch.float64, device="cuda:0"))
+    torch.cuda.synchronize()
+    assert torch.equal(lm2, snap), "an unbound buffer must not be written any more"
+    env.close()
+
+
+def test_mirror_rejects_pageable_memory():
+    from gym_drone2d_activeperception_b200 import _native
+    from gym_drone2d_activeperception_b200.params import Params
+    import ctypes as C
+    env = _env(Params(debug=False, planner="NoMove", agent_number=3), 4, None)
+    with pytest.raises(ValueError):
+        env.bind_host_mirror(torch.empty((4, 1, 33, 33), dtype=torch.uint8), None, None)
+    pageable = np.empty(4 * 1089, dtype=np.uint8)
+    rc = env._lib.d2d_bind_host_mirror(env._h, C.c_void_p(pageable.ctypes.data), None, None)
+    assert rc == -1 and b"pinned" in env._lib.d2d_last_error(env._h)
+    env.close()

@@ -200,6 +200,7 @@ def test_step_host_buffers_and_explicit_reset():
     dict(name="full_circle_250_rays", kw=dict(agent_number=8, drone_view_range=360), B=5, steps=30, strip_width=2),
     dict(name="random_radius", kw=dict(agent_number=12, agent_radius=-1, agent_max_speed=60), B=9, steps=60),
     dict(name="many_agents_radius5", kw=dict(agent_number=64, agent_radius=5, agent_max_speed=30), B=5, steps=40),
+    dict(name="culled_list_over_32", kw=dict(agent_number=400, agent_radius=5, agent_max_speed=30), B=6, steps=30),
 ], ids=lambda c: c["name"])
 def test_cuda_matches_oracle_edge_configs(case):
     """Edge configurations of the reference's Params: empty agent list, static pillars (per-env ground truth),
