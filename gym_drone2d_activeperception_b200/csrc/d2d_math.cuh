@@ -187,8 +187,72 @@ D2D_HD d2d_dd d2d_tan_small(d2d_dd d) {
     return dd_add(d, dp);
 }
 
-// tan(a) for 0 <= |a| < 1e5, rounded to nearest from a double-double result (rel. error < 2^-80 before rounding)
+// tan(a) for 0 <= |a| < 1e5, rounded to nearest from a double-double result (rel. error < 2^-90 before rounding).
+// Lean double-double arithmetic: every step below carries only the renormalisations its error budget needs
+// (tests/test_host.py holds the result to 50-digit mpmath and to the fully renormalised evaluation d2d_tan_ref).
 D2D_HD double d2d_tan(double a) {
+    // ---- r = a - q*(pi/2), q = nearest integer (Cody-Waite, 33-bit pieces: q*P1, q*P2, q*P3 are exact for q < 2^19)
+    const double INV_PIO2 = 6.36619772367581382433e-01;
+    const double P1 = 1.57079632673412561417e+00, P2 = 6.07710050630396597660e-11;
+    const double P3 = 2.02226624871116645580e-21, P3T = 8.47842766036889956997e-32;
+    const double q = D2D_RINT(a * INV_PIO2);
+    const bool odd = (((int)q) & 1) != 0;
+    const double z = a - q * P1;                       // exact (cancellation)
+    d2d_dd r = dd_two_sum(z, -(q * P2));
+    r.l += -(q * P3) - (q * P3T);                      // |q*P3| <= 2^-66: its rounding error is < 2^-118
+    r = dd_fast_two_sum(r.h, r.l);
+    const bool neg = r.h < 0;
+    if (neg) { r.h = -r.h; r.l = -r.l; }
+    // ---- d = r - j/32, |d| <= 1/64 (+ table end): the subtraction of the heads is exact (Sterbenz / j == 0)
+    int j = (int)(r.h * 32.0 + 0.5);
+    if (j > 25) j = 25;
+    const d2d_dd d = dd_two_sum(r.h - (double)j * 0.03125, r.l);
+    // ---- t = tan(d) = d + d*p, p = d^2/3 + 2 d^4/15 + ... (p <= 2^-13.6: it needs ~2^-60 relative accuracy, so only the
+    //      1/3 term is carried in double-double; no renormalisation in between, the low words stay far below the heads)
+    d2d_dd u = dd_two_prod(d.h, d.h);
+    u.l += 2.0 * d.h * d.l;
+    const double THIRD_H = 3.33333333333333314830e-01, THIRD_L = 1.85037170770859413132e-17;
+    d2d_dd p = dd_two_prod(u.h, THIRD_H);
+    const double uh = u.h;
+    // 2/15, 17/315, 62/2835, 1382/155925, 21844/6081075, 929569/638512875
+    const double tail = 1.33333333333333333333e-01 +
+                        uh * (5.39682539682539682540e-02 +
+                              uh * (2.18694885361552028219e-02 +
+                                    uh * (8.86323552990219656886e-03 +
+                                          uh * (3.59212803657248101693e-03 + uh * 1.45583438705131826825e-03))));
+    p.l += (uh * THIRD_L + u.l * THIRD_H) + (uh * uh) * tail;
+    d2d_dd dp = dd_two_prod(d.h, p.h);
+    dp.l += d.h * p.l + d.l * p.h;
+    d2d_dd t = dd_fast_two_sum(d.h, dp.h);             // |dp| <= 2^-13 |d|
+    t.l += d.l + dp.l;
+    // ---- tan(j/32 + d) = (T + t) / (1 - T t); an odd quadrant swaps the operands: tan(r + pi/2) = -1/tan(r).
+    //      Branch-free: every lane of a warp runs the same instruction stream (T = 0 makes j == 0 a no-op).
+    const double Th = D2D_TAN_TAB[j][0], Tl = D2D_TAN_TAB[j][1];
+    d2d_dd num = dd_fast_two_sum(Th, t.h);             // Th >= tan(1/32) > |t| or Th == 0
+    num.l += Tl + t.l;
+    d2d_dd tt = dd_two_prod(Th, t.h);
+    tt.l += Th * t.l + Tl * t.h;
+    d2d_dd den = dd_fast_two_sum(1.0, -tt.h);          // |T t| < 1/32
+    den.l -= tt.l;
+    num = dd_fast_two_sum(num.h, num.l);
+    den = dd_fast_two_sum(den.h, den.l);
+    const double ah = odd ? den.h : num.h, al = odd ? den.l : num.l;
+    const double bh = odd ? num.h : den.h, bl = odd ? num.l : den.l;
+    // ---- quotient: q1 = fl(ah / bh); the remainder (ah + al) - q1 (bh + bl) is formed exactly in its leading part
+    //      (ah - fl(bh q1) cancels exactly) and in plain double below that, which is 2^-104 of the result
+    const double inv = 1.0 / bh;
+    const double q1 = ah * inv;
+    const d2d_dd pq = dd_two_prod(bh, q1);
+    const double rem = (((ah - pq.h) - pq.l) + al) - q1 * bl;
+    const double q2 = rem * inv;
+    double v = q1 + q2;
+    if (odd) v = -v;
+    return neg ? -v : v;
+}
+
+// the same function with fully renormalised double-double steps (rel. error < 2^-80); kept as the cross-check of the lean
+// evaluation above (tests/test_host.py), not used by any kernel
+D2D_HD double d2d_tan_ref(double a) {
     int quad;
     d2d_dd r = d2d_rem_pio2(a, &quad);
     const bool neg = r.h < 0;
@@ -197,8 +261,6 @@ D2D_HD double d2d_tan(double a) {
     if (j > 25) j = 25;
     d2d_dd d = dd_add_d(r, -(double)j * 0.03125);
     d2d_dd t = d2d_tan_small(d);
-    // branch-free: every lane of a warp runs the same instruction stream (tan(0) = 0 makes j == 0 a no-op), and the
-    // quadrant only swaps the operands of the single double-double division: tan(r + pi/2) = -1/tan(r)
     d2d_dd T;
     T.h = D2D_TAN_TAB[j][0];
     T.l = D2D_TAN_TAB[j][1];

@@ -248,8 +248,7 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     if (lane == 0) d2d_leader_begin(P, s);
     __syncwarp();
     RayOut ro;
-    ro.bel_s = c.belief; ro.bel_g = P.belief + (size_t)e * D2D_BELIEF_STRIDE;
-    ro.obs = nullptr; ro.obs_m = nullptr; ro.wi = 0; ro.wj = 0; ro.chg = chg; ro.nchg = &cnt[1];
+    ro.bel_s = c.belief; ro.e = e; ro.patch = 0; ro.wi = 0; ro.wj = 0; ro.chg = chg; ro.nchg = &cnt[1];
     d2d_mbar_wait(c.mbar, 0);
     d2d_phase_rays_warp<false>(P, c, ro, lane);
     __syncwarp();

@@ -255,26 +255,28 @@ __device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &
 
 // ------------------------------------------------------------------------------------------ P2: Raycast.castRay
 struct RayOut {
-    uint8_t *bel_s, *bel_g;   // belief grid in shared memory / HBM
-    uint8_t *obs;             // env's local_map slice when it can be patched in place (window unchanged), else null
-    uint8_t *obs_m;           // same slice of the host mirror (null if none); only read when obs != null
+    uint8_t *bel_s;           // belief grid in shared memory
+    int e;                    // env index: the HBM addresses (belief row, local_map slice, host mirror) are formed from the
+                              // kernel parameters on the rare store path instead of living in registers across the march
+    int patch;                // 1: the env's local_map slice is patched in place (window unchanged this step)
     int wi, wj;               // window origin cell (ix-16, iy-16)
     uint32_t *chg;            // optional shared-memory list of changed cells (cell | value << 16), null if unused
     int *nchg;                // its counter (entries beyond the capacity are counted but not stored)
 };
 #define D2D_CHG_CAP 64
 
-__device__ __forceinline__ void d2d_mark(const RayOut &o, int ci, int cj, uint8_t v) {
+__device__ __forceinline__ void d2d_mark(const DevP &P, const RayOut &o, int ci, int cj, uint8_t v) {
     const int cell = ci * D2D_GRID + cj;
     if (o.bel_s[cell] != v) {   // monotone + idempotent: every writer of a cell writes the same value
         o.bel_s[cell] = v;
-        o.bel_g[cell] = v;
-        if (o.obs) {            // the cell is always inside the 33x33 window (view reach < 16 cells)
+        P.belief[(size_t)o.e * D2D_BELIEF_STRIDE + cell] = v;
+        if (o.patch) {          // the cell is always inside the 33x33 window (view reach < 16 cells)
             const int u = ci - o.wi, w = cj - o.wj;
             if ((unsigned)u < (unsigned)D2D_LOCAL && (unsigned)w < (unsigned)D2D_LOCAL) {
-                o.obs[u * D2D_LOCAL + w] = v;
-                if (o.obs_m) {      // one byte over PCIe; counted in the padding word behind the shared belief grid
-                    o.obs_m[u * D2D_LOCAL + w] = v;
+                const size_t off = (size_t)o.e * D2D_LOCAL_CELLS + u * D2D_LOCAL + w;
+                P.local_map[off] = v;
+                if (P.lm_mirror) {  // one byte over PCIe; counted in the padding word behind the shared belief grid
+                    P.lm_mirror[off] = v;
                     atomicAdd((int *)(o.bel_s + D2D_MIRCNT_OFF), 1);
                 }
             }
@@ -311,7 +313,7 @@ __device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, doubl
         xs = faced_right ? step : -step;
         ys = xs * slope;
     }
-    double x = s.px, y = s.py;
+    const double x0 = s.px, y0 = s.py;
     const int nc = s.ncull;
     // Per-ray prefilter (conservative): a culled disc can only contain a sample of this ray if its centre lies within
     // r (+slack) of the ray's line.  |cross((c - p), d)| <= (r + slack) * |d|, compared squared.  Most rays have no
@@ -329,7 +331,7 @@ __device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, doubl
 #pragma unroll 1
         for (int q = 0; q < ncm; q++) {
             const int k = cull[q];
-            const double cx = sx[k] - x, cy = sy[k] - y;
+            const double cx = sx[k] - x0, cy = sy[k] - y0;
             const double cr = cx * ys - cy * xs;
             const double rr = sr2[k] * 1.000001 + 1e-3;          // (r + slack)^2 upper bound
             if (cr * cr <= rr * dd2) {
@@ -342,25 +344,34 @@ __device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, doubl
         }
         if (nc > 32) { mlo = 0; mhi = 0x7fff; }                  // unfiltered tail of a very long culled list
     }
-    // int(x // scale) tracked incrementally: |step| < scale, so a sample moves at most one cell per axis, and
-    // x in [scale*ci, scale*(ci+1)) is exactly CPython's floor (multiples of the scale are exact doubles).
+    const unsigned mspan = mhi >= mlo ? (unsigned)(mhi - mlo) : 0u;   // no candidate: mlo = 0x7fff, (m - mlo) wraps to huge
+    // The march runs in MIRRORED coordinates: u = x when the ray moves up the axis, -x when it moves down (negation is
+    // exact and round-to-nearest is sign-symmetric, so u accumulates bit for bit like x).  In these coordinates every ray
+    // moves towards +u, the next cell boundary ub is always ahead and always advances by +scale, and the only direction
+    // dependence left is the strictness of the crossing test.
+    // int(x // scale) is tracked incrementally: |step| < scale, so a sample moves at most one cell per axis, and
+    // x in [scale*ci, scale*(ci+1)) is exactly CPython's floor (multiples of the scale are exact doubles):
+    //   moving up  : new cell iff x >= scale*(ci+1)            <=> u >= ub
+    //   moving down: new cell iff x <  scale*ci  <=> -x > -scale*ci  <=> u >  ub
     int ci = s.ix, cj = s.iy;
-    // a ray moves monotonically along each axis, so only the boundary ahead can be crossed: xb / yb is the next
-    // boundary in the direction of travel (upper bound of the cell when stepping up, lower bound when stepping down)
     const bool xup = xs > 0.0, yup = ys > 0.0;
     const int sxi = xup ? 1 : -1, syi = yup ? 1 : -1;
-    const double sxd = xup ? P.scale : -P.scale, syd = yup ? P.scale : -P.scale;
-    double xb = P.scale * (double)(ci + (xup ? 1 : 0)), yb = P.scale * (double)(cj + (yup ? 1 : 0));
+    const double uxs = fabs(xs), uys = fabs(ys);
+    double ux = xup ? x0 : -x0, uy = yup ? y0 : -y0;
+    double uxb = xup ? P.scale * (double)(ci + 1) : -(P.scale * (double)ci);
+    double uyb = yup ? P.scale * (double)(cj + 1) : -(P.scale * (double)cj);
     // sample m lies at most m * step * sqrt(2) from the drone: while that bound is below the view depth the
     // `dist >= depth^2` test (utils.py:668) cannot fire and is skipped (P.m_far, margin >> accumulated rounding).
     int m = 0;
     for (;;) {
         // loop condition utils.py:654: 0 < x < W and 0 < y < H; interior cells satisfy it by construction
         if ((unsigned)(ci - 1) >= (unsigned)(D2D_GRID - 2) || (unsigned)(cj - 1) >= (unsigned)(D2D_GRID - 2)) {
+            const double x = xup ? ux : -ux, y = yup ? uy : -uy;
             if (!(0.0 < x && x < P.map_w && 0.0 < y && y < P.map_h)) break;
         }
-        bool any = false;
-        if (m >= mlo && m <= mhi) {
+        if ((unsigned)(m - mlo) <= mspan) {
+            const double x = xup ? ux : -ux, y = yup ? uy : -uy;
+            bool any = false;
             uint32_t mm = cmask;
             while (mm) {
                 const int q = __ffs(mm) - 1;
@@ -381,26 +392,29 @@ __device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, doubl
                     any = true;
                 }
             }
+            if (any) break;
         }
-        if (any) break;
         const bool wall = (gt[ci] >> cj) & 1ull;
         bool far = false;
         if (m >= P.m_far) {
-            const double fx = x - s.px, fy = y - s.py;
+            const double fx = ux - (xup ? x0 : -x0), fy = uy - (yup ? y0 : -y0);   // = +-(x - px): same square
             far = (fx * fx + fy * fy) >= P.depth2;
         }
         if (wall || far) {
-            if (wall) d2d_mark(o, ci, cj, 1);
+            if (wall) d2d_mark(P, o, ci, cj, 1);
             break;
         }
-        d2d_mark(o, ci, cj, 2);
-        x = x + xs;
-        y = y + ys;
+        d2d_mark(P, o, ci, cj, 2);
+        ux = ux + uxs;
+        uy = uy + uys;
         m += 1;
-        const bool cx = xup ? (x >= xb) : (x < xb);
-        const bool cy = yup ? (y >= yb) : (y < yb);
-        if (cx) { ci += sxi; xb += sxd; }
-        if (cy) { cj += syi; yb += syd; }
+        bool cx = ux >= uxb, cy = uy >= uyb;
+        if (ux == uxb || uy == uyb) {       // a sample exactly on a cell boundary (rare): moving down it stays in its cell
+            if (ux == uxb && !xup) cx = false;
+            if (uy == uyb && !yup) cy = false;
+        }
+        if (cx) { ci += sxi; uxb += P.scale; }
+        if (cy) { cj += syi; uyb += P.scale; }
     }
 }
 
@@ -412,8 +426,7 @@ __device__ __forceinline__ void d2d_phase_rays(const DevP &P, const BlockCtx &c,
         if (!s.valid) continue;
         RayOut o;
         o.bel_s = c.belief + (size_t)i * D2D_BELIEF_STRIDE;
-        o.bel_g = P.belief + (size_t)(env0 + i) * D2D_BELIEF_STRIDE;
-        o.obs = nullptr; o.obs_m = nullptr; o.wi = 0; o.wj = 0; o.chg = nullptr; o.nchg = nullptr;
+        o.e = env0 + i; o.patch = 0; o.wi = 0; o.wj = 0; o.chg = nullptr; o.nchg = nullptr;
         const double a = d2d_ray_angle(P, s.yaw, ray);
         d2d_cast_ray(P, s, a, d2d_tan(a), o, c.gt + (size_t)i * D2D_GRID, c.sx + i * NP, c.sy + i * NP, c.sr2 + i * NP,
                      c.cull + i * NP, c.hitw + i * P.HW);
@@ -957,9 +970,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     __syncwarp();
     const bool patch = !s.reset && oix == s.ix && oiy == s.iy;
     RayOut ro;
-    ro.bel_s = c.belief; ro.bel_g = P.belief + (size_t)e * D2D_BELIEF_STRIDE;
-    ro.obs = patch ? P.local_map + (size_t)e * D2D_LOCAL_CELLS : nullptr;
-    ro.obs_m = P.lm_mirror ? P.lm_mirror + (size_t)e * D2D_LOCAL_CELLS : nullptr;
+    ro.bel_s = c.belief; ro.e = e; ro.patch = patch ? 1 : 0;
     ro.wi = s.ix - 16; ro.wj = s.iy - 16; ro.chg = nullptr; ro.nchg = nullptr;
     d2d_mbar_wait(c.mbar, 0);
     D2D_PROF(1);

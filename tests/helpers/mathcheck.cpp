@@ -3,6 +3,7 @@
 #include "../../gym_drone2d_activeperception_b200/csrc/d2d_math.cuh"
 extern "C" {
 void mc_tan(const double *a, double *out, long n) { for (long i = 0; i < n; i++) out[i] = d2d_tan(a[i]); }
+void mc_tan_ref(const double *a, double *out, long n) { for (long i = 0; i < n; i++) out[i] = d2d_tan_ref(a[i]); }
 void mc_sincos(const double *a, double *s, double *c, long n) { for (long i = 0; i < n; i++) d2d_sincos(a[i], &s[i], &c[i]); }
 void mc_cell(const double *x, int *out, long n, double scale) { for (long i = 0; i < n; i++) out[i] = d2d_cell(x[i], scale, 1.0 / scale); }
 void mc_pymod(const double *x, double *out, long n, double w) { for (long i = 0; i < n; i++) out[i] = d2d_pymod(x[i], w); }

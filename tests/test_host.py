@@ -94,6 +94,7 @@ def mathlib(tmp_path_factory):
     L = C.CDLL(so)
     dp = np.ctypeslib.ndpointer(np.float64, flags="C")
     L.mc_tan.argtypes = [dp, dp, C.c_long]
+    L.mc_tan_ref.argtypes = [dp, dp, C.c_long]
     L.mc_sincos.argtypes = [dp, dp, dp, C.c_long]
     L.mc_cell.argtypes = [dp, np.ctypeslib.ndpointer(np.int32, flags="C"), C.c_long, C.c_double]
     L.mc_pymod.argtypes = [dp, dp, C.c_long, C.c_double]
@@ -116,6 +117,22 @@ def test_device_tan_vs_glibc(mathlib):
     mp.mp.dps = 50
     for v, o in zip(a[:3000], out[:3000]):
         assert float(mp.tan(mp.mpf(float(v)))) == o
+
+
+def test_device_tan_lean_equals_fully_renormalised(mathlib):
+    """The kernels' d2d_tan drops every double-double renormalisation its error budget does not need; it must return the
+    same double as the fully renormalised evaluation (d2d_tan_ref) everywhere, including next to the poles / zeros and
+    next to the table nodes j/32."""
+    rng = np.random.RandomState(5)
+    sets = [rng.uniform(0, 2 * math.pi, 1000000), rng.uniform(-10, 100, 300000),
+            rng.randint(0, 9, 300000) * (math.pi / 4) + rng.normal(0, 1e-6, 300000) * rng.choice([1, 1e-3, 1e-6, 1e-9], 300000),
+            rng.randint(0, 200, 300000) / 32.0 + rng.normal(0, 1e-9, 300000)]
+    for a in sets:
+        a = np.ascontiguousarray(a)
+        o1, o2 = np.empty_like(a), np.empty_like(a)
+        mathlib.mc_tan(a, o1, a.size)
+        mathlib.mc_tan_ref(a, o2, a.size)
+        assert np.array_equal(o1, o2)
 
 
 def test_device_tan_on_reachable_lattice(mathlib):
