@@ -69,6 +69,21 @@ D2D_HD double d2d_pymod(double x, double w) {
 
 D2D_HD double d2d_sqrt(double v) { return D2D_SQRT(v); }
 D2D_HD double d2d_norm2(double x, double y) { return d2d_sqrt(D2D_FMA(y, y, x * x)); }
+// `np.linalg.norm([x, y]) <= R` / `< R` for R >= 0, exactly, without the square root unless the squared norm lies within
+// 1e-12 (relative) of R^2: sqrt is monotone and correctly rounded, so outside that band the comparison of the squares
+// decides (the band is four orders of magnitude wider than the rounding of R*R and of the final sqrt).
+D2D_HD bool d2d_norm2_le(double x, double y, double R) {
+    const double t = D2D_FMA(y, y, x * x), R2 = R * R;
+    if (t <= R2 * (1.0 - 1e-12)) return true;
+    if (t >= R2 * (1.0 + 1e-12)) return false;
+    return d2d_sqrt(t) <= R;
+}
+D2D_HD bool d2d_norm2_lt(double x, double y, double R) {
+    const double t = D2D_FMA(y, y, x * x), R2 = R * R;
+    if (t < R2 * (1.0 - 1e-12)) return true;
+    if (t > R2 * (1.0 + 1e-12)) return false;
+    return d2d_sqrt(t) < R;
+}
 
 // ------------------------------------------------------------------------------------------------ double-double
 struct d2d_dd {

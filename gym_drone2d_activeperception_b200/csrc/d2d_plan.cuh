@@ -232,8 +232,19 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     const int par = P.plan_list[P.B + 3] & 1;
     if (blockIdx.x == 0 && threadIdx.x == 0) { P.plan_list[P.B + 4] = par; P.plan_list[P.B + 1 + (par ^ 1)] = 0; }
 
+    // all HBM requests up front (see d2d_step_fused_warp_kernel): agents speculatively from the live arrays, bulk copies,
+    // then the scalars
+    double2 pf_pos = double2{0.0, 0.0}, pf_pref = double2{0.0, 0.0};
+    double pf_r = 0.0;
+    if (lane < P.N) {
+        const size_t g = (size_t)e * P.NP + lane;
+        pf_pos = P.apos[g]; pf_pref = P.apref[g]; pf_r = P.arad[g];
+    }
     if (lane == 0) {
         d2d_mbar_init(c.mbar, 1);
+        d2d_mbar_expect_tx(c.mbar, D2D_GT_ROW_BYTES + D2D_BELIEF_STRIDE);
+        d2d_bulk_g2s(c.gt, P.gt_rows + (size_t)e * D2D_GRID, D2D_GT_ROW_BYTES, c.mbar);
+        d2d_bulk_g2s(c.belief, P.belief + (size_t)e * D2D_BELIEF_STRIDE, D2D_BELIEF_STRIDE, c.mbar);
         c.misc[0] = 0;
         d2d_load_env_scalars(P, s, e);
         c.misc[1] = s.reset;
@@ -242,9 +253,8 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
 #pragma unroll 1
     for (int w = lane; w < P.HW; w += 32) c.hitw[w] = 0u;
     __syncwarp();
-    if (lane == 0) d2d_issue_bulk(P, c, e, 1, true);
-    d2d_reset_arrays(P, c, e, 1, lane, 32);
-    d2d_phase_agents<false>(P, c, e, 1, lane, 32);
+    d2d_reset_arrays(P, c, e, 1, lane, 32, c.mbar);
+    d2d_phase_agents<false, true>(P, c, e, 1, lane, 32, pf_pos, pf_pref, pf_r);
     if (lane == 0) d2d_leader_begin(P, s);
     __syncwarp();
     RayOut ro;

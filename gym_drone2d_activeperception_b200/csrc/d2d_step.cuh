@@ -171,8 +171,12 @@ __device__ __forceinline__ void d2d_issue_bulk(const DevP &P, const BlockCtx &c,
 }
 
 // envs being reset: zero belief in shared memory and HBM; restore the Oxford policy state
-__device__ D2D_COLD void d2d_reset_arrays(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
+__device__ D2D_COLD void d2d_reset_arrays(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T,
+                                          uint64_t *early_bulk = nullptr) {
     if (!c.misc[1]) return;   // block-uniform: no env of this block is being reset (the common case)
+    // warp kernels start the bulk copy of the belief grid before they know whether the env is being reset: it must have
+    // landed before the shared copy is zeroed
+    if (early_bulk) d2d_mbar_wait(early_bulk, 0);
     const int W = D2D_BELIEF_STRIDE / 4;
 #pragma unroll 1
     for (int w = tid; w < E * W; w += T) {
@@ -204,8 +208,12 @@ __device__ D2D_COLD void d2d_reset_arrays(const DevP &P, const BlockCtx &c, int 
 }
 
 // ------------------------------------------------------------------------------------------ P1: Agent.step
-template <bool COLLIDE_HERE>
-__device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
+// PF: the caller (one warp, E == 1) already holds agent `tid` of the live arrays in registers (pf_*), loaded before the env
+// scalars were known so that the two DRAM round trips overlap; an env being reset re-reads its snapshot instead.
+template <bool COLLIDE_HERE, bool PF = false>
+__device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T,
+                                                 double2 pf_pos = double2{0.0, 0.0}, double2 pf_pref = double2{0.0, 0.0},
+                                                 double pf_r = 0.0) {
     const double C6 = 0.8660254037844387, S6 = 0.49999999999999994;   // math.cos(pi/6), math.sin(pi/6) (glibc)
     const int N = P.N, NP = P.NP;
 #pragma unroll 1
@@ -215,14 +223,18 @@ __device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &
         if (!s.valid) continue;
         const size_t g = (size_t)(env0 + i) * NP + k;
         double2 pos, pref;
-        if (s.reset) { pos = P.apos0[g]; pref = P.apref0[g]; }
-        else { pos = P.apos[g]; pref = P.apref[g]; }
-        const double r = P.arad[g];
+        double r;
+        if (PF && w == tid && !s.reset) { pos = pf_pos; pref = pf_pref; r = pf_r; }
+        else {
+            if (s.reset) { pos = P.apos0[g]; pref = P.apref0[g]; }
+            else { pos = P.apos[g]; pref = P.apref[g]; }
+            r = P.arad[g];
+        }
         // drone_v2.py:178  velocity IS pref_velocity (same ndarray)
         double vx = pref.x, vy = pref.y;
         const double nx = pos.x + vx * P.dt, ny = pos.y + vy * P.dt;
         bool rebound = false;
-        if (d2d_norm2(vx, vy) <= 5.0) {   // utils.py:476-477: rotation by 30 deg rebinds pref_velocity
+        if (d2d_norm2_le(vx, vy, 5.0)) {   // utils.py:476-477: rotation by 30 deg rebinds pref_velocity
             const double qx = D2D_FMA(C6, pref.x, -S6 * pref.y);
             const double qy = D2D_FMA(S6, pref.x, C6 * pref.y);
             pref.x = qx; pref.y = qy;
@@ -248,7 +260,7 @@ __device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &
             c.cull[i * NP + slot] = (uint16_t)k;
         }
         if (COLLIDE_HERE) {   // Drone2D.is_collide utils.py:773-776 (drone does not move under NoMove)
-            if (d2d_norm2(ddx, ddy) < r + P.drone_r) atomicOr(&s.coll_agent, 1);
+            if (d2d_norm2_lt(ddx, ddy, r + P.drone_r)) atomicOr(&s.coll_agent, 1);
         }
     }
 }
@@ -711,8 +723,8 @@ __device__ D2D_COLD void d2d_leader_flags(const DevP &P, EnvS &s, const uint64_t
     else if (s.coll_agent) col = 2;
     int dead = 0, frz = 0;
     if (col == 0) {   // drone_v2.py:222-225
-        if (d2d_norm2(s.px - s.tgx, s.py - s.tgy) <= 10.0) s.sm = SM_GOAL_REACHED;
-        dead = (s.fail >= 10 && d2d_norm2(s.vx, s.vy) == 0.0) ? 1 : 0;
+        if (d2d_norm2_le(s.px - s.tgx, s.py - s.tgy, 10.0)) s.sm = SM_GOAL_REACHED;
+        dead = (s.fail >= 10 && D2D_FMA(s.vy, s.vy, s.vx * s.vx) == 0.0) ? 1 : 0;   // sqrt(t) == 0 <=> t == 0
         frz = ((double)s.steps >= P.max_steps && !dead) ? 1 : 0;
     }
     const int done = (col != 0 || dead || frz || (s.sm == SM_GOAL_REACHED && s.tcur >= P.n_targets)) ? 1 : 0;
@@ -950,10 +962,21 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     const BlockCtx c = d2d_carve(smem + (size_t)wid * d2d_warp_slice_bytes(P.NP, P.HW, 0), 1, P.NP, P.HW);
     EnvS &s = c.S[0];
     D2D_PROF(0);
-    const int oix = P.obs_ix[e], oiy = P.obs_iy[e];                  // issued first: overlaps the scalar loads below
-
+    // Everything the step needs from HBM is requested up front so that the cold-miss latencies overlap instead of
+    // chaining: observation cursor, first 32 agents (speculatively from the live arrays), the bulk copies of the belief
+    // grid + ground-truth rows, then the env scalars.
+    const int oix = P.obs_ix[e], oiy = P.obs_iy[e];
+    double2 pf_pos = double2{0.0, 0.0}, pf_pref = double2{0.0, 0.0};
+    double pf_r = 0.0;
+    if (lane < P.N) {
+        const size_t g = (size_t)e * P.NP + lane;
+        pf_pos = P.apos[g]; pf_pref = P.apref[g]; pf_r = P.arad[g];
+    }
     if (lane == 0) {
         d2d_mbar_init(c.mbar, 1);
+        d2d_mbar_expect_tx(c.mbar, D2D_GT_ROW_BYTES + D2D_BELIEF_STRIDE);
+        d2d_bulk_g2s(c.gt, P.gt_rows + (size_t)e * D2D_GRID, D2D_GT_ROW_BYTES, c.mbar);
+        d2d_bulk_g2s(c.belief, P.belief + (size_t)e * D2D_BELIEF_STRIDE, D2D_BELIEF_STRIDE, c.mbar);
         c.misc[0] = 0;
         d2d_load_env_scalars(P, s, e);
         c.misc[1] = s.reset;
@@ -961,9 +984,8 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
 #pragma unroll 1
     for (int w = lane; w < P.HW; w += 32) c.hitw[w] = 0u;
     __syncwarp();
-    if (lane == 0) d2d_issue_bulk(P, c, e, 1, true);
-    d2d_reset_arrays(P, c, e, 1, lane, 32);
-    d2d_phase_agents<true>(P, c, e, 1, lane, 32);
+    d2d_reset_arrays(P, c, e, 1, lane, 32, c.mbar);
+    d2d_phase_agents<true, true>(P, c, e, 1, lane, 32, pf_pos, pf_pref, pf_r);
     if (lane == 0) d2d_leader_begin(P, s);
     // NoMove: the drone cell cannot change during the step, so if the observation tensor already holds this window it
     // is patched in place by the rays (only cells whose value changes) instead of being rewritten

@@ -7,5 +7,6 @@ void mc_tan_ref(const double *a, double *out, long n) { for (long i = 0; i < n; 
 void mc_sincos(const double *a, double *s, double *c, long n) { for (long i = 0; i < n; i++) d2d_sincos(a[i], &s[i], &c[i]); }
 void mc_cell(const double *x, int *out, long n, double scale) { for (long i = 0; i < n; i++) out[i] = d2d_cell(x[i], scale, 1.0 / scale); }
 void mc_pymod(const double *x, double *out, long n, double w) { for (long i = 0; i < n; i++) out[i] = d2d_pymod(x[i], w); }
+void mc_norm2_cmp(const double *x, const double *y, const double *R, int *le, int *lt, long n) { for (long i = 0; i < n; i++) { le[i] = d2d_norm2_le(x[i], y[i], R[i]); lt[i] = d2d_norm2_lt(x[i], y[i], R[i]); } }
 void mc_norm2(const double *x, const double *y, double *out, long n) { for (long i = 0; i < n; i++) out[i] = d2d_norm2(x[i], y[i]); }
 }

@@ -99,6 +99,8 @@ def mathlib(tmp_path_factory):
     L.mc_cell.argtypes = [dp, np.ctypeslib.ndpointer(np.int32, flags="C"), C.c_long, C.c_double]
     L.mc_pymod.argtypes = [dp, dp, C.c_long, C.c_double]
     L.mc_norm2.argtypes = [dp, dp, dp, C.c_long]
+    ip = np.ctypeslib.ndpointer(np.int32, flags="C")
+    L.mc_norm2_cmp.argtypes = [dp, dp, dp, ip, ip, C.c_long]
     return L
 
 
@@ -117,6 +119,27 @@ def test_device_tan_vs_glibc(mathlib):
     mp.mp.dps = 50
     for v, o in zip(a[:3000], out[:3000]):
         assert float(mp.tan(mp.mpf(float(v)))) == o
+
+
+def test_device_norm_comparisons_without_sqrt(mathlib):
+    """d2d_norm2_le / _lt decide `np.linalg.norm([x, y]) <= R` / `< R` from the squares unless the case is borderline;
+    they must agree with the square-root form everywhere, in particular ON the boundary (integer and 1-ulp cases)."""
+    rng = np.random.RandomState(9)
+    n = 400000
+    R = rng.choice([5.0, 10.0, 20.0, 25.0, 13.7, 0.0, 17.25], n)
+    ang = rng.uniform(0, 2 * math.pi, n)
+    rad = R * (1 + rng.choice([0, 0, 1e-16, -1e-16, 2e-16, -2e-16, 1e-13, -1e-13, 1e-9, -1e-9, 0.3, -0.3], n))
+    x, y = rad * np.cos(ang), rad * np.sin(ang)
+    k = rng.randint(0, n, n // 4)                       # exact lattice cases: (3,4,5), (6,8,10), (0,R), ...
+    x[k], y[k] = R[k] * 0.6, R[k] * 0.8
+    k = rng.randint(0, n, n // 8)
+    x[k], y[k] = 0.0, R[k]
+    nrm = np.empty(n)
+    mathlib.mc_norm2(x, y, nrm, n)
+    le, lt = np.empty(n, np.int32), np.empty(n, np.int32)
+    mathlib.mc_norm2_cmp(x, y, R, le, lt, n)
+    assert np.array_equal(le != 0, nrm <= R) and np.array_equal(lt != 0, nrm < R)
+    assert (nrm == R).sum() > 1000                      # the boundary itself is exercised
 
 
 def test_device_tan_lean_equals_fully_renormalised(mathlib):
