@@ -34,11 +34,13 @@ CONFIGS = {
     2: dict(name="configs[1]: empty_map.npy, 4096 envs/GPU, 10 agents, perception+dynamics (NoMove)", envs=4096,
             params=dict(planner="NoMove", static_map="maps/empty_map.npy", agent_number=10, agent_radius=15,
                         agent_max_speed=20, map_id=1)),
-    3: dict(name="configs[2]: random_map_0.npy, 65536 envs/GPU, 20 agents radius 15", envs=65536,
-            params=dict(planner="NoMove", static_map="maps/random_map_0.npy", agent_number=20, agent_radius=15,
+    3: dict(name="configs[2]: random_map_0.npy, 65536 envs/GPU, 20 agents radius 15, Primitive planner checks on device",
+            envs=65536,
+            params=dict(planner="Primitive", static_map="maps/random_map_0.npy", agent_number=20, agent_radius=15,
                         agent_max_speed=40, map_id=1)),
-    4: dict(name="configs[3]: obstacle_map.npy, 65536 envs/GPU, 10 agents speed 20", envs=65536,
-            params=dict(planner="NoMove", static_map="maps/obstacle_map.npy", agent_number=10, agent_radius=10,
+    4: dict(name="configs[3]: obstacle_map.npy, 65536 envs/GPU, 10 agents speed 20, Primitive planner + Oxford gaze scoring",
+            envs=65536, gaze="Oxford",
+            params=dict(planner="Primitive", static_map="maps/obstacle_map.npy", agent_number=10, agent_radius=10,
                         agent_max_speed=20, map_id=1)),
     5: dict(name="configs[4]: shaped_obstacle_map.npy, 131072 envs/GPU, 50 agents", envs=131072,
             params=dict(planner="NoMove", static_map="maps/shaped_obstacle_map.npy", agent_number=50, agent_radius=10,
@@ -124,7 +126,7 @@ def algorithmic_bytes(n_agents):
     return 2406 + 104 * n_agents          # SURVEY.md §8(d); tracker traffic deliberately NOT counted
 
 
-def cpu_port_run(pk, n_envs, steps, threads, seed0=1):
+def cpu_port_run(pk, n_envs, steps, threads, seed0=1, oxford=False):
     """Times the oracle port of the reference path on the host: n_envs envs x steps steps over `threads` threads
     (ctypes releases the GIL).  Returns env-steps/s."""
     import ctypes as C
@@ -148,6 +150,9 @@ def cpu_port_run(pk, n_envs, steps, threads, seed0=1):
 
     def run_slice(idx, nsteps):
         arr = (C.POINTER(oracle.Env) * len(idx))(*[envs[i]._ptr for i in idx])
+        if oxford:      # Oxford.plan picks every action (config 4 workload)
+            L.d2do_run_many_oxford(arr, len(idx), nsteps)
+            return
         acts = np.ascontiguousarray(table[rng.randint(0, 6, (len(idx), nsteps))])
         L.d2do_run_many(arr, len(idx), nsteps, acts.ctypes.data_as(C.POINTER(C.c_double)))
 
@@ -175,7 +180,8 @@ def run_reference(args, cfg):
     vals = []
     t_all = time.perf_counter()
     for it in range(args.warmup + args.steps):
-        v, dt = cpu_port_run(cfg["params"], n_envs, steps_per, cores, seed0=1 + it)
+        v, dt = cpu_port_run({k: v for k, v in cfg["params"].items() if k != "gaze_method"}, n_envs, steps_per, cores,
+                             seed0=1 + it, oxford=args.gaze == "Oxford")
         if it >= args.warmup:
             vals.append((n_envs * steps_per, dt))
         if time.perf_counter() - t_all > 240 and len(vals) >= 1:
@@ -211,13 +217,16 @@ def main():
     ap.add_argument("--view-range", type=int, default=0, help="drone_view_range in degrees (config 5 sweep: 90/180/360)")
     ap.add_argument("--planner", default=None, choices=["NoMove", "Primitive"], help="override the config's planner")
     ap.add_argument("--e2e-full-copy", action="store_true", help="e2e leg with plain D2H copies instead of the zero-copy mirror")
-    ap.add_argument("--gaze", default="scripted", choices=["scripted", "Oxford"],
+    ap.add_argument("--gaze", default=None, choices=["scripted", "Oxford"],
                     help="scripted: random actions from the Oxford action set; Oxford: d2d_plan_oxford every step")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
+    if args.gaze is None:
+        args.gaze = cfg.get("gaze", "scripted")
     if args.planner:
         cfg["params"] = dict(cfg["params"], planner=args.planner)
-        cfg["name"] += " [planner=%s]" % args.planner
+        if args.planner != CONFIGS[args.config]["params"]["planner"]:
+            cfg["name"] += " [planner=%s]" % args.planner
     if args.view_range:
         cfg["params"] = dict(cfg["params"], drone_view_range=args.view_range)
         cfg["name"] += " [view_range=%d]" % args.view_range
@@ -225,7 +234,8 @@ def main():
         cfg["name"] += " [strip_width=%d]" % args.strip_width
     if args.gaze == "Oxford":
         cfg["params"] = dict(cfg["params"], gaze_method="Oxford")
-        cfg["name"] += " [gaze=Oxford on device]"
+        if CONFIGS[args.config].get("gaze") != "Oxford":
+            cfg["name"] += " [gaze=Oxford on device]"
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
@@ -404,7 +414,7 @@ def main():
             oracle.build()
             cores = len(os.sched_getaffinity(0))
             n_envs, steps_c = max(cores * 64, 1024), 200
-            v, dt = cpu_port_run(pk, n_envs, steps_c, cores)
+            v, dt = cpu_port_run(pk, n_envs, steps_c, cores, oxford=use_ox)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                     "sample": "%d envs x %d steps of the same workload (%.1f s)" % (n_envs, steps_c, dt)}
         print(json.dumps(line), flush=True)

@@ -23,8 +23,14 @@
 // ------------------------------------------------------------------------------------------ shared helpers
 // waypoint `a` (absolute index) of the stored trajectory: segment a / n_way, sample time t_way[n_way-1 - a % n_way]
 // (the reference builds each segment with t = arange(2, 0, -dt) and reverses the whole list, traj_planner.py:212-217)
+// q / d for 0 <= q < 2^15, 1 <= d <= 64 without the integer-division sequence: (q + 0.5) / d is at least 0.5 / 64 away
+// from every integer, three orders of magnitude more than the fp32 error of the product at these sizes
+__device__ __forceinline__ int d2d_div_small(int q, int d) {
+    return __float2int_rz(((float)q + 0.5f) * __frcp_rn((float)d));
+}
+
 __device__ __forceinline__ void d2d_waypoint_pos(const DevP &P, int e, int a, double &x, double &y) {
-    const int seg = a / P.n_way, ws = a - seg * P.n_way, ti = P.n_way - 1 - ws;
+    const int seg = d2d_div_small(a, P.n_way), ws = a - seg * P.n_way, ti = P.n_way - 1 - ws;
     const double *cf = P.traj_coeff + ((size_t)e * D2D_MAX_SEGMENTS + seg) * 6;
     const double t = P.tab->t_way[ti], t2 = P.tab->t_way2[ti];
     x = rint(D2D_FMA(t2, cf[2], cf[0] + t * cf[1]));
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
         for (int k = 0; k < na && !hit; k++) {
             const double *m = trk + 5 * k;
             const double ex = m[0] + ti * m[2], ey = m[1] + ti * m[3];
-            if (d2d_norm2(ex - x, ey - y) <= P.drone_r + m[4]) hit = true;               // :225-229
+            if (d2d_norm2_le(ex - x, ey - y, P.drone_r + m[4])) hit = true;              // :225-229
         }
     }
     const bool rep = __any_sync(0xffffffffu, hit);
@@ -950,7 +956,8 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         const int wi = i1 - i0 + 1, wj = j1 - j0 + 1;
 #pragma unroll 1
         for (int q = tid; q < wi * wj; q += T) {
-            const int i = i0 + q / wj, j = j0 + q % wj;
+            const int qi = d2d_div_small(q, wj);
+            const int i = i0 + qi, j = j0 + (q - qi * wj);
             const int c = i * D2D_GRID + j;
             if (d2d_ox_visible(P, c, dx, dy, cs_s[ny], sn_s[ny])) seen[c] = (uint16_t)ncall;
         }
@@ -976,7 +983,8 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         const int wr = r1 - r0 + 1, wq = q1 - q0 + 1;
 #pragma unroll 1
         for (int q = tid; q < wr * wq; q += T) {
-            const int i = r0 + q / wq, j = q0 + q % wq;
+            const int qi = d2d_div_small(q, wq);
+            const int i = r0 + qi, j = q0 + (q - qi * wq);
             const int c = i * D2D_GRID + j, o = c - lo;
             const double x = (double)i * P.scale, y = (double)j * P.scale;
             const double ex = wx - x, ey = wy - y;
@@ -1006,7 +1014,7 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         const int q = qb + tid;
         const bool act = q < ny * nleaf * 8;
         const int u = q & 7, kl = q >> 3;
-        const int k = act ? kl / nleaf : 0, l = l0 + (act ? kl - k * nleaf : 0);
+        const int k = act ? d2d_div_small(kl, nleaf) : 0, l = l0 + (act ? kl - k * nleaf : 0);
         const int off = prog->leaf_off[l], n = prog->leaf_len[l];
         const int nb = n - (n % 8);                     // elements covered by the 8 accumulators
         double r = 0.0;

@@ -92,6 +92,8 @@ def lib():
         L.d2do_policy_plan.restype = C.c_double
         L.d2do_run_many.argtypes = [_P(_P(Env)), C.c_int, C.c_int, _P(C.c_double)]
         L.d2do_run_many.restype = C.c_int64
+        L.d2do_run_many_oxford.argtypes = [_P(_P(Env)), C.c_int, C.c_int]
+        L.d2do_run_many_oxford.restype = C.c_int64
         L.d2do_sizeof_params.restype = C.c_size_t
         L.d2do_sizeof_env.restype = C.c_size_t
         assert L.d2do_sizeof_params() == C.sizeof(Params), (L.d2do_sizeof_params(), C.sizeof(Params))
