@@ -20,7 +20,7 @@ class D2DConfig(C.Structure):
         ("struct_size", C.c_int32), ("device", C.c_int32), ("num_envs", C.c_int32), ("num_agents", C.c_int32),
         ("planner", C.c_int32), ("trackers", C.c_int32), ("auto_reset", C.c_int32), ("oxford", C.c_int32),
         ("envs_per_block", C.c_int32), ("n_rays", C.c_int32), ("n_targets", C.c_int32),
-        ("n_u", C.c_int32), ("n_samp", C.c_int32), ("n_way", C.c_int32), ("n_yaw", C.c_int32), ("reserved0", C.c_int32),
+        ("n_u", C.c_int32), ("n_samp", C.c_int32), ("n_way", C.c_int32), ("n_yaw", C.c_int32), ("motion_profile", C.c_int32),
         ("dt", C.c_double), ("map_scale", C.c_double), ("map_w", C.c_double), ("map_h", C.c_double),
         ("agent_radius", C.c_double),
         ("drone_max_acceleration", C.c_double), ("drone_radius", C.c_double), ("drone_max_yaw_speed", C.c_double),
@@ -39,7 +39,7 @@ class D2DBufferInfo(C.Structure):
                 ("shape", C.c_int64 * 4), ("strides", C.c_int64 * 4)]
 
 
-EXPORTS = ["d2d_version", "d2d_last_error", "d2d_create", "d2d_destroy", "d2d_set_world", "d2d_set_rng", "d2d_reset", "d2d_step",
+EXPORTS = ["d2d_version", "d2d_last_error", "d2d_create", "d2d_destroy", "d2d_set_world", "d2d_set_rng", "d2d_set_rvo", "d2d_reset", "d2d_step",
            "d2d_step_host", "d2d_bind_host_mirror", "d2d_plan_oxford", "d2d_plan_gaze", "d2d_set_drone_pose", "d2d_get_buffer", "d2d_stats",
            "d2d_launch_count"]
 
@@ -68,6 +68,7 @@ def load():
     L.d2d_destroy.argtypes = [vp]
     L.d2d_set_world.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
     L.d2d_set_rng.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
+    L.d2d_set_rvo.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32]
     L.d2d_reset.argtypes = [vp, vp, vp]
     L.d2d_step.argtypes = [vp, vp, vp]
     L.d2d_step_host.argtypes = [vp, vp, vp, vp, vp, vp]

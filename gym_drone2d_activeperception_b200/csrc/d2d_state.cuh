@@ -17,6 +17,8 @@
 #define D2D_LOCAL_CELLS 1089
 #define D2D_OX_TAB 4096        // table length of the last_time_observed accumulation sequences
 #define D2D_OX_SEEN_STRIDE 2560
+#define D2D_RVO_THETAS 32       // len(np.arange(0, 2*3.14, 0.2))
+#define D2D_RVO_MAX_OBS 16      // circular obstacles (pillars) per env under the RVO motion profile
 #define D2D_MIRCNT_OFF 2552    // int counter in the zero padding behind the 2500 belief bytes of a shared-memory belief copy
 
 struct DevTables {   // lookup tables in global memory (read through the read-only path)
@@ -24,6 +26,7 @@ struct DevTables {   // lookup tables in global memory (read through the read-on
     double t_samp[D2D_MAX_SAMP], t_samp2[D2D_MAX_SAMP];
     double t_way[D2D_MAX_WAY], t_way2[D2D_MAX_WAY], t_way_x2[D2D_MAX_WAY];
     double v_yaw_space[D2D_MAX_YAW];
+    double rvo_cos[D2D_RVO_THETAS], rvo_sin[D2D_RVO_THETAS];   // glibc cos / sin of np.arange(0, 2*3.14, 0.2) (utils.py:365)
 };
 
 struct DevP {
@@ -38,6 +41,11 @@ struct DevP {
     double targets[D2D_MAX_TARGETS][2];
     // agents [B][NP] (env-major)
     double2 *apos, *apref, *apos0, *apref0;
+    // RVO motion profile (motion_rvo != 0): agent.velocity is its own array (current / reset snapshot / output of d2d_rvo_kernel)
+    int motion_rvo;
+    double2 *avel, *avel0, *avel_next;
+    double *rvo_obs;             // [B][D2D_RVO_MAX_OBS][3] x, y, rad
+    int *rvo_nobs;               // [B]
     double *arad, *trk_radius0;
     uint64_t *gt_rows;           // [B][50]
     uint8_t *belief;             // [B][D2D_BELIEF_STRIDE]

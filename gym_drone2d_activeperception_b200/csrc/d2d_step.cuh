@@ -230,8 +230,16 @@ __device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &
             else { pos = P.apos[g]; pref = P.apref[g]; }
             r = P.arad[g];
         }
-        // drone_v2.py:178  velocity IS pref_velocity (same ndarray)
+        // CVM (drone_v2.py:178): velocity IS pref_velocity (same ndarray).  RVO (drone_v2.py:169-173): the velocity chosen
+        // by d2d_rvo_kernel is an array of its own -- Agent.step rotates / bounces pref_velocity only and moves with the
+        // velocity, which is published here as the agent's current one.
         double vx = pref.x, vy = pref.y;
+        const bool rvo = P.motion_rvo != 0;
+        if (rvo) {
+            const double2 v = P.avel_next[g];
+            P.avel[g] = v;
+            vx = v.x; vy = v.y;
+        }
         const double nx = pos.x + vx * P.dt, ny = pos.y + vy * P.dt;
         bool rebound = false;
         if (d2d_norm2_le(vx, vy, 5.0)) {   // utils.py:476-477: rotation by 30 deg rebinds pref_velocity
@@ -245,7 +253,7 @@ __device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &
         else if (nx > P.map_w - edge - r) pref.x = -fabs(pref.x);
         if (ny < edge + r) pref.y = fabs(pref.y);
         else if (ny > P.map_h - edge - r) pref.y = -fabs(pref.y);
-        if (!rebound) { vx = pref.x; vy = pref.y; }
+        if (!rebound && !rvo) { vx = pref.x; vy = pref.y; }   // CVM aliasing: the bounce is visible through velocity
         pos.x = pos.x + vx * P.dt;
         pos.y = pos.y + vy * P.dt;
         P.apos[g] = pos;

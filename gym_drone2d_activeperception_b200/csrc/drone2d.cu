@@ -12,6 +12,7 @@
 #include "d2d_math.cuh"
 #include "d2d_step.cuh"
 #include "d2d_plan.cuh"
+#include "d2d_rvo.cuh"
 
 // ------------------------------------------------------------------------------------------ handle
 struct BufDesc {
@@ -33,6 +34,7 @@ struct d2d_handle {
     int64_t step_count = 0;
     bool world_set = false;
     bool rng_set = false;
+    bool rvo_set = false;
     std::string err;
     size_t smem_step = 0, smem_post = 0;
     int plan_threads = 64;
@@ -95,6 +97,7 @@ __global__ void d2d_reset_kernel(const DevP P, const uint8_t *__restrict__ mask)
     for (int k = tid; k < P.N; k += T) {
         P.apos[base + k] = P.apos0[base + k];
         P.apref[base + k] = P.apref0[base + k];
+        if (P.motion_rvo) P.avel[base + k] = P.avel0[base + k];
         P.hit[base + k] = 0;
         P.trk_active[base + k] = 0;
         P.trk_radius[base + k] = P.trk_radius0[base + k];
@@ -158,6 +161,10 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     if (!cfg || !out) { g_create_err = "null argument"; return D2D_ERR_INVALID; }
     if (cfg->struct_size != (int32_t)sizeof(d2d_config)) { g_create_err = "d2d_config size mismatch (ABI)"; return D2D_ERR_INVALID; }
     if (cfg->num_envs <= 0 || cfg->num_agents < 0 || cfg->num_agents > 4000) { g_create_err = "bad num_envs / num_agents"; return D2D_ERR_INVALID; }
+    if (cfg->motion_profile != D2D_MOTION_CVM && cfg->motion_profile != D2D_MOTION_RVO) { g_create_err = "bad motion_profile"; return D2D_ERR_INVALID; }
+    if (cfg->motion_profile == D2D_MOTION_RVO && d2d_rvo_smem_bytes(cfg->num_agents) > 200 * 1024) {
+        g_create_err = "RVO motion profile: too many agents for one block's shared memory"; return D2D_ERR_INVALID;
+    }
     if ((int)(cfg->map_w / cfg->map_scale) != D2D_GRID || (int)(cfg->map_h / cfg->map_scale) != D2D_GRID) {
         g_create_err = "only 50x50-cell maps are supported (map_size // map_scale == 50)"; return D2D_ERR_INVALID;
     }
@@ -200,6 +207,14 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     size_t o_apref = add_buf(h, cur, "agent_pref", D2D_F64, 3, SHP(B, N, 2), SHP(NP * 2, 2, 1), (size_t)sB * NP * 2);
     size_t o_apos0 = add_buf(h, cur, "agent_pos0", D2D_F64, 3, SHP(B, N, 2), SHP(NP * 2, 2, 1), (size_t)sB * NP * 2);
     size_t o_apref0 = add_buf(h, cur, "agent_pref0", D2D_F64, 3, SHP(B, N, 2), SHP(NP * 2, 2, 1), (size_t)sB * NP * 2);
+    const bool rvo = cfg->motion_profile == D2D_MOTION_RVO;
+    const size_t vel_elems = rvo ? (size_t)sB * NP * 2 : 2;
+    size_t o_avel = add_buf(h, cur, "agent_vel", D2D_F64, 3, SHP(B, N, 2), SHP(NP * 2, 2, 1), vel_elems);
+    size_t o_avel0 = add_buf(h, cur, "agent_vel0", D2D_F64, 3, SHP(B, N, 2), SHP(NP * 2, 2, 1), vel_elems);
+    size_t o_aveln = add_buf(h, cur, "agent_vel_next", D2D_F64, 3, SHP(B, N, 2), SHP(NP * 2, 2, 1), vel_elems);
+    size_t o_robs = add_buf(h, cur, "rvo_obstacles", D2D_F64, 3, SHP(B, D2D_RVO_MAX_OBS, 3), SHP(D2D_RVO_MAX_OBS * 3, 3, 1),
+                            rvo ? (size_t)sB * D2D_RVO_MAX_OBS * 3 : 4);
+    size_t o_rnobs = add_buf(h, cur, "rvo_num_obstacles", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_arad = add_buf(h, cur, "agent_radius", D2D_F64, 2, SHP(B, N), SHP(NP, 1), (size_t)sB * NP);
     size_t o_trad0 = add_buf(h, cur, "tracker_radius0", D2D_F64, 2, SHP(B, N), SHP(NP, 1), (size_t)sB * NP);
     size_t o_gt = add_buf(h, cur, "gt_rows", D2D_I64, 2, SHP(B, D2D_GRID), SHP(D2D_GRID, 1), (size_t)sB * D2D_GRID);
@@ -301,6 +316,9 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.apos = (double2 *)(A + o_apos); P.apref = (double2 *)(A + o_apref);
     P.apos0 = (double2 *)(A + o_apos0); P.apref0 = (double2 *)(A + o_apref0);
     P.arad = (double *)(A + o_arad); P.trk_radius0 = (double *)(A + o_trad0);
+    P.motion_rvo = rvo ? 1 : 0;
+    P.avel = (double2 *)(A + o_avel); P.avel0 = (double2 *)(A + o_avel0); P.avel_next = (double2 *)(A + o_aveln);
+    P.rvo_obs = (double *)(A + o_robs); P.rvo_nobs = (int *)(A + o_rnobs);
     P.gt_rows = (uint64_t *)(A + o_gt); P.belief = A + o_bel;
     P.drone_x = (double *)(A + o_dx); P.drone_y = (double *)(A + o_dy); P.drone_yaw = (double *)(A + o_dyaw);
     P.drone_vx = (double *)(A + o_dvx); P.drone_vy = (double *)(A + o_dvy); P.pose0 = (double *)(A + o_pose0);
@@ -339,6 +357,9 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     memcpy(tab.t_way, cfg->t_way, sizeof(tab.t_way)); memcpy(tab.t_way2, cfg->t_way2, sizeof(tab.t_way2));
     memcpy(tab.t_way_x2, cfg->t_way_x2, sizeof(tab.t_way_x2));
     memcpy(tab.v_yaw_space, cfg->v_yaw_space, sizeof(tab.v_yaw_space));
+    // RVO candidate directions np.arange(0, 2*3.14, 0.2) (utils.py:365): element i is 0 + i*0.2; math.cos / math.sin are
+    // this host's libm, the same functions the reference calls
+    for (int i = 0; i < D2D_RVO_THETAS; i++) { const double th = 0.0 + (double)i * 0.2; tab.rvo_cos[i] = cos(th); tab.rvo_sin[i] = sin(th); }
     ce = cudaMemcpy(A + o_tab, &tab, sizeof(tab), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { g_create_err = std::string("cudaMemcpy tables: ") + cudaGetErrorString(ce); cudaFree(h->arena); delete h; return D2D_ERR_CUDA; }
 
@@ -488,6 +509,35 @@ extern "C" int d2d_set_rng(d2d_handle *h, int32_t first_env, int32_t count, cons
     return D2D_OK;
 }
 
+extern "C" int d2d_set_rvo(d2d_handle *h, int32_t first_env, int32_t count, const double *agent_vel, const double *obstacles,
+                           const int32_t *num_obstacles, int32_t max_obstacles) {
+    if (!h || first_env < 0 || count <= 0 || first_env + count > h->B || !num_obstacles || max_obstacles < 0 ||
+        max_obstacles > D2D_RVO_MAX_OBS || (h->N > 0 && !agent_vel) || (max_obstacles > 0 && !obstacles)) {
+        if (h) h->err = "d2d_set_rvo: bad argument (at most 16 obstacles per env)";
+        return D2D_ERR_INVALID;
+    }
+    if (!h->P.motion_rvo) { h->err = "d2d_set_rvo: handle was created with motion_profile = CVM"; return D2D_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const DevP &P = h->P;
+    const size_t e0 = (size_t)first_env;
+    if (h->N > 0) {
+        CUDA_TRY(h, cudaMemcpy(P.avel0 + e0 * h->NP, agent_vel, (size_t)count * h->N * 16, cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(P.avel + e0 * h->NP, agent_vel, (size_t)count * h->N * 16, cudaMemcpyHostToDevice));
+    }
+    std::vector<double> ob((size_t)count * D2D_RVO_MAX_OBS * 3, 0.0);
+    std::vector<int> nob((size_t)count);
+    for (int c = 0; c < count; c++) {
+        const int m = num_obstacles[c];
+        if (m < 0 || m > max_obstacles) { h->err = "d2d_set_rvo: num_obstacles out of range"; return D2D_ERR_INVALID; }
+        nob[c] = m;
+        for (int q = 0; q < m * 3; q++) ob[(size_t)c * D2D_RVO_MAX_OBS * 3 + q] = obstacles[((size_t)c * max_obstacles) * 3 + q];
+    }
+    CUDA_TRY(h, cudaMemcpy(P.rvo_obs + e0 * D2D_RVO_MAX_OBS * 3, ob.data(), ob.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(P.rvo_nobs + e0, nob.data(), nob.size() * 4, cudaMemcpyHostToDevice));
+    h->rvo_set = true;
+    return D2D_OK;
+}
+
 extern "C" int d2d_reset(d2d_handle *h, const uint8_t *mask_dev, void *stream) {
     if (!h) return D2D_ERR_INVALID;
     if (!h->world_set) { h->err = "d2d_reset before d2d_set_world"; return D2D_ERR_STATE; }
@@ -586,6 +636,18 @@ extern "C" int d2d_step(d2d_handle *h, const double *actions_dev, void *stream) 
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    if (h->P.motion_rvo) {      // RVO.RVO_update (drone_v2.py:169-171) for every env, before Agent.step
+        if (!h->rvo_set) { h->err = "motion_profile = RVO: d2d_set_rvo must provide velocities and obstacles"; return D2D_ERR_STATE; }
+        static bool attr_done[64] = {false};
+        const int dev = h->cfg.device;
+        const size_t sm = d2d_rvo_smem_bytes(h->N);
+        if (!attr_done[dev & 63]) {
+            CUDA_TRY(h, cudaFuncSetAttribute(d2d_rvo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_done[dev & 63] = true;
+        }
+        d2d_rvo_kernel<<<h->B, D2D_RVO_WARPS * 32, sm, st>>>(h->P);
+        h->launches++;
+    }
     const int epb = h->cfg.envs_per_block;
     if (h->cfg.planner == D2D_PLANNER_NOMOVE && epb <= 0) {
         // default: one warp per env, single copy of the ray body (smallest code: the kernel is instruction-cache

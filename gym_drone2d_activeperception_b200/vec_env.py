@@ -63,8 +63,9 @@ def make_config(params, num_envs, num_agents, device_index, auto_reset=True, tra
     cfg.num_agents = num_agents
     if params.planner not in ("NoMove", "Primitive"):
         raise ValueError("planner %r is not supported (NoMove, Primitive)" % (params.planner,))
-    if params.motion_profile != "CVM":
-        raise ValueError("motion_profile %r is not supported (CVM)" % (params.motion_profile,))
+    if params.motion_profile not in ("CVM", "RVO"):
+        raise ValueError("motion_profile %r is not supported (CVM, RVO)" % (params.motion_profile,))
+    cfg.motion_profile = {"CVM": 0, "RVO": 1}[params.motion_profile]
     cfg.planner = {"NoMove": 0, "Primitive": 1}[params.planner]
     cfg.trackers = 1 if trackers else 0
     cfg.auto_reset = 1 if auto_reset else 0
@@ -177,6 +178,16 @@ class Drone2DVecEnv(object):
         keep = [p(w["agent_pos"], np.float64), p(w["agent_pref"], np.float64), p(w["agent_radius"], np.float64),
                 p(w["tracker_radius"], np.float64), p(w["gt_grid"], np.uint8), p(w["drone_pose"], np.float64)]
         self._check(self._lib.d2d_set_world(self._h, first_env, count, *[k[1] for k in keep]), "d2d_set_world")
+        if self.cfg.motion_profile == 1:      # RVO: initial velocities + circular obstacles (d2d_set_rvo)
+            if "agent_vel" not in w or "obstacles" not in w:
+                raise ValueError("motion_profile 'RVO' needs worlds with 'agent_vel' and 'obstacles' (world.generate_worlds)")
+            obs = np.ascontiguousarray(w["obstacles"], dtype=np.float64).reshape(count, -1, 3)
+            if obs.shape[1] > 16:
+                raise ValueError("motion_profile 'RVO': at most 16 circular obstacles (pillar_number) per env")
+            nobs = np.full(count, obs.shape[1], dtype=np.int32)
+            rv = [p(w["agent_vel"], np.float64), p(obs, np.float64), p(nobs, np.int32)]
+            self._check(self._lib.d2d_set_rvo(self._h, first_env, count, rv[0][1], rv[1][1], rv[2][1], int(obs.shape[1])),
+                        "d2d_set_rvo")
         if "rng_key" in w:      # legacy np.random stream state (only consumed when var_cam != 0)
             rk = [p(w["rng_key"], np.uint32), p(w["rng_pos"], np.int32), p(w["rng_has_gauss"], np.int32),
                   p(w["rng_gauss"], np.float64)]

@@ -150,8 +150,17 @@ def generate_world(params, seed, static_map=None):
     return dict(rng_key=np.asarray(st[1], dtype=np.uint32).copy(), rng_pos=np.int32(st[2]), rng_has_gauss=np.int32(st[3]),
                 rng_gauss=np.float64(st[4]),
                 agent_pos=agent_pos, agent_pref=agent_pref, agent_radius=agent_radius, tracker_radius=tracker_radius,
+                agent_vel=_initial_velocities(agent_pref, params.agent_number),
                 gt_grid=gt, drone_pose=np.array([float(dx), float(dy), float(yaw0)]),
                 obstacles=np.array(obstacles, dtype=np.float64).reshape(len(obstacles), 3))
+
+
+def _initial_velocities(agent_pref, agent_number):
+    """Agent.velocity right after __init__: `(0., 0.)` for the random agents (drone_v2.py:19), the group velocity for the
+    map-cell agents (drone_v2.py:62).  Only read under the RVO motion profile (CVM overwrites it with pref_velocity)."""
+    v = np.array(agent_pref, dtype=np.float64, copy=True).reshape(-1, 2)
+    v[:agent_number] = 0.0
+    return v
 
 
 def generate_worlds(params, seeds, static_map=None):
@@ -161,4 +170,6 @@ def generate_worlds(params, seeds, static_map=None):
     keys = ("agent_pos", "agent_pref", "agent_radius", "tracker_radius", "gt_grid", "drone_pose")
     if getattr(params, "var_cam", 0) != 0:
         keys = keys + ("rng_key", "rng_pos", "rng_has_gauss", "rng_gauss")
+    if getattr(params, "motion_profile", "CVM") == "RVO":       # RVO.RVO_update reads velocities and the pillars
+        keys = keys + ("agent_vel", "obstacles")
     return {k: np.ascontiguousarray(np.stack([w[k] for w in ws])) for k in keys}

@@ -46,6 +46,9 @@ typedef enum d2d_status {
 
 typedef enum d2d_planner { D2D_PLANNER_NOMOVE = 0, D2D_PLANNER_PRIMITIVE = 1 } d2d_planner;
 
+/* params.motion_profile: constant-velocity agents (velocity IS pref_velocity) or reciprocal velocity obstacles */
+typedef enum d2d_motion { D2D_MOTION_CVM = 0, D2D_MOTION_RVO = 1 } d2d_motion;
+
 /* scalar gaze policies of yaw_planner.py that d2d_plan_gaze evaluates for every env */
 typedef enum d2d_gaze { D2D_GAZE_NOCONTROL = 0, D2D_GAZE_ROTATING = 1, D2D_GAZE_LOOKAHEAD = 2, D2D_GAZE_LOOKGOAL = 3 } d2d_gaze;
 
@@ -76,7 +79,7 @@ typedef struct d2d_config {
     int32_t n_rays;                  /* ceil(map_size[0] / strip_width), utils.py:587 */
     int32_t n_targets;
     int32_t n_u, n_samp, n_way, n_yaw;
-    int32_t reserved0;
+    int32_t motion_profile;          /* d2d_motion: how the agents move (params.motion_profile, drone_v2.py:169-179) */
     double dt, map_scale, map_w, map_h;
     double agent_radius;             /* params.agent_radius */
     double drone_max_acceleration, drone_radius, drone_max_yaw_speed;
@@ -123,6 +126,15 @@ int d2d_set_world(d2d_handle *h, int32_t first_env, int32_t count, const double 
  * `sigma * np.random.randn(2)` (utils.py:605) continues this stream; reset() restores it. */
 int d2d_set_rng(d2d_handle *h, int32_t first_env, int32_t count, const uint32_t *key, const int32_t *pos,
                 const int32_t *has_gauss, const double *gauss);
+
+/* Needed when cfg.motion_profile = D2D_MOTION_RVO (RVO.RVO_update, utils.py:299-357, called at drone_v2.py:169-175): the
+ * agents' initial velocities (drone_v2.py:19 `(0., 0.)` for the random agents, :62 the group velocity for map-cell agents)
+ * and the circular obstacles of init_obstacles_random_size (drone_v2.py:14-27), HOST arrays:
+ *   agent_vel [count][N][2] f64, obstacles [count][max_obstacles][3] f64 (x, y, rad), num_obstacles [count] i32 (<= 16).
+ * Stored as part of the reset snapshot.  The step then runs d2d_rvo_kernel before Agent.step; atan2 / asin / sin / cos of
+ * run-time values are CUDA's, so agent state matches the reference to 1e-9 rather than bit for bit under this profile. */
+int d2d_set_rvo(d2d_handle *h, int32_t first_env, int32_t count, const double *agent_vel, const double *obstacles,
+                const int32_t *num_obstacles, int32_t max_obstacles);
 
 /* Replaces Drone2DEnv2.reset() (drone_v2.py:259-261) for every env whose mask byte is non-zero
  * (mask_dev == NULL: all).  mask_dev is a DEVICE pointer to num_envs bytes. */

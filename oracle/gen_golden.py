@@ -107,6 +107,17 @@ def main():
             continue
         r = rr.run_episode(800, policy="Oxford", planner="Primitive", stop_on_done=True, record_oxford=True, **kw)
         save(name, r, WORLD + STEP_CORE + TRACK + PLAN + ["ox_last"])
+    # --- RVO motion profile (utils.py:299-460): agents avoid each other and the pillars; velocity is its own array
+    rvo = [
+        ("rvo_nomove_pillars_s3", dict(map_id=3, agent_number=6, pillar_number=2), 60, None, "NoMove"),
+        ("rvo_nomove_crowd_s1", dict(map_id=1, agent_number=40, agent_radius=15, agent_max_speed=20), 30, (250.0, 250.0, 90.0), "NoMove"),
+        ("rvo_primitive_s7", dict(map_id=7, agent_number=8, pillar_number=3), 120, None, "Primitive"),
+    ]
+    for name, kw, steps, pose, planner in rvo:
+        if only not in name:
+            continue
+        r = rr.run_episode(steps, actions=acts, set_pose=pose, planner=planner, motion_profile="RVO", stop_on_done=True, **kw)
+        save(name, r, WORLD + ["agent_vel0", "obstacles", "agent_vel"] + STEP_CORE + TRACK + (PLAN if planner == "Primitive" else []))
 
 
 if __name__ == "__main__":

@@ -57,6 +57,8 @@ class Env(C.Structure):
         ("n_samples", C.c_int64),
         ("rng_key", C.c_uint32 * 624), ("rng_pos", C.c_int32), ("rng_has_gauss", C.c_int32), ("rng_gauss", C.c_double),
         ("meas", _P(C.c_double)),
+        ("motion_rvo", C.c_int32), ("n_obs", C.c_int32), ("avel", _P(C.c_double)), ("obs", _P(C.c_double)),
+        ("rvo_fallbacks", C.c_int64),
     ]
 
 
@@ -94,6 +96,7 @@ def lib():
         L.d2do_run_many.restype = C.c_int64
         L.d2do_run_many_oxford.argtypes = [_P(_P(Env)), C.c_int, C.c_int]
         L.d2do_run_many_oxford.restype = C.c_int64
+        L.d2do_set_rvo.argtypes = [_P(Env), _P(C.c_double), _P(C.c_double), C.c_int]
         L.d2do_sizeof_params.restype = C.c_size_t
         L.d2do_sizeof_env.restype = C.c_size_t
         assert L.d2do_sizeof_params() == C.sizeof(Params), (L.d2do_sizeof_params(), C.sizeof(Params))
@@ -215,6 +218,14 @@ class OracleEnv(object):
         for i, v in enumerate(np.asarray(key, dtype=np.uint32).tolist()):
             self.c.rng_key[i] = v
         self.c.rng_pos, self.c.rng_has_gauss, self.c.rng_gauss = int(pos), int(has_gauss), float(gauss)
+
+    def set_rvo(self, vel0, obstacles):
+        """motion_profile == 'RVO' (drone_v2.py:169-175): initial agent velocities [n,2] and pillars [m,3] (x, y, rad)"""
+        v = np.ascontiguousarray(np.asarray(vel0, dtype=np.float64).reshape(max(self.n, 0), 2))
+        o = np.ascontiguousarray(np.asarray(obstacles, dtype=np.float64).reshape(-1, 3))
+        dp = C.POINTER(C.c_double)
+        lib().d2do_set_rvo(self._ptr, v.ctypes.data_as(dp), o.ctypes.data_as(dp), int(o.shape[0]))
+        self.avel = np.ctypeslib.as_array(self.c.avel, (max(self.n, 1), 2))
 
     def step(self, a):
         return bool(lib().d2do_step(self._ptr, float(a)))

@@ -82,6 +82,8 @@ def world_snapshot(env):
         tracker_radius=np.array([float(env.drone.trackers[i].radius) for i in range(n)]),
         gt_grid=env.map_gt.grid_map.copy(),
         drone0=np.array([float(env.drone.x), float(env.drone.y), float(env.drone.yaw)]),
+        agent_vel0=np.array([np.asarray(a.velocity, dtype=np.float64) for a in env.agents]).reshape(n, 2),
+        obstacles=np.array([np.asarray(o, dtype=np.float64) for o in env.obstacles]).reshape(len(env.obstacles), 3),
     )
 
 
@@ -149,7 +151,7 @@ def run_episode(steps, actions=None, policy=None, set_pose=None, stop_on_done=Fa
     env.planner.plan = plan_spy
     env.planner.replan_check = replan_spy
 
-    rec = {k: [] for k in ("action", "agent_pos", "agent_pref", "belief", "hit", "newly", "collision", "done",
+    rec = {k: [] for k in ("action", "agent_pos", "agent_pref", "agent_vel", "belief", "hit", "newly", "collision", "done",
                            "dead_lock", "freezing", "state_machine", "fail_count", "drone", "drone_vel",
                            "local_map", "yaw_obs", "traj_len", "replan", "plan_ok", "planned", "target",
                            "trk_active", "trk_mu", "trk_sigma", "trk_radius", "trk_ts", "buf_count", "buf_ts",
@@ -167,6 +169,7 @@ def run_episode(steps, actions=None, policy=None, set_pose=None, stop_on_done=Fa
             rec["action"].append(float(a))
             rec["agent_pos"].append(np.array([np.asarray(ag.position, dtype=np.float64) for ag in env.agents]).reshape(n, 2))
             rec["agent_pref"].append(np.array([np.asarray(ag.pref_velocity, dtype=np.float64) for ag in env.agents]).reshape(n, 2))
+            rec["agent_vel"].append(np.array([np.asarray(ag.velocity, dtype=np.float64) for ag in env.agents]).reshape(n, 2))
             rec["belief"].append(env.drone.map.grid_map.copy())
             rec["hit"].append(seen["hit"].copy())
             rec["newly"].append(int(seen["newly"]))

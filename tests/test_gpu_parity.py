@@ -257,7 +257,7 @@ def test_error_paths_are_loud():
     with pytest.raises(ValueError):
         _env(Params(debug=False, planner="MPC"), 4, None)
     with pytest.raises(ValueError):
-        _env(Params(debug=False, planner="NoMove", motion_profile="RVO"), 4, None)
+        _env(Params(debug=False, planner="NoMove", motion_profile="ORCA"), 4, None)
     env = _env(Params(debug=False, planner="NoMove", agent_number=3), 4, None, oxford=False)
     with pytest.raises(_native.Drone2DNativeError):
         env.plan_oxford()

@@ -31,6 +31,8 @@ def _run_against_golden(g, use_oxford):
         assert (e.c.x, e.c.y, e.c.yaw) == tuple(g["drone"][t]), ("drone", t)
         assert (e.c.vx, e.c.vy) == tuple(g["drone_vel"][t]), ("vel", t)
         assert np.array_equal(e.apos[:n], g["agent_pos"][t]) and np.array_equal(e.apref[:n], g["agent_pref"][t]), ("agents", t)
+        if "agent_vel" in g:      # RVO motion profile: agent.velocity is its own array (utils.py:299-357)
+            assert np.array_equal(e.avel[:n], g["agent_vel"][t]), ("agent velocity", t)
         assert e.c.newly_tracked == g["newly"][t]
         if has_trk:
             act = g["trk_active"][t]
@@ -51,7 +53,18 @@ def _run_against_golden(g, use_oxford):
                 plan_i += 1
         if d and first_done == T:
             first_done = t
+    fallbacks = int(e.c.rvo_fallbacks)
     e.close()
+    return fallbacks
+
+
+@pytest.mark.parametrize("path", util.golden_files("rvo_"), ids=lambda p: p.split("/")[-1][:-4])
+def test_oracle_matches_reference_rvo(path):
+    """RVO.RVO_update / intersect / in_between (utils.py:299-460) restated in C: positions, velocities and preferred
+    velocities bit for bit against the reference's own run (glibc atan2 / asin / sin / cos on both sides)."""
+    fb = _run_against_golden(util.load_golden(path), use_oxford=False)
+    if "crowd" in path:
+        assert fb > 0, "the crowded fixture must reach the 'no suitable velocity' branch (utils.py:399-430)"
 
 
 @pytest.mark.parametrize("path", util.golden_files("nomove_"), ids=lambda p: p.split("/")[-1][:-4])

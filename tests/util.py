@@ -52,6 +52,8 @@ def oracle_env_from_world(p, world, i=None, drone=None):
                          targets=p.target_list)
     if "rng_key" in w:
         e.set_rng(w["rng_key"], w["rng_pos"], w["rng_has_gauss"], w["rng_gauss"])
+    if getattr(p, "motion_profile", "CVM") == "RVO":
+        e.set_rvo(w["agent_vel"], w["obstacles"])
     return e
 
 
@@ -60,6 +62,8 @@ def world_from_golden(g, copies=1):
              tracker_radius=g["tracker_radius"], gt_grid=g["gt_grid"], drone_pose=g["drone0"])
     if "rng_key" in g and g["params"].get("var_cam", 0) != 0:
         w.update(rng_key=g["rng_key"], rng_pos=g["rng_pos"], rng_has_gauss=g["rng_has_gauss"], rng_gauss=g["rng_gauss"])
+    if g["params"].get("motion_profile", "CVM") == "RVO":
+        w.update(agent_vel=g["agent_vel0"], obstacles=g["obstacles"])
     return {k: np.ascontiguousarray(np.stack([v] * copies)) for k, v in w.items()}
 
 
