@@ -143,6 +143,9 @@ def cpu_port_run(pk, n_envs, steps, threads, seed0=1, oxford=False):
     envs = [oracle.OracleEnv(op, worlds["agent_pos"][i], worlds["agent_pref"][i], worlds["agent_radius"][i],
                              worlds["gt_grid"][i], worlds["tracker_radius"][i], drone=worlds["drone_pose"][i],
                              targets=p.target_list) for i in range(n_envs)]
+    if p.motion_profile == "RVO":
+        for i, e in enumerate(envs):
+            e.set_rvo(worlds["agent_vel"][i], worlds["obstacles"][i])
     L = oracle.lib()
     table = np.arange(-80, 80, 80 / 3) / 80
     rng = np.random.RandomState(0)
@@ -216,6 +219,7 @@ def main():
     ap.add_argument("--strip-width", type=int, default=10, help="ray strip width: rays = ceil(500 / strip_width) (config 5 sweep: 10/5/2)")
     ap.add_argument("--view-range", type=int, default=0, help="drone_view_range in degrees (config 5 sweep: 90/180/360)")
     ap.add_argument("--planner", default=None, choices=["NoMove", "Primitive"], help="override the config's planner")
+    ap.add_argument("--motion-profile", default=None, choices=["CVM", "RVO"], help="agent motion profile (default CVM)")
     ap.add_argument("--e2e-full-copy", action="store_true", help="e2e leg with plain D2H copies instead of the zero-copy mirror")
     ap.add_argument("--gaze", default=None, choices=["scripted", "Oxford"],
                     help="scripted: random actions from the Oxford action set; Oxford: d2d_plan_oxford every step")
@@ -227,6 +231,9 @@ def main():
         cfg["params"] = dict(cfg["params"], planner=args.planner)
         if args.planner != CONFIGS[args.config]["params"]["planner"]:
             cfg["name"] += " [planner=%s]" % args.planner
+    if args.motion_profile and args.motion_profile != "CVM":
+        cfg["params"] = dict(cfg["params"], motion_profile=args.motion_profile)
+        cfg["name"] += " [motion_profile=%s]" % args.motion_profile
     if args.view_range:
         cfg["params"] = dict(cfg["params"], drone_view_range=args.view_range)
         cfg["name"] += " [view_range=%d]" % args.view_range

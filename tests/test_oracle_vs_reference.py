@@ -18,7 +18,8 @@ def _compare(steps, policy=None, set_pose=None, **kw):
     p = Params(debug=False, **{k: P[k] for k in util.PARAM_KEYS if k in P}, init_pos=P["init_position"],
                target_list=P["target_list"])
     world = dict(agent_pos=r["agent_pos0"], agent_pref=r["agent_pref0"], agent_radius=r["agent_radius"],
-                 tracker_radius=r["tracker_radius"], gt_grid=r["gt_grid"], drone_pose=r["drone0"])
+                 tracker_radius=r["tracker_radius"], gt_grid=r["gt_grid"], drone_pose=r["drone0"],
+                 agent_vel=r["agent_vel0"], obstacles=r["obstacles"])
     e = util.oracle_env_from_world(p, world)
     n = r["n_agents"]
     for t in range(len(r["done"])):
@@ -30,6 +31,8 @@ def _compare(steps, policy=None, set_pose=None, **kw):
         assert (e.c.collision, d) == (r["collision"][t], bool(r["done"][t])), t
         assert (e.c.x, e.c.y, e.c.yaw, e.c.vx, e.c.vy) == (*r["drone"][t], *r["drone_vel"][t]), t
         assert np.array_equal(e.apos[:n], r["agent_pos"][t]), t
+        if p.motion_profile == "RVO":
+            assert np.array_equal(e.avel[:n], r["agent_vel"][t]) and np.array_equal(e.apref[:n], r["agent_pref"][t]), t
         assert np.array_equal(e.local_map, r["local_map"][t]), t
         assert e.c.traj_len == r["traj_len"][t] and e.c.state_machine == r["state_machine"][t], t
         assert np.array_equal(e.trk_active[:n].astype(bool), r["trk_active"][t]), t
@@ -40,6 +43,13 @@ def _compare(steps, policy=None, set_pose=None, **kw):
 @pytest.mark.parametrize("smap", ["maps/empty_map.npy", "maps/obstacle_map.npy"])
 def test_nomove_live(seed, smap):
     _compare(40, planner="NoMove", map_id=seed, static_map=smap, set_pose=(200.5 + seed, 260.25, 77.0))
+
+
+@pytest.mark.parametrize("kw", [dict(map_id=13, agent_number=7, pillar_number=2), dict(map_id=2, agent_number=40, agent_radius=15, agent_max_speed=20)],
+                         ids=["pillars", "crowd"])
+def test_rvo_live(kw):
+    """RVO motion profile (utils.py:299-460): velocities, preferred velocities and positions bit for bit."""
+    _compare(25, planner="NoMove", motion_profile="RVO", **kw)
 
 
 def test_full_episode_live():
@@ -64,6 +74,8 @@ def test_world_generation_live(kw):
         assert np.array_equal(w["agent_pos"], ws["agent_pos0"]) and np.array_equal(w["agent_pref"], ws["agent_pref0"])
         assert np.array_equal(w["agent_radius"], ws["agent_radius"]) and np.array_equal(w["tracker_radius"], ws["tracker_radius"])
         assert np.array_equal(w["gt_grid"] == 1, ws["gt_grid"] == 1), seed
+        # inputs of the RVO motion profile: Agent.velocity after __init__ and the pillars (drone_v2.py:14-27, 19, 62)
+        assert np.array_equal(w["agent_vel"], ws["agent_vel0"]) and np.array_equal(w["obstacles"], ws["obstacles"]), seed
 
 
 @pytest.mark.parametrize("policy,kind", [("LookAhead", 2), ("LookGoal", 3), ("Rotating", 1), ("NoControl", 0)])
@@ -76,7 +88,8 @@ def test_scalar_gaze_policies_live(policy, kind):
     p = Params(debug=False, **{k: P[k] for k in util.PARAM_KEYS if k in P}, init_pos=P["init_position"],
                target_list=P["target_list"])
     world = dict(agent_pos=r["agent_pos0"], agent_pref=r["agent_pref0"], agent_radius=r["agent_radius"],
-                 tracker_radius=r["tracker_radius"], gt_grid=r["gt_grid"], drone_pose=r["drone0"])
+                 tracker_radius=r["tracker_radius"], gt_grid=r["gt_grid"], drone_pose=r["drone0"],
+                 agent_vel=r["agent_vel0"], obstacles=r["obstacles"])
     e = util.oracle_env_from_world(p, world)
     for t in range(len(r["done"])):
         a = e.policy_plan(kind)
