@@ -52,7 +52,7 @@ __device__ __forceinline__ void d2d_rvo_make_cone(RvoCone &c, double pAx, double
 }
 
 __global__ void __launch_bounds__(D2D_RVO_WARPS * 32) d2d_rvo_kernel(const DevP P) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int N = P.N, NP = P.NP;
     if (e >= P.B || N <= 0) return;                 // drone_v2.py:170: only with at least one agent

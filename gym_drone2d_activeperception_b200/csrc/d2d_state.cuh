@@ -63,7 +63,7 @@ struct DevP {
     float *yaw_mirror;           // [B] or null
     uint8_t *done_mirror;        // [B] or null
 #ifdef D2D_WARP_PROF
-    unsigned long long *prof;    // [B][6]: 4 globaltimer stamps, smid, warpid of the fused warp kernel (tools/warp_prof.py builds with -DD2D_WARP_PROF)
+    unsigned long long *prof;    // [B][12]: 10 globaltimer stamps, smid, warpid of the fused warp kernel (tools/warp_prof.py builds with -DD2D_WARP_PROF)
 #endif
     float *reward;               // [B] zeros (drone_v2.py:257)
     int8_t *hit;                 // [B][NP]

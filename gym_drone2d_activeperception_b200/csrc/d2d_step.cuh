@@ -948,10 +948,10 @@ __device__ D2D_COLD void d2d_obs_env_warp(const DevP &P, const uint8_t *bel, int
 #ifdef D2D_WARP_PROF
 __device__ __forceinline__ void d2d_prof_stamp(const DevP &P, int e, int k, int lane) {
     if (lane == 0) {
-        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); P.prof[(size_t)e * 6 + k] = t;
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); P.prof[(size_t)e * 12 + k] = t;
         if (k == 0) {
             unsigned sm, wi; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); asm volatile("mov.u32 %0, %%warpid;" : "=r"(wi));
-            P.prof[(size_t)e * 6 + 4] = sm; P.prof[(size_t)e * 6 + 5] = wi;
+            P.prof[(size_t)e * 12 + 10] = sm; P.prof[(size_t)e * 12 + 11] = wi;
         }
     }
 }
@@ -992,8 +992,10 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
 #pragma unroll 1
     for (int w = lane; w < P.HW; w += 32) c.hitw[w] = 0u;
     __syncwarp();
+    D2D_PROF(4);
     d2d_reset_arrays(P, c, e, 1, lane, 32, c.mbar);
     d2d_phase_agents<true, true>(P, c, e, 1, lane, 32, pf_pos, pf_pref, pf_r);
+    D2D_PROF(5);
     if (lane == 0) d2d_leader_begin(P, s);
     // NoMove: the drone cell cannot change during the step, so if the observation tensor already holds this window it
     // is patched in place by the rays (only cells whose value changes) instead of being rewritten
@@ -1002,6 +1004,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     RayOut ro;
     ro.bel_s = c.belief; ro.e = e; ro.patch = patch ? 1 : 0;
     ro.wi = s.ix - 16; ro.wj = s.iy - 16; ro.chg = nullptr; ro.nchg = nullptr;
+    D2D_PROF(6);
     d2d_mbar_wait(c.mbar, 0);
     D2D_PROF(1);
     d2d_phase_rays_warp<ILP2>(P, c, ro, lane);
@@ -1012,8 +1015,10 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
         __syncwarp();
     }
     d2d_phase_trackers(P, c, e, 1, lane, 32);
+    D2D_PROF(7);
     const int shit = __any_sync(0xffffffffu, lane < 5 ? d2d_static_probe(P, c.gt, s.px, s.py, lane) : 0);
     __syncwarp();
+    D2D_PROF(8);
     if (lane == 0) {
         // NoMove.plan traj_planner.py:70-73 / NoMove.replan_check :75-76
         s.tgx = -1.0; s.tgy = -1.0;
@@ -1028,6 +1033,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
         }
     }
     __syncwarp();
+    D2D_PROF(9);
     if (!patch || s.ix != oix || s.iy != oiy) {
         d2d_obs_env_warp(P, c.belief, s.ix, s.iy, e, lane);
         if (lane == 0) { P.obs_ix[e] = s.ix; P.obs_iy[e] = s.iy; }

@@ -336,7 +336,7 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.ox_calls = (int *)(A + o_oxc); P.ox_tab = (const double *)(A + o_oxt); P.ox_last = nullptr;
     P.lm_mirror = nullptr; P.yaw_mirror = nullptr; P.done_mirror = nullptr;
 #ifdef D2D_WARP_PROF
-    cudaMalloc((void **)&P.prof, (size_t)B * 48); cudaMemset(P.prof, 0, (size_t)B * 48);
+    cudaMalloc((void **)&P.prof, (size_t)B * 96); cudaMemset(P.prof, 0, (size_t)B * 96);
 #endif
     P.tmp_act_cnt = (int *)(A + o_tac); P.tmp_act_ts = (int *)(A + o_tat); P.ox_fresh = A + o_oxf;
     P.obs_ix = (int *)(A + o_obx); P.obs_iy = (int *)(A + o_oby);
@@ -419,9 +419,9 @@ extern "C" int d2d_get_buffer(d2d_handle *h, const char *name, d2d_buffer_info *
     }
 #ifdef D2D_WARP_PROF
     if (std::string(name) == "warp_prof") {
-        out->dev_ptr = h->P.prof; out->nbytes = (int64_t)h->B * 48; out->dtype = D2D_I64; out->ndim = 2;
-        out->shape[0] = h->B; out->shape[1] = 6; out->shape[2] = 1; out->shape[3] = 1;
-        out->strides[0] = 6; out->strides[1] = 1; out->strides[2] = 1; out->strides[3] = 1;
+        out->dev_ptr = h->P.prof; out->nbytes = (int64_t)h->B * 96; out->dtype = D2D_I64; out->ndim = 2;
+        out->shape[0] = h->B; out->shape[1] = 12; out->shape[2] = 1; out->shape[3] = 1;
+        out->strides[0] = 12; out->strides[1] = 1; out->strides[2] = 1; out->strides[3] = 1;
         return D2D_OK;
     }
 #endif

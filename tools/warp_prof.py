@@ -41,6 +41,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
     prof = env.buffer("warp_prof")
     rows = []
+    fine_rows = []
     by_nc = {}
     for t in range(args.steps):
         flush.fill_(t & 255)
@@ -60,6 +61,9 @@ def main():
                                 hit=env.buffer("hit").cpu().numpy(), belief_cells=(env.buffer("belief") != 0).sum((1, 2)).cpu().numpy(),
                                 tracker_active=env.buffer("tracker_active").cpu().numpy(), act=acts[t].cpu().numpy())
         if t >= 10:
+            seq = [0, 4, 5, 6, 1, 2, 7, 8, 9, 3]        # stamp slots in program order
+            fine_rows.append([np.median(p[:, seq[k + 1]] - p[:, seq[k]]) for k in range(len(seq) - 1)])
+        if t >= 10:
             # culled-list length per env (agents within depth + 9*sqrt(2) + r of the drone), from the post-step state
             ap = env.buffer("agent_pos").cpu().numpy().reshape(B, -1, 2)
             ar = env.buffer("agent_radius").cpu().numpy().reshape(B, -1)
@@ -76,6 +80,13 @@ def main():
     names = ["kernel_ns(first entry -> last exit)", "start_p50", "start_max", "dur_p50", "dur_p90", "dur_max", "pre_p50",
              "rays_p50", "tail_p50", "n_reset_envs", "dur_mean_of_reset_envs", "last_env", "last_env_was_reset",
              "pre_max", "rays_max", "tail_max"]
+    fine = np.array(fine_rows)
+    labels = ["entry -> scalars in shared (loads, bulk issue, hit-mask clear)", "agents phase (Agent.step, culling)",
+              "leader_begin + patch decision", "wait for the bulk copies", "ray phase", "trackers", "static probes",
+              "leader finish / flags / scalar stores", "observation rewrite + done stats"]
+    print("median per-warp phase durations, ns (mean over steps):")
+    for lab, v in zip(labels, fine.mean(0)):
+        print("  %-62s %8.1f" % (lab, v))
     for i, n in enumerate(names):
         print("%-38s mean %10.1f   min %10.1f   max %10.1f" % (n, r[:, i].mean(), r[:, i].min(), r[:, i].max()))
     print("ray-phase ns by culled-list length (mean over steps; envs per step):")
