@@ -186,15 +186,19 @@ __device__ D2D_COLD void d2d_finish_env_warp(const DevP &P, const BlockCtx &c, E
     }
     const bool any_hit = __any_sync(0xffffffffu, hit);
     const int shit = __any_sync(0xffffffffu, lane < 5 ? d2d_static_probe(P, c.gt, s.px, s.py, lane) : 0);
-    const int oix = P.obs_ix[e], oiy = P.obs_iy[e];
     if (lane == 0) {
         s.coll_agent = any_hit ? 1 : 0;
         d2d_leader_flags(P, s, c.gt, e, shit);
-        d2d_store_env_scalars(P, s, e);
         atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], 1ull);
     }
     __syncwarp();
-    if (allow_patch && !s.reset && oix == s.ix && oiy == s.iy && nchg <= D2D_CHG_CAP) {
+    // the observation tensor holds the window of cell (obs_ix, obs_iy): patch it if that is still the drone's cell
+    const bool do_patch = allow_patch && !s.reset && s.obs_ix == s.ix && s.obs_iy == s.iy && nchg <= D2D_CHG_CAP;
+    __syncwarp();
+    if (!do_patch && lane == 0) { s.obs_ix = s.ix; s.obs_iy = s.iy; }
+    __syncwarp();
+    d2d_store_env_warp(P, s, e, lane);
+    if (do_patch) {
         uint8_t *out = P.local_map + (size_t)e * D2D_LOCAL_CELLS;
         uint8_t *out_m = P.lm_mirror ? P.lm_mirror + (size_t)e * D2D_LOCAL_CELLS : nullptr;
 #pragma unroll 1
@@ -209,7 +213,6 @@ __device__ D2D_COLD void d2d_finish_env_warp(const DevP &P, const BlockCtx &c, E
         if (out_m && lane == 0 && nchg) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)nchg);
     } else {
         d2d_obs_env_warp(P, c.belief, s.ix, s.iy, e, lane);
-        if (lane == 0) { P.obs_ix[e] = s.ix; P.obs_iy[e] = s.iy; }
     }
     if (s.done_now) {
         int cnt = 0;
@@ -242,25 +245,29 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     // then the scalars
     double2 pf_pos = double2{0.0, 0.0}, pf_pref = double2{0.0, 0.0};
     double pf_r = 0.0;
+    uint8_t pf_act = 0;
     if (lane < P.N) {
         const size_t g = (size_t)e * P.NP + lane;
         pf_pos = P.apos[g]; pf_pref = P.apref[g]; pf_r = P.arad[g];
+        if (P.trackers) pf_act = P.trk_active[g];
     }
+    const double action = actions[e];
     if (lane == 0) {
         d2d_mbar_init(c.mbar, 1);
         d2d_mbar_expect_tx(c.mbar, D2D_GT_ROW_BYTES + D2D_BELIEF_STRIDE);
         d2d_bulk_g2s(c.gt, P.gt_rows + (size_t)e * D2D_GRID, D2D_GT_ROW_BYTES, c.mbar);
         d2d_bulk_g2s(c.belief, P.belief + (size_t)e * D2D_BELIEF_STRIDE, D2D_BELIEF_STRIDE, c.mbar);
         c.misc[0] = 0;
-        d2d_load_env_scalars(P, s, e);
-        c.misc[1] = s.reset;
         cnt[0] = 0; cnt[1] = 0;
     }
+    d2d_load_env_warp(P, s, e, lane);
+    if (lane == 0) c.misc[1] = s.reset;
 #pragma unroll 1
     for (int w = lane; w < P.HW; w += 32) c.hitw[w] = 0u;
     __syncwarp();
     d2d_reset_arrays(P, c, e, 1, lane, 32, c.mbar);
     d2d_phase_agents<false, true>(P, c, e, 1, lane, 32, pf_pos, pf_pref, pf_r);
+    if (pf_act && !s.reset) d2d_prefetch_tracker(P, (size_t)e * P.NP + lane);
     if (lane == 0) d2d_leader_begin(P, s);
     __syncwarp();
     RayOut ro;
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
         if (lane == 0) d2d_measure_env(P, c, e);
         __syncwarp();
     }
-    d2d_phase_trackers(P, c, e, 1, lane, 32);
+    d2d_phase_trackers<true>(P, c, e, 1, lane, 32, pf_act);
     __syncwarp();
     // ---- Primitive.replan_check (traj_planner.py:220-233)
     d2d_gather_trackers(P, e, trk, &cnt[0], lane, 32);
@@ -308,14 +315,16 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     const bool need = (s.nseg * P.n_way - s.cursor) == 0;
     if (!need) {
         if (lane == 0) P.need_plan[e] = 0;
-        d2d_finish_env_warp(P, c, s, e, lane, actions[e], true, true, cnt[1], chg, true);
-    } else if (lane == 0) {
-        P.need_plan[e] = 1;
-        const int slot = atomicAdd(&P.plan_list[P.B + 1 + par], 1);
-        P.plan_list[slot] = e;
-        P.tmp_act_cnt[e] = s.act_cnt; P.tmp_act_ts[e] = s.act_ts;
-        d2d_store_env_scalars(P, s, e);
-        P.done[e] = 0;
+        d2d_finish_env_warp(P, c, s, e, lane, action, true, true, cnt[1], chg, true);
+    } else {
+        if (lane == 0) {
+            P.need_plan[e] = 1;
+            const int slot = atomicAdd(&P.plan_list[P.B + 1 + par], 1);
+            P.plan_list[slot] = e;
+            P.tmp_act_cnt[e] = s.act_cnt; P.tmp_act_ts[e] = s.act_ts;
+            P.done[e] = 0;
+        }
+        d2d_store_env_warp(P, s, e, lane);
     }
 }
 
@@ -564,9 +573,9 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
                 d[5] = d2d_sq_threshold(P.drone_r + rad + 5.0 + P.var_cam);
             }
         }
-        const double tx = P.target_x[e], ty = P.target_y[e];
+        const double tx = P.rec[e].tgx, ty = P.rec[e].tgy;
         if (tid == 0) {   // start node (traj_planner.py:136-146)
-            const double x = P.drone_x[e], y = P.drone_y[e], vx = P.drone_vx[e], vy = P.drone_vy[e];
+            const double x = P.rec[e].px, y = P.rec[e].py, vx = P.rec[e].vx, vy = P.rec[e].vy;
             w.px[0] = x; w.py[0] = y; w.vx[0] = vx; w.vy[0] = vy; h.cost[0] = 0.0;
             h.open_total[0] = d2d_node_total(0.0, x, y, vx, vy, tx, ty);
             w.parent[0] = -1; w.itr[0] = 0; w.act[0] = 0;
@@ -720,9 +729,9 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
                     cf[0] = w.px[par]; cf[1] = w.vx[par]; cf[2] = P.tab->u_space[pidx / nu] / 2.0;
                     cf[3] = w.py[par]; cf[4] = w.vy[par]; cf[5] = P.tab->u_space[pidx - (pidx / nu) * nu] / 2.0;
                 }
-                P.traj_nseg[e] = depth; P.traj_cursor[e] = 0; P.plan_ok[e] = 1;
+                P.rec[e].nseg = depth; P.rec[e].cursor = 0; P.plan_ok[e] = 1;
             } else {
-                P.traj_nseg[e] = 0; P.traj_cursor[e] = 0; P.plan_ok[e] = 0;
+                P.rec[e].nseg = 0; P.rec[e].cursor = 0; P.plan_ok[e] = 0;
                 atomicAdd(&P.stats[D2D_STAT_PLAN_FAILURES], 1ull);
             }
         }
@@ -744,11 +753,10 @@ __global__ void __launch_bounds__(256) d2d_step_post_kernel(const DevP P, const 
         s.valid = e < P.B;
         s.reset = 0; s.coll_agent = 0; s.done_now = 0;
         if (s.valid) {
-            s.px = P.drone_x[e]; s.py = P.drone_y[e]; s.yaw = P.drone_yaw[e];
-            s.vx = P.drone_vx[e]; s.vy = P.drone_vy[e]; s.tgx = P.target_x[e]; s.tgy = P.target_y[e];
-            s.steps = P.steps[e]; s.sm = P.state_machine[e]; s.fail = P.fail_count[e]; s.tcur = P.target_cursor[e];
-            s.bufc = P.buf_count[e]; s.bufts = P.buf_ts[e]; s.tracked = P.tracked_agent[e];
-            s.nseg = P.traj_nseg[e]; s.cursor = P.traj_cursor[e];
+            const uint4 *src = (const uint4 *)(P.rec + e);   // the whole record: it is stored back verbatim below
+#pragma unroll
+            for (int i = 0; i < 8; i++) ((uint4 *)&s)[i] = src[i];
+            s.ix = 0; s.iy = 0; s.ncull = 0; s.ox_was_fresh = 0;
             s.arch_cnt = 0; s.arch_ts = 0; s.newly = 0;      // already applied by the pre kernel
             s.act_cnt = P.tmp_act_cnt[e]; s.act_ts = P.tmp_act_ts[e];
         }
@@ -900,10 +908,10 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
     if (e >= P.B) return;
     // an env that reported done and will be re-initialised by its next step is seen by the policy as freshly reset
     // (the reference builds a new env + policy per episode, experiment.py:27-34)
-    const bool fresh = P.pending_reset[e] || (P.auto_reset && P.done[e]);
-    const double dx = fresh ? P.pose0[e] : P.drone_x[e], dy = fresh ? P.pose0[P.B + e] : P.drone_y[e];
-    const double yaw = fresh ? P.pose0[2 * P.B + e] : P.drone_yaw[e];
-    const int len = fresh ? 0 : P.traj_nseg[e] * P.n_way - P.traj_cursor[e], cursor = fresh ? 0 : P.traj_cursor[e];
+    const bool fresh = P.rec[e].pending_reset || (P.auto_reset && P.done[e]);
+    const double dx = fresh ? P.rec[e].p0x : P.rec[e].px, dy = fresh ? P.rec[e].p0y : P.rec[e].py;
+    const double yaw = fresh ? P.rec[e].p0yaw : P.rec[e].yaw;
+    const int len = fresh ? 0 : P.rec[e].nseg * P.n_way - P.rec[e].cursor, cursor = fresh ? 0 : P.rec[e].cursor;
     const int ny = P.n_yaw;
     uint16_t *seen = P.ox_seen + (size_t)e * D2D_OX_SEEN_STRIDE;
     const int ncall = (fresh ? 0 : P.ox_calls[e]) + 1;          // index of this policy call within the episode
@@ -963,7 +971,7 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         }
     }
     if (len == 0) {                                                  // :117-118
-        if (tid == 0) { actions_out[e] = 0.0; P.ox_calls[e] = ncall; if (fresh) P.ox_fresh[e] = 1; }
+        if (tid == 0) { actions_out[e] = 0.0; P.ox_calls[e] = ncall; if (fresh) P.rec[e].ox_fresh = 1; }
         return;
     }
     __syncthreads();
@@ -1092,18 +1100,18 @@ __global__ void __launch_bounds__(128) d2d_gaze_kernel(const DevP P, int policy,
     if (e >= P.B) return;
     const double RAD2DEG = 180.0 / D2D_PI;      // CPython math.degrees
     // an env that reported done and will be re-initialised by its next step is seen as freshly reset
-    const bool fresh = P.pending_reset[e] || (P.auto_reset && P.done[e]);
+    const bool fresh = P.rec[e].pending_reset || (P.auto_reset && P.done[e]);
     double a = 0.0;
     if (policy == D2D_GAZE_ROTATING) a = 1.0;
     else if (policy == D2D_GAZE_LOOKAHEAD) {
-        const double vx = fresh ? 0.0 : P.drone_vx[e], vy = fresh ? 0.0 : P.drone_vy[e];
+        const double vx = fresh ? 0.0 : P.rec[e].vx, vy = fresh ? 0.0 : P.rec[e].vy;
         if (!(vy == 0.0 && vx == 0.0)) {
             const double ty = d2d_pymod(atan2(-vy, vx) * RAD2DEG, 360.0);
-            a = d2d_turn_towards(P, ty, P.drone_yaw[e]);
+            a = d2d_turn_towards(P, ty, P.rec[e].yaw);
         }
     } else if (policy == D2D_GAZE_LOOKGOAL) {
-        const int cursor = P.traj_cursor[e];
-        const int len = fresh ? 0 : P.traj_nseg[e] * P.n_way - cursor;
+        const int cursor = P.rec[e].cursor;
+        const int len = fresh ? 0 : P.rec[e].nseg * P.n_way - cursor;
         if (len > 0) {
             const uint8_t *bel = P.belief + (size_t)e * D2D_BELIEF_STRIDE;
             int first = len;                       // first waypoint lying in an UNEXPLORED belief cell
@@ -1118,8 +1126,8 @@ __global__ void __launch_bounds__(128) d2d_gaze_kernel(const DevP P, int policy,
             for (int off = 16; off > 0; off >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, off));
             double xl, yl;
             d2d_waypoint_pos(P, e, cursor + (first < len ? first : len - 1), xl, yl);
-            const double ty = d2d_pymod(atan2(-(yl - P.drone_y[e]), xl - P.drone_x[e]) * RAD2DEG, 360.0);
-            a = d2d_turn_towards(P, ty, P.drone_yaw[e]);
+            const double ty = d2d_pymod(atan2(-(yl - P.rec[e].py), xl - P.rec[e].px) * RAD2DEG, 360.0);
+            a = d2d_turn_towards(P, ty, P.rec[e].yaw);
         }
     }
     if (lane == 0) actions_out[e] = a;

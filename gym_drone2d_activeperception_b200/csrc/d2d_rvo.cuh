@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(D2D_RVO_WARPS * 32) d2d_rvo_kernel(const DevP 
     double *candx = (double *)(cones + N + D2D_RVO_MAX_OBS), *candy = candx + D2D_RVO_MAX_CAND;
     unsigned char *bad = (unsigned char *)(candy + D2D_RVO_MAX_CAND);
     // an env that is about to be re-initialised by this step (lazy reset) plans from its snapshot
-    const bool rs = P.pending_reset[e] != 0 || (P.auto_reset && P.done[e] != 0);
+    const bool rs = P.rec[e].pending_reset != 0 || (P.auto_reset && P.done[e] != 0);
     const double2 *gpos = (rs ? P.apos0 : P.apos) + (size_t)e * NP, *gvel = (rs ? P.avel0 : P.avel) + (size_t)e * NP;
     const double2 *gpref = (rs ? P.apref0 : P.apref) + (size_t)e * NP;
     for (int k = tid; k < N; k += blockDim.x) { spos[k] = gpos[k]; svel[k] = gvel[k]; }

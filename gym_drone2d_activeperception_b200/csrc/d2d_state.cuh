@@ -29,6 +29,23 @@ struct DevTables {   // lookup tables in global memory (read through the read-on
     double rvo_cos[D2D_RVO_THETAS], rvo_sin[D2D_RVO_THETAS];   // glibc cos / sin of np.arange(0, 2*3.14, 0.2) (utils.py:365)
 };
 
+// Everything persistent and scalar about ONE env, as one 128-byte line: a warp loads / stores it with a single coalesced
+// request (16 lanes x 8 B) instead of ~24 scattered sectors.  d2d_get_buffer exposes the fields as strided [B] views
+// ("drone_x", "steps", ...).  The step kernels copy it verbatim into the head of their shared-memory EnvS.
+struct __align__(16) EnvRec {
+    double px, py, yaw, vx, vy;      // drone pose / velocity (utils.py:714-731)
+    double tgx, tgy;                 // planner target (traj_planner.py:22)
+    double p0x, p0y, p0yaw;          // reset pose (drone_v2.py:88-117)
+    int steps, sm, fail, tcur;       // step counter, state machine, fail_count, next target index (drone_v2.py:153-163)
+    int bufc, bufts, tracked;        // tracker_buffer count / summed ts, newly tracked agents (drone_v2.py:187, 232-235)
+    int nseg, cursor;                // trajectory: remaining waypoints = nseg*n_way - cursor
+    int obs_ix, obs_iy;              // drone cell for which the local_map tensor content is currently valid
+    uint8_t pending_reset;           // reset requested by the host, applied lazily at the start of the next step
+    uint8_t ox_fresh;                // Oxford state already re-initialised for a pending reset
+    uint8_t pad_[2];
+};
+static_assert(sizeof(EnvRec) == 128, "EnvRec must be exactly one 128-byte line");
+
 struct DevP {
     int B, N, NP, HW;            // envs, agents, padded agents, hit words per env
     int n_rays, planner, trackers, auto_reset, n_targets;
@@ -49,11 +66,9 @@ struct DevP {
     double *arad, *trk_radius0;
     uint64_t *gt_rows;           // [B][50]
     uint8_t *belief;             // [B][D2D_BELIEF_STRIDE]
-    // drone + env bookkeeping [B]
-    double *drone_x, *drone_y, *drone_yaw, *drone_vx, *drone_vy, *pose0;  // pose0: [3][B]
-    double *target_x, *target_y;
-    int *steps, *state_machine, *fail_count, *target_cursor;
-    uint8_t *collision, *dead_lock, *freezing, *done, *pending_reset;
+    // drone + env bookkeeping: one 128-B record per env, plus the per-step verdict arrays [B]
+    EnvRec *rec;
+    uint8_t *collision, *dead_lock, *freezing, *done;
     // observation
     uint8_t *local_map;          // [B][1][33][33]
     float *yaw_obs;              // [B][1]
@@ -71,14 +86,10 @@ struct DevP {
     uint8_t *trk_active;
     double *trk_mu, *trk_sigma, *trk_radius;   // [B][NP][4], [B][NP][16], [B][NP]
     int *trk_ts;
-    int *buf_count, *buf_ts, *tracked_agent;   // [B]
     // trajectory as A* segments
     double *traj_coeff;          // [B][D2D_MAX_SEGMENTS][6]
-    int *traj_nseg, *traj_cursor;  // remaining waypoints = nseg*n_way - cursor
     uint8_t *need_plan, *plan_ok, *replan;
     int *tmp_act_cnt, *tmp_act_ts;   // still-active tracker totals, pre kernel -> post kernel
-    uint8_t *ox_fresh;           // Oxford state already re-initialised for a pending reset
-    int *obs_ix, *obs_iy;        // drone cell for which the local_map tensor content is currently valid
     // legacy np.random stream per env (MT19937 + cached gaussian), consumed by noisy measurements (var_cam != 0)
     uint32_t *rng_key, *rng_key0;   // [B][624] current / reset snapshot
     int *rng_pos, *rng_pos0, *rng_has, *rng_has0;

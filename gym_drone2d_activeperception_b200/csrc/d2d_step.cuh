@@ -57,13 +57,11 @@ __device__ __forceinline__ void d2d_mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------------------------------ shared-memory context
-struct EnvS {
-    double px, py, yaw, vx, vy, tgx, tgy;
-    int steps, sm, fail, tcur;
-    int bufc, bufts, tracked;
+// per-env working set in shared memory: the env's persistent record (copied verbatim from / to HBM) + this step's scratch
+struct EnvS : EnvRec {
     int valid, reset, ncull, coll_agent;
     int arch_cnt, arch_ts, act_cnt, act_ts, newly;
-    int done_now, nseg, cursor, ix, iy, ox_fresh;
+    int done_now, ix, iy, ox_was_fresh;
 };
 
 struct BlockCtx {
@@ -83,6 +81,7 @@ __host__ __device__ inline size_t d2d_step_smem_bytes(int E, int NP, int HW) {
     b += (size_t)E * NP * 8 * 5;
     b += ((size_t)E * NP * 2 + 15) / 16 * 16;
     b += ((size_t)E * HW * 4 + 15) / 16 * 16;
+    b = (b + 15) / 16 * 16;              // EnvS is copied with 16-byte accesses
     b += (size_t)E * sizeof(EnvS);
     b += 16 + 16;
     return b;
@@ -100,6 +99,7 @@ __device__ __forceinline__ BlockCtx d2d_carve(unsigned char *base, int E, int NP
     c.my = (double *)(base + o); o += (size_t)E * NP * 8;
     c.cull = (uint16_t *)(base + o); o += ((size_t)E * NP * 2 + 15) / 16 * 16;
     c.hitw = (uint32_t *)(base + o); o += ((size_t)E * HW * 4 + 15) / 16 * 16;
+    o = (o + 15) / 16 * 16;
     c.S = (EnvS *)(base + o); o += (size_t)E * sizeof(EnvS);
     c.mbar = (uint64_t *)(base + o); o += 16;
     c.misc = (int *)(base + o);
@@ -107,49 +107,56 @@ __device__ __forceinline__ BlockCtx d2d_carve(unsigned char *base, int E, int NP
 }
 
 // ------------------------------------------------------------------------------------------ P0: scalars + bulk loads
+// After the record has been copied into the head of `s`: lazy reset (Drone2DEnv2.__init__, drone_v2.py:88-117: drone at the
+// init pose, zero velocity, WAIT_FOR_GOAL; Planner.__init__ traj_planner.py:22) and this step's scratch.  One thread.
+__device__ __forceinline__ void d2d_env_begin(const DevP &P, EnvS &s, bool was_done) {
+    const bool rs = s.pending_reset != 0 || (P.auto_reset && was_done);
+    s.ox_was_fresh = s.ox_fresh;
+    s.pending_reset = 0; s.ox_fresh = 0;       // consumed; written back with the record at the end of the step
+    if (rs) {
+        s.px = s.p0x; s.py = s.p0y; s.yaw = s.p0yaw; s.vx = 0; s.vy = 0; s.tgx = s.p0x; s.tgy = s.p0y;
+        s.steps = 0; s.sm = SM_WAIT_FOR_GOAL; s.fail = 0; s.tcur = 0; s.bufc = 0; s.bufts = 0; s.tracked = 0;
+        s.nseg = 0; s.cursor = 0;
+    }
+    s.ix = d2d_cell(s.px, P.scale, P.inv_scale); s.iy = d2d_cell(s.py, P.scale, P.inv_scale);
+    s.valid = 1; s.reset = rs;
+    s.ncull = 0; s.coll_agent = 0; s.arch_cnt = 0; s.arch_ts = 0; s.act_cnt = 0; s.act_ts = 0; s.newly = 0; s.done_now = 0;
+}
+
+// single-thread load / store of an env's record (block kernels, list kernels): eight 16-byte accesses of one 128-byte line
 __device__ D2D_COLD void d2d_load_env_scalars(const DevP &P, EnvS &s, int e) {
-    // All global loads are issued into registers BEFORE anything is written to shared memory: the compiler cannot
-    // prove that the EnvS reference does not alias the global arrays, so interleaved load/store pairs would
-    // serialise ~20 DRAM round trips.
     if (e >= P.B) {
         s.valid = 0; s.reset = 0; s.done_now = 0; s.ncull = 0; s.coll_agent = 0;
         return;
     }
-    const bool pend = P.pending_reset[e] != 0, was_done = P.done[e] != 0;
-    const int oxf = P.ox_fresh[e];
-    const double p0x = P.pose0[e], p0y = P.pose0[P.B + e], p0yaw = P.pose0[2 * P.B + e];
-    const double gx = P.drone_x[e], gy = P.drone_y[e], gyaw = P.drone_yaw[e], gvx = P.drone_vx[e], gvy = P.drone_vy[e];
-    const double gtx = P.target_x[e], gty = P.target_y[e];
-    const int gsteps = P.steps[e], gsm = P.state_machine[e], gfail = P.fail_count[e], gtcur = P.target_cursor[e];
-    const int gbufc = P.buf_count[e], gbufts = P.buf_ts[e], gtracked = P.tracked_agent[e];
-    const int gnseg = P.traj_nseg[e], gcursor = P.traj_cursor[e];
-    const bool rs = pend || (P.auto_reset && was_done);
-    double px, py, yaw, vx, vy, tgx, tgy;
-    int steps, sm, fail, tcur, bufc, bufts, tracked, nseg, cursor;
-    if (rs) {   // Drone2DEnv2.__init__ (drone_v2.py:88-117): drone at init pose, zero velocity, WAIT_FOR_GOAL
-        px = p0x; py = p0y; yaw = p0yaw; vx = 0; vy = 0; tgx = p0x; tgy = p0y;   // Planner.__init__ traj_planner.py:22
-        steps = 0; sm = SM_WAIT_FOR_GOAL; fail = 0; tcur = 0; bufc = 0; bufts = 0; tracked = 0; nseg = 0; cursor = 0;
-    } else {
-        px = gx; py = gy; yaw = gyaw; vx = gvx; vy = gvy; tgx = gtx; tgy = gty;
-        steps = gsteps; sm = gsm; fail = gfail; tcur = gtcur; bufc = gbufc; bufts = gbufts; tracked = gtracked;
-        nseg = gnseg; cursor = gcursor;
-    }
-    const int ix = d2d_cell(px, P.scale, P.inv_scale), iy = d2d_cell(py, P.scale, P.inv_scale);
-    s.valid = 1; s.reset = rs; s.ox_fresh = oxf;
-    s.ncull = 0; s.coll_agent = 0; s.arch_cnt = 0; s.arch_ts = 0; s.act_cnt = 0; s.act_ts = 0; s.newly = 0; s.done_now = 0;
-    s.px = px; s.py = py; s.yaw = yaw; s.vx = vx; s.vy = vy; s.tgx = tgx; s.tgy = tgy;
-    s.steps = steps; s.sm = sm; s.fail = fail; s.tcur = tcur; s.bufc = bufc; s.bufts = bufts; s.tracked = tracked;
-    s.nseg = nseg; s.cursor = cursor; s.ix = ix; s.iy = iy;
-    if (pend) P.pending_reset[e] = 0;
-    if (oxf) P.ox_fresh[e] = 0;
+    const bool was_done = P.done[e] != 0;
+    const uint4 *src = (const uint4 *)(P.rec + e);
+    uint4 r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = src[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) ((uint4 *)&s)[i] = r[i];
+    d2d_env_begin(P, s, was_done);
 }
 
 __device__ D2D_COLD void d2d_store_env_scalars(const DevP &P, const EnvS &s, int e) {
-    P.drone_x[e] = s.px; P.drone_y[e] = s.py; P.drone_yaw[e] = s.yaw; P.drone_vx[e] = s.vx; P.drone_vy[e] = s.vy;
-    P.target_x[e] = s.tgx; P.target_y[e] = s.tgy;
-    P.steps[e] = s.steps; P.state_machine[e] = s.sm; P.fail_count[e] = s.fail; P.target_cursor[e] = s.tcur;
-    P.buf_count[e] = s.bufc; P.buf_ts[e] = s.bufts; P.tracked_agent[e] = s.tracked;
-    P.traj_nseg[e] = s.nseg; P.traj_cursor[e] = s.cursor;
+    uint4 *dst = (uint4 *)(P.rec + e);
+#pragma unroll
+    for (int i = 0; i < 8; i++) dst[i] = ((const uint4 *)&s)[i];
+}
+
+// warp-cooperative variants (one env per warp): a single coalesced 128-byte request each way
+__device__ __forceinline__ void d2d_load_env_warp(const DevP &P, EnvS &s, int e, int lane) {
+    unsigned long long w = 0ull;
+    uint8_t was_done = 0;
+    if (lane < 16) w = ((const unsigned long long *)(P.rec + e))[lane];
+    if (lane == 0) was_done = P.done[e];
+    if (lane < 16) ((unsigned long long *)&s)[lane] = w;
+    __syncwarp();
+    if (lane == 0) d2d_env_begin(P, s, was_done != 0);
+}
+__device__ __forceinline__ void d2d_store_env_warp(const DevP &P, const EnvS &s, int e, int lane) {
+    if (lane < 16) ((unsigned long long *)(P.rec + e))[lane] = ((const unsigned long long *)&s)[lane];
 }
 
 // issue the bulk copies for the block (thread 0) -- belief only for envs that are not being reset
@@ -200,7 +207,7 @@ __device__ D2D_COLD void d2d_reset_arrays(const DevP &P, const BlockCtx &c, int 
 #pragma unroll 1
         for (int w = tid; w < E * W; w += T) {
             const int i = w / W, o = w - i * W;
-            if (!c.S[i].valid || !c.S[i].reset || c.S[i].ox_fresh) continue;
+            if (!c.S[i].valid || !c.S[i].reset || c.S[i].ox_was_fresh) continue;
             ((uint32_t *)(P.ox_seen + (size_t)(env0 + i) * D2D_OX_SEEN_STRIDE))[o] = 0u;
             if (o == 0) P.ox_calls[env0 + i] = 0;
         }
@@ -318,9 +325,13 @@ __device__ __forceinline__ double d2d_ray_angle(const DevP &P, double yaw, int r
     return a;
 }
 
-__device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, double a, double slope, const RayOut &o,
-                                             const uint64_t *gt, const double *sx, const double *sy, const double *sr2,
-                                             const uint16_t *cull, uint32_t *hitw) {
+// Hits on the first 32 entries of the culled list are returned as a bit mask over the LIST SLOTS (the caller ORs the
+// masks of its rays and publishes them once: no shared-memory atomics inside the march, where a disc seen by ~20 rays
+// at the same sample index would serialise them); hits on the unfiltered tail go to `hitw` directly.
+__device__ __forceinline__ uint32_t d2d_cast_ray(const DevP &P, const EnvS &s, double a, double slope, const RayOut &o,
+                                                 const uint64_t *gt, const double *sx, const double *sy, const double *sr2,
+                                                 const uint16_t *cull, uint32_t *hitw) {
+    uint32_t hm = 0u;
     const bool faced_right = (a < 90.0 * D2D_DEG2RAD) || (a > 270.0 * D2D_DEG2RAD);
     const bool faced_up = a > D2D_PI;
     const double step = P.scale - 1.0;
@@ -399,7 +410,7 @@ __device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, doubl
                 const int k = cull[q];
                 const double ex = sx[k] - x, ey = sy[k] - y;
                 if (ex * ex + ey * ey <= sr2[k]) {
-                    atomicOr(&hitw[k >> 5], 1u << (k & 31));
+                    hm |= 1u << q;
                     any = true;
                 }
             }
@@ -436,6 +447,17 @@ __device__ __forceinline__ void d2d_cast_ray(const DevP &P, const EnvS &s, doubl
         if (cx) { ci += sxi; uxb += P.scale; }
         if (cy) { cj += syi; uyb += P.scale; }
     }
+    return hm;
+}
+
+// publish a slot mask returned by d2d_cast_ray: bit q -> agent cull[q]
+__device__ __forceinline__ void d2d_publish_hits(uint32_t hm, const uint16_t *cull, uint32_t *hitw) {
+    while (hm) {
+        const int q = __ffs(hm) - 1;
+        hm &= hm - 1u;
+        const int k = cull[q];
+        atomicOr(&hitw[k >> 5], 1u << (k & 31));
+    }
 }
 
 __device__ __forceinline__ void d2d_phase_rays(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
@@ -448,8 +470,9 @@ __device__ __forceinline__ void d2d_phase_rays(const DevP &P, const BlockCtx &c,
         o.bel_s = c.belief + (size_t)i * D2D_BELIEF_STRIDE;
         o.e = env0 + i; o.patch = 0; o.wi = 0; o.wj = 0; o.chg = nullptr; o.nchg = nullptr;
         const double a = d2d_ray_angle(P, s.yaw, ray);
-        d2d_cast_ray(P, s, a, d2d_tan(a), o, c.gt + (size_t)i * D2D_GRID, c.sx + i * NP, c.sy + i * NP, c.sr2 + i * NP,
-                     c.cull + i * NP, c.hitw + i * P.HW);
+        const uint32_t hm = d2d_cast_ray(P, s, a, d2d_tan(a), o, c.gt + (size_t)i * D2D_GRID, c.sx + i * NP, c.sy + i * NP,
+                                         c.sr2 + i * NP, c.cull + i * NP, c.hitw + i * P.HW);
+        d2d_publish_hits(hm, c.cull + i * NP, c.hitw + i * P.HW);
     }
 }
 
@@ -463,20 +486,27 @@ template <bool ILP2>
 __device__ __forceinline__ void d2d_phase_rays_warp(const DevP &P, const BlockCtx &c, const RayOut &o, int lane) {
     const EnvS &s = c.S[0];
     const int R = P.n_rays;
+    uint32_t hm = 0u;
     if (ILP2) {
         for (int r0 = lane; r0 < R; r0 += 64) {
             const int r1 = r0 + 32;
             const double a0 = d2d_ray_angle(P, s.yaw, r0), a1 = d2d_ray_angle(P, s.yaw, r1);
             const double t0 = d2d_tan(a0), t1 = d2d_tan(a1);
-            d2d_cast_ray(P, s, a0, t0, o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
-            if (r1 < R) d2d_cast_ray(P, s, a1, t1, o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
+            hm |= d2d_cast_ray(P, s, a0, t0, o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
+            if (r1 < R) hm |= d2d_cast_ray(P, s, a1, t1, o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
         }
     } else {
 #pragma unroll 1
         for (int ray = lane; ray < R; ray += 32) {
             const double a = d2d_ray_angle(P, s.yaw, ray);
-            d2d_cast_ray(P, s, a, d2d_tan(a), o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
+            hm |= d2d_cast_ray(P, s, a, d2d_tan(a), o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
         }
+    }
+    // OR over the warp, then lane q publishes slot q (all rays of the env are cast by this warp)
+    hm = __reduce_or_sync(0xffffffffu, hm);
+    if ((hm >> lane) & 1u) {
+        const int k = c.cull[lane];
+        atomicOr(&c.hitw[k >> 5], 1u << (k & 31));
     }
 }
 
@@ -538,11 +568,12 @@ __device__ __forceinline__ void d2d_measure_env(const DevP &P, const BlockCtx &c
 }
 
 // ------------------------------------------------------------------------------------------ P3: hit mask + trackers
-__device__ D2D_COLD void d2d_tracker_update(const DevP &P, EnvS &s, size_t g, bool measured, double z0, double z1) {
+__device__ D2D_COLD void d2d_tracker_update(const DevP &P, EnvS &s, size_t g, bool measured, double z0, double z1,
+                                            bool was_active) {
     // KalmanFilter.update utils.py:242-275; F = I + 0.1*shift, H = [I 0], Sigma_z = var_cam*I, Sigma_x = q*I
     const double q = (P.var_cam != 0.0) ? 0.1 : 0.001;
     double *mu = P.trk_mu + g * 4, *Sg = P.trk_sigma + g * 16;
-    bool active = s.reset ? false : (P.trk_active[g] != 0);
+    bool active = was_active;                      // already false for an env that is being reset
     int ts = s.reset ? 1 : P.trk_ts[g];
     if (s.reset) {   // fresh KalmanFilter(params) + drone_v2.py:46 radius
         P.trk_radius[g] = P.trk_radius0[g];
@@ -633,7 +664,11 @@ __device__ D2D_COLD void d2d_tracker_update(const DevP &P, EnvS &s, size_t g, bo
     }
 }
 
-__device__ __forceinline__ void d2d_phase_trackers(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T) {
+// PF: the caller (one warp, E == 1) loaded trk_active of tracker `tid` into pf_act at kernel entry, so the phase does not
+// start with a DRAM round trip
+template <bool PF = false>
+__device__ __forceinline__ void d2d_phase_trackers(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T,
+                                                   uint8_t pf_act = 0) {
     const int N = P.N, NP = P.NP;
 #pragma unroll 1
     for (int w = tid; w < E * N; w += T) {
@@ -644,15 +679,23 @@ __device__ __forceinline__ void d2d_phase_trackers(const DevP &P, const BlockCtx
         const bool hit = (c.hitw[i * P.HW + (k >> 5)] >> (k & 31)) & 1u;
         P.hit[g] = hit ? 1 : 0;
         if (P.trackers) {
-            const bool was_active = s.reset ? false : (P.trk_active[g] != 0);
+            const bool was_active = s.reset ? false : ((PF && w == tid) ? (pf_act != 0) : (P.trk_active[g] != 0));
             if (hit && !was_active) atomicAdd(&s.newly, 1);   // utils.py:606-607
             if (was_active || hit || s.reset) {
                 const bool noisy = P.var_cam != 0.0;
                 d2d_tracker_update(P, s, g, hit, noisy ? c.mx[i * NP + k] : c.sx[i * NP + k],
-                                   noisy ? c.my[i * NP + k] : c.sy[i * NP + k]);
+                                   noisy ? c.my[i * NP + k] : c.sy[i * NP + k], was_active);
             }
         }
     }
+}
+
+__device__ __forceinline__ void d2d_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// an active tracker's state (ts, mu, Sigma: 4 + 32 + 128 B) is needed long after the ray phase: have it waiting in L2
+__device__ __forceinline__ void d2d_prefetch_tracker(const DevP &P, size_t g) {
+    d2d_prefetch_l2(P.trk_ts + g);
+    d2d_prefetch_l2(P.trk_mu + g * 4);
+    d2d_prefetch_l2(P.trk_sigma + g * 16);
 }
 
 // ------------------------------------------------------------------------------------------ P4: leaders
@@ -973,34 +1016,37 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     // Everything the step needs from HBM is requested up front so that the cold-miss latencies overlap instead of
     // chaining: observation cursor, first 32 agents (speculatively from the live arrays), the bulk copies of the belief
     // grid + ground-truth rows, then the env scalars.
-    const int oix = P.obs_ix[e], oiy = P.obs_iy[e];
     double2 pf_pos = double2{0.0, 0.0}, pf_pref = double2{0.0, 0.0};
     double pf_r = 0.0;
+    uint8_t pf_act = 0;
     if (lane < P.N) {
         const size_t g = (size_t)e * P.NP + lane;
         pf_pos = P.apos[g]; pf_pref = P.apref[g]; pf_r = P.arad[g];
+        if (P.trackers) pf_act = P.trk_active[g];
     }
+    const double action = actions[e];                                // same address in every lane: one broadcast request
     if (lane == 0) {
         d2d_mbar_init(c.mbar, 1);
         d2d_mbar_expect_tx(c.mbar, D2D_GT_ROW_BYTES + D2D_BELIEF_STRIDE);
         d2d_bulk_g2s(c.gt, P.gt_rows + (size_t)e * D2D_GRID, D2D_GT_ROW_BYTES, c.mbar);
         d2d_bulk_g2s(c.belief, P.belief + (size_t)e * D2D_BELIEF_STRIDE, D2D_BELIEF_STRIDE, c.mbar);
         c.misc[0] = 0;
-        d2d_load_env_scalars(P, s, e);
-        c.misc[1] = s.reset;
     }
+    d2d_load_env_warp(P, s, e, lane);
+    if (lane == 0) c.misc[1] = s.reset;
 #pragma unroll 1
     for (int w = lane; w < P.HW; w += 32) c.hitw[w] = 0u;
     __syncwarp();
     D2D_PROF(4);
     d2d_reset_arrays(P, c, e, 1, lane, 32, c.mbar);
     d2d_phase_agents<true, true>(P, c, e, 1, lane, 32, pf_pos, pf_pref, pf_r);
+    if (pf_act && !s.reset) d2d_prefetch_tracker(P, (size_t)e * P.NP + lane);
     D2D_PROF(5);
     if (lane == 0) d2d_leader_begin(P, s);
     // NoMove: the drone cell cannot change during the step, so if the observation tensor already holds this window it
     // is patched in place by the rays (only cells whose value changes) instead of being rewritten
     __syncwarp();
-    const bool patch = !s.reset && oix == s.ix && oiy == s.iy;
+    const bool patch = !s.reset && s.obs_ix == s.ix && s.obs_iy == s.iy;
     RayOut ro;
     ro.bel_s = c.belief; ro.e = e; ro.patch = patch ? 1 : 0;
     ro.wi = s.ix - 16; ro.wj = s.iy - 16; ro.chg = nullptr; ro.nchg = nullptr;
@@ -1014,7 +1060,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
         if (lane == 0) d2d_measure_env(P, c, e);
         __syncwarp();
     }
-    d2d_phase_trackers(P, c, e, 1, lane, 32);
+    d2d_phase_trackers<true>(P, c, e, 1, lane, 32, pf_act);
     D2D_PROF(7);
     const int shit = __any_sync(0xffffffffu, lane < 5 ? d2d_static_probe(P, c.gt, s.px, s.py, lane) : 0);
     __syncwarp();
@@ -1023,9 +1069,8 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
         // NoMove.plan traj_planner.py:70-73 / NoMove.replan_check :75-76
         s.tgx = -1.0; s.tgy = -1.0;
         P.replan[e] = 0; P.plan_ok[e] = 1; P.need_plan[e] = 0;
-        d2d_leader_finish(P, s, c.gt, e, actions[e], true);
+        d2d_leader_finish(P, s, c.gt, e, action, true);
         d2d_leader_flags(P, s, c.gt, e, shit);
-        d2d_store_env_scalars(P, s, e);
         atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], 1ull);
         if (patch && P.lm_mirror) {
             const int nb = *(const int *)(c.belief + D2D_MIRCNT_OFF);
@@ -1034,10 +1079,13 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     }
     __syncwarp();
     D2D_PROF(9);
-    if (!patch || s.ix != oix || s.iy != oiy) {
-        d2d_obs_env_warp(P, c.belief, s.ix, s.iy, e, lane);
-        if (lane == 0) { P.obs_ix[e] = s.ix; P.obs_iy[e] = s.iy; }
-    }
+    // NoMove never moves the drone, but a pose set from outside (d2d_set_drone_pose) invalidates the window
+    const bool rewrite = !patch || s.ix != s.obs_ix || s.iy != s.obs_iy;
+    __syncwarp();
+    if (rewrite && lane == 0) { s.obs_ix = s.ix; s.obs_iy = s.iy; }
+    __syncwarp();
+    d2d_store_env_warp(P, s, e, lane);
+    if (rewrite) d2d_obs_env_warp(P, c.belief, s.ix, s.iy, e, lane);
     if (s.done_now) {
         int cnt = 0;
 #pragma unroll 1

@@ -1,5 +1,6 @@
 // drone2d.cu -- C-ABI implementation of libdrone2d.so (see include/drone2d.h).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3 --shared -Xcompiler -fPIC
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -80,6 +81,16 @@ static size_t add_buf(d2d_handle *h, size_t &cursor, const char *name, int dtype
     return b.offset;
 }
 
+// registers a named strided view of bytes that another buffer owns (fields of the per-env EnvRec records)
+static void add_view(d2d_handle *h, const char *name, int dtype, int ndim, std::initializer_list<int64_t> shape,
+                     std::initializer_list<int64_t> strides, size_t offset, size_t nbytes) {
+    BufDesc b;
+    b.name = name; b.dtype = dtype; b.ndim = ndim;
+    for (int i = 0; i < 4; i++) { b.shape[i] = i < ndim ? shape.begin()[i] : 1; b.strides[i] = i < ndim ? strides.begin()[i] : 1; }
+    b.offset = offset; b.nbytes = nbytes;
+    h->bufs.push_back(b);
+}
+
 extern "C" int d2d_version(void) { return D2D_VERSION; }
 
 extern "C" const char *d2d_last_error(const d2d_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
@@ -115,26 +126,26 @@ __global__ void d2d_reset_kernel(const DevP P, const uint8_t *__restrict__ mask)
     if (P.rng_key)
         for (int w = tid; w < 624; w += T) P.rng_key[(size_t)e * 624 + w] = P.rng_key0[(size_t)e * 624 + w];
     if (tid == 0) {
-        const double x = P.pose0[e], y = P.pose0[P.B + e], yaw = P.pose0[2 * P.B + e];
-        P.drone_x[e] = x; P.drone_y[e] = y; P.drone_yaw[e] = yaw; P.drone_vx[e] = 0; P.drone_vy[e] = 0;
-        P.target_x[e] = x; P.target_y[e] = y;
-        P.steps[e] = 0; P.state_machine[e] = SM_WAIT_FOR_GOAL; P.fail_count[e] = 0; P.target_cursor[e] = 0;
-        P.collision[e] = 0; P.dead_lock[e] = 0; P.freezing[e] = 0; P.done[e] = 0; P.pending_reset[e] = 0;
-        P.buf_count[e] = 0; P.buf_ts[e] = 0; P.tracked_agent[e] = 0;
-        P.traj_nseg[e] = 0; P.traj_cursor[e] = 0; P.need_plan[e] = 0; P.plan_ok[e] = 1; P.replan[e] = 0;
+        const double x = P.rec[e].p0x, y = P.rec[e].p0y, yaw = P.rec[e].p0yaw;
+        P.rec[e].px = x; P.rec[e].py = y; P.rec[e].yaw = yaw; P.rec[e].vx = 0; P.rec[e].vy = 0;
+        P.rec[e].tgx = x; P.rec[e].tgy = y;
+        P.rec[e].steps = 0; P.rec[e].sm = SM_WAIT_FOR_GOAL; P.rec[e].fail = 0; P.rec[e].tcur = 0;
+        P.collision[e] = 0; P.dead_lock[e] = 0; P.freezing[e] = 0; P.done[e] = 0; P.rec[e].pending_reset = 0;
+        P.rec[e].bufc = 0; P.rec[e].bufts = 0; P.rec[e].tracked = 0;
+        P.rec[e].nseg = 0; P.rec[e].cursor = 0; P.need_plan[e] = 0; P.plan_ok[e] = 1; P.replan[e] = 0;
         P.yaw_obs[e] = (float)yaw;
-        P.ox_fresh[e] = 0; P.tmp_act_cnt[e] = 0; P.tmp_act_ts[e] = 0; P.ox_calls[e] = 0;
+        P.rec[e].ox_fresh = 0; P.tmp_act_cnt[e] = 0; P.tmp_act_ts[e] = 0; P.ox_calls[e] = 0;
         P.rng_pos[e] = P.rng_pos0[e]; P.rng_has[e] = P.rng_has0[e]; P.rng_gauss[e] = P.rng_gauss0[e];
         // local_map was zeroed above, which IS the window of an all-unexplored belief grid at the initial cell
-        P.obs_ix[e] = d2d_cell(x, P.scale, P.inv_scale); P.obs_iy[e] = d2d_cell(y, P.scale, P.inv_scale);
+        P.rec[e].obs_ix = d2d_cell(x, P.scale, P.inv_scale); P.rec[e].obs_iy = d2d_cell(y, P.scale, P.inv_scale);
     }
 }
 
 __global__ void d2d_set_pose_kernel(const DevP P, const double *__restrict__ pose) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= P.B) return;
-    P.drone_x[e] = pose[3 * e]; P.drone_y[e] = pose[3 * e + 1]; P.drone_yaw[e] = pose[3 * e + 2];
-    P.obs_ix[e] = -1000000; P.obs_iy[e] = -1000000;   // the observation window must be rebuilt
+    P.rec[e].px = pose[3 * e]; P.rec[e].py = pose[3 * e + 1]; P.rec[e].yaw = pose[3 * e + 2];
+    P.rec[e].obs_ix = -1000000; P.rec[e].obs_iy = -1000000;   // the observation window must be rebuilt
 }
 
 // NumPy pairwise-sum recursion for a contiguous run of n doubles -> leaf blocks + post-order combine program
@@ -220,23 +231,30 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     size_t o_gt = add_buf(h, cur, "gt_rows", D2D_I64, 2, SHP(B, D2D_GRID), SHP(D2D_GRID, 1), (size_t)sB * D2D_GRID);
     size_t o_bel = add_buf(h, cur, "belief", D2D_U8, 3, SHP(B, D2D_GRID, D2D_GRID), SHP(D2D_BELIEF_STRIDE, D2D_GRID, 1),
                            (size_t)sB * D2D_BELIEF_STRIDE);
-    size_t o_dx = add_buf(h, cur, "drone_x", D2D_F64, 1, SHP(B), SHP(1), sB);
-    size_t o_dy = add_buf(h, cur, "drone_y", D2D_F64, 1, SHP(B), SHP(1), sB);
-    size_t o_dyaw = add_buf(h, cur, "drone_yaw", D2D_F64, 1, SHP(B), SHP(1), sB);
-    size_t o_dvx = add_buf(h, cur, "drone_vx", D2D_F64, 1, SHP(B), SHP(1), sB);
-    size_t o_dvy = add_buf(h, cur, "drone_vy", D2D_F64, 1, SHP(B), SHP(1), sB);
-    size_t o_pose0 = add_buf(h, cur, "drone_pose0", D2D_F64, 2, SHP(3, B), SHP(B, 1), (size_t)3 * sB);
-    size_t o_tx = add_buf(h, cur, "target_x", D2D_F64, 1, SHP(B), SHP(1), sB);
-    size_t o_ty = add_buf(h, cur, "target_y", D2D_F64, 1, SHP(B), SHP(1), sB);
-    size_t o_steps = add_buf(h, cur, "steps", D2D_I32, 1, SHP(B), SHP(1), sB);
-    size_t o_sm = add_buf(h, cur, "state_machine", D2D_I32, 1, SHP(B), SHP(1), sB);
-    size_t o_fail = add_buf(h, cur, "fail_count", D2D_I32, 1, SHP(B), SHP(1), sB);
-    size_t o_tcur = add_buf(h, cur, "target_cursor", D2D_I32, 1, SHP(B), SHP(1), sB);
+    // per-env scalar state: one 128-byte EnvRec per env; its fields are exposed as strided [B] views
+    size_t o_rec = add_buf(h, cur, "env_records", D2D_U8, 2, SHP(B, (int64_t)sizeof(EnvRec)), SHP((int64_t)sizeof(EnvRec), 1),
+                           (size_t)sB * sizeof(EnvRec));
+    {
+        const size_t rb = (size_t)sB * sizeof(EnvRec);
+        const int64_t s8 = sizeof(EnvRec) / 8, s4 = sizeof(EnvRec) / 4, s1 = sizeof(EnvRec);
+#define RECF(name, field, dt, st) add_view(h, name, dt, 1, SHP(B), SHP(st), o_rec + offsetof(EnvRec, field), rb - offsetof(EnvRec, field))
+        RECF("drone_x", px, D2D_F64, s8); RECF("drone_y", py, D2D_F64, s8); RECF("drone_yaw", yaw, D2D_F64, s8);
+        RECF("drone_vx", vx, D2D_F64, s8); RECF("drone_vy", vy, D2D_F64, s8);
+        RECF("target_x", tgx, D2D_F64, s8); RECF("target_y", tgy, D2D_F64, s8);
+        RECF("steps", steps, D2D_I32, s4); RECF("state_machine", sm, D2D_I32, s4); RECF("fail_count", fail, D2D_I32, s4);
+        RECF("target_cursor", tcur, D2D_I32, s4);
+        RECF("tracker_buffer_count", bufc, D2D_I32, s4); RECF("tracker_buffer_ts", bufts, D2D_I32, s4);
+        RECF("tracked_agent", tracked, D2D_I32, s4);
+        RECF("traj_nseg", nseg, D2D_I32, s4); RECF("traj_cursor", cursor, D2D_I32, s4);
+        RECF("obs_ix", obs_ix, D2D_I32, s4); RECF("obs_iy", obs_iy, D2D_I32, s4);
+        RECF("pending_reset", pending_reset, D2D_U8, s1); RECF("oxford_fresh", ox_fresh, D2D_U8, s1);
+#undef RECF
+        add_view(h, "drone_pose0", D2D_F64, 2, SHP(3, B), SHP(1, s8), o_rec + offsetof(EnvRec, p0x), rb - offsetof(EnvRec, p0x));
+    }
     size_t o_col = add_buf(h, cur, "collision_flag", D2D_U8, 1, SHP(B), SHP(1), sB);
     size_t o_dead = add_buf(h, cur, "dead_lock_flag", D2D_U8, 1, SHP(B), SHP(1), sB);
     size_t o_frz = add_buf(h, cur, "freezing_flag", D2D_U8, 1, SHP(B), SHP(1), sB);
     size_t o_done = add_buf(h, cur, "done", D2D_U8, 1, SHP(B), SHP(1), sB);
-    size_t o_pend = add_buf(h, cur, "pending_reset", D2D_U8, 1, SHP(B), SHP(1), sB);
     size_t o_lm = add_buf(h, cur, "local_map", D2D_U8, 4, SHP(B, 1, D2D_LOCAL, D2D_LOCAL),
                           SHP(D2D_LOCAL_CELLS, D2D_LOCAL_CELLS, D2D_LOCAL, 1), (size_t)sB * D2D_LOCAL_CELLS);
     size_t o_yawo = add_buf(h, cur, "yaw_angle", D2D_F32, 2, SHP(B, 1), SHP(1, 1), sB);
@@ -247,26 +265,18 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     size_t o_tsg = add_buf(h, cur, "tracker_sigma", D2D_F64, 4, SHP(B, N, 4, 4), SHP(NP * 16, 16, 4, 1), (size_t)sB * NP * 16);
     size_t o_trad = add_buf(h, cur, "tracker_radius", D2D_F64, 2, SHP(B, N), SHP(NP, 1), (size_t)sB * NP);
     size_t o_tts = add_buf(h, cur, "tracker_ts", D2D_I32, 2, SHP(B, N), SHP(NP, 1), (size_t)sB * NP);
-    size_t o_bufc = add_buf(h, cur, "tracker_buffer_count", D2D_I32, 1, SHP(B), SHP(1), sB);
-    size_t o_bufts = add_buf(h, cur, "tracker_buffer_ts", D2D_I32, 1, SHP(B), SHP(1), sB);
-    size_t o_trk = add_buf(h, cur, "tracked_agent", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_coef = add_buf(h, cur, "traj_coeff", D2D_F64, 3, SHP(B, D2D_MAX_SEGMENTS, 6), SHP(D2D_MAX_SEGMENTS * 6, 6, 1),
                             cfg->planner == D2D_PLANNER_PRIMITIVE ? (size_t)sB * D2D_MAX_SEGMENTS * 6 : 16);
-    size_t o_nseg = add_buf(h, cur, "traj_nseg", D2D_I32, 1, SHP(B), SHP(1), sB);
-    size_t o_curs = add_buf(h, cur, "traj_cursor", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_need = add_buf(h, cur, "need_plan", D2D_U8, 1, SHP(B), SHP(1), sB);
     size_t o_pok = add_buf(h, cur, "plan_ok", D2D_U8, 1, SHP(B), SHP(1), sB);
     size_t o_rep = add_buf(h, cur, "replan", D2D_U8, 1, SHP(B), SHP(1), sB);
     size_t o_tac = add_buf(h, cur, "tmp_active_count", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_tat = add_buf(h, cur, "tmp_active_ts", D2D_I32, 1, SHP(B), SHP(1), sB);
-    size_t o_oxf = add_buf(h, cur, "oxford_fresh", D2D_U8, 1, SHP(B), SHP(1), sB);
     const bool noisy = cfg->var_cam != 0.0;
     size_t o_rk = add_buf(h, cur, "rng_key", D2D_I32, 2, SHP(B, 624), SHP(624, 1), noisy ? (size_t)sB * 624 : 16);
     size_t o_rk0 = add_buf(h, cur, "rng_key0", D2D_I32, 2, SHP(B, 624), SHP(624, 1), noisy ? (size_t)sB * 624 : 16);
     size_t o_rp = add_buf(h, cur, "rng_pos", D2D_I32, 2, SHP(4, B), SHP(B, 1), (size_t)4 * sB);      // pos, pos0, has, has0
     size_t o_rg = add_buf(h, cur, "rng_gauss", D2D_F64, 2, SHP(2, B), SHP(B, 1), (size_t)2 * sB);     // gauss, gauss0
-    size_t o_obx = add_buf(h, cur, "obs_ix", D2D_I32, 1, SHP(B), SHP(1), sB);
-    size_t o_oby = add_buf(h, cur, "obs_iy", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_oxp = add_buf(h, cur, "oxford_program", D2D_U8, 1, SHP((int64_t)sizeof(OxProgram)), SHP(1), sizeof(OxProgram));
     size_t o_oxs = add_buf(h, cur, "oxford_seen_call", D2D_I32, 1, SHP(1), SHP(1),
                            cfg->oxford ? (size_t)sB * D2D_OX_SEEN_STRIDE / 2 : 4);          // uint16 [B][2560]
@@ -320,17 +330,12 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.avel = (double2 *)(A + o_avel); P.avel0 = (double2 *)(A + o_avel0); P.avel_next = (double2 *)(A + o_aveln);
     P.rvo_obs = (double *)(A + o_robs); P.rvo_nobs = (int *)(A + o_rnobs);
     P.gt_rows = (uint64_t *)(A + o_gt); P.belief = A + o_bel;
-    P.drone_x = (double *)(A + o_dx); P.drone_y = (double *)(A + o_dy); P.drone_yaw = (double *)(A + o_dyaw);
-    P.drone_vx = (double *)(A + o_dvx); P.drone_vy = (double *)(A + o_dvy); P.pose0 = (double *)(A + o_pose0);
-    P.target_x = (double *)(A + o_tx); P.target_y = (double *)(A + o_ty);
-    P.steps = (int *)(A + o_steps); P.state_machine = (int *)(A + o_sm); P.fail_count = (int *)(A + o_fail);
-    P.target_cursor = (int *)(A + o_tcur);
-    P.collision = A + o_col; P.dead_lock = A + o_dead; P.freezing = A + o_frz; P.done = A + o_done; P.pending_reset = A + o_pend;
+    P.rec = (EnvRec *)(A + o_rec);
+    P.collision = A + o_col; P.dead_lock = A + o_dead; P.freezing = A + o_frz; P.done = A + o_done;
     P.local_map = A + o_lm; P.yaw_obs = (float *)(A + o_yawo); P.reward = (float *)(A + o_rew); P.hit = (int8_t *)(A + o_hit);
     P.trk_active = A + o_tact; P.trk_mu = (double *)(A + o_tmu); P.trk_sigma = (double *)(A + o_tsg);
     P.trk_radius = (double *)(A + o_trad); P.trk_ts = (int *)(A + o_tts);
-    P.buf_count = (int *)(A + o_bufc); P.buf_ts = (int *)(A + o_bufts); P.tracked_agent = (int *)(A + o_trk);
-    P.traj_coeff = (double *)(A + o_coef); P.traj_nseg = (int *)(A + o_nseg); P.traj_cursor = (int *)(A + o_curs);
+    P.traj_coeff = (double *)(A + o_coef);
     P.need_plan = A + o_need; P.plan_ok = A + o_pok; P.replan = A + o_rep;
     P.ox_seen = cfg->oxford ? (uint16_t *)(A + o_oxs) : nullptr;
     P.ox_calls = (int *)(A + o_oxc); P.ox_tab = (const double *)(A + o_oxt); P.ox_last = nullptr;
@@ -338,8 +343,7 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
 #ifdef D2D_WARP_PROF
     cudaMalloc((void **)&P.prof, (size_t)B * 96); cudaMemset(P.prof, 0, (size_t)B * 96);
 #endif
-    P.tmp_act_cnt = (int *)(A + o_tac); P.tmp_act_ts = (int *)(A + o_tat); P.ox_fresh = A + o_oxf;
-    P.obs_ix = (int *)(A + o_obx); P.obs_iy = (int *)(A + o_oby);
+    P.tmp_act_cnt = (int *)(A + o_tac); P.tmp_act_ts = (int *)(A + o_tat);
     P.rng_key = noisy ? (uint32_t *)(A + o_rk) : nullptr; P.rng_key0 = noisy ? (uint32_t *)(A + o_rk0) : nullptr;
     P.rng_pos = (int *)(A + o_rp); P.rng_pos0 = P.rng_pos + sB; P.rng_has = P.rng_pos + 2 * sB; P.rng_has0 = P.rng_pos + 3 * sB;
     P.rng_gauss = (double *)(A + o_rg); P.rng_gauss0 = P.rng_gauss + sB;
@@ -464,11 +468,8 @@ extern "C" int d2d_set_world(d2d_handle *h, int32_t first_env, int32_t count, co
             rows[(size_t)c * D2D_GRID + i] = bits;
         }
     CUDA_TRY(h, cudaMemcpy(P.gt_rows + e0 * D2D_GRID, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice));
-    std::vector<double> col((size_t)count);
-    for (int f = 0; f < 3; f++) {
-        for (int c = 0; c < count; c++) col[c] = drone_pose[3 * (size_t)c + f];
-        CUDA_TRY(h, cudaMemcpy(P.pose0 + (size_t)f * P.B + e0, col.data(), (size_t)count * 8, cudaMemcpyHostToDevice));
-    }
+    // reset pose -> the p0x, p0y, p0yaw fields of the env records (24 contiguous bytes per 128-byte record)
+    CUDA_TRY(h, cudaMemcpy2D(&P.rec[e0].p0x, sizeof(EnvRec), drone_pose, 24, 24, (size_t)count, cudaMemcpyHostToDevice));
     // reset exactly those envs
     std::vector<uint8_t> mask((size_t)h->B, 0);
     for (int c = 0; c < count; c++) mask[e0 + c] = 1;
