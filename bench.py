@@ -8,8 +8,10 @@ BASELINE.json configs[1]: empty_map.npy, 4096 envs per GPU, 10 agents, perceptio
 Kalman trackers on as in the reference).  For N > 1 launch with torchrun (one rank per GPU, weak scaling: every
 rank steps its own 4096 envs; the only collective is one NCCL all-reduce of the episode statistics).
 
-Prints ONE JSON line (rank 0).  `value`: whole-job env-steps/s with inputs resident in HBM (per-step CUDA events,
-L2 flushed between steps, flush untimed).  `e2e`: the same metric through d2d_step_host with pinned HOST buffers
+Prints ONE JSON line (rank 0).  `value`: whole-job env-steps/s with inputs resident in HBM: exactly K steps back to back
+(one CUDA graph of the K step launches) between barrier + synchronize, one CUDA-event pair; the L2 is kept cold by
+stepping R independent replicas of the batch round robin so that >= 256 MiB of state is touched between two visits of a
+replica (`per_step_events` repeats the measurement one launch at a time with an explicit L2 flush).  `e2e`: the same metric through d2d_step_host with pinned HOST buffers
 (actions H2D + observation D2H inside the timed region).  `roofline`: algorithmic bytes (SURVEY.md §8d:
 2406 + 104*N per env-step) / measured kernel time vs the measured HBM copy peak.  `cpu_baseline`: the oracle port
 of the reference path (oracle/drone2d_oracle.c) on the host cores, bounded sample.
@@ -48,6 +50,7 @@ CONFIGS = {
 }
 METRIC = "env-steps/sec"
 N_RAYS = 50
+D2D_STATE_BYTES = 2560 + 400 + 128            # read per env and step: belief grid, ground-truth rows, env record
 
 
 def _gen_chunk(args):
@@ -178,8 +181,8 @@ def run_reference(args, cfg):
     import oracle
     oracle.build()
     cores = len(os.sched_getaffinity(0))
-    n_envs = max(cores * 64, 1024)
-    steps_per = 100
+    n_envs = 4096 if cfg["envs"] >= 4096 else cfg["envs"]
+    steps_per = 200
     vals = []
     t_all = time.perf_counter()
     for it in range(args.warmup + args.steps):
@@ -187,7 +190,7 @@ def run_reference(args, cfg):
                              seed0=1 + it, oxford=args.gaze == "Oxford")
         if it >= args.warmup:
             vals.append((n_envs * steps_per, dt))
-        if time.perf_counter() - t_all > 240 and len(vals) >= 1:
+        if time.perf_counter() - t_all > 150 and len(vals) >= 1:
             break
     tot_steps = sum(v[0] for v in vals)
     tot_t = sum(v[1] for v in vals)
@@ -272,51 +275,84 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     p = Params(debug=False, **pk)
     use_ox = args.gaze == "Oxford"
-    env = Drone2DVecEnv(p, B, seeds=seeds, worlds=worlds, device=dev, auto_reset=True, trackers=True, oxford=use_ox,
-                        envs_per_block=args.envs_per_block, strip_width=args.strip_width)
+    def make_env():
+        return Drone2DVecEnv(p, B, seeds=seeds, worlds=worlds, device=dev, auto_reset=True, trackers=True, oxford=use_ox,
+                             envs_per_block=args.envs_per_block, strip_width=args.strip_width)
+    env = make_env()
     n_rays = int(env.cfg.n_rays)
-    ox_out = torch.empty(B, dtype=torch.float64, device=dev)
-
-    def do_step(a):
-        if use_ox:
-            env.step(env.plan_oxford(ox_out))
-        else:
-            env.step(a)
     N = env.num_agents
     K, W = args.steps, args.warmup
+    # Cold-L2 rule: consecutive timed steps must not find their inputs in the 126 MB L2.  The timed region steps R
+    # independent replicas of the batch round robin (same config, same worlds, own state and own action stream), R chosen
+    # so that the state touched between two visits of a replica is >= 256 MiB; big batches (R = 1) already exceed L2.
+    touched = B * (D2D_STATE_BYTES + 56 * N)       # + agents (40 B) and tracker flags / hit mask per agent; = ncu's DRAM read
+    R = 1 if args.no_flush else max(1, min(64, -(-(256 << 20) // touched)))
+    envs = [env] + [make_env() for _ in range(R - 1)]
+    ox_out = torch.empty(B, dtype=torch.float64, device=dev)
+
+    def do_step(a, e=None):
+        e = env if e is None else e
+        if use_ox:
+            e.step(e.plan_oxford(ox_out))
+        else:
+            e.step(a)
     table = torch.as_tensor(np.arange(-80, 80, 80 / 3) / 80, device=dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     actions = table[torch.randint(0, 6, (K + W, B), device=dev, generator=gen)].contiguous()
-    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: per-step CUDA events on the launch stream, L2 flushed (untimed) between steps
-    for t in range(W):
-        do_step(actions[t])
+    # ---- device-resident timing: EXACTLY K steps back to back (one CUDA graph of the K step launches on the launch
+    #      stream), bracketed by barrier + synchronize and one CUDA-event pair
+    for t in range(max(W, R)):                      # eager warm-up: every replica steps at least once
+        do_step(actions[t % (K + W)], envs[t % R])
+    barrier()
+    side = torch.cuda.Stream(device=dev)
+    graph = torch.cuda.CUDAGraph()
+    l0 = sum(e.launch_count() for e in envs)
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for t in range(K):
+                do_step(actions[W + t], envs[t % R])
+    launches = sum(e.launch_count() for e in envs) - l0          # kernel nodes of the graph == launches per K steps
+    barrier()
+    graph.replay()                                  # untimed: graph upload + K more warm-up steps
     barrier()
     sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
                            int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
     sampler.start()
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    l0 = env.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
-    for t in range(K):
-        if flush is not None:
-            flush.fill_(t & 0xFF)
-        ev0[t].record()
-        do_step(actions[W + t])
-        ev1[t].record()
+    ev0.record()
+    graph.replay()
+    ev1.record()
     barrier()
     wall = time.perf_counter() - wall0
-    launches = env.launch_count() - l0
-    step_ms = np.array([a.elapsed_time(b) for a, b in zip(ev0, ev1)])
-    total_ms = float(step_ms.sum())
+    total_ms = float(ev0.elapsed_time(ev1))
+    repeats = []
+    for _ in range(4):                              # run-to-run spread of the same K-step region (reported, not used)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); graph.replay(); e1.record()
+        torch.cuda.synchronize()
+        repeats.append(float(e0.elapsed_time(e1)) / K)
+    # ---- secondary: the same step timed one launch at a time (CUDA events around every step, 256 MiB L2 flush in
+    #      between, untimed): includes ~3-4 us of event / launch gap per step; kept for the per-step distribution
+    Kp = min(K, 100)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    pe0 = [torch.cuda.Event(enable_timing=True) for _ in range(Kp)]
+    pe1 = [torch.cuda.Event(enable_timing=True) for _ in range(Kp)]
+    for t in range(Kp):
+        flush.fill_(t & 0xFF)
+        pe0[t].record()
+        do_step(actions[W + t])
+        pe1[t].record()
+    barrier()
+    step_ms = np.array([a.elapsed_time(b) for a, b in zip(pe0, pe1)])
+    del flush
     # ---- end to end through the C ABI with pinned host buffers
     a_host = actions[W:].cpu().pin_memory()
     lm_host = torch.empty((B, 1, 33, 33), dtype=torch.uint8).pin_memory()
@@ -363,7 +399,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms_max, e2e_ms_max, e2e_copy_ms_max = float(tt[0]), float(tt[1]), float(tt[2])
     # the one collective of the path: all-reduce of the episode statistics
-    stats = torch.as_tensor(env.stats(), device=dev)
+    stats = torch.as_tensor(sum(np.asarray(e.stats(), dtype=np.int64) for e in envs), device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     value = world * B * K / (total_ms_max * 1e-3)
@@ -371,11 +407,11 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        kern_ms = float(np.mean(step_ms))
+        kern_ms = total_ms_max / K            # average launch-to-launch duration inside the timed region
         if cfg["params"]["planner"] == "NoMove":
-            kernel_name = "d2d_step_fused_warp_kernel (1 launch/step; timed per step with CUDA events)"
+            kernel_name = "d2d_step_fused_warp_kernel (1 launch/step; K launches back to back, one event pair)"
         else:
-            kernel_name = "d2d_step_pre_kernel + d2d_plan_kernel + d2d_step_post_kernel" + \
+            kernel_name = "d2d_step_prim_warp_kernel + d2d_plan_kernel + d2d_step_post_list_kernel" + \
                           (" + d2d_oxford_kernel" if use_ox else "") + " (whole step timed)"
         bytes_launch = algorithmic_bytes(N) * B
         achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
@@ -393,8 +429,12 @@ def main():
             "config": {"workload": cfg["name"], "envs_per_gpu": B, "agents_per_env": N, "rays_per_env_step": n_rays,
                        "planner": cfg["params"]["planner"], "gaze": args.gaze, "trackers": True, "auto_reset": True,
                        "unique_worlds_per_gpu": int(unique), "world_gen_s": round(t_world, 2),
-                       "l2": "no flush (state stays L2-resident)" if flush is None else
-                             "flushed between timed steps (256 MiB fill, untimed; per-step CUDA events summed)",
+                       "l2": "no rotation (--no-flush): state stays L2-resident" if args.no_flush else
+                             "inputs larger than L2: %d replica(s) of the batch stepped round robin, %.0f MB of state "
+                             "touched between two visits of a replica (L2 = 126 MB)" % (R, R * touched / 1e6),
+                       "timing": "K steps back to back as one CUDA graph (K step launches), one CUDA-event pair, "
+                                 "barrier + synchronize on both sides",
+                       "replicas": R,
                        "envs_per_block": env.cfg.envs_per_block, "parallelism": "env-sharded x%d" % world},
             "rays_per_sec": value * n_rays,
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": B * 8,
@@ -408,8 +448,13 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_env_step": algorithmic_bytes(N),
-                         "kernel": kernel_name, "kernel_ms": kern_ms,
-                         "step_ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())]},
+                         "kernel": kernel_name, "kernel_ms": kern_ms},
+            "repeat_ms_per_step": repeats,
+            "per_step_events": {"what": "same step, one launch at a time: CUDA events around every step, 256 MiB L2 flush "
+                                        "(untimed) in between; includes the event / launch gap of each step",
+                                "steps": int(Kp), "ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)),
+                                                                     float(step_ms.max())],
+                                "value": world * B / (float(np.mean(step_ms)) * 1e-3)},
             "wall_s_timed_region": wall,
             "episode_stats": {n: int(v) for n, v in zip(
                 ["env_steps", "episodes", "success", "static_collision", "dynamic_collision", "freezing", "dead_lock",
@@ -420,12 +465,17 @@ def main():
             import oracle
             oracle.build()
             cores = len(os.sched_getaffinity(0))
-            n_envs, steps_c = max(cores * 64, 1024), 200
+            # bounded sample of the same workload, sized for ~10 s of CPU work from a short calibration run
+            n_envs = min(B, 4096)
+            v0, dt0 = cpu_port_run(pk, n_envs, 20, cores, oxford=use_ox)
+            steps_c = int(min(5000, max(50, 10.0 * v0 / n_envs)))
             v, dt = cpu_port_run(pk, n_envs, steps_c, cores, oxford=use_ox)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                     "sample": "%d envs x %d steps of the same workload (%.1f s)" % (n_envs, steps_c, dt)}
         print(json.dumps(line), flush=True)
-    env.close()
+    del graph
+    for e in envs:
+        e.close()
     if world > 1:
         dist.destroy_process_group()
 
