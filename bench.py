@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--envs-per-block", type=int, default=0)
     ap.add_argument("--unique-worlds", type=int, default=0, help="cap distinct generated worlds (0 = all unique up to 8192)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--burn-in", type=int, default=1000, help="untimed steps per replica before the timed region")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps (reported in config)")
     ap.add_argument("--strip-width", type=int, default=10, help="ray strip width: rays = ceil(500 / strip_width) (config 5 sweep: 10/5/2)")
     ap.add_argument("--view-range", type=int, default=0, help="drone_view_range in degrees (config 5 sweep: 90/180/360)")
@@ -310,6 +311,11 @@ def main():
     #      stream), bracketed by barrier + synchronize and one CUDA-event pair
     for t in range(max(W, R)):                      # eager warm-up: every replica steps at least once
         do_step(actions[t % (K + W)], envs[t % R])
+    # burn-in (untimed): episodes last up to 800 steps, so the mix of fresh / explored / tracking envs -- and with it the
+    # cost of a step -- only becomes stationary after about a thousand steps (1000 steps with auto-reset)
+    for t in range(args.burn_in):
+        for e in envs:
+            do_step(actions[t % (K + W)], e)
     barrier()
     side = torch.cuda.Stream(device=dev)
     graph = torch.cuda.CUDAGraph()
@@ -434,7 +440,7 @@ def main():
                              "touched between two visits of a replica (L2 = 126 MB)" % (R, R * touched / 1e6),
                        "timing": "K steps back to back as one CUDA graph (K step launches), one CUDA-event pair, "
                                  "barrier + synchronize on both sides",
-                       "replicas": R,
+                       "replicas": R, "burn_in_steps_per_replica": args.burn_in,
                        "envs_per_block": env.cfg.envs_per_block, "parallelism": "env-sharded x%d" % world},
             "rays_per_sec": value * n_rays,
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": B * 8,

@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     RayOut ro;
     ro.bel_s = c.belief; ro.e = e; ro.patch = 0; ro.wi = 0; ro.wj = 0; ro.chg = chg; ro.nchg = &cnt[1];
     d2d_mbar_wait(c.mbar, 0);
+    ro.border_ok = d2d_border_intact(c.gt, lane);
     d2d_phase_rays_warp<false>(P, c, ro, lane);
     __syncwarp();
     if (P.var_cam != 0.0) {

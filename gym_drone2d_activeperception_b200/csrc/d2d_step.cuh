@@ -287,32 +287,36 @@ struct RayOut {
                               // kernel parameters on the rare store path instead of living in registers across the march
     int patch;                // 1: the env's local_map slice is patched in place (window unchanged this step)
     int wi, wj;               // window origin cell (ix-16, iy-16)
+    int border_ok;            // 1: every border cell of this env's ground truth is a wall (no ray can leave the grid)
     uint32_t *chg;            // optional shared-memory list of changed cells (cell | value << 16), null if unused
     int *nchg;                // its counter (entries beyond the capacity are counted but not stored)
 };
 #define D2D_CHG_CAP 64
 
-__device__ __forceinline__ void d2d_mark(const DevP &P, const RayOut &o, int ci, int cj, uint8_t v) {
-    const int cell = ci * D2D_GRID + cj;
-    if (o.bel_s[cell] != v) {   // monotone + idempotent: every writer of a cell writes the same value
-        o.bel_s[cell] = v;
-        P.belief[(size_t)o.e * D2D_BELIEF_STRIDE + cell] = v;
-        if (o.patch) {          // the cell is always inside the 33x33 window (view reach < 16 cells)
-            const int u = ci - o.wi, w = cj - o.wj;
-            if ((unsigned)u < (unsigned)D2D_LOCAL && (unsigned)w < (unsigned)D2D_LOCAL) {
-                const size_t off = (size_t)o.e * D2D_LOCAL_CELLS + u * D2D_LOCAL + w;
-                P.local_map[off] = v;
-                if (P.lm_mirror) {  // one byte over PCIe; counted in the padding word behind the shared belief grid
-                    P.lm_mirror[off] = v;
-                    atomicAdd((int *)(o.bel_s + D2D_MIRCNT_OFF), 1);
-                }
+// a belief cell changes value (0 -> 1 or 0 -> 2): shared copy, HBM grid, and whatever mirrors the observation
+__device__ __forceinline__ void d2d_mark_store(const DevP &P, const RayOut &o, int cell, uint8_t v) {
+    o.bel_s[cell] = v;
+    P.belief[(size_t)o.e * D2D_BELIEF_STRIDE + cell] = v;
+    if (o.patch) {          // the cell is always inside the 33x33 window (view reach < 16 cells)
+        const int ci = cell / D2D_GRID, cj = cell - ci * D2D_GRID;
+        const int u = ci - o.wi, w = cj - o.wj;
+        if ((unsigned)u < (unsigned)D2D_LOCAL && (unsigned)w < (unsigned)D2D_LOCAL) {
+            const size_t off = (size_t)o.e * D2D_LOCAL_CELLS + u * D2D_LOCAL + w;
+            P.local_map[off] = v;
+            if (P.lm_mirror) {  // one byte over PCIe; counted in the padding word behind the shared belief grid
+                P.lm_mirror[off] = v;
+                atomicAdd((int *)(o.bel_s + D2D_MIRCNT_OFF), 1);
             }
         }
-        if (o.chg) {
-            const int slot = atomicAdd(o.nchg, 1);
-            if (slot < D2D_CHG_CAP) o.chg[slot] = (uint32_t)cell | ((uint32_t)v << 16);
-        }
     }
+    if (o.chg) {
+        const int slot = atomicAdd(o.nchg, 1);
+        if (slot < D2D_CHG_CAP) o.chg[slot] = (uint32_t)cell | ((uint32_t)v << 16);
+    }
+}
+__device__ __forceinline__ void d2d_mark(const DevP &P, const RayOut &o, int ci, int cj, uint8_t v) {
+    const int cell = ci * D2D_GRID + cj;
+    if (o.bel_s[cell] != v) d2d_mark_store(P, o, cell, v);   // monotone + idempotent: every writer of a cell writes the same value
 }
 
 // wrapped ray angle, utils.py:594, 626, 612-618
@@ -328,6 +332,7 @@ __device__ __forceinline__ double d2d_ray_angle(const DevP &P, double yaw, int r
 // Hits on the first 32 entries of the culled list are returned as a bit mask over the LIST SLOTS (the caller ORs the
 // masks of its rays and publishes them once: no shared-memory atomics inside the march, where a disc seen by ~20 rays
 // at the same sample index would serialise them); hits on the unfiltered tail go to `hitw` directly.
+template <bool SAFE = false>
 __device__ __forceinline__ uint32_t d2d_cast_ray(const DevP &P, const EnvS &s, double a, double slope, const RayOut &o,
                                                  const uint64_t *gt, const double *sx, const double *sy, const double *sr2,
                                                  const uint16_t *cull, uint32_t *hitw) {
@@ -384,6 +389,97 @@ __device__ __forceinline__ uint32_t d2d_cast_ray(const DevP &P, const EnvS &s, d
     // x in [scale*ci, scale*(ci+1)) is exactly CPython's floor (multiples of the scale are exact doubles):
     //   moving up  : new cell iff x >= scale*(ci+1)            <=> u >= ub
     //   moving down: new cell iff x <  scale*ci  <=> -x > -scale*ci  <=> u >  ub
+    if (SAFE) {
+        // Belief-first march for envs whose border ring is all wall (o.border_ok) and whose drone is inside the grid: a ray
+        // cannot leave the grid without entering a wall cell first (|step| < cell size), so the loop condition of
+        // utils.py:654 can only fail on a border cell, where it is checked exactly.  The belief grid itself tells what the
+        // ground truth of a visited cell is (2 = free, 1 = wall; it is only ever written from the ground truth), so the
+        // bitmap is consulted for unexplored cells only, and only the linear cell index is tracked.
+        const bool xup = xs > 0.0, yup = ys > 0.0;
+        int dcx = xup ? D2D_GRID : -D2D_GRID, dcy = yup ? 1 : -1;
+        // opaque to the optimiser from here on: otherwise it re-derives both increments from the signs of xs / ys in every
+        // iteration instead of keeping two registers
+        asm volatile("" : "+r"(dcx), "+r"(dcy));
+        const double uxs = fabs(xs), uys = fabs(ys);
+        const double ux0 = xup ? x0 : -x0, uy0 = yup ? y0 : -y0;
+        double ux = ux0, uy = uy0;
+        double uxb = xup ? P.scale * (double)(s.ix + 1) : -(P.scale * (double)s.ix);
+        double uyb = yup ? P.scale * (double)(s.iy + 1) : -(P.scale * (double)s.iy);
+        const double scale = P.scale;
+        // the loop variable is the SHARED-MEMORY ADDRESS of the current belief cell (one LDS per sample, no index arithmetic)
+        const uint32_t bel0 = d2d_smem_u32(o.bel_s);
+        uint32_t caddr = bel0 + (uint32_t)(s.ix * D2D_GRID + s.iy);
+        int m = 0;
+        for (;;) {
+            if ((unsigned)(m - mlo) <= mspan) {
+                const double x = dcx > 0 ? ux : -ux, y = dcy > 0 ? uy : -uy;
+                if (!(0.0 < x && 0.0 < y)) break;                      // utils.py:654 comes before the agent test
+                bool any = false;
+                uint32_t mm = cmask;
+                while (mm) {
+                    const int q = __ffs(mm) - 1;
+                    mm &= mm - 1u;
+                    const int k = cull[q];
+                    const double ex = sx[k] - x, ey = sy[k] - y;
+                    if (ex * ex + ey * ey <= sr2[k]) { hm |= 1u << q; any = true; }
+                }
+#pragma unroll 1
+                for (int q = 32; q < nc; q++) {
+                    const int k = cull[q];
+                    const double ex = sx[k] - x, ey = sy[k] - y;
+                    if (ex * ex + ey * ey <= sr2[k]) { atomicOr(&hitw[k >> 5], 1u << (k & 31)); any = true; }
+                }
+                if (any) break;
+            }
+            uint32_t bel;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(bel) : "r"(caddr));
+            if (bel != 2u) {
+                if (bel == 1u) break;                                  // known wall: nothing to mark
+                const int cell = (int)(caddr - bel0);
+                const int ci = cell / D2D_GRID, cj = cell - ci * D2D_GRID;
+                if ((gt[ci] >> cj) & 1ull) {                           // unexplored wall cell (utils.py:666-670)
+                    bool in_map = true;                                // a sample exactly on x == 0 or y == 0 ends the loop first
+                    if (ci == 0 || cj == 0) {
+                        const double x = dcx > 0 ? ux : -ux, y = dcy > 0 ? uy : -uy;
+                        in_map = 0.0 < x && 0.0 < y;
+                    }
+                    if (in_map) d2d_mark_store(P, o, cell, 1);
+                    break;
+                }
+                if (m >= P.m_far) {
+                    const double fx = ux - ux0, fy = uy - uy0;
+                    if ((fx * fx + fy * fy) >= P.depth2) break;
+                }
+                d2d_mark_store(P, o, cell, 2);
+            } else if (m >= P.m_far) {                                 // explored free cell: only the view depth can end the ray
+                const double fx = ux - ux0, fy = uy - uy0;             // = +-(x - px): same square
+                if ((fx * fx + fy * fy) >= P.depth2) break;
+            }
+            m += 1;
+            // advance one sample and track the cell (see the general march below for the derivation): a new cell on an axis
+            // iff u >= ub, except that a sample exactly on the boundary stays in its cell when the ray moves DOWN that axis.
+            // Written out as predicated PTX: 7 instructions per axis.
+            asm("{\n\t"
+                ".reg .pred pe, pn;\n\t"
+                "add.rn.f64 %0, %0, %3;\n\t"
+                "setp.lt.s32 pn, %4, 0;\n\t"
+                "setp.eq.and.f64 pe, %0, %1, pn;\n\t"
+                "setp.lt.or.f64 pe, %0, %1, pe;\n\t"
+                "@!pe add.s32 %2, %2, %4;\n\t"
+                "@!pe add.rn.f64 %1, %1, %5;\n\t"
+                "}" : "+d"(ux), "+d"(uxb), "+r"(caddr) : "d"(uxs), "r"(dcx), "d"(scale));
+            asm("{\n\t"
+                ".reg .pred pe, pn;\n\t"
+                "add.rn.f64 %0, %0, %3;\n\t"
+                "setp.lt.s32 pn, %4, 0;\n\t"
+                "setp.eq.and.f64 pe, %0, %1, pn;\n\t"
+                "setp.lt.or.f64 pe, %0, %1, pe;\n\t"
+                "@!pe add.s32 %2, %2, %4;\n\t"
+                "@!pe add.rn.f64 %1, %1, %5;\n\t"
+                "}" : "+d"(uy), "+d"(uyb), "+r"(caddr) : "d"(uys), "r"(dcy), "d"(scale));
+        }
+        return hm;
+    }
     int ci = s.ix, cj = s.iy;
     const bool xup = xs > 0.0, yup = ys > 0.0;
     const int sxi = xup ? 1 : -1, syi = yup ? 1 : -1;
@@ -468,12 +564,25 @@ __device__ __forceinline__ void d2d_phase_rays(const DevP &P, const BlockCtx &c,
         if (!s.valid) continue;
         RayOut o;
         o.bel_s = c.belief + (size_t)i * D2D_BELIEF_STRIDE;
-        o.e = env0 + i; o.patch = 0; o.wi = 0; o.wj = 0; o.chg = nullptr; o.nchg = nullptr;
+        o.e = env0 + i; o.patch = 0; o.wi = 0; o.wj = 0; o.border_ok = 0; o.chg = nullptr; o.nchg = nullptr;
         const double a = d2d_ray_angle(P, s.yaw, ray);
         const uint32_t hm = d2d_cast_ray(P, s, a, d2d_tan(a), o, c.gt + (size_t)i * D2D_GRID, c.sx + i * NP, c.sy + i * NP,
                                          c.sr2 + i * NP, c.cull + i * NP, c.hitw + i * P.HW);
         d2d_publish_hits(hm, c.cull + i * NP, c.hitw + i * P.HW);
     }
+}
+
+// all 196 border cells of the env's ground truth are walls (true for every world unless an agent disc erased border
+// cells at world generation, utils.py:508-525); evaluated by one warp on the shared-memory row bitmap
+__device__ __forceinline__ int d2d_border_intact(const uint64_t *gt, int lane) {
+    const uint64_t FULL = (1ull << D2D_GRID) - 1ull, EDGE = 1ull | (1ull << (D2D_GRID - 1));
+    bool ok = true;
+#pragma unroll
+    for (int r = lane; r < D2D_GRID; r += 32) {
+        const uint64_t need = (r == 0 || r == D2D_GRID - 1) ? FULL : EDGE;
+        ok = ok && ((gt[r] & need) == need);
+    }
+    return __all_sync(0xffffffffu, ok) ? 1 : 0;
 }
 
 // one env per warp: lane handles rays `lane` and `lane + 32` (+64, ...); the two tangent evaluations of a pair are
@@ -496,10 +605,14 @@ __device__ __forceinline__ void d2d_phase_rays_warp(const DevP &P, const BlockCt
             if (r1 < R) hm |= d2d_cast_ray(P, s, a1, t1, o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
         }
     } else {
+        // warp-uniform: border ring intact and drone inside the grid -> the belief-first march
+        const bool safe = o.border_ok && (unsigned)s.ix < (unsigned)D2D_GRID && (unsigned)s.iy < (unsigned)D2D_GRID;
 #pragma unroll 1
         for (int ray = lane; ray < R; ray += 32) {
             const double a = d2d_ray_angle(P, s.yaw, ray);
-            hm |= d2d_cast_ray(P, s, a, d2d_tan(a), o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
+            const double tn = d2d_tan(a);
+            if (safe) hm |= d2d_cast_ray<true>(P, s, a, tn, o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
+            else hm |= d2d_cast_ray<false>(P, s, a, tn, o, c.gt, c.sx, c.sy, c.sr2, c.cull, c.hitw);
         }
     }
     // OR over the warp, then lane q publishes slot q (all rays of the env are cast by this warp)
@@ -1052,6 +1165,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     ro.wi = s.ix - 16; ro.wj = s.iy - 16; ro.chg = nullptr; ro.nchg = nullptr;
     D2D_PROF(6);
     d2d_mbar_wait(c.mbar, 0);
+    ro.border_ok = d2d_border_intact(c.gt, lane);
     D2D_PROF(1);
     d2d_phase_rays_warp<ILP2>(P, c, ro, lane);
     __syncwarp();

@@ -679,8 +679,22 @@ extern "C" int d2d_step_host(d2d_handle *h, const double *actions_host, uint8_t 
     if (!h || !actions_host) return D2D_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(h, cudaMemcpyAsync(h->stage_actions, actions_host, (size_t)h->B * 8, cudaMemcpyHostToDevice, st));
-    int rc = d2d_step(h, h->stage_actions, stream);
+    // Pinned (page-locked, device-mapped) actions are read by the step kernels straight from host memory: every warp
+    // requests its env's action at kernel entry and uses it at the end of the step, so the PCIe latency is hidden and no
+    // copy has to be enqueued.  Pageable memory goes through the device staging buffer.
+    const double *act = nullptr;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, actions_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            act = (const double *)at.devicePointer;
+        else
+            cudaGetLastError();
+    }
+    if (!act) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->stage_actions, actions_host, (size_t)h->B * 8, cudaMemcpyHostToDevice, st));
+        act = h->stage_actions;
+    }
+    int rc = d2d_step(h, act, stream);
     if (rc != D2D_OK) return rc;
     // a buffer bound as the zero-copy mirror was already written by the step kernels (only the bytes that changed);
     // anything else -- or a mirror that missed an eager reset -- is copied back in full

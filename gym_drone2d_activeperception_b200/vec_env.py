@@ -154,6 +154,7 @@ class Drone2DVecEnv(object):
             worlds = generate_worlds(params, self.seeds, self._smap)
         self.set_worlds(worlds)
         self._views = {}
+        self._mirror, self._mirror_ptrs = None, (None, None, None)
         self.local_map_size = 4 * (params.drone_view_depth // params.map_scale) + 1
         self.reward = self.buffer("reward")
         self._zero_actions = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
@@ -242,13 +243,22 @@ class Drone2DVecEnv(object):
         return self._obs(), self.reward, self.buffer("done"), self.info
 
     def step_host(self, actions_host, local_map_host=None, yaw_host=None, done_host=None):
-        """Same step through HOST buffers (pinned torch tensors or numpy arrays): H2D actions, step, D2H observation."""
+        """Same step through HOST buffers (pinned torch tensors or numpy arrays): actions to the device (pinned memory is
+        read by the kernels in place), step, observation back on the host.  Output buffers that are the bound mirror
+        (`bind_host_mirror`) cost nothing here: their pointers are cached and the library copies nothing."""
         def ptr(x):
             if x is None:
                 return None
-            return C.c_void_p(x.data_ptr() if torch.is_tensor(x) else x.ctypes.data)
-        self._check(self._lib.d2d_step_host(self._h, ptr(actions_host), ptr(local_map_host), ptr(yaw_host),
-                                            ptr(done_host), self._stream()), "d2d_step_host")
+            return x.data_ptr() if torch.is_tensor(x) else x.ctypes.data
+        m = self._mirror
+        if m is not None and local_map_host is m[0] and yaw_host is m[1] and done_host is m[2]:
+            lp, yp, dp = self._mirror_ptrs
+        else:
+            lp, yp, dp = ptr(local_map_host), ptr(yaw_host), ptr(done_host)
+        rc = self._lib.d2d_step_host(self._h, ptr(actions_host), lp, yp, dp,
+                                     torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            self._check(rc, "d2d_step_host")
 
     def bind_host_mirror(self, local_map_host=None, yaw_host=None, done_host=None):
         """Zero-copy observation mirror (d2d_bind_host_mirror): the step kernels repeat every observation store into these
@@ -262,6 +272,7 @@ class Drone2DVecEnv(object):
         self._check(self._lib.d2d_bind_host_mirror(self._h, ptr(local_map_host), ptr(yaw_host), ptr(done_host)),
                     "d2d_bind_host_mirror")
         self._mirror = (local_map_host, yaw_host, done_host)      # keep the buffers alive while bound
+        self._mirror_ptrs = tuple(None if x is None else x.data_ptr() for x in self._mirror)
 
     @property
     def info(self):

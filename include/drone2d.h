@@ -144,8 +144,9 @@ int d2d_reset(d2d_handle *h, const uint8_t *mask_dev, void *stream);
  * Results land in the buffers "local_map", "yaw_angle", "done", "collision_flag", ... (d2d_get_buffer). */
 int d2d_step(d2d_handle *h, const double *actions_dev, void *stream);
 
-/* Same step with HOST buffers (the call an FFI user makes): copies actions host->device, steps, copies the
- * observation back and synchronises.  Any output pointer may be NULL.
+/* Same step with HOST buffers (the call an FFI user makes): gets the actions to the device (pinned memory is read by
+ * the kernels directly over PCIe, pageable memory is copied first), steps, copies the observation back and
+ * synchronises.  Any output pointer may be NULL.
  *   local_map_host [num_envs][1][L][L] u8, yaw_host [num_envs] f32, done_host [num_envs] u8 */
 int d2d_step_host(d2d_handle *h, const double *actions_host, uint8_t *local_map_host, float *yaw_host,
                   uint8_t *done_host, void *stream);
