@@ -214,13 +214,7 @@ __device__ D2D_COLD void d2d_finish_env_warp(const DevP &P, const BlockCtx &c, E
     } else {
         d2d_obs_env_warp(P, c.belief, s.ix, s.iy, e, lane);
     }
-    if (s.done_now) {
-        int cnt = 0;
-#pragma unroll 1
-        for (int o = lane; o < D2D_CELLS; o += 32) cnt += (c.belief[o] != 0);
-        for (int off = 16; off > 0; off >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, off);
-        if (lane == 0 && cnt) atomicAdd(&P.stats[D2D_STAT_GRID_DISCOVERED], (unsigned long long)cnt);
-    }
+    if (s.done_now) d2d_count_explored_warp(P, c.belief, lane);
 }
 
 template <int WPB>
@@ -265,6 +259,7 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
 #pragma unroll 1
     for (int w = lane; w < P.HW; w += 32) c.hitw[w] = 0u;
     __syncwarp();
+    d2d_reset_prefetch(P, s, e, lane, pf_pos, pf_pref);
     d2d_reset_arrays(P, c, e, 1, lane, 32, c.mbar);
     d2d_phase_agents<false, true>(P, c, e, 1, lane, 32, pf_pos, pf_pref, pf_r);
     if (pf_act && !s.reset) d2d_prefetch_tracker(P, (size_t)e * P.NP + lane);

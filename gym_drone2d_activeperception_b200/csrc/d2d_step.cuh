@@ -214,6 +214,17 @@ __device__ D2D_COLD void d2d_reset_arrays(const DevP &P, const BlockCtx &c, int 
     }
 }
 
+// an env that is being reset restarts from its snapshot: request it (and the tracker radii the tracker phase will need)
+// before the zeroing pass of d2d_reset_arrays so that the DRAM round trip overlaps it (one warp per env)
+__device__ __forceinline__ void d2d_reset_prefetch(const DevP &P, const EnvS &s, int e, int lane, double2 &pf_pos,
+                                                   double2 &pf_pref) {
+    if (s.reset && lane < P.N) {
+        const size_t g = (size_t)e * P.NP + lane;
+        pf_pos = P.apos0[g]; pf_pref = P.apref0[g];
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.trk_radius0 + g));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ P1: Agent.step
 // PF: the caller (one warp, E == 1) already holds agent `tid` of the live arrays in registers (pf_*), loaded before the env
 // scalars were known so that the two DRAM round trips overlap; an env being reset re-reads its snapshot instead.
@@ -231,7 +242,7 @@ __device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &
         const size_t g = (size_t)(env0 + i) * NP + k;
         double2 pos, pref;
         double r;
-        if (PF && w == tid && !s.reset) { pos = pf_pos; pref = pf_pref; r = pf_r; }
+        if (PF && w == tid) { pos = pf_pos; pref = pf_pref; r = pf_r; }   // live state, or the snapshot if the env is being reset
         else {
             if (s.reset) { pos = P.apos0[g]; pref = P.apref0[g]; }
             else { pos = P.apos[g]; pref = P.apref[g]; }
@@ -1101,6 +1112,16 @@ __device__ D2D_COLD void d2d_obs_env_warp(const DevP &P, const uint8_t *bel, int
     if (out_m && lane == 0) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)D2D_LOCAL_CELLS);
 }
 
+// explored-cell count of an env that finished this step (experiment.py:90 "Grid discovered"), one warp, four cells per
+// word (the 60 padding bytes behind the 2500 cells are zero except the mirror counter word, which is skipped)
+__device__ __forceinline__ void d2d_count_explored_warp(const DevP &P, const uint8_t *bel, int lane) {
+    int cnt = 0;
+#pragma unroll 1
+    for (int w = lane; w < D2D_CELLS / 4; w += 32) cnt += __popc(__vcmpne4(((const uint32_t *)bel)[w], 0u) & 0x01010101u);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0 && cnt) atomicAdd(&P.stats[D2D_STAT_GRID_DISCOVERED], (unsigned long long)cnt);
+}
+
 #ifdef D2D_WARP_PROF
 __device__ __forceinline__ void d2d_prof_stamp(const DevP &P, int e, int k, int lane) {
     if (lane == 0) {
@@ -1151,6 +1172,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     for (int w = lane; w < P.HW; w += 32) c.hitw[w] = 0u;
     __syncwarp();
     D2D_PROF(4);
+    d2d_reset_prefetch(P, s, e, lane, pf_pos, pf_pref);
     d2d_reset_arrays(P, c, e, 1, lane, 32, c.mbar);
     d2d_phase_agents<true, true>(P, c, e, 1, lane, 32, pf_pos, pf_pref, pf_r);
     if (pf_act && !s.reset) d2d_prefetch_tracker(P, (size_t)e * P.NP + lane);
@@ -1200,12 +1222,6 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     __syncwarp();
     d2d_store_env_warp(P, s, e, lane);
     if (rewrite) d2d_obs_env_warp(P, c.belief, s.ix, s.iy, e, lane);
-    if (s.done_now) {
-        int cnt = 0;
-#pragma unroll 1
-        for (int o = lane; o < D2D_CELLS; o += 32) cnt += (c.belief[o] != 0);
-        for (int off = 16; off > 0; off >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, off);
-        if (lane == 0 && cnt) atomicAdd(&P.stats[D2D_STAT_GRID_DISCOVERED], (unsigned long long)cnt);
-    }
+    if (s.done_now) d2d_count_explored_warp(P, c.belief, lane);
     D2D_PROF(3);
 }

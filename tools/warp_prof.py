@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--envs", type=int, default=0)
     ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--burn-in", type=int, default=1000, help="untimed steps before profiling (stationary episode mix)")
     args = ap.parse_args()
     from gym_drone2d_activeperception_b200 import build as b, _native
     lib = os.path.join(os.path.dirname(b.LIB), "libdrone2d_prof.so")
@@ -39,6 +40,8 @@ def main():
     g.manual_seed(1)
     acts = table[torch.randint(0, 6, (args.steps, B), device="cuda:0", generator=g)].contiguous()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+    for t in range(args.burn_in):
+        env.step(acts[t % args.steps])
     prof = env.buffer("warp_prof")
     rows = []
     fine_rows = []
