@@ -365,15 +365,24 @@ def main():
     yaw_host = torch.empty((B,), dtype=torch.float32).pin_memory()
     done_host = torch.empty((B,), dtype=torch.uint8).pin_memory()
     Ke = min(K, 100)
+    a_rows = [a_host[t] for t in range(Ke)]          # views of the pinned action buffer, one per step
+    stage = env.buffer("actions_staging")
+
+    def e2e_step(t):
+        if use_ox:      # the policy runs on the device: its actions never leave the GPU, the observation still does
+            env.plan_oxford(stage)
+            env.step_host(None, lm_host, yaw_host, done_host)
+        else:
+            env.step_host(a_rows[t], lm_host, yaw_host, done_host)
 
     def e2e_loop():
         for t in range(3):
-            env.step_host(a_host[t], lm_host, yaw_host, done_host)
+            e2e_step(t)
         barrier()
         st0 = env.stats()
         t0 = time.perf_counter()
         for t in range(Ke):
-            env.step_host(a_host[t], lm_host, yaw_host, done_host)
+            e2e_step(t)
         barrier()
         return time.perf_counter() - t0, env.stats() - st0
 
@@ -443,7 +452,7 @@ def main():
                        "replicas": R, "burn_in_steps_per_replica": args.burn_in,
                        "envs_per_block": env.cfg.envs_per_block, "parallelism": "env-sharded x%d" % world},
             "rays_per_sec": value * n_rays,
-            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": B * 8,
+            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": 0 if use_ox else B * 8,
                     "d2h_bytes_per_step": B * (1089 + 4 + 1) if mirror_bytes is None else int(round(B * 5 + mirror_bytes)),
                     "steps": Ke,
                     "transport": "cudaMemcpyAsync of the whole observation every step" if mirror_bytes is None else

@@ -676,14 +676,16 @@ extern "C" int d2d_step(d2d_handle *h, const double *actions_dev, void *stream) 
 
 extern "C" int d2d_step_host(d2d_handle *h, const double *actions_host, uint8_t *local_map_host, float *yaw_host,
                              uint8_t *done_host, void *stream) {
-    if (!h || !actions_host) return D2D_ERR_INVALID;
+    if (!h) return D2D_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
+    // actions_host == NULL: the actions are already on the device, in the buffer "actions_staging" (written there by
+    // d2d_plan_oxford / d2d_plan_gaze when the policy runs on the GPU).
     // Pinned (page-locked, device-mapped) actions are read by the step kernels straight from host memory: every warp
     // requests its env's action at kernel entry and uses it at the end of the step, so the PCIe latency is hidden and no
     // copy has to be enqueued.  Pageable memory goes through the device staging buffer.
-    const double *act = nullptr;
-    {
+    const double *act = actions_host ? nullptr : h->stage_actions;
+    if (actions_host) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, actions_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
             act = (const double *)at.devicePointer;

@@ -146,7 +146,8 @@ int d2d_step(d2d_handle *h, const double *actions_dev, void *stream);
 
 /* Same step with HOST buffers (the call an FFI user makes): gets the actions to the device (pinned memory is read by
  * the kernels directly over PCIe, pageable memory is copied first), steps, copies the observation back and
- * synchronises.  Any output pointer may be NULL.
+ * synchronises.  Any output pointer may be NULL.  actions_host == NULL: the actions are taken from the device buffer
+ * "actions_staging" (d2d_get_buffer), e.g. written there by d2d_plan_oxford / d2d_plan_gaze.
  *   local_map_host [num_envs][1][L][L] u8, yaw_host [num_envs] f32, done_host [num_envs] u8 */
 int d2d_step_host(d2d_handle *h, const double *actions_host, uint8_t *local_map_host, float *yaw_host,
                   uint8_t *done_host, void *stream);

@@ -96,3 +96,33 @@ def test_mirror_rejects_pageable_memory():
     rc = env._lib.d2d_bind_host_mirror(env._h, C.c_void_p(pageable.ctypes.data), None, None)
     assert rc == -1 and b"pinned" in env._lib.d2d_last_error(env._h)
     env.close()
+
+
+@pytest.mark.parametrize("planner", ["NoMove", "Primitive"])
+def test_step_host_action_sources_agree(planner):
+    """d2d_step_host takes its actions from pinned host memory (read in place by the kernels), from pageable host memory
+    (copied to the staging buffer first) or, with actions_host == NULL, from the device buffer "actions_staging": three
+    envs fed the same actions through the three routes must stay identical."""
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200 import generate_worlds
+    B, steps = 19, 120
+    p = Params(debug=False, planner=planner, map_id=5, agent_number=10, agent_radius=15, agent_max_speed=40)
+    worlds = generate_worlds(p, 5 + np.arange(B))
+    envs = [_env(p, B, worlds, auto_reset=True, oxford=False) for _ in range(3)]
+    table = util.action_table()
+    rng = np.random.RandomState(2)
+    outs = [_pinned(B) for _ in range(3)]
+    for t in range(steps):
+        a = np.ascontiguousarray(table[rng.randint(0, 6, B)])
+        envs[0].step_host(torch.from_numpy(a).pin_memory(), *outs[0])          # pinned: zero-copy read
+        envs[1].step_host(a, *outs[1])                                         # pageable numpy: staged copy
+        envs[2].buffer("actions_staging").copy_(torch.from_numpy(a))           # already on the device
+        envs[2].step_host(None, *outs[2])
+        for k in (1, 2):
+            for x, y in zip(outs[0], outs[k]):
+                assert torch.equal(x, y), (planner, t, k)
+    for name in ("belief", "drone_yaw", "agent_pos", "steps", "tracker_mu"):
+        for k in (1, 2):
+            assert torch.equal(envs[0].buffer(name), envs[k].buffer(name)), (name, k)
+    for e in envs:
+        e.close()
