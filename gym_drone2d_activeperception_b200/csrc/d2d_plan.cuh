@@ -189,7 +189,6 @@ __device__ D2D_COLD void d2d_finish_env_warp(const DevP &P, const BlockCtx &c, E
     if (lane == 0) {
         s.coll_agent = any_hit ? 1 : 0;
         d2d_leader_flags(P, s, c.gt, e, shit);
-        atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], 1ull);
     }
     __syncwarp();
     // the observation tensor holds the window of cell (obs_ix, obs_iy): patch it if that is still the drone's cell
@@ -233,7 +232,10 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     // plan-list counters are double buffered by a step parity that lives in DEVICE memory (plan_list[B+3], advanced by
     // the post kernel), so a captured CUDA graph replays correctly; [B+4] publishes this step's parity to the later kernels
     const int par = P.plan_list[P.B + 3] & 1;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { P.plan_list[P.B + 4] = par; P.plan_list[P.B + 1 + (par ^ 1)] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.plan_list[P.B + 4] = par; P.plan_list[P.B + 1 + (par ^ 1)] = 0;
+        atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], (unsigned long long)P.B);    // every env steps once per d2d_step
+    }
 
     // all HBM requests up front (see d2d_step_fused_warp_kernel): agents speculatively from the live arrays, bulk copies,
     // then the scalars

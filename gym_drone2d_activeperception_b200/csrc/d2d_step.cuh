@@ -1202,12 +1202,12 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     __syncwarp();
     D2D_PROF(8);
     if (lane == 0) {
-        // NoMove.plan traj_planner.py:70-73 / NoMove.replan_check :75-76
+        // NoMove.plan traj_planner.py:70-73 / NoMove.replan_check :75-76; the verdict arrays (replan = 0, plan_ok = 1,
+        // need_plan = 0) never change under NoMove: d2d_reset_kernel wrote them once
         s.tgx = -1.0; s.tgy = -1.0;
-        P.replan[e] = 0; P.plan_ok[e] = 1; P.need_plan[e] = 0;
         d2d_leader_finish(P, s, c.gt, e, action, true);
         d2d_leader_flags(P, s, c.gt, e, shit);
-        atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], 1ull);
+        if (e == 0) atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], (unsigned long long)P.B);   // every env steps once per launch
         if (patch && P.lm_mirror) {
             const int nb = *(const int *)(c.belief + D2D_MIRCNT_OFF);
             if (nb) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)nb);
