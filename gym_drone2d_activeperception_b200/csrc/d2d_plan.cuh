@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     }
     __syncwarp();
     const bool need = (s.nseg * P.n_way - s.cursor) == 0;
+    __syncwarp();                 // every lane has read the trajectory length before lane 0 pops a waypoint (step_pos)
     if (!need) {
         if (lane == 0) P.need_plan[e] = 0;
         d2d_finish_env_warp(P, c, s, e, lane, action, true, true, cnt[1], chg, true);

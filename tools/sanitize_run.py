@@ -1,0 +1,39 @@
+"""Small workload for compute-sanitizer (GPU box):  compute-sanitizer --tool memcheck python tools/sanitize_run.py
+Steps a NoMove batch (fused warp kernel, both march variants: seed 8 has a broken border ring), a Primitive + Oxford batch and
+an RVO batch for a few dozen steps with auto-reset, host mirror bound, and prints the episode statistics."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    from gym_drone2d_activeperception_b200 import Params
+    from gym_drone2d_activeperception_b200.vec_env import Drone2DVecEnv
+    table = torch.as_tensor(np.arange(-80, 80, 80 / 3) / 80)
+    g = torch.Generator().manual_seed(0)
+    for name, kw, B, steps, ox in [("NoMove", dict(planner="NoMove", map_id=1), 40, 40, False),
+                                   ("Primitive+Oxford", dict(planner="Primitive", gaze_method="Oxford", map_id=1), 24, 40, True),
+                                   ("RVO", dict(planner="NoMove", motion_profile="RVO", map_id=3), 8, 10, False)]:
+        p = Params(debug=False, agent_number=10, agent_radius=15, agent_max_speed=20, **kw)
+        env = Drone2DVecEnv(p, B, seeds=1 + np.arange(B), device="cuda:0", auto_reset=True, oxford=ox)
+        lm = torch.empty((B, 1, 33, 33), dtype=torch.uint8).pin_memory()
+        yaw = torch.empty((B,), dtype=torch.float32).pin_memory()
+        dn = torch.empty((B,), dtype=torch.uint8).pin_memory()
+        env.bind_host_mirror(lm, yaw, dn)
+        for t in range(steps):
+            if ox:
+                env.plan_oxford(env.buffer("actions_staging"))
+                env.step_host(None, lm, yaw, dn)
+            else:
+                env.step_host(table[torch.randint(0, 6, (B,), generator=g)].contiguous().pin_memory(), lm, yaw, dn)
+        print(name, env.stats()[:8])
+        env.close()
+
+
+if __name__ == "__main__":
+    main()
