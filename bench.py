@@ -432,7 +432,7 @@ def main():
         achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic_config%d.json" % args.config)
-        if os.path.isfile(tpath):
+        if os.path.isfile(tpath) and cfg["params"]["planner"] == "NoMove":     # captured for the fused NoMove kernel only
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
