@@ -204,10 +204,30 @@ def run_reference(args, cfg):
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: everything else that libraries print there (NCCL's version banner
+    under torchrun, for one) is sent to stderr by re-pointing fd 1; the JSON line goes to the saved descriptor."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -483,11 +503,11 @@ def main():
             # bounded sample of the same workload, sized for ~10 s of CPU work from a short calibration run
             n_envs = min(B, 4096)
             v0, dt0 = cpu_port_run(pk, n_envs, 20, cores, oxford=use_ox)
-            steps_c = int(min(5000, max(50, 10.0 * v0 / n_envs)))
+            steps_c = int(min(20000, max(50, 25.0 * v0 / n_envs)))   # the 20-step calibration under-reads the rate ~2x
             v, dt = cpu_port_run(pk, n_envs, steps_c, cores, oxford=use_ox)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                     "sample": "%d envs x %d steps of the same workload (%.1f s)" % (n_envs, steps_c, dt)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     del graph
     for e in envs:
         e.close()
