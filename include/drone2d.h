@@ -11,8 +11,9 @@
  * (a `cudaStream_t` passed as void*, NULL = legacy default stream); only the *_host variants and d2d_stats
  * synchronise that stream.
  *
- * Memory: the library owns one device arena per handle (SoA state for `num_envs` environments, laid out
- * env-major so one thread block streams the state of its environments with coalesced / bulk copies).
+ * Memory: the library owns one device arena per handle (state for `num_envs` environments, laid out env-major:
+ * per-agent arrays, one belief grid and ground-truth bitmap per env, and one 128-byte record per env with the
+ * drone / bookkeeping scalars, so the warp that owns an env streams its state with coalesced / bulk copies).
  * d2d_get_buffer() exposes every state and observation array as a raw device pointer + shape/strides so the
  * host language can wrap them zero-copy (the Python host wraps them as torch tensors).
  */
