@@ -228,3 +228,14 @@ def test_device_norm_equals_numpy(mathlib):
     mathlib.mc_norm2(np.ascontiguousarray(v[:, 0]), np.ascontiguousarray(v[:, 1]), out, 50000)
     ref = np.array([np.linalg.norm(r) for r in v])
     assert (out == ref).mean() > 0.999      # exact on the OpenBLAS build the fixtures were generated with
+
+
+def test_obstacle_density_matches_reference_golden():
+    """metrics.obstacle_density (density_calculator.py:13-30) vs values computed on the reference's own worlds."""
+    import json
+    from gym_drone2d_activeperception_b200 import Params
+    from gym_drone2d_activeperception_b200.metrics import obstacle_density
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_survivability.npz"))
+    for ci, c in enumerate(json.loads(str(g["cases"]))):
+        p = Params(debug=False, planner="NoMove", gaze_method="NoControl", **c)
+        assert np.array_equal(obstacle_density(p, g["seeds"]), g["density_%d" % ci]), c
