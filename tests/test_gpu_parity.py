@@ -306,3 +306,36 @@ def test_trackers_disabled_and_primitive_step_host():
             assert np.array_equal(lm[i, 0].numpy(), e.local_map) and int(dn[i]) == e.c.done, (t, i)
             assert float(yaw[i]) == float(np.float32(e.c.yaw_obs))
     env.close()
+
+
+def test_cuda_matches_oracle_awkward_poses():
+    """Drone poses the belief-first / general ray marches must treat exactly like the reference loop `while 0 < x < W and
+    0 < y < H` (utils.py:654): inside border wall cells, exactly on x == 0 / y == 0, exactly on cell boundaries and on
+    the far map edge, and outside the map; yaws on the axes and diagonals (rays running along cell boundaries)."""
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200.world import generate_worlds
+    xy = [(5.0, 5.0), (0.0, 250.0), (250.0, 0.0), (0.0, 0.0), (10.0, 10.0), (20.0, 490.0), (495.0, 495.0), (499.999, 250.0),
+          (500.0, 250.0), (-5.0, 100.0), (100.0, 505.0), (250.0, 250.0), (30.0, 30.0), (470.0, 20.0), (9.999999999, 40.0),
+          (490.0, 250.0), (40.0, 0.0), (250.0, 489.99999)]
+    yaws = [0.0, 90.0, 180.0, 270.0, 45.0, 135.0, 225.0, 315.0]
+    poses = np.array([(x, y, yw) for (x, y) in xy for yw in yaws], dtype=np.float64)
+    B, steps = len(poses), 24
+    p = Params(debug=False, planner="NoMove", map_id=300, agent_number=12, agent_radius=15, agent_max_speed=40)
+    worlds = generate_worlds(p, 300 + np.arange(B) % 7)
+    env = _env(p, B, worlds, auto_reset=False)
+    n = env.num_agents
+    env.set_drone_pose(poses)
+    oracles = [util.oracle_env_from_world(p, worlds, i, drone=poses[i]) for i in range(B)]
+    table = util.action_table()
+    rng = np.random.RandomState(5)
+    for t in range(steps):
+        acts = table[rng.randint(0, 6, B)] if t % 3 else np.zeros(B)      # zero action: the yaw stays on the axis / diagonal
+        env.step(torch.as_tensor(acts, device="cuda:0"))
+        for i, e in enumerate(oracles):
+            e.step(float(acts[i]))
+        h = _host(env)
+        for i, e in enumerate(oracles):
+            _cmp_env_to_oracle(h, i, e, n, t, "pose %s" % (poses[i],))
+    for e in oracles:
+        e.close()
+    env.close()
