@@ -15,7 +15,8 @@ PARAM_KEYS = ("dt", "map_scale", "map_size", "agent_radius", "drone_max_accelera
 
 
 def golden_files(prefix=""):
-    return sorted(glob.glob(os.path.join(GOLDEN, prefix + "*.npz")))
+    """Episode / step fixtures (tests/golden/metrics_*.npz hold difficulty-metric values and have their own tests)."""
+    return sorted(f for f in glob.glob(os.path.join(GOLDEN, prefix + "*.npz")) if not os.path.basename(f).startswith("metrics_"))
 
 
 def load_golden(path):
