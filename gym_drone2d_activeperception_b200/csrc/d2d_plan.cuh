@@ -806,6 +806,11 @@ struct OxProgram {
     int n_leaves, n_ops;
     int leaf_off[D2D_OX_MAX_LEAVES], leaf_len[D2D_OX_MAX_LEAVES];
     int ops[2 * D2D_OX_MAX_LEAVES];     // post-order: >= 0 push leaf, -1 add top two
+    // the same program as a tree: node ids 0 .. n_leaves-1 are the leaves, internal nodes follow in post-order; internal
+    // nodes sorted by level (1 = both children are leaves ...), level L occupies [lev_off[L-1], lev_off[L]) of node_*
+    int n_levels, root;
+    int lev_off[16];
+    int node_id[D2D_OX_MAX_LEAVES], node_l[D2D_OX_MAX_LEAVES], node_r[D2D_OX_MAX_LEAVES];
 };
 
 __device__ __forceinline__ double d2d_np_leaf_sum(const double *a, int n) {
@@ -892,14 +897,14 @@ __global__ void d2d_oxford_export_kernel(const DevP P, double *__restrict__ out)
 //     to whole leaves of NumPy's pairwise recursion) and each candidate gets a visibility BITMASK over that range.
 //  D. leaf sums in NumPy's order -- 8 strided accumulators (one lane each; a lane only visits the set bits of its
 //     residue class), combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail; leaves outside the range are exactly
-//     +0.0 (x + 0.0 == x) -- then the recursion's post-order combine and the strict-< argmax.
+//     +0.0 (x + 0.0 == x).
+//  E. the recursion's combine as a level-parallel tree (same operand pairs), then the strict-< argmax.
 __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P, const OxProgram *__restrict__ prog,
                                                                     double *__restrict__ actions_out) {
     __shared__ double reward[D2D_OX_SPAN];
     __shared__ uint32_t vmask[D2D_MAX_YAW][D2D_OX_WORDS];
     __shared__ int swep_w[D2D_OX_SPAN];                 // largest waypoint index per cell of the range (-1: none)
     __shared__ double leaf[D2D_MAX_YAW][D2D_OX_MAX_LEAVES];
-    __shared__ double score[D2D_MAX_YAW];
     __shared__ double cs_s[D2D_MAX_YAW + 1], sn_s[D2D_MAX_YAW + 1];
     __shared__ double wpt[2];
     __shared__ int geo[12];                             // r0 r1 q0 q1 lo hi l0 l1 i0 i1 j0 j1
@@ -1058,22 +1063,37 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         }
     }
     __syncthreads();
-    if (tid < ny) {
-        double st[16];
-        int sp = 0;
-        for (int o = 0; o < prog->n_ops; o++) {
-            const int op = prog->ops[o];
-            if (op >= 0) st[sp++] = (op >= l0 && op <= l1) ? leaf[tid][op] : 0.0;
-            else { sp--; st[sp - 1] = st[sp - 1] + st[sp]; }
+    // ---- E: NumPy's pairwise combine, evaluated as a tree: every internal node adds its two children -- the operand pairs
+    //      of the recursion's post-order program, so the same roundings -- and the nodes of one level are independent
+    //      (the serial stack program on one thread per candidate kept the other 120 threads at the barrier for ~2500 cycles)
+    {
+        const int nl = prog->n_leaves;
+#pragma unroll 1
+        for (int q = tid; q < ny * nl; q += T) {                  // leaves outside the materialised range: exactly +0.0
+            const int k = d2d_div_small(q, nl), l = q - k * nl;
+            if (l < l0 || l > l1) leaf[k][l] = 0.0;
         }
-        score[tid] = 0.0 + st[0];
+        __syncthreads();
+        const int nlev = prog->n_levels;
+#pragma unroll 1
+        for (int lev = 0; lev < nlev; lev++) {
+            const int a = prog->lev_off[lev], cnt = prog->lev_off[lev + 1] - a;
+#pragma unroll 1
+            for (int q = tid; q < ny * cnt; q += T) {
+                const int k = d2d_div_small(q, cnt), j = a + (q - k * cnt);
+                leaf[k][prog->node_id[j]] = leaf[k][prog->node_l[j]] + leaf[k][prog->node_r[j]];
+            }
+            __syncthreads();
+        }
     }
-    __syncthreads();
     if (tid == 0) {
         double max_reward = 0.0;
         int best = 0;
-        for (int k = 0; k < ny; k++)
-            if (max_reward < score[k]) { best = k; max_reward = score[k]; }   // strict <, first maximum (:123-125)
+        const int root = prog->root;
+        for (int k = 0; k < ny; k++) {
+            const double sc = 0.0 + leaf[k][root];
+            if (max_reward < sc) { best = k; max_reward = sc; }               // strict <, first maximum (:123-125)
+        }
         actions_out[e] = P.tab->v_yaw_space[best] / P.max_yaw_speed;
         P.ox_calls[e] = ncall;
     }

@@ -165,6 +165,28 @@ static void ox_rec(OxProgram *p, int off, int n) {
 static void build_ox_program(OxProgram *p, int n) {
     memset(p, 0, sizeof(*p));
     ox_rec(p, 0, n);
+    // the post-order program as a tree with level-sorted internal nodes (see OxProgram)
+    int st[64], lvl[2 * D2D_OX_MAX_LEAVES] = {0}, L[D2D_OX_MAX_LEAVES], R[D2D_OX_MAX_LEAVES], ID[D2D_OX_MAX_LEAVES];
+    int sp = 0, next = p->n_leaves, ni = 0, maxlev = 0;
+    for (int o = 0; o < p->n_ops; o++) {
+        const int op = p->ops[o];
+        if (op >= 0) { st[sp++] = op; continue; }
+        const int r = st[--sp], l = st[--sp];
+        L[ni] = l; R[ni] = r; ID[ni] = next;
+        lvl[next] = 1 + (lvl[l] > lvl[r] ? lvl[l] : lvl[r]);
+        if (lvl[next] > maxlev) maxlev = lvl[next];
+        st[sp++] = next++;
+        ni++;
+    }
+    p->root = st[0];
+    p->n_levels = maxlev;
+    int w = 0;
+    for (int lev = 1; lev <= maxlev; lev++) {
+        p->lev_off[lev - 1] = w;
+        for (int j = 0; j < ni; j++)
+            if (lvl[ID[j]] == lev) { p->node_id[w] = ID[j]; p->node_l[w] = L[j]; p->node_r[w] = R[j]; w++; }
+    }
+    p->lev_off[maxlev] = w;
 }
 
 // ------------------------------------------------------------------------------------------ create / destroy
