@@ -920,7 +920,8 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
     uint16_t *seen = P.ox_seen + (size_t)e * D2D_OX_SEEN_STRIDE;
     const int ncall = (fresh ? 0 : P.ox_calls[e]) + 1;          // index of this policy call within the episode
 
-    // ---- A
+    // ---- A: three independent pieces on three warps (warp 0 alone used to run them back to back -- ~2000 cycles of
+    //      double-double sin/cos, then the DRAM round trip of the first waypoint -- with the other warps at the barrier)
     if (wid == 0) {
         if (lane <= ny) {
             // candidate yaws: Drone2D(..., yaw_i) stores yaw_i % 360 (utils.py:718); entry n_yaw is the current pose
@@ -929,6 +930,7 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
             d2d_sincos(y * D2D_DEG2RAD, &sn, &cs);
             cs_s[lane] = cs; sn_s[lane] = -sn;    // vec_yaw = [cos, -sin] (yaw_planner.py:72)
         }
+    } else if (wid == 1) {
         int r0 = 0, r1 = -1, q0 = 0, q1 = -1, i0, i1, j0, j1;
         d2d_ox_window(P, dx, i0, i1);
         d2d_ox_window(P, dy, j0, j1);
@@ -938,23 +940,26 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
             d2d_ox_window(P, wx, r0, r1);
             d2d_ox_window(P, wy, q0, q1);
             if (r1 - r0 + 1 > D2D_OX_ROWS) r1 = r0 + D2D_OX_ROWS - 1;       // cannot happen for depth <= 9 cells
-            if (lane < prog->n_leaves) {
+#pragma unroll 1
+            for (int l = lane; l < prog->n_leaves; l += 32) {
                 const int b0 = r0 * D2D_GRID, b1 = (r1 + 1) * D2D_GRID - 1;
-                const int off = prog->leaf_off[lane], n = prog->leaf_len[lane];
-                if (b0 >= off && b0 < off + n) { geo[6] = lane; geo[4] = off; }
-                if (b1 >= off && b1 < off + n) { geo[7] = lane; geo[5] = off + n; }
+                const int off = prog->leaf_off[l], n = prog->leaf_len[l];
+                if (b0 >= off && b0 < off + n) { geo[6] = l; geo[4] = off; }
+                if (b1 >= off && b1 < off + n) { geo[7] = l; geo[5] = off + n; }
             }
         }
         if (lane == 0) {
             geo[0] = r0; geo[1] = r1; geo[2] = q0; geo[3] = q1; geo[8] = i0; geo[9] = i1; geo[10] = j0; geo[11] = j1;
             wpt[0] = wx; wpt[1] = wy;
         }
+    } else {
 #pragma unroll 1
-        for (int o = lane; o < D2D_MAX_YAW * D2D_OX_WORDS; o += 32) (&vmask[0][0])[o] = 0u;
-    } else if (fresh) {
-        // first call of a new episode: nothing has been seen yet
+        for (int o = tid - 64; o < D2D_MAX_YAW * D2D_OX_WORDS; o += D2D_OX_THREADS - 64) (&vmask[0][0])[o] = 0u;
+        if (fresh) {
+            // first call of a new episode: nothing has been seen yet
 #pragma unroll 1
-        for (int o = tid - 32; o < D2D_OX_SEEN_STRIDE / 2; o += D2D_OX_THREADS - 32) ((uint32_t *)seen)[o] = 0u;
+            for (int o = tid - 64; o < D2D_OX_SEEN_STRIDE / 2; o += D2D_OX_THREADS - 64) ((uint32_t *)seen)[o] = 0u;
+        }
     }
     __syncthreads();
     const int r0 = geo[0], r1 = geo[1], q0 = geo[2], q1 = geo[3], lo = geo[4], hi = geo[5], l0 = geo[6], l1 = geo[7];
