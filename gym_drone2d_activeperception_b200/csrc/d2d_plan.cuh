@@ -92,6 +92,7 @@ d2d_step_pre_kernel(const DevP P) {
     const int env0 = blockIdx.x * E;
 
     if (tid == 0) { d2d_mbar_init(c.mbar, 1); c.misc[0] = 0; c.misc[1] = 0; }
+    if (blockIdx.x == 0 && tid == 0) P.plan_list[P.B + 5] = 0;              // ticket counter of d2d_plan_kernel
     for (int w = tid; w < E * P.HW; w += T) c.hitw[w] = 0u;
     if (tid < E) { nact[tid] = 0; rep[tid] = 0; }
     __syncthreads();
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     const int par = P.plan_list[P.B + 3] & 1;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.plan_list[P.B + 4] = par; P.plan_list[P.B + 1 + (par ^ 1)] = 0;
+        P.plan_list[P.B + 5] = 0;                                            // ticket counter of d2d_plan_kernel
         atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], (unsigned long long)P.B);    // every env steps once per d2d_step
     }
 
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
     double *trk = (double *)(psm + D2D_BELIEF_STRIDE);          // [NP][6]
     double *red_v = trk + (size_t)P.NP * 6;                     // [8] warp partials
     int *red_i = (int *)(red_v + 8);                            // [8]
-    int *sh = red_i + 8;                                        // [8] cur, n_nodes, n_open, -, nact
+    int *sh = red_i + 8;                                        // [8] cur, n_nodes, n_open, -, nact, -, -, ticket
     int *wsum = sh + 8;                                         // [8] warp prefix
     uint8_t *prim_ok = (uint8_t *)(wsum + 8);                   // [nprim]
     const PlanWs w = d2d_plan_carve(P.plan_ws + (size_t)blockIdx.x * d2d_plan_workspace_bytes(P.n_u), P.n_u);
@@ -548,9 +550,17 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
     }
     const int count = min(P.plan_list[P.B + (P.use_parity ? 1 + P.plan_list[P.B + 4] : 0)], P.B);
 
-    for (int li = blockIdx.x; li < count; li += gridDim.x) {
-        const int e = P.plan_list[li];
+    // Searches differ widely in length (1 .. 99 expansions), so the list entries are handed out dynamically: a block takes
+    // the next one when it is done (ticket counter plan_list[B+5], zeroed by the step kernel that fills the list).  With
+    // the static grid-stride assignment the SMs were busy 48 % of the kernel.  Which block runs a search does not matter:
+    // every search is self-contained in the block's own workspace.
+    for (;;) {
         __syncthreads();
+        if (tid == 0) sh[7] = atomicAdd(&P.plan_list[P.B + 5], 1);      // sh[7]: this block's ticket
+        __syncthreads();
+        const int li = sh[7];
+        if (li >= count) break;
+        const int e = P.plan_list[li];
         for (int o = tid; o < D2D_BELIEF_STRIDE / 4; o += T)
             ((uint32_t *)bel)[o] = ((const uint32_t *)(P.belief + (size_t)e * D2D_BELIEF_STRIDE))[o];
         if (h.fast) {
