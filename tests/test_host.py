@@ -239,3 +239,20 @@ def test_obstacle_density_matches_reference_golden():
     for ci, c in enumerate(json.loads(str(g["cases"]))):
         p = Params(debug=False, planner="NoMove", gaze_method="NoControl", **c)
         assert np.array_equal(obstacle_density(p, g["seeds"]), g["density_%d" % ci]), c
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): stdout is exactly one JSON line carrying the
+    contract keys; everything else goes to stderr."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(util.ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "3"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "env-steps/sec" and d["unit"] == "env-steps/s" and d["value"] > 0
+    assert d["higher_is_better"] is True and d["gpu_launches"] == 0 and d["config"]["workload"].startswith("configs[1]")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
