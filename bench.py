@@ -3,20 +3,31 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5] [--envs B]
 
-A "step" is one pass of Drone2DEnv2.step over one batch of synthetic (seeded) environments.  Default workload is
-BASELINE.json configs[1]: empty_map.npy, 4096 envs per GPU, 10 agents, perception + dynamics (NoMove planner,
-Kalman trackers on as in the reference).  For N > 1 launch with torchrun (one rank per GPU, weak scaling: every
-rank steps its own 4096 envs; the only collective is one NCCL all-reduce of the episode statistics).
+A "step" is one pass of Drone2DEnv2.step over one batch of synthetic (seeded) environments.  The headline workload is
+BASELINE.json configs[1]: empty_map.npy, 4096 envs per GPU, 10 agents, perception + dynamics (NoMove planner, Kalman
+trackers on as in the reference).  For N > 1 launch with torchrun (one rank per GPU, weak scaling: every rank steps its own
+batch; the only collective of the path is one NCCL all-reduce of the episode statistics).
 
-Prints ONE JSON line (rank 0).  `value`: whole-job env-steps/s with inputs resident in HBM: exactly K steps back to back
-(one CUDA graph of the K step launches) between barrier + synchronize, one CUDA-event pair; the L2 is kept cold by
-stepping R independent replicas of the batch round robin so that >= 256 MiB of state is touched between two visits of a
-replica (`per_step_events` repeats the measurement one launch at a time with an explicit L2 flush).  `e2e`: the same metric through d2d_step_host with pinned HOST buffers
-(actions H2D + observation D2H inside the timed region).  `roofline`: algorithmic bytes (SURVEY.md §8d:
-2406 + 104*N per env-step) / measured kernel time vs the measured HBM copy peak.  `cpu_baseline`: the oracle port
-of the reference path (oracle/drone2d_oracle.c) on the host cores, bounded sample.
+Prints ONE JSON line (rank 0).
+  value      whole-job env-steps/s with inputs resident in HBM.  The K steps are captured once as a CUDA graph of the K step
+             launches; the graph is replayed M times back to back (M chosen so that the region lasts >= ~100 ms per rank),
+             every replay bracketed by its own CUDA-event pair on the launch stream, barrier + synchronize around the region.
+             Per rank the MEDIAN replay is taken; the job's figure is the MAX over ranks of those medians (a 0.5 ms region
+             with a plain max-reduce is one scheduling hiccup away from -26 %: round-1 SCALE at N = 8).  Every rank's
+             median / min / max is in `per_rank`.  The L2 is kept cold by data size: R independent replicas of the batch
+             are stepped round robin so that >= 256 MiB of state is touched between two visits of a replica.
+  e2e        the same metric through d2d_step_host with pinned HOST buffers, host<->device traffic inside the timed region:
+             headline = zero-copy mirror transport (d2d_bind_host_mirror), `e2e.full_copy` = plain copies of the whole
+             observation every step.
+  roofline   algorithmic bytes (2406 + 104*N per env-step) / measured step time vs the measured HBM copy peak.
+  workloads  the other BASELINE configs at their own batch sizes in the same run (config 3: Primitive planner, config 4:
+             Primitive + Oxford, config 5: 96 agents, and one point of the config-5 ray / FOV sweep), each with value, e2e,
+             roofline and per-rank figures.
+  shard_invariant (N > 1)  every rank also steps a 64-env slice of its neighbour's shard; the state hashes agree.
+  cpu_baseline   the oracle port of the reference path (oracle/drone2d_oracle.c) on the host cores, bounded sample.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -32,7 +43,7 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, _p)
 
 CONFIGS = {
-    # BASELINE.json configs[1..4] (SURVEY.md §8d parameters)
+    # BASELINE.json configs[1..4] (SURVEY.md 8d parameters)
     2: dict(name="configs[1]: empty_map.npy, 4096 envs/GPU, 10 agents, perception+dynamics (NoMove)", envs=4096,
             params=dict(planner="NoMove", static_map="maps/empty_map.npy", agent_number=10, agent_radius=15,
                         agent_max_speed=20, map_id=1)),
@@ -49,8 +60,51 @@ CONFIGS = {
                         agent_max_speed=40, map_id=1)),
 }
 METRIC = "env-steps/sec"
-N_RAYS = 50
 D2D_STATE_BYTES = 2560 + 400 + 128            # read per env and step: belief grid, ground-truth rows, env record
+L2_NOTE = "inputs larger than L2: replicas of the batch stepped round robin, >= 256 MiB of state touched between two " \
+          "visits of a replica (L2 = 126 MB); batches above that size need one replica"
+
+
+# ------------------------------------------------------------------------------------------ workload description
+def make_cfg(config_id, planner=None, gaze=None, view_range=0, strip_width=10, motion_profile=None, envs=0):
+    base = CONFIGS[config_id]
+    cfg = dict(base, params=dict(base["params"]), config_id=config_id, strip_width=strip_width)
+    cfg["gaze"] = gaze or base.get("gaze", "scripted")
+    if planner and planner != base["params"]["planner"]:
+        cfg["params"]["planner"] = planner
+        cfg["name"] += " [planner=%s]" % planner
+    if motion_profile and motion_profile != "CVM":
+        cfg["params"]["motion_profile"] = motion_profile
+        cfg["name"] += " [motion_profile=%s]" % motion_profile
+    if view_range:
+        cfg["params"]["drone_view_range"] = view_range
+        cfg["name"] += " [view_range=%d]" % view_range
+    if strip_width != 10:
+        cfg["name"] += " [strip_width=%d]" % strip_width
+    if cfg["gaze"] == "Oxford":
+        cfg["params"]["gaze_method"] = "Oxford"
+        if base.get("gaze") != "Oxford":
+            cfg["name"] += " [gaze=Oxford on device]"
+    if envs:
+        cfg["envs"] = envs
+    return cfg
+
+
+def n_rays_of(cfg):
+    return -(-500 // cfg["strip_width"])            # ceil(map_size[0] / strip_width), utils.py:587
+
+
+def n_agents_of(cfg):
+    from gym_drone2d_activeperception_b200 import Params, count_agents, load_static_map
+    p = Params(debug=False, **cfg["params"])
+    return count_agents(p, load_static_map(p.static_map))
+
+
+def public_config(cfg, n_gpus):
+    """The `config` object of the JSON line: identical for both arms (--impl ours / reference) of the same workload."""
+    return {"workload": cfg["name"], "envs_per_gpu": cfg["envs"], "agents_per_env": n_agents_of(cfg),
+            "rays_per_env_step": n_rays_of(cfg), "planner": cfg["params"]["planner"], "gaze": cfg["gaze"],
+            "trackers": True, "auto_reset": True, "l2": L2_NOTE, "parallelism": "env-sharded x%d" % n_gpus}
 
 
 def _gen_chunk(args):
@@ -59,14 +113,14 @@ def _gen_chunk(args):
     return generate_worlds(Params(debug=False, **pk), seeds)
 
 
-def make_worlds(pk, seeds, unique=None):
+def make_worlds(pk, seeds, unique=None, max_procs=32):
     """Host-side world generation (seeded, the reference's own procedure).  `unique` caps the number of distinct
     worlds (tiled to the batch) to bound set-up time for the very large configs; the default keeps every env unique."""
     import multiprocessing as mp
     seeds = np.asarray(seeds)
     B = len(seeds)
     gen = seeds if unique is None or unique >= B else seeds[:unique]
-    nproc = max(1, min(len(os.sched_getaffinity(0)), 32, len(gen) // 64))
+    nproc = max(1, min(len(os.sched_getaffinity(0)), max_procs, len(gen) // 64))
     chunks = np.array_split(gen, nproc)
     if nproc > 1:
         with mp.get_context("fork").Pool(nproc) as pool:
@@ -114,7 +168,8 @@ class ClockSampler(threading.Thread):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm),
-                "window": "back-to-back steps for 1.5 s right after the timed region (reasons: whole run)"}
+                "window": "the timed graph replays of the headline workload plus back-to-back steps for 1.5 s right after "
+                          "(reasons: whole run)"}
 
 
 def measured_peak():
@@ -126,15 +181,14 @@ def measured_peak():
 
 
 def algorithmic_bytes(n_agents):
-    return 2406 + 104 * n_agents          # SURVEY.md §8(d); tracker traffic deliberately NOT counted
+    return 2406 + 104 * n_agents          # SURVEY.md 8(d); tracker / Oxford-state traffic deliberately NOT counted
 
 
+# ------------------------------------------------------------------------------------------ CPU arm (oracle port)
 def cpu_port_run(pk, n_envs, steps, threads, seed0=1, oxford=False):
     """Times the oracle port of the reference path on the host: n_envs envs x steps steps over `threads` threads
-    (ctypes releases the GIL).  Returns env-steps/s."""
-    import ctypes as C
+    (ctypes releases the GIL), with the batched env's auto-reset rule.  Returns (env-steps/s, seconds)."""
     import oracle
-    from concurrent.futures import ThreadPoolExecutor
     from gym_drone2d_activeperception_b200 import Params
     p = Params(debug=False, **pk)
     worlds = make_worlds(pk, seed0 + np.arange(n_envs))
@@ -149,26 +203,16 @@ def cpu_port_run(pk, n_envs, steps, threads, seed0=1, oxford=False):
     if p.motion_profile == "RVO":
         for i, e in enumerate(envs):
             e.set_rvo(worlds["agent_vel"][i], worlds["obstacles"][i])
-    L = oracle.lib()
+    ob = oracle.OracleBatch(envs, threads=threads)
     table = np.arange(-80, 80, 80 / 3) / 80
     rng = np.random.RandomState(0)
-    slices = np.array_split(np.arange(n_envs), threads)
-
-    def run_slice(idx, nsteps):
-        arr = (C.POINTER(oracle.Env) * len(idx))(*[envs[i]._ptr for i in idx])
-        if oxford:      # Oxford.plan picks every action (config 4 workload)
-            L.d2do_run_many_oxford(arr, len(idx), nsteps)
-            return
-        acts = np.ascontiguousarray(table[rng.randint(0, 6, (len(idx), nsteps))])
-        L.d2do_run_many(arr, len(idx), nsteps, acts.ctypes.data_as(C.POINTER(C.c_double)))
-
-    with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(lambda s: run_slice(s, 2), slices))            # warm-up
-        t0 = time.perf_counter()
-        list(ex.map(lambda s: run_slice(s, steps), slices))
-        dt = time.perf_counter() - t0
-    for e in envs:
-        e.close()
+    policy = "Oxford" if oxford else "scripted"
+    ob.run(2, None if oxford else table[rng.randint(0, 6, (2, n_envs))], policy=policy)        # warm-up
+    acts = None if oxford else table[rng.randint(0, 6, (steps, n_envs))]
+    t0 = time.perf_counter()
+    ob.run(steps, acts, policy=policy)
+    dt = time.perf_counter() - t0
+    ob.close()
     return n_envs * steps / dt, dt
 
 
@@ -181,13 +225,13 @@ def run_reference(args, cfg):
     import oracle
     oracle.build()
     cores = len(os.sched_getaffinity(0))
-    n_envs = 4096 if cfg["envs"] >= 4096 else cfg["envs"]
+    n_envs = min(4096, cfg["envs"])
     steps_per = 200
     vals = []
     t_all = time.perf_counter()
+    pk = {k: v for k, v in cfg["params"].items() if k != "gaze_method"}
     for it in range(args.warmup + args.steps):
-        v, dt = cpu_port_run({k: v for k, v in cfg["params"].items() if k != "gaze_method"}, n_envs, steps_per, cores,
-                             seed0=1 + it, oxford=args.gaze == "Oxford")
+        v, dt = cpu_port_run(pk, n_envs, steps_per, cores, seed0=1 + it, oxford=cfg["gaze"] == "Oxford")
         if it >= args.warmup:
             vals.append((n_envs * steps_per, dt))
         if time.perf_counter() - t_all > 150 and len(vals) >= 1:
@@ -195,12 +239,13 @@ def run_reference(args, cfg):
     tot_steps = sum(v[0] for v in vals)
     tot_t = sum(v[1] for v in vals)
     value = tot_steps / tot_t
-    sample = "%d envs x %d steps per bench step, %d bench steps, %d threads" % (n_envs, steps_per, len(vals), cores)
+    n_rays = n_rays_of(cfg)
+    sample = "%d envs x %d steps per bench step (auto-reset on), %d bench steps, %d threads" % (n_envs, steps_per, len(vals), cores)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(vals)),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["name"], "rays_per_env_step": N_RAYS},
-            "rays_per_sec": value * N_RAYS,
+            "config": public_config(cfg, args.gpus),
+            "rays_per_sec": value * n_rays,
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -226,79 +271,57 @@ def emit(line):
     out.flush()
 
 
-def main():
-    _claim_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
-    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the config's)")
-    ap.add_argument("--envs-per-block", type=int, default=0)
-    ap.add_argument("--unique-worlds", type=int, default=0, help="cap distinct generated worlds (0 = all unique up to 8192)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--burn-in", type=int, default=1000, help="untimed steps per replica before the timed region")
-    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps (reported in config)")
-    ap.add_argument("--strip-width", type=int, default=10, help="ray strip width: rays = ceil(500 / strip_width) (config 5 sweep: 10/5/2)")
-    ap.add_argument("--view-range", type=int, default=0, help="drone_view_range in degrees (config 5 sweep: 90/180/360)")
-    ap.add_argument("--planner", default=None, choices=["NoMove", "Primitive"], help="override the config's planner")
-    ap.add_argument("--motion-profile", default=None, choices=["CVM", "RVO"], help="agent motion profile (default CVM)")
-    ap.add_argument("--e2e-full-copy", action="store_true", help="e2e leg with plain D2H copies instead of the zero-copy mirror")
-    ap.add_argument("--gaze", default=None, choices=["scripted", "Oxford"],
-                    help="scripted: random actions from the Oxford action set; Oxford: d2d_plan_oxford every step")
-    args = ap.parse_args()
-    cfg = dict(CONFIGS[args.config])
-    if args.gaze is None:
-        args.gaze = cfg.get("gaze", "scripted")
-    if args.planner:
-        cfg["params"] = dict(cfg["params"], planner=args.planner)
-        if args.planner != CONFIGS[args.config]["params"]["planner"]:
-            cfg["name"] += " [planner=%s]" % args.planner
-    if args.motion_profile and args.motion_profile != "CVM":
-        cfg["params"] = dict(cfg["params"], motion_profile=args.motion_profile)
-        cfg["name"] += " [motion_profile=%s]" % args.motion_profile
-    if args.view_range:
-        cfg["params"] = dict(cfg["params"], drone_view_range=args.view_range)
-        cfg["name"] += " [view_range=%d]" % args.view_range
-    if args.strip_width != 10:
-        cfg["name"] += " [strip_width=%d]" % args.strip_width
-    if args.gaze == "Oxford":
-        cfg["params"] = dict(cfg["params"], gaze_method="Oxford")
-        if CONFIGS[args.config].get("gaze") != "Oxford":
-            cfg["name"] += " [gaze=Oxford on device]"
-    if args.warmup < 3:
-        args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args, cfg)
-        return
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    B = args.envs or cfg["envs"]
-    pk = cfg["params"]
-    unique = args.unique_worlds or min(B, 16384)
-    # worlds are generated before CUDA is touched (fork-based pool)
-    seeds = pk["map_id"] + rank * B + np.arange(B)
-    t0 = time.perf_counter()
-    worlds = make_worlds(pk, seeds, unique=unique)
-    t_world = time.perf_counter() - t0
 
+# ------------------------------------------------------------------------------------------ GPU arm: one workload
+class Ctx(object):
+    """Per-process context: rank / device / collectives (through the package's distributed helpers)."""
+
+    def __init__(self, args):
+        import torch
+        from gym_drone2d_activeperception_b200 import distributed as D
+        self.rank, self.local_rank, self.world = D.rank_world()
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        D.init_process_group("nccl", device=self.dev)
+        self.D = D
+        self.args = args
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_rows(self, row):
+        """all-gather of one small float64 row per rank -> [world, len(row)] numpy"""
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([row], dtype=torch.float64, device=self.dev)
+        if self.world == 1:
+            return t.cpu().numpy()
+        out = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t)
+        return torch.cat(out).cpu().numpy()
+
+
+def measure(ctx, cfg, worlds, t_world, unique, headline):
+    """Times one workload on this rank's GPU and reduces over ranks; returns the result dict (meaningful on every rank)."""
     import torch
-    import torch.distributed as dist
     from gym_drone2d_activeperception_b200 import Params
     from gym_drone2d_activeperception_b200.vec_env import Drone2DVecEnv
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    args, dev, world, rank = ctx.args, ctx.dev, ctx.world, ctx.rank
+    B, pk = cfg["envs"], cfg["params"]
     p = Params(debug=False, **pk)
-    use_ox = args.gaze == "Oxford"
+    use_ox = cfg["gaze"] == "Oxford"
+    seeds = ctx.D.shard_seeds(pk["map_id"], B, rank)
+
     def make_env():
         return Drone2DVecEnv(p, B, seeds=seeds, worlds=worlds, device=dev, auto_reset=True, trackers=True, oxford=use_ox,
-                             envs_per_block=args.envs_per_block, strip_width=args.strip_width)
+                             envs_per_block=args.envs_per_block, strip_width=cfg["strip_width"])
     env = make_env()
     n_rays = int(env.cfg.n_rays)
     N = env.num_agents
@@ -321,22 +344,16 @@ def main():
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     actions = table[torch.randint(0, 6, (K + W, B), device=dev, generator=gen)].contiguous()
+    burn = args.burn_in if headline else min(args.burn_in, 300)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing: EXACTLY K steps back to back (one CUDA graph of the K step launches on the launch
-    #      stream), bracketed by barrier + synchronize and one CUDA-event pair
     for t in range(max(W, R)):                      # eager warm-up: every replica steps at least once
         do_step(actions[t % (K + W)], envs[t % R])
     # burn-in (untimed): episodes last up to 800 steps, so the mix of fresh / explored / tracking envs -- and with it the
     # cost of a step -- only becomes stationary after about a thousand steps (1000 steps with auto-reset)
-    for t in range(args.burn_in):
+    for t in range(burn):
         for e in envs:
             do_step(actions[t % (K + W)], e)
-    barrier()
+    ctx.barrier()
     side = torch.cuda.Stream(device=dev)
     graph = torch.cuda.CUDAGraph()
     l0 = sum(e.launch_count() for e in envs)
@@ -345,66 +362,85 @@ def main():
             for t in range(K):
                 do_step(actions[W + t], envs[t % R])
     launches = sum(e.launch_count() for e in envs) - l0          # kernel nodes of the graph == launches per K steps
-    barrier()
-    graph.replay()                                  # untimed: graph upload + K more warm-up steps
-    barrier()
-    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wall0 = time.perf_counter()
-    ev0.record()
+    ctx.barrier()
+    # untimed replays: graph upload, K more warm-up steps, and an estimate of the replay time to size M
     graph.replay()
-    ev1.record()
-    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); graph.replay(); e1.record()
+    torch.cuda.synchronize()
+    est_ms = max(1e-3, float(e0.elapsed_time(e1)))
+    M = int(min(4000, max(7, -(-args.region_ms // est_ms))))
+    if world > 1:                                   # same M on every rank
+        M = int(ctx.gather_rows([float(M)])[:, 0].max())
+    sampler = None
+    if headline:
+        sampler = ClockSampler(ctx.local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                               int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[ctx.local_rank]))
+        sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(M + 1)]
+    ctx.barrier()
+    if sampler is not None:
+        sampler.mark = len(sampler.rows)
+    wall0 = time.perf_counter()
+    evs[0].record()
+    for m in range(M):
+        graph.replay()
+        evs[m + 1].record()
+    ctx.barrier()
     wall = time.perf_counter() - wall0
-    total_ms = float(ev0.elapsed_time(ev1))
-    repeats = []
-    for _ in range(4):                              # run-to-run spread of the same K-step region (reported, not used)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); graph.replay(); e1.record()
-        torch.cuda.synchronize()
-        repeats.append(float(e0.elapsed_time(e1)) / K)
-    # ---- secondary: the same step timed one launch at a time (CUDA events around every step, 256 MiB L2 flush in
-    #      between, untimed): includes ~3-4 us of event / launch gap per step; kept for the per-step distribution
-    Kp = min(K, 100)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    pe0 = [torch.cuda.Event(enable_timing=True) for _ in range(Kp)]
-    pe1 = [torch.cuda.Event(enable_timing=True) for _ in range(Kp)]
-    for t in range(Kp):
-        flush.fill_(t & 0xFF)
-        pe0[t].record()
-        do_step(actions[W + t])
-        pe1[t].record()
-    barrier()
-    step_ms = np.array([a.elapsed_time(b) for a, b in zip(pe0, pe1)])
-    del flush
-    # ---- end to end through the C ABI with pinned host buffers
-    a_host = actions[W:].cpu().pin_memory()
+    rep_ms = np.array([evs[m].elapsed_time(evs[m + 1]) for m in range(M)], dtype=np.float64)
+    med_ms, min_ms, max_ms = float(np.median(rep_ms)), float(rep_ms.min()), float(rep_ms.max())
+
+    per_step = None
+    if headline:
+        # secondary: the same step timed one launch at a time (CUDA events around every step, 256 MiB L2 flush in between,
+        # untimed): includes ~3-4 us of event / launch gap per step; kept for the per-step distribution
+        Kp = min(K, 100)
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        pe0 = [torch.cuda.Event(enable_timing=True) for _ in range(Kp)]
+        pe1 = [torch.cuda.Event(enable_timing=True) for _ in range(Kp)]
+        for t in range(Kp):
+            flush.fill_(t & 0xFF)
+            pe0[t].record()
+            do_step(actions[W + t])
+            pe1[t].record()
+        ctx.barrier()
+        step_ms = np.array([a.elapsed_time(b) for a, b in zip(pe0, pe1)])
+        del flush
+        per_step = {"what": "same step, one launch at a time: CUDA events around every step, 256 MiB L2 flush (untimed) in "
+                            "between; includes the event / launch gap of each step",
+                    "steps": int(Kp), "ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
+                    "value": world * B / (float(np.mean(step_ms)) * 1e-3)}
+
+    # ---- end to end through the C ABI with pinned host buffers (wall clock, synchronise per step)
+    a_host = actions.cpu().pin_memory()
     lm_host = torch.empty((B, 1, 33, 33), dtype=torch.uint8).pin_memory()
     yaw_host = torch.empty((B,), dtype=torch.float32).pin_memory()
     done_host = torch.empty((B,), dtype=torch.uint8).pin_memory()
-    Ke = min(K, 100)
-    a_rows = [a_host[t] for t in range(Ke)]          # views of the pinned action buffer, one per step
+    a_rows = [a_host[t] for t in range(K + W)]       # views of the pinned action buffer, one per step
     stage = env.buffer("actions_staging")
+    Ke = int(min(2000, max(K, -(-(0.5 * args.region_ms) // (est_ms / K + 0.02)))))
 
     def e2e_step(t):
         if use_ox:      # the policy runs on the device: its actions never leave the GPU, the observation still does
             env.plan_oxford(stage)
             env.step_host(None, lm_host, yaw_host, done_host)
         else:
-            env.step_host(a_rows[t], lm_host, yaw_host, done_host)
+            env.step_host(a_rows[t % (K + W)], lm_host, yaw_host, done_host)
 
     def e2e_loop():
         for t in range(3):
             e2e_step(t)
-        barrier()
+        ctx.barrier()
         st0 = env.stats()
         t0 = time.perf_counter()
         for t in range(Ke):
             e2e_step(t)
-        barrier()
-        return time.perf_counter() - t0, env.stats() - st0
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        ctx.barrier()
+        return dt, env.stats() - st0
 
     # (a) plain copies: every step moves the whole observation tensor device -> host
     e2e_copy_s, _ = e2e_loop()
@@ -418,99 +454,198 @@ def main():
         mirror_bytes = float(dst[14]) / Ke
         assert torch.equal(lm_host, env.buffer("local_map").cpu()) and torch.equal(done_host, env.buffer("done").cpu())
         env.bind_host_mirror(None, None, None)
-    # clock / throttle sampling needs a loaded window much longer than the millisecond-scale timed region:
-    # keep stepping back to back (untimed, same kernel) for ~1.5 s while nvidia-smi samples every 100 ms
-    t_probe = time.perf_counter()
-    sampler.mark = len(sampler.rows)
-    while time.perf_counter() - t_probe < 1.5:
-        for t in range(50):
-            do_step(actions[W + (t % K)])
-        torch.cuda.synchronize()
-    clocks = sampler.stop()
+    clocks = None
+    if headline:
+        # clock / throttle sampling needs a loaded window: keep stepping back to back (untimed, same kernel) for ~1.5 s
+        t_probe = time.perf_counter()
+        while time.perf_counter() - t_probe < 1.5:
+            graph.replay()
+            torch.cuda.synchronize()
+        clocks = sampler.stop()
 
-    # max over ranks (device time), whole-job throughput
-    tt = torch.tensor([total_ms, e2e_s * 1e3, e2e_copy_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms_max, e2e_ms_max, e2e_copy_ms_max = float(tt[0]), float(tt[1]), float(tt[2])
+    # ---- over ranks: max of the per-rank medians; every rank's figures are reported
+    rows = ctx.gather_rows([med_ms / K, min_ms / K, max_ms / K, e2e_s * 1e3 / Ke, e2e_copy_s * 1e3 / Ke])
+    ms_step = float(rows[:, 0].max())
+    e2e_ms, e2e_copy_ms = float(rows[:, 3].max()), float(rows[:, 4].max())
     # the one collective of the path: all-reduce of the episode statistics
-    stats = torch.as_tensor(sum(np.asarray(e.stats(), dtype=np.int64) for e in envs), device=dev)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-    value = world * B * K / (total_ms_max * 1e-3)
-    e2e = world * B * Ke / (e2e_ms_max * 1e-3)
+    stats = ctx.D.allreduce_stats(sum(np.asarray(e.stats(), dtype=np.int64) for e in envs), device=dev)
+    value = world * B / (ms_step * 1e-3)
+    e2e = world * B / (e2e_ms * 1e-3)
+
+    peak, peak_src = measured_peak()
+    if pk["planner"] == "NoMove":
+        kernel_name = "d2d_step_fused_warp_kernel (1 launch/step)"
+    else:
+        kernel_name = "d2d_step_prim_warp_kernel + d2d_plan_kernel + d2d_step_post_list_kernel" + \
+                      (" + d2d_oxford_kernel" if use_ox else "") + " (whole step timed)"
+    achieved = algorithmic_bytes(N) * B / (ms_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_config%d.json" % cfg["config_id"])
+    if os.path.isfile(tpath) and pk["planner"] == "NoMove" and n_rays == 50 and "view_range" not in cfg["name"]:
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    res = {
+        "value": value, "unit": "env-steps/s", "ms_per_step": ms_step, "rays_per_sec": value * n_rays,
+        "config": public_config(cfg, world),
+        "method": {"timing": "K = %d steps captured as one CUDA graph (K step launches), replayed M = %d times back to back, "
+                             "one CUDA-event pair per replay on the launch stream, barrier + synchronize around the region; "
+                             "per rank the median replay, over ranks the max of the medians" % (K, M),
+                   "graph_replays": M, "timed_region_ms_this_rank": float(rep_ms.sum()), "wall_s_timed_region": wall,
+                   "replicas": R, "state_touched_between_visits_mb": round(R * touched / 1e6, 1),
+                   "l2": "no rotation (--no-flush): state stays L2-resident" if args.no_flush else L2_NOTE,
+                   "burn_in_steps_per_replica": burn, "unique_worlds_per_gpu": int(unique), "world_gen_s": round(t_world, 2),
+                   "envs_per_block": int(env.cfg.envs_per_block)},
+        "per_rank": [{"rank": r, "ms_per_step_median": float(rows[r, 0]), "ms_per_step_min": float(rows[r, 1]),
+                      "ms_per_step_max": float(rows[r, 2]), "e2e_ms_per_step": float(rows[r, 3])} for r in range(world)],
+        "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": 0 if use_ox else B * 8,
+                "d2h_bytes_per_step": B * (1089 + 4 + 1) if mirror_bytes is None else int(round(B * 5 + mirror_bytes)),
+                "steps": Ke,
+                "transport": "cudaMemcpyAsync of the whole observation every step" if mirror_bytes is None else
+                             "d2d_bind_host_mirror: kernels store changed observation bytes + yaw + done straight into "
+                             "the pinned host buffers (bytes counted on the device, mean per step, this rank)",
+                "full_copy": {"value": world * B / (e2e_copy_ms * 1e-3), "d2h_bytes_per_step": B * (1089 + 4 + 1)}},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "bytes_per_env_step": algorithmic_bytes(N),
+                     "kernel": kernel_name, "kernel_ms": ms_step},
+        "episode_stats": {n: int(v) for n, v in zip(
+            ["env_steps", "episodes", "success", "static_collision", "dynamic_collision", "freezing", "dead_lock",
+             "flight_steps", "grid_discovered", "agents_tracked", "tracked_steps", "plans", "plan_failures", "replans"],
+            stats.tolist()[:14])},
+    }
+    if per_step is not None:
+        res["per_step_events"] = per_step
+    if clocks is not None:
+        res["clocks"] = clocks
+    del graph
+    for e in envs:
+        e.close()
+    torch.cuda.empty_cache()
+    return res
+
+
+def shard_invariance(ctx, cfg, steps=48, n=64):
+    """N > 1: a given global env must evolve identically whichever GPU runs it.  Every rank steps the first `n` envs of its
+    own shard and the first `n` envs of its right neighbour's shard (worlds regenerated here from the global seeds, actions
+    a function of (global env, t)); the state hashes are all-gathered and compared."""
+    import torch
+    from gym_drone2d_activeperception_b200 import Params, generate_worlds
+    from gym_drone2d_activeperception_b200.vec_env import Drone2DVecEnv
+    if ctx.world == 1:
+        return None
+    pk, B = cfg["params"], cfg["envs"]
+    p = Params(debug=False, **pk)
+    table = np.arange(-80, 80, 80 / 3) / 80
+
+    def run(owner):
+        seeds = ctx.D.shard_seeds(pk["map_id"], B, owner)[:n]
+        env = Drone2DVecEnv(p, n, seeds=seeds, worlds=generate_worlds(p, seeds), device=ctx.dev, auto_reset=True)
+        g = owner * B + np.arange(n)
+        for t in range(steps):
+            env.step(torch.as_tensor(table[(g * 7 + t * 13) % 6], device=ctx.dev))
+        torch.cuda.synchronize()
+        hsh = hashlib.sha256()
+        for name in ("belief", "local_map", "agent_pos", "agent_pref", "drone_yaw", "done", "steps", "tracker_mu", "hit"):
+            hsh.update(env.buffer(name).contiguous().cpu().numpy().tobytes())
+        env.close()
+        return float(int.from_bytes(hsh.digest()[:6], "little"))         # 48 bits: exact in a float64
+    own, nb = run(ctx.rank), run((ctx.rank + 1) % ctx.world)
+    rows = ctx.gather_rows([own, nb])
+    return bool(all(rows[r, 1] == rows[(r + 1) % ctx.world, 0] for r in range(ctx.world)))
+
+
+def main():
+    _claim_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the config's)")
+    ap.add_argument("--envs-per-block", type=int, default=0)
+    ap.add_argument("--unique-worlds", type=int, default=0, help="cap distinct generated worlds (0 = all unique up to 16384)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="headline workload only (skip the `workloads` list)")
+    ap.add_argument("--burn-in", type=int, default=1000, help="untimed steps per replica before the timed region")
+    ap.add_argument("--region-ms", type=float, default=100.0, help="minimum length of the timed region per rank")
+    ap.add_argument("--no-flush", action="store_true", help="do not rotate replicas (state stays in L2; reported)")
+    ap.add_argument("--strip-width", type=int, default=10, help="ray strip width: rays = ceil(500 / strip_width) (config 5 sweep: 10/5/2)")
+    ap.add_argument("--view-range", type=int, default=0, help="drone_view_range in degrees (config 5 sweep: 90/180/360)")
+    ap.add_argument("--planner", default=None, choices=["NoMove", "Primitive"], help="override the config's planner")
+    ap.add_argument("--motion-profile", default=None, choices=["CVM", "RVO"], help="agent motion profile (default CVM)")
+    ap.add_argument("--e2e-full-copy", action="store_true", help="e2e leg with plain D2H copies instead of the zero-copy mirror")
+    ap.add_argument("--gaze", default=None, choices=["scripted", "Oxford"],
+                    help="scripted: random actions from the Oxford action set; Oxford: d2d_plan_oxford every step")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    cfg = make_cfg(args.config, planner=args.planner, gaze=args.gaze, view_range=args.view_range,
+                   strip_width=args.strip_width, motion_profile=args.motion_profile, envs=args.envs)
+    if args.impl == "reference":
+        run_reference(args, cfg)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # the default run (BASELINE config 2 headline, no overrides) also measures the other BASELINE configs
+    default_run = args.config == 2 and not (args.planner or args.gaze or args.view_range or args.motion_profile or
+                                           args.envs or args.strip_width != 10)
+    extra = []
+    if default_run and not args.no_workloads:
+        extra = [make_cfg(3), make_cfg(4), make_cfg(5), make_cfg(5, view_range=360, strip_width=2)]
+    # worlds of every workload are generated before CUDA is touched (fork-based pool)
+    procs = max(2, len(os.sched_getaffinity(0)) // max(1, world))
+    gen = []
+    for c in [cfg] + extra:
+        B = c["envs"]
+        unique = args.unique_worlds or min(B, 16384 if c is cfg else 8192)
+        t0 = time.perf_counter()
+        seeds = c["params"]["map_id"] + rank * B + np.arange(B)
+        gen.append((c, make_worlds(c["params"], seeds, unique=unique, max_procs=procs), time.perf_counter() - t0, unique))
+        log("worlds for", c["name"], "in %.1f s" % gen[-1][2])
+
+    import torch.distributed as dist
+    ctx = Ctx(args)
+    line = None
+    workloads = []
+    for i, (c, worlds, t_world, unique) in enumerate(gen):
+        t0 = time.perf_counter()
+        res = measure(ctx, c, worlds, t_world, unique, headline=(i == 0))
+        log("%s: %.1f M env-steps/s, e2e %.1f M (%.1f s)" % (c["name"], res["value"] / 1e6, res["e2e"]["value"] / 1e6,
+                                                            time.perf_counter() - t0))
+        gen[i] = None                                # release the host arrays of this workload
+        if i == 0:
+            line = res
+        else:
+            workloads.append(res)
+    inv = shard_invariance(ctx, cfg)
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        kern_ms = total_ms_max / K            # average launch-to-launch duration inside the timed region
-        if cfg["params"]["planner"] == "NoMove":
-            kernel_name = "d2d_step_fused_warp_kernel (1 launch/step; K launches back to back, one event pair)"
-        else:
-            kernel_name = "d2d_step_prim_warp_kernel + d2d_plan_kernel + d2d_step_post_list_kernel" + \
-                          (" + d2d_oxford_kernel" if use_ox else "") + " (whole step timed)"
-        bytes_launch = algorithmic_bytes(N) * B
-        achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_config%d.json" % args.config)
-        if os.path.isfile(tpath) and cfg["params"]["planner"] == "NoMove":     # captured for the fused NoMove kernel only
-            try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        line = {
-            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["name"], "envs_per_gpu": B, "agents_per_env": N, "rays_per_env_step": n_rays,
-                       "planner": cfg["params"]["planner"], "gaze": args.gaze, "trackers": True, "auto_reset": True,
-                       "unique_worlds_per_gpu": int(unique), "world_gen_s": round(t_world, 2),
-                       "l2": "no rotation (--no-flush): state stays L2-resident" if args.no_flush else
-                             "inputs larger than L2: %d replica(s) of the batch stepped round robin, %.0f MB of state "
-                             "touched between two visits of a replica (L2 = 126 MB)" % (R, R * touched / 1e6),
-                       "timing": "K steps back to back as one CUDA graph (K step launches), one CUDA-event pair, "
-                                 "barrier + synchronize on both sides",
-                       "replicas": R, "burn_in_steps_per_replica": args.burn_in,
-                       "envs_per_block": env.cfg.envs_per_block, "parallelism": "env-sharded x%d" % world},
-            "rays_per_sec": value * n_rays,
-            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": 0 if use_ox else B * 8,
-                    "d2h_bytes_per_step": B * (1089 + 4 + 1) if mirror_bytes is None else int(round(B * 5 + mirror_bytes)),
-                    "steps": Ke,
-                    "transport": "cudaMemcpyAsync of the whole observation every step" if mirror_bytes is None else
-                                 "d2d_bind_host_mirror: kernels store changed observation bytes + yaw + done straight into "
-                                 "the pinned host buffers (bytes counted on the device, mean per step, this rank)",
-                    "full_copy": {"value": world * B * Ke / (e2e_copy_ms_max * 1e-3), "d2h_bytes_per_step": B * (1089 + 4 + 1)}},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "bytes_per_env_step": algorithmic_bytes(N),
-                         "kernel": kernel_name, "kernel_ms": kern_ms},
-            "repeat_ms_per_step": repeats,
-            "per_step_events": {"what": "same step, one launch at a time: CUDA events around every step, 256 MiB L2 flush "
-                                        "(untimed) in between; includes the event / launch gap of each step",
-                                "steps": int(Kp), "ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)),
-                                                                     float(step_ms.max())],
-                                "value": world * B / (float(np.mean(step_ms)) * 1e-3)},
-            "wall_s_timed_region": wall,
-            "episode_stats": {n: int(v) for n, v in zip(
-                ["env_steps", "episodes", "success", "static_collision", "dynamic_collision", "freezing", "dead_lock",
-                 "flight_steps", "grid_discovered", "agents_tracked", "tracked_steps", "plans", "plan_failures", "replans"],
-                stats.tolist()[:14])},
-        }
+        out = {"metric": METRIC, "value": line["value"], "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": line["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+        out.update({k: v for k, v in line.items() if k not in out})
+        if inv is not None:
+            out["shard_invariant"] = inv
+        if workloads:
+            out["workloads"] = workloads
         if not args.no_cpu_baseline and world == 1:
             import oracle
             oracle.build()
             cores = len(os.sched_getaffinity(0))
             # bounded sample of the same workload, sized for ~10 s of CPU work from a short calibration run
-            n_envs = min(B, 4096)
+            pk = cfg["params"]
+            n_envs = min(cfg["envs"], 4096)
+            use_ox = cfg["gaze"] == "Oxford"
             v0, dt0 = cpu_port_run(pk, n_envs, 20, cores, oxford=use_ox)
             steps_c = int(min(20000, max(50, 25.0 * v0 / n_envs)))   # the 20-step calibration under-reads the rate ~2x
             v, dt = cpu_port_run(pk, n_envs, steps_c, cores, oxford=use_ox)
-            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": "%d envs x %d steps of the same workload (%.1f s)" % (n_envs, steps_c, dt)}
-        emit(line)
-    del graph
-    for e in envs:
-        e.close()
+            out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                   "sample": "%d envs x %d steps of the same workload, auto-reset on (%.1f s)" % (n_envs, steps_c, dt)}
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 

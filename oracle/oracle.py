@@ -97,6 +97,16 @@ def lib():
         L.d2do_run_many_oxford.argtypes = [_P(_P(Env)), C.c_int, C.c_int]
         L.d2do_run_many_oxford.restype = C.c_int64
         L.d2do_set_rvo.argtypes = [_P(Env), _P(C.c_double), _P(C.c_double), C.c_int]
+        L.d2do_snapshot.argtypes = [_P(Env)]
+        L.d2do_snapshot.restype = C.c_void_p
+        L.d2do_snapshot_free.argtypes = [C.c_void_p]
+        L.d2do_restore.argtypes = [_P(Env), C.c_void_p]
+        L.d2do_step_batch.argtypes = [_P(_P(Env)), _P(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.d2do_step_batch.restype = C.c_int64
+        L.d2do_gather.argtypes = [_P(_P(Env)), C.c_int] + [C.c_void_p] * 14
+        L.d2do_run_batch.argtypes = [_P(_P(Env)), _P(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.d2do_run_batch.restype = C.c_int64
+        L.d2do_gather.restype = None
         L.d2do_sizeof_params.restype = C.c_size_t
         L.d2do_sizeof_env.restype = C.c_size_t
         assert L.d2do_sizeof_params() == C.sizeof(Params), (L.d2do_sizeof_params(), C.sizeof(Params))
@@ -251,3 +261,103 @@ class OracleEnv(object):
             self.close()
         except Exception:
             pass
+
+
+POLICY = {"scripted": -1, "NoControl": 0, "Rotating": 1, "LookAhead": 2, "LookGoal": 3, "Oxford": 4}
+
+
+class OracleBatch(object):
+    """B oracle envs stepped side by side with a CUDA batch (full-batch parity tests, mismatch campaigns).
+
+    `envs` are OracleEnv objects in their INITIAL state (world, pose, rng, rvo already set): a snapshot of each is
+    kept so that `step(auto_reset=True)` mirrors the batched env's auto-reset (an env whose previous step returned
+    done is re-initialised before it plans / steps).  Slices of the batch run on a thread pool (ctypes drops the GIL);
+    `gather` packs the compared outputs into batch arrays in C."""
+
+    INT_FIELDS = ("collision_flag", "dead_lock_flag", "freezing_flag", "done", "state_machine", "fail_count", "steps",
+                  "tracker_buffer_count", "tracker_buffer_ts", "traj_len", "replan", "plan_ok")
+
+    def __init__(self, envs, threads=None):
+        from concurrent.futures import ThreadPoolExecutor
+        self.L = lib()
+        self.envs = list(envs)
+        self.B = len(self.envs)
+        self.n = self.envs[0].n
+        self.params = self.envs[0]._params
+        self._ptrs = (_P(Env) * self.B)(*[e._ptr for e in self.envs])
+        self._snaps = (C.c_void_p * self.B)(*[self.L.d2do_snapshot(e._ptr) for e in self.envs])
+        self.threads = max(1, min(threads or len(os.sched_getaffinity(0)), self.B))
+        self._pool = ThreadPoolExecutor(self.threads)
+        b = np.linspace(0, self.B, self.threads + 1).astype(int)
+        self._slices = [(int(b[i]), int(b[i + 1])) for i in range(self.threads) if b[i + 1] > b[i]]
+
+    def _off(self, arr, i0, ctype):
+        return C.cast(C.addressof(arr) + i0 * C.sizeof(ctype), C.POINTER(ctype))
+
+    def step(self, actions=None, policy="scripted", auto_reset=True):
+        """Steps every env once; returns (applied actions [B] float64, number of envs that reported done)."""
+        pol = POLICY[policy] if isinstance(policy, str) else int(policy)
+        acts = None
+        if pol < 0:
+            acts = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.B)
+        out = np.empty(self.B, dtype=np.float64)
+
+        def run(sl):
+            i0, i1 = sl
+            return self.L.d2do_step_batch(self._off(self._ptrs, i0, _P(Env)), self._off(self._snaps, i0, C.c_void_p),
+                                          i1 - i0, None if acts is None else acts[i0:].ctypes.data, 1 if auto_reset else 0,
+                                          pol, out[i0:].ctypes.data)
+        dones = sum(self._pool.map(run, self._slices))
+        return out, int(dones)
+
+    def run(self, steps, actions=None, policy="scripted", auto_reset=True):
+        """`steps` steps of every env with the step loop inside C (one call per thread): the timed CPU-baseline loop.
+        actions: [steps, B] float64 when policy is "scripted".  Returns the number of done reports."""
+        pol = POLICY[policy] if isinstance(policy, str) else int(policy)
+        parts = []
+        if pol < 0:
+            acts = np.asarray(actions, dtype=np.float64).reshape(steps, self.B)
+            parts = [np.ascontiguousarray(acts[:, i0:i1]) for i0, i1 in self._slices]
+
+        def go(j):
+            i0, i1 = self._slices[j]
+            return self.L.d2do_run_batch(self._off(self._ptrs, i0, _P(Env)), self._off(self._snaps, i0, C.c_void_p), i1 - i0,
+                                         int(steps), parts[j].ctypes.data if parts else None, 1 if auto_reset else 0, pol)
+        return int(sum(self._pool.map(go, range(len(self._slices)))))
+
+    def gather(self, trackers=True, rvo=False):
+        B, n = self.B, max(self.n, 1)
+        p = self.params
+        cells, L = p.gw * p.gh, p.local * p.local
+        o = {"belief": np.empty((B, p.gw, p.gh), np.uint8), "hit": np.empty((B, n), np.int8),
+             "local_map": np.empty((B, p.local, p.local), np.uint8), "ints": np.empty((B, 12), np.int32),
+             "state": np.empty((B, 5), np.float64), "yaw_angle": np.empty((B,), np.float32),
+             "agent_pos": np.empty((B, n, 2), np.float64), "agent_pref": np.empty((B, n, 2), np.float64)}
+        if trackers:
+            o.update(tracker_active=np.empty((B, n), np.uint8), tracker_ts=np.empty((B, n), np.int64),
+                     tracker_radius=np.empty((B, n), np.float64), tracker_mu=np.empty((B, n, 4), np.float64),
+                     tracker_sigma=np.empty((B, n, 16), np.float64))
+        if rvo:
+            o["agent_vel"] = np.empty((B, n, 2), np.float64)
+        order = ["belief", "hit", "local_map", "ints", "state", "yaw_angle", "agent_pos", "agent_pref", "tracker_active",
+                 "tracker_ts", "tracker_radius", "tracker_mu", "tracker_sigma", "agent_vel"]
+
+        def run(sl):
+            i0, i1 = sl
+            args = [(o[k][i0:].ctypes.data if k in o else None) for k in order]
+            self.L.d2do_gather(self._off(self._ptrs, i0, _P(Env)), i1 - i0, *args)
+        list(self._pool.map(run, self._slices))
+        for j, name in enumerate(self.INT_FIELDS):
+            o[name] = o["ints"][:, j]
+        for j, name in enumerate(("drone_x", "drone_y", "drone_yaw", "drone_vx", "drone_vy")):
+            o[name] = o["state"][:, j]
+        return o
+
+    def close(self):
+        if self._snaps is not None:
+            for s in self._snaps:
+                self.L.d2do_snapshot_free(s)
+            self._snaps = None
+            self._pool.shutdown()
+            for e in self.envs:
+                e.close()

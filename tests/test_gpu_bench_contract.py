@@ -25,7 +25,10 @@ def test_bench_prints_contract_line():
     assert d["metric"] == "env-steps/sec" and d["steps"] == 12 and d["n_gpus"] == 1 and d["dtype"] == "f64"
     assert d["gpu_launches"] == 12 and d["value"] > 0 and d["vs_baseline"] is None and d["scaling"] == "weak"
     assert abs(d["value"] - 512 / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
-    assert d["config"]["replicas"] >= 2 and "workload" in d["config"]          # a small batch needs replicas to stay L2-cold
+    assert d["method"]["replicas"] >= 2 and "workload" in d["config"] and "l2" in d["config"]   # a small batch needs replicas to stay L2-cold
+    assert d["method"]["graph_replays"] >= 7 and d["method"]["timed_region_ms_this_rank"] >= 50.0
+    assert len(d["per_rank"]) == 1 and abs(d["per_rank"][0]["ms_per_step_median"] - d["ms_per_step"]) < 1e-12
+    assert "workloads" not in d                                              # only the default (config 2, full size) run carries them
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 512 * 8 and e["d2h_bytes_per_step"] > 0
     rf = d["roofline"]

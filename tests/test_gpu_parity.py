@@ -104,7 +104,15 @@ def test_cuda_matches_reference_golden_nomove(path):
     dict(static_map="maps/empty_map.npy", agent_number=6, agent_radius=10, agent_max_speed=40, B=11, steps=60, epb=4),
     dict(static_map="maps/empty_map.npy", agent_number=6, agent_radius=10, agent_max_speed=40, B=18, steps=40, epb=16),
     dict(static_map="maps/empty_map.npy", agent_number=3, agent_radius=10, agent_max_speed=40, B=1, steps=40, epb=8),
-], ids=["cfg2_empty", "cfg4_obstacle", "cfg3_random0", "cfg5_shaped", "ragged7", "ragged11", "ragged18", "single"])
+    # the same seeded batches on the DEFAULT kernel (envs_per_block = 0: d2d_step_fused_warp_kernel, the one bench.py times)
+    dict(static_map="maps/empty_map.npy", agent_number=10, agent_radius=15, agent_max_speed=20, B=96, steps=160, epb=0),
+    dict(static_map="maps/obstacle_map.npy", agent_number=10, agent_radius=10, agent_max_speed=20, B=40, steps=100, epb=0),
+    dict(static_map="maps/random_map_0.npy", agent_number=20, agent_radius=15, agent_max_speed=40, B=24, steps=40, epb=0),
+    dict(static_map="maps/shaped_obstacle_map.npy", agent_number=50, agent_radius=10, agent_max_speed=40, B=20, steps=40, epb=0),
+    dict(static_map="maps/empty_map.npy", agent_number=6, agent_radius=10, agent_max_speed=40, B=11, steps=60, epb=0),
+    dict(static_map="maps/empty_map.npy", agent_number=3, agent_radius=10, agent_max_speed=40, B=1, steps=40, epb=0),
+], ids=["cfg2_empty", "cfg4_obstacle", "cfg3_random0", "cfg5_shaped", "ragged7", "ragged11", "ragged18", "single",
+        "cfg2_empty_warp", "cfg4_obstacle_warp", "cfg3_random0_warp", "cfg5_shaped_warp", "ragged11_warp", "single_warp"])
 def test_cuda_matches_oracle_batch_nomove(cfg):
     """Seeded batch (world generation on the host, random actions from the Oxford action set) stepped by the CUDA
     path and by the oracle; every field compared every step; envs keep stepping after done (auto_reset off)."""

@@ -68,7 +68,8 @@ def test_cuda_matches_reference_golden_episode(path):
     dict(static_map="maps/obstacle_map.npy", agent_number=10, agent_radius=10, agent_max_speed=20, drone_max_speed=40, B=14, steps=200),
     dict(static_map="maps/empty_map.npy", agent_number=30, agent_radius=10, agent_max_speed=40, drone_max_speed=20, B=9, steps=200),
 ], ids=["cfg1_like", "cfg4_obstacle", "speed20_crowded"])
-def test_cuda_matches_oracle_primitive_oxford_with_auto_reset(cfg):
+@pytest.mark.parametrize("epb", [4, 0], ids=["block4", "warp"])
+def test_cuda_matches_oracle_primitive_oxford_with_auto_reset(cfg, epb):
     """Seeded batch, Primitive planner + Oxford policy on the device vs the oracle, with auto-reset: when an episode
     ends the oracle env and its policy state are rebuilt from the same world (what the reference's reset() does)."""
     from gym_drone2d_activeperception_b200.params import Params
@@ -78,7 +79,7 @@ def test_cuda_matches_oracle_primitive_oxford_with_auto_reset(cfg):
                agent_number=cfg["agent_number"], agent_radius=cfg["agent_radius"], agent_max_speed=cfg["agent_max_speed"],
                drone_max_speed=cfg["drone_max_speed"])
     worlds = generate_worlds(p, 500 + np.arange(B))
-    env = _env(p, B, worlds, auto_reset=True, oxford=True, envs_per_block=4)
+    env = _env(p, B, worlds, auto_reset=True, oxford=True, envs_per_block=epb)   # 0: d2d_step_prim_warp_kernel (default)
     n = env.num_agents
     oracles = [util.oracle_env_from_world(p, worlds, i) for i in range(B)]
     episodes = 0

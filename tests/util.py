@@ -79,3 +79,73 @@ def rel_err(a, b):
     if a.size == 0:
         return 0.0
     return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
+
+
+# ------------------------------------------------------------------------------------------ full-batch parity helpers
+DISCRETE_FIELDS = ("belief", "hit", "local_map", "collision_flag", "dead_lock_flag", "freezing_flag", "done",
+                   "state_machine", "fail_count", "steps", "tracker_buffer_count", "tracker_buffer_ts", "yaw_angle")
+STATE_FIELDS = ("drone_x", "drone_y", "drone_yaw", "drone_vx", "drone_vy", "agent_pos", "agent_pref")
+
+
+def oracle_batch(p, worlds, poses=None, threads=None):
+    """oracle.OracleBatch over every env of `worlds` (initial state; optional externally set drone poses [B,3])."""
+    import oracle
+    B = worlds["drone_pose"].shape[0]
+    envs = [oracle_env_from_world(p, worlds, i, drone=None if poses is None else poses[i]) for i in range(B)]
+    return oracle.OracleBatch(envs, threads=threads)
+
+
+def gpu_fields(env, names):
+    import torch
+    torch.cuda.synchronize()
+    return {k: env.buffer(k).cpu().numpy() for k in names}
+
+
+def batch_mismatch(h, o, n, trackers=True, planner=False):
+    """Per-env mismatch masks between the CUDA batch (h: dict of host arrays named like d2d_get_buffer) and the oracle
+    batch (o: OracleBatch.gather()).  Returns (discrete: dict name -> bool[B], rel: dict name -> float[B]).
+    Discrete fields are compared bit for bit; continuous ones by max |a-b| / max(1, |b|) per env (absolute below 1:
+    positions are O(100), velocities O(10); the north-star bar is 1e-9 relative)."""
+    B = o["done"].shape[0]
+    d, r = {}, {}
+    flat = lambda a: np.asarray(a).reshape(B, -1)
+    d["belief"] = (flat(h["belief"]) != flat(o["belief"])).any(1)
+    d["hit"] = (flat(h["hit"])[:, :n] != flat(o["hit"])[:, :n]).any(1)
+    d["local_map"] = (flat(h["local_map"]) != flat(o["local_map"])).any(1)
+    d["yaw_angle"] = flat(h["yaw_angle"])[:, 0] != o["yaw_angle"]
+    for k in ("collision_flag", "dead_lock_flag", "freezing_flag", "done", "state_machine", "fail_count", "steps"):
+        d[k] = h[k].astype(np.int64) != o[k].astype(np.int64)
+    if planner:
+        d["traj_len"] = (h["traj_nseg"].astype(np.int64) * planner - h["traj_cursor"]) != o["traj_len"]
+        d["plan_ok"] = h["plan_ok"].astype(np.int64) != o["plan_ok"]
+        d["replan"] = h["replan"].astype(np.int64) != o["replan"]
+
+    def rel(a, b):
+        a, b = flat(a).astype(np.float64), flat(b).astype(np.float64)
+        return (np.abs(a - b) / np.maximum(1.0, np.abs(b))).max(1) if a.shape[1] else np.zeros(B)
+    for k in ("drone_x", "drone_y", "drone_yaw", "drone_vx", "drone_vy"):
+        r[k] = rel(h[k], o[k])
+    r["agent_pos"] = rel(h["agent_pos"][:, :n], o["agent_pos"][:, :n])
+    r["agent_pref"] = rel(h["agent_pref"][:, :n], o["agent_pref"][:, :n])
+    if trackers:
+        act = o["tracker_active"][:, :n].astype(bool)
+        d["tracker_active"] = (h["tracker_active"][:, :n].astype(bool) != act).any(1)
+        d["tracker_ts"] = ((h["tracker_ts"][:, :n].astype(np.int64) != o["tracker_ts"][:, :n]) & act).any(1)
+        d["tracker_radius"] = (h["tracker_radius"][:, :n] != o["tracker_radius"][:, :n]).any(1)
+        d["tracker_buffer"] = (h["tracker_buffer_count"].astype(np.int64) != o["tracker_buffer_count"]) | \
+                              (h["tracker_buffer_ts"].astype(np.int64) != o["tracker_buffer_ts"])
+        mu_h, mu_o = h["tracker_mu"][:, :n], o["tracker_mu"][:, :n]
+        sg_h, sg_o = h["tracker_sigma"][:, :n].reshape(B, n, 16), o["tracker_sigma"][:, :n]
+        em = np.abs(mu_h - mu_o) / np.maximum(1.0, np.abs(mu_o))
+        es = np.abs(sg_h - sg_o) / np.maximum(1.0, np.abs(sg_o))
+        r["tracker_mu"] = np.where(act[:, :, None], em, 0.0).reshape(B, -1).max(1) if n else np.zeros(B)
+        r["tracker_sigma"] = np.where(act[:, :, None], es, 0.0).reshape(B, -1).max(1) if n else np.zeros(B)
+    return d, r
+
+
+BATCH_FIELDS = ["belief", "hit", "local_map", "yaw_angle", "collision_flag", "dead_lock_flag", "freezing_flag", "done",
+                "state_machine", "fail_count", "steps", "drone_x", "drone_y", "drone_yaw", "drone_vx", "drone_vy", "agent_pos",
+                "agent_pref"]
+TRACKER_FIELDS = ["tracker_active", "tracker_ts", "tracker_radius", "tracker_mu", "tracker_sigma", "tracker_buffer_count",
+                  "tracker_buffer_ts"]
+PLANNER_FIELDS = ["traj_nseg", "traj_cursor", "plan_ok", "replan"]
