@@ -2,13 +2,8 @@
 
 template <int E>
 static int launch_pre(d2d_handle *h, cudaStream_t st) {
-    static bool attr_done[64] = {false};
-    const int dev = h->cfg.device;
-    if (!attr_done[dev & 63]) {
-        cudaError_t ce = cudaFuncSetAttribute(d2d_step_pre_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute(pre): ") + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
-        attr_done[dev & 63] = true;
-    }
+    const int rc = ensure_smem_attr(h, (const void *)d2d_step_pre_kernel<E>, "pre");
+    if (rc != D2D_OK) return rc;
     d2d_step_pre_kernel<E><<<(h->B + E - 1) / E, h->T, h->smem_pre, st>>>(h->P);
     h->launches++;
     return D2D_OK;
@@ -16,16 +11,11 @@ static int launch_pre(d2d_handle *h, cudaStream_t st) {
 
 template <int WPB>
 static int launch_prim_warp(d2d_handle *h, const double *actions, cudaStream_t st) {
-    static bool attr_done[64] = {false};
-    const int dev = h->cfg.device;
     const size_t smem = (size_t)WPB * d2d_warp_slice_bytes(h->NP, h->HW, d2d_prim_warp_extra(h->NP));
     if (smem > 227 * 1024) { h->err = "warp-per-env Primitive kernel: shared memory per block exceeds 227 KB"; return D2D_ERR_INVALID; }
-    if (!attr_done[dev & 63]) {
-        cudaError_t ce = cudaFuncSetAttribute(d2d_step_prim_warp_kernel<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(d2d_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
-        attr_done[dev & 63] = true;
-    }
+    int rca = ensure_smem_attr(h, (const void *)d2d_step_prim_warp_kernel<WPB>, "prim warp");
+    if (rca == D2D_OK) rca = ensure_smem_attr(h, (const void *)d2d_plan_kernel, "plan");
+    if (rca != D2D_OK) return rca;
     h->P.use_parity = 1;
     d2d_step_prim_warp_kernel<WPB><<<(h->B + WPB - 1) / WPB, WPB * 32, smem, st>>>(h->P, actions);
     const int pgrid = h->B < D2D_PLAN_SLOTS ? h->B : D2D_PLAN_SLOTS;
@@ -47,13 +37,8 @@ static int step_primitive(d2d_handle *h, const double *actions, cudaStream_t st)
     }
     if (rc != D2D_OK) return rc;
     {
-        static bool attr_done[64] = {false};
-        const int dev = h->cfg.device;
-        if (!attr_done[dev & 63]) {
-            cudaError_t ce = cudaFuncSetAttribute(d2d_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            if (ce != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute(plan): ") + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
-            attr_done[dev & 63] = true;
-        }
+        const int rca = ensure_smem_attr(h, (const void *)d2d_plan_kernel, "plan");
+        if (rca != D2D_OK) return rca;
         const int grid = h->B < D2D_PLAN_SLOTS ? h->B : D2D_PLAN_SLOTS;
         d2d_plan_kernel<<<grid, D2D_PLAN_THREADS2, h->smem_plan, st>>>(h->P);
         h->launches++;

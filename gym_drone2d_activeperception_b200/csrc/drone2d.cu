@@ -46,7 +46,18 @@ struct d2d_handle {
     uint8_t *mir_lm = nullptr; float *mir_yaw = nullptr; uint8_t *mir_done = nullptr;
     bool mir_stale = true;
     size_t smem_pre = 0, smem_plan = 0;
+    std::vector<const void *> attr_funcs;   // kernels whose dynamic shared-memory limit this handle has raised
 };
+
+// Raises the dynamic shared-memory limit of `func` to 227 KB once per handle.  Per handle, not per process: a handle is
+// driven by one thread at a time (drone2d.h), so no state is shared between threads that drive distinct handles.
+static int ensure_smem_attr(d2d_handle *h, const void *func, const char *what) {
+    for (const void *f : h->attr_funcs) if (f == func) return D2D_OK;
+    cudaError_t ce = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (ce != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute(") + what + "): " + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
+    h->attr_funcs.push_back(func);
+    return D2D_OK;
+}
 
 static thread_local std::string g_create_err;
 
@@ -621,13 +632,8 @@ extern "C" int d2d_set_drone_pose(d2d_handle *h, const double *pose_host, void *
 // ------------------------------------------------------------------------------------------ step
 template <int E>
 static int launch_fused(d2d_handle *h, const double *actions, cudaStream_t st) {
-    static bool attr_done[64] = {false};
-    const int dev = h->cfg.device;
-    if (!attr_done[dev & 63]) {
-        cudaError_t ce = cudaFuncSetAttribute(d2d_step_fused_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
-        attr_done[dev & 63] = true;
-    }
+    const int rc = ensure_smem_attr(h, (const void *)d2d_step_fused_kernel<E>, "fused");
+    if (rc != D2D_OK) return rc;
     const int grid = (h->B + E - 1) / E;
     d2d_step_fused_kernel<E><<<grid, h->T, h->smem_step, st>>>(h->P, actions);
     h->launches++;
@@ -636,15 +642,10 @@ static int launch_fused(d2d_handle *h, const double *actions, cudaStream_t st) {
 
 template <int WPB, int MINB, bool ILP2>
 static int launch_fused_warp(d2d_handle *h, const double *actions, cudaStream_t st) {
-    static bool attr_done[64] = {false};
-    const int dev = h->cfg.device;
     const size_t smem = (size_t)WPB * d2d_warp_slice_bytes(h->NP, h->HW, 0);
     if (smem > 227 * 1024) { h->err = "warp-per-env kernel: shared memory per block exceeds 227 KB"; return D2D_ERR_INVALID; }
-    if (!attr_done[dev & 63]) {
-        cudaError_t ce = cudaFuncSetAttribute(d2d_step_fused_warp_kernel<WPB, MINB, ILP2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (ce != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce); return D2D_ERR_CUDA; }
-        attr_done[dev & 63] = true;
-    }
+    const int rc = ensure_smem_attr(h, (const void *)d2d_step_fused_warp_kernel<WPB, MINB, ILP2>, "fused warp");
+    if (rc != D2D_OK) return rc;
     d2d_step_fused_warp_kernel<WPB, MINB, ILP2><<<(h->B + WPB - 1) / WPB, WPB * 32, smem, st>>>(h->P, actions);
     h->launches++;
     return D2D_OK;
@@ -661,13 +662,9 @@ extern "C" int d2d_step(d2d_handle *h, const double *actions_dev, void *stream) 
     int rc;
     if (h->P.motion_rvo) {      // RVO.RVO_update (drone_v2.py:169-171) for every env, before Agent.step
         if (!h->rvo_set) { h->err = "motion_profile = RVO: d2d_set_rvo must provide velocities and obstacles"; return D2D_ERR_STATE; }
-        static bool attr_done[64] = {false};
-        const int dev = h->cfg.device;
         const size_t sm = d2d_rvo_smem_bytes(h->N);
-        if (!attr_done[dev & 63]) {
-            CUDA_TRY(h, cudaFuncSetAttribute(d2d_rvo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_done[dev & 63] = true;
-        }
+        const int rca = ensure_smem_attr(h, (const void *)d2d_rvo_kernel, "rvo");
+        if (rca != D2D_OK) return rca;
         d2d_rvo_kernel<<<h->B, D2D_RVO_WARPS * 32, sm, st>>>(h->P);
         h->launches++;
     }

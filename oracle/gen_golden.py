@@ -107,6 +107,18 @@ def main():
             continue
         r = rr.run_episode(800, policy="Oxford", planner="Primitive", stop_on_done=True, record_oxford=True, **kw)
         save(name, r, WORLD + STEP_CORE + TRACK + PLAN + ["ox_last"])
+    # --- Owl gaze policy (yaw_planner.py:151-222) with the reference's call pattern (class object as instance, experiment.py:33-34)
+    owl = [
+        ("owl_s3", dict(map_id=3, agent_number=8)),
+        ("owl_crowd_s7", dict(map_id=7, agent_number=20, agent_radius=15, agent_max_speed=20)),
+        ("owl_obstacle_s5", dict(map_id=5, agent_number=30, static_map="maps/obstacle_map.npy")),
+        ("owl_speed20_s9", dict(map_id=9, agent_number=10, drone_max_speed=20)),
+    ]
+    for name, kw in owl:
+        if only not in name:
+            continue
+        r = rr.run_episode(800, policy="Owl", planner="Primitive", gaze_method="Owl", stop_on_done=True, **kw)
+        save(name, r, WORLD + STEP_CORE + TRACK + PLAN)
     # --- RVO motion profile (utils.py:299-460): agents avoid each other and the pillars; velocity is its own array
     rvo = [
         ("rvo_nomove_pillars_s3", dict(map_id=3, agent_number=6, pillar_number=2), 60, None, "NoMove"),

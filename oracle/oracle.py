@@ -59,6 +59,7 @@ class Env(C.Structure):
         ("meas", _P(C.c_double)),
         ("motion_rvo", C.c_int32), ("n_obs", C.c_int32), ("avel", _P(C.c_double)), ("obs", _P(C.c_double)),
         ("rvo_fallbacks", C.c_int64),
+        ("owl_U", C.c_double * 36), ("owl_q", C.c_int32), ("pad3", C.c_int32), ("owl_u", C.c_double),
     ]
 
 
@@ -90,6 +91,8 @@ def lib():
         L.d2do_step.restype = C.c_int
         L.d2do_oxford_plan.argtypes = [_P(Env)]
         L.d2do_oxford_plan.restype = C.c_double
+        L.d2do_owl_plan.argtypes = [_P(Env)]
+        L.d2do_owl_plan.restype = C.c_double
         L.d2do_policy_plan.argtypes = [_P(Env), C.c_int]
         L.d2do_policy_plan.restype = C.c_double
         L.d2do_run_many.argtypes = [_P(_P(Env)), C.c_int, C.c_int, _P(C.c_double)]
@@ -243,6 +246,10 @@ class OracleEnv(object):
     def oxford_plan(self):
         return float(lib().d2do_oxford_plan(self._ptr))
 
+    def owl_plan(self):
+        """Owl.plan (yaw_planner.py:191-222) with the class-object-as-instance call pattern of experiment.py:33-34"""
+        return float(lib().d2do_owl_plan(self._ptr))
+
     def policy_plan(self, kind):
         """kind: 0 NoControl, 1 Rotating, 2 LookAhead, 3 LookGoal (yaw_planner.py)"""
         return float(lib().d2do_policy_plan(self._ptr, int(kind)))
@@ -263,7 +270,7 @@ class OracleEnv(object):
             pass
 
 
-POLICY = {"scripted": -1, "NoControl": 0, "Rotating": 1, "LookAhead": 2, "LookGoal": 3, "Oxford": 4}
+POLICY = {"scripted": -1, "NoControl": 0, "Rotating": 1, "LookAhead": 2, "LookGoal": 3, "Oxford": 4, "Owl": 5}
 
 
 class OracleBatch(object):

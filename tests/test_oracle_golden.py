@@ -5,7 +5,7 @@ import pytest
 import util
 
 
-def _run_against_golden(g, use_oxford):
+def _run_against_golden(g, use_oxford, use_owl=False):
     import oracle
     p = util.params_from_golden(g)
     e = util.oracle_env_from_world(p, util.world_from_golden(g), 0)
@@ -19,6 +19,9 @@ def _run_against_golden(g, use_oxford):
             a = e.oxford_plan()
             assert a == g["action"][t], ("action", t)
             assert np.array_equal(e.ox_last, g["ox_last"][t]), ("oxford last_time_observed", t)
+        if use_owl:
+            a = e.owl_plan()
+            assert a == g["action"][t], ("owl action", t, a, g["action"][t])
         a = float(g["action"][t])
         d = e.step(a)
         assert np.array_equal(e.belief, g["belief"][t]), ("belief", t)
@@ -76,6 +79,15 @@ def test_oracle_matches_reference_nomove(path):
 def test_oracle_matches_reference_full_episode(path):
     """Primitive A* planner + Kalman trackers + Oxford gaze, whole episodes (config 1 of BASELINE.json among them)."""
     _run_against_golden(util.load_golden(path), use_oxford=True)
+
+
+@pytest.mark.parametrize("path", util.golden_files("owl_"), ids=lambda p: p.split("/")[-1][:-4])
+def test_oracle_matches_reference_owl_episode(path):
+    """Owl gaze policy (yaw_planner.py:151-222) driven the way experiment.py:33-34 drives it (class object as the instance):
+    every action of whole Primitive-planner episodes equals the reference's, bit for bit."""
+    g = util.load_golden(path)
+    assert len(set(np.round(g["action"], 6).tolist())) >= 5, "the fixture must exercise more than the NaN / queue paths"
+    _run_against_golden(g, use_oxford=False, use_owl=True)
 
 
 def test_config1_known_answer():

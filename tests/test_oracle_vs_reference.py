@@ -97,3 +97,24 @@ def test_scalar_gaze_policies_live(policy, kind):
         e.step(a)
         assert np.array_equal(e.belief, r["belief"][t]) and (e.c.x, e.c.y, e.c.yaw) == tuple(r["drone"][t]), t
     e.close()
+
+
+def test_owl_policy_live():
+    """Owl (yaw_planner.py:151-222) with the reference's real call pattern (experiment.py:33-34: the class object is the
+    instance, so the @classmethod helpers resolve): every action of a whole episode, bit for bit."""
+    from gym_drone2d_activeperception_b200.params import Params
+    kw = dict(planner="Primitive", map_id=21, agent_number=14, agent_radius=12, agent_max_speed=30, gaze_method="Owl")
+    r = ref_runner.run_episode(400, policy="Owl", stop_on_done=True, **kw)
+    P = r["params"]
+    p = Params(debug=False, **{k: P[k] for k in util.PARAM_KEYS if k in P}, init_pos=P["init_position"],
+               target_list=P["target_list"])
+    world = dict(agent_pos=r["agent_pos0"], agent_pref=r["agent_pref0"], agent_radius=r["agent_radius"],
+                 tracker_radius=r["tracker_radius"], gt_grid=r["gt_grid"], drone_pose=r["drone0"],
+                 agent_vel=r["agent_vel0"], obstacles=r["obstacles"])
+    e = util.oracle_env_from_world(p, world)
+    for t in range(len(r["done"])):
+        a = e.owl_plan()
+        assert a == r["action"][t], (t, a, r["action"][t])
+        e.step(a)
+        assert np.array_equal(e.belief, r["belief"][t]) and (e.c.x, e.c.y, e.c.yaw) == tuple(r["drone"][t]), t
+    e.close()
