@@ -8,7 +8,8 @@ LIB_PATH = os.path.join(HERE, "libdrone2d.so")
 
 MAX_TARGETS, MAX_U, MAX_SAMP, MAX_WAY, MAX_YAW = 8, 64, 32, 64, 16
 NUM_STATS = 16
-GAZE = {"NoControl": 0, "Rotating": 1, "LookAhead": 2, "LookGoal": 3}
+GAZE = {"NoControl": 0, "Rotating": 1, "LookAhead": 2, "LookGoal": 3, "Owl": 4}
+POLICY_OXFORD, POLICY_OWL, MAX_OWL_U = 1, 2, 32
 BELIEF_STRIDE = 2560
 STAT_NAMES = ["env_steps", "episodes", "success", "static_collision", "dynamic_collision", "freezing", "dead_lock",
               "flight_steps", "grid_discovered", "agents_tracked", "tracked_steps", "plans", "plan_failures", "replans",
@@ -31,6 +32,7 @@ class D2DConfig(C.Structure):
         ("t_samp", C.c_double * MAX_SAMP), ("t_samp2", C.c_double * MAX_SAMP),
         ("t_way", C.c_double * MAX_WAY), ("t_way2", C.c_double * MAX_WAY), ("t_way_x2", C.c_double * MAX_WAY),
         ("v_yaw_space", C.c_double * MAX_YAW),
+        ("n_owl_u", C.c_int32), ("owl_repeat", C.c_int32), ("owl_u_space", C.c_double * MAX_OWL_U),
     ]
 
 
@@ -40,7 +42,7 @@ class D2DBufferInfo(C.Structure):
 
 
 EXPORTS = ["d2d_version", "d2d_last_error", "d2d_create", "d2d_destroy", "d2d_set_world", "d2d_set_rng", "d2d_set_rvo", "d2d_reset", "d2d_step",
-           "d2d_step_host", "d2d_bind_host_mirror", "d2d_plan_oxford", "d2d_plan_gaze", "d2d_set_drone_pose", "d2d_get_buffer", "d2d_stats",
+           "d2d_step_host", "d2d_bind_host_mirror", "d2d_bind_host_io", "d2d_step_bound", "d2d_plan_oxford", "d2d_plan_gaze", "d2d_set_drone_pose", "d2d_get_buffer", "d2d_stats",
            "d2d_launch_count"]
 
 _lib = None
@@ -73,6 +75,8 @@ def load():
     L.d2d_step.argtypes = [vp, vp, vp]
     L.d2d_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.d2d_bind_host_mirror.argtypes = [vp, vp, vp, vp]
+    L.d2d_bind_host_io.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.d2d_step_bound.argtypes = [vp]
     L.d2d_plan_oxford.argtypes = [vp, vp, vp]
     L.d2d_plan_gaze.argtypes = [vp, C.c_int32, vp, vp]
     L.d2d_set_drone_pose.argtypes = [vp, vp, vp]

@@ -315,8 +315,8 @@ D2D_HD void d2d_sincos_small(d2d_dd d, d2d_dd *s, d2d_dd *c) {
     *c = dd_add_d(pc, 1.0);
 }
 
-// sin(a), cos(a) for |a| < 1e5, each rounded to nearest from a double-double
-D2D_HD_NOINLINE void d2d_sincos(double a, double *sn, double *cs) {
+// sin(a), cos(a) for |a| < 1e5 as double-doubles (relative error ~2^-100)
+D2D_HD void d2d_sincos_dd(double a, d2d_dd *sn, d2d_dd *cs) {
     int quad;
     d2d_dd r = d2d_rem_pio2(a, &quad);
     const bool neg = r.h < 0;
@@ -335,12 +335,33 @@ D2D_HD_NOINLINE void d2d_sincos(double a, double *sn, double *cs) {
         S = dd_add(dd_mul(Sj, cd), dd_mul(Cj, sd));
         Cc = dd_add(dd_mul(Cj, cd), dd_neg(dd_mul(Sj, sd)));
     }
-    double s = S.h + S.l, c = Cc.h + Cc.l;
-    if (neg) s = -s;
+    if (neg) S = dd_neg(S);
     switch (quad) {
-        case 0: *sn = s; *cs = c; break;
-        case 1: *sn = c; *cs = -s; break;
-        case 2: *sn = -s; *cs = -c; break;
-        default: *sn = -c; *cs = s; break;
+        case 0: *sn = S; *cs = Cc; break;
+        case 1: *sn = Cc; *cs = dd_neg(S); break;
+        case 2: *sn = dd_neg(S); *cs = dd_neg(Cc); break;
+        default: *sn = dd_neg(Cc); *cs = S; break;
     }
 }
+
+// sin(a), cos(a) for |a| < 1e5, each rounded to nearest from a double-double
+D2D_HD_NOINLINE void d2d_sincos(double a, double *sn, double *cs) {
+    d2d_dd S, C;
+    d2d_sincos_dd(a, &S, &C);
+    *sn = S.h + S.l;
+    *cs = C.h + C.l;
+}
+
+// atan2(y, x) rounded to nearest: the library value t0 (CUDA: <= 2 ulp; glibc on the host) plus one Newton step
+// tan(theta - t0) = (y cos t0 - x sin t0) / (x cos t0 + y sin t0) with sin / cos of t0 in double-double, so the correction is
+// known to ~2^-48 of itself (2^-100 of the result).  The gaze policies compare bearings against bin / wedge boundaries
+// (yaw_planner.py:144-189) and a drone on the integer lattice produces bearings that sit exactly on them (atan2(a, a)).
+D2D_HD double d2d_atan2_refine(double t0, double y, double x) {
+    if (!(fabs(t0) <= 4.0) || t0 == 0.0 || !(fabs(x) <= 1e300) || !(fabs(y) <= 1e300)) return t0;   // NaN, signed zero, infinities
+    d2d_dd S, C;
+    d2d_sincos_dd(t0, &S, &C);
+    const d2d_dd num = dd_add(dd_mul_d(C, y), dd_neg(dd_mul_d(S, x)));
+    const d2d_dd den = dd_add(dd_mul_d(C, x), dd_mul_d(S, y));
+    return t0 + num.h / den.h;
+}
+D2D_HD_NOINLINE double d2d_atan2_cr(double y, double x) { return d2d_atan2_refine(atan2(y, x), y, x); }

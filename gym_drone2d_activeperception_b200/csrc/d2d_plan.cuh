@@ -1117,8 +1117,8 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
 
 // ------------------------------------------------------------------------------------------ scalar gaze policies
 // NoControl / Rotating / LookAhead / LookGoal (yaw_planner.py:10-39, 136-142, 225-255), one warp per env.
-// atan2 is CUDA's (<= 2 ulp; glibc's differs at the ulp level): actions are held to 1e-12, not bit-exact, unless they
-// saturate at +-1 (the common case).
+// atan2 is d2d_atan2_cr (correctly rounded; glibc's is < 1 ulp and differs from it on ~0.09 % of inputs by one ulp): actions
+// are held to 1e-12, and are bit-exact wherever glibc rounds correctly or the action saturates at +-1 (the common case).
 __device__ __forceinline__ double d2d_turn_towards(const DevP &P, double target_yaw, double yaw) {
     const double m = P.max_yaw_speed;
     double v = (target_yaw - yaw) / P.dt;
@@ -1140,7 +1140,7 @@ __global__ void __launch_bounds__(128) d2d_gaze_kernel(const DevP P, int policy,
     else if (policy == D2D_GAZE_LOOKAHEAD) {
         const double vx = fresh ? 0.0 : P.rec[e].vx, vy = fresh ? 0.0 : P.rec[e].vy;
         if (!(vy == 0.0 && vx == 0.0)) {
-            const double ty = d2d_pymod(atan2(-vy, vx) * RAD2DEG, 360.0);
+            const double ty = d2d_pymod(d2d_atan2_cr(-vy, vx) * RAD2DEG, 360.0);
             a = d2d_turn_towards(P, ty, P.rec[e].yaw);
         }
     } else if (policy == D2D_GAZE_LOOKGOAL) {
@@ -1160,9 +1160,155 @@ __global__ void __launch_bounds__(128) d2d_gaze_kernel(const DevP P, int policy,
             for (int off = 16; off > 0; off >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, off));
             double xl, yl;
             d2d_waypoint_pos(P, e, cursor + (first < len ? first : len - 1), xl, yl);
-            const double ty = d2d_pymod(atan2(-(yl - P.rec[e].py), xl - P.rec[e].px) * RAD2DEG, 360.0);
+            const double ty = d2d_pymod(d2d_atan2_cr(-(yl - P.rec[e].py), xl - P.rec[e].px) * RAD2DEG, 360.0);
             a = d2d_turn_towards(P, ty, P.rec[e].yaw);
         }
     }
     if (lane == 0) actions_out[e] = a;
+}
+
+
+// ------------------------------------------------------------------------------------------ Owl  yaw_planner.py:144-222
+// Owl.plan for every env, called the way experiment.py:33-34 calls it (the class object is the instance).  One warp per env:
+//   queue    a chosen action is repeated owl_repeat (= int(0.8 // dt) - 1) more times before the policy plans again (:193-196)
+//   update_U the 36 direction-uncertainty bins move by -dp.d_i / depth + (l_hit inside the view wedge | l_miss outside),
+//            clamped to [0, 1] (:178-185); lanes own bins
+//   bearings d_g (goal), d_v (velocity; NaN for a drone at rest, which makes every cost NaN and argmin return 0),
+//            d_o (k-th ACTIVE tracker), all through d2d_atan2_cr
+//   costs    lane i owns candidate yaw rate u_space[i]: f = [G*(1-U), |v/10|^2*G*(1-U), sum_k ratio_k*G, U(yaw), |rad|],
+//            cost = f . lamb as a sequential FMA chain (ndarray.dot on the reference image), first-minimum / first-NaN argmin.
+//            zip(d_o, trackers) pairs the k-th active tracker's bearing with trackers[k] (:212-213): reproduced.
+// Discrete output (one of 20 actions): bit-exact vs the reference wherever glibc's atan2 is correctly rounded; pow(x, 2) is x*x.
+#define D2D_OWL_WARPS 4
+#define D2D_OWL_MAX_TRK 480
+
+__device__ __forceinline__ double d2d_owl_between(double a1m, double a2m) {   // angle_between on `% 360`-reduced operands
+    const double diff = fabs(a1m - a2m), o = 360.0 - diff;
+    if (diff != diff) return diff;                                           // np.minimum propagates NaN
+    return diff <= o ? diff : o;
+}
+__device__ __forceinline__ double d2d_owl_G(double theta, double theta_h, double hp, double hm) {   // :172-177
+    const double t = d2d_pymod(theta, 360.0);
+    if (d2d_owl_between(t, 0.0) <= theta_h * 0.5) return 0.0;
+    return (d2d_owl_between(t, hp) * D2D_DEG2RAD) * (d2d_owl_between(t, hm) * D2D_DEG2RAD);
+}
+__device__ __forceinline__ double d2d_owl_U(const double *U, double theta) {  // :186-189
+    const double t = d2d_pymod(theta, 360.0);
+    double bv = d2d_owl_between(0.0, t);
+    if (bv != bv) return U[0];
+    int best = 0;
+#pragma unroll 1
+    for (int i = 1; i < D2D_OWL_BINS; i++) {
+        const double v = d2d_owl_between(10.0 * (double)i, t);
+        if (v < bv) { bv = v; best = i; }
+    }
+    return U[best];
+}
+
+__global__ void __launch_bounds__(D2D_OWL_WARPS * 32) d2d_owl_kernel(const DevP P, double *__restrict__ actions_out) {
+    __shared__ double U_s[D2D_OWL_WARPS][D2D_OWL_BINS];
+    __shared__ double do_s[D2D_OWL_WARPS][D2D_OWL_MAX_TRK];      // bearing of the k-th active tracker
+    __shared__ double ratio_s[D2D_OWL_WARPS][D2D_OWL_MAX_TRK];   // |mu_vel| / |mu_pos - p| of tracker k
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int e = blockIdx.x * D2D_OWL_WARPS + wid;
+    if (e >= P.B) return;
+    const EnvRec &r = P.rec[e];
+    const bool fresh = r.pending_reset || (P.auto_reset && P.done[e]);
+    const double maxyaw = P.max_yaw_speed;
+    const int q = fresh ? 0 : P.owl_q[e];
+    if (q > 0) {                                                 // :193-196
+        if (lane == 0) { P.owl_q[e] = q - 1; actions_out[e] = P.owl_u[e] / maxyaw; }
+        return;
+    }
+    const double x = fresh ? r.p0x : r.px, y = fresh ? r.p0y : r.py, yaw = fresh ? r.p0yaw : r.yaw;
+    const double vx = fresh ? 0.0 : r.vx, vy = fresh ? 0.0 : r.vy;
+    const double tgx = fresh ? r.p0x : r.tgx, tgy = fresh ? r.p0y : r.tgy;   // Planner.__init__: target = drone position
+    const double dt = 0.8, theta_h = P.view_range_deg;
+    const double RAD2DEG = 180.0 / D2D_PI;
+    double *U = U_s[wid];
+    // ---- update_U
+    {
+        const double dp0 = vx * dt, dp1 = vy * dt;
+        const double nyaw = d2d_pymod(-yaw, 360.0);
+        const double depth = P.view_depth;
+#pragma unroll 1
+        for (int i = lane; i < D2D_OWL_BINS; i += 32) {
+            const double u0 = fresh ? 0.0 : P.owl_U[(size_t)e * D2D_OWL_BINS + i];
+            double L = -D2D_FMA(dp1, P.tab->owl_sin[i], dp0 * P.tab->owl_cos[i]) / depth;
+            L += (d2d_owl_between(10.0 * (double)i, nyaw) < theta_h * 0.5) ? 0.4 : -0.05;
+            double u = u0 + L;
+            u = (1.0 < u) ? 1.0 : u;
+            u = (0.0 > u) ? 0.0 : u;
+            P.owl_U[(size_t)e * D2D_OWL_BINS + i] = u;
+            U[i] = u;
+        }
+    }
+    // ---- bearings
+    const double d_g = d2d_atan2_cr(tgy - y, tgx - x) * RAD2DEG;
+    const double nv = d2d_norm2(vx, vy);
+    const double d_v = d2d_atan2_cr(vy / nv, vx / nv) * RAD2DEG;
+    int n_o = 0;
+    if (!fresh && P.trackers) {
+#pragma unroll 1
+        for (int base = 0; base < P.N; base += 32) {
+            const int k = base + lane;
+            const size_t g = (size_t)e * P.NP + k;
+            const bool act = k < P.N && P.trk_active[g] != 0;
+            const unsigned b = __ballot_sync(0xffffffffu, act);
+            const int pos = n_o + __popc(b & ((1u << lane) - 1u));
+            if (act && pos < D2D_OWL_MAX_TRK) do_s[wid][pos] = d2d_atan2_cr(P.trk_mu[g * 4 + 1] - y, P.trk_mu[g * 4] - x) * RAD2DEG;
+            n_o += __popc(b);
+        }
+        if (n_o > D2D_OWL_MAX_TRK) n_o = D2D_OWL_MAX_TRK;
+#pragma unroll 1
+        for (int k = lane; k < n_o; k += 32) {
+            const double *mu = P.trk_mu + ((size_t)e * P.NP + k) * 4;
+            ratio_s[wid][k] = d2d_norm2(mu[2], mu[3]) / d2d_norm2(mu[0] - x, mu[1] - y);
+        }
+    }
+    __syncwarp();
+    // ---- candidate costs
+    const double hp = d2d_pymod(theta_h * 0.5, 360.0), hm = d2d_pymod(-(theta_h * 0.5), 360.0);
+    const double nv10 = d2d_norm2(vx / 10.0, vy / 10.0);
+    const double f1a = nv10 * nv10;
+    const double ug = 1.0 - d2d_owl_U(U, d_g), uv = 1.0 - d2d_owl_U(U, d_v);
+    double cost = 0.0;
+    const bool cand = lane < P.n_owl_u;
+    if (cand) {
+        const double us = P.tab->owl_u_space[lane];
+        const double cy = -(yaw + us * dt);
+        const double f0 = d2d_owl_G(cy - d_g, theta_h, hp, hm) * ug;
+        const double f1 = f1a * d2d_owl_G(cy - d_v, theta_h, hp, hm) * uv;
+        double f2 = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < n_o; k++) f2 += ratio_s[wid][k] * d2d_owl_G(cy - do_s[wid][k], theta_h, hp, hm);
+        const double f3 = d2d_owl_U(U, cy);
+        const double f4 = fabs((us * dt) * D2D_DEG2RAD);
+        cost = D2D_FMA(f0, 0.2, 0.0);
+        cost = D2D_FMA(f1, 0.9, cost);
+        cost = D2D_FMA(f2, 1.0, cost);
+        cost = D2D_FMA(f3, 0.1, cost);
+        cost = D2D_FMA(f4, 0.0, cost);
+    }
+    // ---- np.argmin: the first NaN if any, else the first minimum
+    const unsigned nanm = __ballot_sync(0xffffffffu, cand && cost != cost);
+    int best;
+    if (nanm) best = __ffs(nanm) - 1;
+    else {
+        double bc = cand ? cost : 1.0e308 * 10.0;     // +inf for idle lanes
+        int bi = lane;
+        for (int off = 16; off > 0; off >>= 1) {
+            const double oc = __shfl_xor_sync(0xffffffffu, bc, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (oc < bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+        }
+        best = bi;
+    }
+    if (lane == 0) {
+        const double u = P.tab->owl_u_space[best];
+        P.owl_q[e] = P.owl_repeat;
+        P.owl_u[e] = u;
+        actions_out[e] = u / maxyaw;
+        if (fresh) P.rec[e].owl_fresh = 1;
+    }
 }

@@ -53,7 +53,7 @@ static int step_primitive(d2d_handle *h, const double *actions, cudaStream_t st)
 
 extern "C" int d2d_plan_oxford(d2d_handle *h, double *actions_out_dev, void *stream) {
     if (!h || !actions_out_dev) return D2D_ERR_INVALID;
-    if (!h->cfg.oxford) { h->err = "d2d_plan_oxford: handle was created with oxford = 0"; return D2D_ERR_STATE; }
+    if (!(h->cfg.oxford & D2D_POLICY_OXFORD)) { h->err = "d2d_plan_oxford: handle was created without the Oxford state (cfg.oxford & 1)"; return D2D_ERR_STATE; }
     if (!h->world_set) { h->err = "d2d_plan_oxford before d2d_set_world"; return D2D_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     d2d_oxford_kernel<<<h->B, D2D_OX_THREADS, 0, (cudaStream_t)stream>>>(h->P, h->ox_prog, actions_out_dev);
@@ -64,10 +64,16 @@ extern "C" int d2d_plan_oxford(d2d_handle *h, double *actions_out_dev, void *str
 
 extern "C" int d2d_plan_gaze(d2d_handle *h, int32_t policy, double *actions_out_dev, void *stream) {
     if (!h || !actions_out_dev) return D2D_ERR_INVALID;
-    if (policy < D2D_GAZE_NOCONTROL || policy > D2D_GAZE_LOOKGOAL) { h->err = "d2d_plan_gaze: unknown policy"; return D2D_ERR_INVALID; }
+    if (policy < D2D_GAZE_NOCONTROL || policy > D2D_GAZE_OWL) { h->err = "d2d_plan_gaze: unknown policy"; return D2D_ERR_INVALID; }
     if (!h->world_set) { h->err = "d2d_plan_gaze before d2d_set_world"; return D2D_ERR_STATE; }
+    if (policy == D2D_GAZE_OWL && !(h->cfg.oxford & D2D_POLICY_OWL)) {
+        h->err = "d2d_plan_gaze(Owl): handle was created without the Owl state (cfg.oxford & D2D_POLICY_OWL)"; return D2D_ERR_STATE;
+    }
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    d2d_gaze_kernel<<<(h->B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(h->P, policy, actions_out_dev);
+    if (policy == D2D_GAZE_OWL)
+        d2d_owl_kernel<<<(h->B + D2D_OWL_WARPS - 1) / D2D_OWL_WARPS, D2D_OWL_WARPS * 32, 0, (cudaStream_t)stream>>>(h->P, actions_out_dev);
+    else
+        d2d_gaze_kernel<<<(h->B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(h->P, policy, actions_out_dev);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return D2D_OK;

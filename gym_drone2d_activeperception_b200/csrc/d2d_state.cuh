@@ -19,6 +19,7 @@
 #define D2D_OX_SEEN_STRIDE 2560
 #define D2D_RVO_THETAS 32       // len(np.arange(0, 2*3.14, 0.2))
 #define D2D_RVO_MAX_OBS 16      // circular obstacles (pillars) per env under the RVO motion profile
+#define D2D_OWL_BINS 36         // len(np.arange(0, 360, 10)): Owl.U_list (yaw_planner.py:171)
 #define D2D_MIRCNT_OFF 2552    // int counter in the zero padding behind the 2500 belief bytes of a shared-memory belief copy
 
 struct DevTables {   // lookup tables in global memory (read through the read-only path)
@@ -27,6 +28,8 @@ struct DevTables {   // lookup tables in global memory (read through the read-on
     double t_way[D2D_MAX_WAY], t_way2[D2D_MAX_WAY], t_way_x2[D2D_MAX_WAY];
     double v_yaw_space[D2D_MAX_YAW];
     double rvo_cos[D2D_RVO_THETAS], rvo_sin[D2D_RVO_THETAS];   // glibc cos / sin of np.arange(0, 2*3.14, 0.2) (utils.py:365)
+    double owl_u_space[D2D_MAX_OWL_U];                         // np.arange(-max_yaw_speed, max_yaw_speed, max_yaw_speed/10)
+    double owl_cos[D2D_OWL_BINS], owl_sin[D2D_OWL_BINS];       // glibc cos / sin of radians(np.arange(0, 360, 10)) (yaw_planner.py:181-182)
 };
 
 // Everything persistent and scalar about ONE env, as one 128-byte line: a warp loads / stores it with a single coalesced
@@ -42,7 +45,8 @@ struct __align__(16) EnvRec {
     int obs_ix, obs_iy;              // drone cell for which the local_map tensor content is currently valid
     uint8_t pending_reset;           // reset requested by the host, applied lazily at the start of the next step
     uint8_t ox_fresh;                // Oxford state already re-initialised for a pending reset
-    uint8_t pad_[2];
+    uint8_t owl_fresh;               // same for the Owl state
+    uint8_t pad_[1];
 };
 static_assert(sizeof(EnvRec) == 128, "EnvRec must be exactly one 128-byte line");
 
@@ -55,6 +59,7 @@ struct DevP {
     double dt, scale, inv_scale, map_w, map_h, agent_radius, max_acc, drone_r, max_yaw_speed;
     double ray_a0, ray_da;       // -FOV/2 and FOV/n_rays (utils.py:594)
     double depth2, fov, max_steps, var_cam, max_speed, cull_reach, ox_cos_thresh;
+    double view_depth, view_range_deg;   // params.drone_view_depth, params.drone_view_range as given (Owl: yaw_planner.py:168, 183)
     double targets[D2D_MAX_TARGETS][2];
     // agents [B][NP] (env-major)
     double2 *apos, *apref, *apos0, *apref0;
@@ -77,6 +82,11 @@ struct DevP {
     uint8_t *lm_mirror;          // [B][1][33][33] or null
     float *yaw_mirror;           // [B] or null
     uint8_t *done_mirror;        // [B] or null
+    // completion signal of the bound host path (d2d_bind_host_io / d2d_step_bound): every warp counts itself out after a
+    // system-scope fence; the last one publishes the step's sequence number into mapped host memory, which the host polls
+    unsigned int *sig_ctr;       // device counter (null: no signal)
+    volatile unsigned int *sig_flag;   // device-visible address of the pinned host flag
+    unsigned int sig_seq;
 #ifdef D2D_WARP_PROF
     unsigned long long *prof;    // [B][12]: 10 globaltimer stamps, smid, warpid of the fused warp kernel (tools/warp_prof.py builds with -DD2D_WARP_PROF)
 #endif
@@ -101,6 +111,11 @@ struct DevP {
     int *ox_calls;               // [B] policy calls since reset
     const double *ox_tab;        // [2][D2D_OX_TAB] : from 0.0 (seen) and from 5.0 (never seen)
     double *ox_last;             // [B][2500] materialised on demand by d2d_oxford_export_kernel (may be null)
+    // Owl policy state (yaw_planner.py:160-172), null unless cfg.oxford & D2D_POLICY_OWL
+    double *owl_U;               // [B][36] direction-uncertainty bins U_list
+    int *owl_q;                  // [B] entries left in the repeated-action queue `self.u`
+    double *owl_u;               // [B] the queued action (deg/s)
+    int n_owl_u, owl_repeat;
     unsigned long long *stats;   // [D2D_NUM_STATS]
     unsigned char *plan_ws;      // A* workspaces (Primitive planner)
     int *plan_list;              // [B+8]: compacted list of envs that need a plan; [B] count (block path); [B+1], [B+2]

@@ -61,7 +61,7 @@ __device__ __forceinline__ void d2d_mbar_wait(uint64_t *bar, uint32_t parity) {
 struct EnvS : EnvRec {
     int valid, reset, ncull, coll_agent;
     int arch_cnt, arch_ts, act_cnt, act_ts, newly;
-    int done_now, ix, iy, ox_was_fresh;
+    int done_now, ix, iy, ox_was_fresh, owl_was_fresh;
 };
 
 struct BlockCtx {
@@ -111,8 +111,8 @@ __device__ __forceinline__ BlockCtx d2d_carve(unsigned char *base, int E, int NP
 // init pose, zero velocity, WAIT_FOR_GOAL; Planner.__init__ traj_planner.py:22) and this step's scratch.  One thread.
 __device__ __forceinline__ void d2d_env_begin(const DevP &P, EnvS &s, bool was_done) {
     const bool rs = s.pending_reset != 0 || (P.auto_reset && was_done);
-    s.ox_was_fresh = s.ox_fresh;
-    s.pending_reset = 0; s.ox_fresh = 0;       // consumed; written back with the record at the end of the step
+    s.ox_was_fresh = s.ox_fresh; s.owl_was_fresh = s.owl_fresh;
+    s.pending_reset = 0; s.ox_fresh = 0; s.owl_fresh = 0;   // consumed; written back with the record at the end of the step
     if (rs) {
         s.px = s.p0x; s.py = s.p0y; s.yaw = s.p0yaw; s.vx = 0; s.vy = 0; s.tgx = s.p0x; s.tgy = s.p0y;
         s.steps = 0; s.sm = SM_WAIT_FOR_GOAL; s.fail = 0; s.tcur = 0; s.bufc = 0; s.bufts = 0; s.tracked = 0;
@@ -210,6 +210,15 @@ __device__ D2D_COLD void d2d_reset_arrays(const DevP &P, const BlockCtx &c, int 
             if (!c.S[i].valid || !c.S[i].reset || c.S[i].ox_was_fresh) continue;
             ((uint32_t *)(P.ox_seen + (size_t)(env0 + i) * D2D_OX_SEEN_STRIDE))[o] = 0u;
             if (o == 0) P.ox_calls[env0 + i] = 0;
+        }
+    }
+    if (P.owl_U) {    // Owl.__init__ (yaw_planner.py:160-171): U_list zeros, empty queue
+#pragma unroll 1
+        for (int w = tid; w < E * D2D_OWL_BINS; w += T) {
+            const int i = w / D2D_OWL_BINS, o = w - i * D2D_OWL_BINS;
+            if (!c.S[i].valid || !c.S[i].reset || c.S[i].owl_was_fresh) continue;
+            P.owl_U[(size_t)(env0 + i) * D2D_OWL_BINS + o] = 0.0;
+            if (o == 0) P.owl_q[env0 + i] = 0;
         }
     }
 }
@@ -703,6 +712,12 @@ __device__ D2D_COLD void d2d_tracker_update(const DevP &P, EnvS &s, size_t g, bo
         P.trk_radius[g] = P.trk_radius0[g];
         P.trk_active[g] = 0;
         P.trk_ts[g] = 1;
+        if (!measured) {   // mu_upds = [zeros], Sigma_upds = [diag(1, 1, 10, 10)] (utils.py:181-197): same state as the eager reset
+#pragma unroll
+            for (int i = 0; i < 4; i++) mu[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) Sg[i] = (i == 0 || i == 5) ? 1.0 : ((i == 10 || i == 15) ? 10.0 : 0.0);
+        }
     }
     if (!active && !measured) return;
     double m[4], S[16];
@@ -1224,4 +1239,14 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     if (rewrite) d2d_obs_env_warp(P, c.belief, s.ix, s.iy, e, lane);
     if (s.done_now) d2d_count_explored_warp(P, c.belief, lane);
     D2D_PROF(3);
+    if (P.sig_ctr) {
+        // bound host path: this warp's stores into the host mirror must be visible to the host before the flag is
+        __syncwarp();
+        __threadfence_system();
+        if (lane == 0 && atomicAdd(P.sig_ctr, 1u) == (unsigned)(P.B - 1)) {
+            *P.sig_ctr = 0u;                       // every warp has counted: rearm for the next launch
+            __threadfence_system();
+            *P.sig_flag = P.sig_seq;
+        }
+    }
 }

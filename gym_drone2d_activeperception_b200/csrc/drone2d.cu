@@ -47,6 +47,14 @@ struct d2d_handle {
     bool mir_stale = true;
     size_t smem_pre = 0, smem_plan = 0;
     std::vector<const void *> attr_funcs;   // kernels whose dynamic shared-memory limit this handle has raised
+    // bound host path (d2d_bind_host_io)
+    bool io_bound = false;
+    const double *io_actions_dev = nullptr;      // device-visible address of the caller's pinned action buffer (or staging)
+    uint8_t *io_lm = nullptr; float *io_yaw = nullptr; uint8_t *io_done = nullptr;
+    cudaStream_t io_stream = nullptr;
+    volatile unsigned int *sig_host = nullptr;   // pinned, mapped
+    unsigned int *sig_dev_flag = nullptr, *sig_ctr = nullptr;
+    unsigned int sig_seq = 0;
 };
 
 // Raises the dynamic shared-memory limit of `func` to 227 KB once per handle.  Per handle, not per process: a handle is
@@ -134,6 +142,8 @@ __global__ void d2d_reset_kernel(const DevP P, const uint8_t *__restrict__ mask)
     for (int w = tid; w < D2D_LOCAL_CELLS; w += T) P.local_map[(size_t)e * D2D_LOCAL_CELLS + w] = 0;
     if (P.ox_seen)
         for (int w = tid; w < D2D_OX_SEEN_STRIDE / 2; w += T) ((uint32_t *)(P.ox_seen + (size_t)e * D2D_OX_SEEN_STRIDE))[w] = 0u;
+    if (P.owl_U)
+        for (int w = tid; w < D2D_OWL_BINS; w += T) P.owl_U[(size_t)e * D2D_OWL_BINS + w] = 0.0;
     if (P.rng_key)
         for (int w = tid; w < 624; w += T) P.rng_key[(size_t)e * 624 + w] = P.rng_key0[(size_t)e * 624 + w];
     if (tid == 0) {
@@ -145,7 +155,7 @@ __global__ void d2d_reset_kernel(const DevP P, const uint8_t *__restrict__ mask)
         P.rec[e].bufc = 0; P.rec[e].bufts = 0; P.rec[e].tracked = 0;
         P.rec[e].nseg = 0; P.rec[e].cursor = 0; P.need_plan[e] = 0; P.plan_ok[e] = 1; P.replan[e] = 0;
         P.yaw_obs[e] = (float)yaw;
-        P.rec[e].ox_fresh = 0; P.tmp_act_cnt[e] = 0; P.tmp_act_ts[e] = 0; P.ox_calls[e] = 0;
+        P.rec[e].ox_fresh = 0; P.rec[e].owl_fresh = 0; P.owl_q[e] = 0; P.owl_u[e] = 0.0; P.tmp_act_cnt[e] = 0; P.tmp_act_ts[e] = 0; P.ox_calls[e] = 0;
         P.rng_pos[e] = P.rng_pos0[e]; P.rng_has[e] = P.rng_has0[e]; P.rng_gauss[e] = P.rng_gauss0[e];
         // local_map was zeroed above, which IS the window of an all-unexplored belief grid at the initial cell
         P.rec[e].obs_ix = d2d_cell(x, P.scale, P.inv_scale); P.rec[e].obs_iy = d2d_cell(y, P.scale, P.inv_scale);
@@ -216,7 +226,8 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
         g_create_err = "only drone_view_depth // map_scale == 8 (33x33 local map) is supported"; return D2D_ERR_INVALID;
     }
     if (cfg->n_rays <= 0 || cfg->n_rays > 1024 || cfg->n_targets < 1 || cfg->n_targets > D2D_MAX_TARGETS ||
-        cfg->n_u > D2D_MAX_U || cfg->n_samp > D2D_MAX_SAMP || cfg->n_way > D2D_MAX_WAY || cfg->n_yaw > D2D_MAX_YAW) {
+        cfg->n_u > D2D_MAX_U || cfg->n_samp > D2D_MAX_SAMP || cfg->n_way > D2D_MAX_WAY || cfg->n_yaw > D2D_MAX_YAW ||
+        cfg->n_owl_u < 0 || cfg->n_owl_u > D2D_MAX_OWL_U || cfg->owl_repeat < 0) {
         g_create_err = "table size out of range"; return D2D_ERR_INVALID;
     }
     if (cfg->var_cam != 0.0 && cfg->envs_per_block > 0) {
@@ -281,6 +292,7 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
         RECF("traj_nseg", nseg, D2D_I32, s4); RECF("traj_cursor", cursor, D2D_I32, s4);
         RECF("obs_ix", obs_ix, D2D_I32, s4); RECF("obs_iy", obs_iy, D2D_I32, s4);
         RECF("pending_reset", pending_reset, D2D_U8, s1); RECF("oxford_fresh", ox_fresh, D2D_U8, s1);
+        RECF("owl_fresh", owl_fresh, D2D_U8, s1);
 #undef RECF
         add_view(h, "drone_pose0", D2D_F64, 2, SHP(3, B), SHP(1, s8), o_rec + offsetof(EnvRec, p0x), rb - offsetof(EnvRec, p0x));
     }
@@ -312,9 +324,13 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     size_t o_rg = add_buf(h, cur, "rng_gauss", D2D_F64, 2, SHP(2, B), SHP(B, 1), (size_t)2 * sB);     // gauss, gauss0
     size_t o_oxp = add_buf(h, cur, "oxford_program", D2D_U8, 1, SHP((int64_t)sizeof(OxProgram)), SHP(1), sizeof(OxProgram));
     size_t o_oxs = add_buf(h, cur, "oxford_seen_call", D2D_I32, 1, SHP(1), SHP(1),
-                           cfg->oxford ? (size_t)sB * D2D_OX_SEEN_STRIDE / 2 : 4);          // uint16 [B][2560]
+                           (cfg->oxford & D2D_POLICY_OXFORD) ? (size_t)sB * D2D_OX_SEEN_STRIDE / 2 : 4);   // uint16 [B][2560]
     size_t o_oxc = add_buf(h, cur, "oxford_calls", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_oxt = add_buf(h, cur, "oxford_tables", D2D_F64, 2, SHP(2, D2D_OX_TAB), SHP(D2D_OX_TAB, 1), 2 * D2D_OX_TAB);
+    const bool owl = (cfg->oxford & D2D_POLICY_OWL) != 0;
+    size_t o_owlU = add_buf(h, cur, "owl_U", D2D_F64, 2, SHP(B, D2D_OWL_BINS), SHP(D2D_OWL_BINS, 1), owl ? (size_t)sB * D2D_OWL_BINS : 2);
+    size_t o_owlq = add_buf(h, cur, "owl_queue_len", D2D_I32, 1, SHP(B), SHP(1), sB);
+    size_t o_owlu = add_buf(h, cur, "owl_queue_value", D2D_F64, 1, SHP(B), SHP(1), sB);
     size_t o_stats = add_buf(h, cur, "stats", D2D_I64, 1, SHP(D2D_NUM_STATS), SHP(1), D2D_NUM_STATS);
     size_t o_tab = add_buf(h, cur, "tables", D2D_U8, 1, SHP((int64_t)sizeof(DevTables)), SHP(1), sizeof(DevTables));
     size_t o_stage = add_buf(h, cur, "actions_staging", D2D_F64, 1, SHP(B), SHP(1), sB);
@@ -345,6 +361,7 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.fov = cfg->drone_view_range * D2D_DEG2RAD;                 // radians(drone.yaw_range), utils.py:575
     P.max_steps = cfg->max_flight_time / cfg->dt;                // drone_v2.py:89
     P.var_cam = cfg->var_cam; P.max_speed = cfg->drone_max_speed;
+    P.view_depth = cfg->drone_view_depth; P.view_range_deg = cfg->drone_view_range;
     // a sample is evaluated only if the previous one was closer than depth: reach = depth + step*sqrt(2) (+ slack)
     P.cull_reach = cfg->drone_view_depth + (cfg->map_scale - 1.0) * 1.4142135623730951 + 1e-3;
     P.ray_a0 = -P.fov / 2; P.ray_da = P.fov / (double)cfg->n_rays;
@@ -370,7 +387,9 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.trk_radius = (double *)(A + o_trad); P.trk_ts = (int *)(A + o_tts);
     P.traj_coeff = (double *)(A + o_coef);
     P.need_plan = A + o_need; P.plan_ok = A + o_pok; P.replan = A + o_rep;
-    P.ox_seen = cfg->oxford ? (uint16_t *)(A + o_oxs) : nullptr;
+    P.ox_seen = (cfg->oxford & D2D_POLICY_OXFORD) ? (uint16_t *)(A + o_oxs) : nullptr;
+    P.owl_U = owl ? (double *)(A + o_owlU) : nullptr; P.owl_q = (int *)(A + o_owlq); P.owl_u = (double *)(A + o_owlu);
+    P.n_owl_u = cfg->n_owl_u; P.owl_repeat = cfg->owl_repeat;
     P.ox_calls = (int *)(A + o_oxc); P.ox_tab = (const double *)(A + o_oxt); P.ox_last = nullptr;
     P.lm_mirror = nullptr; P.yaw_mirror = nullptr; P.done_mirror = nullptr;
 #ifdef D2D_WARP_PROF
@@ -397,6 +416,9 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     // RVO candidate directions np.arange(0, 2*3.14, 0.2) (utils.py:365): element i is 0 + i*0.2; math.cos / math.sin are
     // this host's libm, the same functions the reference calls
     for (int i = 0; i < D2D_RVO_THETAS; i++) { const double th = 0.0 + (double)i * 0.2; tab.rvo_cos[i] = cos(th); tab.rvo_sin[i] = sin(th); }
+    // Owl.update_U (yaw_planner.py:181-182): cos / sin of math.radians(d_i), d_i = 0, 10, ..., 350 (this host's libm, as above)
+    memcpy(tab.owl_u_space, cfg->owl_u_space, sizeof(tab.owl_u_space));
+    for (int i = 0; i < D2D_OWL_BINS; i++) { const double r = (10.0 * i) * (D2D_PI / 180.0); tab.owl_cos[i] = cos(r); tab.owl_sin[i] = sin(r); }
     ce = cudaMemcpy(A + o_tab, &tab, sizeof(tab), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { g_create_err = std::string("cudaMemcpy tables: ") + cudaGetErrorString(ce); cudaFree(h->arena); delete h; return D2D_ERR_CUDA; }
 
@@ -431,6 +453,8 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
 extern "C" int d2d_destroy(d2d_handle *h) {
     if (!h) return D2D_OK;
     cudaSetDevice(h->cfg.device);
+    if (h->sig_host) cudaFreeHost((void *)h->sig_host);
+    if (h->sig_ctr) cudaFree(h->sig_ctr);
     if (h->arena) cudaFree(h->arena);
     if (h->ox_export) cudaFree(h->ox_export);
     delete h;
@@ -442,7 +466,7 @@ extern "C" int d2d_get_buffer(d2d_handle *h, const char *name, d2d_buffer_info *
     if (std::string(name) == "oxford_last_time_observed") {
         // Oxford.last_time_observed_map (yaw_planner.py:49,95-97) as float64 [B,50,50]: expanded from the compact state by a
         // kernel on the legacy default stream, then synchronised (debug / test accessor, not part of the hot path)
-        if (!h->cfg.oxford) { h->err = "oxford_last_time_observed: handle was created with oxford = 0"; return D2D_ERR_STATE; }
+        if (!(h->cfg.oxford & D2D_POLICY_OXFORD)) { h->err = "oxford_last_time_observed: handle was created without the Oxford state"; return D2D_ERR_STATE; }
         CUDA_TRY(h, cudaSetDevice(h->cfg.device));
         if (!h->ox_export) CUDA_TRY(h, cudaMalloc((void **)&h->ox_export, (size_t)h->B * D2D_CELLS * 8));
         CUDA_TRY(h, cudaDeviceSynchronize());
@@ -731,6 +755,84 @@ extern "C" int d2d_step_host(d2d_handle *h, const double *actions_host, uint8_t 
     if (h->mir_stale && (!h->mir_lm || local_map_host == h->mir_lm) && (!h->mir_yaw || yaw_host == h->mir_yaw) &&
         (!h->mir_done || done_host == h->mir_done))
         h->mir_stale = false;
+    return D2D_OK;
+}
+
+extern "C" int d2d_bind_host_io(d2d_handle *h, const double *actions_host, uint8_t *local_map_host, float *yaw_host,
+                                uint8_t *done_host, void *stream) {
+    if (!h) return D2D_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = d2d_bind_host_mirror(h, local_map_host, yaw_host, done_host);     // synchronises the device first
+    if (rc != D2D_OK) return rc;
+    h->io_bound = false;
+    if (!actions_host && !local_map_host && !yaw_host && !done_host) return D2D_OK;
+    if (actions_host) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, actions_host) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+            cudaGetLastError();
+            h->err = "d2d_bind_host_io: actions_host is not pinned host memory (cudaHostAlloc / cudaHostRegister)";
+            return D2D_ERR_INVALID;
+        }
+        h->io_actions_dev = (const double *)at.devicePointer;
+    } else {
+        h->io_actions_dev = h->stage_actions;
+    }
+    if (!h->sig_host) {
+        void *p = nullptr;
+        CUDA_TRY(h, cudaHostAlloc(&p, 64, cudaHostAllocMapped));
+        h->sig_host = (volatile unsigned int *)p;
+        *h->sig_host = 0u;
+        void *dp = nullptr;
+        CUDA_TRY(h, cudaHostGetDevicePointer(&dp, p, 0));
+        h->sig_dev_flag = (unsigned int *)dp;
+        CUDA_TRY(h, cudaMalloc((void **)&h->sig_ctr, 64));
+        CUDA_TRY(h, cudaMemset(h->sig_ctr, 0, 64));
+    }
+    h->io_lm = local_map_host; h->io_yaw = yaw_host; h->io_done = done_host;
+    h->io_stream = (cudaStream_t)stream;
+    h->io_bound = true;
+    return D2D_OK;
+}
+
+extern "C" int d2d_step_bound(d2d_handle *h) {
+    if (!h) return D2D_ERR_INVALID;
+    if (!h->io_bound) { h->err = "d2d_step_bound before d2d_bind_host_io"; return D2D_ERR_STATE; }
+    // the in-kernel completion signal exists in the fused NoMove warp kernel; everything else, and the first step after a
+    // bind / reset (the mirror needs one full refresh copy), goes through the synchronising path
+    const bool fast = h->cfg.planner == D2D_PLANNER_NOMOVE && h->cfg.envs_per_block <= 0 && !h->P.motion_rvo && !h->mir_stale;
+    if (!fast) {
+        const int rc = d2d_step(h, h->io_actions_dev, (void *)h->io_stream);
+        if (rc != D2D_OK) return rc;
+        cudaStream_t st = h->io_stream;
+        if (h->mir_stale) {
+            if (h->io_lm) CUDA_TRY(h, cudaMemcpyAsync(h->io_lm, h->P.local_map, (size_t)h->B * D2D_LOCAL_CELLS, cudaMemcpyDeviceToHost, st));
+            if (h->io_yaw) CUDA_TRY(h, cudaMemcpyAsync(h->io_yaw, h->P.yaw_obs, (size_t)h->B * 4, cudaMemcpyDeviceToHost, st));
+            if (h->io_done) CUDA_TRY(h, cudaMemcpyAsync(h->io_done, h->P.done, (size_t)h->B, cudaMemcpyDeviceToHost, st));
+        }
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+        if ((!h->mir_lm || h->io_lm == h->mir_lm) && (!h->mir_yaw || h->io_yaw == h->mir_yaw) && (!h->mir_done || h->io_done == h->mir_done))
+            h->mir_stale = false;
+        return D2D_OK;
+    }
+    if (!h->world_set) { h->err = "d2d_step before d2d_set_world"; return D2D_ERR_STATE; }
+    if (h->cfg.var_cam != 0.0 && !h->rng_set) { h->err = "var_cam != 0: d2d_set_rng must provide the np.random stream state"; return D2D_ERR_STATE; }
+    const unsigned int seq = ++h->sig_seq ? h->sig_seq : ++h->sig_seq;         // never 0
+    h->P.sig_ctr = h->sig_ctr; h->P.sig_flag = h->sig_dev_flag; h->P.sig_seq = seq;
+    const int rc = launch_fused_warp<4, 7, false>(h, h->io_actions_dev, h->io_stream);
+    h->P.sig_ctr = nullptr;
+    if (rc != D2D_OK) return rc;
+    // poll the flag; look at the stream now and then so that a failed launch / kernel fault cannot hang the caller
+    volatile unsigned int *flag = h->sig_host;
+    for (unsigned long spins = 1; *flag != seq; spins++) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0xFFFFF) == 0) {
+            const cudaError_t q = cudaStreamQuery(h->io_stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) { h->err = std::string("d2d_step_bound: ") + cudaGetErrorString(q); return D2D_ERR_CUDA; }
+            if (q == cudaSuccess && *flag != seq) { h->err = "d2d_step_bound: kernel finished without signalling"; return D2D_ERR_CUDA; }
+        }
+    }
     return D2D_OK;
 }
 

@@ -28,9 +28,33 @@ class _GridMapProxy(object):
     def grid_map(self):
         if self._which == "belief":
             return self._env._vec.buffer("belief")[0].cpu().numpy()
-        rows = self._env._vec.buffer("gt_rows")[0].cpu().numpy().astype(np.uint64)
+        v = self._env._vec
+        rows = v.buffer("gt_rows")[0].cpu().numpy().astype(np.uint64)
         bits = (rows[:, None] >> np.arange(self.height, dtype=np.uint64)[None, :]) & np.uint64(1)
-        return np.where(bits == 1, 1, 2).astype(np.uint8)     # OCCUPIED / UNOCCUPIED (dynamic marks are not kept)
+        g = np.where(bits == 1, 1, 2).astype(np.uint8)        # OCCUPIED / UNOCCUPIED
+        # DYNAMIC_OCCUPIED marks (value 3).  The step kernels never compute them -- nothing on the hot path reads them
+        # (perception, collision and observation test `== 1`) -- so the view is synthesised here from the agent state:
+        pos = v.buffer("agent_pos")[0].cpu().numpy().reshape(-1, 2)
+        rad = v.buffer("agent_radius")[0].cpu().numpy().reshape(-1)
+        if int(v.buffer("steps")[0].item()) == 0:
+            # right after __init__ / reset(): init_obstacles marks every cell whose CENTRE lies in an agent disc, border
+            # cells included (utils.py:520-525)
+            cx = self.x_scale * (np.arange(self.width) + 0.5)
+            cy = self.y_scale * (np.arange(self.height) + 0.5)
+            for (ax, ay), r in zip(pos, rad):
+                g[((cx[:, None] - ax) ** 2 + (cy[None, :] - ay) ** 2) <= r ** 2] = 3
+            return g
+        # after a step: update_dynamic_grid (utils.py:527-540) stamps a (2*(r // scale) + 1)^2 box of cells around every
+        # agent's cell, except on OCCUPIED cells; last step's marks were demoted to UNOCCUPIED first
+        for (ax, ay), r in zip(pos, rad):
+            ux, uy = int(r // self.x_scale), int(r // self.y_scale)
+            pi, pj = int(ax // self.x_scale), int(ay // self.y_scale)
+            i0, i1 = max(pi - ux, 0), min(pi + ux + 1, self.width)
+            j0, j1 = max(pj - uy, 0), min(pj + uy + 1, self.height)
+            if i1 > i0 and j1 > j0:
+                box = g[i0:i1, j0:j1]
+                box[box != 1] = 3
+        return g
 
     def get_grid(self, x, y):                                 # utils.py:545-548
         if x >= self.dim[0] or x < 0 or y >= self.dim[1] or y < 0:
@@ -146,7 +170,12 @@ class _AgentProxy(object):
     def pref_velocity(self):
         return self._env._vec.buffer("agent_pref")[0, self._i].cpu().numpy()
 
-    velocity = pref_velocity        # CVM: velocity IS pref_velocity (drone_v2.py:178)
+    @property
+    def velocity(self):
+        # CVM: velocity IS pref_velocity (drone_v2.py:178); RVO: the velocity RVO_update chose (drone_v2.py:169-173)
+        if self._env._vec.cfg.motion_profile == 1:
+            return self._env._vec.buffer("agent_vel")[0, self._i].cpu().numpy()
+        return self.pref_velocity
 
     @property
     def radius(self):
@@ -172,13 +201,17 @@ class Drone2DEnv2(object):
         self.dt = params.dt
         self.max_steps = params.max_flight_time / params.dt
         self.target_list = [list(t) for t in params.target_list]
-        self._vec = Drone2DVecEnv(params, 1, seeds=[params.map_id], device=device, auto_reset=False,
-                                  oxford=getattr(params, "gaze_method", "") == "Oxford")
+        from .world import generate_worlds
+        worlds = generate_worlds(params, [params.map_id])
+        self._vec = Drone2DVecEnv(params, 1, seeds=[params.map_id], device=device, auto_reset=False, worlds=worlds,
+                                  oxford=getattr(params, "gaze_method", "") == "Oxford",
+                                  owl=getattr(params, "gaze_method", "") == "Owl")
         self.drone = _DroneProxy(self)
         self.planner = _PlannerProxy(self)
         self.agents = [_AgentProxy(self, i) for i in range(self._vec.num_agents)]
         self.map_gt = _GridMapProxy(self, "gt")
-        self.obstacles = []
+        # circular pillars [x, y, rad] of init_obstacles_random_size (drone_v2.py:14-27); empty unless pillar_number > 0
+        self.obstacles = [list(o) for o in np.asarray(self._pillars(params), dtype=np.float64).reshape(-1, 3)]
         L = self._vec.local_map_size
         box = types.SimpleNamespace
         self.action_space = box(low=np.array([-1.0]), high=np.array([1.0]), shape=(1,))
@@ -186,6 +219,13 @@ class Drone2DEnv2(object):
                                              "local_map": box(shape=(1, L, L), dtype=np.float32),
                                              "swep_map": box(shape=(1, L, L), dtype=np.float32)})
         self._a = torch.zeros(1, dtype=torch.float64, device=self._vec.device)
+
+    @staticmethod
+    def _pillars(params):
+        from .world import generate_world, load_static_map
+        if getattr(params, "pillar_number", 0) <= 0:
+            return np.zeros((0, 3))
+        return generate_world(params, int(params.map_id), load_static_map(params.static_map))["obstacles"]
 
     # ---- reference attributes
     @property

@@ -57,8 +57,8 @@ class Experiment(object):
 
 
 def run_batched(params, num_envs, steps, device="cuda:0", seeds=None):
-    """Plays `steps` env-steps of `num_envs` seeded envs (auto-reset on) with the params' gaze method (Oxford, LookAhead,
-    LookGoal, Rotating, NoControl) evaluated on the device.  Returns the statistics dict."""
+    """Plays `steps` env-steps of `num_envs` seeded envs (auto-reset on) with the params' gaze method (Oxford, Owl,
+    LookAhead, LookGoal, Rotating, NoControl) evaluated on the device.  Returns the statistics dict."""
     import torch
     from .vec_env import Drone2DVecEnv
     if params.gaze_method == "NoControl":

@@ -3,7 +3,7 @@
 `global_survivability` is script/difficulty_calculator/glob_survivability_calculator.py:13-44: for every world and every
 start position of an 8x8 grid (x, y in range(map_scale + drone_radius, size - map_scale - drone_radius, 60)) the drone is
 pinned at the position (`env.drone.x = x` before every step), the env is stepped with the NoMove planner and action 0 for
-T / dt steps, and `collision_state[ix, iy, t] = 1` whenever `info['collision_flag'] == 2`.  The reference runs the
+T / dt steps, and `collision_state[ix, iy, int(t / 0.1)] = 1` whenever `info['collision_flag'] == 2`.  The reference runs the
 64 x 240 steps of one world sequentially on one env object; here all (world, position) pairs are one batch."""
 import numpy as np
 import torch
@@ -38,11 +38,15 @@ def global_survivability(params, seeds, T=24, position_step=60, device="cuda:0")
     pose[:, 1] = np.tile(grid[:, 1], nw)
     env.set_drone_pose(pose)            # NoMove never moves the drone, so pinning once == pinning before every step
     zero = torch.zeros(nw * npos, dtype=torch.float64, device=env.device)
-    out = torch.empty((steps, nw * npos), dtype=torch.uint8, device=env.device)
+    out = torch.zeros((steps, nw * npos), dtype=torch.uint8, device=env.device)
     col = env.buffer("collision_flag")
-    for t in range(steps):
+    # the reference walks `for t in np.arange(0, T, 0.1)` and writes slot int(t / 0.1) (glob_survivability_calculator.py:34-39):
+    # t is k * 0.1 rounded, so for some k the slot is k - 1 (T = 24: k = 43, 81, 86, ...) -- that slot then collects two
+    # steps and slot k stays 0.  Reproduced, not corrected.
+    slots = [int(t / 0.1) for t in np.arange(0, T, 0.1)][:steps]
+    for k in range(len(slots)):
         env.step(zero)
-        out[t] = (col == 2)
+        out[slots[k]] |= (col == 2).to(torch.uint8)
     res = out.cpu().numpy().T.reshape(nw, len(xs), len(ys), steps)
     env.close()
     return res

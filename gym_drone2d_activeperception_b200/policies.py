@@ -55,10 +55,12 @@ class LookGoal(object):                      # yaw_planner.py:225-255
             return 0
         positions = trajectory.positions
         x_look, y_look = positions[-1][0], positions[-1][1]
-        grid = drone.map.grid_map
+        grid = drone.map.grid_map                 # one device read; then OccupancyGridMap.get_grid (utils.py:545-548)
+        w, h = self.params.map_size
+        scale = self.params.map_scale
         for position in positions:
             x, y = position[0], position[1]
-            val = 1 if (x >= 500 or x < 0 or y >= 500 or y < 0) else grid[int(x // 10), int(y // 10)]
+            val = 1 if (x >= w or x < 0 or y >= h or y < 0) else grid[int(x // scale), int(y // scale)]
             if val == 0:
                 x_look, y_look = x, y
                 break
@@ -81,5 +83,22 @@ class Oxford(object):                        # yaw_planner.py:41-127, executed b
         raise AttributeError("policy state lives on the device: env._vec.buffer('oxford_last_time_observed')")
 
 
+class Owl(object):                           # yaw_planner.py:151-222, executed by d2d_owl_kernel
+    """State (U_list, the repeated-action queue) lives on the device and is re-initialised with the env."""
+
+    def __init__(self, params):
+        self.params = params
+        self.dt = 0.8
+        self.u_space = np.arange(-params.drone_max_yaw_speed, params.drone_max_yaw_speed, params.drone_max_yaw_speed / 10)
+
+    def plan(self, observation):
+        env = observation["drone"]._env
+        return float(env._vec.plan_gaze("Owl")[0].item())
+
+    @property
+    def U_list(self):
+        raise AttributeError("policy state lives on the device: env._vec.buffer('owl_U')")
+
+
 policy_list = {"LookAhead": LookAhead, "NoControl": NoControl, "Oxford": Oxford, "Rotating": Rotating,
-               "LookGoal": LookGoal}
+               "LookGoal": LookGoal, "Owl": Owl}

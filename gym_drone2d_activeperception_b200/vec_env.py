@@ -54,7 +54,7 @@ def oxford_cos_threshold(view_range_deg):
 
 
 def make_config(params, num_envs, num_agents, device_index, auto_reset=True, trackers=True, oxford=False,
-                envs_per_block=0, strip_width=10):
+                envs_per_block=0, strip_width=10, owl=False):
     """Fills d2d_config from a reference-style Params object; lookup tables use the reference's numpy expressions."""
     cfg = _native.D2DConfig()
     cfg.struct_size = C.sizeof(_native.D2DConfig)
@@ -69,7 +69,7 @@ def make_config(params, num_envs, num_agents, device_index, auto_reset=True, tra
     cfg.planner = {"NoMove": 0, "Primitive": 1}[params.planner]
     cfg.trackers = 1 if trackers else 0
     cfg.auto_reset = 1 if auto_reset else 0
-    cfg.oxford = 1 if oxford else 0
+    cfg.oxford = (_native.POLICY_OXFORD if oxford else 0) | (_native.POLICY_OWL if owl else 0)
     cfg.envs_per_block = envs_per_block
     cfg.n_rays = math.ceil(params.map_size[0] / strip_width)            # utils.py:587
     cfg.dt, cfg.map_scale = params.dt, params.map_scale
@@ -112,6 +112,14 @@ def make_config(params, num_envs, num_agents, device_index, auto_reset=True, tra
     cfg.n_yaw = len(vy)                                                  # yaw_planner.py:65
     for i, v in enumerate(vy):
         cfg.v_yaw_space[i] = float(v)
+    # Owl.__init__ yaw_planner.py:153-167
+    ou = np.arange(-params.drone_max_yaw_speed, params.drone_max_yaw_speed, params.drone_max_yaw_speed / 10)
+    if len(ou) > _native.MAX_OWL_U:
+        raise ValueError("Owl u_space too large")
+    cfg.n_owl_u = len(ou)
+    for i, v in enumerate(ou):
+        cfg.owl_u_space[i] = float(v)
+    cfg.owl_repeat = max(0, int(0.8 // params.dt) - 1)                   # yaw_planner.py:220
     return cfg
 
 
@@ -129,7 +137,7 @@ class Drone2DVecEnv(object):
     metadata = {"render.modes": []}
 
     def __init__(self, params, num_envs, seeds=None, device="cuda:0", auto_reset=True, trackers=True, oxford=None,
-                 envs_per_block=0, strip_width=10, worlds=None):
+                 envs_per_block=0, strip_width=10, worlds=None, owl=None):
         if not torch.cuda.is_available():
             raise _native.Drone2DNativeError("CUDA device required: Drone2DVecEnv has no CPU path")
         self.params = params
@@ -141,9 +149,11 @@ class Drone2DVecEnv(object):
         self.num_agents = count_agents(params, self._smap)
         if oxford is None:
             oxford = getattr(params, "gaze_method", "") == "Oxford"
+        if owl is None:
+            owl = getattr(params, "gaze_method", "") == "Owl"
         self.cfg = make_config(params, self.num_envs, self.num_agents, self._dev_index, auto_reset=auto_reset,
                                trackers=trackers, oxford=oxford, envs_per_block=envs_per_block,
-                               strip_width=strip_width)
+                               strip_width=strip_width, owl=owl)
         self._h = C.c_void_p()
         rc = self._lib.d2d_create(C.byref(self.cfg), C.byref(self._h))
         if rc != 0:
@@ -274,6 +284,31 @@ class Drone2DVecEnv(object):
         self._mirror = (local_map_host, yaw_host, done_host)      # keep the buffers alive while bound
         self._mirror_ptrs = tuple(None if x is None else x.data_ptr() for x in self._mirror)
 
+    def bind_host_io(self, actions_host=None, local_map_host=None, yaw_host=None, done_host=None):
+        """Bound form of `step_host` (d2d_bind_host_io): all PINNED host tensors are given once -- the caller rewrites
+        `actions_host` in place before every step and reads the three observation tensors after it -- and a step is then
+        `step_bound()`, one C call without per-step pointer marshalling; with the NoMove planner it returns on the step
+        kernel's own completion flag instead of a driver synchronisation.  actions_host=None: the actions come from the
+        device buffer "actions_staging".  All None unbinds."""
+        for x in (actions_host, local_map_host, yaw_host, done_host):
+            if x is not None and not (torch.is_tensor(x) and x.is_pinned() and x.is_contiguous()):
+                raise ValueError("bind_host_io needs contiguous pinned torch tensors (tensor.pin_memory())")
+        def ptr(x):
+            return None if x is None else C.c_void_p(x.data_ptr())
+        self._check(self._lib.d2d_bind_host_io(self._h, ptr(actions_host), ptr(local_map_host), ptr(yaw_host), ptr(done_host),
+                                               self._stream()), "d2d_bind_host_io")
+        self._io = (actions_host, local_map_host, yaw_host, done_host)      # keep the buffers alive while bound
+        self._mirror = (local_map_host, yaw_host, done_host)
+        self._mirror_ptrs = tuple(None if x is None else x.data_ptr() for x in self._mirror)
+        self._step_bound = self._lib.d2d_step_bound
+        self._hv = self._h.value
+
+    def step_bound(self):
+        """One step through the buffers bound by `bind_host_io`."""
+        rc = self._step_bound(self._hv)
+        if rc != 0:
+            self._check(rc, "d2d_step_bound")
+
     @property
     def info(self):
         """Batched counterpart of `env.info` (drone_v2.py:238-250): tensors aliasing device state."""
@@ -306,8 +341,9 @@ class Drone2DVecEnv(object):
         return out
 
     def plan_gaze(self, policy, out=None):
-        """NoControl / Rotating / LookAhead / LookGoal .plan for every env (yaw_planner.py), on the device.
-        policy: name or d2d_gaze value.  'Oxford' is routed to plan_oxford()."""
+        """NoControl / Rotating / LookAhead / LookGoal / Owl .plan for every env (yaw_planner.py), on the device.
+        policy: name or d2d_gaze value.  'Oxford' is routed to plan_oxford().  'Owl' needs the env created with owl=True
+        (or params.gaze_method == 'Owl')."""
         if policy == "Oxford":
             return self.plan_oxford(out)
         code = _native.GAZE[policy] if isinstance(policy, str) else int(policy)

@@ -50,8 +50,16 @@ typedef enum d2d_planner { D2D_PLANNER_NOMOVE = 0, D2D_PLANNER_PRIMITIVE = 1 } d
 /* params.motion_profile: constant-velocity agents (velocity IS pref_velocity) or reciprocal velocity obstacles */
 typedef enum d2d_motion { D2D_MOTION_CVM = 0, D2D_MOTION_RVO = 1 } d2d_motion;
 
-/* scalar gaze policies of yaw_planner.py that d2d_plan_gaze evaluates for every env */
-typedef enum d2d_gaze { D2D_GAZE_NOCONTROL = 0, D2D_GAZE_ROTATING = 1, D2D_GAZE_LOOKAHEAD = 2, D2D_GAZE_LOOKGOAL = 3 } d2d_gaze;
+/* gaze policies of yaw_planner.py that d2d_plan_gaze evaluates for every env (Oxford has its own entry point) */
+typedef enum d2d_gaze {
+    D2D_GAZE_NOCONTROL = 0, D2D_GAZE_ROTATING = 1, D2D_GAZE_LOOKAHEAD = 2, D2D_GAZE_LOOKGOAL = 3,
+    D2D_GAZE_OWL = 4             /* stateful (yaw_planner.py:151-222): needs cfg.oxford & D2D_POLICY_OWL */
+} d2d_gaze;
+
+/* bits of d2d_config.oxford: which gaze-policy state lives in the arena */
+#define D2D_POLICY_OXFORD 1      /* Oxford.last_time_observed_map (yaw_planner.py:49-50) */
+#define D2D_POLICY_OWL 2         /* Owl.U_list + the repeated-action queue (yaw_planner.py:160-172) */
+#define D2D_MAX_OWL_U 32
 
 typedef enum d2d_dtype { D2D_U8 = 0, D2D_I8 = 1, D2D_I32 = 2, D2D_I64 = 3, D2D_F32 = 4, D2D_F64 = 5 } d2d_dtype;
 
@@ -75,7 +83,7 @@ typedef struct d2d_config {
     int32_t planner;                 /* d2d_planner */
     int32_t trackers;                /* 1: run the Kalman trackers (utils.py:242-275) every step, as the reference does */
     int32_t auto_reset;              /* 1: an env that reported done is re-initialised at the start of its next step */
-    int32_t oxford;                  /* 1: allocate the Oxford gaze-policy state (yaw_planner.py:49-50) */
+    int32_t oxford;                  /* D2D_POLICY_* bits: gaze-policy state to allocate (1 = Oxford, as before) */
     int32_t envs_per_block;          /* 0 = library default; tuning knob (4, 8 or 16) */
     int32_t n_rays;                  /* ceil(map_size[0] / strip_width), utils.py:587 */
     int32_t n_targets;
@@ -91,6 +99,10 @@ typedef struct d2d_config {
     double t_samp[D2D_MAX_SAMP], t_samp2[D2D_MAX_SAMP];
     double t_way[D2D_MAX_WAY], t_way2[D2D_MAX_WAY], t_way_x2[D2D_MAX_WAY];
     double v_yaw_space[D2D_MAX_YAW];
+    /* Owl (yaw_planner.py:151-172): u_space = np.arange(-max_yaw_speed, max_yaw_speed, max_yaw_speed / 10) evaluated by the
+     * host, and how often a chosen action is repeated: int(0.8 // params.dt) - 1 (yaw_planner.py:220-221) */
+    int32_t n_owl_u, owl_repeat;
+    double owl_u_space[D2D_MAX_OWL_U];
 } d2d_config;
 
 typedef struct d2d_handle d2d_handle;
@@ -164,12 +176,28 @@ int d2d_step_host(d2d_handle *h, const double *actions_host, uint8_t *local_map_
  * d2d_step_host after a bind, d2d_reset or d2d_set_world refreshes the mirror with one full copy. */
 int d2d_bind_host_mirror(d2d_handle *h, uint8_t *local_map_host, float *yaw_host, uint8_t *done_host);
 
+/* Bound form of d2d_step_host for callers that step in a tight loop (a vectorised-env worker): all host buffers and the
+ * stream are given ONCE, a step is then d2d_step_bound(h).
+ *   actions_host  PINNED [num_envs] f64 the caller rewrites before every step (read by the kernels in place over PCIe);
+ *                 NULL: actions come from the device buffer "actions_staging" (policy on the GPU)
+ *   local_map_host / yaw_host / done_host  PINNED, become the zero-copy observation mirror (d2d_bind_host_mirror rules)
+ * With the NoMove planner the step kernel itself reports completion: every warp fences its mirror stores at system scope
+ * and the last one writes the step number into a pinned flag the host polls, so the call returns without a driver
+ * synchronisation (about 6 us per step at BASELINE config 2).  Other planners synchronise the stream as d2d_step_host does.
+ * Binding with all pointers NULL unbinds. */
+int d2d_bind_host_io(d2d_handle *h, const double *actions_host, uint8_t *local_map_host, float *yaw_host, uint8_t *done_host,
+                     void *stream);
+int d2d_step_bound(d2d_handle *h);
+
 /* Replaces Oxford.plan(env.info) (yaw_planner.py:81-127) for all envs: writes the chosen action per env to
  * actions_out_dev (DEVICE [num_envs] f64) and advances the policy state.  Requires cfg.oxford = 1. */
 int d2d_plan_oxford(d2d_handle *h, double *actions_out_dev, void *stream);
 
-/* Replaces NoControl / Rotating / LookAhead / LookGoal .plan(env.info) (yaw_planner.py:10-39, 136-142, 225-255) for all envs:
- * writes the action per env to actions_out_dev (DEVICE [num_envs] f64).  `policy` is a d2d_gaze value. */
+/* Replaces NoControl / Rotating / LookAhead / LookGoal / Owl .plan(env.info) (yaw_planner.py:10-39, 136-255) for all envs:
+ * writes the action per env to actions_out_dev (DEVICE [num_envs] f64).  `policy` is a d2d_gaze value.  Owl is called the
+ * way experiment.py:33-34 calls it (the class object is the instance); its state (36 direction-uncertainty bins, the queue
+ * of repeated actions) lives in the arena (cfg.oxford & D2D_POLICY_OWL), advances with every call and is re-initialised
+ * with the env (a new policy per episode, experiment.py:27-34). */
 int d2d_plan_gaze(d2d_handle *h, int32_t policy, double *actions_out_dev, void *stream);
 
 /* Replaces direct writes to env.drone.x / .y / .yaw by the metric scripts

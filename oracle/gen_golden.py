@@ -107,6 +107,10 @@ def main():
             continue
         r = rr.run_episode(800, policy="Oxford", planner="Primitive", stop_on_done=True, record_oxford=True, **kw)
         save(name, r, WORLD + STEP_CORE + TRACK + PLAN + ["ox_last"])
+    # --- env.map_gt.grid_map as callers of the facade see it (value-3 marks; seed 8 has a border cell overridden at init)
+    if only in "gtgrid_empty_s8":
+        r = rr.run_episode(12, actions=acts, planner="NoMove", record_gt=True, record_trackers=False, map_id=8)
+        save("gtgrid_empty_s8", r, WORLD + ["action", "gt_dyn"])
     # --- Owl gaze policy (yaw_planner.py:151-222) with the reference's call pattern (class object as instance, experiment.py:33-34)
     owl = [
         ("owl_s3", dict(map_id=3, agent_number=8)),

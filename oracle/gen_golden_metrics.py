@@ -37,6 +37,36 @@ def survive_times(env, params, T, position_step=60):
     return st
 
 
+def global_collision_state(env, params, T, position_step):
+    # glob_survivability_calculator.py:24-41, loop for loop (the script itself runs a sweep at import time)
+    x_range = range(params.map_scale + params.drone_radius, params.map_size[0] - params.map_scale - params.drone_radius, position_step)
+    y_range = range(params.map_scale + params.drone_radius, params.map_size[1] - params.map_scale - params.drone_radius, position_step)
+    collision_state = np.zeros((len(x_range), len(y_range), int(T / 0.1)))
+    for x in x_range:
+        for y in y_range:
+            env.reset()
+            for t in np.arange(0, T, 0.1):
+                env.drone.x = x
+                env.drone.y = y
+                _, _, done, info = env.step(0)
+                if info['collision_flag'] == 2:
+                    collision_state[int((x - params.map_scale - params.drone_radius) / position_step),
+                                    int((y - params.map_scale - params.drone_radius) / position_step), int(t / 0.1)] = 1
+    return collision_state
+
+
+def main_global():
+    """T = 24 as in the script: int(t / 0.1) maps 10 of the 240 steps to the previous slot (k = 43, 81, 86, ...)."""
+    T, step, seed = 24, 120, 5
+    kw = dict(agent_number=30, agent_radius=20, agent_max_speed=40)
+    env, params = rr.make_env(planner="NoMove", gaze_method="NoControl", map_id=seed, debug=False, **kw)
+    with rr._reference_cwd():
+        cs = global_collision_state(env, params, T, step)
+    print("global survivability golden: collisions", int(cs.sum()), "shape", cs.shape)
+    np.savez_compressed(os.path.join(OUT, "metrics_global_survivability.npz"), collision_state=cs.astype(np.uint8), T=T,
+                        position_step=step, seed=seed, params=json.dumps(kw), provenance=json.dumps(provenance()))
+
+
 def main():
     cases = [dict(agent_number=10, agent_radius=15, agent_max_speed=20), dict(agent_number=20, agent_radius=8, agent_max_speed=45)]
     seeds = [0, 3, 7]
@@ -58,4 +88,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "global" in sys.argv[1:]:
+        main_global()
+    else:
+        main()

@@ -88,7 +88,7 @@ def world_snapshot(env):
 
 
 def run_episode(steps, actions=None, policy=None, set_pose=None, stop_on_done=False, record_trackers=True,
-                record_oxford=False, **param_kw):
+                record_oxford=False, record_gt=False, **param_kw):
     """Step the reference and record everything the parity tests compare.
 
     actions: sequence of floats (cycled) when policy is None; policy: 'Oxford' uses the reference's own
@@ -155,7 +155,7 @@ def run_episode(steps, actions=None, policy=None, set_pose=None, stop_on_done=Fa
                            "dead_lock", "freezing", "state_machine", "fail_count", "drone", "drone_vel",
                            "local_map", "yaw_obs", "traj_len", "replan", "plan_ok", "planned", "target",
                            "trk_active", "trk_mu", "trk_sigma", "trk_radius", "trk_ts", "buf_count", "buf_ts",
-                           "ox_last", "tracked_agent")}
+                           "ox_last", "tracked_agent", "gt_dyn")}
     with _reference_cwd():
         for t in range(steps):
             if pol is not None:
@@ -192,6 +192,8 @@ def run_episode(steps, actions=None, policy=None, set_pose=None, stop_on_done=Fa
             rec["planned"].append(bool(seen.get("planned", False)))
             rec["target"].append(np.asarray(env.planner.target, dtype=np.float64).copy())
             rec["tracked_agent"].append(int(env.tracked_agent))
+            if record_gt:      # env.map_gt.grid_map with the DYNAMIC_OCCUPIED marks of update_dynamic_grid (utils.py:527-540)
+                rec["gt_dyn"].append(env.map_gt.grid_map.copy())
             if record_trackers:
                 trk = env.drone.trackers[:n]
                 rec["trk_active"].append(np.array([bool(k.active) for k in trk]))

@@ -99,6 +99,7 @@ def mathlib(tmp_path_factory):
     L.mc_cell.argtypes = [dp, np.ctypeslib.ndpointer(np.int32, flags="C"), C.c_long, C.c_double]
     L.mc_pymod.argtypes = [dp, dp, C.c_long, C.c_double]
     L.mc_norm2.argtypes = [dp, dp, dp, C.c_long]
+    L.mc_atan2.argtypes = [dp, dp, dp, C.c_long, C.c_int]
     ip = np.ctypeslib.ndpointer(np.int32, flags="C")
     L.mc_norm2_cmp.argtypes = [dp, dp, dp, ip, ip, C.c_long]
     return L
@@ -119,6 +120,43 @@ def test_device_tan_vs_glibc(mathlib):
     mp.mp.dps = 50
     for v, o in zip(a[:3000], out[:3000]):
         assert float(mp.tan(mp.mpf(float(v)))) == o
+
+
+def test_device_atan2_is_correctly_rounded_from_any_nearby_seed(mathlib):
+    """d2d_atan2_cr = library atan2 + one double-double Newton step: the result must not depend on the seed's last bits
+    (CUDA's atan2 is <= 2 ulp) and must be the correctly rounded value -- which is what glibc's atan2 returns on (nearly) all
+    inputs, in particular on the lattice bearings the Owl / LookGoal policies bin (atan2(a, a), atan2(a, 0), ...)."""
+    rng = np.random.RandomState(4)
+    n = 200000
+    y, x = rng.uniform(-500, 500, n), rng.uniform(-500, 500, n)
+    k = n // 4
+    y[:k], x[:k] = rng.randint(-460, 461, k).astype(float), rng.randint(-460, 461, k).astype(float)   # integer lattice
+    y[k:k + 2000] = x[k:k + 2000]                                                                      # exact diagonals
+    y[k + 2000:k + 3000] = 0.0
+    x[k + 3000:k + 4000] = 0.0
+    ref = np.arctan2(y, x)            # glibc via numpy (same libm as math.atan2)
+    ref = np.array([math.atan2(a, b) for a, b in zip(y.tolist(), x.tolist())])
+    outs = []
+    for ulps in (0, 1, -1, 2, -2):
+        out = np.empty(n)
+        mathlib.mc_atan2(y, x, out, n, ulps)
+        outs.append(out)
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0], equal_nan=True), "the Newton step must erase a 2-ulp seed error"
+    neq = outs[0] != ref
+    # glibc 2.39's atan2 is < 1 ulp but not correctly rounded: ~0.09 % of inputs differ by one ulp (glibc is the farther one,
+    # checked against mpmath below); the bearings that sit ON a bin / wedge boundary -- diagonals and axes -- are exact
+    assert neq.mean() < 2e-3, neq.mean()
+    assert np.all(np.abs(outs[0][neq] - ref[neq]) <= np.spacing(np.abs(ref[neq])))
+    assert not neq[k:k + 4000].any(), "diagonal / axis bearings must match glibc exactly"
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    idx = np.concatenate([np.arange(0, 1500), np.arange(k, k + 300), np.nonzero(neq)[0][:200]])
+    for i in idx:
+        if x[i] == 0.0 and y[i] == 0.0:
+            assert outs[0][i] == 0.0
+            continue
+        assert float(mp.atan2(mp.mpf(float(y[i])), mp.mpf(float(x[i])))) == outs[0][i], (y[i], x[i])
 
 
 def test_device_norm_comparisons_without_sqrt(mathlib):

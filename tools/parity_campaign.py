@@ -36,6 +36,8 @@ LEGS = [
          agent_radius=10, agent_max_speed=20, planner="Primitive", gaze="Oxford", B=8192, steps=300),
     dict(name="empty_map Primitive + Oxford (config 1 loop)", static_map="maps/empty_map.npy", agent_number=10,
          agent_radius=15, agent_max_speed=20, planner="Primitive", gaze="Oxford", B=4096, steps=250),
+    dict(name="empty_map Primitive + Owl", static_map="maps/empty_map.npy", agent_number=10, agent_radius=15,
+         agent_max_speed=20, planner="Primitive", gaze="Owl", B=4096, steps=250),
     dict(name="random_map_0 N=142 Primitive scripted gaze (config 3)", static_map="maps/random_map_0.npy", agent_number=20,
          agent_radius=15, agent_max_speed=40, planner="Primitive", B=4096, steps=150),
     dict(name="empty_map noisy measurements var_cam=0.5", static_map="maps/empty_map.npy", agent_number=10, agent_radius=15,
@@ -54,15 +56,16 @@ def run_leg(leg, scale, seed0):
     from gym_drone2d_activeperception_b200.world import generate_worlds
     B = max(64, int(leg["B"] * min(1.0, scale)))
     steps = max(10, int(leg["steps"] * max(1.0, scale) if scale >= 1 else leg["steps"] * scale))
-    use_ox = leg.get("gaze") == "Oxford"
+    gaze = leg.get("gaze")
+    use_ox = gaze in ("Oxford", "Owl")                     # a gaze policy on the device picks the actions
     rvo = leg.get("motion_profile") == "RVO"
-    p = Params(debug=False, planner=leg["planner"], gaze_method="Oxford" if use_ox else "NoControl", map_id=seed0,
+    p = Params(debug=False, planner=leg["planner"], gaze_method=gaze if use_ox else "NoControl", map_id=seed0,
                static_map=leg["static_map"], agent_number=leg["agent_number"], agent_radius=leg["agent_radius"],
                agent_max_speed=leg["agent_max_speed"], var_cam=leg.get("var_cam", 0),
                motion_profile=leg.get("motion_profile", "CVM"), pillar_number=leg.get("pillar_number", 0))
     t0 = time.time()
     worlds = generate_worlds(p, seed0 + np.arange(B))
-    env = Drone2DVecEnv(p, B, worlds=worlds, device="cuda:0", auto_reset=True, oxford=use_ox)
+    env = Drone2DVecEnv(p, B, worlds=worlds, device="cuda:0", auto_reset=True)     # policy state follows p.gaze_method
     n = env.num_agents
     rng = np.random.RandomState(seed0)
     poses = None
@@ -89,8 +92,8 @@ def run_leg(leg, scale, seed0):
     for t in range(steps):
         act_bad = np.zeros(B, dtype=bool)
         if use_ox:
-            a_dev = env.plan_oxford()
-            want, _ = ob.step(policy="Oxford", auto_reset=True)
+            a_dev = env.plan_gaze(gaze)
+            want, _ = ob.step(policy=gaze, auto_reset=True)
             act_bad = a_dev.cpu().numpy() != want
             a_dev = torch.as_tensor(want, device="cuda:0")        # keep diverged envs from cascading through the action
         else:
@@ -102,7 +105,7 @@ def run_leg(leg, scale, seed0):
         o = ob.gather(trackers=True, rvo=rvo)
         d, r = util.batch_mismatch(h, o, n, trackers=True, planner=n_way)
         if use_ox:
-            d["oxford_action"] = act_bad
+            d["gaze_action"] = act_bad
         if rvo:
             a, b = h["agent_vel"][:, :n].reshape(B, -1), o["agent_vel"][:, :n].reshape(B, -1)
             r["agent_vel"] = (np.abs(a - b) / np.maximum(1.0, np.abs(b))).max(1)
