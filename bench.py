@@ -422,21 +422,27 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
     stage = env.buffer("actions_staging")
     Ke = int(min(2000, max(K, -(-(0.5 * args.region_ms) // (est_ms / K + 0.02)))))
 
-    def e2e_step(t):
+    def e2e_step_host(t):
         if use_ox:      # the policy runs on the device: its actions never leave the GPU, the observation still does
             env.plan_oxford(stage)
             env.step_host(None, lm_host, yaw_host, done_host)
         else:
             env.step_host(a_rows[t % (K + W)], lm_host, yaw_host, done_host)
+    stepper = [e2e_step_host]
+    warm = [True]
+    e2e_bound_s = None
 
     def e2e_loop():
+        step = stepper[0]
+        warm[0] = True
         for t in range(3):
-            e2e_step(t)
+            step(t)
+        warm[0] = False
         ctx.barrier()
         st0 = env.stats()
         t0 = time.perf_counter()
         for t in range(Ke):
-            e2e_step(t)
+            step(t)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         ctx.barrier()
@@ -445,15 +451,46 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
     # (a) plain copies: every step moves the whole observation tensor device -> host
     e2e_copy_s, _ = e2e_loop()
     # (b) the library's zero-copy mirror (d2d_bind_host_mirror): the kernels store the observation bytes that change
-    #     straight into the pinned host buffers; the step call copies nothing back.  This is the headline e2e.
+    #     straight into the pinned host buffers; the step call copies nothing back
+    e2e_mirror_s = None
     if args.e2e_full_copy:
         e2e_s, mirror_bytes = e2e_copy_s, None
     else:
         env.bind_host_mirror(lm_host, yaw_host, done_host)
-        e2e_s, dst = e2e_loop()
+        e2e_mirror_s, dst = e2e_loop()
         mirror_bytes = float(dst[14]) / Ke
         assert torch.equal(lm_host, env.buffer("local_map").cpu()) and torch.equal(done_host, env.buffer("done").cpu())
         env.bind_host_mirror(None, None, None)
+        # (c) the bound form of the same call (d2d_bind_host_io + d2d_step_bound): host buffers given once, the caller
+        #     rewrites the pinned action buffer in place (a 8*B-byte host memcpy, inside the timed region), one C call per
+        #     step; with the NoMove planner the step kernel signals completion through a pinned flag the host polls.
+        #     This is the headline e2e.
+        import ctypes
+        a_bound = torch.zeros(B, dtype=torch.float64).pin_memory()
+        env.bind_host_io(None if use_ox else a_bound, lm_host, yaw_host, done_host)
+        dstp, nbytes = a_bound.data_ptr(), B * 8
+        srcs = [r.data_ptr() for r in a_rows]
+
+        def e2e_step_bound(t):
+            if use_ox:
+                env.plan_oxford(stage)
+            else:
+                ctypes.memmove(dstp, srcs[t % (K + W)], nbytes)
+            env.step_bound()
+
+        def e2e_step_pipelined(t):
+            # the timed loop runs t = 0 .. Ke-1 after a 3-step warm-up: the warm-up's last step and the run's last step do not
+            # pre-launch (the loop's barrier / statistics calls follow them)
+            ctypes.memmove(dstp, srcs[t % (K + W)], nbytes)
+            env.step_pipelined(prelaunch_next=not (t == Ke - 1 or (t == 2 and warm[0])))
+        stepper[0] = e2e_step_bound
+        e2e_bound_s, _ = e2e_loop()
+        if not use_ox and pk["planner"] == "NoMove":
+            stepper[0] = e2e_step_pipelined
+        e2e_s, dst = e2e_loop()
+        mirror_bytes = float(dst[14]) / Ke
+        assert torch.equal(lm_host, env.buffer("local_map").cpu()) and torch.equal(done_host, env.buffer("done").cpu())
+        env.bind_host_io(None, None, None, None)
     clocks = None
     if headline:
         # clock / throttle sampling needs a loaded window: keep stepping back to back (untimed, same kernel) for ~1.5 s
@@ -464,9 +501,12 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
         clocks = sampler.stop()
 
     # ---- over ranks: max of the per-rank medians; every rank's figures are reported
-    rows = ctx.gather_rows([med_ms / K, min_ms / K, max_ms / K, e2e_s * 1e3 / Ke, e2e_copy_s * 1e3 / Ke])
+    rows = ctx.gather_rows([med_ms / K, min_ms / K, max_ms / K, e2e_s * 1e3 / Ke, e2e_copy_s * 1e3 / Ke,
+                            (e2e_mirror_s if e2e_mirror_s is not None else e2e_copy_s) * 1e3 / Ke,
+                            (e2e_bound_s if e2e_bound_s is not None else e2e_copy_s) * 1e3 / Ke])
     ms_step = float(rows[:, 0].max())
-    e2e_ms, e2e_copy_ms = float(rows[:, 3].max()), float(rows[:, 4].max())
+    e2e_ms, e2e_copy_ms, e2e_mirror_ms = float(rows[:, 3].max()), float(rows[:, 4].max()), float(rows[:, 5].max())
+    e2e_bound_ms = float(rows[:, 6].max())
     # the one collective of the path: all-reduce of the episode statistics
     stats = ctx.D.allreduce_stats(sum(np.asarray(e.stats(), dtype=np.int64) for e in envs), device=dev)
     value = world * B / (ms_step * 1e-3)
@@ -503,9 +543,19 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
                 "d2h_bytes_per_step": B * (1089 + 4 + 1) if mirror_bytes is None else int(round(B * 5 + mirror_bytes)),
                 "steps": Ke,
                 "transport": "cudaMemcpyAsync of the whole observation every step" if mirror_bytes is None else
-                             "d2d_bind_host_mirror: kernels store changed observation bytes + yaw + done straight into "
-                             "the pinned host buffers (bytes counted on the device, mean per step, this rank)",
-                "full_copy": {"value": world * B / (e2e_copy_ms * 1e-3), "d2h_bytes_per_step": B * (1089 + 4 + 1)}},
+                             "d2d_bind_host_io: pinned action buffer rewritten by the caller every step (memcpy inside the timed "
+                             "region) and read by the kernels in place; kernels store changed observation bytes + yaw + done "
+                             "straight into the pinned host buffers (bytes counted on the device, mean per step, this rank); " +
+                             ("d2d_step_bound, stream synchronised per step" if (use_ox or pk["planner"] != "NoMove") else
+                              "d2d_step_pipelined: the next step's kernel is launched behind the current one and waits for its "
+                              "actions at a gate before the yaw update (the only action-dependent part of a step); every call "
+                              "returns this step's observation before the next actions are written"),
+                "bound_sync": {"value": world * B / (e2e_bound_ms * 1e-3),
+                               "what": "d2d_step_bound per step (bound buffers, stream synchronised every step, nothing pre-launched)"},
+                "mirror_step_host": {"value": world * B / (e2e_mirror_ms * 1e-3),
+                                     "what": "d2d_step_host per step with the zero-copy mirror bound (round-1 headline path)"},
+                "full_copy": {"value": world * B / (e2e_copy_ms * 1e-3), "d2h_bytes_per_step": B * (1089 + 4 + 1),
+                              "what": "d2d_step_host per step, whole observation copied device -> host every step"}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "bytes_per_env_step": algorithmic_bytes(N),

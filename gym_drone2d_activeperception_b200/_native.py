@@ -36,13 +36,26 @@ class D2DConfig(C.Structure):
     ]
 
 
+JERK_H, JERK_MAXT = 72, 40
+
+
+class D2DJerkTables(C.Structure):
+    _fields_ = [
+        ("dx", C.c_double * JERK_H), ("dy", C.c_double * JERK_H),
+        ("T", C.c_double * JERK_H), ("Tp", (C.c_double * 4) * JERK_H),
+        ("times", C.c_int32 * JERK_H),
+        ("tt", (C.c_double * JERK_MAXT) * JERK_H), ("ttp", ((C.c_double * 4) * JERK_MAXT) * JERK_H),
+        ("tie_order", (C.c_uint8 * JERK_H) * 144),
+    ]
+
+
 class D2DBufferInfo(C.Structure):
     _fields_ = [("dev_ptr", C.c_void_p), ("nbytes", C.c_int64), ("dtype", C.c_int32), ("ndim", C.c_int32),
                 ("shape", C.c_int64 * 4), ("strides", C.c_int64 * 4)]
 
 
-EXPORTS = ["d2d_version", "d2d_last_error", "d2d_create", "d2d_destroy", "d2d_set_world", "d2d_set_rng", "d2d_set_rvo", "d2d_reset", "d2d_step",
-           "d2d_step_host", "d2d_bind_host_mirror", "d2d_bind_host_io", "d2d_step_bound", "d2d_plan_oxford", "d2d_plan_gaze", "d2d_set_drone_pose", "d2d_get_buffer", "d2d_stats",
+EXPORTS = ["d2d_version", "d2d_last_error", "d2d_create", "d2d_destroy", "d2d_set_world", "d2d_set_rng", "d2d_set_rvo", "d2d_set_jerk_tables", "d2d_reset", "d2d_step",
+           "d2d_step_host", "d2d_bind_host_mirror", "d2d_bind_host_io", "d2d_step_bound", "d2d_step_pipelined", "d2d_plan_oxford", "d2d_plan_gaze", "d2d_set_drone_pose", "d2d_get_buffer", "d2d_stats",
            "d2d_launch_count"]
 
 _lib = None
@@ -71,12 +84,14 @@ def load():
     L.d2d_set_world.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
     L.d2d_set_rng.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
     L.d2d_set_rvo.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32]
+    L.d2d_set_jerk_tables.argtypes = [vp, C.POINTER(D2DJerkTables)]
     L.d2d_reset.argtypes = [vp, vp, vp]
     L.d2d_step.argtypes = [vp, vp, vp]
     L.d2d_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.d2d_bind_host_mirror.argtypes = [vp, vp, vp, vp]
     L.d2d_bind_host_io.argtypes = [vp, vp, vp, vp, vp, vp]
     L.d2d_step_bound.argtypes = [vp]
+    L.d2d_step_pipelined.argtypes = [vp, C.c_int32]
     L.d2d_plan_oxford.argtypes = [vp, vp, vp]
     L.d2d_plan_gaze.argtypes = [vp, C.c_int32, vp, vp]
     L.d2d_set_drone_pose.argtypes = [vp, vp, vp]

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     if (lane == 0) d2d_leader_begin(P, s);
     __syncwarp();
     RayOut ro;
-    ro.bel_s = c.belief; ro.e = e; ro.patch = 0; ro.wi = 0; ro.wj = 0; ro.chg = chg; ro.nchg = &cnt[1];
+    ro.bel_s = c.belief; ro.e = e; ro.patch = 0; ro.wi = 0; ro.wj = 0; ro.chg = chg; ro.nchg = &cnt[1]; ro.defer_mirror = 0;
     d2d_mbar_wait(c.mbar, 0);
     ro.border_ok = d2d_border_intact(c.gt, lane);
     d2d_phase_rays_warp<false>(P, c, ro, lane);
@@ -327,6 +327,191 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
         }
         d2d_store_env_warp(P, s, e, lane);
     }
+}
+
+
+// ------------------------------------------------------------------------------------------ Jerk_Primitive  traj_planner.py:403-516
+// Every step: rank the 72 headings by squared angular distance to the goal bearing (:471-478), take the first heading whose
+// minimum-jerk primitive (Mueller's closed form, :413-460) is collision-free at every sample (:482-491) and append its FIRST
+// sample as the waypoint step_pos consumes in the same step (:496-499).  One warp per env, whole step in one launch.
+//   * heading order: unique (ascending cost) unless the bearing is an exact multiple of 2.5 degrees, where pairs tie and the
+//     order is the host numpy's recorded argsort (d2d_jerk_tables.tie_order);
+//   * per-heading constants (end-point offset, T and its powers, sample times and their powers) come from the host tables;
+//   * evaluation: lanes = (heading in rank order, sample); PACK headings are tested per pass, the lowest-ranked free one wins.
+// replan_check (:503-516) always sees an empty trajectory (plan appends one waypoint, step_pos pops it) and returns False.
+__device__ __forceinline__ bool d2d_jerk_plan_warp(const DevP &P, EnvS &s, const uint8_t *bel, const double *trk, int nact,
+                                                   int e, int lane, double *cost_s, uint8_t *order_s) {
+    const d2d_jerk_tables &J = *P.jerk;
+    const double RAD2DEG = 180.0 / D2D_PI;
+    const double p0x = s.px, p0y = s.py, v0x = s.vx, v0y = s.vy;
+    const double2 a0 = s.reset ? double2{0.0, 0.0} : P.drone_acc[e];
+    const double phi_h = d2d_atan2_cr(s.tgy - p0y, s.tgx - p0x) * RAD2DEG;
+    const double pm = d2d_pymod(phi_h, 360.0);
+    const double q = pm / 2.5;
+    if (q == floor(q) && q >= 0.0 && q < 144.0) {
+        const uint8_t *row = J.tie_order[(int)q];
+        for (int i = lane; i < D2D_JERK_H; i += 32) order_s[i] = row[i];
+    } else {
+        for (int i = lane; i < D2D_JERK_H; i += 32) {
+            const double d = fabs(5.0 * (double)i - pm);
+            const double c = d <= 180.0 ? d : 360.0 - d;
+            cost_s[i] = c * c;
+        }
+        __syncwarp();
+        for (int i = lane; i < D2D_JERK_H; i += 32) {          // rank by counting (stable; the costs are distinct here)
+            const double ci = cost_s[i];
+            int r = 0;
+#pragma unroll 1
+            for (int j = 0; j < D2D_JERK_H; j++) { const double cj = cost_s[j]; r += (cj < ci || (cj == ci && j < i)) ? 1 : 0; }
+            order_s[r] = (uint8_t)i;
+        }
+    }
+    __syncwarp();
+    int tmax = 1;
+    for (int i = lane; i < D2D_JERK_H; i += 32) tmax = max(tmax, J.times[i]);
+    tmax = __reduce_max_sync(0xffffffffu, tmax);
+    const int pack = tmax <= 32 ? 32 / tmax : 1;               // headings tested per pass
+    const double v_max = P.max_speed;
+    bool found = false;
+#pragma unroll 1
+    for (int r0 = 0; r0 < D2D_JERK_H && !found; r0 += pack) {
+        // samples beyond 32 (drone_max_speed < ~12): the lane walks them with stride 32 (pack == 1 then)
+        const int sub = pack > 1 ? lane / tmax : 0, jj0 = pack > 1 ? lane - sub * tmax : lane;
+        const int r = r0 + sub;
+        const bool live = sub < pack && r < D2D_JERK_H;
+        const int h = live ? order_s[r] : 0;
+        bool coll = false;
+        double fpx = 0, fpy = 0, fvx = 0, fvy = 0, fax = 0, fay = 0;
+        if (live) {
+            const double T = J.T[h];
+            const double *Tp = J.Tp[h];
+            const double pfx = p0x + J.dx[h], pfy = p0y + J.dy[h];
+            const double lx = s.tgx - pfx, ly = s.tgy - pfy;
+            const double sc = 0.5 * v_max / d2d_norm2(lx, ly);
+            const double vfx = sc * lx, vfy = sc * ly;
+            double al[2], be[2], ga[2];
+            const double a0v[2] = {a0.x, a0.y}, v0v[2] = {v0x, v0y}, p0v[2] = {p0x, p0y}, pfv[2] = {pfx, pfy}, vfv[2] = {vfx, vfy};
+#pragma unroll
+            for (int ii = 0; ii < 2; ii++) {
+                const double delt_a = 0.0 - a0v[ii];
+                const double delt_v = vfv[ii] - v0v[ii] - a0v[ii] * T;
+                const double delt_p = pfv[ii] - p0v[ii] - v0v[ii] * T - 0.5 * a0v[ii] * Tp[0];
+                al[ii] = delt_a * 60.0 / Tp[1] - delt_v * 360.0 / Tp[2] + delt_p * 720.0 / Tp[3];
+                be[ii] = -delt_a * 24.0 / Tp[0] + delt_v * 168.0 / Tp[1] - delt_p * 360.0 / Tp[2];
+                ga[ii] = delt_a * 3.0 / T - delt_v * 24.0 / Tp[0] + delt_p * 60.0 / Tp[1];
+            }
+            const int times = J.times[h];
+#pragma unroll 1
+            for (int jj = jj0; jj < times; jj += (pack > 1 ? D2D_JERK_MAXT : 32)) {
+                const double tt = J.tt[h][jj];
+                const double *tp = J.ttp[h][jj];
+                double pos[2], vel[2], acc[2];
+#pragma unroll
+                for (int ii = 0; ii < 2; ii++) {
+                    pos[ii] = al[ii] / 120.0 * tp[3] + be[ii] / 24.0 * tp[2] + ga[ii] / 6.0 * tp[1] + a0v[ii] / 2.0 * tp[0] + v0v[ii] * tt + p0v[ii];
+                    vel[ii] = al[ii] / 24.0 * tp[2] + be[ii] / 6.0 * tp[1] + ga[ii] / 2.0 * tp[0] + a0v[ii] * tt + v0v[ii];
+                    acc[ii] = al[ii] / 6.0 * tp[1] + be[ii] / 2.0 * tp[0] + ga[ii] * tt + a0v[ii];
+                }
+                if (jj == 0) { fpx = pos[0]; fpy = pos[1]; fvx = vel[0]; fvy = vel[1]; fax = acc[0]; fay = acc[1]; }
+                if (!d2d_is_free(P, bel, pos[0], pos[1], tt, trk, nact)) coll = true;
+            }
+        }
+        const unsigned cm = __ballot_sync(0xffffffffu, coll);
+        int win = -1;
+        for (int k = 0; k < pack && win < 0; k++) {
+            if (r0 + k >= D2D_JERK_H) break;
+            const unsigned m = pack > 1 ? (((tmax >= 32 ? 0xffffffffu : ((1u << tmax) - 1u))) << (k * tmax)) : 0xffffffffu;
+            if ((cm & m) == 0u) win = k;
+        }
+        if (win >= 0) {
+            found = true;
+            const int src = pack > 1 ? win * tmax : 0;             // the lane that evaluated sample 0 of the winning heading
+            fpx = __shfl_sync(0xffffffffu, fpx, src); fpy = __shfl_sync(0xffffffffu, fpy, src);
+            fvx = __shfl_sync(0xffffffffu, fvx, src); fvy = __shfl_sync(0xffffffffu, fvy, src);
+            fax = __shfl_sync(0xffffffffu, fax, src); fay = __shfl_sync(0xffffffffu, fay, src);
+            if (lane == 0) {
+                s.jerk_has = 1; s.jerk_px = fpx; s.jerk_py = fpy; s.jerk_vx = fvx; s.jerk_vy = fvy; s.jerk_ax = fax; s.jerk_ay = fay;
+            }
+        }
+    }
+    __syncwarp();
+    return found;
+}
+
+__host__ __device__ inline size_t d2d_jerk_warp_extra(int NP) { return d2d_prim_warp_extra(NP) + D2D_JERK_H * 8 + 96; }
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_jerk_warp_kernel(const DevP P,
+                                                                               const double *__restrict__ actions) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int e = blockIdx.x * WPB + wid;
+    if (e >= P.B) return;
+    unsigned char *slice = smem + (size_t)wid * d2d_warp_slice_bytes(P.NP, P.HW, d2d_jerk_warp_extra(P.NP));
+    const BlockCtx c = d2d_carve(slice, 1, P.NP, P.HW);
+    double *trk = (double *)(slice + d2d_step_smem_bytes(1, P.NP, P.HW));   // [NP][5]
+    uint32_t *chg = (uint32_t *)(trk + (size_t)P.NP * 5);                  // [D2D_CHG_CAP]
+    int *cnt = (int *)(chg + D2D_CHG_CAP);                                 // [0] nact, [1] nchg
+    double *cost_s = (double *)(cnt + 8);                                  // [72]
+    uint8_t *order_s = (uint8_t *)(cost_s + D2D_JERK_H);                   // [72]
+    EnvS &s = c.S[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], (unsigned long long)P.B);
+    double2 pf_pos = double2{0.0, 0.0}, pf_pref = double2{0.0, 0.0};
+    double pf_r = 0.0;
+    uint8_t pf_act = 0;
+    if (lane < P.N) {
+        const size_t g = (size_t)e * P.NP + lane;
+        pf_pos = P.apos[g]; pf_pref = P.apref[g]; pf_r = P.arad[g];
+        if (P.trackers) pf_act = P.trk_active[g];
+    }
+    const double action = actions[e];
+    if (lane == 0) {
+        d2d_mbar_init(c.mbar, 1);
+        d2d_mbar_expect_tx(c.mbar, D2D_GT_ROW_BYTES + D2D_BELIEF_STRIDE);
+        d2d_bulk_g2s(c.gt, P.gt_rows + (size_t)e * D2D_GRID, D2D_GT_ROW_BYTES, c.mbar);
+        d2d_bulk_g2s(c.belief, P.belief + (size_t)e * D2D_BELIEF_STRIDE, D2D_BELIEF_STRIDE, c.mbar);
+        c.misc[0] = 0;
+        cnt[0] = 0; cnt[1] = 0;
+    }
+    d2d_load_env_warp(P, s, e, lane);
+    if (lane == 0) c.misc[1] = s.reset;
+#pragma unroll 1
+    for (int w = lane; w < P.HW; w += 32) c.hitw[w] = 0u;
+    __syncwarp();
+    d2d_reset_prefetch(P, s, e, lane, pf_pos, pf_pref);
+    d2d_reset_arrays(P, c, e, 1, lane, 32, c.mbar);
+    d2d_phase_agents<false, true>(P, c, e, 1, lane, 32, pf_pos, pf_pref, pf_r);
+    if (pf_act && !s.reset) d2d_prefetch_tracker(P, (size_t)e * P.NP + lane);
+    if (lane == 0) d2d_leader_begin(P, s);
+    __syncwarp();
+    RayOut ro;
+    ro.bel_s = c.belief; ro.e = e; ro.patch = 0; ro.wi = 0; ro.wj = 0; ro.chg = chg; ro.nchg = &cnt[1]; ro.defer_mirror = 0;
+    d2d_mbar_wait(c.mbar, 0);
+    ro.border_ok = d2d_border_intact(c.gt, lane);
+    d2d_phase_rays_warp<false>(P, c, ro, lane);
+    __syncwarp();
+    if (P.var_cam != 0.0) {
+        if (lane == 0) d2d_measure_env(P, c, e);
+        __syncwarp();
+    }
+    d2d_phase_trackers<true>(P, c, e, 1, lane, 32, pf_act);
+    __syncwarp();
+    d2d_gather_trackers(P, e, trk, &cnt[0], lane, 32);
+    __syncwarp();
+    if (lane == 0) {
+        s.bufc += s.arch_cnt; s.bufts += s.arch_ts; s.tracked += s.newly;
+        s.arch_cnt = 0; s.arch_ts = 0; s.newly = 0;
+    }
+    __syncwarp();
+    const bool ok = d2d_jerk_plan_warp(P, s, c.belief, trk, cnt[0], e, lane, cost_s, order_s);
+    if (lane == 0) {
+        P.replan[e] = 0; P.plan_ok[e] = ok ? 1 : 0; P.need_plan[e] = 0;
+        if (s.reset) P.drone_acc[e] = double2{0.0, 0.0};
+        atomicAdd(&P.stats[D2D_STAT_PLANS], 1ull);
+        if (!ok) atomicAdd(&P.stats[D2D_STAT_PLAN_FAILURES], 1ull);
+    }
+    __syncwarp();
+    d2d_finish_env_warp(P, c, s, e, lane, action, ok, true, cnt[1], chg, true);
 }
 
 // completes the step of the envs that went through d2d_plan_kernel (one warp per list entry, grid-stride)

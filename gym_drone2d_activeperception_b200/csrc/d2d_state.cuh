@@ -82,11 +82,11 @@ struct DevP {
     uint8_t *lm_mirror;          // [B][1][33][33] or null
     float *yaw_mirror;           // [B] or null
     uint8_t *done_mirror;        // [B] or null
-    // completion signal of the bound host path (d2d_bind_host_io / d2d_step_bound): every warp counts itself out after a
-    // system-scope fence; the last one publishes the step's sequence number into mapped host memory, which the host polls
-    unsigned int *sig_ctr;       // device counter (null: no signal)
-    volatile unsigned int *sig_flag;   // device-visible address of the pinned host flag
-    unsigned int sig_seq;
+    // pipelined host path (d2d_step_pipelined): the kernel of a step is launched BEFORE the caller has chosen that step's
+    // actions and runs everything that does not depend on them; just before the yaw update every warp waits until its
+    // action has replaced the sentinel in the device staging buffer (delivered by the host's copy engine)
+    unsigned long long *gate;            // the device staging buffer viewed as 64-bit slots (null: actions are valid at launch)
+    unsigned int *gate_fault;            // pinned host word, set when a warp gave up waiting (the actions never came)
 #ifdef D2D_WARP_PROF
     unsigned long long *prof;    // [B][12]: 10 globaltimer stamps, smid, warpid of the fused warp kernel (tools/warp_prof.py builds with -DD2D_WARP_PROF)
 #endif
@@ -116,6 +116,9 @@ struct DevP {
     int *owl_q;                  // [B] entries left in the repeated-action queue `self.u`
     double *owl_u;               // [B] the queued action (deg/s)
     int n_owl_u, owl_repeat;
+    // Jerk_Primitive planner (traj_planner.py:403-516)
+    const d2d_jerk_tables *jerk; // per-heading tables in device memory (null unless planner == D2D_PLANNER_JERK)
+    double2 *drone_acc;          // [B] Drone2D.acceleration (utils.py:724, 735): only this planner reads it
     unsigned long long *stats;   // [D2D_NUM_STATS]
     unsigned char *plan_ws;      // A* workspaces (Primitive planner)
     int *plan_list;              // [B+8]: compacted list of envs that need a plan; [B] count (block path); [B+1], [B+2]

@@ -62,6 +62,9 @@ struct EnvS : EnvRec {
     int valid, reset, ncull, coll_agent;
     int arch_cnt, arch_ts, act_cnt, act_ts, newly;
     int done_now, ix, iy, ox_was_fresh, owl_was_fresh;
+    // Jerk_Primitive: the single waypoint plan() appended this step (traj_planner.py:496-499), consumed by step_pos
+    int jerk_has;
+    double jerk_px, jerk_py, jerk_vx, jerk_vy, jerk_ax, jerk_ay;
 };
 
 struct BlockCtx {
@@ -117,9 +120,10 @@ __device__ __forceinline__ void d2d_env_begin(const DevP &P, EnvS &s, bool was_d
         s.px = s.p0x; s.py = s.p0y; s.yaw = s.p0yaw; s.vx = 0; s.vy = 0; s.tgx = s.p0x; s.tgy = s.p0y;
         s.steps = 0; s.sm = SM_WAIT_FOR_GOAL; s.fail = 0; s.tcur = 0; s.bufc = 0; s.bufts = 0; s.tracked = 0;
         s.nseg = 0; s.cursor = 0;
+        if (P.planner == D2D_PLANNER_JERK) { s.tgx = 0.0; s.tgy = 0.0; }   // Jerk_Primitive.__init__: target = np.zeros(4) (:406)
     }
     s.ix = d2d_cell(s.px, P.scale, P.inv_scale); s.iy = d2d_cell(s.py, P.scale, P.inv_scale);
-    s.valid = 1; s.reset = rs;
+    s.valid = 1; s.reset = rs; s.jerk_has = 0;
     s.ncull = 0; s.coll_agent = 0; s.arch_cnt = 0; s.arch_ts = 0; s.act_cnt = 0; s.act_ts = 0; s.newly = 0; s.done_now = 0;
 }
 
@@ -310,8 +314,12 @@ struct RayOut {
     int border_ok;            // 1: every border cell of this env's ground truth is a wall (no ray can leave the grid)
     uint32_t *chg;            // optional shared-memory list of changed cells (cell | value << 16), null if unused
     int *nchg;                // its counter (entries beyond the capacity are counted but not stored)
+    int defer_mirror;         // 1: host-mirror stores of patched cells are NOT issued here but replayed from `chg` at the end of
+                              // the step (fused warp kernel: keeps PCIe stores out of the march and behind the action gate)
 };
 #define D2D_CHG_CAP 64
+#define D2D_ACTION_SENTINEL 0x7FF8D2D0AC710F05ull      // a NaN payload no caller produces: "action not delivered yet"
+#define D2D_FUSED_WARP_EXTRA (D2D_CHG_CAP * 4 + 16)   // changed-cell list + counter behind every warp slice of the fused kernel
 
 // a belief cell changes value (0 -> 1 or 0 -> 2): shared copy, HBM grid, and whatever mirrors the observation
 __device__ __forceinline__ void d2d_mark_store(const DevP &P, const RayOut &o, int cell, uint8_t v) {
@@ -323,7 +331,7 @@ __device__ __forceinline__ void d2d_mark_store(const DevP &P, const RayOut &o, i
         if ((unsigned)u < (unsigned)D2D_LOCAL && (unsigned)w < (unsigned)D2D_LOCAL) {
             const size_t off = (size_t)o.e * D2D_LOCAL_CELLS + u * D2D_LOCAL + w;
             P.local_map[off] = v;
-            if (P.lm_mirror) {  // one byte over PCIe; counted in the padding word behind the shared belief grid
+            if (P.lm_mirror && !o.defer_mirror) {  // one byte over PCIe; counted in the padding word behind the shared belief grid
                 P.lm_mirror[off] = v;
                 atomicAdd((int *)(o.bel_s + D2D_MIRCNT_OFF), 1);
             }
@@ -584,7 +592,7 @@ __device__ __forceinline__ void d2d_phase_rays(const DevP &P, const BlockCtx &c,
         if (!s.valid) continue;
         RayOut o;
         o.bel_s = c.belief + (size_t)i * D2D_BELIEF_STRIDE;
-        o.e = env0 + i; o.patch = 0; o.wi = 0; o.wj = 0; o.border_ok = 0; o.chg = nullptr; o.nchg = nullptr;
+        o.e = env0 + i; o.patch = 0; o.wi = 0; o.wj = 0; o.border_ok = 0; o.chg = nullptr; o.nchg = nullptr; o.defer_mirror = 0;
         const double a = d2d_ray_angle(P, s.yaw, ray);
         const uint32_t hm = d2d_cast_ray(P, s, a, d2d_tan(a), o, c.gt + (size_t)i * D2D_GRID, c.sx + i * NP, c.sy + i * NP,
                                          c.sr2 + i * NP, c.cull + i * NP, c.hitw + i * P.HW);
@@ -878,7 +886,13 @@ __device__ D2D_COLD void d2d_leader_finish(const DevP &P, EnvS &s, const uint64_
     }
     // step_pos utils.py:733-739: pop one waypoint
     const int remaining = s.nseg * P.n_way - s.cursor;
-    if (remaining > 0) {
+    if (P.planner == D2D_PLANNER_JERK) {
+        if (s.jerk_has) {       // acceleration, velocity = the waypoint's; x, y = round(position)
+            P.drone_acc[e] = double2{s.jerk_ax, s.jerk_ay};
+            s.vx = s.jerk_vx; s.vy = s.jerk_vy;
+            s.px = rint(s.jerk_px); s.py = rint(s.jerk_py);
+        }
+    } else if (remaining > 0) {
         const int seg = s.cursor / P.n_way, ws = s.cursor - seg * P.n_way;
         const int ti = P.n_way - 1 - ws;
         const double *cf = P.traj_coeff + ((size_t)e * D2D_MAX_SEGMENTS + seg) * 6;
@@ -1152,14 +1166,22 @@ __device__ __forceinline__ void d2d_prof_stamp(const DevP &P, int e, int k, int 
 #define D2D_PROF(k)
 #endif
 
-template <int WPB, int MINB, bool ILP2>
+// HOSTIO: the instantiation launched while host buffers are attached (d2d_bind_host_mirror / d2d_bind_host_io): host-mirror
+// stores of patched cells are replayed from a changed-cell list at the end of the step instead of being issued inside the
+// march, and the action may arrive late through the gate (d2d_step_pipelined).  The device-resident instantiation
+// (HOSTIO = false) carries none of that.
+template <int WPB, int MINB, bool ILP2, bool HOSTIO>
 __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(const DevP P,
                                                                              const double *__restrict__ actions) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int e = blockIdx.x * WPB + wid;
     if (e >= P.B) return;                                            // warp-uniform
-    const BlockCtx c = d2d_carve(smem + (size_t)wid * d2d_warp_slice_bytes(P.NP, P.HW, 0), 1, P.NP, P.HW);
+    unsigned char *slice = smem + (size_t)wid * d2d_warp_slice_bytes(P.NP, P.HW, HOSTIO ? D2D_FUSED_WARP_EXTRA : 0);
+    const BlockCtx c = d2d_carve(slice, 1, P.NP, P.HW);
+    // changed-cell list of this step (host mirror bound: the PCIe stores are replayed from it at the end of the step)
+    uint32_t *chg = (uint32_t *)(slice + d2d_step_smem_bytes(1, P.NP, P.HW));
+    int *nchg = (int *)(chg + D2D_CHG_CAP);
     EnvS &s = c.S[0];
     D2D_PROF(0);
     // Everything the step needs from HBM is requested up front so that the cold-miss latencies overlap instead of
@@ -1173,8 +1195,10 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
         pf_pos = P.apos[g]; pf_pref = P.apref[g]; pf_r = P.arad[g];
         if (P.trackers) pf_act = P.trk_active[g];
     }
-    const double action = actions[e];                                // same address in every lane: one broadcast request
+    // same address in every lane: one broadcast request.  Pipelined host path: the action is not chosen yet (see the gate)
+    double action = (HOSTIO && P.gate) ? 0.0 : actions[e];
     if (lane == 0) {
+        if (HOSTIO) *nchg = 0;
         d2d_mbar_init(c.mbar, 1);
         d2d_mbar_expect_tx(c.mbar, D2D_GT_ROW_BYTES + D2D_BELIEF_STRIDE);
         d2d_bulk_g2s(c.gt, P.gt_rows + (size_t)e * D2D_GRID, D2D_GT_ROW_BYTES, c.mbar);
@@ -1197,9 +1221,11 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     // is patched in place by the rays (only cells whose value changes) instead of being rewritten
     __syncwarp();
     const bool patch = !s.reset && s.obs_ix == s.ix && s.obs_iy == s.iy;
+    const bool mirror = HOSTIO && P.lm_mirror != nullptr;
     RayOut ro;
     ro.bel_s = c.belief; ro.e = e; ro.patch = patch ? 1 : 0;
-    ro.wi = s.ix - 16; ro.wj = s.iy - 16; ro.chg = nullptr; ro.nchg = nullptr;
+    ro.wi = s.ix - 16; ro.wj = s.iy - 16;
+    ro.chg = (mirror && patch) ? chg : nullptr; ro.nchg = nchg; ro.defer_mirror = HOSTIO ? 1 : 0;
     D2D_PROF(6);
     d2d_mbar_wait(c.mbar, 0);
     ro.border_ok = d2d_border_intact(c.gt, lane);
@@ -1216,6 +1242,24 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     const int shit = __any_sync(0xffffffffu, lane < 5 ? d2d_static_probe(P, c.gt, s.px, s.py, lane) : 0);
     __syncwarp();
     D2D_PROF(8);
+    if (HOSTIO && P.gate) {
+        // Everything above is independent of this step's action (it only turns the yaw at the end of the step,
+        // utils.py:741-743).  P.gate is the device staging buffer: it holds a sentinel until the host's copy engine has
+        // delivered this step's actions (ONE async copy per step, no separate gate word: an aligned 8-byte word arrives
+        // whole).  Each warp waits for its own word, takes it and puts the sentinel back for the next step.  Everything is in
+        // DEVICE memory: a kernel polling pinned host memory is served one PCIe read at a time (measured ~17 ns per warp).
+        if (lane == 0) {
+            volatile unsigned long long *slot = P.gate + e;
+            const long long t0 = clock64();
+            unsigned long long bits;
+            while ((bits = *slot) == D2D_ACTION_SENTINEL) {
+                if (clock64() - t0 > 4000000000ll) { *P.gate_fault = 1u; bits = 0ull; break; }   // ~2 s: the host never came back
+            }
+            action = __longlong_as_double((long long)bits);
+            *slot = D2D_ACTION_SENTINEL;
+        }
+        __syncwarp();
+    }
     if (lane == 0) {
         // NoMove.plan traj_planner.py:70-73 / NoMove.replan_check :75-76; the verdict arrays (replan = 0, plan_ok = 1,
         // need_plan = 0) never change under NoMove: d2d_reset_kernel wrote them once
@@ -1223,30 +1267,27 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
         d2d_leader_finish(P, s, c.gt, e, action, true);
         d2d_leader_flags(P, s, c.gt, e, shit);
         if (e == 0) atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], (unsigned long long)P.B);   // every env steps once per launch
-        if (patch && P.lm_mirror) {
-            const int nb = *(const int *)(c.belief + D2D_MIRCNT_OFF);
-            if (nb) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)nb);
-        }
     }
     __syncwarp();
     D2D_PROF(9);
-    // NoMove never moves the drone, but a pose set from outside (d2d_set_drone_pose) invalidates the window
-    const bool rewrite = !patch || s.ix != s.obs_ix || s.iy != s.obs_iy;
+    // NoMove never moves the drone, but a pose set from outside (d2d_set_drone_pose) invalidates the window; a step that
+    // changed more cells than the list holds rewrites the window as well (the mirror must not miss a cell)
+    const int n_changed = mirror ? *nchg : 0;
+    const bool rewrite = !patch || s.ix != s.obs_ix || s.iy != s.obs_iy || (mirror && n_changed > D2D_CHG_CAP);
     __syncwarp();
     if (rewrite && lane == 0) { s.obs_ix = s.ix; s.obs_iy = s.iy; }
     __syncwarp();
     d2d_store_env_warp(P, s, e, lane);
     if (rewrite) d2d_obs_env_warp(P, c.belief, s.ix, s.iy, e, lane);
+    else if (mirror && n_changed > 0) {
+        // replay this step's changed cells into the host mirror (one byte each over PCIe)
+        for (int q = lane; q < n_changed; q += 32) {
+            const int cell = (int)(chg[q] & 0xFFFFu);
+            const int ci = cell / D2D_GRID, cj = cell - ci * D2D_GRID;
+            P.lm_mirror[(size_t)e * D2D_LOCAL_CELLS + (ci - ro.wi) * D2D_LOCAL + (cj - ro.wj)] = (uint8_t)(chg[q] >> 16);
+        }
+        if (lane == 0) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)n_changed);
+    }
     if (s.done_now) d2d_count_explored_warp(P, c.belief, lane);
     D2D_PROF(3);
-    if (P.sig_ctr) {
-        // bound host path: this warp's stores into the host mirror must be visible to the host before the flag is
-        __syncwarp();
-        __threadfence_system();
-        if (lane == 0 && atomicAdd(P.sig_ctr, 1u) == (unsigned)(P.B - 1)) {
-            *P.sig_ctr = 0u;                       // every warp has counted: rearm for the next launch
-            __threadfence_system();
-            *P.sig_flag = P.sig_seq;
-        }
-    }
 }

@@ -36,6 +36,7 @@ struct d2d_handle {
     bool world_set = false;
     bool rng_set = false;
     bool rvo_set = false;
+    bool jerk_set = false;
     std::string err;
     size_t smem_step = 0, smem_post = 0;
     int plan_threads = 64;
@@ -52,10 +53,27 @@ struct d2d_handle {
     const double *io_actions_dev = nullptr;      // device-visible address of the caller's pinned action buffer (or staging)
     uint8_t *io_lm = nullptr; float *io_yaw = nullptr; uint8_t *io_done = nullptr;
     cudaStream_t io_stream = nullptr;
-    volatile unsigned int *sig_host = nullptr;   // pinned, mapped
-    unsigned int *sig_dev_flag = nullptr, *sig_ctr = nullptr;
-    unsigned int sig_seq = 0;
+    // pipelined stepping (d2d_step_pipelined): gate word + fault word in one pinned, mapped allocation
+    volatile unsigned int *gate_host = nullptr;  // pinned: [16] fault word written by a kernel that gave up waiting
+    unsigned int *gate_dev = nullptr;            // device-visible address of gate_host
+    const double *io_actions_host = nullptr;     // the caller's pinned action buffer (host address)
+    cudaStream_t copy_stream = nullptr;          // carries the per-step action copy
+    unsigned int pipe_seq = 0;
+    bool pipe_inflight = false;                  // the kernel of the NEXT step has been launched and waits at its gate
+    cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};   // [0], [1]: completion of alternate steps; [2]: sentinels in place
+    // D2D_PIPE_DEBUG=1: host-side time of the phases of d2d_step_pipelined, printed by d2d_destroy
+    double dbg_launch_ns = 0, dbg_wait_ns = 0, dbg_total_ns = 0; long dbg_n = 0, dbg_polls = 0;
 };
+#include <time.h>
+static inline double now_ns() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e9 + t.tv_nsec; }
+
+#define D2D_NO_PIPE(h)                                                                                                 \
+    do {                                                                                                               \
+        if ((h)->pipe_inflight) {                                                                                      \
+            (h)->err = "a pipelined step is in flight: finish it with d2d_step_pipelined(h, 0) first";                 \
+            return D2D_ERR_STATE;                                                                                      \
+        }                                                                                                              \
+    } while (0)
 
 // Raises the dynamic shared-memory limit of `func` to 227 KB once per handle.  Per handle, not per process: a handle is
 // driven by one thread at a time (drone2d.h), so no state is shared between threads that drive distinct handles.
@@ -150,6 +168,8 @@ __global__ void d2d_reset_kernel(const DevP P, const uint8_t *__restrict__ mask)
         const double x = P.rec[e].p0x, y = P.rec[e].p0y, yaw = P.rec[e].p0yaw;
         P.rec[e].px = x; P.rec[e].py = y; P.rec[e].yaw = yaw; P.rec[e].vx = 0; P.rec[e].vy = 0;
         P.rec[e].tgx = x; P.rec[e].tgy = y;
+        if (P.planner == D2D_PLANNER_JERK) { P.rec[e].tgx = 0.0; P.rec[e].tgy = 0.0; }   // Jerk_Primitive.__init__ :406
+        P.drone_acc[e] = double2{0.0, 0.0};
         P.rec[e].steps = 0; P.rec[e].sm = SM_WAIT_FOR_GOAL; P.rec[e].fail = 0; P.rec[e].tcur = 0;
         P.collision[e] = 0; P.dead_lock[e] = 0; P.freezing[e] = 0; P.done[e] = 0; P.rec[e].pending_reset = 0;
         P.rec[e].bufc = 0; P.rec[e].bufts = 0; P.rec[e].tracked = 0;
@@ -216,6 +236,11 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     if (cfg->struct_size != (int32_t)sizeof(d2d_config)) { g_create_err = "d2d_config size mismatch (ABI)"; return D2D_ERR_INVALID; }
     if (cfg->num_envs <= 0 || cfg->num_agents < 0 || cfg->num_agents > 4000) { g_create_err = "bad num_envs / num_agents"; return D2D_ERR_INVALID; }
     if (cfg->motion_profile != D2D_MOTION_CVM && cfg->motion_profile != D2D_MOTION_RVO) { g_create_err = "bad motion_profile"; return D2D_ERR_INVALID; }
+    if (cfg->planner < D2D_PLANNER_NOMOVE || cfg->planner > D2D_PLANNER_JERK) { g_create_err = "bad planner"; return D2D_ERR_INVALID; }
+    if (cfg->planner == D2D_PLANNER_JERK && cfg->envs_per_block > 0) {
+        g_create_err = "the Jerk_Primitive planner is only implemented on the default warp-per-env kernel (envs_per_block = 0)";
+        return D2D_ERR_INVALID;
+    }
     if (cfg->motion_profile == D2D_MOTION_RVO && d2d_rvo_smem_bytes(cfg->num_agents) > 200 * 1024) {
         g_create_err = "RVO motion profile: too many agents for one block's shared memory"; return D2D_ERR_INVALID;
     }
@@ -331,6 +356,9 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     size_t o_owlU = add_buf(h, cur, "owl_U", D2D_F64, 2, SHP(B, D2D_OWL_BINS), SHP(D2D_OWL_BINS, 1), owl ? (size_t)sB * D2D_OWL_BINS : 2);
     size_t o_owlq = add_buf(h, cur, "owl_queue_len", D2D_I32, 1, SHP(B), SHP(1), sB);
     size_t o_owlu = add_buf(h, cur, "owl_queue_value", D2D_F64, 1, SHP(B), SHP(1), sB);
+    size_t o_dacc = add_buf(h, cur, "drone_acc", D2D_F64, 2, SHP(B, 2), SHP(2, 1), (size_t)sB * 2);
+    size_t o_jerk = add_buf(h, cur, "jerk_tables", D2D_U8, 1, SHP((int64_t)sizeof(d2d_jerk_tables)), SHP(1),
+                            cfg->planner == D2D_PLANNER_JERK ? sizeof(d2d_jerk_tables) : 16);
     size_t o_stats = add_buf(h, cur, "stats", D2D_I64, 1, SHP(D2D_NUM_STATS), SHP(1), D2D_NUM_STATS);
     size_t o_tab = add_buf(h, cur, "tables", D2D_U8, 1, SHP((int64_t)sizeof(DevTables)), SHP(1), sizeof(DevTables));
     size_t o_stage = add_buf(h, cur, "actions_staging", D2D_F64, 1, SHP(B), SHP(1), sB);
@@ -390,6 +418,8 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.ox_seen = (cfg->oxford & D2D_POLICY_OXFORD) ? (uint16_t *)(A + o_oxs) : nullptr;
     P.owl_U = owl ? (double *)(A + o_owlU) : nullptr; P.owl_q = (int *)(A + o_owlq); P.owl_u = (double *)(A + o_owlu);
     P.n_owl_u = cfg->n_owl_u; P.owl_repeat = cfg->owl_repeat;
+    P.drone_acc = (double2 *)(A + o_dacc);
+    P.jerk = cfg->planner == D2D_PLANNER_JERK ? (const d2d_jerk_tables *)(A + o_jerk) : nullptr;
     P.ox_calls = (int *)(A + o_oxc); P.ox_tab = (const double *)(A + o_oxt); P.ox_last = nullptr;
     P.lm_mirror = nullptr; P.yaw_mirror = nullptr; P.done_mirror = nullptr;
 #ifdef D2D_WARP_PROF
@@ -453,8 +483,18 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
 extern "C" int d2d_destroy(d2d_handle *h) {
     if (!h) return D2D_OK;
     cudaSetDevice(h->cfg.device);
-    if (h->sig_host) cudaFreeHost((void *)h->sig_host);
-    if (h->sig_ctr) cudaFree(h->sig_ctr);
+    if (h->pipe_inflight) {          // release the kernel that waits for its actions (the state is going away anyway)
+        cudaMemsetAsync(h->stage_actions, 0, (size_t)h->B * 8, h->copy_stream);
+        cudaStreamSynchronize(h->io_stream);
+        h->pipe_inflight = false;
+    }
+    if (h->dbg_n && getenv("D2D_PIPE_DEBUG"))
+        fprintf(stderr, "[d2d pipelined] calls %ld: publish+launch %.2f us, wait %.2f us (%.1f event polls), total %.2f us per call\n",
+                h->dbg_n, h->dbg_launch_ns / h->dbg_n * 1e-3, h->dbg_wait_ns / h->dbg_n * 1e-3, (double)h->dbg_polls / h->dbg_n,
+                h->dbg_total_ns / h->dbg_n * 1e-3);
+    if (h->gate_host) cudaFreeHost((void *)h->gate_host);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 3; i++) if (h->pipe_ev[i]) cudaEventDestroy(h->pipe_ev[i]);
     if (h->arena) cudaFree(h->arena);
     if (h->ox_export) cudaFree(h->ox_export);
     delete h;
@@ -596,8 +636,22 @@ extern "C" int d2d_set_rvo(d2d_handle *h, int32_t first_env, int32_t count, cons
     return D2D_OK;
 }
 
+extern "C" int d2d_set_jerk_tables(d2d_handle *h, const d2d_jerk_tables *tables) {
+    if (!h || !tables) return D2D_ERR_INVALID;
+    if (h->cfg.planner != D2D_PLANNER_JERK) { h->err = "d2d_set_jerk_tables: handle was not created with planner = D2D_PLANNER_JERK"; return D2D_ERR_STATE; }
+    for (int i = 0; i < D2D_JERK_H; i++) {
+        if (tables->times[i] <= 0 || tables->times[i] > D2D_JERK_MAXT) { h->err = "d2d_set_jerk_tables: times out of range"; return D2D_ERR_INVALID; }
+        for (int m = 0; m < 144; m++) if (tables->tie_order[m][i] >= D2D_JERK_H) { h->err = "d2d_set_jerk_tables: bad tie order"; return D2D_ERR_INVALID; }
+    }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaMemcpy((void *)h->P.jerk, tables, sizeof(d2d_jerk_tables), cudaMemcpyHostToDevice));
+    h->jerk_set = true;
+    return D2D_OK;
+}
+
 extern "C" int d2d_reset(d2d_handle *h, const uint8_t *mask_dev, void *stream) {
     if (!h) return D2D_ERR_INVALID;
+    D2D_NO_PIPE(h);
     if (!h->world_set) { h->err = "d2d_reset before d2d_set_world"; return D2D_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     d2d_reset_kernel<<<h->B, 128, 0, (cudaStream_t)stream>>>(h->P, mask_dev);
@@ -638,6 +692,7 @@ extern "C" int d2d_bind_host_mirror(d2d_handle *h, uint8_t *local_map_host, floa
 
 extern "C" int d2d_set_drone_pose(d2d_handle *h, const double *pose_host, void *stream) {
     if (!h || !pose_host) return D2D_ERR_INVALID;
+    D2D_NO_PIPE(h);
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     double *tmp = nullptr;
     CUDA_TRY(h, cudaMalloc((void **)&tmp, (size_t)h->B * 24));
@@ -664,21 +719,45 @@ static int launch_fused(d2d_handle *h, const double *actions, cudaStream_t st) {
     return D2D_OK;
 }
 
-template <int WPB, int MINB, bool ILP2>
-static int launch_fused_warp(d2d_handle *h, const double *actions, cudaStream_t st) {
-    const size_t smem = (size_t)WPB * d2d_warp_slice_bytes(h->NP, h->HW, 0);
+template <int WPB, int MINB, bool ILP2, bool HOSTIO>
+static int launch_fused_warp_io(d2d_handle *h, const double *actions, cudaStream_t st) {
+    const size_t smem = (size_t)WPB * d2d_warp_slice_bytes(h->NP, h->HW, HOSTIO ? D2D_FUSED_WARP_EXTRA : 0);
     if (smem > 227 * 1024) { h->err = "warp-per-env kernel: shared memory per block exceeds 227 KB"; return D2D_ERR_INVALID; }
-    const int rc = ensure_smem_attr(h, (const void *)d2d_step_fused_warp_kernel<WPB, MINB, ILP2>, "fused warp");
+    const int rc = ensure_smem_attr(h, (const void *)d2d_step_fused_warp_kernel<WPB, MINB, ILP2, HOSTIO>, "fused warp");
     if (rc != D2D_OK) return rc;
-    d2d_step_fused_warp_kernel<WPB, MINB, ILP2><<<(h->B + WPB - 1) / WPB, WPB * 32, smem, st>>>(h->P, actions);
+    d2d_step_fused_warp_kernel<WPB, MINB, ILP2, HOSTIO><<<(h->B + WPB - 1) / WPB, WPB * 32, smem, st>>>(h->P, actions);
     h->launches++;
     return D2D_OK;
+}
+__global__ void d2d_fill_sentinel_kernel(unsigned long long *p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = D2D_ACTION_SENTINEL;
+}
+
+// host buffers attached (mirror bound / pipelined gate) -> the HOSTIO instantiation; otherwise the device-resident one
+template <int WPB, int MINB, bool ILP2>
+static int launch_fused_warp(d2d_handle *h, const double *actions, cudaStream_t st) {
+    const bool io = h->P.lm_mirror || h->P.yaw_mirror || h->P.done_mirror || h->P.gate;
+    if (io) return launch_fused_warp_io<WPB, MINB, ILP2, true>(h, actions, st);
+    return launch_fused_warp_io<WPB, MINB, ILP2, false>(h, actions, st);
 }
 
 static int step_primitive(d2d_handle *h, const double *actions, cudaStream_t st);
 
+template <int WPB>
+static int launch_jerk_warp(d2d_handle *h, const double *actions, cudaStream_t st) {
+    const size_t smem = (size_t)WPB * d2d_warp_slice_bytes(h->NP, h->HW, d2d_jerk_warp_extra(h->NP));
+    if (smem > 227 * 1024) { h->err = "Jerk_Primitive step kernel: shared memory per block exceeds 227 KB"; return D2D_ERR_INVALID; }
+    const int rc = ensure_smem_attr(h, (const void *)d2d_step_jerk_warp_kernel<WPB>, "jerk warp");
+    if (rc != D2D_OK) return rc;
+    d2d_step_jerk_warp_kernel<WPB><<<(h->B + WPB - 1) / WPB, WPB * 32, smem, st>>>(h->P, actions);
+    h->launches++;
+    return D2D_OK;
+}
+
 extern "C" int d2d_step(d2d_handle *h, const double *actions_dev, void *stream) {
     if (!h || !actions_dev) return D2D_ERR_INVALID;
+    D2D_NO_PIPE(h);
     if (!h->world_set) { h->err = "d2d_step before d2d_set_world"; return D2D_ERR_STATE; }
     if (h->cfg.var_cam != 0.0 && !h->rng_set) { h->err = "var_cam != 0: d2d_set_rng must provide the np.random stream state"; return D2D_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
@@ -709,6 +788,9 @@ extern "C" int d2d_step(d2d_handle *h, const double *actions_dev, void *stream) 
             case 16: rc = launch_fused<16>(h, actions_dev, st); break;
             default: rc = launch_fused<8>(h, actions_dev, st); break;
         }
+    } else if (h->cfg.planner == D2D_PLANNER_JERK) {
+        if (!h->jerk_set) { h->err = "planner = Jerk_Primitive: d2d_set_jerk_tables must provide the heading tables"; return D2D_ERR_STATE; }
+        rc = launch_jerk_warp<4>(h, actions_dev, st);
     } else {
         rc = step_primitive(h, actions_dev, st);
     }
@@ -762,6 +844,12 @@ extern "C" int d2d_bind_host_io(d2d_handle *h, const double *actions_host, uint8
                                 uint8_t *done_host, void *stream) {
     if (!h) return D2D_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->pipe_inflight) {          // re-binding abandons the pre-launched step: it completes with action 0, then re-sync
+        CUDA_TRY(h, cudaMemsetAsync(h->stage_actions, 0, (size_t)h->B * 8, h->copy_stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->io_stream));
+        h->pipe_inflight = false;
+        h->pipe_seq += 1;
+    }
     int rc = d2d_bind_host_mirror(h, local_map_host, yaw_host, done_host);     // synchronises the device first
     if (rc != D2D_OK) return rc;
     h->io_bound = false;
@@ -774,19 +862,22 @@ extern "C" int d2d_bind_host_io(d2d_handle *h, const double *actions_host, uint8
             return D2D_ERR_INVALID;
         }
         h->io_actions_dev = (const double *)at.devicePointer;
+        h->io_actions_host = actions_host;
     } else {
         h->io_actions_dev = h->stage_actions;
+        h->io_actions_host = nullptr;
     }
-    if (!h->sig_host) {
+    if (!h->gate_host) {
         void *p = nullptr;
-        CUDA_TRY(h, cudaHostAlloc(&p, 64, cudaHostAllocMapped));
-        h->sig_host = (volatile unsigned int *)p;
-        *h->sig_host = 0u;
+        CUDA_TRY(h, cudaHostAlloc(&p, 128, cudaHostAllocMapped));
+        memset(p, 0, 128);
+        h->gate_host = (volatile unsigned int *)p;
         void *dp = nullptr;
         CUDA_TRY(h, cudaHostGetDevicePointer(&dp, p, 0));
-        h->sig_dev_flag = (unsigned int *)dp;
-        CUDA_TRY(h, cudaMalloc((void **)&h->sig_ctr, 64));
-        CUDA_TRY(h, cudaMemset(h->sig_ctr, 0, 64));
+        h->gate_dev = (unsigned int *)dp;
+        for (int i = 0; i < 3; i++) CUDA_TRY(h, cudaEventCreateWithFlags(&h->pipe_ev[i], cudaEventDisableTiming));
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+
     }
     h->io_lm = local_map_host; h->io_yaw = yaw_host; h->io_done = done_host;
     h->io_stream = (cudaStream_t)stream;
@@ -794,50 +885,88 @@ extern "C" int d2d_bind_host_io(d2d_handle *h, const double *actions_host, uint8
     return D2D_OK;
 }
 
+// one synchronous step through the bound buffers (also refreshes a stale mirror with full copies)
+static int step_bound_sync(d2d_handle *h) {
+    const int rc = d2d_step(h, h->io_actions_dev, (void *)h->io_stream);
+    if (rc != D2D_OK) return rc;
+    cudaStream_t st = h->io_stream;
+    if (h->mir_stale) {
+        if (h->io_lm) CUDA_TRY(h, cudaMemcpyAsync(h->io_lm, h->P.local_map, (size_t)h->B * D2D_LOCAL_CELLS, cudaMemcpyDeviceToHost, st));
+        if (h->io_yaw) CUDA_TRY(h, cudaMemcpyAsync(h->io_yaw, h->P.yaw_obs, (size_t)h->B * 4, cudaMemcpyDeviceToHost, st));
+        if (h->io_done) CUDA_TRY(h, cudaMemcpyAsync(h->io_done, h->P.done, (size_t)h->B, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    h->mir_stale = false;
+    return D2D_OK;
+}
+
 extern "C" int d2d_step_bound(d2d_handle *h) {
     if (!h) return D2D_ERR_INVALID;
     if (!h->io_bound) { h->err = "d2d_step_bound before d2d_bind_host_io"; return D2D_ERR_STATE; }
-    // the in-kernel completion signal exists in the fused NoMove warp kernel; everything else, and the first step after a
-    // bind / reset (the mirror needs one full refresh copy), goes through the synchronising path
-    const bool fast = h->cfg.planner == D2D_PLANNER_NOMOVE && h->cfg.envs_per_block <= 0 && !h->P.motion_rvo && !h->mir_stale;
-    if (!fast) {
-        const int rc = d2d_step(h, h->io_actions_dev, (void *)h->io_stream);
-        if (rc != D2D_OK) return rc;
-        cudaStream_t st = h->io_stream;
-        if (h->mir_stale) {
-            if (h->io_lm) CUDA_TRY(h, cudaMemcpyAsync(h->io_lm, h->P.local_map, (size_t)h->B * D2D_LOCAL_CELLS, cudaMemcpyDeviceToHost, st));
-            if (h->io_yaw) CUDA_TRY(h, cudaMemcpyAsync(h->io_yaw, h->P.yaw_obs, (size_t)h->B * 4, cudaMemcpyDeviceToHost, st));
-            if (h->io_done) CUDA_TRY(h, cudaMemcpyAsync(h->io_done, h->P.done, (size_t)h->B, cudaMemcpyDeviceToHost, st));
-        }
-        CUDA_TRY(h, cudaStreamSynchronize(st));
-        if ((!h->mir_lm || h->io_lm == h->mir_lm) && (!h->mir_yaw || h->io_yaw == h->mir_yaw) && (!h->mir_done || h->io_done == h->mir_done))
-            h->mir_stale = false;
-        return D2D_OK;
+    D2D_NO_PIPE(h);
+    return step_bound_sync(h);
+}
+
+extern "C" int d2d_step_pipelined(d2d_handle *h, int32_t prelaunch_next) {
+    if (!h) return D2D_ERR_INVALID;
+    if (!h->io_bound) { h->err = "d2d_step_pipelined before d2d_bind_host_io"; return D2D_ERR_STATE; }
+    // The gate lives in the fused NoMove warp kernel; everything else, and a step that must refresh a stale mirror, runs
+    // synchronously (same results, nothing pre-launched).
+    const bool can_pipe = h->cfg.planner == D2D_PLANNER_NOMOVE && h->cfg.envs_per_block <= 0 && !h->P.motion_rvo &&
+                          h->io_actions_dev != h->stage_actions;
+    if (!can_pipe || (h->mir_stale && !h->pipe_inflight)) {
+        D2D_NO_PIPE(h);
+        return step_bound_sync(h);
     }
     if (!h->world_set) { h->err = "d2d_step before d2d_set_world"; return D2D_ERR_STATE; }
     if (h->cfg.var_cam != 0.0 && !h->rng_set) { h->err = "var_cam != 0: d2d_set_rng must provide the np.random stream state"; return D2D_ERR_STATE; }
-    const unsigned int seq = ++h->sig_seq ? h->sig_seq : ++h->sig_seq;         // never 0
-    h->P.sig_ctr = h->sig_ctr; h->P.sig_flag = h->sig_dev_flag; h->P.sig_seq = seq;
-    const int rc = launch_fused_warp<4, 7, false>(h, h->io_actions_dev, h->io_stream);
-    h->P.sig_ctr = nullptr;
-    if (rc != D2D_OK) return rc;
-    // poll the flag; look at the stream now and then so that a failed launch / kernel fault cannot hang the caller
-    volatile unsigned int *flag = h->sig_host;
-    for (unsigned long spins = 1; *flag != seq; spins++) {
+    cudaStream_t st = h->io_stream;
+    const double t_in = now_ns();
+    const unsigned int seq = h->pipe_seq + 1;            // the step whose actions the caller has just written
+    h->P.gate = (unsigned long long *)h->stage_actions; h->P.gate_fault = h->gate_dev + 16;
+    int rc = D2D_OK;
+    if (!h->pipe_inflight) {                              // first step of a pipelined run: nothing was pre-launched
+        // sentinels first; the copy stream must not deliver the actions before they are in place
+        d2d_fill_sentinel_kernel<<<(h->B + 255) / 256, 256, 0, st>>>((unsigned long long *)h->stage_actions, h->B);
+        h->launches++;
+        if (cudaEventRecord(h->pipe_ev[2], st) != cudaSuccess || cudaStreamWaitEvent(h->copy_stream, h->pipe_ev[2], 0) != cudaSuccess)
+            rc = D2D_ERR_CUDA;
+        if (rc == D2D_OK) rc = launch_fused_warp<4, 7, false>(h, h->stage_actions, st);
+        if (rc == D2D_OK && cudaEventRecord(h->pipe_ev[seq & 1], st) != cudaSuccess) rc = D2D_ERR_CUDA;
+    }
+    // publish: ONE async copy moves the caller's actions over the sentinels in the device staging buffer.  The previous
+    // step's kernel has completed (its event was waited for) and has put the sentinels back.
+    if (rc == D2D_OK && cudaMemcpyAsync(h->stage_actions, h->io_actions_host, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess) rc = D2D_ERR_CUDA;
+    h->pipe_seq = seq;
+    h->pipe_inflight = false;
+    if (rc == D2D_OK && prelaunch_next) {                 // the next step starts behind this one and runs up to its gate
+        rc = launch_fused_warp<4, 7, false>(h, h->stage_actions, st);
+        if (rc == D2D_OK && cudaEventRecord(h->pipe_ev[(seq + 1) & 1], st) != cudaSuccess) rc = D2D_ERR_CUDA;
+        if (rc == D2D_OK) h->pipe_inflight = true;
+    }
+    h->P.gate = nullptr; h->P.gate_fault = nullptr;
+    if (rc != D2D_OK && h->err.empty()) h->err = std::string("d2d_step_pipelined: ") + cudaGetErrorString(cudaGetLastError());
+    if (rc != D2D_OK) { if (h->err.empty()) h->err = "d2d_step_pipelined: launch failed"; return rc; }
+    // wait for THIS step only (the pre-launched one keeps running): poll its event, no blocking driver call
+    const double t_l = now_ns();
+    for (;;) {
+        const cudaError_t q = cudaEventQuery(h->pipe_ev[seq & 1]);
+        h->dbg_polls++;
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) { h->err = std::string("d2d_step_pipelined: ") + cudaGetErrorString(q); return D2D_ERR_CUDA; }
 #if defined(__x86_64__) || defined(__i386__)
         __builtin_ia32_pause();
 #endif
-        if ((spins & 0xFFFFF) == 0) {
-            const cudaError_t q = cudaStreamQuery(h->io_stream);
-            if (q != cudaSuccess && q != cudaErrorNotReady) { h->err = std::string("d2d_step_bound: ") + cudaGetErrorString(q); return D2D_ERR_CUDA; }
-            if (q == cudaSuccess && *flag != seq) { h->err = "d2d_step_bound: kernel finished without signalling"; return D2D_ERR_CUDA; }
-        }
     }
+    const double t_out = now_ns();
+    h->dbg_launch_ns += t_l - t_in; h->dbg_wait_ns += t_out - t_l; h->dbg_total_ns += t_out - t_in; h->dbg_n++;
+    if (h->gate_host[16]) { h->err = "d2d_step_pipelined: a step kernel gave up waiting for its actions"; return D2D_ERR_STATE; }
     return D2D_OK;
 }
 
 extern "C" int d2d_stats(d2d_handle *h, int64_t *out_host, int32_t reset, void *stream) {
     if (!h || !out_host) return D2D_ERR_INVALID;
+    D2D_NO_PIPE(h);
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(h, cudaMemcpyAsync(out_host, h->P.stats, D2D_NUM_STATS * 8, cudaMemcpyDeviceToHost, st));

@@ -61,12 +61,12 @@ def make_config(params, num_envs, num_agents, device_index, auto_reset=True, tra
     cfg.device = device_index
     cfg.num_envs = num_envs
     cfg.num_agents = num_agents
-    if params.planner not in ("NoMove", "Primitive"):
-        raise ValueError("planner %r is not supported (NoMove, Primitive)" % (params.planner,))
+    if params.planner not in ("NoMove", "Primitive", "Jerk_Primitive"):
+        raise ValueError("planner %r is not supported (NoMove, Primitive, Jerk_Primitive)" % (params.planner,))
     if params.motion_profile not in ("CVM", "RVO"):
         raise ValueError("motion_profile %r is not supported (CVM, RVO)" % (params.motion_profile,))
     cfg.motion_profile = {"CVM": 0, "RVO": 1}[params.motion_profile]
-    cfg.planner = {"NoMove": 0, "Primitive": 1}[params.planner]
+    cfg.planner = {"NoMove": 0, "Primitive": 1, "Jerk_Primitive": 2}[params.planner]
     cfg.trackers = 1 if trackers else 0
     cfg.auto_reset = 1 if auto_reset else 0
     cfg.oxford = (_native.POLICY_OXFORD if oxford else 0) | (_native.POLICY_OWL if owl else 0)
@@ -137,7 +137,7 @@ class Drone2DVecEnv(object):
     metadata = {"render.modes": []}
 
     def __init__(self, params, num_envs, seeds=None, device="cuda:0", auto_reset=True, trackers=True, oxford=None,
-                 envs_per_block=0, strip_width=10, worlds=None, owl=None):
+                 envs_per_block=0, strip_width=10, worlds=None, owl=None, jerk_tie_orders=None):
         if not torch.cuda.is_available():
             raise _native.Drone2DNativeError("CUDA device required: Drone2DVecEnv has no CPU path")
         self.params = params
@@ -159,6 +159,10 @@ class Drone2DVecEnv(object):
         if rc != 0:
             msg = self._lib.d2d_last_error(None)
             raise _native.Drone2DNativeError("d2d_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+        if self.cfg.planner == 2:       # Jerk_Primitive: per-heading tables evaluated with the reference's numpy expressions
+            from . import jerk
+            self._jerk_tables = jerk.make_tables(params, jerk_tie_orders)
+            self._check(self._lib.d2d_set_jerk_tables(self._h, C.byref(self._jerk_tables)), "d2d_set_jerk_tables")
         self.seeds = np.asarray(seeds if seeds is not None else params.map_id + np.arange(self.num_envs), dtype=np.int64)
         if worlds is None:
             worlds = generate_worlds(params, self.seeds, self._smap)
@@ -287,9 +291,8 @@ class Drone2DVecEnv(object):
     def bind_host_io(self, actions_host=None, local_map_host=None, yaw_host=None, done_host=None):
         """Bound form of `step_host` (d2d_bind_host_io): all PINNED host tensors are given once -- the caller rewrites
         `actions_host` in place before every step and reads the three observation tensors after it -- and a step is then
-        `step_bound()`, one C call without per-step pointer marshalling; with the NoMove planner it returns on the step
-        kernel's own completion flag instead of a driver synchronisation.  actions_host=None: the actions come from the
-        device buffer "actions_staging".  All None unbinds."""
+        `step_bound()` or `step_pipelined()`, one C call without per-step pointer marshalling.  actions_host=None: the
+        actions come from the device buffer "actions_staging".  All None unbinds."""
         for x in (actions_host, local_map_host, yaw_host, done_host):
             if x is not None and not (torch.is_tensor(x) and x.is_pinned() and x.is_contiguous()):
                 raise ValueError("bind_host_io needs contiguous pinned torch tensors (tensor.pin_memory())")
@@ -301,6 +304,7 @@ class Drone2DVecEnv(object):
         self._mirror = (local_map_host, yaw_host, done_host)
         self._mirror_ptrs = tuple(None if x is None else x.data_ptr() for x in self._mirror)
         self._step_bound = self._lib.d2d_step_bound
+        self._step_pipelined = self._lib.d2d_step_pipelined
         self._hv = self._h.value
 
     def step_bound(self):
@@ -308,6 +312,14 @@ class Drone2DVecEnv(object):
         rc = self._step_bound(self._hv)
         if rc != 0:
             self._check(rc, "d2d_step_bound")
+
+    def step_pipelined(self, prelaunch_next=True):
+        """One step through the bound buffers with the NEXT step's kernel pre-launched (d2d_step_pipelined): the action only
+        turns the yaw at the end of a step, so the next step's action-independent work overlaps the caller's handling of this
+        observation.  `prelaunch_next=True` promises another `step_pipelined` call; pass False on the last step of a run."""
+        rc = self._step_pipelined(self._hv, 1 if prelaunch_next else 0)
+        if rc != 0:
+            self._check(rc, "d2d_step_pipelined")
 
     @property
     def info(self):

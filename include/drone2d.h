@@ -45,7 +45,11 @@ typedef enum d2d_status {
     D2D_ERR_STATE = -4           /* call sequence error, e.g. step before set_world */
 } d2d_status;
 
-typedef enum d2d_planner { D2D_PLANNER_NOMOVE = 0, D2D_PLANNER_PRIMITIVE = 1 } d2d_planner;
+typedef enum d2d_planner {
+    D2D_PLANNER_NOMOVE = 0,      /* traj_planner.py:68-76 */
+    D2D_PLANNER_PRIMITIVE = 1,   /* traj_planner.py:80-233 */
+    D2D_PLANNER_JERK = 2         /* Jerk_Primitive, traj_planner.py:403-516; needs d2d_set_jerk_tables */
+} d2d_planner;
 
 /* params.motion_profile: constant-velocity agents (velocity IS pref_velocity) or reciprocal velocity obstacles */
 typedef enum d2d_motion { D2D_MOTION_CVM = 0, D2D_MOTION_RVO = 1 } d2d_motion;
@@ -105,6 +109,23 @@ typedef struct d2d_config {
     double owl_u_space[D2D_MAX_OWL_U];
 } d2d_config;
 
+/* Jerk_Primitive (traj_planner.py:403-516): constants of the 72 candidate headings np.arange(0, 360, 5), evaluated by the host
+ * with the reference's own numpy expressions (np.cos / np.sin of math.radians, numpy-scalar `**`, np.arange, np.floor), and
+ * the heading order `cost[:, 0].argsort()` produces for the goal bearings where the cost ties. */
+#define D2D_JERK_H 72
+#define D2D_JERK_MAXT 40
+typedef struct d2d_jerk_tables {
+    double dx[D2D_JERK_H], dy[D2D_JERK_H];            /* d * np.cos(radians(theta)), d * np.sin(radians(theta)), d = 30 (:409, 414-415) */
+    double T[D2D_JERK_H], Tp[D2D_JERK_H][4];          /* T (:429-432) and T**2 .. T**5 */
+    int32_t times[D2D_JERK_H];                        /* int(np.floor(T / dt)) (:434) */
+    double tt[D2D_JERK_H][D2D_JERK_MAXT];             /* np.arange(dt, times*dt + dt, dt)[:times] (:438) */
+    double ttp[D2D_JERK_H][D2D_JERK_MAXT][4];         /* tt**2 .. tt**5 */
+    /* cost[:, 0].argsort() (:478) of the host's numpy for goal bearings phi_h % 360 == 2.5 * m, m = 0..143: the cost is
+     * symmetric about the bearing there, pairs of headings tie, and numpy's default argsort is unstable -- the order is
+     * recorded from the library.  Any other bearing has distinct costs (ascending order is unique). */
+    uint8_t tie_order[144][D2D_JERK_H];
+} d2d_jerk_tables;
+
 typedef struct d2d_handle d2d_handle;
 
 typedef struct d2d_buffer_info {
@@ -132,6 +153,9 @@ int d2d_destroy(d2d_handle *h);
 int d2d_set_world(d2d_handle *h, int32_t first_env, int32_t count, const double *agent_pos, const double *agent_pref,
                   const double *agent_radius, const double *tracker_radius, const uint8_t *gt_grid,
                   const double *drone_pose);
+
+/* Required once when cfg.planner = D2D_PLANNER_JERK (before the first step): the per-heading tables above (HOST). */
+int d2d_set_jerk_tables(d2d_handle *h, const d2d_jerk_tables *tables);
 
 /* State of the reference's global legacy `np.random` stream right after world generation (np.random.seed(map_id),
  * drone_v2.py:80, then the 100 heading draws, :54), as returned by RandomState.get_state(): key [count][624] u32, pos,
@@ -177,17 +201,30 @@ int d2d_step_host(d2d_handle *h, const double *actions_host, uint8_t *local_map_
 int d2d_bind_host_mirror(d2d_handle *h, uint8_t *local_map_host, float *yaw_host, uint8_t *done_host);
 
 /* Bound form of d2d_step_host for callers that step in a tight loop (a vectorised-env worker): all host buffers and the
- * stream are given ONCE, a step is then d2d_step_bound(h).
+ * stream are given ONCE, a step is then d2d_step_bound(h) or d2d_step_pipelined(h, more).
  *   actions_host  PINNED [num_envs] f64 the caller rewrites before every step (read by the kernels in place over PCIe);
  *                 NULL: actions come from the device buffer "actions_staging" (policy on the GPU)
  *   local_map_host / yaw_host / done_host  PINNED, become the zero-copy observation mirror (d2d_bind_host_mirror rules)
- * With the NoMove planner the step kernel itself reports completion: every warp fences its mirror stores at system scope
- * and the last one writes the step number into a pinned flag the host polls, so the call returns without a driver
- * synchronisation (about 6 us per step at BASELINE config 2).  Other planners synchronise the stream as d2d_step_host does.
  * Binding with all pointers NULL unbinds. */
 int d2d_bind_host_io(d2d_handle *h, const double *actions_host, uint8_t *local_map_host, float *yaw_host, uint8_t *done_host,
                      void *stream);
+
+/* One step through the bound buffers: d2d_step_host without per-call pointer resolution. */
 int d2d_step_bound(d2d_handle *h);
+
+/* The same step, pipelined.  In Drone2DEnv2.step the action only turns the yaw at the very END of the step (step_yaw,
+ * utils.py:741-743, called at drone_v2.py:214); agent motion, ray casting, trackers and collision tests never see it.  With
+ * prelaunch_next != 0 the kernel of the FOLLOWING step is therefore launched before this call returns: it runs right behind
+ * the current step, does everything that does not depend on its action while the caller is still looking at this step's
+ * observation and choosing the next actions, and waits at a gate just before its yaw update.  The next
+ * d2d_step_pipelined call publishes the actions (the caller has written them into the bound pinned buffer) and opens the
+ * gate.  Host-mirror stores of a step are issued only behind its gate, so the observation buffers stay valid until the
+ * next call, as with d2d_step_host.  Results are identical to d2d_step_bound; launch latency and completion wake-up leave
+ * the critical path.  Contract: prelaunch_next promises one more d2d_step_pipelined call; until that call (pass 0 on the
+ * last step of a run) every other entry point of this handle returns D2D_ERR_STATE.  A pre-launched kernel whose actions
+ * never arrive gives up after ~2 s and the next call reports it.  Planners other than NoMove, the RVO profile and actions
+ * taken from "actions_staging" run synchronously (same results, nothing pre-launched). */
+int d2d_step_pipelined(d2d_handle *h, int32_t prelaunch_next);
 
 /* Replaces Oxford.plan(env.info) (yaw_planner.py:81-127) for all envs: writes the chosen action per env to
  * actions_out_dev (DEVICE [num_envs] f64) and advances the policy state.  Requires cfg.oxford = 1. */

@@ -123,6 +123,22 @@ def main():
             continue
         r = rr.run_episode(800, policy="Owl", planner="Primitive", gaze_method="Owl", stop_on_done=True, **kw)
         save(name, r, WORLD + STEP_CORE + TRACK + PLAN)
+    # --- Jerk_Primitive planner (traj_planner.py:403-516).  jerk_s3 is the canonical scenario (start (50, 50), target (50, 460):
+    #     goal bearing exactly 90 degrees, every pair of headings ties in the unstable argsort) with a blocked straight line.
+    #     The fixture records how THIS machine's numpy ordered the ties (oracle.jerk_tie_orders) next to the episode.
+    import oracle as _oracle
+    jerk = [
+        ("jerk_s3", dict(map_id=3, agent_number=8), "LookAhead"),
+        ("jerk_crowd_s7", dict(map_id=7, agent_number=20, agent_radius=15, agent_max_speed=20), "LookAhead"),
+        ("jerk_obstacle_s5", dict(map_id=5, agent_number=30, static_map="maps/obstacle_map.npy"), "LookAhead"),
+        ("jerk_speed20_s9", dict(map_id=9, agent_number=10, drone_max_speed=20), "LookGoal"),
+        ("jerk_offset_s2", dict(map_id=2, agent_number=10, target_list=[[73, 460]]), "Rotating"),
+    ]
+    for name, kw, pol in jerk:
+        if only not in name:
+            continue
+        r = rr.run_episode(800, policy=pol, planner="Jerk_Primitive", gaze_method=pol, stop_on_done=True, **kw)
+        save(name, r, WORLD + STEP_CORE + TRACK + PLAN, extra={"jerk_tie_orders": _oracle.jerk_tie_orders()})
     # --- RVO motion profile (utils.py:299-460): agents avoid each other and the pillars; velocity is its own array
     rvo = [
         ("rvo_nomove_pillars_s3", dict(map_id=3, agent_number=6, pillar_number=2), 60, None, "NoMove"),

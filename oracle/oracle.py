@@ -29,7 +29,75 @@ class Params(C.Structure):
         ("n_yaw", C.c_int32), ("pad1", C.c_int32),
         ("v_yaw_space", C.c_double * 16),
         ("ox_cos_thresh", C.c_double),
+        ("jerk", C.c_void_p),
     ]
+
+
+JERK_H, JERK_MAXT = 72, 40
+
+
+class JerkTables(C.Structure):
+    _fields_ = [
+        ("dx", C.c_double * JERK_H), ("dy", C.c_double * JERK_H),
+        ("T", C.c_double * JERK_H), ("Tp", (C.c_double * 4) * JERK_H),
+        ("times", C.c_int32 * JERK_H),
+        ("tt", (C.c_double * JERK_MAXT) * JERK_H), ("ttp", ((C.c_double * 4) * JERK_MAXT) * JERK_H),
+        ("tie_order", (C.c_uint8 * JERK_H) * 144),
+        ("unexpected_ties", C.c_int64),
+    ]
+
+
+def jerk_tie_orders():
+    """`cost[:, 0].argsort()` (traj_planner.py:471-478) of THIS host's numpy for the 144 goal bearings that are exact
+    multiples of 2.5 degrees, where the cost is symmetric about the bearing and every pair of headings ties: numpy's default
+    argsort is unstable (x86-simd-sort networks; AVX-512 and AVX2 builds order ties differently), so the order is recorded
+    from the library instead of being guessed.  Returns uint8 [144, 72]."""
+    theta_range = np.arange(0, 360, 5)
+    out = np.zeros((144, JERK_H), dtype=np.uint8)
+    for m in range(144):
+        phi_h = 2.5 * m
+        cost = np.zeros((theta_range.shape[0], 2))
+        for i, theta in enumerate(theta_range):
+            a = abs(theta % 360 - phi_h % 360)
+            cost[i, 0] = 1 * (a if a <= 180 else 360 - a) ** 2
+            cost[i, 1] = theta
+        out[m] = cost[:, 0].argsort()
+    return out
+
+
+def jerk_tables(drone_max_speed=40, dt=0.1, d=30, tie_orders=None):
+    """Per-heading constants of Jerk_Primitive.generate_primitive (traj_planner.py:413-460), evaluated with the reference's
+    own expressions (np.cos / np.sin of math.radians, numpy-scalar `**`, np.arange, np.floor)."""
+    from math import radians
+    from numpy.linalg import norm
+    t = JerkTables()
+    theta_range = np.arange(0, 360, 5)
+    cost1 = np.zeros(theta_range.shape[0])
+    for i, theta in enumerate(theta_range):
+        cost1[i] = theta
+    v_max = drone_max_speed
+    for i in range(JERK_H):
+        theta_h = cost1[i]                                     # cost[seq, 1]: the heading as a float64 array element
+        delt_x = d * np.cos(radians(theta_h))
+        delt_y = d * np.sin(radians(theta_h))
+        T = 1.2 * norm(np.array([delt_x, delt_y])) / (norm(v_max))
+        T = T if T >= 0.5 else 0.5
+        times = int(np.floor(T / dt))
+        assert 0 < times <= JERK_MAXT
+        tarr = np.arange(dt, times * dt + dt, dt)
+        t.dx[i], t.dy[i], t.T[i], t.times[i] = float(delt_x), float(delt_y), float(T), times
+        for k, e in enumerate((2, 3, 4, 5)):
+            t.Tp[i][k] = float(T ** e)
+        for jj in range(times):
+            tt = tarr[jj]
+            t.tt[i][jj] = float(tt)
+            for k, e in enumerate((2, 3, 4, 5)):
+                t.ttp[i][jj][k] = float(tt ** e)
+    ties = jerk_tie_orders() if tie_orders is None else np.asarray(tie_orders, dtype=np.uint8)
+    for m in range(144):
+        for i in range(JERK_H):
+            t.tie_order[m][i] = int(ties[m, i])
+    return t
 
 
 _P = C.POINTER
@@ -60,10 +128,12 @@ class Env(C.Structure):
         ("motion_rvo", C.c_int32), ("n_obs", C.c_int32), ("avel", _P(C.c_double)), ("obs", _P(C.c_double)),
         ("rvo_fallbacks", C.c_int64),
         ("owl_U", C.c_double * 36), ("owl_q", C.c_int32), ("pad3", C.c_int32), ("owl_u", C.c_double),
+        ("ax", C.c_double), ("ay", C.c_double), ("next_ax", C.c_double), ("next_ay", C.c_double),
     ]
 
 
 _lib = None
+_KEEP = []
 
 
 def build(force=False):
@@ -113,6 +183,8 @@ def lib():
         L.d2do_sizeof_params.restype = C.c_size_t
         L.d2do_sizeof_env.restype = C.c_size_t
         assert L.d2do_sizeof_params() == C.sizeof(Params), (L.d2do_sizeof_params(), C.sizeof(Params))
+        L.d2do_sizeof_jerk_tables.restype = C.c_size_t
+        assert L.d2do_sizeof_jerk_tables() == C.sizeof(JerkTables), (L.d2do_sizeof_jerk_tables(), C.sizeof(JerkTables))
         assert L.d2do_sizeof_env() == C.sizeof(Env), (L.d2do_sizeof_env(), C.sizeof(Env))
         _lib = L
     return _lib
@@ -143,7 +215,8 @@ def oxford_cos_threshold(view_range_deg):
 
 def make_params(dt=0.1, map_scale=10, map_size=(500, 500), agent_radius=10, drone_max_acceleration=40,
                 drone_radius=10, drone_max_yaw_speed=80, drone_view_depth=80, drone_view_range=90,
-                max_flight_time=80, var_cam=0, drone_max_speed=40, planner="NoMove", strip_width=10, **_ignored):
+                max_flight_time=80, var_cam=0, drone_max_speed=40, planner="NoMove", strip_width=10, jerk_tie_orders=None,
+                **_ignored):
     """Builds the C params block with the reference's own numpy expressions for the lookup tables
     (traj_planner.py:98-104,180,212; yaw_planner.py:65; utils.py:587)."""
     import math
@@ -152,7 +225,11 @@ def make_params(dt=0.1, map_scale=10, map_size=(500, 500), agent_radius=10, dron
     p.agent_radius, p.drone_max_acc, p.drone_radius = agent_radius, drone_max_acceleration, drone_radius
     p.drone_max_yaw_speed, p.view_depth, p.view_range = drone_max_yaw_speed, drone_view_depth, drone_view_range
     p.max_flight_time, p.var_cam, p.drone_max_speed = max_flight_time, var_cam, drone_max_speed
-    p.planner = {"NoMove": 0, "Primitive": 1}[planner]
+    p.planner = {"NoMove": 0, "Primitive": 1, "Jerk_Primitive": 2}[planner]
+    if p.planner == 2:
+        jt = jerk_tables(drone_max_speed, dt, tie_orders=jerk_tie_orders)
+        _KEEP.append(jt)                                       # shared by every env created from these params
+        p.jerk = C.addressof(jt)
     p.n_rays = math.ceil(map_size[0] / strip_width)
     p.gw, p.gh = map_size[0] // map_scale, map_size[1] // map_scale
     p.local = 4 * (drone_view_depth // map_scale) + 1
@@ -223,8 +300,11 @@ class OracleEnv(object):
         self.c.n_targets = len(targets)
         for i, t in enumerate(targets):
             self.c.targets[i][0], self.c.targets[i][1] = float(t[0]), float(t[1])
-        # Planner.__init__ traj_planner.py:22: target = [drone.x, drone.y, 0, 0]
-        self.c.target[0], self.c.target[1] = float(drone[0]), float(drone[1])
+        # Planner.__init__ traj_planner.py:22: target = [drone.x, drone.y, 0, 0]; Jerk_Primitive.__init__ :406: np.zeros(4)
+        if params.planner == 2:
+            self.c.target[0], self.c.target[1] = 0.0, 0.0
+        else:
+            self.c.target[0], self.c.target[1] = float(drone[0]), float(drone[1])
 
     def set_rng(self, key, pos, has_gauss, gauss):
         """legacy np.random state right after world generation (RandomState.get_state()); needed when var_cam != 0"""

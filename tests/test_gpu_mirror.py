@@ -126,3 +126,79 @@ def test_step_host_action_sources_agree(planner):
             assert torch.equal(envs[0].buffer(name), envs[k].buffer(name)), (name, k)
     for e in envs:
         e.close()
+
+
+@pytest.mark.parametrize("planner,B,steps,pipelined", [("NoMove", 37, 300, False), ("NoMove", 37, 300, True),
+                                                        ("NoMove", 4096, 60, True), ("Primitive", 23, 120, False),
+                                                        ("Primitive", 23, 60, True)])
+def test_bound_host_io_equals_step_host(planner, B, steps, pipelined):
+    """d2d_bind_host_io + d2d_step_bound / d2d_step_pipelined against d2d_step_host on a twin env: host observation buffers
+    and device state identical after every step, across auto-resets, an eager reset and a pose write (which end the pipelined
+    run and force the synchronising refresh path once).  Pipelined: when the call returns, the next step's kernel is already
+    running behind the current one (it owns the GPU until its actions arrive, so the twin runs afterwards, not interleaved),
+    and the observation buffers must still hold THIS step's observation."""
+    import time
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200 import generate_worlds
+    p = Params(debug=False, planner=planner, map_id=7, agent_number=10, agent_radius=15, agent_max_speed=40)
+    worlds = generate_worlds(p, 7 + np.arange(min(B, 256)))
+    worlds = {k: np.concatenate([v] * (-(-B // len(v))))[:B] for k, v in worlds.items()}
+    table = torch.as_tensor(util.action_table())
+    g = torch.Generator().manual_seed(5)
+    acts = table[torch.randint(0, 6, (steps, B), generator=g)].contiguous()
+    mask = torch.zeros(B, dtype=torch.uint8, device="cuda:0")
+    mask[::3] = 1
+    pose = np.stack([np.full(B, 250.0), np.full(B, 250.0), np.full(B, 45.0)], 1)
+    names = ("belief", "agent_pos", "steps", "tracker_mu", "drone_yaw", "local_map", "done")
+
+    def run(bound):
+        env = _env(p, B, worlds, auto_reset=True, oxford=False)
+        lm, yaw, dn = _pinned(B)
+        a_bound = torch.zeros(B, dtype=torch.float64).pin_memory()
+        if bound:
+            env.bind_host_io(a_bound, lm, yaw, dn)
+        obs, state = [], []
+        for t in range(steps):
+            last = t in (steps // 2, steps // 2 + 5, steps - 1) or t % 20 == 0     # steps followed by another API call
+            if not bound:
+                env.step_host(acts[t].clone().pin_memory(), lm, yaw, dn)
+            else:
+                a_bound.copy_(acts[t])             # the caller rewrites the bound action buffer in place
+                if pipelined:
+                    env.step_pipelined(prelaunch_next=not last)
+                else:
+                    env.step_bound()
+            obs.append((lm.clone(), yaw.clone(), dn.clone()))
+            if bound and pipelined and not last and planner == "NoMove":
+                if t % 7 == 0:                      # a pre-launched step is in flight: only the call that completes it is accepted
+                    with pytest.raises(Exception):
+                        env.stats()
+                if t % 11 == 0:
+                    time.sleep(0.002)               # let the pre-launched kernel reach its gate and wait there
+                    assert torch.equal(lm, obs[-1][0]) and torch.equal(dn, obs[-1][2]), "observation changed before the next call"
+            if last:
+                _check(env, lm, yaw, dn, ("bound" if bound else "host", t))
+                state.append({k: env.buffer(k).clone() for k in names})
+            if t == steps // 2:
+                env.reset(mask)
+            if t == steps // 2 + 5:
+                env.set_drone_pose(pose)
+        if bound:
+            env.bind_host_io(None, None, None, None)
+            with pytest.raises(Exception):
+                env.step_bound()
+        env.close()
+        return obs, state
+
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):                   # the bound env runs on its own stream
+        oa, sa = run(True)
+    torch.cuda.synchronize()
+    ob_, sb = run(False)
+    assert sum(int(o[2].sum()) for o in ob_) > 0, "the run must cross auto-resets"
+    for t, (x, y) in enumerate(zip(oa, ob_)):
+        assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) and torch.equal(x[2], y[2]), (planner, "host buffers", t)
+    for k, (x, y) in enumerate(zip(sa, sb)):
+        for name in names:
+            assert torch.equal(x[name], y[name]), (name, k)

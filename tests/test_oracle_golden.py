@@ -8,7 +8,7 @@ import util
 def _run_against_golden(g, use_oxford, use_owl=False):
     import oracle
     p = util.params_from_golden(g)
-    e = util.oracle_env_from_world(p, util.world_from_golden(g), 0)
+    e = util.oracle_env_from_world(p, util.world_from_golden(g), 0, jerk_tie_orders=g.get("jerk_tie_orders"))
     n = int(g["n_agents"])
     T = len(g["done"])
     has_trk = "trk_active" in g
@@ -88,6 +88,17 @@ def test_oracle_matches_reference_owl_episode(path):
     g = util.load_golden(path)
     assert len(set(np.round(g["action"], 6).tolist())) >= 5, "the fixture must exercise more than the NaN / queue paths"
     _run_against_golden(g, use_oxford=False, use_owl=True)
+
+
+@pytest.mark.parametrize("path", util.golden_files("jerk_"), ids=lambda p: p.split("/")[-1][:-4])
+def test_oracle_matches_reference_jerk_primitive(path):
+    """Jerk_Primitive planner (traj_planner.py:403-516): whole episodes, drone position / velocity exact, including the
+    canonical scenario whose goal bearing (exactly 90 degrees) makes every pair of headings tie in numpy's unstable argsort --
+    reproduced from the tie orders recorded on the generating machine (stored in the fixture)."""
+    g = util.load_golden(path)
+    _run_against_golden(g, use_oxford=False)
+    if "jerk_s3" in path:
+        assert (~g["plan_ok"]).sum() > 0 and g["jerk_tie_orders"].shape == (144, 72)
 
 
 def test_config1_known_answer():

@@ -118,3 +118,28 @@ def test_owl_policy_live():
         e.step(a)
         assert np.array_equal(e.belief, r["belief"][t]) and (e.c.x, e.c.y, e.c.yaw) == tuple(r["drone"][t]), t
     e.close()
+
+
+@pytest.mark.parametrize("kw,policy", [(dict(map_id=13, agent_number=16, agent_radius=12, agent_max_speed=30), "LookAhead"),
+                                       (dict(map_id=3, agent_number=8), "LookAhead"),
+                                       (dict(map_id=4, agent_number=25, agent_radius=15, agent_max_speed=20), "Oxford")],
+                         ids=["generic", "canonical_tie", "oxford"])
+def test_jerk_primitive_live(kw, policy):
+    """Jerk_Primitive (traj_planner.py:403-516) restated in the oracle vs the live reference; the tie orders of the unstable
+    argsort are taken from this machine's numpy, which is also the one the reference runs on here."""
+    from gym_drone2d_activeperception_b200.params import Params
+    r = ref_runner.run_episode(400, policy=policy, stop_on_done=True, planner="Jerk_Primitive", gaze_method=policy, **kw)
+    P = r["params"]
+    p = Params(debug=False, **{k: P[k] for k in util.PARAM_KEYS if k in P}, init_pos=P["init_position"],
+               target_list=P["target_list"])
+    world = dict(agent_pos=r["agent_pos0"], agent_pref=r["agent_pref0"], agent_radius=r["agent_radius"],
+                 tracker_radius=r["tracker_radius"], gt_grid=r["gt_grid"], drone_pose=r["drone0"])
+    e = util.oracle_env_from_world(p, world)
+    for t in range(len(r["done"])):
+        if policy == "Oxford":
+            assert e.oxford_plan() == r["action"][t]
+        e.step(float(r["action"][t]))
+        assert (e.c.x, e.c.y, e.c.yaw, e.c.vx, e.c.vy) == (*r["drone"][t], *r["drone_vel"][t]), t
+        assert np.array_equal(e.belief, r["belief"][t]) and e.c.done == int(r["done"][t]), t
+        assert bool(e.c.plan_ok) == bool(r["plan_ok"][t]) and e.c.traj_len == r["traj_len"][t], t
+    e.close()

@@ -35,20 +35,30 @@ def params_from_golden(g):
     return Params(debug=False, **kw)
 
 
-def oracle_params(p):
+def oracle_params(p, **kw):
     import oracle
-    return oracle.make_params(dt=p.dt, map_scale=p.map_scale, map_size=p.map_size, agent_radius=p.agent_radius,
+    return oracle.make_params(**kw, dt=p.dt, map_scale=p.map_scale, map_size=p.map_size, agent_radius=p.agent_radius,
                               drone_max_acceleration=p.drone_max_acceleration, drone_radius=p.drone_radius,
                               drone_max_yaw_speed=p.drone_max_yaw_speed, drone_view_depth=p.drone_view_depth,
                               drone_view_range=p.drone_view_range, max_flight_time=p.max_flight_time, var_cam=p.var_cam,
                               drone_max_speed=p.drone_max_speed, planner=p.planner)
 
 
-def oracle_env_from_world(p, world, i=None, drone=None):
+_OP_CACHE = {}
+
+
+def oracle_env_from_world(p, world, i=None, drone=None, jerk_tie_orders=None):
     """world: dict of arrays (one env, or batched with index i)."""
     import oracle
     w = {k: (v[i] if i is not None else v) for k, v in world.items()}
-    e = oracle.OracleEnv(oracle_params(p), w["agent_pos"], w["agent_pref"], w["agent_radius"], w["gt_grid"],
+    if p.planner == "Jerk_Primitive":          # the per-heading tables are shared by every env built from one params object
+        key = (tuple(sorted((k, repr(v)) for k, v in vars(p).items())), None if jerk_tie_orders is None else jerk_tie_orders.tobytes())
+        if key not in _OP_CACHE:
+            _OP_CACHE[key] = oracle_params(p, jerk_tie_orders=jerk_tie_orders)
+        op = _OP_CACHE[key]
+    else:
+        op = oracle_params(p)
+    e = oracle.OracleEnv(op, w["agent_pos"], w["agent_pref"], w["agent_radius"], w["gt_grid"],
                          w["tracker_radius"], drone=(w["drone_pose"] if drone is None else drone),
                          targets=p.target_list)
     if "rng_key" in w:
@@ -87,11 +97,12 @@ DISCRETE_FIELDS = ("belief", "hit", "local_map", "collision_flag", "dead_lock_fl
 STATE_FIELDS = ("drone_x", "drone_y", "drone_yaw", "drone_vx", "drone_vy", "agent_pos", "agent_pref")
 
 
-def oracle_batch(p, worlds, poses=None, threads=None):
+def oracle_batch(p, worlds, poses=None, threads=None, jerk_tie_orders=None):
     """oracle.OracleBatch over every env of `worlds` (initial state; optional externally set drone poses [B,3])."""
     import oracle
     B = worlds["drone_pose"].shape[0]
-    envs = [oracle_env_from_world(p, worlds, i, drone=None if poses is None else poses[i]) for i in range(B)]
+    envs = [oracle_env_from_world(p, worlds, i, drone=None if poses is None else poses[i], jerk_tie_orders=jerk_tie_orders)
+            for i in range(B)]
     return oracle.OracleBatch(envs, threads=threads)
 
 

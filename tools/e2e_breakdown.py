@@ -40,6 +40,42 @@ def main():
         print("%-64s %7.2f us/step  %7.1f M env-steps/s" % (name, dt * 1e6, B / dt / 1e6))
 
     timeit("env.step_host (python wrapper, mirror bound)", lambda t: env.step_host(a_host[t], lm, yaw, done))
+    a_bound = torch.zeros(B, dtype=torch.float64).pin_memory()
+    env.bind_host_io(a_bound, lm, yaw, done)
+    env.step_bound()
+
+    def bound_step(t):
+        a_bound.copy_(a_host[t])
+        env.step_bound()
+    timeit("env.step_bound (bound buffers, stream sync) + action memcpy", bound_step)
+    timeit("env.step_bound only (same actions every step)", lambda t: env.step_bound())
+    import ctypes
+    dst, nb = a_bound.data_ptr(), B * 8
+    src = [a_host[t].data_ptr() for t in range(K)]
+
+    def pipe_step(t):
+        ctypes.memmove(dst, src[t], nb)
+        env.step_pipelined(prelaunch_next=t != K - 1)
+    timeit("env.step_pipelined (next step pre-launched, gated on its actions) + action memcpy", pipe_step)
+
+    def pipe_step_slow_policy(t):
+        ctypes.memmove(dst, src[t], nb)
+        env.step_pipelined(prelaunch_next=t != K - 1)
+        t_end = time.perf_counter() + 20e-6           # a host policy that needs 20 us per step
+        while time.perf_counter() < t_end:
+            pass
+    timeit("env.step_pipelined + a 20 us host policy per step", pipe_step_slow_policy)
+
+    def bound_step_slow_policy(t):
+        ctypes.memmove(dst, src[t], nb)
+        env.step_bound()
+        t_end = time.perf_counter() + 20e-6
+        while time.perf_counter() < t_end:
+            pass
+    timeit("env.step_bound + a 20 us host policy per step", bound_step_slow_policy)
+    env.bind_host_io(None, None, None, None)
+    env.bind_host_mirror(lm, yaw, done)
+    env.step_host(a_host[0], lm, yaw, done)
     L, h = env._lib, env._h
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     ap = [C.c_void_p(a_host[t].data_ptr()) for t in range(K)]
