@@ -1166,18 +1166,19 @@ __device__ __forceinline__ void d2d_prof_stamp(const DevP &P, int e, int k, int 
 #define D2D_PROF(k)
 #endif
 
-// HOSTIO: the instantiation launched while host buffers are attached (d2d_bind_host_mirror / d2d_bind_host_io): host-mirror
-// stores of patched cells are replayed from a changed-cell list at the end of the step instead of being issued inside the
-// march, and the action may arrive late through the gate (d2d_step_pipelined).  The device-resident instantiation
-// (HOSTIO = false) carries none of that.
-template <int WPB, int MINB, bool ILP2, bool HOSTIO>
+// GATED: the instantiation d2d_step_pipelined launches.  The step's action arrives late (the warp waits for it just before
+// the yaw update), and every store into the host mirror is held back until then: patched cells are recorded in a
+// changed-cell list and replayed behind the gate, so the caller's observation buffers keep the previous step's content until
+// it has published the next actions.  The plain instantiation (GATED = false) issues mirror stores as they occur (measured:
+// deferring them costs ~15 % at 131072 envs and gains nothing at 4096) and carries none of the gate code.
+template <int WPB, int MINB, bool ILP2, bool GATED>
 __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(const DevP P,
                                                                              const double *__restrict__ actions) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int e = blockIdx.x * WPB + wid;
     if (e >= P.B) return;                                            // warp-uniform
-    unsigned char *slice = smem + (size_t)wid * d2d_warp_slice_bytes(P.NP, P.HW, HOSTIO ? D2D_FUSED_WARP_EXTRA : 0);
+    unsigned char *slice = smem + (size_t)wid * d2d_warp_slice_bytes(P.NP, P.HW, GATED ? D2D_FUSED_WARP_EXTRA : 0);
     const BlockCtx c = d2d_carve(slice, 1, P.NP, P.HW);
     // changed-cell list of this step (host mirror bound: the PCIe stores are replayed from it at the end of the step)
     uint32_t *chg = (uint32_t *)(slice + d2d_step_smem_bytes(1, P.NP, P.HW));
@@ -1196,9 +1197,9 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
         if (P.trackers) pf_act = P.trk_active[g];
     }
     // same address in every lane: one broadcast request.  Pipelined host path: the action is not chosen yet (see the gate)
-    double action = (HOSTIO && P.gate) ? 0.0 : actions[e];
+    double action = GATED ? 0.0 : actions[e];
     if (lane == 0) {
-        if (HOSTIO) *nchg = 0;
+        if (GATED) *nchg = 0;
         d2d_mbar_init(c.mbar, 1);
         d2d_mbar_expect_tx(c.mbar, D2D_GT_ROW_BYTES + D2D_BELIEF_STRIDE);
         d2d_bulk_g2s(c.gt, P.gt_rows + (size_t)e * D2D_GRID, D2D_GT_ROW_BYTES, c.mbar);
@@ -1221,11 +1222,11 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     // is patched in place by the rays (only cells whose value changes) instead of being rewritten
     __syncwarp();
     const bool patch = !s.reset && s.obs_ix == s.ix && s.obs_iy == s.iy;
-    const bool mirror = HOSTIO && P.lm_mirror != nullptr;
+    const bool mirror = GATED && P.lm_mirror != nullptr;
     RayOut ro;
     ro.bel_s = c.belief; ro.e = e; ro.patch = patch ? 1 : 0;
     ro.wi = s.ix - 16; ro.wj = s.iy - 16;
-    ro.chg = (mirror && patch) ? chg : nullptr; ro.nchg = nchg; ro.defer_mirror = HOSTIO ? 1 : 0;
+    ro.chg = (mirror && patch) ? chg : nullptr; ro.nchg = nchg; ro.defer_mirror = GATED ? 1 : 0;
     D2D_PROF(6);
     d2d_mbar_wait(c.mbar, 0);
     ro.border_ok = d2d_border_intact(c.gt, lane);
@@ -1242,7 +1243,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     const int shit = __any_sync(0xffffffffu, lane < 5 ? d2d_static_probe(P, c.gt, s.px, s.py, lane) : 0);
     __syncwarp();
     D2D_PROF(8);
-    if (HOSTIO && P.gate) {
+    if (GATED) {
         // Everything above is independent of this step's action (it only turns the yaw at the end of the step,
         // utils.py:741-743).  P.gate is the device staging buffer: it holds a sentinel until the host's copy engine has
         // delivered this step's actions (ONE async copy per step, no separate gate word: an aligned 8-byte word arrives
@@ -1267,6 +1268,10 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
         d2d_leader_finish(P, s, c.gt, e, action, true);
         d2d_leader_flags(P, s, c.gt, e, shit);
         if (e == 0) atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], (unsigned long long)P.B);   // every env steps once per launch
+        if (!GATED && patch && P.lm_mirror) {
+            const int nb = *(const int *)(c.belief + D2D_MIRCNT_OFF);
+            if (nb) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)nb);
+        }
     }
     __syncwarp();
     D2D_PROF(9);

@@ -222,8 +222,11 @@ int d2d_step_bound(d2d_handle *h);
  * next call, as with d2d_step_host.  Results are identical to d2d_step_bound; launch latency and completion wake-up leave
  * the critical path.  Contract: prelaunch_next promises one more d2d_step_pipelined call; until that call (pass 0 on the
  * last step of a run) every other entry point of this handle returns D2D_ERR_STATE.  A pre-launched kernel whose actions
- * never arrive gives up after ~2 s and the next call reports it.  Planners other than NoMove, the RVO profile and actions
- * taken from "actions_staging" run synchronously (same results, nothing pre-launched). */
+ * never arrive gives up after ~2 s and the next call reports it.  Planners other than NoMove, the RVO profile, actions
+ * taken from "actions_staging" and batches above ~16k envs (whose step dwarfs the latency being hidden) run synchronously
+ * (same results, nothing pre-launched).  Meant for HOST policies: a pre-launched kernel holds the GPU until its actions
+ * arrive, so work queued on the same GPU in between (a policy network) would wait for it -- such callers use d2d_step with
+ * device actions, which needs no host round trip in the first place. */
 int d2d_step_pipelined(d2d_handle *h, int32_t prelaunch_next);
 
 /* Replaces Oxford.plan(env.info) (yaw_planner.py:81-127) for all envs: writes the chosen action per env to
