@@ -926,18 +926,22 @@ extern "C" int d2d_step_pipelined(d2d_handle *h, int32_t prelaunch_next) {
     const unsigned int seq = h->pipe_seq + 1;            // the step whose actions the caller has just written
     h->P.gate = (unsigned long long *)h->stage_actions; h->P.gate_fault = h->gate_dev + 16;
     int rc = D2D_OK;
-    if (!h->pipe_inflight) {                              // first step of a pipelined run: nothing was pre-launched
+    const bool first = !h->pipe_inflight;                 // first step of a pipelined run: nothing was pre-launched
+    if (first) {
         // sentinels first; the copy stream must not deliver the actions before they are in place
         d2d_fill_sentinel_kernel<<<(h->B + 255) / 256, 256, 0, st>>>((unsigned long long *)h->stage_actions, h->B);
         h->launches++;
         if (cudaEventRecord(h->pipe_ev[2], st) != cudaSuccess || cudaStreamWaitEvent(h->copy_stream, h->pipe_ev[2], 0) != cudaSuccess)
             rc = D2D_ERR_CUDA;
+    }
+    // publish: ONE async copy moves the caller's actions over the sentinels in the device staging buffer.  The previous
+    // step's kernel has completed (its event was waited for) and has put the sentinels back.  Issued before this step's own
+    // kernel in the first-step case, so that blocking launches (CUDA_LAUNCH_BLOCKING, sanitizers) cannot starve it.
+    if (rc == D2D_OK && cudaMemcpyAsync(h->stage_actions, h->io_actions_host, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess) rc = D2D_ERR_CUDA;
+    if (first) {
         if (rc == D2D_OK) rc = launch_fused_warp<4, 7, false>(h, h->stage_actions, st);
         if (rc == D2D_OK && cudaEventRecord(h->pipe_ev[seq & 1], st) != cudaSuccess) rc = D2D_ERR_CUDA;
     }
-    // publish: ONE async copy moves the caller's actions over the sentinels in the device staging buffer.  The previous
-    // step's kernel has completed (its event was waited for) and has put the sentinels back.
-    if (rc == D2D_OK && cudaMemcpyAsync(h->stage_actions, h->io_actions_host, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->copy_stream) != cudaSuccess) rc = D2D_ERR_CUDA;
     h->pipe_seq = seq;
     h->pipe_inflight = false;
     if (rc == D2D_OK && prelaunch_next) {                 // the next step starts behind this one and runs up to its gate

@@ -6,17 +6,19 @@ T=${1:-cap}
 O=gpurun_out
 mkdir -p $O
 (python -m pytest tests -m gpu -q) > $O/${T}_tests.log 2>&1; tail -2 $O/${T}_tests.log
-python bench.py > $O/${T}_bench_cfg2.json 2> $O/${T}_bench_cfg2.err
-python bench.py --impl reference --steps 5 --warmup 3 > $O/${T}_bench_cfg2_reference_arm.json 2>> $O/${T}_bench_cfg2.err
-for c in 3 4 5; do python bench.py --config $c --steps 50 --warmup 5 --burn-in 300 > $O/${T}_bench_cfg$c.json 2> $O/${T}_bench_cfg$c.err; done
-python bench.py --config 4 --planner NoMove --gaze scripted --steps 50 --warmup 5 --burn-in 300 --no-cpu-baseline > $O/${T}_bench_cfg4_nomove.json 2>> $O/${T}_bench_cfg4.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/${T}_launches_cfg2.csv python bench.py --steps 20 --warmup 3 --burn-in 5 --no-cpu-baseline > $O/${T}_l2.log 2>&1
+python bench.py --steps 200 --warmup 20 > $O/${T}_bench_default.json 2> $O/${T}_bench_default.err      # headline + workloads list
+python bench.py --impl reference --steps 5 --warmup 3 > $O/${T}_bench_cfg2_reference_arm.json 2>> $O/${T}_bench_default.err
+python bench.py --config 4 --planner NoMove --gaze scripted --steps 50 --warmup 5 --burn-in 300 --no-cpu-baseline > $O/${T}_bench_cfg4_nomove.json 2> $O/${T}_bench_cfg4.err
+python bench.py --config 2 --motion-profile RVO --steps 20 --warmup 5 --burn-in 100 --no-cpu-baseline > $O/${T}_bench_cfg2_rvo.json 2>> $O/${T}_bench_cfg4.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/${T}_launches_cfg2.csv python bench.py --steps 20 --warmup 3 --burn-in 5 --no-cpu-baseline --no-workloads > $O/${T}_l2.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches_cfg4.csv python bench.py --config 4 --steps 5 --warmup 3 --burn-in 100 --no-cpu-baseline > $O/${T}_l4.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:d2d_step_fused_warp_kernel -s 2700 -c 1 -f -o $O/${T}_fused_cfg2 python bench.py --steps 20 --warmup 5 --burn-in 200 --no-cpu-baseline > $O/${T}_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:d2d_step_fused_warp_kernel -s 2700 -c 1 -f -o $O/${T}_fused_cfg2 python bench.py --steps 20 --warmup 5 --burn-in 200 --no-cpu-baseline --no-workloads > $O/${T}_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:d2d_oxford_kernel -s 150 -c 1 -f -o $O/${T}_oxford_cfg4 python bench.py --config 4 --steps 5 --warmup 3 --burn-in 150 --no-cpu-baseline > $O/${T}_ncu4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:d2d_step_prim_warp_kernel -s 150 -c 1 -f -o $O/${T}_prim_cfg4 python bench.py --config 4 --steps 5 --warmup 3 --burn-in 150 --no-cpu-baseline > $O/${T}_ncu5.log 2>&1
 python tools/warp_prof.py --config 2 > $O/${T}_warp_timeline_cfg2.txt 2>&1
 timeout 300 compute-sanitizer --tool memcheck python tools/sanitize_run.py > $O/${T}_sanitizer_memcheck.txt 2>&1
 timeout 300 compute-sanitizer --tool racecheck python tools/sanitize_run.py > $O/${T}_sanitizer_racecheck.txt 2>&1
-for f in $O/${T}_bench_cfg*.json; do python - "$f" <<'PY'
+for f in $O/${T}_bench_*.json; do python - "$f" <<'PY'
 import json,sys
 try:
     d=json.load(open(sys.argv[1])); print(sys.argv[1].split('/')[-1], round(d["value"]/1e6,2), "M  ms", round(d["ms_per_step"],4), "e2e", round(d["e2e"]["value"]/1e6,2), "frac", d.get("roofline",{}).get("frac"), "cpu", d.get("cpu_baseline",{}).get("value"))

@@ -38,6 +38,8 @@ LEGS = [
          agent_radius=15, agent_max_speed=20, planner="Primitive", gaze="Oxford", B=4096, steps=250),
     dict(name="empty_map Primitive + Owl", static_map="maps/empty_map.npy", agent_number=10, agent_radius=15,
          agent_max_speed=20, planner="Primitive", gaze="Owl", B=4096, steps=250),
+    dict(name="empty_map Jerk_Primitive planner, scripted gaze", static_map="maps/empty_map.npy", agent_number=10, agent_radius=15,
+         agent_max_speed=20, planner="Jerk_Primitive", B=4096, steps=250),
     dict(name="random_map_0 N=142 Primitive scripted gaze (config 3)", static_map="maps/random_map_0.npy", agent_number=20,
          agent_radius=15, agent_max_speed=40, planner="Primitive", B=4096, steps=150),
     dict(name="empty_map noisy measurements var_cam=0.5", static_map="maps/empty_map.npy", agent_number=10, agent_radius=15,
@@ -78,7 +80,7 @@ def run_leg(leg, scale, seed0):
         env.set_drone_pose(poses)
         env.buffer("drone_pose0").copy_(torch.as_tensor(poses.T.copy(), device="cuda:0"))
     ob = util.oracle_batch(p, worlds, poses)
-    n_way = int(env.cfg.n_way) if leg["planner"] == "Primitive" else 0
+    n_way = int(env.cfg.n_way) if leg["planner"] in ("Primitive", "Jerk_Primitive") else 0
     fields = util.BATCH_FIELDS + util.TRACKER_FIELDS + (util.PLANNER_FIELDS if n_way else []) + (["agent_vel"] if rvo else [])
     table = util.action_table()
     alive = np.ones(B, dtype=bool)

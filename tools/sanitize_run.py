@@ -1,6 +1,7 @@
 """Small workload for compute-sanitizer (GPU box):  compute-sanitizer --tool memcheck python tools/sanitize_run.py
 Steps a NoMove batch (fused warp kernel, both march variants: seed 8 has a broken border ring), a Primitive + Oxford batch and
-an RVO batch for a few dozen steps with auto-reset, host mirror bound, and prints the episode statistics."""
+an RVO batch, a Primitive + Owl batch, a Jerk_Primitive batch and a pipelined NoMove run (d2d_step_pipelined: gated kernel,
+deferred mirror stores) for a few dozen steps with auto-reset, host buffers bound, and prints the episode statistics."""
 import os
 import sys
 
@@ -33,6 +34,33 @@ def main():
                 env.step_host(table[torch.randint(0, 6, (B,), generator=g)].contiguous().pin_memory(), lm, yaw, dn)
         print(name, env.stats()[:8])
         env.close()
+    # round 2: Owl policy, Jerk_Primitive planner, pipelined bound stepping
+    p = Params(debug=False, agent_number=10, agent_radius=15, agent_max_speed=20, planner="Primitive", gaze_method="Owl", map_id=1)
+    env = Drone2DVecEnv(p, 16, seeds=1 + np.arange(16), device="cuda:0", auto_reset=True)
+    for t in range(40):
+        env.step(env.plan_gaze("Owl"))
+    print("Primitive+Owl", env.stats()[:8])
+    env.close()
+    p = Params(debug=False, agent_number=10, agent_radius=15, agent_max_speed=20, planner="Jerk_Primitive", gaze_method="LookAhead", map_id=1)
+    env = Drone2DVecEnv(p, 16, seeds=1 + np.arange(16), device="cuda:0", auto_reset=True)
+    for t in range(40):
+        env.step(env.plan_gaze("LookAhead"))
+    print("Jerk_Primitive+LookAhead", env.stats()[:8])
+    env.close()
+    B = 40
+    p = Params(debug=False, agent_number=10, agent_radius=15, agent_max_speed=20, planner="NoMove", map_id=1)
+    env = Drone2DVecEnv(p, B, seeds=1 + np.arange(B), device="cuda:0", auto_reset=True)
+    lm = torch.empty((B, 1, 33, 33), dtype=torch.uint8).pin_memory()
+    yaw = torch.empty((B,), dtype=torch.float32).pin_memory()
+    dn = torch.empty((B,), dtype=torch.uint8).pin_memory()
+    acts = torch.zeros(B, dtype=torch.float64).pin_memory()
+    env.bind_host_io(acts, lm, yaw, dn)
+    for t in range(40):
+        acts.copy_(table[torch.randint(0, 6, (B,), generator=g)])
+        env.step_pipelined(prelaunch_next=False)     # sanitizers make launches blocking: a pre-launched kernel would starve
+    env.bind_host_io(None, None, None, None)
+    print("NoMove pipelined", env.stats()[:8])
+    env.close()
 
 
 if __name__ == "__main__":

@@ -28,10 +28,15 @@ def main():
     ap.add_argument("--region-ms", type=float, default=150.0)
     ap.add_argument("--planner", default=None)
     ap.add_argument("--lib", default=None, help="alternative libdrone2d build to load")
+    ap.add_argument("--trackers", type=int, default=1, help="0: Kalman trackers off (what-if: cost of the tracker phase)")
+    ap.add_argument("--agent-number", type=int, default=-1, help="override the config's agent_number (what-if: 0 = no agents)")
+    ap.add_argument("--no-auto-reset", action="store_true", help="what-if: no env is ever re-initialised")
     args = ap.parse_args()
     import bench
     cfg = bench.make_cfg(args.config, planner=args.planner, envs=args.envs)
     B, pk = cfg["envs"], cfg["params"]
+    if args.agent_number >= 0:
+        pk = dict(pk, agent_number=args.agent_number)
     worlds = bench.make_worlds(pk, pk["map_id"] + np.arange(B), unique=min(B, 16384))
     from gym_drone2d_activeperception_b200 import _native
     if args.lib:
@@ -49,7 +54,8 @@ def main():
     ref_state = None
     out = []
     for v in [int(x) for x in args.variants.split(",")]:
-        mk = lambda: Drone2DVecEnv(p, B, worlds=worlds, device=dev, auto_reset=True, envs_per_block=v)
+        mk = lambda: Drone2DVecEnv(p, B, worlds=worlds, device=dev, auto_reset=not args.no_auto_reset, envs_per_block=v,
+                                   trackers=bool(args.trackers))
         env = mk()
         N = env.num_agents
         touched = B * (bench.D2D_STATE_BYTES + 56 * N)
