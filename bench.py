@@ -392,6 +392,42 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
     rep_ms = np.array([evs[m].elapsed_time(evs[m + 1]) for m in range(M)], dtype=np.float64)
     med_ms, min_ms, max_ms = float(np.median(rep_ms)), float(rep_ms.min()), float(rep_ms.max())
 
+    # ---- the same K steps as ONE launch per replica (d2d_rollout): every warp walks its env through the K steps with the
+    #      env's working set resident on chip -- the device-resident form of a scripted-gaze run (experiment.py:65-70).
+    #      Replicas are visited round robin exactly as above; the launches are captured once and replayed for >= region-ms.
+    rollout = None
+    if pk["planner"] == "NoMove" and not use_ox and pk.get("motion_profile", "CVM") != "RVO" and args.envs_per_block <= 0:
+        act_k = actions[W:W + K].contiguous()
+        for e in envs:                               # warm-up launch per replica (also a K-step continuation of the burn-in)
+            e.rollout(act_k)
+        torch.cuda.synchronize()
+        rgraph = torch.cuda.CUDAGraph()
+        r0 = sum(e.launch_count() for e in envs)
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(rgraph, stream=side):
+                for e in envs:
+                    e.rollout(act_k)
+        r_launches = sum(e.launch_count() for e in envs) - r0
+        rgraph.replay()
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record(); rgraph.replay(); q1.record()
+        torch.cuda.synchronize()
+        Mr = int(min(4000, max(7, -(-args.region_ms // max(1e-3, float(q0.elapsed_time(q1)))))))
+        if world > 1:
+            Mr = int(ctx.gather_rows([float(Mr)])[:, 0].max())
+        revs = [torch.cuda.Event(enable_timing=True) for _ in range(Mr + 1)]
+        ctx.barrier()
+        revs[0].record()
+        for m in range(Mr):
+            rgraph.replay()
+            revs[m + 1].record()
+        ctx.barrier()
+        r_ms = np.array([revs[m].elapsed_time(revs[m + 1]) for m in range(Mr)], dtype=np.float64) / (K * R)
+        rollout = {"med": float(np.median(r_ms)), "min": float(r_ms.min()), "max": float(r_ms.max()), "replays": Mr,
+                   "launches": int(r_launches), "region_ms": float(r_ms.sum() * K * R)}
+        del rgraph
+
     per_step = None
     if headline:
         # secondary: the same step timed one launch at a time (CUDA events around every step, 256 MiB L2 flush in between,
@@ -503,8 +539,12 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
     # ---- over ranks: max of the per-rank medians; every rank's figures are reported
     rows = ctx.gather_rows([med_ms / K, min_ms / K, max_ms / K, e2e_s * 1e3 / Ke, e2e_copy_s * 1e3 / Ke,
                             (e2e_mirror_s if e2e_mirror_s is not None else e2e_copy_s) * 1e3 / Ke,
-                            (e2e_bound_s if e2e_bound_s is not None else e2e_copy_s) * 1e3 / Ke])
-    ms_step = float(rows[:, 0].max())
+                            (e2e_bound_s if e2e_bound_s is not None else e2e_copy_s) * 1e3 / Ke,
+                            rollout["med"] if rollout else 0.0, rollout["min"] if rollout else 0.0,
+                            rollout["max"] if rollout else 0.0])
+    ms_launch_per_step = float(rows[:, 0].max())     # K single-step launches
+    # headline: the K steps through the fastest device-resident entry point that executes exactly these K steps
+    ms_step = float(rows[:, 7].max()) if rollout else ms_launch_per_step
     e2e_ms, e2e_copy_ms, e2e_mirror_ms = float(rows[:, 3].max()), float(rows[:, 4].max()), float(rows[:, 5].max())
     e2e_bound_ms = float(rows[:, 6].max())
     # the one collective of the path: all-reduce of the episode statistics
@@ -513,14 +553,16 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
     e2e = world * B / (e2e_ms * 1e-3)
 
     peak, peak_src = measured_peak()
-    if pk["planner"] == "NoMove":
+    if rollout:
+        kernel_name = "d2d_rollout_warp_kernel (K steps per launch, env state resident on chip)"
+    elif pk["planner"] == "NoMove":
         kernel_name = "d2d_step_fused_warp_kernel (1 launch/step)"
     else:
         kernel_name = "d2d_step_prim_warp_kernel + d2d_plan_kernel + d2d_step_post_list_kernel" + \
                       (" + d2d_oxford_kernel" if use_ox else "") + " (whole step timed)"
     achieved = algorithmic_bytes(N) * B / (ms_step * 1e-3) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_config%d.json" % cfg["config_id"])
+    tpath = os.path.join(ROOT, "profiles", ("traffic_rollout_config%d.json" if rollout else "traffic_config%d.json") % cfg["config_id"])
     if os.path.isfile(tpath) and pk["planner"] == "NoMove" and n_rays == 50 and "view_range" not in cfg["name"]:
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
@@ -529,16 +571,20 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
     res = {
         "value": value, "unit": "env-steps/s", "ms_per_step": ms_step, "rays_per_sec": value * n_rays,
         "config": public_config(cfg, world),
-        "method": {"timing": "K = %d steps captured as one CUDA graph (K step launches), replayed M = %d times back to back, "
+        "method": {"timing": (("K = %d steps of every env as ONE d2d_rollout launch per replica (R = %d launches captured as a CUDA "
+                              "graph, replayed M = %d times back to back); " % (K, R, rollout["replays"])) if rollout else
+                              ("K = %d steps captured as one CUDA graph (K step launches), replayed M = %d times back to back, " % (K, M))) +
                              "one CUDA-event pair per replay on the launch stream, barrier + synchronize around the region; "
-                             "per rank the median replay, over ranks the max of the medians" % (K, M),
-                   "graph_replays": M, "timed_region_ms_this_rank": float(rep_ms.sum()), "wall_s_timed_region": wall,
+                             "per rank the median replay, over ranks the max of the medians",
+                   "graph_replays": rollout["replays"] if rollout else M,
+                   "timed_region_ms_this_rank": rollout["region_ms"] if rollout else float(rep_ms.sum()), "wall_s_timed_region": wall,
                    "replicas": R, "state_touched_between_visits_mb": round(R * touched / 1e6, 1),
                    "l2": "no rotation (--no-flush): state stays L2-resident" if args.no_flush else L2_NOTE,
                    "burn_in_steps_per_replica": burn, "unique_worlds_per_gpu": int(unique), "world_gen_s": round(t_world, 2),
                    "envs_per_block": int(env.cfg.envs_per_block)},
-        "per_rank": [{"rank": r, "ms_per_step_median": float(rows[r, 0]), "ms_per_step_min": float(rows[r, 1]),
-                      "ms_per_step_max": float(rows[r, 2]), "e2e_ms_per_step": float(rows[r, 3])} for r in range(world)],
+        "per_rank": [{"rank": r, "ms_per_step_median": float(rows[r, 7 if rollout else 0]),
+                      "ms_per_step_min": float(rows[r, 8 if rollout else 1]), "ms_per_step_max": float(rows[r, 9 if rollout else 2]),
+                      "single_step_launch_ms_median": float(rows[r, 0]), "e2e_ms_per_step": float(rows[r, 3])} for r in range(world)],
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": 0 if use_ox else B * 8,
                 "d2h_bytes_per_step": B * (1089 + 4 + 1) if mirror_bytes is None else int(round(B * 5 + mirror_bytes)),
                 "steps": Ke,
@@ -547,16 +593,18 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
                              "region) and read by the kernels in place; kernels store changed observation bytes + yaw + done "
                              "straight into the pinned host buffers (bytes counted on the device, mean per step, this rank); " +
                              ("d2d_step_bound, stream synchronised per step" if (use_ox or pk["planner"] != "NoMove") else
-                              "d2d_step_pipelined: the next step's kernel is launched behind the current one and waits for its "
-                              "actions at a gate before the yaw update (the only action-dependent part of a step); every call "
-                              "returns this step's observation before the next actions are written"),
+                              "d2d_step_pipelined: at <= 4116 envs ONE resident kernel serves the whole run (env state stays on chip; "
+                              "a courier block pulls each step's actions out of the pinned buffer once the host has stamped the step; "
+                              "everything but the yaw update runs before that gate; completion is a pinned word the host polls); "
+                              "larger batches: the next step's kernel is pre-launched behind the current one and waits at the same "
+                              "gate.  Every call returns this step's observation before the next actions are written"),
                 "bound_sync": {"value": world * B / (e2e_bound_ms * 1e-3),
                                "what": "d2d_step_bound per step (bound buffers, stream synchronised every step, nothing pre-launched)"},
                 "mirror_step_host": {"value": world * B / (e2e_mirror_ms * 1e-3),
                                      "what": "d2d_step_host per step with the zero-copy mirror bound (round-1 headline path)"},
                 "full_copy": {"value": world * B / (e2e_copy_ms * 1e-3), "d2h_bytes_per_step": B * (1089 + 4 + 1),
                               "what": "d2d_step_host per step, whole observation copied device -> host every step"}},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(rollout["launches"] // R) if rollout else int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "bytes_per_env_step": algorithmic_bytes(N),
                      "kernel": kernel_name, "kernel_ms": ms_step},
@@ -565,6 +613,13 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
              "flight_steps", "grid_discovered", "agents_tracked", "tracked_steps", "plans", "plan_failures", "replans"],
             stats.tolist()[:14])},
     }
+    if rollout:
+        res["single_step_launches"] = {
+            "value": world * B / (ms_launch_per_step * 1e-3), "ms_per_step": ms_launch_per_step, "gpu_launches": int(launches),
+            "what": "the same K steps as K d2d_step launches (one fused kernel per step, captured as one CUDA graph, M = %d replays): "
+                    "the per-step entry point a device-side policy calls; round-1 / early round-2 headline" % M,
+            "roofline_frac": algorithmic_bytes(N) * B / (ms_launch_per_step * 1e-3) / 1e9 / peak}
+        res["gpu_launches_note"] = "launches per K steps of ONE replica of the batch (the timed region visits R replicas round robin)"
     if per_step is not None:
         res["per_step_events"] = per_step
     if clocks is not None:

@@ -87,6 +87,13 @@ struct DevP {
     // action has replaced the sentinel in the device staging buffer (delivered by the host's copy engine)
     unsigned long long *gate;            // the device staging buffer viewed as 64-bit slots (null: actions are valid at launch)
     unsigned int *gate_fault;            // pinned host word, set when a warp gave up waiting (the actions never came)
+    // resident form (d2d_rollout_warp_kernel<GATED>): one kernel serves a whole run of host-driven steps
+    unsigned long long *gate_count;      // device: (env, step) pairs completed since the kernel started
+    unsigned int *gate_done;             // pinned host word: sequence number of the last step whose stores are all visible
+    // courier block of the resident kernel (when an SM is free for it): polls the stamp word in pinned HOST memory and pulls
+    // the step's actions out of the caller's pinned buffer itself -- no copy-engine transfer, no driver call per step
+    const unsigned long long *gate_src;          // device-visible address of the caller's pinned action buffer (null: copy engine)
+    const unsigned long long *gate_stamp_host;   // device-visible address of the pinned stamp word the host stores per step
 #ifdef D2D_WARP_PROF
     unsigned long long *prof;    // [B][12]: 10 globaltimer stamps, smid, warpid of the fused warp kernel (tools/warp_prof.py builds with -DD2D_WARP_PROF)
 #endif

@@ -244,7 +244,7 @@ __device__ __forceinline__ void d2d_reset_prefetch(const DevP &P, const EnvS &s,
 template <bool COLLIDE_HERE, bool PF = false>
 __device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &c, int env0, int E, int tid, int T,
                                                  double2 pf_pos = double2{0.0, 0.0}, double2 pf_pref = double2{0.0, 0.0},
-                                                 double pf_r = 0.0) {
+                                                 double pf_r = 0.0, double2 *keep_pos = nullptr, double2 *keep_pref = nullptr) {
     const double C6 = 0.8660254037844387, S6 = 0.49999999999999994;   // math.cos(pi/6), math.sin(pi/6) (glibc)
     const int N = P.N, NP = P.NP;
 #pragma unroll 1
@@ -289,6 +289,7 @@ __device__ __forceinline__ void d2d_phase_agents(const DevP &P, const BlockCtx &
         pos.y = pos.y + vy * P.dt;
         P.apos[g] = pos;
         P.apref[g] = pref;
+        if (PF && keep_pos && w == tid) { *keep_pos = pos; *keep_pref = pref; }   // multi-step kernels: next step's input
         const int q = i * NP + k;
         c.sx[q] = pos.x; c.sy[q] = pos.y; c.sr2[q] = r * r;
         // broad phase: a ray sample is never farther than depth + 9*sqrt(2) from the drone
@@ -868,7 +869,7 @@ __device__ __forceinline__ void d2d_leader_begin(const DevP &P, EnvS &s) {
 
 // second half (drone_v2.py:196-235) after the planner verdict `success`
 __device__ D2D_COLD void d2d_leader_finish(const DevP &P, EnvS &s, const uint64_t *gt, int e, double action,
-                                                  bool success) {
+                                                  bool success, bool with_yaw = true) {
     if (!success) {   // Drone2D.brake utils.py:755-762
         const double nv = d2d_norm2(s.vx, s.vy);
         if (nv <= P.max_acc * P.dt) { s.vx = 0.0; s.vy = 0.0; }
@@ -905,8 +906,8 @@ __device__ D2D_COLD void d2d_leader_finish(const DevP &P, EnvS &s, const uint64_
         s.cursor += 1;
         if (s.cursor == s.nseg * P.n_way) { s.nseg = 0; s.cursor = 0; }
     }
-    // step_yaw utils.py:741-743
-    s.yaw = d2d_pymod(s.yaw + (action * P.max_yaw_speed) * P.dt, 360.0);
+    // step_yaw utils.py:741-743 (the resident gated kernel runs everything above before the action is known, this after)
+    if (with_yaw) s.yaw = d2d_pymod(s.yaw + (action * P.max_yaw_speed) * P.dt, 360.0);
 }
 
 // the five static probes of Drone2D.is_collide (utils.py:766-771); q = 0..4
@@ -916,7 +917,8 @@ __device__ __forceinline__ int d2d_static_probe(const DevP &P, const uint64_t *g
     return d2d_gt_probe(P, gt, px + ox, py + oy);
 }
 
-__device__ D2D_COLD void d2d_leader_flags(const DevP &P, EnvS &s, const uint64_t *gt, int e, int static_hit = -1) {
+__device__ D2D_COLD void d2d_leader_flags(const DevP &P, EnvS &s, const uint64_t *gt, int e, int static_hit = -1,
+                                         bool mirror_scalars = true) {
     // is_collide utils.py:764-778
     int col = 0;
     if (static_hit < 0) {
@@ -938,9 +940,11 @@ __device__ D2D_COLD void d2d_leader_flags(const DevP &P, EnvS &s, const uint64_t
     s.done_now = done;
     s.ix = d2d_cell(s.px, P.scale, P.inv_scale); s.iy = d2d_cell(s.py, P.scale, P.inv_scale);
     P.collision[e] = (uint8_t)col; P.dead_lock[e] = (uint8_t)dead; P.freezing[e] = (uint8_t)frz; P.done[e] = (uint8_t)done;
-    P.yaw_obs[e] = (float)s.yaw;
-    if (P.yaw_mirror) P.yaw_mirror[e] = (float)s.yaw;
-    if (P.done_mirror) P.done_mirror[e] = (uint8_t)done;
+    if (mirror_scalars) P.yaw_obs[e] = (float)s.yaw;
+    if (mirror_scalars) {        // the resident gated kernel publishes these per block, coalesced
+        if (P.yaw_mirror) P.yaw_mirror[e] = (float)s.yaw;
+        if (P.done_mirror) P.done_mirror[e] = (uint8_t)done;
+    }
     if (done) {
         atomicAdd(&P.stats[D2D_STAT_EPISODES], 1ull);
         if (s.sm == SM_GOAL_REACHED) atomicAdd(&P.stats[D2D_STAT_SUCCESS], 1ull);
@@ -1112,14 +1116,15 @@ __device__ __forceinline__ uint32_t d2d_obs_word(const uint8_t *bel, int ix, int
     return w;
 }
 
-__device__ D2D_COLD void d2d_obs_env_warp(const DevP &P, const uint8_t *bel, int ix, int iy, int e, int lane) {
+__device__ D2D_COLD void d2d_obs_env_warp(const DevP &P, const uint8_t *bel, int ix, int iy, int e, int lane,
+                                         bool to_mirror = true) {
     // bytes [1089*e, 1089*e + 1089) of the observation tensor: unaligned head / tail (1089 = 1 mod 4) as byte stores,
     // the middle as coalesced 32-bit stores assembled with funnel shifts from aligned shared-memory words.
     uint8_t *out = P.local_map + (size_t)e * D2D_LOCAL_CELLS;
     const int head = (4 - (e & 3)) & 3;                 // arena buffers are 256-B aligned
     const int nwords = (D2D_LOCAL_CELLS - head) >> 2;
     const int tail0 = head + 4 * nwords;
-    uint8_t *out_m = P.lm_mirror ? P.lm_mirror + (size_t)e * D2D_LOCAL_CELLS : nullptr;   // base 4-byte aligned (checked at bind)
+    uint8_t *out_m = (to_mirror && P.lm_mirror) ? P.lm_mirror + (size_t)e * D2D_LOCAL_CELLS : nullptr;   // base 4-byte aligned (checked at bind)
     if (lane < head) {
         const uint8_t v = (uint8_t)d2d_obs_cell(bel, ix, iy, lane);
         out[lane] = v;
@@ -1139,6 +1144,23 @@ __device__ D2D_COLD void d2d_obs_env_warp(const DevP &P, const uint8_t *bel, int
         if (ow_m) ow_m[j] = v;
     }
     if (out_m && lane == 0) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)D2D_LOCAL_CELLS);
+}
+
+// env e's freshly rewritten observation slice, device tensor -> host mirror (resident gated kernel: the rewrite itself runs
+// before the gate, only this copy behind it).  Reads bypass L1: the slice was written by other lanes of this warp.
+__device__ __forceinline__ void d2d_obs_mirror_copy_warp(const DevP &P, int e, int lane) {
+    const uint8_t *src = P.local_map + (size_t)e * D2D_LOCAL_CELLS;
+    uint8_t *dst = P.lm_mirror + (size_t)e * D2D_LOCAL_CELLS;
+    const int head = (4 - (e & 3)) & 3;
+    const int nwords = (D2D_LOCAL_CELLS - head) >> 2;
+    const int tail0 = head + 4 * nwords;
+    if (lane < head) dst[lane] = __ldcg(src + lane);
+    if (lane < D2D_LOCAL_CELLS - tail0) dst[tail0 + lane] = __ldcg(src + tail0 + lane);
+    const uint32_t *sw = (const uint32_t *)(src + head);
+    uint32_t *dw = (uint32_t *)(dst + head);
+#pragma unroll 4
+    for (int j = lane; j < nwords; j += 32) dw[j] = __ldcg(sw + j);
+    if (lane == 0) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)D2D_LOCAL_CELLS);
 }
 
 // explored-cell count of an env that finished this step (experiment.py:90 "Grid discovered"), one warp, four cells per
@@ -1295,4 +1317,295 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     }
     if (s.done_now) d2d_count_explored_warp(P, c.belief, lane);
     D2D_PROF(3);
+}
+
+// =============================================================================================================
+// Multi-step ("rollout") variant of the fused warp kernel: consecutive Drone2DEnv2.step calls of an env in ONE launch.
+// Step k+1 of an env depends on step k of the SAME env only, so a warp that owns an env can walk it through many steps
+// without ever meeting the other warps: the env's working set (belief grid, ground-truth bitmap, agents, record) is
+// fetched from HBM once and stays in shared memory / registers, and every store of a step goes out exactly as the
+// single-step kernel issues it (belief cells, patched observation bytes, agents, trackers, verdict arrays).
+//
+// GATED = false (d2d_rollout): K steps, actions[t * action_stride + e] is the action of env e at step t (stride 0: the
+//   same [B] vector every step).  Outputs are bit-identical to K single-step launches (tests/test_gpu_rollout.py); the
+//   per-step verdict arrays / observation hold the LAST step's values, the statistics counters the sum over the steps.
+// GATED = true (d2d_step_pipelined): a host policy drives the loop.  The kernel stays resident for a whole run of steps;
+//   the action of every step arrives through the gate (P.gate: device staging slots holding a sentinel until the host's
+//   copy engine has delivered the step's actions), together with a stamped word that says whether another step follows.
+//   Everything of step t+1 that does not depend on its action (agents, rays, trackers, probes) runs while the host is
+//   still looking at observation t; host-mirror stores are held back behind the gate and replayed; when the last warp
+//   has finished step t (all its stores fenced system-wide) it writes t into a pinned host word the host polls.
+//
+// SYNC: the warps of a block start every step together (one block barrier per step).  Warps that run the same phase at
+//   the same time share their instruction fetches; without it the 28 warps of an SM drift apart within a few dozen steps,
+//   their combined footprint (the hot path of a step is ~30 KB of SASS) no longer fits the SM's 32 KB L1.5 instruction
+//   cache and a third of the warp-state samples become `no_instruction` stalls (profiles/r2_ncu_rollout_cfg2_nosync.txt:
+//   20.1 us per step without the barrier, 16.9 us with 28-warp blocks and one barrier per step).  The gate re-aligns the
+//   warps by itself, so the GATED form needs no barrier.
+// =============================================================================================================
+#define D2D_GATE_STAMP_SLOT(B) ((size_t)(B))     // staging slot behind the B action slots: (session step << 1) | more
+
+template <int WPB, int MINB, bool SYNC, bool GATED>
+__global__ void __launch_bounds__(WPB * 32, MINB) d2d_rollout_warp_kernel(const DevP P, const double *__restrict__ actions,
+                                                                          int K, long long action_stride, int sync_every,
+                                                                          unsigned int t_first) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int e = blockIdx.x * WPB + wid;
+    if (GATED) {                                                     // block arrival counter (see the end of the step)
+        if (threadIdx.x == 0) *(int *)(smem + (size_t)WPB * d2d_warp_slice_bytes(P.NP, P.HW, D2D_FUSED_WARP_EXTRA)) = 0;
+        __syncthreads();
+    }
+    if (GATED && P.gate_src && blockIdx.x == gridDim.x - 1) {
+        // ---- courier block (owns no env).  Per step: thread 0 polls the stamp word in pinned host memory (one PCIe read in
+        // flight at a time: ~1.5 us per poll); when the host has stamped the step, the block pulls the B actions out of the
+        // caller's pinned buffer with coalesced reads, drops them over the sentinels in the device staging slots the env warps
+        // are polling, and then publishes the stamp on the device.  The host's part of a step is ONE store.
+        // (no static __shared__ here: the kernel's dynamic shared-memory limit is raised to the 227 KB maximum)
+        unsigned long long &cst = *(unsigned long long *)(smem + (size_t)WPB * d2d_warp_slice_bytes(P.NP, P.HW, D2D_FUSED_WARP_EXTRA) + 128);
+        const volatile unsigned long long *hs = (const volatile unsigned long long *)P.gate_stamp_host;
+        for (unsigned int t = 0;; t++) {
+            if (threadIdx.x == 0) {
+                const unsigned long long want = (unsigned long long)(t_first + t);
+                const long long t0 = clock64();
+                unsigned long long st;
+                while ((((st = *hs) >> 1) & 0xffffffffull) != want) {
+                    if (clock64() - t0 > 4000000000ll) { *P.gate_fault = 1u; st = (want << 1) | (1ull << 62); break; }   // ~2 s
+                }
+                cst = st;
+            }
+            __syncthreads();
+            const unsigned long long st = cst;
+            const bool zero = (st >> 62) & 1ull;                     // abandoned run (or fault): finish the step with action 0
+            // all PCIe reads of a thread in flight before its first store (a load -> store loop would pay one ~2 us round trip
+            // per iteration)
+#pragma unroll 1
+            for (int i0 = threadIdx.x; i0 < P.B; i0 += 8 * (int)blockDim.x) {
+                unsigned long long v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int i = i0 + k * (int)blockDim.x;
+                    v[k] = (i < P.B && !zero) ? __ldcv(P.gate_src + i) : 0ull;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int i = i0 + k * (int)blockDim.x;
+                    if (i < P.B) P.gate[i] = v[k];
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                *(volatile unsigned long long *)(P.gate + D2D_GATE_STAMP_SLOT(P.B)) = st & 0x1ffffffffull;
+            }
+            if (!(st & 1ull)) return;
+        }
+    }
+    if (e >= P.B) {                                                  // warp-uniform; a spare warp only keeps the barriers whole
+        if (SYNC) for (int t = 1; t < K; t++) if (t % sync_every == 0) __syncthreads();
+        return;
+    }
+    unsigned char *slice = smem + (size_t)wid * d2d_warp_slice_bytes(P.NP, P.HW, GATED ? D2D_FUSED_WARP_EXTRA : 0);
+    const BlockCtx c = d2d_carve(slice, 1, P.NP, P.HW);
+    uint32_t *chg = (uint32_t *)(slice + d2d_step_smem_bytes(1, P.NP, P.HW));   // GATED: this step's changed cells
+    int *nchg = (int *)(chg + D2D_CHG_CAP);
+    // GATED: block-level publication area behind the warp slices: arrival counter, this step's yaw / done of the block's envs
+    unsigned char *blk = smem + (size_t)WPB * d2d_warp_slice_bytes(P.NP, P.HW, GATED ? D2D_FUSED_WARP_EXTRA : 0);
+    int *blk_cnt = (int *)blk;
+    float *blk_yaw = (float *)(blk + 16);
+    uint8_t *blk_done = blk + 16 + WPB * 4;
+    const int blk_envs = min(WPB, P.B - (int)blockIdx.x * WPB);
+    EnvS &s = c.S[0];
+    const size_t ga = (size_t)e * P.NP + lane;
+    double2 pf_pos = double2{0.0, 0.0}, pf_pref = double2{0.0, 0.0};
+    double pf_r = 0.0;
+    uint8_t pf_act = 0;
+    if (lane < P.N) {
+        pf_pos = P.apos[ga]; pf_pref = P.apref[ga]; pf_r = P.arad[ga];
+        if (P.trackers) pf_act = P.trk_active[ga];
+    }
+    double action = GATED ? 0.0 : actions[e];
+    if (lane == 0) {
+        if (GATED) *nchg = 0;
+        d2d_mbar_init(c.mbar, 1);
+        d2d_mbar_expect_tx(c.mbar, D2D_GT_ROW_BYTES + D2D_BELIEF_STRIDE);
+        d2d_bulk_g2s(c.gt, P.gt_rows + (size_t)e * D2D_GRID, D2D_GT_ROW_BYTES, c.mbar);
+        d2d_bulk_g2s(c.belief, P.belief + (size_t)e * D2D_BELIEF_STRIDE, D2D_BELIEF_STRIDE, c.mbar);
+        c.misc[0] = 0;
+    }
+    d2d_load_env_warp(P, s, e, lane);
+    if (lane == 0) c.misc[1] = s.reset;
+#pragma unroll 1
+    for (int w = lane; w < P.HW; w += 32) c.hitw[w] = 0u;
+    __syncwarp();
+    int border_ok = 0;
+    const bool mirror = GATED && P.lm_mirror != nullptr;
+#pragma unroll 1
+    for (int t = 0;;) {
+        // here: the record is begun (d2d_env_begin), c.misc[1] = s.reset, the hit words are clear, pf_* hold the live agent
+        // state of lane's agent (replaced by the snapshot just below when the env is being reset)
+        D2D_PROF(0);
+        d2d_reset_prefetch(P, s, e, lane, pf_pos, pf_pref);
+        d2d_reset_arrays(P, c, e, 1, lane, 32, t == 0 ? c.mbar : nullptr);
+        d2d_phase_agents<true, true>(P, c, e, 1, lane, 32, pf_pos, pf_pref, pf_r, &pf_pos, &pf_pref);
+        if (t == 0 && pf_act && !s.reset) d2d_prefetch_tracker(P, ga);
+        if (lane == 0) d2d_leader_begin(P, s);
+        __syncwarp();
+        const bool patch = !s.reset && s.obs_ix == s.ix && s.obs_iy == s.iy;
+        RayOut ro;
+        ro.bel_s = c.belief; ro.e = e; ro.patch = patch ? 1 : 0;
+        ro.wi = s.ix - 16; ro.wj = s.iy - 16;
+        ro.chg = (mirror && patch) ? chg : nullptr; ro.nchg = nchg; ro.defer_mirror = GATED ? 1 : 0;
+        if (t == 0) {
+            d2d_mbar_wait(c.mbar, 0);
+            border_ok = d2d_border_intact(c.gt, lane);               // the ground truth never changes
+        }
+        ro.border_ok = border_ok;
+        D2D_PROF(1);
+        d2d_phase_rays_warp<false>(P, c, ro, lane);
+        __syncwarp();
+        D2D_PROF(2);
+        if (P.var_cam != 0.0) {
+            if (lane == 0) d2d_measure_env(P, c, e);
+            __syncwarp();
+        }
+        d2d_phase_trackers<true>(P, c, e, 1, lane, 32, pf_act);
+        const int shit = __any_sync(0xffffffffu, lane < 5 ? d2d_static_probe(P, c.gt, s.px, s.py, lane) : 0);
+        __syncwarp();
+        int more = (t + 1 < K) ? 1 : 0;
+        bool rewrite = false;
+        int n_changed = 0;
+        if (GATED) {
+            // Everything of the step except the yaw update is independent of the action (utils.py:741-743 is the only place it
+            // is used): planner verdict, step_pos, collision / done flags, statistics and the device-side observation all run
+            // BEFORE the gate, while the host is still choosing the action.
+            if (lane == 0) {
+                s.tgx = -1.0; s.tgy = -1.0;                          // NoMove.plan traj_planner.py:70-73
+                d2d_leader_finish(P, s, c.gt, e, 0.0, true, false);
+                d2d_leader_flags(P, s, c.gt, e, shit, false);
+            }
+            __syncwarp();
+            n_changed = mirror ? *nchg : 0;
+            rewrite = !patch || s.ix != s.obs_ix || s.iy != s.obs_iy || (mirror && n_changed > D2D_CHG_CAP);
+            __syncwarp();
+            if (rewrite && lane == 0) { s.obs_ix = s.ix; s.obs_iy = s.iy; }
+            __syncwarp();
+            if (rewrite) d2d_obs_env_warp(P, c.belief, s.ix, s.iy, e, lane, false);      // device tensor only
+            if (s.done_now) d2d_count_explored_warp(P, c.belief, lane);
+            D2D_PROF(8);
+            // Wait for this env's slot to lose the sentinel, take the action, put the sentinel back; then read the stamped word
+            // that travels with the actions: (session step << 1) | (another step follows).
+            if (lane == 0) {
+                volatile unsigned long long *slot = P.gate + e;
+                volatile unsigned long long *stamp = P.gate + D2D_GATE_STAMP_SLOT(P.B);
+                const unsigned long long want = (unsigned long long)(t_first + (unsigned int)t);
+                const long long t0 = clock64();
+                unsigned long long bits, st = 0ull;
+                bool fault = false;
+                while ((bits = *slot) == D2D_ACTION_SENTINEL) {
+                    if (clock64() - t0 > 4000000000ll) { fault = true; break; }      // ~2 s: the host never came back
+                }
+                if (!fault) {
+                    while (((st = *stamp) >> 1) != want) {
+                        if (clock64() - t0 > 4000000000ll) { fault = true; break; }
+                    }
+                }
+                if (fault) { *P.gate_fault = 1u; bits = 0ull; st = 0ull; }            // finish the step with action 0 and leave
+                action = __longlong_as_double((long long)bits);
+                *slot = D2D_ACTION_SENTINEL;
+                more = (int)(st & 1ull);
+                s.yaw = d2d_pymod(s.yaw + (action * P.max_yaw_speed) * P.dt, 360.0);   // step_yaw utils.py:741-743
+                P.yaw_obs[e] = (float)s.yaw;
+            }
+            more = __shfl_sync(0xffffffffu, more, 0);
+            D2D_PROF(9);
+            // behind the gate: this step's observation bytes go out to the host mirror
+            if (mirror) {
+                if (rewrite) {
+                    __syncwarp();
+                    d2d_obs_mirror_copy_warp(P, e, lane);
+                } else if (n_changed > 0) {
+                    for (int q = lane; q < n_changed; q += 32) {      // one byte each over PCIe
+                        const int cell = (int)(chg[q] & 0xFFFFu);
+                        const int ci = cell / D2D_GRID, cj = cell - ci * D2D_GRID;
+                        P.lm_mirror[(size_t)e * D2D_LOCAL_CELLS + (ci - ro.wi) * D2D_LOCAL + (cj - ro.wj)] = (uint8_t)(chg[q] >> 16);
+                    }
+                    if (lane == 0) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)n_changed);
+                }
+            }
+            __syncwarp();
+        } else {
+            if (lane == 0) {
+                s.tgx = -1.0; s.tgy = -1.0;                          // NoMove.plan traj_planner.py:70-73
+                d2d_leader_finish(P, s, c.gt, e, action, true);
+                d2d_leader_flags(P, s, c.gt, e, shit);
+                if (patch && P.lm_mirror) {
+                    int *cnt = (int *)(c.belief + D2D_MIRCNT_OFF);
+                    const int nb = *cnt;
+                    if (nb) { atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)nb); *cnt = 0; }
+                }
+            }
+            __syncwarp();
+            rewrite = !patch || s.ix != s.obs_ix || s.iy != s.obs_iy;
+            __syncwarp();
+            if (rewrite && lane == 0) { s.obs_ix = s.ix; s.obs_iy = s.iy; }
+            __syncwarp();
+            if (rewrite) d2d_obs_env_warp(P, c.belief, s.ix, s.iy, e, lane);
+            if (s.done_now) d2d_count_explored_warp(P, c.belief, lane);
+        }
+        D2D_PROF(4);
+        if (GATED) {
+            // Step complete for this env.  The block's LAST warp to get here publishes the block: yaw / done of its envs as two
+            // coalesced stores into the host mirror, a device-scope fence and one global arrival count; the last block of the
+            // step issues the step's ONE system-scope fence and writes the step's sequence number into the pinned word the
+            // host polls.  Every warp's own mirror stores are ordered before that flag through the chain block fence + block
+            // counter -> device fence + global counter -> system fence (fences are cumulative).  Measured: a system fence
+            // per warp (4096 per step, each waiting for its PCIe writes) 15 us, one per block 10 us, one per step ~1 us.
+            int last = 0;
+            if (lane == 0) {
+                blk_yaw[wid] = (float)s.yaw; blk_done[wid] = (uint8_t)s.done_now;
+                __threadfence_block();
+                last = atomicAdd(blk_cnt, 1) == blk_envs - 1 ? 1 : 0;
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                __threadfence_block();
+                const int e0 = (int)blockIdx.x * WPB;
+                if (lane < blk_envs) {
+                    if (P.yaw_mirror) P.yaw_mirror[e0 + lane] = blk_yaw[lane];
+                    if (P.done_mirror) P.done_mirror[e0 + lane] = blk_done[lane];
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    *blk_cnt = 0;
+                    __threadfence();                      // device scope: cheap; the step's ONE system fence is below
+                    const unsigned long long n = atomicAdd(P.gate_count, (unsigned long long)blk_envs) + (unsigned long long)blk_envs;
+                    if (n == (unsigned long long)P.B * (unsigned long long)(t + 1)) {
+                        atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], (unsigned long long)P.B);   // every env stepped once
+                        __threadfence_system();           // cumulative: orders every block's mirror stores before the flag
+                        *(volatile unsigned int *)P.gate_done = t_first + (unsigned int)t;
+                    }
+                }
+            }
+        }
+        D2D_PROF(3);
+        t += 1;
+        if (!more) break;
+        if (SYNC && t % sync_every == 0) __syncthreads();
+        // ---- next step of the same env: what d2d_load_env_warp does at kernel entry, from the live record
+        if (!GATED) action = actions[(size_t)t * (size_t)action_stride + e];
+        if (P.trackers && lane < P.N) pf_act = P.trk_active[ga];     // written by this very lane in the tracker phase
+#pragma unroll 1
+        for (int w = lane; w < P.HW; w += 32) c.hitw[w] = 0u;
+        __syncwarp();
+        if (lane == 0) {
+            const bool was_done = s.done_now != 0;
+            d2d_env_begin(P, s, was_done);
+            c.misc[1] = s.reset;
+            if (GATED) *nchg = 0;
+        }
+        __syncwarp();
+    }
+    d2d_store_env_warp(P, s, e, lane);
+    if (!GATED && e == 0 && lane == 0) atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], (unsigned long long)P.B * (unsigned long long)K);
 }

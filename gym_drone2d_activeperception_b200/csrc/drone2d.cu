@@ -60,6 +60,12 @@ struct d2d_handle {
     cudaStream_t copy_stream = nullptr;          // carries the per-step action copy
     unsigned int pipe_seq = 0;
     bool pipe_inflight = false;                  // the kernel of the NEXT step has been launched and waits at its gate
+    int pipe_mode = 0;                           // 1: one pre-launched kernel per step; 2: resident kernel (whole run, B <= one wave)
+    double *pipe_pub = nullptr;                  // pinned [B + 1]: the step's actions + stamp word, source of the ONE copy per step
+    unsigned long long *pipe_count = nullptr;    // device counter behind DevP::gate_count
+    int resident_capacity = -1;                  // envs the resident kernel can hold at once (blocks/SM x SMs x warps/block)
+    int resident_blocks = 0;                     // ... and the blocks that are co-resident (one may serve as the courier)
+    bool pipe_courier = false;                   // this run's actions are pulled by the kernel's courier block (no copy engine)
     cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};   // [0], [1]: completion of alternate steps; [2]: sentinels in place
     // D2D_PIPE_DEBUG=1: host-side time of the phases of d2d_step_pipelined, printed by d2d_destroy
     double dbg_launch_ns = 0, dbg_wait_ns = 0, dbg_total_ns = 0; long dbg_n = 0, dbg_polls = 0;
@@ -361,7 +367,7 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
                             cfg->planner == D2D_PLANNER_JERK ? sizeof(d2d_jerk_tables) : 16);
     size_t o_stats = add_buf(h, cur, "stats", D2D_I64, 1, SHP(D2D_NUM_STATS), SHP(1), D2D_NUM_STATS);
     size_t o_tab = add_buf(h, cur, "tables", D2D_U8, 1, SHP((int64_t)sizeof(DevTables)), SHP(1), sizeof(DevTables));
-    size_t o_stage = add_buf(h, cur, "actions_staging", D2D_F64, 1, SHP(B), SHP(1), sB);
+    size_t o_stage = add_buf(h, cur, "actions_staging", D2D_F64, 1, SHP(B), SHP(1), sB + 8);   // + the stamp slot of the resident gated kernel
     size_t o_plan_ws = 0;
     size_t plan_ws_bytes = 0;
     if (cfg->planner == D2D_PLANNER_PRIMITIVE) {
@@ -480,14 +486,31 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     return D2D_OK;
 }
 
+// A kernel is waiting at its gate for actions that will not come (destroy / re-bind): complete that step with action 0.
+static void pipe_release(d2d_handle *h) {
+    if (h->pipe_mode == 2 && h->pipe_courier) {      // resident kernel with a courier: stamp "last step, actions = 0"
+        const unsigned long long stamp = ((unsigned long long)(h->pipe_seq + 1) << 1) | (1ull << 62);
+        __atomic_store_n((unsigned long long *)(h->gate_host + 8), stamp, __ATOMIC_RELEASE);
+    } else if (h->pipe_mode == 2 && h->pipe_pub) {   // resident kernel fed by the copy engine: a proper stamp that says "last step"
+        memset(h->pipe_pub, 0, (size_t)h->B * 8);
+        const unsigned long long stamp = ((unsigned long long)(h->pipe_seq + 1) << 1);
+        memcpy(h->pipe_pub + h->B, &stamp, 8);
+        cudaMemcpyAsync(h->stage_actions, h->pipe_pub, (size_t)(h->B + 1) * 8, cudaMemcpyHostToDevice, h->copy_stream);
+    } else {
+        cudaMemsetAsync(h->stage_actions, 0, (size_t)h->B * 8, h->copy_stream);
+    }
+    cudaStreamSynchronize(h->io_stream);
+    h->pipe_inflight = false;
+    h->pipe_mode = 0;
+    h->pipe_seq += 1;
+}
+
 extern "C" int d2d_destroy(d2d_handle *h) {
     if (!h) return D2D_OK;
     cudaSetDevice(h->cfg.device);
-    if (h->pipe_inflight) {          // release the kernel that waits for its actions (the state is going away anyway)
-        cudaMemsetAsync(h->stage_actions, 0, (size_t)h->B * 8, h->copy_stream);
-        cudaStreamSynchronize(h->io_stream);
-        h->pipe_inflight = false;
-    }
+    if (h->pipe_inflight) pipe_release(h);   // release the kernel that waits for its actions (the state is going away anyway)
+    if (h->pipe_pub) cudaFreeHost(h->pipe_pub);
+    if (h->pipe_count) cudaFree(h->pipe_count);
     if (h->dbg_n && getenv("D2D_PIPE_DEBUG"))
         fprintf(stderr, "[d2d pipelined] calls %ld: publish+launch %.2f us, wait %.2f us (%.1f event polls), total %.2f us per call\n",
                 h->dbg_n, h->dbg_launch_ns / h->dbg_n * 1e-3, h->dbg_wait_ns / h->dbg_n * 1e-3, (double)h->dbg_polls / h->dbg_n,
@@ -798,6 +821,67 @@ extern "C" int d2d_step(d2d_handle *h, const double *actions_dev, void *stream) 
     return D2D_OK;
 }
 
+#define D2D_RESIDENT_WPB 28          // resident gated kernel: one 28-warp block per SM (28 x 148 = 4144 envs in flight)
+
+template <int WPB, int MINB, bool SYNC, bool GATED>
+static int launch_rollout(d2d_handle *h, const double *actions, int K, long long stride, cudaStream_t st, unsigned int t_first = 0,
+                          int extra_blocks = 0) {
+    const size_t smem = (size_t)WPB * d2d_warp_slice_bytes(h->NP, h->HW, GATED ? D2D_FUSED_WARP_EXTRA : 0) + (GATED ? 256 : 0);
+    if (smem > 227 * 1024) { h->err = "rollout kernel: shared memory per block exceeds 227 KB"; return D2D_ERR_INVALID; }
+    const int rc = ensure_smem_attr(h, (const void *)d2d_rollout_warp_kernel<WPB, MINB, SYNC, GATED>, "rollout warp");
+    if (rc != D2D_OK) return rc;
+    static const int sync_every = getenv("D2D_ROLLOUT_SYNC") ? atoi(getenv("D2D_ROLLOUT_SYNC")) : 1;
+    d2d_rollout_warp_kernel<WPB, MINB, SYNC, GATED><<<(h->B + WPB - 1) / WPB + extra_blocks, WPB * 32, smem, st>>>(
+        h->P, actions, K, stride, sync_every > 0 ? sync_every : 1, t_first);
+    return D2D_OK;
+}
+
+// envs the resident gated kernel can hold at once: every env's warp must be on an SM for the whole run (a warp that waits
+// for a later wave's slot would wait forever: the first wave only leaves when the host ends the run)
+static int resident_capacity(d2d_handle *h) {
+    if (h->resident_capacity >= 0) return h->resident_capacity;
+    constexpr int WPB = D2D_RESIDENT_WPB;
+    const size_t smem = (size_t)WPB * d2d_warp_slice_bytes(h->NP, h->HW, D2D_FUSED_WARP_EXTRA) + 256;
+    int cap = 0, nb = 0, sms = 0;
+    if (smem <= 227 * 1024 && ensure_smem_attr(h, (const void *)d2d_rollout_warp_kernel<WPB, 1, false, true>, "rollout warp") == D2D_OK &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, d2d_rollout_warp_kernel<WPB, 1, false, true>, WPB * 32, smem) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device) == cudaSuccess)
+        { cap = nb * sms * WPB; h->resident_blocks = nb * sms; }
+    else
+        cudaGetLastError();
+    if (getenv("D2D_PIPE_DEBUG")) fprintf(stderr, "[d2d pipelined] resident kernel: %d blocks/SM x %d SMs, smem %zu B -> capacity %d envs (%s)\n", nb, sms, smem, cap, cudaGetErrorString(cudaPeekAtLastError()));
+    h->resident_capacity = cap;
+    return cap;
+}
+
+extern "C" int d2d_rollout(d2d_handle *h, const double *actions_dev, int32_t num_steps, int64_t action_stride, void *stream) {
+    if (!h || !actions_dev || num_steps < 1) return D2D_ERR_INVALID;
+    D2D_NO_PIPE(h);
+    if (!h->world_set) { h->err = "d2d_rollout before d2d_set_world"; return D2D_ERR_STATE; }
+    if (h->cfg.var_cam != 0.0 && !h->rng_set) { h->err = "var_cam != 0: d2d_set_rng must provide the np.random stream state"; return D2D_ERR_STATE; }
+    if (h->cfg.planner != D2D_PLANNER_NOMOVE || h->P.motion_rvo || h->cfg.envs_per_block > 0) {
+        h->err = "d2d_rollout: NoMove planner, CVM motion profile and the default warp kernels only (use d2d_step)";
+        return D2D_ERR_INVALID;
+    }
+    if (action_stride != 0 && action_stride < h->B) { h->err = "d2d_rollout: action_stride must be 0 or >= num_envs"; return D2D_ERR_INVALID; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // experiment knob (tools/rollout_bench.py): block shape / per-step block barrier of the rollout kernel
+    static const int variant = getenv("D2D_ROLLOUT_VARIANT") ? atoi(getenv("D2D_ROLLOUT_VARIANT")) : 0;
+    int rc;
+    switch (variant) {
+        case 1: rc = launch_rollout<4, 7, false, false>(h, actions_dev, num_steps, action_stride, st); break;
+        case 2: rc = launch_rollout<4, 7, true, false>(h, actions_dev, num_steps, action_stride, st); break;
+        case 3: rc = launch_rollout<7, 4, true, false>(h, actions_dev, num_steps, action_stride, st); break;
+        case 4: rc = launch_rollout<14, 2, true, false>(h, actions_dev, num_steps, action_stride, st); break;
+        default: rc = launch_rollout<28, 1, true, false>(h, actions_dev, num_steps, action_stride, st); break;
+    }
+    if (rc != D2D_OK) return rc;
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return D2D_OK;
+}
+
 extern "C" int d2d_step_host(d2d_handle *h, const double *actions_host, uint8_t *local_map_host, float *yaw_host,
                              uint8_t *done_host, void *stream) {
     if (!h) return D2D_ERR_INVALID;
@@ -843,12 +927,7 @@ extern "C" int d2d_bind_host_io(d2d_handle *h, const double *actions_host, uint8
                                 uint8_t *done_host, void *stream) {
     if (!h) return D2D_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    if (h->pipe_inflight) {          // re-binding abandons the pre-launched step: it completes with action 0, then re-sync
-        CUDA_TRY(h, cudaMemsetAsync(h->stage_actions, 0, (size_t)h->B * 8, h->copy_stream));
-        CUDA_TRY(h, cudaStreamSynchronize(h->io_stream));
-        h->pipe_inflight = false;
-        h->pipe_seq += 1;
-    }
+    if (h->pipe_inflight) pipe_release(h);   // re-binding abandons the pre-launched step: it completes with action 0, then re-sync
     int rc = d2d_bind_host_mirror(h, local_map_host, yaw_host, done_host);     // synchronises the device first
     if (rc != D2D_OK) return rc;
     h->io_bound = false;
@@ -906,21 +985,7 @@ extern "C" int d2d_step_bound(d2d_handle *h) {
     return step_bound_sync(h);
 }
 
-extern "C" int d2d_step_pipelined(d2d_handle *h, int32_t prelaunch_next) {
-    if (!h) return D2D_ERR_INVALID;
-    if (!h->io_bound) { h->err = "d2d_step_pipelined before d2d_bind_host_io"; return D2D_ERR_STATE; }
-    // The gate lives in the fused NoMove warp kernel; everything else, and a step that must refresh a stale mirror, runs
-    // synchronously (same results, nothing pre-launched).
-    // ... and so do batches whose step lasts much longer than the launch + wake-up latency being hidden (~10 us): beyond
-    // ~16k envs the gated instantiation's bookkeeping costs more than the overlap returns (measured at 131072 envs: -6 %).
-    const bool can_pipe = h->cfg.planner == D2D_PLANNER_NOMOVE && h->cfg.envs_per_block <= 0 && !h->P.motion_rvo &&
-                          h->io_actions_dev != h->stage_actions && (long long)h->B * h->cfg.n_rays <= 16384ll * 50;
-    if (!can_pipe || (h->mir_stale && !h->pipe_inflight)) {
-        D2D_NO_PIPE(h);
-        return step_bound_sync(h);
-    }
-    if (!h->world_set) { h->err = "d2d_step before d2d_set_world"; return D2D_ERR_STATE; }
-    if (h->cfg.var_cam != 0.0 && !h->rng_set) { h->err = "var_cam != 0: d2d_set_rng must provide the np.random stream state"; return D2D_ERR_STATE; }
+static int step_pipelined_prelaunch(d2d_handle *h, int32_t prelaunch_next) {
     cudaStream_t st = h->io_stream;
     const double t_in = now_ns();
     const unsigned int seq = h->pipe_seq + 1;            // the step whose actions the caller has just written
@@ -944,10 +1009,11 @@ extern "C" int d2d_step_pipelined(d2d_handle *h, int32_t prelaunch_next) {
     }
     h->pipe_seq = seq;
     h->pipe_inflight = false;
+    h->pipe_mode = 0;
     if (rc == D2D_OK && prelaunch_next) {                 // the next step starts behind this one and runs up to its gate
         rc = launch_fused_warp<4, 7, false>(h, h->stage_actions, st);
         if (rc == D2D_OK && cudaEventRecord(h->pipe_ev[(seq + 1) & 1], st) != cudaSuccess) rc = D2D_ERR_CUDA;
-        if (rc == D2D_OK) h->pipe_inflight = true;
+        if (rc == D2D_OK) { h->pipe_inflight = true; h->pipe_mode = 1; }
     }
     h->P.gate = nullptr; h->P.gate_fault = nullptr;
     if (rc != D2D_OK && h->err.empty()) h->err = std::string("d2d_step_pipelined: ") + cudaGetErrorString(cudaGetLastError());
@@ -967,6 +1033,119 @@ extern "C" int d2d_step_pipelined(d2d_handle *h, int32_t prelaunch_next) {
     h->dbg_launch_ns += t_l - t_in; h->dbg_wait_ns += t_out - t_l; h->dbg_total_ns += t_out - t_in; h->dbg_n++;
     if (h->gate_host[16]) { h->err = "d2d_step_pipelined: a step kernel gave up waiting for its actions"; return D2D_ERR_STATE; }
     return D2D_OK;
+}
+
+// Resident form: ONE kernel (d2d_rollout_warp_kernel<GATED>) serves the whole run.  Per step the host copies the caller's
+// actions plus a stamp word ((sequence number << 1) | another step follows) into the device staging slots with one async
+// copy and polls a pinned word the kernel writes when every env has finished the step.  No launch and no stream completion
+// on the per-step path; the envs' working sets never leave the SMs between steps.
+static int step_pipelined_resident(d2d_handle *h, int32_t more) {
+    cudaStream_t st = h->io_stream;
+    const double t_in = now_ns();
+    const unsigned int seq = h->pipe_seq + 1;
+    const bool first = !h->pipe_inflight;
+    volatile unsigned long long *stamp_host = (volatile unsigned long long *)(h->gate_host + 8);   // byte 32 of the pinned block
+    if (first) {
+        // An SM that holds no env block runs the courier block: the kernel then pulls the actions out of the caller's pinned
+        // buffer by itself.  Otherwise (the batch fills every SM) the copy engine delivers them, one async copy per step.
+        const bool no_courier = getenv("D2D_NO_COURIER") != nullptr;    // test / measurement knob
+        h->pipe_courier = !no_courier && (h->B + D2D_RESIDENT_WPB - 1) / D2D_RESIDENT_WPB + 1 <= h->resident_blocks;
+        if (!h->pipe_count) CUDA_TRY(h, cudaMalloc((void **)&h->pipe_count, 64));
+        if (!h->pipe_courier && !h->pipe_pub) {
+            void *p = nullptr;
+            CUDA_TRY(h, cudaHostAlloc(&p, (size_t)(h->B + 1) * 8, cudaHostAllocDefault));
+            h->pipe_pub = (double *)p;
+        }
+    }
+    const unsigned long long stamp = ((unsigned long long)seq << 1) | (more ? 1ull : 0ull);
+    if (!h->pipe_courier) {
+        memcpy(h->pipe_pub, h->io_actions_host, (size_t)h->B * 8);
+        memcpy(h->pipe_pub + h->B, &stamp, 8);
+    }
+    int rc = D2D_OK;
+    if (first) {
+        // sentinels (and a stamp that matches no step) first; nothing may deliver actions before they are in place
+        d2d_fill_sentinel_kernel<<<(h->B + 1 + 255) / 256, 256, 0, st>>>((unsigned long long *)h->stage_actions, h->B + 1);
+        h->launches++;
+        if (cudaMemsetAsync(h->pipe_count, 0, 8, st) != cudaSuccess || cudaEventRecord(h->pipe_ev[2], st) != cudaSuccess ||
+            cudaStreamWaitEvent(h->copy_stream, h->pipe_ev[2], 0) != cudaSuccess)
+            rc = D2D_ERR_CUDA;
+    }
+    // publish (before the launch in the first-step case: blocking launches -- sanitizers -- must not starve the kernel)
+    if (h->pipe_courier) {
+        __atomic_store_n((unsigned long long *)stamp_host, stamp, __ATOMIC_RELEASE);    // the caller's action stores come first
+    } else if (rc == D2D_OK && cudaMemcpyAsync(h->stage_actions, h->pipe_pub, (size_t)(h->B + 1) * 8, cudaMemcpyHostToDevice,
+                                               h->copy_stream) != cudaSuccess) {
+        rc = D2D_ERR_CUDA;
+    }
+    if (first && rc == D2D_OK) {
+        h->P.gate = (unsigned long long *)h->stage_actions; h->P.gate_fault = h->gate_dev + 16;
+        h->P.gate_count = h->pipe_count; h->P.gate_done = h->gate_dev;
+        h->P.gate_src = h->pipe_courier ? (const unsigned long long *)h->io_actions_dev : nullptr;
+        h->P.gate_stamp_host = (const unsigned long long *)(h->gate_dev + 8);
+        rc = launch_rollout<D2D_RESIDENT_WPB, 1, false, true>(h, h->stage_actions, 0x7fffffff, 0, st, seq, h->pipe_courier ? 1 : 0);
+        h->P.gate = nullptr; h->P.gate_fault = nullptr; h->P.gate_count = nullptr; h->P.gate_done = nullptr;
+        h->P.gate_src = nullptr; h->P.gate_stamp_host = nullptr;
+        if (rc == D2D_OK) h->launches++;
+    }
+    if (rc != D2D_OK) {
+        if (h->err.empty()) h->err = std::string("d2d_step_pipelined: ") + cudaGetErrorString(cudaGetLastError());
+        return rc;
+    }
+    h->pipe_seq = seq;
+    h->pipe_inflight = more != 0;
+    h->pipe_mode = more ? 2 : 0;
+    const double t_l = now_ns();
+    // wait for THIS step: the kernel writes its sequence number once every env's stores are visible
+    long polls = 0;
+    while (h->gate_host[0] != seq) {
+        if (h->gate_host[16]) break;
+        if ((++polls & 0xfff) == 0) {
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q != cudaErrorNotReady && q != cudaSuccess) {
+                h->pipe_inflight = false; h->pipe_mode = 0;
+                h->err = std::string("d2d_step_pipelined: ") + cudaGetErrorString(q); return D2D_ERR_CUDA;
+            }
+            if (now_ns() - t_l > 20e9) {
+                h->pipe_inflight = false; h->pipe_mode = 0;
+                h->err = "d2d_step_pipelined: the resident step kernel did not complete the step within 20 s"; return D2D_ERR_STATE;
+            }
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    h->dbg_polls += polls;
+    if (!more || h->gate_host[16]) {                     // the run ends: the kernel writes the env records back and leaves
+        h->pipe_inflight = false; h->pipe_mode = 0;
+        CUDA_TRY(h, cudaStreamSynchronize(st));
+    }
+    const double t_out = now_ns();
+    h->dbg_launch_ns += t_l - t_in; h->dbg_wait_ns += t_out - t_l; h->dbg_total_ns += t_out - t_in; h->dbg_n++;
+    if (h->gate_host[16]) { h->gate_host[16] = 0; h->err = "d2d_step_pipelined: the step kernel gave up waiting for its actions"; return D2D_ERR_STATE; }
+    return D2D_OK;
+}
+
+extern "C" int d2d_step_pipelined(d2d_handle *h, int32_t prelaunch_next) {
+    if (!h) return D2D_ERR_INVALID;
+    if (!h->io_bound) { h->err = "d2d_step_pipelined before d2d_bind_host_io"; return D2D_ERR_STATE; }
+    // The gate lives in the NoMove warp kernels; everything else, and a step that must refresh a stale mirror, runs
+    // synchronously (same results, nothing pre-launched).
+    // ... and so do batches whose step lasts much longer than the launch + wake-up latency being hidden (~10 us): beyond
+    // ~16k envs the gated instantiation's bookkeeping costs more than the overlap returns (measured at 131072 envs: -6 %).
+    const bool can_pipe = h->cfg.planner == D2D_PLANNER_NOMOVE && h->cfg.envs_per_block <= 0 && !h->P.motion_rvo &&
+                          h->io_actions_dev != h->stage_actions && (long long)h->B * h->cfg.n_rays <= 16384ll * 50;
+    if (!can_pipe || (h->mir_stale && !h->pipe_inflight)) {
+        D2D_NO_PIPE(h);
+        return step_bound_sync(h);
+    }
+    if (!h->world_set) { h->err = "d2d_step before d2d_set_world"; return D2D_ERR_STATE; }
+    if (h->cfg.var_cam != 0.0 && !h->rng_set) { h->err = "var_cam != 0: d2d_set_rng must provide the np.random stream state"; return D2D_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    // a batch that fits the GPU in one wave is served by the resident kernel; a larger one by one pre-launched kernel per step
+    const bool no_resident = getenv("D2D_NO_RESIDENT") != nullptr;      // test / measurement knob
+    const int mode = h->pipe_inflight ? h->pipe_mode : ((!no_resident && h->B <= resident_capacity(h)) ? 2 : 1);
+    return mode == 2 ? step_pipelined_resident(h, prelaunch_next) : step_pipelined_prelaunch(h, prelaunch_next);
 }
 
 extern "C" int d2d_stats(d2d_handle *h, int64_t *out_host, int32_t reset, void *stream) {

@@ -256,6 +256,21 @@ class Drone2DVecEnv(object):
         self._check(self._lib.d2d_step(self._h, C.c_void_p(a.data_ptr()), self._stream()), "d2d_step")
         return self._obs(), self.reward, self.buffer("done"), self.info
 
+    def rollout(self, actions):
+        """K consecutive steps in ONE launch (d2d_rollout): `actions` is a float64 CUDA tensor [K, B] (row t = the actions of
+        step t) or [B] with `steps` implied 1.  Every warp walks its env through the K steps with the env's state resident on
+        chip; all buffers and statistics end up bit-identical to K `step` calls, the per-step outputs hold the last step's
+        values.  NoMove planner / CVM profile only (other configurations raise).  Returns what the last `step` would."""
+        a = actions.to(device=self.device, dtype=torch.float64)
+        if a.dim() == 1:
+            a = a.reshape(1, -1)
+        a = a.reshape(a.shape[0], -1).contiguous()
+        if a.shape[1] != self.num_envs:
+            raise ValueError("expected [K, %d] actions, got %s" % (self.num_envs, tuple(a.shape)))
+        self._check(self._lib.d2d_rollout(self._h, C.c_void_p(a.data_ptr()), int(a.shape[0]), int(a.shape[1]), self._stream()),
+                    "d2d_rollout")
+        return self._obs(), self.reward, self.buffer("done"), self.info
+
     def step_host(self, actions_host, local_map_host=None, yaw_host=None, done_host=None):
         """Same step through HOST buffers (pinned torch tensors or numpy arrays): actions to the device (pinned memory is
         read by the kernels in place), step, observation back on the host.  Output buffers that are the bound mirror

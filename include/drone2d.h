@@ -181,6 +181,16 @@ int d2d_reset(d2d_handle *h, const uint8_t *mask_dev, void *stream);
  * Results land in the buffers "local_map", "yaw_angle", "done", "collision_flag", ... (d2d_get_buffer). */
 int d2d_step(d2d_handle *h, const double *actions_dev, void *stream);
 
+/* K consecutive steps in ONE launch (replaces the `for t in range(K): env.step(a[t])` loop of experiment.py:65-70 when the
+ * actions of the K steps are known up front -- scripted / constant gaze -- or were produced on the device).
+ * actions_dev: DEVICE f64, action of env e at step t = actions_dev[t * action_stride + e] (action_stride >= num_envs, or 0:
+ * the same [num_envs] vector every step).  Every warp walks ITS env through the K steps with the env's working set resident
+ * in shared memory (fetched from HBM once, not once per step) and never waits for the other envs between steps.  All buffers
+ * and statistics end up bit-identical to K d2d_step calls; the per-step outputs ("done", "local_map", ...) hold the LAST
+ * step's values.  NoMove planner, CVM motion profile, default warp kernels (envs_per_block <= 0) only: everything else
+ * returns D2D_ERR_INVALID (those steps consist of several dependent launches; call d2d_step). */
+int d2d_rollout(d2d_handle *h, const double *actions_dev, int32_t num_steps, int64_t action_stride, void *stream);
+
 /* Same step with HOST buffers (the call an FFI user makes): gets the actions to the device (pinned memory is read by
  * the kernels directly over PCIe, pageable memory is copied first), steps, copies the observation back and
  * synchronises.  Any output pointer may be NULL.  actions_host == NULL: the actions are taken from the device buffer

@@ -23,7 +23,10 @@ def test_bench_prints_contract_line():
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
         assert k in d, k
     assert d["metric"] == "env-steps/sec" and d["steps"] == 12 and d["n_gpus"] == 1 and d["dtype"] == "f64"
-    assert d["gpu_launches"] == 12 and d["value"] > 0 and d["vs_baseline"] is None and d["scaling"] == "weak"
+    # NoMove + scripted gaze: the K steps of a replica are ONE d2d_rollout launch; the per-step-launch figure rides along
+    assert d["gpu_launches"] == 1 and d["value"] > 0 and d["vs_baseline"] is None and d["scaling"] == "weak"
+    ssl = d["single_step_launches"]
+    assert ssl["gpu_launches"] == 12 and ssl["value"] > 0 and abs(ssl["value"] - 512 / (ssl["ms_per_step"] * 1e-3)) <= 1e-6 * ssl["value"]
     assert abs(d["value"] - 512 / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
     assert d["method"]["replicas"] >= 2 and "workload" in d["config"] and "l2" in d["config"]   # a small batch needs replicas to stay L2-cold
     assert d["method"]["graph_replays"] >= 7 and d["method"]["timed_region_ms_this_rank"] >= 50.0

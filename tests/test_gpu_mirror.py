@@ -128,10 +128,16 @@ def test_step_host_action_sources_agree(planner):
         e.close()
 
 
-@pytest.mark.parametrize("planner,B,steps,pipelined", [("NoMove", 37, 300, False), ("NoMove", 37, 300, True),
-                                                        ("NoMove", 4096, 60, True), ("Primitive", 23, 120, False),
-                                                        ("Primitive", 23, 60, True)])
-def test_bound_host_io_equals_step_host(planner, B, steps, pipelined):
+# knob: which transport d2d_step_pipelined uses for a NoMove batch.  Default: the resident kernel with a courier block (one SM is
+# free: B <= 4116); D2D_NO_COURIER: resident kernel fed by the copy engine (also what a batch that fills all 148 SMs gets:
+# B = 4144); D2D_NO_RESIDENT: one pre-launched kernel per step (also what a batch above one wave gets: B = 4200).
+@pytest.mark.parametrize("planner,B,steps,pipelined,knob", [
+    ("NoMove", 37, 300, False, None), ("NoMove", 37, 300, True, None), ("NoMove", 4096, 60, True, None),
+    ("NoMove", 37, 120, True, "D2D_NO_COURIER"), ("NoMove", 4096, 40, True, "D2D_NO_COURIER"),
+    ("NoMove", 37, 120, True, "D2D_NO_RESIDENT"), ("NoMove", 4096, 40, True, "D2D_NO_RESIDENT"),
+    ("NoMove", 4144, 40, True, None), ("NoMove", 4200, 40, True, None),
+    ("Primitive", 23, 120, False, None), ("Primitive", 23, 60, True, None)])
+def test_bound_host_io_equals_step_host(planner, B, steps, pipelined, knob, monkeypatch):
     """d2d_bind_host_io + d2d_step_bound / d2d_step_pipelined against d2d_step_host on a twin env: host observation buffers
     and device state identical after every step, across auto-resets, an eager reset and a pose write (which end the pipelined
     run and force the synchronising refresh path once).  Pipelined: when the call returns, the next step's kernel is already
@@ -140,6 +146,8 @@ def test_bound_host_io_equals_step_host(planner, B, steps, pipelined):
     import time
     from gym_drone2d_activeperception_b200.params import Params
     from gym_drone2d_activeperception_b200 import generate_worlds
+    if knob:
+        monkeypatch.setenv(knob, "1")
     p = Params(debug=False, planner=planner, map_id=7, agent_number=10, agent_radius=15, agent_max_speed=40)
     worlds = generate_worlds(p, 7 + np.arange(min(B, 256)))
     worlds = {k: np.concatenate([v] * (-(-B // len(v))))[:B] for k, v in worlds.items()}
