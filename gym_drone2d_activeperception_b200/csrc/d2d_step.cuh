@@ -1146,6 +1146,29 @@ __device__ D2D_COLD void d2d_obs_env_warp(const DevP &P, const uint8_t *bel, int
     if (out_m && lane == 0) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)D2D_LOCAL_CELLS);
 }
 
+// NoMove: an env that is re-initialised keeps its window (same pose, new episode), so the observation of its first step is
+// the ZERO window plus the cells that step marks: clear the slice with coalesced stores and let the rays patch it in place,
+// instead of gathering 1089 bytes through the funnel-shift path after the step (~1000 warp-instructions on what are already
+// the slowest warps of a step: fresh envs march every ray through unexplored cells).
+__device__ __forceinline__ void d2d_obs_clear_warp(const DevP &P, int e, int lane, bool to_mirror) {
+    uint8_t *out = P.local_map + (size_t)e * D2D_LOCAL_CELLS;
+    uint8_t *out_m = (to_mirror && P.lm_mirror) ? P.lm_mirror + (size_t)e * D2D_LOCAL_CELLS : nullptr;
+    const int head = (4 - (e & 3)) & 3;
+    const int nwords = (D2D_LOCAL_CELLS - head) >> 2;
+    const int tail0 = head + 4 * nwords;
+    if (lane < head) { out[lane] = 0; if (out_m) out_m[lane] = 0; }
+    if (lane < D2D_LOCAL_CELLS - tail0) { out[tail0 + lane] = 0; if (out_m) out_m[tail0 + lane] = 0; }
+    uint32_t *ow = (uint32_t *)(out + head);
+#pragma unroll 3
+    for (int j = lane; j < nwords; j += 32) ow[j] = 0u;
+    if (out_m) {
+        uint32_t *om = (uint32_t *)(out_m + head);
+#pragma unroll 3
+        for (int j = lane; j < nwords; j += 32) om[j] = 0u;
+        if (lane == 0) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)D2D_LOCAL_CELLS);
+    }
+}
+
 // env e's freshly rewritten observation slice, device tensor -> host mirror (resident gated kernel: the rewrite itself runs
 // before the gate, only this copy behind it).  Reads bypass L1: the slice was written by other lanes of this warp.
 __device__ __forceinline__ void d2d_obs_mirror_copy_warp(const DevP &P, int e, int lane) {
@@ -1243,7 +1266,10 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     // NoMove: the drone cell cannot change during the step, so if the observation tensor already holds this window it
     // is patched in place by the rays (only cells whose value changes) instead of being rewritten
     __syncwarp();
-    const bool patch = !s.reset && s.obs_ix == s.ix && s.obs_iy == s.iy;
+    const bool same_win = s.obs_ix == s.ix && s.obs_iy == s.iy;
+    const bool refill = !GATED && s.reset && same_win;   // new episode, same window: clear + patch (see d2d_obs_clear_warp)
+    if (refill) d2d_obs_clear_warp(P, e, lane, true);
+    const bool patch = (!s.reset || refill) && same_win;
     const bool mirror = GATED && P.lm_mirror != nullptr;
     RayOut ro;
     ro.bel_s = c.belief; ro.e = e; ro.patch = patch ? 1 : 0;
@@ -1451,11 +1477,16 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_rollout_warp_kernel(const 
         if (t == 0 && pf_act && !s.reset) d2d_prefetch_tracker(P, ga);
         if (lane == 0) d2d_leader_begin(P, s);
         __syncwarp();
-        const bool patch = !s.reset && s.obs_ix == s.ix && s.obs_iy == s.iy;
+        // same window as the observation tensor holds: patched in place by the rays; an env that starts a new episode there
+        // has its slice cleared first (d2d_obs_clear_warp) -- GATED: on the device only, the host mirror gets the finished slice
+        // behind the gate
+        const bool patch = s.obs_ix == s.ix && s.obs_iy == s.iy;
+        const bool refill = s.reset && patch;
+        if (refill) d2d_obs_clear_warp(P, e, lane, !GATED);
         RayOut ro;
         ro.bel_s = c.belief; ro.e = e; ro.patch = patch ? 1 : 0;
         ro.wi = s.ix - 16; ro.wj = s.iy - 16;
-        ro.chg = (mirror && patch) ? chg : nullptr; ro.nchg = nchg; ro.defer_mirror = GATED ? 1 : 0;
+        ro.chg = (mirror && patch && !refill) ? chg : nullptr; ro.nchg = nchg; ro.defer_mirror = GATED ? 1 : 0;
         if (t == 0) {
             d2d_mbar_wait(c.mbar, 0);
             border_ok = d2d_border_intact(c.gt, lane);               // the ground truth never changes
@@ -1485,7 +1516,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_rollout_warp_kernel(const 
                 d2d_leader_flags(P, s, c.gt, e, shit, false);
             }
             __syncwarp();
-            n_changed = mirror ? *nchg : 0;
+            n_changed = (mirror && !refill) ? *nchg : 0;
             rewrite = !patch || s.ix != s.obs_ix || s.iy != s.obs_iy || (mirror && n_changed > D2D_CHG_CAP);
             __syncwarp();
             if (rewrite && lane == 0) { s.obs_ix = s.ix; s.obs_iy = s.iy; }
@@ -1521,7 +1552,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_rollout_warp_kernel(const 
             D2D_PROF(9);
             // behind the gate: this step's observation bytes go out to the host mirror
             if (mirror) {
-                if (rewrite) {
+                if (rewrite || refill) {
                     __syncwarp();
                     d2d_obs_mirror_copy_warp(P, e, lane);
                 } else if (n_changed > 0) {

@@ -133,9 +133,9 @@ def test_step_host_action_sources_agree(planner):
 # B = 4144); D2D_NO_RESIDENT: one pre-launched kernel per step (also what a batch above one wave gets: B = 4200).
 @pytest.mark.parametrize("planner,B,steps,pipelined,knob", [
     ("NoMove", 37, 300, False, None), ("NoMove", 37, 300, True, None), ("NoMove", 4096, 60, True, None),
-    ("NoMove", 37, 120, True, "D2D_NO_COURIER"), ("NoMove", 4096, 40, True, "D2D_NO_COURIER"),
-    ("NoMove", 37, 120, True, "D2D_NO_RESIDENT"), ("NoMove", 4096, 40, True, "D2D_NO_RESIDENT"),
-    ("NoMove", 4144, 40, True, None), ("NoMove", 4200, 40, True, None),
+    ("NoMove", 37, 120, True, "D2D_NO_COURIER"), ("NoMove", 4096, 48, True, "D2D_NO_COURIER"),
+    ("NoMove", 37, 120, True, "D2D_NO_RESIDENT"), ("NoMove", 4096, 48, True, "D2D_NO_RESIDENT"),
+    ("NoMove", 4144, 48, True, None), ("NoMove", 4200, 48, True, None),     # 48: no sync-refresh step lands on a t % 7 == 0 probe
     ("Primitive", 23, 120, False, None), ("Primitive", 23, 60, True, None)])
 def test_bound_host_io_equals_step_host(planner, B, steps, pipelined, knob, monkeypatch):
     """d2d_bind_host_io + d2d_step_bound / d2d_step_pipelined against d2d_step_host on a twin env: host observation buffers
