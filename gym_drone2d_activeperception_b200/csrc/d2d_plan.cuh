@@ -1061,6 +1061,12 @@ __device__ __forceinline__ void d2d_ox_window(const DevP &P, double dx, int &lo,
 #define D2D_OX_SPAN (D2D_OX_ROWS * D2D_GRID + 2 * 128)   // materialised flattened range, extended to whole leaves
 #define D2D_OX_WORDS ((D2D_OX_SPAN + 31) / 32)
 #define D2D_OX_THREADS 128
+// candidate yaw rates the kernel holds per env (Oxford.v_yaw_space has 6, yaw_planner.py:65); sized so that the kernel's static
+// shared memory (21.5 KB) and registers (48) let 10 blocks = 40 warps share an SM instead of 8 = 32
+#define D2D_OX_MAX_YAW 8
+#ifndef D2D_OX_MINB
+#define D2D_OX_MINB 10
+#endif
 
 // last_time_observed of a cell after policy call n (yaw_planner.py:95-97): 0 if visible at call n, else the += dt
 // sequence continued from 0.0 (last seen at call s) or from the initial 5.0 (never seen), read from the exact table
@@ -1094,13 +1100,13 @@ __global__ void d2d_oxford_export_kernel(const DevP P, double *__restrict__ out)
 //     residue class), combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail; leaves outside the range are exactly
 //     +0.0 (x + 0.0 == x).
 //  E. the recursion's combine as a level-parallel tree (same operand pairs), then the strict-< argmax.
-__global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P, const OxProgram *__restrict__ prog,
+__global__ void __launch_bounds__(D2D_OX_THREADS, D2D_OX_MINB) d2d_oxford_kernel(const DevP P, const OxProgram *__restrict__ prog,
                                                                     double *__restrict__ actions_out) {
     __shared__ double reward[D2D_OX_SPAN];
-    __shared__ uint32_t vmask[D2D_MAX_YAW][D2D_OX_WORDS];
+    __shared__ uint32_t vmask[D2D_OX_MAX_YAW][D2D_OX_WORDS];
     __shared__ int swep_w[D2D_OX_SPAN];                 // largest waypoint index per cell of the range (-1: none)
-    __shared__ double leaf[D2D_MAX_YAW][D2D_OX_MAX_LEAVES];
-    __shared__ double cs_s[D2D_MAX_YAW + 1], sn_s[D2D_MAX_YAW + 1];
+    __shared__ double leaf[D2D_OX_MAX_YAW][D2D_OX_MAX_LEAVES];
+    __shared__ double cs_s[D2D_OX_MAX_YAW + 1], sn_s[D2D_OX_MAX_YAW + 1];
     __shared__ double wpt[2];
     __shared__ int geo[12];                             // r0 r1 q0 q1 lo hi l0 l1 i0 i1 j0 j1
     const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5;
@@ -1149,7 +1155,7 @@ __global__ void __launch_bounds__(D2D_OX_THREADS) d2d_oxford_kernel(const DevP P
         }
     } else {
 #pragma unroll 1
-        for (int o = tid - 64; o < D2D_MAX_YAW * D2D_OX_WORDS; o += D2D_OX_THREADS - 64) (&vmask[0][0])[o] = 0u;
+        for (int o = tid - 64; o < D2D_OX_MAX_YAW * D2D_OX_WORDS; o += D2D_OX_THREADS - 64) (&vmask[0][0])[o] = 0u;
         if (fresh) {
             // first call of a new episode: nothing has been seen yet
 #pragma unroll 1

@@ -261,6 +261,9 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
         cfg->n_owl_u < 0 || cfg->n_owl_u > D2D_MAX_OWL_U || cfg->owl_repeat < 0) {
         g_create_err = "table size out of range"; return D2D_ERR_INVALID;
     }
+    if ((cfg->oxford & D2D_POLICY_OXFORD) && cfg->n_yaw > D2D_OX_MAX_YAW) {
+        g_create_err = "Oxford policy: at most 8 candidate yaw rates (the reference has 6, yaw_planner.py:65)"; return D2D_ERR_INVALID;
+    }
     if (cfg->var_cam != 0.0 && cfg->envs_per_block > 0) {
         g_create_err = "var_cam != 0 (noisy measurements) is only implemented on the default warp-per-env kernels (envs_per_block = 0)";
         return D2D_ERR_INVALID;

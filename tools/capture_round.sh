@@ -15,7 +15,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:d2d_step_fused_warp_kernel -s 2700 -c 1 -f -o $O/${T}_fused_cfg2 python bench.py --steps 20 --warmup 5 --burn-in 200 --no-cpu-baseline --no-workloads > $O/${T}_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:d2d_oxford_kernel -s 150 -c 1 -f -o $O/${T}_oxford_cfg4 python bench.py --config 4 --steps 5 --warmup 3 --burn-in 150 --no-cpu-baseline > $O/${T}_ncu4.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:d2d_step_prim_warp_kernel -s 150 -c 1 -f -o $O/${T}_prim_cfg4 python bench.py --config 4 --steps 5 --warmup 3 --burn-in 150 --no-cpu-baseline > $O/${T}_ncu5.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:d2d_rollout_warp_kernel -s 20 -c 1 -f -o $O/${T}_rollout_cfg2 python bench.py --steps 200 --warmup 5 --burn-in 200 --no-cpu-baseline --no-workloads > $O/${T}_ncu6.log 2>&1
 python tools/warp_prof.py --config 2 > $O/${T}_warp_timeline_cfg2.txt 2>&1
+D2D_PIPE_DEBUG=1 python tools/resident_timeline.py > $O/${T}_resident_timeline_cfg2.txt 2>&1
+(for v in 0 1; do echo "D2D_ROLLOUT_VARIANT=$v (0: 28-warp blocks + one block barrier per step, 1: 4-warp blocks, no barrier)"; D2D_ROLLOUT_VARIANT=$v python tools/rollout_bench.py --config 2 --chunks 16,64,200; done) > $O/${T}_rollout_variants_cfg2.txt 2>&1
+python tools/rollout_bench.py --config 5 --burn-in 300 --chunks 64 > $O/${T}_rollout_cfg5.txt 2>&1
 timeout 300 compute-sanitizer --tool memcheck python tools/sanitize_run.py > $O/${T}_sanitizer_memcheck.txt 2>&1
 timeout 300 compute-sanitizer --tool racecheck python tools/sanitize_run.py > $O/${T}_sanitizer_racecheck.txt 2>&1
 for f in $O/${T}_bench_*.json; do python - "$f" <<'PY'

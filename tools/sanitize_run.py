@@ -1,7 +1,7 @@
 """Small workload for compute-sanitizer (GPU box):  compute-sanitizer --tool memcheck python tools/sanitize_run.py
 Steps a NoMove batch (fused warp kernel, both march variants: seed 8 has a broken border ring), a Primitive + Oxford batch and
-an RVO batch, a Primitive + Owl batch, a Jerk_Primitive batch and a pipelined NoMove run (d2d_step_pipelined: gated kernel,
-deferred mirror stores) for a few dozen steps with auto-reset, host buffers bound, and prints the episode statistics."""
+an RVO batch, a Primitive + Owl batch, a Jerk_Primitive batch, a pipelined NoMove run (d2d_step_pipelined: resident gated kernel
+with its courier block, deferred mirror stores; one-step runs, since sanitizers make launches blocking) and d2d_rollout for a few dozen steps with auto-reset, host buffers bound, and prints the episode statistics."""
 import os
 import sys
 
@@ -60,6 +60,10 @@ def main():
         env.step_pipelined(prelaunch_next=False)     # sanitizers make launches blocking: a pre-launched kernel would starve
     env.bind_host_io(None, None, None, None)
     print("NoMove pipelined", env.stats()[:8])
+    # d2d_rollout: 12 steps in one launch (28-warp blocks, one block barrier per step), across auto-resets
+    env.rollout(table[torch.randint(0, 6, (12, B), generator=g)].cuda())
+    env.rollout(table[torch.randint(0, 6, (12, B), generator=g)].cuda())
+    print("NoMove rollout", env.stats()[:8])
     env.close()
 
 
