@@ -1438,8 +1438,8 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_rollout_warp_kernel(const 
     // GATED: block-level publication area behind the warp slices: arrival counter, this step's yaw / done of the block's envs
     unsigned char *blk = smem + (size_t)WPB * d2d_warp_slice_bytes(P.NP, P.HW, GATED ? D2D_FUSED_WARP_EXTRA : 0);
     int *blk_cnt = (int *)blk;
-    float *blk_yaw = (float *)(blk + 16);
-    uint8_t *blk_done = blk + 16 + WPB * 4;
+    unsigned int *blk_yaw = (unsigned int *)(blk + 16);             // float bits; handed over with shared-memory atomics (below)
+    unsigned int *blk_done = (unsigned int *)(blk + 16 + WPB * 4);
     const int blk_envs = min(WPB, P.B - (int)blockIdx.x * WPB);
     EnvS &s = c.S[0];
     const size_t ga = (size_t)e * P.NP + lane;
@@ -1594,7 +1594,9 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_rollout_warp_kernel(const 
             // per warp (4096 per step, each waiting for its PCIe writes) 15 us, one per block 10 us, one per step ~1 us.
             int last = 0;
             if (lane == 0) {
-                blk_yaw[wid] = (float)s.yaw; blk_done[wid] = (uint8_t)s.done_now;
+                // (atomic accesses on both sides of the hand-over: plain ones are ordered just as well by the fences, but
+                // compute-sanitizer's racecheck only models barriers and reports a fence + counter hand-over as a hazard)
+                atomicExch(&blk_yaw[wid], __float_as_uint((float)s.yaw)); atomicExch(&blk_done[wid], (unsigned int)s.done_now);
                 __threadfence_block();
                 last = atomicAdd(blk_cnt, 1) == blk_envs - 1 ? 1 : 0;
             }
@@ -1603,8 +1605,8 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_rollout_warp_kernel(const 
                 __threadfence_block();
                 const int e0 = (int)blockIdx.x * WPB;
                 if (lane < blk_envs) {
-                    if (P.yaw_mirror) P.yaw_mirror[e0 + lane] = blk_yaw[lane];
-                    if (P.done_mirror) P.done_mirror[e0 + lane] = blk_done[lane];
+                    if (P.yaw_mirror) P.yaw_mirror[e0 + lane] = __uint_as_float(atomicOr(&blk_yaw[lane], 0u));
+                    if (P.done_mirror) P.done_mirror[e0 + lane] = (uint8_t)atomicOr(&blk_done[lane], 0u);
                 }
                 __syncwarp();
                 if (lane == 0) {

@@ -223,20 +223,28 @@ int d2d_bind_host_io(d2d_handle *h, const double *actions_host, uint8_t *local_m
 int d2d_step_bound(d2d_handle *h);
 
 /* The same step, pipelined.  In Drone2DEnv2.step the action only turns the yaw at the very END of the step (step_yaw,
- * utils.py:741-743, called at drone_v2.py:214); agent motion, ray casting, trackers and collision tests never see it.  With
- * prelaunch_next != 0 the kernel of the FOLLOWING step is therefore launched before this call returns: it runs right behind
- * the current step, does everything that does not depend on its action while the caller is still looking at this step's
- * observation and choosing the next actions, and waits at a gate just before its yaw update.  The next
- * d2d_step_pipelined call publishes the actions (the caller has written them into the bound pinned buffer) and opens the
- * gate.  Host-mirror stores of a step are issued only behind its gate, so the observation buffers stay valid until the
- * next call, as with d2d_step_host.  Results are identical to d2d_step_bound; launch latency and completion wake-up leave
- * the critical path.  Contract: prelaunch_next promises one more d2d_step_pipelined call; until that call (pass 0 on the
- * last step of a run) every other entry point of this handle returns D2D_ERR_STATE.  A pre-launched kernel whose actions
- * never arrive gives up after ~2 s and the next call reports it.  Planners other than NoMove, the RVO profile, actions
- * taken from "actions_staging" and batches above ~16k envs (whose step dwarfs the latency being hidden) run synchronously
- * (same results, nothing pre-launched).  Meant for HOST policies: a pre-launched kernel holds the GPU until its actions
- * arrive, so work queued on the same GPU in between (a policy network) would wait for it -- such callers use d2d_step with
- * device actions, which needs no host round trip in the first place. */
+ * utils.py:741-743, called at drone_v2.py:214); agent motion, ray casting, trackers, collision tests and the done logic
+ * never see it.  prelaunch_next != 0 promises that another d2d_step_pipelined call follows; the library then starts the
+ * FOLLOWING step before this call returns: everything of it that does not depend on its action runs while the caller is
+ * still looking at this step's observation and choosing the next actions, and stops at a gate just before the yaw update.
+ * The next d2d_step_pipelined call publishes the actions (the caller has written them into the bound pinned buffer) and
+ * opens the gate.  Host-mirror stores of a step are issued only behind its gate, so the observation buffers stay valid
+ * until the next call, as with d2d_step_host.  Results are identical to d2d_step_bound.
+ *   Batches of at most one wave of warps (4116 envs on a 148-SM B200): ONE resident kernel serves the whole run of calls.
+ *     Each env's working set stays in shared memory between steps; a courier block on the one SM that holds no env polls a
+ *     stamp word in pinned host memory and pulls the step's actions out of the bound buffer itself, so the host's part of a
+ *     step is one store (no launch, no copy, no stream synchronisation); completion of a step is a pinned word the last
+ *     block writes after the step's single system-scope fence, and the call polls it.  4117 .. 4144 envs fill every SM: same
+ *     kernel, actions delivered by one async copy per step instead of the courier.
+ *   Larger batches (up to ~16k envs): one kernel per step, launched behind the current one (the round-1 design).
+ *   Planners other than NoMove, the RVO profile, actions taken from "actions_staging" and batches above ~16k envs (whose
+ *     step dwarfs the latency being hidden) run synchronously (same results, nothing started ahead).
+ * Contract: until the call that passes prelaunch_next = 0 (the last step of a run) every other entry point of this handle
+ * returns D2D_ERR_STATE, and the kernel that waits for the next actions OWNS the GPU: work queued on the same device in
+ * between (a policy network, a cudaDeviceSynchronize) waits for it.  This entry point is meant for HOST policies; a policy
+ * on the GPU calls d2d_step / d2d_rollout with device actions, which needs no host round trip in the first place.  A
+ * kernel whose actions never arrive gives up after ~2 s and the next call reports it; d2d_destroy and re-binding release
+ * a waiting kernel (it completes its step with action 0). */
 int d2d_step_pipelined(d2d_handle *h, int32_t prelaunch_next);
 
 /* Replaces Oxford.plan(env.info) (yaw_planner.py:81-127) for all envs: writes the chosen action per env to

@@ -43,6 +43,12 @@ with torch.cuda.stream(side):
         print("   gate pass spread: med %.1f p90 %.1f max %.1f us after the first | publication (post-gate work done -> end): med %.1f max %.1f | post-gate work med %.1f max %.1f"
               % (np.median(p[:, 9] - g0) / 1e3, np.percentile(p[:, 9] - g0, 90) / 1e3, (p[:, 9].max() - g0) / 1e3, np.median(pub), pub.max(),
                  np.median(p[:, 4] - p[:, 9]) / 1e3, (p[:, 4] - p[:, 9]).max() / 1e3))
+        steps_now = env.buffer("steps").cpu().numpy(); hits = (env.buffer("hit").cpu().numpy() > 0).sum(1)
+        act = env.buffer("tracker_active").cpu().numpy().sum(1)
+        order = np.argsort(-pre)[:12]
+        print("   slowest action-independent parts: " + "; ".join(
+            "env %d pre %.1f (head %.1f rays %.1f tail %.1f) steps=%d hits=%d trk=%d" % (
+                i, pre[i], (p[i, 1] - p[i, 0]) / 1e3, rays[i], (p[i, 8] - p[i, 2]) / 1e3, steps_now[i], hits[i], act[i]) for i in order))
         print("%d steps: %.1f us per call | last step, per warp (us): start spread %.1f | pre-gate med %.1f p90 %.1f max %.1f (rays med %.1f) | "
               "gate wait med %.1f min %.1f max %.1f | gate -> end med %.1f max %.1f | first start -> last gate arrival %.1f, -> first gate open %.1f, -> last end %.1f"
               % (n, dt, (p[:, 0].max() - k0) / 1e3, np.median(pre), np.percentile(pre, 90), pre.max(), np.median(rays),

@@ -17,7 +17,8 @@ def main():
     from gym_drone2d_activeperception_b200.vec_env import Drone2DVecEnv
     table = torch.as_tensor(np.arange(-80, 80, 80 / 3) / 80)
     g = torch.Generator().manual_seed(0)
-    for name, kw, B, steps, ox in [("NoMove", dict(planner="NoMove", map_id=1), 40, 40, False),
+    only_resident = "--resident-only" in sys.argv       # just the round-2 resident kernels (short racecheck reports)
+    for name, kw, B, steps, ox in [] if only_resident else [("NoMove", dict(planner="NoMove", map_id=1), 40, 40, False),
                                    ("Primitive+Oxford", dict(planner="Primitive", gaze_method="Oxford", map_id=1), 24, 40, True),
                                    ("RVO", dict(planner="NoMove", motion_profile="RVO", map_id=3), 8, 10, False)]:
         p = Params(debug=False, agent_number=10, agent_radius=15, agent_max_speed=20, **kw)
@@ -35,18 +36,8 @@ def main():
         print(name, env.stats()[:8])
         env.close()
     # round 2: Owl policy, Jerk_Primitive planner, pipelined bound stepping
-    p = Params(debug=False, agent_number=10, agent_radius=15, agent_max_speed=20, planner="Primitive", gaze_method="Owl", map_id=1)
-    env = Drone2DVecEnv(p, 16, seeds=1 + np.arange(16), device="cuda:0", auto_reset=True)
-    for t in range(40):
-        env.step(env.plan_gaze("Owl"))
-    print("Primitive+Owl", env.stats()[:8])
-    env.close()
-    p = Params(debug=False, agent_number=10, agent_radius=15, agent_max_speed=20, planner="Jerk_Primitive", gaze_method="LookAhead", map_id=1)
-    env = Drone2DVecEnv(p, 16, seeds=1 + np.arange(16), device="cuda:0", auto_reset=True)
-    for t in range(40):
-        env.step(env.plan_gaze("LookAhead"))
-    print("Jerk_Primitive+LookAhead", env.stats()[:8])
-    env.close()
+    if not only_resident:
+        run_owl_jerk(Params, Drone2DVecEnv)
     B = 40
     p = Params(debug=False, agent_number=10, agent_radius=15, agent_max_speed=20, planner="NoMove", map_id=1)
     env = Drone2DVecEnv(p, B, seeds=1 + np.arange(B), device="cuda:0", auto_reset=True)
@@ -64,6 +55,22 @@ def main():
     env.rollout(table[torch.randint(0, 6, (12, B), generator=g)].cuda())
     env.rollout(table[torch.randint(0, 6, (12, B), generator=g)].cuda())
     print("NoMove rollout", env.stats()[:8])
+    env.close()
+
+
+def run_owl_jerk(Params, Drone2DVecEnv):
+    import torch
+    p = Params(debug=False, agent_number=10, agent_radius=15, agent_max_speed=20, planner="Primitive", gaze_method="Owl", map_id=1)
+    env = Drone2DVecEnv(p, 16, seeds=1 + np.arange(16), device="cuda:0", auto_reset=True)
+    for t in range(40):
+        env.step(env.plan_gaze("Owl"))
+    print("Primitive+Owl", env.stats()[:8])
+    env.close()
+    p = Params(debug=False, agent_number=10, agent_radius=15, agent_max_speed=20, planner="Jerk_Primitive", gaze_method="LookAhead", map_id=1)
+    env = Drone2DVecEnv(p, 16, seeds=1 + np.arange(16), device="cuda:0", auto_reset=True)
+    for t in range(40):
+        env.step(env.plan_gaze("LookAhead"))
+    print("Jerk_Primitive+LookAhead", env.stats()[:8])
     env.close()
 
 
