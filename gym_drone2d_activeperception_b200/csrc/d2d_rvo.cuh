@@ -6,20 +6,33 @@
 // `avel_next`; the step kernels consume them in Agent.step and publish them as the current velocity.
 // Trigonometry: cos / sin of the 32 constant candidate angles come from a host (glibc) table; atan2 / asin / sin / cos of
 // run-time values are CUDA's double-precision functions (<= 2 ulp, not glibc's bits): continuous agent state is held
-// to 1e-9, not bit-exact, under this profile.
+// to 1e-9, not bit-exact, under this profile.  The N * 160 * (N - 1) cone tests of a step compare angles through cross
+// products (d2d_rvo_inside_fast) and evaluate atan2 only where that is not certain.
 #pragma once
 #include "d2d_state.cuh"
 #include "d2d_math.cuh"
 
-#define D2D_RVO_WARPS 4
+#define D2D_RVO_MAX_WARPS 8
+// warps per block (= agents in flight per env): the count in [4, 8] that leaves the fewest idle warp slots in the last round
+// (10 agents: 5 warps x 2 rounds instead of 4 x 3)
+__host__ __device__ inline int d2d_rvo_warps(int N) {
+    int best = 4, waste = (N + 3) / 4 * 4 - N;
+    for (int w = 5; w <= D2D_RVO_MAX_WARPS; w++) {
+        const int x = (N + w - 1) / w * w - N;
+        if (x < waste) { best = w; waste = x; }
+    }
+    return best;
+}
 #define D2D_RVO_MAX_CAND (D2D_RVO_THETAS * 8 + 1)
 
-struct RvoCone { double tx, ty, th_left, th_right, dist, rad; };
+// rx, ry / lx, ly: the vectors atan2 turned into th_right / th_left; mode: which branch of in_between the cone takes
+// (0: |th_right - th_left| <= 3.14, 1: left < 0 < right, 2: right < 0 < left, 3: never inside, 4: decide with atan2 only)
+struct RvoCone { double tx, ty, th_left, th_right, dist, rad, rx, ry, lx, ly; int mode, pad_; };
 
 __host__ __device__ inline size_t d2d_rvo_smem_bytes(int N) {
     const size_t cones = (size_t)(N + D2D_RVO_MAX_OBS) * sizeof(RvoCone);
     const size_t cand = (size_t)D2D_RVO_MAX_CAND * 17;
-    return (size_t)N * 32 + D2D_RVO_WARPS * ((cones + cand + 15) / 16 * 16) + 64;
+    return (size_t)N * 32 + d2d_rvo_warps(N) * ((cones + cand + 15) / 16 * 16) + 64;
 }
 
 // RVO.in_between utils.py:434-460 (None counts as False)
@@ -38,6 +51,38 @@ __device__ __forceinline__ bool d2d_rvo_in_between(double theta_right, double th
     return false;
 }
 
+// --- in_between without atan2.  theta_dif = atan2(d) is only ever COMPARED with th_right = atan2(r) and th_left = atan2(l), and
+// atan2 is monotone in the true angle, so the order of two angles in (-pi, pi] follows from the half-planes of the vectors and
+// the sign of their cross product.  Wherever that is not certain by a wide margin (|cross| within 1e-9 relative, a vector
+// within 1e-9 of the x axis -- the +-pi seam and the sign of theta_dif --, or one of the cases where the reference's `3.14` /
+// `2*3.14` constants bite) the caller falls back to the atan2 evaluation, so the verdicts are those of d2d_rvo_in_between
+// on CUDA's atan2 everywhere.  ~25 instructions instead of ~150 for the N * 160 * (N - 1) tests of a step.
+#define D2D_RVO_TOL 1e-9
+// 1: angle(a) <= angle(b), 0: angle(a) > angle(b), -1: uncertain.  Both vectors strictly off the x axis (checked by the caller).
+__device__ __forceinline__ int d2d_rvo_angle_le(double ax, double ay, double bx, double by) {
+    const bool ua = ay > 0.0, ub = by > 0.0;
+    if (ua != ub) return ub ? 1 : 0;                      // lower half-plane (-pi, 0) comes before the upper one (0, pi)
+    const double p = ax * by, q = ay * bx, cr = p - q;    // same open half-plane: the angles differ by less than pi
+    if (fabs(cr) <= D2D_RVO_TOL * (fabs(p) + fabs(q))) return -1;
+    return cr > 0.0 ? 1 : 0;
+}
+// 1 / 0: verdict of in_between(th_right, atan2(dy, dx), th_left); -1: evaluate with atan2
+__device__ __forceinline__ int d2d_rvo_inside_fast(const RvoCone &c, double dx, double dy) {
+    if (c.mode == 3) return 0;
+    if (c.mode == 4 || !(fabs(dy) > D2D_RVO_TOL * fabs(dx))) return -1;
+    if (c.mode == 0) {                                    // th_right <= theta_dif <= th_left
+        const int a = d2d_rvo_angle_le(c.rx, c.ry, dx, dy);
+        if (a == 0) return 0;
+        const int b = d2d_rvo_angle_le(dx, dy, c.lx, c.ly);
+        if (b == 0) return 0;
+        return (a < 0 || b < 0) ? -1 : 1;
+    }
+    if (c.mode == 1)                                      // left < 0 < right: theta_dif >= 0 -> right <= dif; < 0 -> dif <= left
+        return dy > 0.0 ? d2d_rvo_angle_le(c.rx, c.ry, dx, dy) : d2d_rvo_angle_le(dx, dy, c.lx, c.ly);
+    // mode 2, right < 0 < left: theta_dif >= 0 -> left <= dif; < 0 -> dif <= right
+    return dy > 0.0 ? d2d_rvo_angle_le(c.lx, c.ly, dx, dy) : d2d_rvo_angle_le(dx, dy, c.rx, c.ry);
+}
+
 __device__ __forceinline__ void d2d_rvo_make_cone(RvoCone &c, double pAx, double pAy, double tx, double ty, double pBx,
                                                   double pBy, double reach) {
     c.tx = tx; c.ty = ty;
@@ -47,11 +92,23 @@ __device__ __forceinline__ void d2d_rvo_make_cone(RvoCone &c, double pAx, double
     const double ort = asin(reach / dist);
     const double tl = theta_BA + ort, tr = theta_BA - ort;
     c.dist = dist; c.rad = reach;
-    c.th_right = atan2(sin(tr), cos(tr));       // atan2(bound_right[1], bound_right[0]), utils.py:372
-    c.th_left = atan2(sin(tl), cos(tl));
+    c.rx = cos(tr); c.ry = sin(tr); c.lx = cos(tl); c.ly = sin(tl);
+    c.th_right = atan2(c.ry, c.rx);             // atan2(bound_right[1], bound_right[0]), utils.py:372
+    c.th_left = atan2(c.ly, c.lx);
+    // which branch of in_between (utils.py:434-460) this cone takes, and whether the shortcut is safe for it: in the wrapped
+    // branches the reference adds 2 * 3.14 (not 2 pi) to one bound and to a negative theta_dif, which only changes a verdict
+    // when a bound lies within 0.0032 of +-pi -- those cones keep the atan2 path
+    const double PI_UP = 3.1415926535897936;    // > pi: no atan2 result exceeds it
+    int mode;
+    if (fabs(c.th_right - c.th_left) <= 3.14) mode = 0;
+    else if (c.th_left < 0 && c.th_right > 0) mode = (c.th_left + 2 * 3.14 < PI_UP || c.th_right > 2 * 3.14 - PI_UP) ? 4 : 1;
+    else if (c.th_left > 0 && c.th_right < 0) mode = (c.th_right + 2 * 3.14 < PI_UP || c.th_left > 2 * 3.14 - PI_UP) ? 4 : 2;
+    else mode = 3;
+    if (!(fabs(c.ry) > D2D_RVO_TOL * fabs(c.rx)) || !(fabs(c.ly) > D2D_RVO_TOL * fabs(c.lx))) mode = (mode == 3) ? 3 : 4;
+    c.mode = mode; c.pad_ = 0;
 }
 
-__global__ void __launch_bounds__(D2D_RVO_WARPS * 32) d2d_rvo_kernel(const DevP P) {
+__global__ void __launch_bounds__(D2D_RVO_MAX_WARPS * 32) d2d_rvo_kernel(const DevP P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int N = P.N, NP = P.NP;
@@ -71,7 +128,8 @@ __global__ void __launch_bounds__(D2D_RVO_WARPS * 32) d2d_rvo_kernel(const DevP 
     const double ROB_RAD = P.arad[(size_t)e * NP] + 0.01;       // agents[0].radius + 0.01, utils.py:309
     const int nobs = P.rvo_nobs[e];
     const double *obs = P.rvo_obs + (size_t)e * D2D_RVO_MAX_OBS * 3;
-    for (int i = wid; i < N; i += D2D_RVO_WARPS) {
+    const int n_warps = blockDim.x >> 5;
+    for (int i = wid; i < N; i += n_warps) {
         const double pAx = spos[i].x, pAy = spos[i].y, vAx = svel[i].x, vAy = svel[i].y;
         const int nc = N - 1 + nobs;
         // ---- cones (utils.py:314-352); their order does not matter: every use is an `any` or a `min`
@@ -95,20 +153,31 @@ __global__ void __launch_bounds__(D2D_RVO_WARPS * 32) d2d_rvo_kernel(const DevP 
         const double r_next = r_start + r_step, r_delta = r_next - r_start;   // NumPy fill: start + i * (a[1] - a[0])
         const int ncand = D2D_RVO_THETAS * n_rad + 1;
         bool suit_any = false;
-        for (int q = lane; q < ncand; q += 32) {
-            double cx, cy;
-            if (q == ncand - 1) { cx = w.x; cy = w.y; }
-            else {
-                const int it = q / n_rad, ir = q - it * n_rad;
-                const double rad = ir == 0 ? r_start : (ir == 1 ? r_next : r_start + (double)ir * r_delta);
-                cx = rad * P.tab->rvo_cos[it]; cy = rad * P.tab->rvo_sin[it];
-            }
+        for (int q = lane; q < ncand - 1; q += 32) {
+            const int it = q / n_rad, ir = q - it * n_rad;
+            const double rad = ir == 0 ? r_start : (ir == 1 ? r_next : r_start + (double)ir * r_delta);
+            const double cx = rad * P.tab->rvo_cos[it], cy = rad * P.tab->rvo_sin[it];
             bool b = false;
             for (int k = 0; k < nc && !b; k++) {
-                const double theta_dif = atan2(cy + pAy - cones[k].ty, cx + pAx - cones[k].tx);
-                b = d2d_rvo_in_between(cones[k].th_right, theta_dif, cones[k].th_left);
+                const double dy = cy + pAy - cones[k].ty, dx = cx + pAx - cones[k].tx;
+                const int f = d2d_rvo_inside_fast(cones[k], dx, dy);
+                if (f >= 0) b = f != 0;
+                else b = d2d_rvo_in_between(cones[k].th_right, atan2(dy, dx), cones[k].th_left);
             }
             candx[q] = cx; candy[q] = cy; bad[q] = b ? 1 : 0;
+            suit_any |= !b;
+        }
+        {   // the last candidate is the preferred velocity itself (utils.py:377-389): its cones go one per lane instead of
+            // costing a sixth round of the loop above for a single lane (160 = 5 x 32 candidates come before it)
+            bool b = false;
+            for (int k = lane; k < nc; k += 32) {
+                const double dy = w.y + pAy - cones[k].ty, dx = w.x + pAx - cones[k].tx;
+                const int f = d2d_rvo_inside_fast(cones[k], dx, dy);
+                if (f >= 0) b |= f != 0;
+                else b |= d2d_rvo_in_between(cones[k].th_right, atan2(dy, dx), cones[k].th_left);
+            }
+            b = __any_sync(0xffffffffu, b);
+            if (lane == 0) { candx[ncand - 1] = w.x; candy[ncand - 1] = w.y; bad[ncand - 1] = b ? 1 : 0; }
             suit_any |= !b;
         }
         suit_any = __any_sync(0xffffffffu, suit_any);
@@ -127,8 +196,10 @@ __global__ void __launch_bounds__(D2D_RVO_WARPS * 32) d2d_rvo_kernel(const DevP 
                 bool have = false;
                 for (int k = 0; k < nc; k++) {
                     const double dx = ux + pAx - cones[k].tx, dy = uy + pAy - cones[k].ty;
+                    const int f = d2d_rvo_inside_fast(cones[k], dx, dy);
+                    if (f == 0) continue;                       // certainly outside this cone: no angle needed
                     const double theta_dif = atan2(dy, dx);
-                    if (!d2d_rvo_in_between(cones[k].th_right, theta_dif, cones[k].th_left)) continue;
+                    if (f < 0 && !d2d_rvo_in_between(cones[k].th_right, theta_dif, cones[k].th_left)) continue;
                     const double small_theta = fabs(theta_dif - 0.5 * (cones[k].th_left + cones[k].th_right));
                     double rad = cones[k].rad;
                     const double a = fabs(cones[k].dist * sin(small_theta));

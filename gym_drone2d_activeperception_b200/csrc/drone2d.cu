@@ -793,7 +793,7 @@ extern "C" int d2d_step(d2d_handle *h, const double *actions_dev, void *stream) 
         const size_t sm = d2d_rvo_smem_bytes(h->N);
         const int rca = ensure_smem_attr(h, (const void *)d2d_rvo_kernel, "rvo");
         if (rca != D2D_OK) return rca;
-        d2d_rvo_kernel<<<h->B, D2D_RVO_WARPS * 32, sm, st>>>(h->P);
+        d2d_rvo_kernel<<<h->B, d2d_rvo_warps(h->N) * 32, sm, st>>>(h->P);
         h->launches++;
     }
     const int epb = h->cfg.envs_per_block;
