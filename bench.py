@@ -425,7 +425,8 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
         ctx.barrier()
         r_ms = np.array([revs[m].elapsed_time(revs[m + 1]) for m in range(Mr)], dtype=np.float64) / (K * R)
         rollout = {"med": float(np.median(r_ms)), "min": float(r_ms.min()), "max": float(r_ms.max()), "replays": Mr,
-                   "launches": int(r_launches), "region_ms": float(r_ms.sum() * K * R)}
+                   "launches": int(r_launches), "region_ms": float(r_ms.sum() * K * R),
+                   "resident": int(r_launches) == R}     # above two waves of warps d2d_rollout issues K per-step launches
         del rgraph
 
     per_step = None
@@ -553,8 +554,10 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
     e2e = world * B / (e2e_ms * 1e-3)
 
     peak, peak_src = measured_peak()
-    if rollout:
+    if rollout and rollout["resident"]:
         kernel_name = "d2d_rollout_warp_kernel (K steps per launch, env state resident on chip)"
+    elif rollout:
+        kernel_name = "d2d_step_fused_warp_kernel (d2d_rollout above two waves of warps: 1 launch/step)"
     elif pk["planner"] == "NoMove":
         kernel_name = "d2d_step_fused_warp_kernel (1 launch/step)"
     else:
@@ -562,7 +565,8 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
                       (" + d2d_oxford_kernel" if use_ox else "") + " (whole step timed)"
     achieved = algorithmic_bytes(N) * B / (ms_step * 1e-3) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", ("traffic_rollout_config%d.json" if rollout else "traffic_config%d.json") % cfg["config_id"])
+    tpath = os.path.join(ROOT, "profiles", ("traffic_rollout_config%d.json" if (rollout and rollout["resident"]) else
+                                            "traffic_config%d.json") % cfg["config_id"])
     if os.path.isfile(tpath) and pk["planner"] == "NoMove" and n_rays == 50 and "view_range" not in cfg["name"]:
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
@@ -571,8 +575,10 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
     res = {
         "value": value, "unit": "env-steps/s", "ms_per_step": ms_step, "rays_per_sec": value * n_rays,
         "config": public_config(cfg, world),
-        "method": {"timing": (("K = %d steps of every env as ONE d2d_rollout launch per replica (R = %d launches captured as a CUDA "
-                              "graph, replayed M = %d times back to back); " % (K, R, rollout["replays"])) if rollout else
+        "method": {"timing": (("K = %d steps of every env as ONE d2d_rollout call per replica (%s; R = %d calls captured as a CUDA "
+                              "graph, replayed M = %d times back to back); " % (
+                                  K, "one resident launch" if rollout["resident"] else "K per-step launches: batch above two waves",
+                                  R, rollout["replays"])) if rollout else
                               ("K = %d steps captured as one CUDA graph (K step launches), replayed M = %d times back to back, " % (K, M))) +
                              "one CUDA-event pair per replay on the launch stream, barrier + synchronize around the region; "
                              "per rank the median replay, over ranks the max of the medians",

@@ -1266,10 +1266,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_step_fused_warp_kernel(con
     // NoMove: the drone cell cannot change during the step, so if the observation tensor already holds this window it
     // is patched in place by the rays (only cells whose value changes) instead of being rewritten
     __syncwarp();
-    const bool same_win = s.obs_ix == s.ix && s.obs_iy == s.iy;
-    const bool refill = !GATED && s.reset && same_win;   // new episode, same window: clear + patch (see d2d_obs_clear_warp)
-    if (refill) d2d_obs_clear_warp(P, e, lane, true);
-    const bool patch = (!s.reset || refill) && same_win;
+    const bool patch = !s.reset && s.obs_ix == s.ix && s.obs_iy == s.iy;
     const bool mirror = GATED && P.lm_mirror != nullptr;
     RayOut ro;
     ro.bel_s = c.belief; ro.e = e; ro.patch = patch ? 1 : 0;
@@ -1480,9 +1477,11 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_rollout_warp_kernel(const 
         // same window as the observation tensor holds: patched in place by the rays; an env that starts a new episode there
         // has its slice cleared first (d2d_obs_clear_warp) -- GATED: on the device only, the host mirror gets the finished slice
         // behind the gate
-        const bool patch = s.obs_ix == s.ix && s.obs_iy == s.iy;
-        const bool refill = s.reset && patch;
-        if (refill) d2d_obs_clear_warp(P, e, lane, !GATED);
+        // (not with a host mirror that takes its stores as they occur: ~150 single-byte PCIe writes per fresh env cost more
+        // than the one coalesced rewrite)
+        const bool refill = s.reset && s.obs_ix == s.ix && s.obs_iy == s.iy && (GATED || P.lm_mirror == nullptr);
+        const bool patch = (!s.reset || refill) && s.obs_ix == s.ix && s.obs_iy == s.iy;
+        if (refill) d2d_obs_clear_warp(P, e, lane, false);
         RayOut ro;
         ro.bel_s = c.belief; ro.e = e; ro.patch = patch ? 1 : 0;
         ro.wi = s.ix - 16; ro.wj = s.iy - 16;

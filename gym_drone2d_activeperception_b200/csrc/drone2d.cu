@@ -872,6 +872,18 @@ extern "C" int d2d_rollout(d2d_handle *h, const double *actions_dev, int32_t num
     // experiment knob (tools/rollout_bench.py): block shape / per-step block barrier of the rollout kernel
     static const int variant = getenv("D2D_ROLLOUT_VARIANT") ? atoi(getenv("D2D_ROLLOUT_VARIANT")) : 0;
     int rc;
+    // The resident kernel pays off while the batch is a wave or two of 28-warp blocks (4096 envs: 16.7 vs 21.4 us per step).
+    // Large batches keep the SMs busier with the 4-warp blocks of the per-step kernel, which the hardware back-fills one by
+    // one (131072 envs, N = 96: 0.75 ms per step against 0.81 ms), so they run the K steps as K per-step launches -- same
+    // results either way (tests/test_gpu_rollout.py).
+    if (variant == 0 && h->B > 2 * 28 * 148) {
+        for (int t = 0; t < num_steps; t++) {
+            rc = launch_fused_warp<4, 7, false>(h, actions_dev + (size_t)t * (size_t)action_stride, st);
+            if (rc != D2D_OK) return rc;
+        }
+        CUDA_TRY(h, cudaGetLastError());
+        return D2D_OK;
+    }
     switch (variant) {
         case 1: rc = launch_rollout<4, 7, false, false>(h, actions_dev, num_steps, action_stride, st); break;
         case 2: rc = launch_rollout<4, 7, true, false>(h, actions_dev, num_steps, action_stride, st); break;

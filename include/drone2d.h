@@ -187,8 +187,10 @@ int d2d_step(d2d_handle *h, const double *actions_dev, void *stream);
  * the same [num_envs] vector every step).  Every warp walks ITS env through the K steps with the env's working set resident
  * in shared memory (fetched from HBM once, not once per step) and never waits for the other envs between steps.  All buffers
  * and statistics end up bit-identical to K d2d_step calls; the per-step outputs ("done", "local_map", ...) hold the LAST
- * step's values.  NoMove planner, CVM motion profile, default warp kernels (envs_per_block <= 0) only: everything else
- * returns D2D_ERR_INVALID (those steps consist of several dependent launches; call d2d_step). */
+ * step's values.  Batches above two waves of warps (8288 envs on a 148-SM GPU) are stepped by K per-step launches instead
+ * (the per-step kernel's small blocks keep a large batch's SMs busier; same results).  NoMove planner, CVM motion profile,
+ * default warp kernels (envs_per_block <= 0) only: everything else returns D2D_ERR_INVALID (those steps consist of several
+ * dependent launches; call d2d_step). */
 int d2d_rollout(d2d_handle *h, const double *actions_dev, int32_t num_steps, int64_t action_stride, void *stream);
 
 /* Same step with HOST buffers (the call an FFI user makes): gets the actions to the device (pinned memory is read by
