@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdrone2d.so")
+LIB_PATH = os.environ.get("D2D_LIB") or os.path.join(HERE, "libdrone2d.so")     # D2D_LIB: an A/B build of the same ABI (tools/)
 
 MAX_TARGETS, MAX_U, MAX_SAMP, MAX_WAY, MAX_YAW = 8, 64, 32, 64, 16
 NUM_STATS = 16

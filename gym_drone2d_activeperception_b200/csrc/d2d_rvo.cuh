@@ -68,6 +68,9 @@ __device__ __forceinline__ int d2d_rvo_angle_le(double ax, double ay, double bx,
 }
 // 1 / 0: verdict of in_between(th_right, atan2(dy, dx), th_left); -1: evaluate with atan2
 __device__ __forceinline__ int d2d_rvo_inside_fast(const RvoCone &c, double dx, double dy) {
+#ifdef D2D_RVO_NOFAST
+    return -1;      // A/B build (tools/parity_campaign.py with D2D_LIB=...): every verdict through atan2, as before round 2
+#endif
     if (c.mode == 3) return 0;
     if (c.mode == 4 || !(fabs(dy) > D2D_RVO_TOL * fabs(dx))) return -1;
     if (c.mode == 0) {                                    // th_right <= theta_dif <= th_left

@@ -26,6 +26,8 @@ LEGS = [
          agent_radius=15, agent_max_speed=20, planner="NoMove", B=8192, steps=400),
     dict(name="cfg2 scattered poses", static_map="maps/empty_map.npy", agent_number=10, agent_radius=15, agent_max_speed=20,
          planner="NoMove", B=8192, steps=300, scatter=True),
+    dict(name="cfg2 scattered poses through d2d_rollout (16 steps per launch, compared after every launch)", static_map="maps/empty_map.npy",
+         agent_number=10, agent_radius=15, agent_max_speed=20, planner="NoMove", B=4096, steps=640, scatter=True, rollout=16),
     dict(name="obstacle_map N=24 NoMove scattered", static_map="maps/obstacle_map.npy", agent_number=10, agent_radius=10,
          agent_max_speed=20, planner="NoMove", B=8192, steps=200, scatter=True),
     dict(name="shaped_obstacle_map N=96 NoMove scattered", static_map="maps/shaped_obstacle_map.npy", agent_number=50,
@@ -91,9 +93,20 @@ def run_leg(leg, scale, seed0):
     episodes = 0
     t_setup = time.time() - t0
     t0 = time.time()
+    chunk = int(leg.get("rollout", 0))
     for t in range(steps):
         act_bad = np.zeros(B, dtype=bool)
-        if use_ox:
+        if chunk:
+            # resident multi-step kernel: `chunk` steps per launch; the oracle steps beside it, compared after the launch
+            if t % chunk:
+                continue
+            acts_k = table[rng.randint(0, 6, (chunk, B))]
+            for q in range(chunk):
+                ob.step(acts_k[q], auto_reset=True)
+                if q < chunk - 1:
+                    episodes += int(ob.gather(trackers=False)["done"].sum())
+            env.rollout(torch.as_tensor(acts_k, device="cuda:0"))
+        elif use_ox:
             a_dev = env.plan_gaze(gaze)
             want, _ = ob.step(policy=gaze, auto_reset=True)
             act_bad = a_dev.cpu().numpy() != want
@@ -102,7 +115,8 @@ def run_leg(leg, scale, seed0):
             acts = table[rng.randint(0, 6, B)]
             a_dev = torch.as_tensor(acts, device="cuda:0")
             ob.step(acts, auto_reset=True)
-        env.step(a_dev)
+        if not chunk:
+            env.step(a_dev)
         h = util.gpu_fields(env, fields)
         o = ob.gather(trackers=True, rvo=rvo)
         d, r = util.batch_mismatch(h, o, n, trackers=True, planner=n_way)
@@ -111,7 +125,7 @@ def run_leg(leg, scale, seed0):
         if rvo:
             a, b = h["agent_vel"][:, :n].reshape(B, -1), o["agent_vel"][:, :n].reshape(B, -1)
             r["agent_vel"] = (np.abs(a - b) / np.maximum(1.0, np.abs(b))).max(1)
-        compared += int(alive.sum())
+        compared += int(alive.sum()) * (chunk if chunk else 1)
         bad = np.zeros(B, dtype=bool)
         for k, m in d.items():
             mk = m & alive
