@@ -54,7 +54,7 @@ class D2DBufferInfo(C.Structure):
                 ("shape", C.c_int64 * 4), ("strides", C.c_int64 * 4)]
 
 
-EXPORTS = ["d2d_version", "d2d_last_error", "d2d_create", "d2d_destroy", "d2d_set_world", "d2d_set_rng", "d2d_set_rvo", "d2d_set_jerk_tables", "d2d_reset", "d2d_step", "d2d_rollout",
+EXPORTS = ["d2d_version", "d2d_last_error", "d2d_create", "d2d_destroy", "d2d_set_world", "d2d_set_rng", "d2d_set_rvo", "d2d_set_jerk_tables", "d2d_reset", "d2d_request_reset", "d2d_step", "d2d_rollout",
            "d2d_step_host", "d2d_bind_host_mirror", "d2d_bind_host_io", "d2d_step_bound", "d2d_step_pipelined", "d2d_plan_oxford", "d2d_plan_gaze", "d2d_set_drone_pose", "d2d_get_buffer", "d2d_stats",
            "d2d_launch_count"]
 
@@ -86,6 +86,7 @@ def load():
     L.d2d_set_rvo.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, C.c_int32]
     L.d2d_set_jerk_tables.argtypes = [vp, C.POINTER(D2DJerkTables)]
     L.d2d_reset.argtypes = [vp, vp, vp]
+    L.d2d_request_reset.argtypes = [vp, vp, vp]
     L.d2d_step.argtypes = [vp, vp, vp]
     L.d2d_rollout.argtypes = [vp, vp, C.c_int32, C.c_int64, vp]
     L.d2d_step_host.argtypes = [vp, vp, vp, vp, vp, vp]

@@ -43,7 +43,7 @@ struct __align__(16) EnvRec {
     int bufc, bufts, tracked;        // tracker_buffer count / summed ts, newly tracked agents (drone_v2.py:187, 232-235)
     int nseg, cursor;                // trajectory: remaining waypoints = nseg*n_way - cursor
     int obs_ix, obs_iy;              // drone cell for which the local_map tensor content is currently valid
-    uint8_t pending_reset;           // reset requested by the host, applied lazily at the start of the next step
+    uint8_t pending_reset;           // reset requested by the host (d2d_request_reset), applied at the start of the next step
     uint8_t ox_fresh;                // Oxford state already re-initialised for a pending reset
     uint8_t owl_fresh;               // same for the Owl state
     uint8_t pad_[1];

@@ -687,6 +687,22 @@ extern "C" int d2d_reset(d2d_handle *h, const uint8_t *mask_dev, void *stream) {
     return D2D_OK;
 }
 
+__global__ void d2d_request_reset_kernel(const DevP P, const uint8_t *__restrict__ mask) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < P.B && (!mask || mask[e])) P.rec[e].pending_reset = 1;
+}
+
+extern "C" int d2d_request_reset(d2d_handle *h, const uint8_t *mask_dev, void *stream) {
+    if (!h) return D2D_ERR_INVALID;
+    D2D_NO_PIPE(h);
+    if (!h->world_set) { h->err = "d2d_request_reset before d2d_set_world"; return D2D_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    d2d_request_reset_kernel<<<(h->B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->P, mask_dev);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return D2D_OK;
+}
+
 // pinned (page-locked, mapped) host pointer -> the address kernels can store through; null on failure
 static void *mirror_dev_ptr(d2d_handle *h, void *host, const char *what) {
     cudaPointerAttributes at;

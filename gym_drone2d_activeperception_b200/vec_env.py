@@ -235,14 +235,19 @@ class Drone2DVecEnv(object):
         # the reference returns the same crop under both keys (drone_v2.py:252-253)
         return {"local_map": lm, "swep_map": lm, "yaw_angle": self.buffer("yaw_angle")}
 
-    def reset(self, mask=None):
+    def reset(self, mask=None, lazy=False):
         """reset() of the reference re-runs __init__ (drone_v2.py:259-261) and returns {}; here the initial observation
-        is returned (zeros + initial yaw).  mask: optional bool/uint8 CUDA tensor [B] selecting envs."""
+        is returned (zeros + initial yaw).  mask: optional bool/uint8 CUDA tensor [B] selecting envs.  lazy=True only marks
+        the envs (d2d_request_reset): they are re-initialised inside their next step, like an env that returned done under
+        auto_reset; the observation tensors keep their content until then."""
         mptr = None
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
             mptr = C.c_void_p(mask.data_ptr())
-        self._check(self._lib.d2d_reset(self._h, mptr, self._stream()), "d2d_reset")
+        if lazy:
+            self._check(self._lib.d2d_request_reset(self._h, mptr, self._stream()), "d2d_request_reset")
+        else:
+            self._check(self._lib.d2d_reset(self._h, mptr, self._stream()), "d2d_reset")
         return self._obs()
 
     def step(self, actions):

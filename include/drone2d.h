@@ -177,6 +177,12 @@ int d2d_set_rvo(d2d_handle *h, int32_t first_env, int32_t count, const double *a
  * (mask_dev == NULL: all).  mask_dev is a DEVICE pointer to num_envs bytes. */
 int d2d_reset(d2d_handle *h, const uint8_t *mask_dev, void *stream);
 
+/* Lazy form of d2d_reset: marks the selected envs (EnvRec::pending_reset); each is re-initialised from its snapshot at the
+ * START of its next step -- the path auto_reset takes for an env that returned done -- inside the step kernel, without the
+ * separate reset kernel and without touching the observation until then (a gaze policy called in between sees the env as
+ * freshly reset, as it does after done).  After that step the state equals d2d_reset + the same step. */
+int d2d_request_reset(d2d_handle *h, const uint8_t *mask_dev, void *stream);
+
 /* Replaces Drone2DEnv2.step(a) (drone_v2.py:152-257) for all envs.  actions_dev: DEVICE [num_envs] f64 in [-1, 1].
  * Results land in the buffers "local_map", "yaw_angle", "done", "collision_flag", ... (d2d_get_buffer). */
 int d2d_step(d2d_handle *h, const double *actions_dev, void *stream);

@@ -125,3 +125,34 @@ def test_rollout_rejects_other_planners():
     with pytest.raises(_native.Drone2DNativeError):
         env.rollout(torch.zeros((3, 8), dtype=torch.float64, device="cuda:0"))
     env.close()
+
+
+@pytest.mark.parametrize("planner,gaze", [("NoMove", None), ("Primitive", "Oxford")])
+def test_lazy_reset_equals_eager_reset(planner, gaze):
+    """d2d_request_reset (re-initialisation inside the next step, the auto-reset path) against d2d_reset + the same step."""
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200.vec_env import Drone2DVecEnv
+    B = 96
+    p = Params(debug=False, planner=planner, gaze_method=gaze or "NoControl", map_id=1, agent_number=10, agent_radius=15,
+               agent_max_speed=20)
+    mk = lambda: Drone2DVecEnv(p, B, seeds=1 + np.arange(B), device="cuda:0", auto_reset=False, oxford=gaze == "Oxford")
+    a, b = mk(), mk()
+    table = torch.as_tensor(util.action_table(), device="cuda:0")
+    g = torch.Generator(device="cuda:0"); g.manual_seed(9)
+    mask = torch.zeros(B, dtype=torch.uint8, device="cuda:0"); mask[::3] = 1
+    names = util.BATCH_FIELDS + util.TRACKER_FIELDS + ["env_records"] + (["oxford_calls"] if gaze else [])
+
+    def step(env, acts):
+        env.step(env.plan_oxford() if gaze else acts)
+    for t in range(70):
+        acts = table[torch.randint(0, 6, (B,), device="cuda:0", generator=g)]
+        if t in (25, 26, 50):
+            a.reset(mask)
+            b.reset(mask, lazy=True)
+        step(a, acts); step(b, acts)
+        if t >= 25:
+            for k in names:
+                x, y = a.buffer(k).cpu().numpy(), b.buffer(k).cpu().numpy()
+                same = (x == y) | ((x != x) & (y != y)) if x.dtype.kind == "f" else (x == y)
+                assert same.all(), (planner, k, "step", t, np.argwhere(~same)[:3].tolist())
+    a.close(); b.close()
