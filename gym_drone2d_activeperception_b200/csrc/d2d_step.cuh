@@ -325,6 +325,9 @@ struct RayOut {
 // a belief cell changes value (0 -> 1 or 0 -> 2): shared copy, HBM grid, and whatever mirrors the observation
 __device__ __forceinline__ void d2d_mark_store(const DevP &P, const RayOut &o, int cell, uint8_t v) {
     o.bel_s[cell] = v;
+#ifdef D2D_WARP_PROF
+    atomicAdd(&P.prof[(size_t)o.e * 12 + 5], 1ull);     // marks of this env (accumulated over the steps of a launch)
+#endif
     P.belief[(size_t)o.e * D2D_BELIEF_STRIDE + cell] = v;
     if (o.patch) {          // the cell is always inside the 33x33 window (view reach < 16 cells)
         const int ci = cell / D2D_GRID, cj = cell - ci * D2D_GRID;
@@ -507,6 +510,10 @@ __device__ __forceinline__ uint32_t d2d_cast_ray(const DevP &P, const EnvS &s, d
                 "@!pe add.rn.f64 %1, %1, %5;\n\t"
                 "}" : "+d"(uy), "+d"(uyb), "+r"(caddr) : "d"(uys), "r"(dcy), "d"(scale));
         }
+#ifdef D2D_WARP_PROF
+        atomicAdd(&P.prof[(size_t)o.e * 12 + 6], (unsigned long long)(m + 1));   // samples marched by this env's rays
+        atomicMax(&P.prof[(size_t)o.e * 12 + 7], (unsigned long long)(m + 1));   // longest ray
+#endif
         return hm;
     }
     int ci = s.ix, cj = s.iy;
@@ -1181,8 +1188,12 @@ __device__ __forceinline__ void d2d_obs_mirror_copy_warp(const DevP &P, int e, i
     if (lane < D2D_LOCAL_CELLS - tail0) dst[tail0 + lane] = __ldcg(src + tail0 + lane);
     const uint32_t *sw = (const uint32_t *)(src + head);
     uint32_t *dw = (uint32_t *)(dst + head);
-#pragma unroll 4
-    for (int j = lane; j < nwords; j += 32) dw[j] = __ldcg(sw + j);
+    // all loads of a lane in flight before its first store: this copy sits on the critical path of the step's slowest envs
+    uint32_t v[9];                                      // nwords <= 272 = 8.5 x 32
+#pragma unroll
+    for (int k = 0; k < 9; k++) { const int j = lane + 32 * k; v[k] = j < nwords ? __ldcg(sw + j) : 0u; }
+#pragma unroll
+    for (int k = 0; k < 9; k++) { const int j = lane + 32 * k; if (j < nwords) dw[j] = v[k]; }
     if (lane == 0) atomicAdd(&P.stats[D2D_STAT_MIRROR_BYTES], (unsigned long long)D2D_LOCAL_CELLS);
 }
 
@@ -1614,7 +1625,9 @@ __global__ void __launch_bounds__(WPB * 32, MINB) d2d_rollout_warp_kernel(const 
                     const unsigned long long n = atomicAdd(P.gate_count, (unsigned long long)blk_envs) + (unsigned long long)blk_envs;
                     if (n == (unsigned long long)P.B * (unsigned long long)(t + 1)) {
                         atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], (unsigned long long)P.B);   // every env stepped once
-                        __threadfence_system();           // cumulative: orders every block's mirror stores before the flag
+                        // release at system scope (cumulative: orders every block's mirror stores before the flag); acq_rel is
+                        // all a release needs -- __threadfence_system() is the sequentially-consistent fence
+                        asm volatile("fence.acq_rel.sys;" ::: "memory");
                         *(volatile unsigned int *)P.gate_done = t_first + (unsigned int)t;
                     }
                 }

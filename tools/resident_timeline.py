@@ -29,6 +29,7 @@ with torch.cuda.stream(side):
     env.bind_host_io(a_bound, None if os.environ.get("NO_LM") else lm, yaw, done)
     for t in range(5): env.step_bound()
     for n in (200, 200, 200):
+        env.buffer("warp_prof")[:, 5:8] = 0
         t0 = time.perf_counter()
         for t in range(n):
             ctypes.memmove(a_bound.data_ptr(), srcs[t % 64], B * 8)
@@ -49,6 +50,15 @@ with torch.cuda.stream(side):
         print("   slowest action-independent parts: " + "; ".join(
             "env %d pre %.1f (head %.1f rays %.1f tail %.1f) steps=%d hits=%d trk=%d" % (
                 i, pre[i], (p[i, 1] - p[i, 0]) / 1e3, rays[i], (p[i, 8] - p[i, 2]) / 1e3, steps_now[i], hits[i], act[i]) for i in order))
+        # counters accumulate over the n steps of the run: per-step means per env against the LAST step's ray time is only a
+        # hint; the clean signal is the split by "env was re-initialised in the last step" (steps == 1)
+        fresh = steps_now == 1
+        print("   ray phase of the last step: fresh envs (%d) med %.1f us | others med %.1f p99 %.1f max %.1f | marks per env-step (mean over run) %.2f, samples per ray %.2f, longest ray %d samples"
+              % (int(fresh.sum()), np.median(rays[fresh]) if fresh.any() else 0.0, np.median(rays[~fresh]), np.percentile(rays[~fresh], 99), rays[~fresh].max(),
+                 p[:, 5].mean() / n, p[:, 6].mean() / n / 50.0, int(p[:, 7].max())))
+        slow_old = np.argsort(-np.where(fresh, 0, rays))[:6]
+        print("   slowest non-fresh ray phases: " + "; ".join("env %d rays %.1f marks/step %.2f steps=%d ix,iy=%s hits=%d" % (
+            i, rays[i], p[i, 5] / n, steps_now[i], (int(env.buffer("drone_x")[i].item() // 10), int(env.buffer("drone_y")[i].item() // 10)), hits[i]) for i in slow_old))
         print("%d steps: %.1f us per call | last step, per warp (us): start spread %.1f | pre-gate med %.1f p90 %.1f max %.1f (rays med %.1f) | "
               "gate wait med %.1f min %.1f max %.1f | gate -> end med %.1f max %.1f | first start -> last gate arrival %.1f, -> first gate open %.1f, -> last end %.1f"
               % (n, dt, (p[:, 0].max() - k0) / 1e3, np.median(pre), np.percentile(pre, 90), pre.max(), np.median(rays),
