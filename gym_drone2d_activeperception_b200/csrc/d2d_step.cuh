@@ -188,13 +188,13 @@ __device__ D2D_COLD void d2d_reset_arrays(const DevP &P, const BlockCtx &c, int 
     // warp kernels start the bulk copy of the belief grid before they know whether the env is being reset: it must have
     // landed before the shared copy is zeroed
     if (early_bulk) d2d_mbar_wait(early_bulk, 0);
-    const int W = D2D_BELIEF_STRIDE / 4;
+    const int W = D2D_BELIEF_STRIDE / 16;              // 16-byte stores: the grids are 128-byte aligned rows of 2560 bytes
 #pragma unroll 1
     for (int w = tid; w < E * W; w += T) {
         const int i = w / W, o = w - i * W;
         if (!c.S[i].valid || !c.S[i].reset) continue;
-        ((uint32_t *)(c.belief + (size_t)i * D2D_BELIEF_STRIDE))[o] = 0u;
-        ((uint32_t *)(P.belief + (size_t)(env0 + i) * D2D_BELIEF_STRIDE))[o] = 0u;
+        ((uint4 *)(c.belief + (size_t)i * D2D_BELIEF_STRIDE))[o] = uint4{0u, 0u, 0u, 0u};
+        ((uint4 *)(P.belief + (size_t)(env0 + i) * D2D_BELIEF_STRIDE))[o] = uint4{0u, 0u, 0u, 0u};
     }
     if (P.rng_key) {   // reset() re-seeds np.random with map_id (drone_v2.py:80): restore the post-init stream state
 #pragma unroll 1
@@ -325,7 +325,7 @@ struct RayOut {
 // a belief cell changes value (0 -> 1 or 0 -> 2): shared copy, HBM grid, and whatever mirrors the observation
 __device__ __forceinline__ void d2d_mark_store(const DevP &P, const RayOut &o, int cell, uint8_t v) {
     o.bel_s[cell] = v;
-#ifdef D2D_WARP_PROF
+#if defined(D2D_WARP_PROF) && D2D_WARP_PROF >= 2        // counters perturb the timing: tools/resident_timeline.py --counters
     atomicAdd(&P.prof[(size_t)o.e * 12 + 5], 1ull);     // marks of this env (accumulated over the steps of a launch)
 #endif
     P.belief[(size_t)o.e * D2D_BELIEF_STRIDE + cell] = v;
@@ -510,7 +510,7 @@ __device__ __forceinline__ uint32_t d2d_cast_ray(const DevP &P, const EnvS &s, d
                 "@!pe add.rn.f64 %1, %1, %5;\n\t"
                 "}" : "+d"(uy), "+d"(uyb), "+r"(caddr) : "d"(uys), "r"(dcy), "d"(scale));
         }
-#ifdef D2D_WARP_PROF
+#if defined(D2D_WARP_PROF) && D2D_WARP_PROF >= 2
         atomicAdd(&P.prof[(size_t)o.e * 12 + 6], (unsigned long long)(m + 1));   // samples marched by this env's rays
         atomicMax(&P.prof[(size_t)o.e * 12 + 7], (unsigned long long)(m + 1));   // longest ray
 #endif
@@ -1202,7 +1202,12 @@ __device__ __forceinline__ void d2d_obs_mirror_copy_warp(const DevP &P, int e, i
 __device__ __forceinline__ void d2d_count_explored_warp(const DevP &P, const uint8_t *bel, int lane) {
     int cnt = 0;
 #pragma unroll 1
-    for (int w = lane; w < D2D_CELLS / 4; w += 32) cnt += __popc(__vcmpne4(((const uint32_t *)bel)[w], 0u) & 0x01010101u);
+    for (int w = lane; w < D2D_CELLS / 16; w += 32) {            // 156 x 16 bytes = cells 0 .. 2495
+        const uint4 v = ((const uint4 *)bel)[w];
+        cnt += __popc(__vcmpne4(v.x, 0u) & 0x01010101u) + __popc(__vcmpne4(v.y, 0u) & 0x01010101u) +
+               __popc(__vcmpne4(v.z, 0u) & 0x01010101u) + __popc(__vcmpne4(v.w, 0u) & 0x01010101u);
+    }
+    if (lane == 0) cnt += __popc(__vcmpne4(((const uint32_t *)bel)[D2D_CELLS / 4 - 1], 0u) & 0x01010101u);   // cells 2496 .. 2499
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (lane == 0 && cnt) atomicAdd(&P.stats[D2D_STAT_GRID_DISCOVERED], (unsigned long long)cnt);
 }

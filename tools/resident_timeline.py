@@ -7,7 +7,7 @@ sys.path.insert(0, os.getcwd())
 import numpy as np
 from gym_drone2d_activeperception_b200 import build as b, _native
 lib = os.path.join(os.path.dirname(b.LIB), "libdrone2d_prof.so")
-subprocess.run([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")] + b.NVCC_FLAGS + ["-DD2D_WARP_PROF", "-o", lib] +
+subprocess.run([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")] + b.NVCC_FLAGS + ["-DD2D_WARP_PROF=2" if "--counters" in sys.argv else "-DD2D_WARP_PROF", "-o", lib] +
                [os.path.join(b.CSRC, s) for s in b.SOURCES], check=True)
 _native.LIB_PATH = lib
 import torch, bench
