@@ -18,3 +18,18 @@ void mc_atan2(const double *y, const double *x, double *out, long n, int ulps) {
 }
 void mc_norm2(const double *x, const double *y, double *out, long n) { for (long i = 0; i < n; i++) out[i] = d2d_norm2(x[i], y[i]); }
 }
+
+// RVO cone tests (csrc/d2d_rvo_math.cuh): for cone i (agent A at pA, neighbour at pB, combined radius `reach`) and probe
+// vector d: fast[i] = the cross-product shortcut's verdict (-1 = "ask atan2"), slow[i] = in_between on atan2 -- the kernel takes
+// fast when it is >= 0 and slow otherwise, so wherever fast >= 0 the two must agree.
+#include "../../gym_drone2d_activeperception_b200/csrc/d2d_rvo_math.cuh"
+extern "C" void mc_rvo_inside(const double *pA, const double *pB, const double *reach, const double *d, int *fast, int *slow,
+                              int *mode, long n) {
+    for (long i = 0; i < n; i++) {
+        RvoCone c;
+        d2d_rvo_make_cone(c, pA[2 * i], pA[2 * i + 1], 0.0, 0.0, pB[2 * i], pB[2 * i + 1], reach[i]);
+        fast[i] = d2d_rvo_inside_fast(c, d[2 * i], d[2 * i + 1]);
+        slow[i] = d2d_rvo_in_between(c.th_right, atan2(d[2 * i + 1], d[2 * i]), c.th_left) ? 1 : 0;
+        mode[i] = c.mode;
+    }
+}

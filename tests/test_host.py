@@ -102,6 +102,7 @@ def mathlib(tmp_path_factory):
     L.mc_atan2.argtypes = [dp, dp, dp, C.c_long, C.c_int]
     ip = np.ctypeslib.ndpointer(np.int32, flags="C")
     L.mc_norm2_cmp.argtypes = [dp, dp, dp, ip, ip, C.c_long]
+    L.mc_rvo_inside.argtypes = [dp, dp, dp, dp, ip, ip, ip, C.c_long]
     return L
 
 
@@ -266,6 +267,37 @@ def test_device_norm_equals_numpy(mathlib):
     mathlib.mc_norm2(np.ascontiguousarray(v[:, 0]), np.ascontiguousarray(v[:, 1]), out, 50000)
     ref = np.array([np.linalg.norm(r) for r in v])
     assert (out == ref).mean() > 0.999      # exact on the OpenBLAS build the fixtures were generated with
+
+
+def test_rvo_cone_shortcut_agrees_with_atan2(mathlib):
+    """The RVO kernel decides `in_between` (utils.py:434-460) by cross-product angle order and only asks atan2 where the
+    order is not certain (csrc/d2d_rvo_math.cuh).  Wherever the shortcut answers, its verdict must be the atan2 one -- on
+    random cones, on cones straddling the +-pi seam (where the reference's 3.14 / 2*3.14 constants bite), on probes along a
+    cone edge and along the x axis."""
+    rng = np.random.RandomState(11)
+    n = 400000
+    pA = rng.uniform(-400, 400, (n, 2))
+    ang = rng.uniform(-math.pi, math.pi, n)
+    k = n // 4
+    ang[:k] = rng.choice([math.pi, -math.pi, 0.0, math.pi / 2], k) + rng.uniform(-0.3, 0.3, k)      # seam / axis cones
+    dist = rng.uniform(5, 300, n)
+    pB = pA + dist[:, None] * np.stack([np.cos(ang), np.sin(ang)], 1)
+    reach = rng.uniform(2, 40, n)
+    reach[k:k + 2000] = dist[k:k + 2000] * rng.uniform(1.0, 1.5, 2000)                              # overlapping: asin(1)
+    dth = rng.uniform(-math.pi, math.pi, n)
+    j = n // 2
+    half = np.arcsin(np.minimum(reach / np.maximum(dist, reach), 1.0))
+    dth[j:j + k] = ang[j:j + k] + rng.choice([-1.0, 1.0], k) * half[j:j + k] * (1 + rng.uniform(-1e-8, 1e-8, k))  # cone edges
+    dth[j + k:j + k + 3000] = rng.choice([0.0, math.pi, -math.pi], 3000) + rng.uniform(-1e-10, 1e-10, 3000)       # x axis
+    d = rng.uniform(0.1, 50, n)[:, None] * np.stack([np.cos(dth), np.sin(dth)], 1)
+    d[j + k + 3000:j + k + 3500, 1] = 0.0
+    fast, slow, mode = (np.empty(n, np.int32) for _ in range(3))
+    mathlib.mc_rvo_inside(np.ascontiguousarray(pA), np.ascontiguousarray(pB), reach, np.ascontiguousarray(d), fast, slow, mode, n)
+    ans = fast >= 0
+    assert np.array_equal(fast[ans], slow[ans])
+    assert ans[k + 2000:j].mean() > 0.97          # on ordinary cones the shortcut carries the load ...
+    assert (fast[j:j + k] < 0).any()              # ... and hands the edge cases to atan2
+    assert set(np.unique(mode)) >= {0, 1, 2, 4}
 
 
 def test_obstacle_density_matches_reference_golden():
