@@ -561,7 +561,7 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
     elif pk["planner"] == "NoMove":
         kernel_name = "d2d_step_fused_warp_kernel (1 launch/step)"
     else:
-        kernel_name = "d2d_step_prim_warp_kernel + d2d_plan_kernel + d2d_step_post_list_kernel" + \
+        kernel_name = "d2d_step_prim_warp_kernel + d2d_plan_small_kernel (+ d2d_plan_kernel for its overflow list) + d2d_step_post_list_kernel" + \
                       (" + d2d_oxford_kernel" if use_ox else "") + " (whole step timed)"
     achieved = algorithmic_bytes(N) * B / (ms_step * 1e-3) / 1e9
     traffic = None
@@ -619,6 +619,8 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
              "flight_steps", "grid_discovered", "agents_tracked", "tracked_steps", "plans", "plan_failures", "replans"],
             stats.tolist()[:14])},
     }
+    if pk["planner"] == "Primitive":
+        res["episode_stats"]["plan_overflows"] = int(stats.tolist()[15])     # searches redone by the large A* kernel
     if rollout:
         res["single_step_launches"] = {
             "value": world * B / (ms_launch_per_step * 1e-3), "ms_per_step": ms_launch_per_step, "gpu_launches": int(launches),

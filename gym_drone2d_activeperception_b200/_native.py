@@ -13,7 +13,7 @@ POLICY_OXFORD, POLICY_OWL, MAX_OWL_U = 1, 2, 32
 BELIEF_STRIDE = 2560
 STAT_NAMES = ["env_steps", "episodes", "success", "static_collision", "dynamic_collision", "freezing", "dead_lock",
               "flight_steps", "grid_discovered", "agents_tracked", "tracked_steps", "plans", "plan_failures", "replans",
-              "mirror_bytes", "reserved15"]
+              "mirror_bytes", "plan_overflows"]
 
 
 class D2DConfig(C.Structure):

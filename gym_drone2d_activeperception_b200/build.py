@@ -42,5 +42,18 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, extra_flags):
+    """An A/B build of the same ABI next to the product library (selected at run time with D2D_LIB=<path>), e.g.
+    build_variant("psmall40", ["-DD2D_PS_NODES=40", "-DD2D_PS_HASH=128"]): nearly every A* search overflows the
+    small-footprint kernel and is redone by d2d_plan_kernel."""
+    out = os.path.join(HERE, "libdrone2d_%s.so" % name)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

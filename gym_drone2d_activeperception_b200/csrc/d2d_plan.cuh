@@ -43,6 +43,12 @@ __device__ __forceinline__ int d2d_belief_probe(const DevP &P, const uint8_t *be
     return bel[d2d_cell(x, P.scale, P.inv_scale) * D2D_GRID + d2d_cell(y, P.scale, P.inv_scale)];
 }
 
+// the same probe for integer-valued coordinates (A* samples, np.around at traj_planner.py:181): cells by integer arithmetic
+__device__ __forceinline__ int d2d_belief_probe_int(const uint8_t *bel, int x, int y, int w, int h) {
+    if (x >= w || x < 0 || y >= h || y < 0) return 1;            // utils.py:546-547
+    return bel[(x / 10) * D2D_GRID + (y / 10)];
+}
+
 // Planner.is_free (traj_planner.py:28-59); trk = active trackers as [mu0, mu1, mu2, mu3, radius]
 __device__ __forceinline__ bool d2d_is_free(const DevP &P, const uint8_t *bel, double px, double py, double t,
                                             const double *trk, int nact) {
@@ -235,7 +241,8 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     const int par = P.plan_list[P.B + 3] & 1;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.plan_list[P.B + 4] = par; P.plan_list[P.B + 1 + (par ^ 1)] = 0;
-        P.plan_list[P.B + 5] = 0;                                            // ticket counter of d2d_plan_kernel
+        P.plan_list[P.B + 5] = 0;                                            // ticket counter of the A* kernels
+        P.plan_over[P.B] = 0; P.plan_over[P.B + 1] = 0;                      // overflow list of d2d_plan_small_kernel: count, ticket
         atomicAdd(&P.stats[D2D_STAT_ENV_STEPS], (unsigned long long)P.B);    // every env steps once per d2d_step
     }
 
@@ -313,10 +320,43 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     }
     __syncwarp();
     const bool need = (s.nseg * P.n_way - s.cursor) == 0;
+    // A search whose start position is itself not free ends after one expansion: sample 0 of EVERY primitive is the start
+    // position at global time 0 (t = arange(0, 2, ...)[0], traj_planner.py:179-183), so no successor is added, the open set
+    // is empty and plan() returns False (:149-153) -- unless the start already lies within the goal threshold (:160).  74 %
+    // of the searches of BASELINE config 3 and 44 % of config 4 are of this kind; they get their verdict right here, with
+    // the belief grid and the trackers in shared memory, instead of a slot of d2d_plan_kernel + d2d_step_post_list_kernel.
+    bool blocked = false;
+    if (need && !d2d_norm2_le(s.px - s.tgx, s.py - s.tgy, 10.0)) {
+        const double qx = rint(s.px), qy = rint(s.py);
+        bool occ = false;
+        if (qx != qx || qy != qy || !(fabs(qx) < 1e6 && fabs(qy) < 1e6)) occ = true;
+        else {
+            if (lane < 5) {       // Planner.is_free's five probes (traj_planner.py:35-47), one per lane
+                const int sd = (int)(P.drone_r + 10.0), x = (int)qx + (lane == 0 ? -sd : (lane == 2 ? sd : 0)),
+                          y = (int)qy + (lane == 3 ? -sd : (lane == 4 ? sd : 0));
+                occ = d2d_belief_probe_int(c.belief, x, y, (int)P.map_w, (int)P.map_h) == 1;
+            }
+#pragma unroll 1
+            for (int k = lane; k < na; k += 32) {
+                const double *m = trk + 5 * k;
+                const double ex = m[0] + 0.0 * m[2], ey = m[1] + 0.0 * m[3];            // estimate_pos(0) utils.py:220-223
+                if (d2d_norm2_le(qx - ex, qy - ey, P.drone_r + m[4] + 5.0 + P.var_cam)) occ = true;
+            }
+        }
+        blocked = __any_sync(0xffffffffu, occ);
+    }
     __syncwarp();                 // every lane has read the trajectory length before lane 0 pops a waypoint (step_pos)
-    if (!need) {
-        if (lane == 0) P.need_plan[e] = 0;
-        d2d_finish_env_warp(P, c, s, e, lane, action, true, true, cnt[1], chg, true);
+    if (!need || blocked) {
+        if (lane == 0) {
+            P.need_plan[e] = blocked ? 1 : 0;
+            if (blocked) {
+                s.nseg = 0; s.cursor = 0; P.plan_ok[e] = 0;
+                atomicAdd(&P.stats[D2D_STAT_PLANS], 1ull);
+                atomicAdd(&P.stats[D2D_STAT_PLAN_FAILURES], 1ull);
+            }
+        }
+        __syncwarp();
+        d2d_finish_env_warp(P, c, s, e, lane, action, !blocked, true, cnt[1], chg, true);
     } else {
         if (lane == 0) {
             P.need_plan[e] = 1;
@@ -627,10 +667,6 @@ __device__ __forceinline__ double d2d_sq_threshold(double R) {
 
 // Planner.is_free (traj_planner.py:28-59) for the A* samples, whose coordinates are integer-valued doubles
 // (np.around, traj_planner.py:181): cells by integer arithmetic.  trk = [mu0, mu1, mu2, mu3, radius, T] per tracker.
-__device__ __forceinline__ int d2d_belief_probe_int(const uint8_t *bel, int x, int y, int w, int h) {
-    if (x >= w || x < 0 || y >= h || y < 0) return 1;            // utils.py:546-547
-    return bel[(x / 10) * D2D_GRID + (y / 10)];
-}
 __device__ __forceinline__ bool d2d_is_free_int(const DevP &P, const uint8_t *bel, double px, double py, double t,
                                                 const double *trk6, int nact) {
     if (px != px || py != py) return false;
@@ -708,7 +744,8 @@ __device__ __forceinline__ int d2d_plan_find_or_insert(const PlanHot &h, const P
 }
 
 #define D2D_PLAN_THREADS2 256
-__global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP P) {
+// mode 0: the step's planning list (plan_list); mode 1: the searches d2d_plan_small_kernel abandoned (plan_over)
+__global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP P, const int mode) {
     extern __shared__ __align__(16) unsigned char psm[];
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = T >> 5;
     const int nu = P.n_u, nprim = nu * nu, nsamp = P.n_samp;
@@ -733,7 +770,10 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
         h.open_total = w.open_total; h.cost = w.cost; h.hkeys32 = nullptr; h.hvals16 = nullptr;
         h.hkeys64 = w.hkeys; h.hvals32 = w.hvals; h.hcap = w.hcap;
     }
-    const int count = min(P.plan_list[P.B + (P.use_parity ? 1 + P.plan_list[P.B + 4] : 0)], P.B);
+    const int *list = mode ? P.plan_over : P.plan_list;
+    int *ticket = mode ? &P.plan_over[P.B + 1] : &P.plan_list[P.B + 5];
+    const int count = mode ? min(P.plan_over[P.B], P.B)
+                           : min(P.plan_list[P.B + (P.use_parity ? 1 + P.plan_list[P.B + 4] : 0)], P.B);
 
     // Searches differ widely in length (1 .. 99 expansions), so the list entries are handed out dynamically: a block takes
     // the next one when it is done (ticket counter plan_list[B+5], zeroed by the step kernel that fills the list).  With
@@ -741,11 +781,11 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
     // every search is self-contained in the block's own workspace.
     for (;;) {
         __syncthreads();
-        if (tid == 0) sh[7] = atomicAdd(&P.plan_list[P.B + 5], 1);      // sh[7]: this block's ticket
+        if (tid == 0) sh[7] = atomicAdd(ticket, 1);                     // sh[7]: this block's ticket
         __syncthreads();
         const int li = sh[7];
         if (li >= count) break;
-        const int e = P.plan_list[li];
+        const int e = list[li];
         for (int o = tid; o < D2D_BELIEF_STRIDE / 4; o += T)
             ((uint32_t *)bel)[o] = ((const uint32_t *)(P.belief + (size_t)e * D2D_BELIEF_STRIDE))[o];
         if (h.fast) {
@@ -927,6 +967,326 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
             } else {
                 P.rec[e].nseg = 0; P.rec[e].cursor = 0; P.plan_ok[e] = 0;
                 atomicAdd(&P.stats[D2D_STAT_PLAN_FAILURES], 1ull);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ A* kernel, small footprint
+// The same search with EVERYTHING in shared memory, sized for what the searches actually need: on BASELINE configs 3 and 4 no
+// search of 5.6e4 sampled ones (instrumented oracle run) holds more than 384 nodes, while d2d_plan_kernel reserves room for the
+// worst case (99 expansions x 64 primitives = 6336 nodes, 104 KB of shared memory: two searches per SM, 16 warps, schedulers
+// issuing 30 % of the time, every expansion paying two L2 round trips for the cold node fields).  Here a search holds
+// D2D_PS_NODES nodes (all fields) and a D2D_PS_HASH-slot dict in ~37 KB, runs on 4 warps, and six of them share an SM.  A
+// search that would need a 513th node is abandoned and appended to the overflow list, which d2d_plan_kernel (mode 1) works
+// off right afterwards -- every search is self-contained, so who runs it does not matter.
+//   * an expansion is a latency chain and the failed 99-expansion searches set the length of the kernel, so the chain is short:
+//     two block barriers per expansion; every warp first lists the primitives that pass the speed test (typically 10-15 of the
+//     64 -- the others used to occupy lanes that did nothing), then one (feasible primitive, sample) pair per thread with the five
+//     belief probes in flight together; warp 0 alone inserts the successors and picks the next node;
+//   * trackers that cannot come near ANY sample of this expansion are dropped from the test per warp: a primitive that passes
+//     the speed test (:176) has |v(t)| <= max(|v(0)|, v_max) (|v| is convex along it), so its samples stay within
+//     2 max(|v0|, v_max) + 0.71 (rounding) of the node, a tracker estimate moves 2 |v_trk| in the same 2 s, and the test is
+//     only skipped when the clearance at the node's time exceeds all that by a further whole unit.
+#define D2D_PS_THREADS 128
+#ifndef D2D_PS_NODES             // -DD2D_PS_NODES=40 -DD2D_PS_HASH=128: test build in which most searches overflow
+#define D2D_PS_NODES 512
+#define D2D_PS_HASH 1024
+#endif
+#define D2D_PS_MINB 6
+
+__host__ __device__ inline bool d2d_plan_small_ok(int n_u, double max_speed) {
+    return n_u * n_u <= 64 && n_u <= 8 && max_speed < 60.0;      // key32 needs |v| < 64
+}
+__host__ __device__ inline size_t d2d_plan_small_smem_bytes(int NP) {
+    const size_t NPe = (size_t)(NP + 7) / 8 * 8;
+    size_t b = D2D_BELIEF_STRIDE + NPe * 6 * 8 + (size_t)D2D_PS_NODES * 6 * 8 + (8 + 2 * D2D_MAX_SAMP) * 8       // doubles
+             + (size_t)D2D_PS_HASH * 4 + 8 * 4                                                                    // words
+             + (size_t)D2D_PS_HASH * 2 + (size_t)D2D_PS_NODES * 2 + (D2D_PS_THREADS / 32) * NPe * 2               // halves
+             + (size_t)D2D_PS_NODES * 2 + 64 + (D2D_PS_THREADS / 32) * 64;                                        // bytes
+    return (b + 15) / 16 * 16;
+}
+
+// the five belief probes of Planner.is_free (traj_planner.py:35-47) with all loads in flight: 1 if any of them reads OCCUPIED
+// (outside the map counts as occupied, utils.py:546-547)
+__device__ __forceinline__ int d2d_probe5_occ(const uint8_t *bel, int x, int y, int sd, int w, int h) {
+    const int xm = x - sd, xp = x + sd, ym = y - sd, yp = y + sd;
+    if (xm < 0 || xp < 0 || xm >= w || xp >= w || ym < 0 || yp < 0 || ym >= h || yp >= h)       // a probe may leave the map
+        return (d2d_belief_probe_int(bel, xm, y, w, h) == 1) | (d2d_belief_probe_int(bel, x, y, w, h) == 1) |
+               (d2d_belief_probe_int(bel, xp, y, w, h) == 1) | (d2d_belief_probe_int(bel, x, ym, w, h) == 1) |
+               (d2d_belief_probe_int(bel, x, yp, w, h) == 1);
+    const int cx = (x / 10) * D2D_GRID, cy = y / 10;
+    const int a = bel[(xm / 10) * D2D_GRID + cy], b = bel[cx + cy], c = bel[(xp / 10) * D2D_GRID + cy];
+    const int d = bel[cx + ym / 10], f = bel[cx + yp / 10];
+    return (a == 1) | (b == 1) | (c == 1) | (d == 1) | (f == 1);
+}
+
+__global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_kernel(const DevP P) {
+    extern __shared__ __align__(16) unsigned char psm[];
+    constexpr int T = D2D_PS_THREADS, NW = T / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nu = P.n_u, nprim = nu * nu, nsamp = P.n_samp;
+    const int NPe = (P.NP + 7) / 8 * 8;
+    unsigned char *q8 = psm;
+    uint8_t *bel = q8; q8 += D2D_BELIEF_STRIDE;                          // [2560]
+    double *trk = (double *)q8; q8 += (size_t)NPe * 48;                  // [NP][6]
+    double *n_px = (double *)q8; q8 += (size_t)D2D_PS_NODES * 48;        // node fields, SoA
+    double *n_py = n_px + D2D_PS_NODES, *n_vx = n_py + D2D_PS_NODES, *n_vy = n_vx + D2D_PS_NODES;
+    double *n_cost = n_vy + D2D_PS_NODES, *n_open_total = n_cost + D2D_PS_NODES;   // open_total: +inf once closed
+    double *uh = (double *)q8; q8 += 8 * 8;                              // u_space / 2
+    double *ts = (double *)q8; q8 += (size_t)D2D_MAX_SAMP * 8;
+    double *ts2 = (double *)q8; q8 += (size_t)D2D_MAX_SAMP * 8;
+    uint32_t *hkeys = (uint32_t *)q8; q8 += (size_t)D2D_PS_HASH * 4;
+    int *sh = (int *)q8; q8 += 8 * 4;                                    // [0] next node, [1] nodes, [2] open, [3] overflow, [4] nact, [7] ticket
+    uint16_t *hvals = (uint16_t *)q8; q8 += (size_t)D2D_PS_HASH * 2;
+    uint16_t *n_parent = (uint16_t *)q8; q8 += (size_t)D2D_PS_NODES * 2;
+    uint16_t *live = (uint16_t *)q8 + (size_t)wid * NPe; q8 += (size_t)NW * NPe * 2;   // this warp's tracker list
+    uint8_t *n_itr = q8; q8 += D2D_PS_NODES;
+    uint8_t *n_act = q8; q8 += D2D_PS_NODES;
+    uint8_t *vok = q8; q8 += 64;                                         // [64] verdict per speed-feasible primitive (by rank)
+    uint8_t *vlist = q8 + (size_t)wid * 64;                              // [NW][64] this warp's list of speed-feasible primitives
+
+    for (int i = tid; i < nu; i += T) uh[i] = P.tab->u_space[i] / 2.0;
+    for (int i = tid; i < nsamp; i += T) { ts[i] = P.tab->t_samp[i]; ts2[i] = P.tab->t_samp2[i]; }
+    const int count = min(P.plan_list[P.B + (P.use_parity ? 1 + P.plan_list[P.B + 4] : 0)], P.B);
+    // norm([nvx, nvy]) < max_speed  <=>  fma(nvy, nvy, nvx*nvx) <= speed_thr   (exact, no sqrt per item)
+    const double speed_thr = d2d_sq_threshold(__longlong_as_double(__double_as_longlong(P.max_speed) - 1));
+    const int p_sd = (int)(P.drone_r + 10.0), p_w = (int)P.map_w, p_h = (int)P.map_h;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sh[7] = atomicAdd(&P.plan_list[P.B + 5], 1);      // next list entry (see d2d_plan_kernel)
+        __syncthreads();
+        const int li = sh[7];
+        if (li >= count) break;
+        const int e = P.plan_list[li];
+#ifdef D2D_PLAN_PROF
+        unsigned long long prof_t0 = 0;
+        if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_t0));
+#endif
+        for (int o = tid; o < D2D_BELIEF_STRIDE / 4; o += T)
+            ((uint32_t *)bel)[o] = ((const uint32_t *)(P.belief + (size_t)e * D2D_BELIEF_STRIDE))[o];
+        for (int o = tid; o < D2D_PS_HASH; o += T) hkeys[o] = D2D_HASH32_EMPTY;
+        if (tid == 0) sh[4] = 0;
+        __syncthreads();
+#pragma unroll 1
+        for (int k = tid; k < P.N; k += T) {        // active trackers + the exact squared clearance threshold
+            const size_t g = (size_t)e * P.NP + k;
+            if (P.trk_active[g]) {
+                const int slot = atomicAdd(&sh[4], 1);
+                const double *mu = P.trk_mu + g * 4;
+                double *d = trk + 6 * slot;
+                const double rad = P.trk_radius[g];
+                const double clr = P.drone_r + rad + 5.0 + P.var_cam;
+                d[0] = mu[0]; d[1] = mu[1]; d[2] = mu[2]; d[3] = mu[3];
+                d[4] = clr + 2.0 * d2d_norm2(mu[2], mu[3]) + 1.0;       // + how far the estimate moves in 2 s + a whole unit of margin
+                d[5] = d2d_sq_threshold(clr);
+            }
+        }
+        const double tx = P.rec[e].tgx, ty = P.rec[e].tgy;
+        if (tid == 0) {   // start node (traj_planner.py:136-146)
+            const double x = P.rec[e].px, y = P.rec[e].py, vx = P.rec[e].vx, vy = P.rec[e].vy;
+            n_px[0] = x; n_py[0] = y; n_vx[0] = vx; n_vy[0] = vy; n_cost[0] = 0.0;
+            n_open_total[0] = d2d_node_total(0.0, x, y, vx, vy, tx, ty);
+            n_parent[0] = 0; n_itr[0] = 0; n_act[0] = 0;
+            const uint32_t key = d2d_node_key32(x, y, vx, vy);
+            const int s0 = (int)((key * 2654435761u) >> 19) & (D2D_PS_HASH - 1);
+            hkeys[s0] = key; hvals[s0] = 0;
+            sh[0] = 0; sh[1] = 1; sh[2] = 1; sh[3] = 0;          // next node, nodes, open nodes, overflow
+        }
+        if (tid < 64) vok[tid] = 1;
+        __syncthreads();
+        const int nact = sh[4];
+        int goal = -1;
+        bool success = false, overflow = false;
+        int n_nodes = 1, n_open = 1;                     // kept by warp 0, published through sh[1], sh[2] at the end of an expansion
+        int itr = 1;
+        // An expansion is a latency chain, and the failed 99-expansion searches set the length of the kernel, so the chain is
+        // kept short: two block barriers per expansion.  Between (B) and (A) every warp tests samples; between (A) and (B) warp 0
+        // alone closes the node, inserts the successors and picks the next node (sh[0]) while the others wait.
+        for (;; itr++) {
+            if (n_open == 0 || itr >= 100) break;                // traj_planner.py:149
+            const int cur = sh[0];                               // first minimal total_cost in insertion order (:155-158)
+            if (cur == 0x7fffffff) break;                        // only non-finite costs left (cannot happen)
+            const double cpx = n_px[cur], cpy = n_py[cur], cvx = n_vx[cur], cvy = n_vy[cur];
+            const int citr = n_itr[cur];
+            if (d2d_norm2_le(cpx - tx, cpy - ty, 10.0)) {        // :160
+                goal = cur; success = true; break;
+            }
+            const double gt0 = (double)(citr * 2);
+            // ---- per warp (no barrier): the primitives that pass the speed test (:176), in primitive order.  Typically 10-15
+            //      of the 64 do; only their samples are tested, one (primitive, sample) pair per thread.
+            int nv = 0;
+#pragma unroll 1
+            for (int base = 0; base < nprim; base += 32) {
+                const int pp = base + lane;
+                bool pass = false;
+                if (pp < nprim) {
+                    const int ia = d2d_div_small(pp, nu), ib = pp - ia * nu;
+                    const double nvx = 1.0 * cvx + 4.0 * uh[ia], nvy = 1.0 * cvy + 4.0 * uh[ib];
+                    pass = D2D_FMA(nvy, nvy, nvx * nvx) <= speed_thr;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) vlist[nv + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)pp;
+                nv += __popc(bal);
+            }
+            // ---- per warp: the trackers that can come near a sample of this expansion (see the kernel's header)
+            int nlive = 0;
+            {
+                const double c2 = D2D_FMA(cvy, cvy, cvx * cvx);
+                const double reach = 2.0 * (c2 <= P.max_speed * P.max_speed ? P.max_speed : d2d_sqrt(c2) + 1e-6) + 0.71;
+#pragma unroll 1
+                for (int base = 0; base < nact; base += 32) {
+                    const int k = base + lane;
+                    bool keep = false;
+                    if (k < nact) {
+                        const double *m = trk + 6 * k;
+                        const double ddx = cpx - (m[0] + gt0 * m[2]), ddy = cpy - (m[1] + gt0 * m[3]);
+                        const double lim = reach + m[4];             // m[4] = clearance + 2 |v_trk| + 1
+                        keep = !(D2D_FMA(ddy, ddy, ddx * ddx) > lim * lim);
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                    if (keep) live[nlive + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)k;
+                    nlive += __popc(bal);
+                }
+            }
+            __syncwarp();
+            // ---- collision checks of the (primitive, sample) pairs (:174-185); vok[r]: primitive vlist[r] is still free
+            const int nit = nv * nsamp;
+#pragma unroll 1
+            for (int q = tid; q < nit; q += T) {
+                const int sI = d2d_div_small(q, nv), r = q - sI * nv;
+                if (!vok[r]) continue;                           // another sample of the primitive already failed
+                const int pp = vlist[r];
+                const int ia = d2d_div_small(pp, nu), ib = pp - ia * nu;
+                const double xh = uh[ia], yh = uh[ib];
+                const double t = ts[sI], t2 = ts2[sI];
+                const double qx = rint(D2D_FMA(t2, xh, 1.0 * cpx + t * cvx));
+                const double qy = rint(D2D_FMA(t2, yh, 1.0 * cpy + t * cvy));
+                const double tg = t + gt0;
+                bool occ = !(fabs(qx) < 1e6 && fabs(qy) < 1e6);  // NaN or far outside the map: every probe reads OCCUPIED
+                if (!occ) occ = d2d_probe5_occ(bel, (int)qx, (int)qy, p_sd, p_w, p_h) != 0;
+#pragma unroll 1
+                for (int jj = 0; jj < nlive && !occ; jj++) {
+                    const double *m = trk + 6 * (int)live[jj];
+                    const double ex = m[0] + tg * m[2], ey = m[1] + tg * m[3];   // estimate_pos utils.py:220-223
+                    const double ddx = qx - ex, ddy = qy - ey;
+                    occ = D2D_FMA(ddy, ddy, ddx * ddx) <= m[5];                  // norm(...) <= drone_r + radius + 5 + var_cam
+                }
+                if (occ) vok[r] = 0;
+            }
+            __syncthreads();                                     // (A) verdicts of all samples in place
+            if (wid == 0) {
+                if (lane == 0) n_open_total[cur] = INFINITY;     // open -> closed (:167-170)
+                n_open -= 1;
+                const double ccost = n_cost[cur];
+                __syncwarp();
+                // ---- successors in (x_acc, y_acc) loop order (:187-206): vlist is in that order, 32 per round
+#pragma unroll 1
+                for (int base = 0; base < nv; base += 32) {
+                    const int r = base + lane;
+                    const bool ok = r < nv && vok[r];
+                    double nvx = 0, nvy = 0, spx = 0, spy = 0, scost = 0;
+                    int slot = -1, exist_idx = -1, pp = 0;
+                    bool is_new = false;
+                    if (ok) {
+                        pp = vlist[r];
+                        const int ia = d2d_div_small(pp, nu), ib = pp - ia * nu;
+                        const double xa = P.tab->u_space[ia], ya = P.tab->u_space[ib];
+                        nvx = 1.0 * cvx + 4.0 * (xa / 2.0);
+                        nvy = 1.0 * cvy + 4.0 * (ya / 2.0);
+                        spx = rint((1.0 * cpx + 2.0 * cvx) + 4.0 * (xa / 2.0));   // :188
+                        spy = rint((1.0 * cpy + 2.0 * cvy) + 4.0 * (ya / 2.0));
+                        scost = ccost + (xa * xa + ya * ya) / 100.0 + 10.0;      // :190
+                        const uint32_t key = d2d_node_key32(spx, spy, nvx, nvy);
+                        int s = (int)((key * 2654435761u) >> 19) & (D2D_PS_HASH - 1);
+                        for (;;) {
+                            const uint32_t curk = hkeys[s];
+                            if (curk == key) { exist_idx = hvals[s]; break; }
+                            if (curk == D2D_HASH32_EMPTY) {
+                                const uint32_t old = atomicCAS(&hkeys[s], D2D_HASH32_EMPTY, key);
+                                if (old == D2D_HASH32_EMPTY) { is_new = true; break; }
+                                if (old == key) { exist_idx = hvals[s]; break; }
+                            }
+                            s = (s + 1) & (D2D_PS_HASH - 1);
+                        }
+                        slot = s;
+                    }
+                    // ordered slot assignment for the new nodes (insertion order == primitive order)
+                    const unsigned bal = __ballot_sync(0xffffffffu, is_new);
+                    const int tot_new = __popc(bal);
+                    if (n_nodes + tot_new > D2D_PS_NODES) { overflow = true; break; }    // same verdict in every lane
+                    int idx = -1;
+                    if (is_new) {
+                        idx = n_nodes + __popc(bal & ((1u << lane) - 1u));
+                        hvals[slot] = (uint16_t)idx;
+                    } else if (ok) {
+                        // in closed_set -> skip; in open_set -> replace if cheaper, keeping the dict slot (:197-206)
+                        if (n_open_total[exist_idx] != INFINITY && n_cost[exist_idx] > scost) idx = exist_idx;
+                    }
+                    if (idx >= 0) {
+                        n_px[idx] = spx; n_py[idx] = spy; n_vx[idx] = nvx; n_vy[idx] = nvy; n_cost[idx] = scost;
+                        n_open_total[idx] = d2d_node_total(scost, spx, spy, nvx, nvy, tx, ty);
+                        n_parent[idx] = (uint16_t)cur; n_itr[idx] = (uint8_t)(citr + 1); n_act[idx] = (uint8_t)pp;
+                    }
+                    n_nodes += tot_new; n_open += tot_new;
+                }
+                vok[lane] = 1; vok[lane + 32] = 1;               // every primitive starts the next expansion as free
+                __syncwarp();
+                // ---- next node: first minimal total_cost in insertion order (min() over a dict, :155-158)
+                double bv = INFINITY;
+                int bi = 0x7fffffff;
+#pragma unroll 1
+                for (int i = lane; i < n_nodes; i += 32) {
+                    const double v = n_open_total[i];
+                    if (v < bv) { bv = v; bi = i; }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                if (lane == 0) { sh[0] = bi; sh[1] = n_nodes; sh[2] = n_open; sh[3] = overflow ? 1 : 0; }
+            }
+            __syncthreads();                                     // (B) next node, counts and the overflow flag published
+            n_nodes = sh[1]; n_open = sh[2];
+            if (sh[3]) { overflow = true; break; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+#ifdef D2D_PLAN_PROF
+            // tools/plan_prof.py: per search start / end (ns), nodes, outcome, SM, ticket
+            unsigned long long t1; unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            unsigned long long *pr = P.prof + (size_t)e * 12;
+            pr[0] = prof_t0; pr[1] = t1; pr[2] = (unsigned long long)n_nodes; pr[3] = success ? 1 : (overflow ? 2 : 0);
+            pr[4] = smid; pr[5] = (unsigned long long)li; pr[6] = (unsigned long long)n_open; pr[7] = (unsigned long long)nact; pr[8] = (unsigned long long)itr;
+#endif
+            if (overflow) {
+                P.plan_over[atomicAdd(&P.plan_over[P.B], 1)] = e;        // d2d_plan_kernel (mode 1) redoes this search
+                atomicAdd(&P.stats[D2D_STAT_PLAN_OVERFLOWS], 1ull);
+            } else {
+                atomicAdd(&P.stats[D2D_STAT_PLANS], 1ull);
+                if (success) {
+                    // segments from the start outwards (the reference walks parents and reverses, :208-217)
+                    int depth = 0;
+                    for (int c2 = goal; c2 != 0; c2 = n_parent[c2]) depth++;
+                    int seg = depth;
+                    for (int c2 = goal; c2 != 0; c2 = n_parent[c2]) {
+                        seg--;
+                        const int par = n_parent[c2], pidx = n_act[c2];
+                        const int ia = d2d_div_small(pidx, nu), ib = pidx - ia * nu;
+                        double *cf = P.traj_coeff + ((size_t)e * D2D_MAX_SEGMENTS + seg) * 6;
+                        cf[0] = n_px[par]; cf[1] = n_vx[par]; cf[2] = P.tab->u_space[ia] / 2.0;
+                        cf[3] = n_py[par]; cf[4] = n_vy[par]; cf[5] = P.tab->u_space[ib] / 2.0;
+                    }
+                    P.rec[e].nseg = depth; P.rec[e].cursor = 0; P.plan_ok[e] = 1;
+                } else {
+                    P.rec[e].nseg = 0; P.rec[e].cursor = 0; P.plan_ok[e] = 0;
+                    atomicAdd(&P.stats[D2D_STAT_PLAN_FAILURES], 1ull);
+                }
             }
         }
     }

@@ -19,7 +19,27 @@ static int launch_prim_warp(d2d_handle *h, const double *actions, cudaStream_t s
     h->P.use_parity = 1;
     d2d_step_prim_warp_kernel<WPB><<<(h->B + WPB - 1) / WPB, WPB * 32, smem, st>>>(h->P, actions);
     const int pgrid = h->B < D2D_PLAN_SLOTS ? h->B : D2D_PLAN_SLOTS;
-    d2d_plan_kernel<<<pgrid, D2D_PLAN_THREADS2, h->smem_plan, st>>>(h->P);
+    if (h->plan_small < 0) {
+        // the small-footprint A* kernel runs first wherever its packed keys are valid (D2D_PLAN_SMALL=0: A/B switch)
+        const char *ev = getenv("D2D_PLAN_SMALL");
+        h->plan_small = 0;
+        if (d2d_plan_small_ok(h->cfg.n_u, h->cfg.drone_max_speed) && !(ev && ev[0] == '0')) {
+            const size_t ssm = d2d_plan_small_smem_bytes(h->NP);
+            int per_sm = 0, sms = 0;
+            if (ssm <= 227 * 1024 && ensure_smem_attr(h, (const void *)d2d_plan_small_kernel, "plan small") == D2D_OK &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, d2d_plan_small_kernel, D2D_PS_THREADS, ssm) == cudaSuccess &&
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device) == cudaSuccess && per_sm > 0)
+                h->plan_small = per_sm * sms;
+        }
+    }
+    if (h->plan_small > 0) {
+        const int sgrid = h->B < h->plan_small ? h->B : h->plan_small;
+        d2d_plan_small_kernel<<<sgrid, D2D_PS_THREADS, d2d_plan_small_smem_bytes(h->NP), st>>>(h->P);
+        d2d_plan_kernel<<<pgrid, D2D_PLAN_THREADS2, h->smem_plan, st>>>(h->P, 1);      // the abandoned searches, if any
+        h->launches++;
+    } else {
+        d2d_plan_kernel<<<pgrid, D2D_PLAN_THREADS2, h->smem_plan, st>>>(h->P, 0);
+    }
     const int lgrid = (h->B + 3) / 4 < 148 * 4 ? (h->B + 3) / 4 : 148 * 4;
     d2d_step_post_list_kernel<4><<<lgrid, 128, 4 * d2d_warp_slice_bytes(1, 1, 0), st>>>(h->P, actions);
     h->launches += 3;
@@ -40,7 +60,7 @@ static int step_primitive(d2d_handle *h, const double *actions, cudaStream_t st)
         const int rca = ensure_smem_attr(h, (const void *)d2d_plan_kernel, "plan");
         if (rca != D2D_OK) return rca;
         const int grid = h->B < D2D_PLAN_SLOTS ? h->B : D2D_PLAN_SLOTS;
-        d2d_plan_kernel<<<grid, D2D_PLAN_THREADS2, h->smem_plan, st>>>(h->P);
+        d2d_plan_kernel<<<grid, D2D_PLAN_THREADS2, h->smem_plan, st>>>(h->P, 0);
         h->launches++;
     }
     {

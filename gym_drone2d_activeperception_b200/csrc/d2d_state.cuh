@@ -94,7 +94,7 @@ struct DevP {
     // the step's actions out of the caller's pinned buffer itself -- no copy-engine transfer, no driver call per step
     const unsigned long long *gate_src;          // device-visible address of the caller's pinned action buffer (null: copy engine)
     const unsigned long long *gate_stamp_host;   // device-visible address of the pinned stamp word the host stores per step
-#ifdef D2D_WARP_PROF
+#if defined(D2D_WARP_PROF) || defined(D2D_PLAN_PROF)
     unsigned long long *prof;    // [B][12]: 10 globaltimer stamps, smid, warpid of the fused warp kernel (tools/warp_prof.py builds with -DD2D_WARP_PROF)
 #endif
     float *reward;               // [B] zeros (drone_v2.py:257)
@@ -130,5 +130,6 @@ struct DevP {
     unsigned char *plan_ws;      // A* workspaces (Primitive planner)
     int *plan_list;              // [B+8]: compacted list of envs that need a plan; [B] count (block path); [B+1], [B+2]
                                  // double-buffered counts, [B+3] step counter, [B+4] this step's parity (warp path)
+    int *plan_over;              // [B+8]: searches abandoned by d2d_plan_small_kernel (node capacity); [B] count, [B+1] ticket
     const DevTables *tab;
 };

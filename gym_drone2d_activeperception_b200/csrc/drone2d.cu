@@ -47,6 +47,7 @@ struct d2d_handle {
     uint8_t *mir_lm = nullptr; float *mir_yaw = nullptr; uint8_t *mir_done = nullptr;
     bool mir_stale = true;
     size_t smem_pre = 0, smem_plan = 0;
+    int plan_small = -1;                 // d2d_plan_small_kernel: -1 not decided yet, 0 off, > 0 grid size (co-resident blocks)
     std::vector<const void *> attr_funcs;   // kernels whose dynamic shared-memory limit this handle has raised
     // bound host path (d2d_bind_host_io)
     bool io_bound = false;
@@ -378,6 +379,7 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
         o_plan_ws = add_buf(h, cur, "plan_workspace", D2D_U8, 1, SHP((int64_t)plan_ws_bytes), SHP(1), plan_ws_bytes);
     }
     size_t o_plan_list = add_buf(h, cur, "plan_list", D2D_I32, 1, SHP(B + 8), SHP(1), sB + 8);
+    size_t o_plan_over = add_buf(h, cur, "plan_overflow", D2D_I32, 1, SHP(B + 8), SHP(1), sB + 8);
 #undef SHP
     h->arena_bytes = (cur + 255) / 256 * 256;
     ce = cudaMalloc((void **)&h->arena, h->arena_bytes);
@@ -431,7 +433,7 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.jerk = cfg->planner == D2D_PLANNER_JERK ? (const d2d_jerk_tables *)(A + o_jerk) : nullptr;
     P.ox_calls = (int *)(A + o_oxc); P.ox_tab = (const double *)(A + o_oxt); P.ox_last = nullptr;
     P.lm_mirror = nullptr; P.yaw_mirror = nullptr; P.done_mirror = nullptr;
-#ifdef D2D_WARP_PROF
+#if defined(D2D_WARP_PROF) || defined(D2D_PLAN_PROF)
     cudaMalloc((void **)&P.prof, (size_t)B * 96); cudaMemset(P.prof, 0, (size_t)B * 96);
 #endif
     P.tmp_act_cnt = (int *)(A + o_tac); P.tmp_act_ts = (int *)(A + o_tat);
@@ -443,6 +445,7 @@ extern "C" int d2d_create(const d2d_config *cfg, d2d_handle **out) {
     P.tab = (const DevTables *)(A + o_tab);
     P.plan_ws = cfg->planner == D2D_PLANNER_PRIMITIVE ? (A + o_plan_ws) : nullptr;
     P.plan_list = (int *)(A + o_plan_list);
+    P.plan_over = (int *)(A + o_plan_over);
     h->stage_actions = (double *)(A + o_stage);
 
     DevTables tab;
@@ -544,7 +547,7 @@ extern "C" int d2d_get_buffer(d2d_handle *h, const char *name, d2d_buffer_info *
         out->strides[0] = D2D_CELLS; out->strides[1] = D2D_GRID; out->strides[2] = 1; out->strides[3] = 1;
         return D2D_OK;
     }
-#ifdef D2D_WARP_PROF
+#if defined(D2D_WARP_PROF) || defined(D2D_PLAN_PROF)
     if (std::string(name) == "warp_prof") {
         out->dev_ptr = h->P.prof; out->nbytes = (int64_t)h->B * 96; out->dtype = D2D_I64; out->ndim = 2;
         out->shape[0] = h->B; out->shape[1] = 12; out->shape[2] = 1; out->shape[3] = 1;

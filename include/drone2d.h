@@ -73,7 +73,8 @@ enum {
     D2D_STAT_DYNAMIC_COLLISION, D2D_STAT_FREEZING, D2D_STAT_DEAD_LOCK, D2D_STAT_FLIGHT_STEPS,
     D2D_STAT_GRID_DISCOVERED, D2D_STAT_AGENTS_TRACKED, D2D_STAT_TRACKED_STEPS, D2D_STAT_PLANS,
     D2D_STAT_PLAN_FAILURES, D2D_STAT_REPLANS,
-    D2D_STAT_MIRROR_BYTES        /* local_map bytes stored into the host mirror (d2d_bind_host_mirror) */
+    D2D_STAT_MIRROR_BYTES,       /* local_map bytes stored into the host mirror (d2d_bind_host_mirror) */
+    D2D_STAT_PLAN_OVERFLOWS      /* A* searches that outgrew the small-footprint kernel and were redone by the large one */
 };
 
 /* Mirrors the reference `Params` object (utils.py:65-106) plus the batch shape.  The lookup tables are the
