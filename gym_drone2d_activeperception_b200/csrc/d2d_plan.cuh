@@ -993,18 +993,28 @@ __global__ void __launch_bounds__(D2D_PLAN_THREADS2) d2d_plan_kernel(const DevP 
 #define D2D_PS_NODES 512
 #define D2D_PS_HASH 1024
 #endif
-#define D2D_PS_MINB 6
+#define D2D_PS_MINB 5
 
 __host__ __device__ inline bool d2d_plan_small_ok(int n_u, double max_speed) {
     return n_u * n_u <= 64 && n_u <= 8 && max_speed < 60.0;      // key32 needs |v| < 64
 }
 __host__ __device__ inline size_t d2d_plan_small_smem_bytes(int NP) {
     const size_t NPe = (size_t)(NP + 7) / 8 * 8;
-    size_t b = D2D_BELIEF_STRIDE + NPe * 6 * 8 + (size_t)D2D_PS_NODES * 6 * 8 + (8 + 2 * D2D_MAX_SAMP) * 8       // doubles
+    size_t b = D2D_BELIEF_STRIDE + NPe * 6 * 8 + (size_t)D2D_PS_NODES * 6 * 8 + (8 + 2 * D2D_MAX_SAMP + 3 * 64 + 2) * 8   // doubles
              + (size_t)D2D_PS_HASH * 4 + 8 * 4                                                                    // words
              + (size_t)D2D_PS_HASH * 2 + (size_t)D2D_PS_NODES * 2 + (D2D_PS_THREADS / 32) * NPe * 2               // halves
              + (size_t)D2D_PS_NODES * 2 + 64 + (D2D_PS_THREADS / 32) * 64;                                        // bytes
     return (b + 15) / 16 * 16;
+}
+
+// d2d_node_key32 in 32-bit integer arithmetic (same value wherever that one is valid: |coordinate| < 2^31)
+__device__ __forceinline__ uint32_t d2d_node_key32i(double px, double py, double vx, double vy) {
+    const int ax = __double2int_rn(px), ay = __double2int_rn(py);
+    int a = ax / 10, b = ay / 10;
+    if (ax < 0 && a * 10 != ax) a -= 1;              // floor division (Python's //)
+    if (ay < 0 && b * 10 != ay) b -= 1;
+    const int c = __double2int_rn(vx) + 64, d = __double2int_rn(vy) + 64;
+    return ((uint32_t)((a + 32) & 127) << 21) | ((uint32_t)((b + 32) & 127) << 14) | ((uint32_t)(c & 127) << 7) | (uint32_t)(d & 127);
 }
 
 // the five belief probes of Planner.is_free (traj_planner.py:35-47) with all loads in flight: 1 if any of them reads OCCUPIED
@@ -1036,8 +1046,12 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
     double *uh = (double *)q8; q8 += 8 * 8;                              // u_space / 2
     double *ts = (double *)q8; q8 += (size_t)D2D_MAX_SAMP * 8;
     double *ts2 = (double *)q8; q8 += (size_t)D2D_MAX_SAMP * 8;
+    double *hx = (double *)q8; q8 += 64 * 8;                             // per primitive: x_acc / 2, y_acc / 2,
+    double *hy = (double *)q8; q8 += 64 * 8;
+    double *pc = (double *)q8; q8 += 64 * 8;                             // (x_acc^2 + y_acc^2) / 100  (:190)
+    double *cand_v = (double *)q8; q8 += 2 * 8;                          // next-node candidates of warp 0 / warp 1
     uint32_t *hkeys = (uint32_t *)q8; q8 += (size_t)D2D_PS_HASH * 4;
-    int *sh = (int *)q8; q8 += 8 * 4;                                    // [0] next node, [1] nodes, [2] open, [3] overflow, [4] nact, [7] ticket
+    int *sh = (int *)q8; q8 += 8 * 4;                                    // [1] nodes, [2] open, [3] overflow, [4] nact, [5], [6] candidate nodes, [7] ticket
     uint16_t *hvals = (uint16_t *)q8; q8 += (size_t)D2D_PS_HASH * 2;
     uint16_t *n_parent = (uint16_t *)q8; q8 += (size_t)D2D_PS_NODES * 2;
     uint16_t *live = (uint16_t *)q8 + (size_t)wid * NPe; q8 += (size_t)NW * NPe * 2;   // this warp's tracker list
@@ -1048,6 +1062,11 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
 
     for (int i = tid; i < nu; i += T) uh[i] = P.tab->u_space[i] / 2.0;
     for (int i = tid; i < nsamp; i += T) { ts[i] = P.tab->t_samp[i]; ts2[i] = P.tab->t_samp2[i]; }
+    for (int pp = tid; pp < nprim; pp += T) {
+        const int ia = d2d_div_small(pp, nu), ib = pp - ia * nu;
+        const double xa = P.tab->u_space[ia], ya = P.tab->u_space[ib];
+        hx[pp] = xa / 2.0; hy[pp] = ya / 2.0; pc[pp] = (xa * xa + ya * ya) / 100.0;
+    }
     const int count = min(P.plan_list[P.B + (P.use_parity ? 1 + P.plan_list[P.B + 4] : 0)], P.B);
     // norm([nvx, nvy]) < max_speed  <=>  fma(nvy, nvy, nvx*nvx) <= speed_thr   (exact, no sqrt per item)
     const double speed_thr = d2d_sq_threshold(__longlong_as_double(__double_as_longlong(P.max_speed) - 1));
@@ -1089,10 +1108,11 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
             n_px[0] = x; n_py[0] = y; n_vx[0] = vx; n_vy[0] = vy; n_cost[0] = 0.0;
             n_open_total[0] = d2d_node_total(0.0, x, y, vx, vy, tx, ty);
             n_parent[0] = 0; n_itr[0] = 0; n_act[0] = 0;
-            const uint32_t key = d2d_node_key32(x, y, vx, vy);
+            const uint32_t key = d2d_node_key32i(x, y, vx, vy);
             const int s0 = (int)((key * 2654435761u) >> 19) & (D2D_PS_HASH - 1);
             hkeys[s0] = key; hvals[s0] = 0;
-            sh[0] = 0; sh[1] = 1; sh[2] = 1; sh[3] = 0;          // next node, nodes, open nodes, overflow
+            sh[1] = 1; sh[2] = 1; sh[3] = 0;                     // nodes, open nodes, overflow
+            cand_v[0] = n_open_total[0]; sh[5] = 0; cand_v[1] = INFINITY; sh[6] = 0x7fffffff;
         }
         if (tid < 64) vok[tid] = 1;
         __syncthreads();
@@ -1103,10 +1123,11 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
         int itr = 1;
         // An expansion is a latency chain, and the failed 99-expansion searches set the length of the kernel, so the chain is
         // kept short: two block barriers per expansion.  Between (B) and (A) every warp tests samples; between (A) and (B) warp 0
-        // alone closes the node, inserts the successors and picks the next node (sh[0]) while the others wait.
+        // closes the node and inserts the successors while warp 1 scans the older nodes for the next one to expand.
         for (;; itr++) {
             if (n_open == 0 || itr >= 100) break;                // traj_planner.py:149
-            const int cur = sh[0];                               // first minimal total_cost in insertion order (:155-158)
+            // first minimal total_cost in insertion order (min() over a dict, :155-158): the better of the two candidates
+            const int cur = (cand_v[1] < cand_v[0] || (cand_v[1] == cand_v[0] && sh[6] < sh[5])) ? sh[6] : sh[5];
             if (cur == 0x7fffffff) break;                        // only non-finite costs left (cannot happen)
             const double cpx = n_px[cur], cpy = n_py[cur], cvx = n_vx[cur], cvy = n_vy[cur];
             const int citr = n_itr[cur];
@@ -1117,13 +1138,12 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
             // ---- per warp (no barrier): the primitives that pass the speed test (:176), in primitive order.  Typically 10-15
             //      of the 64 do; only their samples are tested, one (primitive, sample) pair per thread.
             int nv = 0;
-#pragma unroll 1
+#pragma unroll 2
             for (int base = 0; base < nprim; base += 32) {
                 const int pp = base + lane;
                 bool pass = false;
                 if (pp < nprim) {
-                    const int ia = d2d_div_small(pp, nu), ib = pp - ia * nu;
-                    const double nvx = 1.0 * cvx + 4.0 * uh[ia], nvy = 1.0 * cvy + 4.0 * uh[ib];
+                    const double nvx = 1.0 * cvx + 4.0 * hx[pp], nvy = 1.0 * cvy + 4.0 * hy[pp];
                     pass = D2D_FMA(nvy, nvy, nvx * nvx) <= speed_thr;
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, pass);
@@ -1158,8 +1178,7 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
                 const int sI = d2d_div_small(q, nv), r = q - sI * nv;
                 if (!vok[r]) continue;                           // another sample of the primitive already failed
                 const int pp = vlist[r];
-                const int ia = d2d_div_small(pp, nu), ib = pp - ia * nu;
-                const double xh = uh[ia], yh = uh[ib];
+                const double xh = hx[pp], yh = hy[pp];
                 const double t = ts[sI], t2 = ts2[sI];
                 const double qx = rint(D2D_FMA(t2, xh, 1.0 * cpx + t * cvx));
                 const double qy = rint(D2D_FMA(t2, yh, 1.0 * cpy + t * cvy));
@@ -1180,6 +1199,8 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
                 if (lane == 0) n_open_total[cur] = INFINITY;     // open -> closed (:167-170)
                 n_open -= 1;
                 const double ccost = n_cost[cur];
+                double wbv = INFINITY;
+                int wbi = 0x7fffffff;
                 __syncwarp();
                 // ---- successors in (x_acc, y_acc) loop order (:187-206): vlist is in that order, 32 per round
 #pragma unroll 1
@@ -1191,14 +1212,13 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
                     bool is_new = false;
                     if (ok) {
                         pp = vlist[r];
-                        const int ia = d2d_div_small(pp, nu), ib = pp - ia * nu;
-                        const double xa = P.tab->u_space[ia], ya = P.tab->u_space[ib];
-                        nvx = 1.0 * cvx + 4.0 * (xa / 2.0);
-                        nvy = 1.0 * cvy + 4.0 * (ya / 2.0);
-                        spx = rint((1.0 * cpx + 2.0 * cvx) + 4.0 * (xa / 2.0));   // :188
-                        spy = rint((1.0 * cpy + 2.0 * cvy) + 4.0 * (ya / 2.0));
-                        scost = ccost + (xa * xa + ya * ya) / 100.0 + 10.0;      // :190
-                        const uint32_t key = d2d_node_key32(spx, spy, nvx, nvy);
+                        const double xh = hx[pp], yh = hy[pp];                   // x_acc / 2, y_acc / 2
+                        nvx = 1.0 * cvx + 4.0 * xh;
+                        nvy = 1.0 * cvy + 4.0 * yh;
+                        spx = rint((1.0 * cpx + 2.0 * cvx) + 4.0 * xh);          // :188
+                        spy = rint((1.0 * cpy + 2.0 * cvy) + 4.0 * yh);
+                        scost = ccost + pc[pp] + 10.0;                           // :190
+                        const uint32_t key = d2d_node_key32i(spx, spy, nvx, nvy);
                         int s = (int)((key * 2654435761u) >> 19) & (D2D_PS_HASH - 1);
                         for (;;) {
                             const uint32_t curk = hkeys[s];
@@ -1225,21 +1245,33 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
                         if (n_open_total[exist_idx] != INFINITY && n_cost[exist_idx] > scost) idx = exist_idx;
                     }
                     if (idx >= 0) {
+                        const double tot = d2d_node_total(scost, spx, spy, nvx, nvy, tx, ty);
                         n_px[idx] = spx; n_py[idx] = spy; n_vx[idx] = nvx; n_vy[idx] = nvy; n_cost[idx] = scost;
-                        n_open_total[idx] = d2d_node_total(scost, spx, spy, nvx, nvy, tx, ty);
+                        n_open_total[idx] = tot;
+                        if (tot < wbv || (tot == wbv && idx < wbi)) { wbv = tot; wbi = idx; }
                         n_parent[idx] = (uint16_t)cur; n_itr[idx] = (uint8_t)(citr + 1); n_act[idx] = (uint8_t)pp;
                     }
                     n_nodes += tot_new; n_open += tot_new;
                 }
                 vok[lane] = 1; vok[lane + 32] = 1;               // every primitive starts the next expansion as free
-                __syncwarp();
-                // ---- next node: first minimal total_cost in insertion order (min() over a dict, :155-158)
+                // warp 0's candidate for the next node: the best of the nodes it has just written (new or made cheaper)
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, wbv, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, wbi, off);
+                    if (ov < wbv || (ov == wbv && oi < wbi)) { wbv = ov; wbi = oi; }
+                }
+                if (lane == 0) { cand_v[0] = wbv; sh[5] = wbi; sh[1] = n_nodes; sh[2] = n_open; sh[3] = overflow ? 1 : 0; }
+            } else if (wid == 1) {
+                // ---- meanwhile warp 1 scans the nodes that existed before this expansion (without the one being closed).  A node
+                //      warp 0 is making cheaper right now may be read with its old, higher total: its new total is in warp 0's
+                //      candidate, so the better of the two candidates is the first minimum over the final values either way.
                 double bv = INFINITY;
                 int bi = 0x7fffffff;
-#pragma unroll 1
+#pragma unroll 2
                 for (int i = lane; i < n_nodes; i += 32) {
                     const double v = n_open_total[i];
-                    if (v < bv) { bv = v; bi = i; }
+                    if (v < bv && i != cur) { bv = v; bi = i; }
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
@@ -1247,7 +1279,7 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
                     const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
                     if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
                 }
-                if (lane == 0) { sh[0] = bi; sh[1] = n_nodes; sh[2] = n_open; sh[3] = overflow ? 1 : 0; }
+                if (lane == 0) { cand_v[1] = bv; sh[6] = bi; }
             }
             __syncthreads();                                     // (B) next node, counts and the overflow flag published
             n_nodes = sh[1]; n_open = sh[2];
@@ -1277,10 +1309,9 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
                     for (int c2 = goal; c2 != 0; c2 = n_parent[c2]) {
                         seg--;
                         const int par = n_parent[c2], pidx = n_act[c2];
-                        const int ia = d2d_div_small(pidx, nu), ib = pidx - ia * nu;
                         double *cf = P.traj_coeff + ((size_t)e * D2D_MAX_SEGMENTS + seg) * 6;
-                        cf[0] = n_px[par]; cf[1] = n_vx[par]; cf[2] = P.tab->u_space[ia] / 2.0;
-                        cf[3] = n_py[par]; cf[4] = n_vy[par]; cf[5] = P.tab->u_space[ib] / 2.0;
+                        cf[0] = n_px[par]; cf[1] = n_vx[par]; cf[2] = hx[pidx];
+                        cf[3] = n_py[par]; cf[4] = n_vy[par]; cf[5] = hy[pidx];
                     }
                     P.rec[e].nseg = depth; P.rec[e].cursor = 0; P.plan_ok[e] = 1;
                 } else {
