@@ -334,9 +334,18 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
     envs = [env] + [make_env() for _ in range(R - 1)]
     ox_out = torch.empty(B, dtype=torch.float64, device=dev)
 
+    # Oxford on the device: one step = Oxford.plan + env.step, through d2d_step_plan_oxford (the step's A* searches beside the
+    # gaze scoring of the envs that did not plan); --no-fused-oxford: the two calls d2d_plan_oxford + d2d_step
+    fused_ox = use_ox and pk["planner"] == "Primitive" and not args.no_fused_oxford
+    ox_next = {}
+
     def do_step(a, e=None):
         e = env if e is None else e
-        if use_ox:
+        if fused_ox:
+            if e not in ox_next:
+                ox_next[e] = e.plan_oxford(torch.empty(B, dtype=torch.float64, device=dev))
+            e.step_plan_oxford(ox_next[e], out=ox_next[e])
+        elif use_ox:
             e.step(e.plan_oxford(ox_out))
         else:
             e.step(a)
@@ -508,7 +517,14 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
         dstp, nbytes = a_bound.data_ptr(), B * 8
         srcs = [r.data_ptr() for r in a_rows]
 
+        if fused_ox:
+            env.plan_oxford(stage)              # primes the first step; every call below leaves the next step's actions there
+            torch.cuda.synchronize()
+
         def e2e_step_bound(t):
+            if fused_ox:
+                env.step_bound_plan_oxford()
+                return
             if use_ox:
                 env.plan_oxford(stage)
             else:
@@ -562,7 +578,8 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
         kernel_name = "d2d_step_fused_warp_kernel (1 launch/step)"
     else:
         kernel_name = "d2d_step_prim_warp_kernel + d2d_plan_small_kernel (+ d2d_plan_kernel for its overflow list) + d2d_step_post_list_kernel" + \
-                      (" + d2d_oxford_kernel" if use_ox else "") + " (whole step timed)"
+                      (" + d2d_oxford_kernel" if use_ox else "") + (" beside the A* kernels (d2d_step_plan_oxford)" if fused_ox else "") + \
+                      " (whole step timed)"
     achieved = algorithmic_bytes(N) * B / (ms_step * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", ("traffic_rollout_config%d.json" if (rollout and rollout["resident"]) else
@@ -598,7 +615,9 @@ def measure(ctx, cfg, worlds, t_world, unique, headline):
                              "d2d_bind_host_io: pinned action buffer rewritten by the caller every step (memcpy inside the timed "
                              "region) and read by the kernels in place; kernels store changed observation bytes + yaw + done "
                              "straight into the pinned host buffers (bytes counted on the device, mean per step, this rank); " +
-                             ("d2d_step_bound, stream synchronised per step" if (use_ox or pk["planner"] != "NoMove") else
+                             ("d2d_step_bound_plan_oxford (Oxford on the device: the actions never leave the GPU; the step's A* searches "
+                              "beside the gaze scoring), stream synchronised per step" if fused_ox else
+                              "d2d_step_bound, stream synchronised per step" if (use_ox or pk["planner"] != "NoMove") else
                               "d2d_step_pipelined: at <= 4116 envs ONE resident kernel serves the whole run (env state stays on chip; "
                               "a courier block pulls each step's actions out of the pinned buffer once the host has stamped the step; "
                               "everything but the yaw update runs before that gate; completion is a pinned word the host polls); "
@@ -689,6 +708,7 @@ def main():
     ap.add_argument("--view-range", type=int, default=0, help="drone_view_range in degrees (config 5 sweep: 90/180/360)")
     ap.add_argument("--planner", default=None, choices=["NoMove", "Primitive"], help="override the config's planner")
     ap.add_argument("--motion-profile", default=None, choices=["CVM", "RVO"], help="agent motion profile (default CVM)")
+    ap.add_argument("--no-fused-oxford", action="store_true", help="Oxford workloads: d2d_plan_oxford + d2d_step instead of d2d_step_plan_oxford")
     ap.add_argument("--e2e-full-copy", action="store_true", help="e2e leg with plain D2H copies instead of the zero-copy mirror")
     ap.add_argument("--gaze", default=None, choices=["scripted", "Oxford"],
                     help="scripted: random actions from the Oxford action set; Oxford: d2d_plan_oxford every step")

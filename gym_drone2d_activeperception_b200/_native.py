@@ -55,7 +55,7 @@ class D2DBufferInfo(C.Structure):
 
 
 EXPORTS = ["d2d_version", "d2d_last_error", "d2d_create", "d2d_destroy", "d2d_set_world", "d2d_set_rng", "d2d_set_rvo", "d2d_set_jerk_tables", "d2d_reset", "d2d_request_reset", "d2d_step", "d2d_rollout",
-           "d2d_step_host", "d2d_bind_host_mirror", "d2d_bind_host_io", "d2d_step_bound", "d2d_step_pipelined", "d2d_plan_oxford", "d2d_plan_gaze", "d2d_set_drone_pose", "d2d_get_buffer", "d2d_stats",
+           "d2d_step_host", "d2d_bind_host_mirror", "d2d_bind_host_io", "d2d_step_bound", "d2d_step_pipelined", "d2d_plan_oxford", "d2d_step_plan_oxford", "d2d_step_bound_plan_oxford", "d2d_plan_gaze", "d2d_set_drone_pose", "d2d_get_buffer", "d2d_stats",
            "d2d_launch_count"]
 
 _lib = None
@@ -95,6 +95,8 @@ def load():
     L.d2d_step_bound.argtypes = [vp]
     L.d2d_step_pipelined.argtypes = [vp, C.c_int32]
     L.d2d_plan_oxford.argtypes = [vp, vp, vp]
+    L.d2d_step_plan_oxford.argtypes = [vp, vp, vp, vp]
+    L.d2d_step_bound_plan_oxford.argtypes = [vp]
     L.d2d_plan_gaze.argtypes = [vp, C.c_int32, vp, vp]
     L.d2d_set_drone_pose.argtypes = [vp, vp, vp]
     L.d2d_get_buffer.argtypes = [vp, C.c_char_p, C.POINTER(D2DBufferInfo)]

@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     __syncwarp();                 // every lane has read the trajectory length before lane 0 pops a waypoint (step_pos)
     if (!need || blocked) {
         if (lane == 0) {
-            P.need_plan[e] = blocked ? 1 : 0;
+            P.need_plan[e] = blocked ? 2 : 0;     // 0: trajectory still valid, 1: waits for an A* search, 2: search decided here
             if (blocked) {
                 s.nseg = 0; s.cursor = 0; P.plan_ok[e] = 0;
                 atomicAdd(&P.stats[D2D_STAT_PLANS], 1ull);
@@ -1491,8 +1491,9 @@ __global__ void d2d_oxford_export_kernel(const DevP P, double *__restrict__ out)
 //     residue class), combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail; leaves outside the range are exactly
 //     +0.0 (x + 0.0 == x).
 //  E. the recursion's combine as a level-parallel tree (same operand pairs), then the strict-< argmax.
-__global__ void __launch_bounds__(D2D_OX_THREADS, D2D_OX_MINB) d2d_oxford_kernel(const DevP P, const OxProgram *__restrict__ prog,
-                                                                    double *__restrict__ actions_out) {
+// One env's Oxford.plan on the calling block (every thread of the block enters and leaves together).
+__device__ __forceinline__ void d2d_oxford_env(const DevP &P, const OxProgram *__restrict__ prog, double *__restrict__ actions_out,
+                                               const int e) {
     __shared__ double reward[D2D_OX_SPAN];
     __shared__ uint32_t vmask[D2D_OX_MAX_YAW][D2D_OX_WORDS];
     __shared__ int swep_w[D2D_OX_SPAN];                 // largest waypoint index per cell of the range (-1: none)
@@ -1500,8 +1501,7 @@ __global__ void __launch_bounds__(D2D_OX_THREADS, D2D_OX_MINB) d2d_oxford_kernel
     __shared__ double cs_s[D2D_OX_MAX_YAW + 1], sn_s[D2D_OX_MAX_YAW + 1];
     __shared__ double wpt[2];
     __shared__ int geo[12];                             // r0 r1 q0 q1 lo hi l0 l1 i0 i1 j0 j1
-    const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5;
-    if (e >= P.B) return;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5;
     // an env that reported done and will be re-initialised by its next step is seen by the policy as freshly reset
     // (the reference builds a new env + policy per episode, experiment.py:27-34)
     const bool fresh = P.rec[e].pending_reset || (P.auto_reset && P.done[e]);
@@ -1693,6 +1693,25 @@ __global__ void __launch_bounds__(D2D_OX_THREADS, D2D_OX_MINB) d2d_oxford_kernel
         }
         actions_out[e] = P.tab->v_yaw_space[best] / P.max_yaw_speed;
         P.ox_calls[e] = ncall;
+    }
+}
+
+// mode 0: every env (d2d_plan_oxford).  mode 1: every env whose step is complete when d2d_step_prim_warp_kernel has run,
+// i.e. all but the ones waiting for an A* search (need_plan == 1) -- d2d_step_plan_oxford runs this beside the searches.
+__global__ void __launch_bounds__(D2D_OX_THREADS, D2D_OX_MINB) d2d_oxford_kernel(const DevP P, const OxProgram *__restrict__ prog,
+                                                                    double *__restrict__ actions_out, const int mode) {
+    const int e = blockIdx.x;
+    if (e >= P.B || (mode == 1 && P.need_plan[e] == 1)) return;
+    d2d_oxford_env(P, prog, actions_out, e);
+}
+// ... and the envs of the step's planning list once their searches and d2d_step_post_list_kernel are done
+__global__ void __launch_bounds__(D2D_OX_THREADS, D2D_OX_MINB) d2d_oxford_list_kernel(const DevP P, const OxProgram *__restrict__ prog,
+                                                                         double *__restrict__ actions_out) {
+    const int count = min(P.plan_list[P.B + 1 + P.plan_list[P.B + 4]], P.B);
+#pragma unroll 1
+    for (int li = blockIdx.x; li < count; li += gridDim.x) {
+        d2d_oxford_env(P, prog, actions_out, P.plan_list[li]);
+        __syncthreads();          // the block's shared arrays are reused by its next env
     }
 }
 

@@ -48,6 +48,10 @@ struct d2d_handle {
     bool mir_stale = true;
     size_t smem_pre = 0, smem_plan = 0;
     int plan_small = -1;                 // d2d_plan_small_kernel: -1 not decided yet, 0 off, > 0 grid size (co-resident blocks)
+    int plan_sms = 0;                    // SMs of the device (set with plan_small)
+    // d2d_step_plan_oxford: the A* searches of a step run on this stream beside the Oxford scoring of the other envs
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t side_ev[2] = {nullptr, nullptr};     // [0] step kernel done (fork), [1] planning envs completed (join)
     std::vector<const void *> attr_funcs;   // kernels whose dynamic shared-memory limit this handle has raised
     // bound host path (d2d_bind_host_io)
     bool io_bound = false;
@@ -523,6 +527,8 @@ extern "C" int d2d_destroy(d2d_handle *h) {
                 h->dbg_total_ns / h->dbg_n * 1e-3);
     if (h->gate_host) cudaFreeHost((void *)h->gate_host);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    for (int i = 0; i < 2; i++) if (h->side_ev[i]) cudaEventDestroy(h->side_ev[i]);
     for (int i = 0; i < 3; i++) if (h->pipe_ev[i]) cudaEventDestroy(h->pipe_ev[i]);
     if (h->arena) cudaFree(h->arena);
     if (h->ox_export) cudaFree(h->ox_export);
@@ -843,6 +849,26 @@ extern "C" int d2d_step(d2d_handle *h, const double *actions_dev, void *stream) 
     return D2D_OK;
 }
 
+static int launch_prim_warp_entry(d2d_handle *h, const double *actions, cudaStream_t st, double *ox_next);
+
+extern "C" int d2d_step_plan_oxford(d2d_handle *h, const double *actions_dev, double *next_actions_dev, void *stream) {
+    if (!h || !actions_dev || !next_actions_dev) return D2D_ERR_INVALID;
+    D2D_NO_PIPE(h);
+    if (!h->world_set) { h->err = "d2d_step_plan_oxford before d2d_set_world"; return D2D_ERR_STATE; }
+    if (!(h->cfg.oxford & D2D_POLICY_OXFORD)) { h->err = "d2d_step_plan_oxford: handle was created without the Oxford state (cfg.oxford & 1)"; return D2D_ERR_STATE; }
+    if (h->cfg.var_cam != 0.0 && !h->rng_set) { h->err = "var_cam != 0: d2d_set_rng must provide the np.random stream state"; return D2D_ERR_STATE; }
+    if (h->cfg.planner != D2D_PLANNER_PRIMITIVE || h->cfg.envs_per_block > 0 || h->P.motion_rvo) {
+        // nothing to overlap (or a path made of other kernels): the two calls this entry point stands for
+        const int rc = d2d_step(h, actions_dev, stream);
+        return rc != D2D_OK ? rc : d2d_plan_oxford(h, next_actions_dev, stream);
+    }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const int rc = launch_prim_warp_entry(h, actions_dev, (cudaStream_t)stream, next_actions_dev);
+    if (rc != D2D_OK) return rc;
+    CUDA_TRY(h, cudaGetLastError());
+    return D2D_OK;
+}
+
 #define D2D_RESIDENT_WPB 28          // resident gated kernel: one 28-warp block per SM (28 x 148 = 4144 envs in flight)
 
 template <int WPB, int MINB, bool SYNC, bool GATED>
@@ -998,8 +1024,9 @@ extern "C" int d2d_bind_host_io(d2d_handle *h, const double *actions_host, uint8
 }
 
 // one synchronous step through the bound buffers (also refreshes a stale mirror with full copies)
-static int step_bound_sync(d2d_handle *h) {
-    const int rc = d2d_step(h, h->io_actions_dev, (void *)h->io_stream);
+static int step_bound_sync(d2d_handle *h, bool plan_oxford = false) {
+    const int rc = plan_oxford ? d2d_step_plan_oxford(h, h->io_actions_dev, h->stage_actions, (void *)h->io_stream)
+                               : d2d_step(h, h->io_actions_dev, (void *)h->io_stream);
     if (rc != D2D_OK) return rc;
     cudaStream_t st = h->io_stream;
     if (h->mir_stale) {
@@ -1017,6 +1044,17 @@ extern "C" int d2d_step_bound(d2d_handle *h) {
     if (!h->io_bound) { h->err = "d2d_step_bound before d2d_bind_host_io"; return D2D_ERR_STATE; }
     D2D_NO_PIPE(h);
     return step_bound_sync(h);
+}
+
+extern "C" int d2d_step_bound_plan_oxford(d2d_handle *h) {
+    if (!h) return D2D_ERR_INVALID;
+    if (!h->io_bound) { h->err = "d2d_step_bound_plan_oxford before d2d_bind_host_io"; return D2D_ERR_STATE; }
+    if (h->io_actions_dev != h->stage_actions) {
+        h->err = "d2d_step_bound_plan_oxford: the actions must come from \"actions_staging\" (bind with actions_host = NULL)";
+        return D2D_ERR_STATE;
+    }
+    D2D_NO_PIPE(h);
+    return step_bound_sync(h, true);
 }
 
 static int step_pipelined_prelaunch(d2d_handle *h, int32_t prelaunch_next) {

@@ -333,6 +333,12 @@ class Drone2DVecEnv(object):
         if rc != 0:
             self._check(rc, "d2d_step_bound")
 
+    def step_bound_plan_oxford(self):
+        """`step_bound()` with the Oxford policy on the device (d2d_step_bound_plan_oxford): steps with the actions in
+        "actions_staging", leaves the observation in the bound host buffers and the next step's actions in the staging buffer.
+        Prime the first step with `plan_oxford(env.buffer("actions_staging"))`."""
+        self._check(self._lib.d2d_step_bound_plan_oxford(self._h), "d2d_step_bound_plan_oxford")
+
     def step_pipelined(self, prelaunch_next=True):
         """One step through the bound buffers with the NEXT step's kernel pre-launched (d2d_step_pipelined): the action only
         turns the yaw at the end of a step, so the next step's action-independent work overlaps the caller's handling of this
@@ -370,6 +376,20 @@ class Drone2DVecEnv(object):
         if out is None:
             out = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
         self._check(self._lib.d2d_plan_oxford(self._h, C.c_void_p(out.data_ptr()), self._stream()), "d2d_plan_oxford")
+        return out
+
+    def step_plan_oxford(self, actions, out=None):
+        """`step(actions)` followed by `plan_oxford(out)` as ONE call (d2d_step_plan_oxford): one iteration of the reference's
+        `action = policy.plan(info); ...; info = env.step(action)` loop with identical results.  Under the Primitive planner
+        the step's A* searches run beside the gaze scoring of the envs that did not plan.  `out` may be `actions` (in place).
+        Returns the next actions (float64 CUDA tensor [B]); observation / done are read from the buffers as after step()."""
+        a = actions.to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
+        if a.numel() != self.num_envs:
+            raise ValueError("expected %d actions, got %d" % (self.num_envs, a.numel()))
+        if out is None:
+            out = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+        self._check(self._lib.d2d_step_plan_oxford(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(out.data_ptr()), self._stream()),
+                    "d2d_step_plan_oxford")
         return out
 
     def plan_gaze(self, policy, out=None):

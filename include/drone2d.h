@@ -260,6 +260,19 @@ int d2d_step_pipelined(d2d_handle *h, int32_t prelaunch_next);
  * actions_out_dev (DEVICE [num_envs] f64) and advances the policy state.  Requires cfg.oxford = 1. */
 int d2d_plan_oxford(d2d_handle *h, double *actions_out_dev, void *stream);
 
+/* d2d_step(actions_dev) followed by d2d_plan_oxford(next_actions_dev) -- one iteration of the reference's loop
+ * `action = policy.plan(info); _, _, done, info = env.step(action)` (main.py / experiment.py:33-36) as ONE call, with the same
+ * results as the two calls.  Under the Primitive planner the A* searches of the step (a latency chain that leaves most of every
+ * SM idle) and the completion of the envs that planned run on an internal side stream while `stream` already scores the gaze
+ * candidates of the envs whose step was complete without a search; the call returns with both joined on `stream`.
+ * next_actions_dev may be actions_dev (in place).  Other planners: the two calls back to back.  Requires cfg.oxford & 1. */
+int d2d_step_plan_oxford(d2d_handle *h, const double *actions_dev, double *next_actions_dev, void *stream);
+
+/* d2d_step_bound with the policy on the device: steps with the actions in "actions_staging" (bound with actions_host = NULL),
+ * leaves the observation in the bound host buffers and the NEXT step's Oxford actions in "actions_staging"
+ * (d2d_step_plan_oxford on the bound stream).  Prime the first step with d2d_plan_oxford(h, staging, stream). */
+int d2d_step_bound_plan_oxford(d2d_handle *h);
+
 /* Replaces NoControl / Rotating / LookAhead / LookGoal / Owl .plan(env.info) (yaw_planner.py:10-39, 136-255) for all envs:
  * writes the action per env to actions_out_dev (DEVICE [num_envs] f64).  `policy` is a d2d_gaze value.  Owl is called the
  * way experiment.py:33-34 calls it (the class object is the instance); its state (36 direction-uncertainty bins, the queue

@@ -296,3 +296,38 @@ def test_measurement_noise_with_auto_reset():
             _cmp_env_to_oracle(h, i, e, n, t, "noise")
     assert resets > 0 and int(env.buffer("tracker_active").sum()) >= 0
     env.close()
+
+
+@pytest.mark.parametrize("static_map,B", [("maps/obstacle_map.npy", 700), ("maps/empty_map.npy", 97)])
+def test_step_plan_oxford_equals_step_then_plan(static_map, B):
+    """d2d_step_plan_oxford (A* searches on the side stream beside the Oxford scoring of the envs that did not plan) against
+    the two calls it stands for, on twin envs with auto-reset: actions, every exposed field, trajectory coefficients, the
+    Oxford state and the statistics stay identical step by step -- also in place (next actions written over the inputs)."""
+    from gym_drone2d_activeperception_b200.params import Params
+    from gym_drone2d_activeperception_b200.world import generate_worlds
+    from test_gpu_parity import FIELDS
+    p = Params(debug=False, planner="Primitive", gaze_method="Oxford", map_id=900, static_map=static_map,
+               agent_number=10, agent_radius=10, agent_max_speed=20, drone_max_speed=40)
+    worlds = generate_worlds(p, 900 + np.arange(B))
+    ref = _env(p, B, worlds, auto_reset=True, oxford=True)
+    fused = _env(p, B, worlds, auto_reset=True, oxford=True)
+    a_f = fused.plan_oxford()
+    extra = ("traj_coeff", "oxford_last_time_observed", "need_plan")
+    planned = 0
+    for t in range(150):
+        a_r = ref.plan_oxford()
+        assert torch.equal(a_r, a_f), ("actions", t)
+        ref.step(a_r)
+        a_f = fused.step_plan_oxford(a_f, out=a_f)          # in place
+        torch.cuda.synchronize()
+        for k in tuple(FIELDS) + extra[:1] + extra[2:]:
+            assert torch.equal(ref.buffer(k), fused.buffer(k)), (k, t)
+        planned += int((ref.buffer("need_plan") == 1).sum())
+    # the policy state after the fused call is one plan() ahead of the reference env: compare after the reference catches up
+    a_r = ref.plan_oxford()
+    assert torch.equal(a_r, a_f)
+    assert torch.equal(ref.buffer(extra[1]), fused.buffer(extra[1]))
+    sr, sf = ref.stats(), fused.stats()
+    assert np.array_equal(sr[:14], sf[:14]) and sr[1] > 0 and planned > 0
+    ref.close()
+    fused.close()
