@@ -174,7 +174,12 @@ d2d_step_pre_kernel(const DevP P) {
 // appended to the compacted list for d2d_plan_kernel and completed by d2d_step_post_list_kernel.
 // The cells changed by this step's rays are recorded, so when the drone's cell (the window origin) is unchanged the
 // observation tensor is patched instead of rewritten.
-__host__ __device__ inline size_t d2d_prim_warp_extra(int NP) { return (size_t)NP * 5 * 8 + D2D_CHG_CAP * 4 + 32; }
+// (list of the env's active trackers [NP][5] +) changed-cell list + two counters.  d2d_step_prim_warp_kernel keeps the tracker list
+// in the agent arrays sx / sy / sr2 / mx / my (5 contiguous [NP] doubles: exactly its size), which nothing reads once the
+// tracker phase is over -- the drone-vs-agent test of the finish reads the new positions back from P.apos instead.  At 142
+// agents that takes a warp's slice from 15.5 KB to 9.8 KB: 5 blocks (20 warps) per SM instead of 3 (12).
+__host__ __device__ inline size_t d2d_trk_warp_extra(int NP) { return (size_t)NP * 5 * 8 + D2D_CHG_CAP * 4 + 32; }
+__host__ __device__ inline size_t d2d_prim_warp_extra(int NP) { (void)NP; return (size_t)D2D_CHG_CAP * 4 + 32; }
 
 __device__ D2D_COLD void d2d_finish_env_warp(const DevP &P, const BlockCtx &c, EnvS &s, int e, int lane,
                                                     double action, bool success, bool agents_in_smem, int nchg,
@@ -232,8 +237,8 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
     if (e >= P.B) return;
     unsigned char *slice = smem + (size_t)wid * d2d_warp_slice_bytes(P.NP, P.HW, d2d_prim_warp_extra(P.NP));
     const BlockCtx c = d2d_carve(slice, 1, P.NP, P.HW);
-    double *trk = (double *)(slice + d2d_step_smem_bytes(1, P.NP, P.HW));   // [NP][5]
-    uint32_t *chg = (uint32_t *)(trk + (size_t)P.NP * 5);                  // [D2D_CHG_CAP]
+    double *trk = c.sx;                                                    // [NP][5] over sx / sy / sr2 / mx / my, from the gather on
+    uint32_t *chg = (uint32_t *)(slice + d2d_step_smem_bytes(1, P.NP, P.HW));   // [D2D_CHG_CAP]
     int *cnt = (int *)(chg + D2D_CHG_CAP);                                 // [0] nact, [1] nchg
     EnvS &s = c.S[0];
     // plan-list counters are double buffered by a step parity that lives in DEVICE memory (plan_list[B+3], advanced by
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_prim_warp_kernel(
             }
         }
         __syncwarp();
-        d2d_finish_env_warp(P, c, s, e, lane, action, !blocked, true, cnt[1], chg, true);
+        d2d_finish_env_warp(P, c, s, e, lane, action, !blocked, false, cnt[1], chg, true);    // agents from P.apos: sx / sy hold the tracker list
     } else {
         if (lane == 0) {
             P.need_plan[e] = 1;
@@ -478,7 +483,7 @@ __device__ __forceinline__ bool d2d_jerk_plan_warp(const DevP &P, EnvS &s, const
     return found;
 }
 
-__host__ __device__ inline size_t d2d_jerk_warp_extra(int NP) { return d2d_prim_warp_extra(NP) + D2D_JERK_H * 8 + 96; }
+__host__ __device__ inline size_t d2d_jerk_warp_extra(int NP) { return d2d_trk_warp_extra(NP) + D2D_JERK_H * 8 + 96; }
 
 template <int WPB>
 __global__ void __launch_bounds__(WPB * 32, 28 / WPB) d2d_step_jerk_warp_kernel(const DevP P,
