@@ -1005,7 +1005,7 @@ __host__ __device__ inline bool d2d_plan_small_ok(int n_u, double max_speed) {
 }
 __host__ __device__ inline size_t d2d_plan_small_smem_bytes(int NP) {
     const size_t NPe = (size_t)(NP + 7) / 8 * 8;
-    size_t b = D2D_BELIEF_STRIDE + NPe * 6 * 8 + (size_t)D2D_PS_NODES * 6 * 8 + (8 + 2 * D2D_MAX_SAMP + 3 * 64 + 2) * 8   // doubles
+    size_t b = D2D_BELIEF_STRIDE + NPe * 6 * 8 + (size_t)D2D_PS_NODES * 6 * 8 + (8 + 2 * D2D_MAX_SAMP + 3 * 64 + 2 + 6 * 64 + 32) * 8   // doubles (+ 64 keys)
              + (size_t)D2D_PS_HASH * 4 + 8 * 4                                                                    // words
              + (size_t)D2D_PS_HASH * 2 + (size_t)D2D_PS_NODES * 2 + (D2D_PS_THREADS / 32) * NPe * 2               // halves
              + (size_t)D2D_PS_NODES * 2 + 64 + (D2D_PS_THREADS / 32) * 64;                                        // bytes
@@ -1020,6 +1020,18 @@ __device__ __forceinline__ uint32_t d2d_node_key32i(double px, double py, double
     if (ay < 0 && b * 10 != ay) b -= 1;
     const int c = __double2int_rn(vx) + 64, d = __double2int_rn(vy) + 64;
     return ((uint32_t)((a + 32) & 127) << 21) | ((uint32_t)((b + 32) & 127) << 14) | ((uint32_t)(c & 127) << 7) | (uint32_t)(d & 127);
+}
+
+// first minimum over a warp of (v, i) pairs with v >= +0.0 (or +inf): the bit patterns of non-negative doubles order like
+// unsigned integers, so three redux.sync steps (high word, low word, index) replace five shuffle rounds on the latency chain.
+// Every lane returns the winner.
+__device__ __forceinline__ void d2d_warp_first_min(double &v, int &i) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    const bool mine = hi == mh && lo == ml;
+    i = (int)__reduce_min_sync(0xffffffffu, mine ? (unsigned)i : 0x7fffffffu);
+    v = __hiloint2double((int)mh, (int)ml);
 }
 
 // the five belief probes of Planner.is_free (traj_planner.py:35-47) with all loads in flight: 1 if any of them reads OCCUPIED
@@ -1055,6 +1067,8 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
     double *hy = (double *)q8; q8 += 64 * 8;
     double *pc = (double *)q8; q8 += 64 * 8;                             // (x_acc^2 + y_acc^2) / 100  (:190)
     double *cand_v = (double *)q8; q8 += 2 * 8;                          // next-node candidates of warp 0 / warp 1
+    double *su = (double *)q8; q8 += 6 * 64 * 8;                         // successor per feasible primitive (by rank): px py vx vy cost total
+    uint32_t *su_key = (uint32_t *)q8; q8 += 64 * 4;                     // ... and its dict key
     uint32_t *hkeys = (uint32_t *)q8; q8 += (size_t)D2D_PS_HASH * 4;
     int *sh = (int *)q8; q8 += 8 * 4;                                    // [1] nodes, [2] open, [3] overflow, [4] nact, [5], [6] candidate nodes, [7] ticket
     uint16_t *hvals = (uint16_t *)q8; q8 += (size_t)D2D_PS_HASH * 2;
@@ -1158,8 +1172,7 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
             // ---- per warp: the trackers that can come near a sample of this expansion (see the kernel's header)
             int nlive = 0;
             {
-                const double c2 = D2D_FMA(cvy, cvy, cvx * cvx);
-                const double reach = 2.0 * (c2 <= P.max_speed * P.max_speed ? P.max_speed : d2d_sqrt(c2) + 1e-6) + 0.71;
+                const double reach = 2.0 * fmax(P.max_speed, fabs(cvx) + fabs(cvy)) + 0.71;     // |v0| <= |v0x| + |v0y|: no square root
 #pragma unroll 1
                 for (int base = 0; base < nact; base += 32) {
                     const int k = base + lane;
@@ -1199,11 +1212,27 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
                 }
                 if (occ) vok[r] = 0;
             }
-            __syncthreads();                                     // (A) verdicts of all samples in place
+            // ---- the successor of every feasible primitive (:187-195), computed by the last warp -- the one with the fewest samples
+            //      to test -- whatever the verdicts will be, so that warp 0 only has the dict and the node arrays left to do
+            if (wid == NW - 1) {
+                const double ccost = n_cost[cur];
+#pragma unroll 1
+                for (int r = lane; r < nv; r += 32) {
+                    const int pp = vlist[r];
+                    const double xh = hx[pp], yh = hy[pp];                       // x_acc / 2, y_acc / 2
+                    const double nvx = 1.0 * cvx + 4.0 * xh, nvy = 1.0 * cvy + 4.0 * yh;
+                    const double spx = rint((1.0 * cpx + 2.0 * cvx) + 4.0 * xh); // :188
+                    const double spy = rint((1.0 * cpy + 2.0 * cvy) + 4.0 * yh);
+                    const double scost = ccost + pc[pp] + 10.0;                  // :190
+                    su[r] = spx; su[64 + r] = spy; su[128 + r] = nvx; su[192 + r] = nvy; su[256 + r] = scost;
+                    su[320 + r] = d2d_node_total(scost, spx, spy, nvx, nvy, tx, ty);
+                    su_key[r] = d2d_node_key32i(spx, spy, nvx, nvy);
+                }
+            }
+            __syncthreads();                                     // (A) verdicts of all samples and the successors in place
             if (wid == 0) {
                 if (lane == 0) n_open_total[cur] = INFINITY;     // open -> closed (:167-170)
                 n_open -= 1;
-                const double ccost = n_cost[cur];
                 double wbv = INFINITY;
                 int wbi = 0x7fffffff;
                 __syncwarp();
@@ -1212,18 +1241,12 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
                 for (int base = 0; base < nv; base += 32) {
                     const int r = base + lane;
                     const bool ok = r < nv && vok[r];
-                    double nvx = 0, nvy = 0, spx = 0, spy = 0, scost = 0;
-                    int slot = -1, exist_idx = -1, pp = 0;
+                    double scost = 0;
+                    int slot = -1, exist_idx = -1;
                     bool is_new = false;
                     if (ok) {
-                        pp = vlist[r];
-                        const double xh = hx[pp], yh = hy[pp];                   // x_acc / 2, y_acc / 2
-                        nvx = 1.0 * cvx + 4.0 * xh;
-                        nvy = 1.0 * cvy + 4.0 * yh;
-                        spx = rint((1.0 * cpx + 2.0 * cvx) + 4.0 * xh);          // :188
-                        spy = rint((1.0 * cpy + 2.0 * cvy) + 4.0 * yh);
-                        scost = ccost + pc[pp] + 10.0;                           // :190
-                        const uint32_t key = d2d_node_key32i(spx, spy, nvx, nvy);
+                        scost = su[256 + r];
+                        const uint32_t key = su_key[r];
                         int s = (int)((key * 2654435761u) >> 19) & (D2D_PS_HASH - 1);
                         for (;;) {
                             const uint32_t curk = hkeys[s];
@@ -1250,22 +1273,17 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
                         if (n_open_total[exist_idx] != INFINITY && n_cost[exist_idx] > scost) idx = exist_idx;
                     }
                     if (idx >= 0) {
-                        const double tot = d2d_node_total(scost, spx, spy, nvx, nvy, tx, ty);
-                        n_px[idx] = spx; n_py[idx] = spy; n_vx[idx] = nvx; n_vy[idx] = nvy; n_cost[idx] = scost;
+                        const double tot = su[320 + r];
+                        n_px[idx] = su[r]; n_py[idx] = su[64 + r]; n_vx[idx] = su[128 + r]; n_vy[idx] = su[192 + r]; n_cost[idx] = scost;
                         n_open_total[idx] = tot;
                         if (tot < wbv || (tot == wbv && idx < wbi)) { wbv = tot; wbi = idx; }
-                        n_parent[idx] = (uint16_t)cur; n_itr[idx] = (uint8_t)(citr + 1); n_act[idx] = (uint8_t)pp;
+                        n_parent[idx] = (uint16_t)cur; n_itr[idx] = (uint8_t)(citr + 1); n_act[idx] = vlist[r];
                     }
                     n_nodes += tot_new; n_open += tot_new;
                 }
                 vok[lane] = 1; vok[lane + 32] = 1;               // every primitive starts the next expansion as free
                 // warp 0's candidate for the next node: the best of the nodes it has just written (new or made cheaper)
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, wbv, off);
-                    const int oi = __shfl_xor_sync(0xffffffffu, wbi, off);
-                    if (ov < wbv || (ov == wbv && oi < wbi)) { wbv = ov; wbi = oi; }
-                }
+                d2d_warp_first_min(wbv, wbi);
                 if (lane == 0) { cand_v[0] = wbv; sh[5] = wbi; sh[1] = n_nodes; sh[2] = n_open; sh[3] = overflow ? 1 : 0; }
             } else if (wid == 1) {
                 // ---- meanwhile warp 1 scans the nodes that existed before this expansion (without the one being closed).  A node
@@ -1278,12 +1296,7 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
                     const double v = n_open_total[i];
                     if (v < bv && i != cur) { bv = v; bi = i; }
                 }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                    if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-                }
+                d2d_warp_first_min(bv, bi);
                 if (lane == 0) { cand_v[1] = bv; sh[6] = bi; }
             }
             __syncthreads();                                     // (B) next node, counts and the overflow flag published
