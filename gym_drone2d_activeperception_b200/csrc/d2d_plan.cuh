@@ -1140,6 +1140,8 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
         bool success = false, overflow = false;
         int n_nodes = 1, n_open = 1;                     // kept by warp 0, published through sh[1], sh[2] at the end of an expansion
         int itr = 1;
+        int pend_i0 = -1, pend_i1 = -1;                  // warp 0: open nodes this lane has made cheaper, totals not yet stored
+        double pend_t0 = 0.0, pend_t1 = 0.0;
         // An expansion is a latency chain, and the failed 99-expansion searches set the length of the kernel, so the chain is
         // kept short: two block barriers per expansion.  Between (B) and (A) every warp tests samples; between (A) and (B) warp 0
         // closes the node and inserts the successors while warp 1 scans the older nodes for the next one to expand.
@@ -1275,7 +1277,11 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
                     if (idx >= 0) {
                         const double tot = su[320 + r];
                         n_px[idx] = su[r]; n_py[idx] = su[64 + r]; n_vx[idx] = su[128 + r]; n_vy[idx] = su[192 + r]; n_cost[idx] = scost;
-                        n_open_total[idx] = tot;
+                        // a new node's total is stored now; the total of an older node made cheaper only after barrier (B), so that
+                        // warp 1's scan of the older nodes reads values nobody is writing (warp 0's candidate carries the new one)
+                        if (is_new) n_open_total[idx] = tot;
+                        else if (base == 0) { pend_i0 = idx; pend_t0 = tot; }
+                        else { pend_i1 = idx; pend_t1 = tot; }
                         if (tot < wbv || (tot == wbv && idx < wbi)) { wbv = tot; wbi = idx; }
                         n_parent[idx] = (uint16_t)cur; n_itr[idx] = (uint8_t)(citr + 1); n_act[idx] = vlist[r];
                     }
@@ -1287,14 +1293,15 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
                 if (lane == 0) { cand_v[0] = wbv; sh[5] = wbi; sh[1] = n_nodes; sh[2] = n_open; sh[3] = overflow ? 1 : 0; }
             } else if (wid == 1) {
                 // ---- meanwhile warp 1 scans the nodes that existed before this expansion (without the one being closed).  A node
-                //      warp 0 is making cheaper right now may be read with its old, higher total: its new total is in warp 0's
-                //      candidate, so the better of the two candidates is the first minimum over the final values either way.
+                //      warp 0 is making cheaper right now still shows its old, higher total: its new total is in warp 0's
+                //      candidate, so the better of the two candidates is the first minimum over the final values.
                 double bv = INFINITY;
                 int bi = 0x7fffffff;
 #pragma unroll 2
                 for (int i = lane; i < n_nodes; i += 32) {
+                    if (i == cur) continue;                      // being closed by warp 0 right now
                     const double v = n_open_total[i];
-                    if (v < bv && i != cur) { bv = v; bi = i; }
+                    if (v < bv) { bv = v; bi = i; }
                 }
                 d2d_warp_first_min(bv, bi);
                 if (lane == 0) { cand_v[1] = bv; sh[6] = bi; }
@@ -1302,6 +1309,10 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
             __syncthreads();                                     // (B) next node, counts and the overflow flag published
             n_nodes = sh[1]; n_open = sh[2];
             if (sh[3]) { overflow = true; break; }
+            if (wid == 0) {                                      // the deferred totals, well before the next barrier (A)
+                if (pend_i0 >= 0) { n_open_total[pend_i0] = pend_t0; pend_i0 = -1; }
+                if (pend_i1 >= 0) { n_open_total[pend_i1] = pend_t1; pend_i1 = -1; }
+            }
         }
         __syncthreads();
         if (tid == 0) {

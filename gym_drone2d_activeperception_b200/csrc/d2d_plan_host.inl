@@ -67,11 +67,13 @@ static int launch_prim_warp(d2d_handle *h, const double *actions, cudaStream_t s
     d2d_step_post_list_kernel<4><<<lgrid, 128, 4 * d2d_warp_slice_bytes(1, 1, 0), ps>>>(h->P, actions);
     h->launches += 3;
     if (ox_next) {
+        // the planning envs are scored on the side stream too, as soon as they are complete: the main stream's Oxford kernel
+        // outlasts the searches (0.8 ms against 0.25 ms on BASELINE config 4), so nothing of them is left on the critical path
+        const int ogrid = h->B < h->plan_sms * D2D_OX_MINB ? h->B : h->plan_sms * D2D_OX_MINB;
+        d2d_oxford_list_kernel<<<ogrid, D2D_OX_THREADS, 0, ps>>>(h->P, h->ox_prog, ox_next);
         CUDA_TRY(h, cudaEventRecord(h->side_ev[1], ps));
         d2d_oxford_kernel<<<h->B, D2D_OX_THREADS, 0, st>>>(h->P, h->ox_prog, ox_next, 1);       // beside the searches
         CUDA_TRY(h, cudaStreamWaitEvent(st, h->side_ev[1], 0));
-        const int ogrid = h->B < h->plan_sms * D2D_OX_MINB ? h->B : h->plan_sms * D2D_OX_MINB;
-        d2d_oxford_list_kernel<<<ogrid, D2D_OX_THREADS, 0, st>>>(h->P, h->ox_prog, ox_next);    // the planning envs, now complete
         h->launches += 2;
     }
     return D2D_OK;

@@ -14,7 +14,7 @@ fi
 for c in 3 4; do
   python bench.py --config $c --steps 200 --warmup 20 --burn-in 300 --no-cpu-baseline --no-workloads > $O/${T}_bench_cfg${c}_small.json 2> $O/${T}_bench_cfg${c}_small.err
   [ -n "$AB_LARGE" ] && D2D_PLAN_SMALL=0 python bench.py --config $c --steps 200 --warmup 20 --burn-in 300 --no-cpu-baseline --no-workloads > $O/${T}_bench_cfg${c}_large.json 2> $O/${T}_bench_cfg${c}_large.err
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches_cfg${c}.csv python bench.py --config $c --steps 5 --warmup 3 --burn-in 100 --no-cpu-baseline --no-workloads > $O/${T}_l${c}.log 2>&1
+  [ -z "$AB_FAST" ] && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches_cfg${c}.csv python bench.py --config $c --steps 5 --warmup 3 --burn-in 100 --no-cpu-baseline --no-workloads > $O/${T}_l${c}.log 2>&1
 done
 T=$T python - <<'PY'
 import json, glob, csv, collections, os

@@ -5,10 +5,10 @@ T=${1:-cap}
 P=${2:-r2}
 O=gpurun_out
 D=profiles
-for f in bench_default bench_cfg2_reference_arm bench_cfg4_nomove bench_cfg2_rvo; do
+for f in bench_default bench_cfg2_reference_arm bench_cfg4_nomove bench_cfg2_rvo bench_cfg4_two_calls; do
   [ -s $O/${T}_$f.json ] && cp $O/${T}_$f.json $D/${P}_$f.json
 done
-for f in launches_cfg2.csv launches_cfg4.csv warp_timeline_cfg2.txt resident_timeline_cfg2.txt rollout_variants_cfg2.txt rollout_cfg5.txt \
+for f in launches_cfg2.csv launches_cfg3.csv launches_cfg4.csv plan_prof_cfg3.txt plan_prof_cfg4.txt warp_timeline_cfg2.txt resident_timeline_cfg2.txt rollout_variants_cfg2.txt rollout_cfg5.txt \
          sanitizer_memcheck.txt sanitizer_racecheck.txt; do
   [ -s $O/${T}_$f ] && cp $O/${T}_$f $D/${P}_$f
 done
@@ -16,6 +16,7 @@ rep() { [ -s $O/${T}_$1.ncu-rep ] && python tools/ncu_report.py $O/${T}_$1.ncu-r
 rep fused_cfg2 fused_cfg2 "ncu --set full --clock-control none --import-source on, one launch of the per-step fused kernel (d2d_step) at BASELINE config 2 (4096 envs, N=10, NoMove), 200 burn-in steps"
 rep rollout_cfg2 rollout_cfg2 "ncu --set full, one 200-step launch of d2d_rollout_warp_kernel<28,1,SYNC> at BASELINE config 2 (4096 envs, N=10, NoMove) -- the kernel behind bench.py's headline value"
 rep oxford_cfg4 oxford_cfg4 "ncu --set full, d2d_oxford_kernel at BASELINE config 4 (65536 envs, N=24, Primitive + Oxford), 150 burn-in steps"
+rep plan_small_cfg3 plan_small_cfg3 "ncu --set full, d2d_plan_small_kernel at BASELINE config 3 (65536 envs, N=142, Primitive planner), 150 burn-in steps"
 rep prim_cfg4 prim_cfg4 "ncu --set full, d2d_step_prim_warp_kernel at BASELINE config 4 (65536 envs, N=24, Primitive + Oxford), 150 burn-in steps"
 if [ -s $O/${T}_rollout_cfg2.ncu-rep ]; then
   python tools/hot_code.py $O/${T}_rollout_cfg2.ncu-rep d2d_rollout_warp_kernel $((4096*200)) > $D/${P}_hot_code_rollout_cfg2.txt

@@ -33,6 +33,12 @@ def main():
                 env.step_host(None, lm, yaw, dn)
             else:
                 env.step_host(table[torch.randint(0, 6, (B,), generator=g)].contiguous().pin_memory(), lm, yaw, dn)
+        if ox:      # d2d_step_plan_oxford: A* searches + completion + scoring of the planning envs on the side stream
+            env.bind_host_mirror(None, None, None)
+            a = env.plan_oxford()
+            for t in range(20):
+                a = env.step_plan_oxford(a, out=a)
+            torch.cuda.synchronize()
         print(name, env.stats()[:8])
         env.close()
     # round 2: Owl policy, Jerk_Primitive planner, pipelined bound stepping
