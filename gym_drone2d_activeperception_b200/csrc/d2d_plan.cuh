@@ -1195,8 +1195,7 @@ __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_ke
             const int nit = nv * nsamp;
 #pragma unroll 1
             for (int q = tid; q < nit; q += T) {
-                const int sI = d2d_div_small(q, nv), r = q - sI * nv;
-                if (!vok[r]) continue;                           // another sample of the primitive already failed
+                const int sI = d2d_div_small(q, nv), r = q - sI * nv;      // (the samples of a primitive run side by side: nothing to skip)
                 const int pp = vlist[r];
                 const double xh = hx[pp], yh = hy[pp];
                 const double t = ts[sI], t2 = ts2[sI];
