@@ -1,16 +1,22 @@
 // d2d_plan.cuh -- kernels for the Primitive planner path and the Oxford gaze policy (sm_100a).
 //
-// With planner == Primitive one env step is three launches (the planner verdict sits in the middle of
+// With planner == Primitive one env step is several launches (the planner verdict sits in the middle of
 // Drone2DEnv2.step, drone_v2.py:194-204, and an A* search is ~1000x longer than the rest of the step, so it gets
-// its own kernel over a compacted list of the envs that actually need a plan):
+// its own kernel over a compacted list of the envs that actually need a plan).  Default (one warp per env):
 //
-//   d2d_step_pre_kernel   P0-P3 of the fused kernel (agents, rays, trackers) + Primitive.replan_check
-//                         (traj_planner.py:220-233) + compaction of the envs whose trajectory is empty
-//   d2d_plan_kernel       Primitive.plan (traj_planner.py:125-218): one thread block per planning env, A* over
-//                         motion primitives with the reference's insertion-ordered-dict tie breaking
-//   d2d_step_post_kernel  brake / step_pos / step_yaw / is_collide / flags / done / observation
+//   d2d_step_prim_warp_kernel   agents, rays, trackers + Primitive.replan_check (traj_planner.py:220-233); envs whose
+//                               trajectory stays valid -- and envs whose search is decided by its start position alone --
+//                               finish their step here; the others are appended to the planning list
+//   d2d_plan_small_kernel       Primitive.plan (traj_planner.py:125-218): A* over motion primitives with the reference's
+//                               insertion-ordered-dict tie breaking, the whole search in shared memory (4 warps, 5 per SM)
+//   d2d_plan_kernel (mode 1)    the searches the small kernel abandoned for lack of node slots (usually none); mode 0: every
+//                               search, where the small kernel's packed keys / primitive count do not apply
+//   d2d_step_post_list_kernel   brake / step_pos / step_yaw / is_collide / flags / done / observation of the planning envs
 //
-// d2d_oxford_kernel is Oxford.plan (yaw_planner.py:81-127), one block per env.
+// Legacy block-per-E-envs path (envs_per_block > 0): d2d_step_pre_kernel -> d2d_plan_kernel -> d2d_step_post_kernel.
+//
+// d2d_oxford_kernel is Oxford.plan (yaw_planner.py:81-127), one block per env; d2d_oxford_list_kernel the same for the envs
+// of the planning list (d2d_step_plan_oxford runs the searches beside the scoring of the other envs).
 #pragma once
 #include "d2d_state.cuh"
 #include "d2d_math.cuh"
