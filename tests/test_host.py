@@ -326,3 +326,52 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["gpu_launches"] == 0 and d["config"]["workload"].startswith("configs[1]")
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_astar_tracker_cull_is_conservative():
+    """d2d_plan_small_kernel drops, per expansion, the trackers that cannot come near any sample: kept unless
+    |node - estimate(t_node)|^2 > (2 max(v_max, |v0x| + |v0y|) + 0.71 + clearance + 2 |v_trk| + 1)^2.  Brute force over random
+    nodes / trackers with the planner's own primitive and sample tables: no (speed-feasible primitive, sample) pair may fail
+    Planner.is_free's tracker test (traj_planner.py:54-58) against a dropped tracker -- also for start nodes faster than v_max."""
+    import oracle
+    vmax, drone_r = 40.0, 10.0
+    op = oracle.make_params(drone_max_speed=vmax, planner="Primitive")
+    u = np.array([op.u_space[i] for i in range(op.n_u)])
+    ts = np.array([op.t_samp[i] for i in range(op.n_samp)])
+    assert len(u) == 8 and ts[0] == 0.0 and ts[-1] < 2.0
+    hx, hy = [a.reshape(-1) for a in np.meshgrid(u / 2.0, u / 2.0, indexing="ij")]          # [64]
+    rng = np.random.RandomState(5)
+    n = 60000
+    c = rng.uniform(0, 500, (n, 2))
+    speed = np.where(rng.rand(n) < 0.85, rng.uniform(0, vmax, n), rng.uniform(vmax, 70, n))    # some start nodes above v_max
+    ang = rng.uniform(-np.pi, np.pi, n)
+    cv = np.stack([speed * np.cos(ang), speed * np.sin(ang)], 1)
+    gt0 = 2.0 * rng.randint(0, 50, n)
+    vt = rng.uniform(-40, 40, (n, 2))
+    rad = rng.uniform(5, 30, n)
+    clr = drone_r + rad + 5.0
+    # tracker estimates placed around the node at its time, from touching to far beyond the cull radius
+    d = rng.uniform(0, 400, n)
+    a2 = rng.uniform(-np.pi, np.pi, n)
+    reach = 2.0 * np.maximum(vmax, np.abs(cv[:, 0]) + np.abs(cv[:, 1])) + 0.71
+    # the last third head-on and just outside the cull radius: node and tracker fly at each other along the same line
+    k = 2 * n // 3
+    vt[k:] = -np.stack([np.cos(ang[k:]), np.sin(ang[k:])], 1) * np.hypot(vt[k:, 0], vt[k:, 1])[:, None]
+    lim = reach + clr + 2.0 * np.hypot(vt[:, 0], vt[:, 1]) + 1.0
+    d[k:], a2[k:] = lim[k:] * (1.0 + 1e-9) + rng.uniform(0, 0.5, n - k), ang[k:]
+    e0 = c + np.stack([d * np.cos(a2), d * np.sin(a2)], 1)                                     # estimate at global time gt0
+    m = e0 - gt0[:, None] * vt                                                                 # mu[:2] such that mu + gt0 v = e0
+    dd = c - (m + gt0[:, None] * vt)
+    keep = ~((dd[:, 1] * dd[:, 1] + dd[:, 0] * dd[:, 0]) > lim * lim)
+    nv = cv[:, None, :] + 4.0 * np.stack([hx, hy], 1)[None]                                    # [n, 64, 2]
+    feasible = np.hypot(nv[..., 0], nv[..., 1]) < vmax                                         # :176
+    hit_any = np.zeros(n, bool)
+    for t in ts:
+        q = np.rint(c[:, None, :] + t * cv[:, None, :] + (t * t) * np.stack([hx, hy], 1)[None])
+        e = (m + (t + gt0)[:, None] * vt)[:, None, :]
+        hit = (np.hypot(q[..., 0] - e[..., 0], q[..., 1] - e[..., 1]) <= clr[:, None]) & feasible
+        hit_any |= hit.any(1)
+    assert hit_any.sum() > 1000 and (~keep).sum() > 10000         # both cases are well populated
+    assert not (hit_any & ~keep).any()                            # a dropped tracker never decides a sample
+    # how much margin the rule leaves: the closest dropped tracker is still farther than its clearance from every sample
+    assert keep[hit_any].all()
