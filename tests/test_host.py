@@ -375,3 +375,30 @@ def test_astar_tracker_cull_is_conservative():
     assert not (hit_any & ~keep).any()                            # a dropped tracker never decides a sample
     # how much margin the rule leaves: the closest dropped tracker is still farther than its clearance from every sample
     assert keep[hit_any].all()
+
+
+def test_nonnegative_doubles_order_like_their_bit_patterns():
+    """d2d_warp_first_min (A* next-node choice) finds the first minimum of non-negative totals with integer redux steps on the
+    (high word, low word) of their bit patterns: for doubles >= +0.0 (incl. denormals and +inf) value order == unsigned order
+    of the 64-bit pattern, and equal values have equal patterns."""
+    rng = np.random.RandomState(9)
+    v = np.concatenate([rng.uniform(0, 1e4, 5000), 10.0 ** rng.uniform(-320, 300, 3000), [0.0, 5e-324, 2.2250738585072014e-308, np.inf, 1.0, 1.0 + 2 ** -52]])
+    v = np.concatenate([v, v[:500]])                      # exact duplicates
+    bits = v.view(np.uint64)
+    hi, lo = (bits >> np.uint64(32)).astype(np.uint64), (bits & np.uint64(0xFFFFFFFF)).astype(np.uint64)
+    i, j = rng.randint(0, v.size, 200000), rng.randint(0, v.size, 200000)
+    lt_bits = (hi[i] < hi[j]) | ((hi[i] == hi[j]) & (lo[i] < lo[j]))
+    assert np.array_equal(v[i] < v[j], lt_bits)
+    assert np.array_equal(v[i] == v[j], bits[i] == bits[j])
+    # the three-step reduction on a "warp" of 32 values picks NumPy's first minimum
+    for _ in range(2000):
+        w = rng.choice(v, 32)
+        idx = rng.permutation(600)[:32]                   # node indices, any order across lanes
+        b = w.view(np.uint64)
+        mh = (b >> np.uint64(32)).min()
+        cand = (b >> np.uint64(32)) == mh
+        ml = (b[cand] & np.uint64(0xFFFFFFFF)).min()
+        mine = cand & ((b & np.uint64(0xFFFFFFFF)) == ml)
+        best = idx[mine].min()
+        order = np.lexsort((idx, w))                      # by value, ties by node index
+        assert best == idx[order[0]]
