@@ -21,6 +21,7 @@
 #include "d2d_state.cuh"
 #include "d2d_math.cuh"
 #include "d2d_step.cuh"
+#include "d2d_plan_math.cuh"
 
 #define D2D_PLAN_SLOTS 296          // concurrent A* workspaces (2 per SM)
 #define D2D_PLAN_THREADS 128
@@ -47,12 +48,6 @@ __device__ __forceinline__ void d2d_waypoint_pos(const DevP &P, int e, int a, do
 __device__ __forceinline__ int d2d_belief_probe(const DevP &P, const uint8_t *bel, double x, double y) {
     if (x >= P.map_w || x < 0 || y >= P.map_h || y < 0) return 1;
     return bel[d2d_cell(x, P.scale, P.inv_scale) * D2D_GRID + d2d_cell(y, P.scale, P.inv_scale)];
-}
-
-// the same probe for integer-valued coordinates (A* samples, np.around at traj_planner.py:181): cells by integer arithmetic
-__device__ __forceinline__ int d2d_belief_probe_int(const uint8_t *bel, int x, int y, int w, int h) {
-    if (x >= w || x < 0 || y >= h || y < 0) return 1;            // utils.py:546-547
-    return bel[(x / 10) * D2D_GRID + (y / 10)];
 }
 
 // Planner.is_free (traj_planner.py:28-59); trk = active trackers as [mu0, mu1, mu2, mu3, radius]
@@ -626,12 +621,6 @@ __device__ __forceinline__ PlanWs d2d_plan_carve(unsigned char *base, int n_u) {
     return w;
 }
 
-// Primitive_Node.get_index (traj_planner.py:92-93): (round(px)//10, round(py)//10, round(vx), round(vy))
-__device__ __forceinline__ long long d2d_floordiv10(long long a) {
-    long long q = a / 10;
-    if ((a % 10 != 0) && (a < 0)) q -= 1;
-    return q;
-}
 __device__ __forceinline__ unsigned long long d2d_node_key(double px, double py, double vx, double vy) {
     const long long a = d2d_floordiv10((long long)rint(px)), b = d2d_floordiv10((long long)rint(py));
     const long long c = (long long)rint(vx), d = (long long)rint(vy);
@@ -721,13 +710,6 @@ __host__ __device__ inline size_t d2d_plan_smem_bytes(int NP, int n_u, int n_sam
     if (d2d_plan_cap(n_u) <= D2D_PLAN_SMEM_NODES)
         b += (size_t)D2D_PLAN_SMEM_NODES * 8 + (size_t)D2D_PLAN_SMEM_HASH * 6;
     return (b + 15) / 16 * 16;
-}
-
-// packs (round(px)//10, round(py)//10, round(vx), round(vy)) into 28 bits; valid for |v| < 64 and cells in [-32, 95]
-__device__ __forceinline__ uint32_t d2d_node_key32(double px, double py, double vx, double vy) {
-    const int a = (int)d2d_floordiv10((long long)rint(px)) + 32, b = (int)d2d_floordiv10((long long)rint(py)) + 32;
-    const int c = (int)rint(vx) + 64, d = (int)rint(vy) + 64;
-    return ((uint32_t)(a & 127) << 21) | ((uint32_t)(b & 127) << 14) | ((uint32_t)(c & 127) << 7) | (uint32_t)(d & 127);
 }
 
 // dict lookup / insert; returns the node index stored for the key (>= 0) or -1 after inserting a fresh slot (*slot)
@@ -1018,16 +1000,6 @@ __host__ __device__ inline size_t d2d_plan_small_smem_bytes(int NP) {
     return (b + 15) / 16 * 16;
 }
 
-// d2d_node_key32 in 32-bit integer arithmetic (same value wherever that one is valid: |coordinate| < 2^31)
-__device__ __forceinline__ uint32_t d2d_node_key32i(double px, double py, double vx, double vy) {
-    const int ax = __double2int_rn(px), ay = __double2int_rn(py);
-    int a = ax / 10, b = ay / 10;
-    if (ax < 0 && a * 10 != ax) a -= 1;              // floor division (Python's //)
-    if (ay < 0 && b * 10 != ay) b -= 1;
-    const int c = __double2int_rn(vx) + 64, d = __double2int_rn(vy) + 64;
-    return ((uint32_t)((a + 32) & 127) << 21) | ((uint32_t)((b + 32) & 127) << 14) | ((uint32_t)(c & 127) << 7) | (uint32_t)(d & 127);
-}
-
 // first minimum over a warp of (v, i) pairs with v >= +0.0 (or +inf): the bit patterns of non-negative doubles order like
 // unsigned integers, so three redux.sync steps (high word, low word, index) replace five shuffle rounds on the latency chain.
 // Every lane returns the winner.
@@ -1038,20 +1010,6 @@ __device__ __forceinline__ void d2d_warp_first_min(double &v, int &i) {
     const bool mine = hi == mh && lo == ml;
     i = (int)__reduce_min_sync(0xffffffffu, mine ? (unsigned)i : 0x7fffffffu);
     v = __hiloint2double((int)mh, (int)ml);
-}
-
-// the five belief probes of Planner.is_free (traj_planner.py:35-47) with all loads in flight: 1 if any of them reads OCCUPIED
-// (outside the map counts as occupied, utils.py:546-547)
-__device__ __forceinline__ int d2d_probe5_occ(const uint8_t *bel, int x, int y, int sd, int w, int h) {
-    const int xm = x - sd, xp = x + sd, ym = y - sd, yp = y + sd;
-    if (xm < 0 || xp < 0 || xm >= w || xp >= w || ym < 0 || yp < 0 || ym >= h || yp >= h)       // a probe may leave the map
-        return (d2d_belief_probe_int(bel, xm, y, w, h) == 1) | (d2d_belief_probe_int(bel, x, y, w, h) == 1) |
-               (d2d_belief_probe_int(bel, xp, y, w, h) == 1) | (d2d_belief_probe_int(bel, x, ym, w, h) == 1) |
-               (d2d_belief_probe_int(bel, x, yp, w, h) == 1);
-    const int cx = (x / 10) * D2D_GRID, cy = y / 10;
-    const int a = bel[(xm / 10) * D2D_GRID + cy], b = bel[cx + cy], c = bel[(xp / 10) * D2D_GRID + cy];
-    const int d = bel[cx + ym / 10], f = bel[cx + yp / 10];
-    return (a == 1) | (b == 1) | (c == 1) | (d == 1) | (f == 1);
 }
 
 __global__ void __launch_bounds__(D2D_PS_THREADS, D2D_PS_MINB) d2d_plan_small_kernel(const DevP P) {

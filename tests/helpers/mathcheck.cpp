@@ -33,3 +33,15 @@ extern "C" void mc_rvo_inside(const double *pA, const double *pB, const double *
         mode[i] = c.mode;
     }
 }
+
+// integer-cell helpers of the A* kernels (csrc/d2d_plan_math.cuh)
+#include "../../gym_drone2d_activeperception_b200/csrc/d2d_plan_math.cuh"
+extern "C" void mc_probe5(const uint8_t *bel, const int *x, const int *y, int *out, long n, int sd, int w, int h) {
+    for (long i = 0; i < n; i++) out[i] = d2d_probe5_occ(bel, x[i], y[i], sd, w, h);
+}
+extern "C" void mc_node_keys(const double *pv, unsigned *k32, unsigned *k32i, long n) {
+    for (long i = 0; i < n; i++) {
+        k32[i] = d2d_node_key32(pv[4 * i], pv[4 * i + 1], pv[4 * i + 2], pv[4 * i + 3]);
+        k32i[i] = d2d_node_key32i(pv[4 * i], pv[4 * i + 1], pv[4 * i + 2], pv[4 * i + 3]);
+    }
+}

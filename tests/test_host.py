@@ -103,6 +103,9 @@ def mathlib(tmp_path_factory):
     ip = np.ctypeslib.ndpointer(np.int32, flags="C")
     L.mc_norm2_cmp.argtypes = [dp, dp, dp, ip, ip, C.c_long]
     L.mc_rvo_inside.argtypes = [dp, dp, dp, dp, ip, ip, ip, C.c_long]
+    L.mc_probe5.argtypes = [np.ctypeslib.ndpointer(np.uint8, flags="C"), ip, ip, ip, C.c_long, C.c_int, C.c_int, C.c_int]
+    up = np.ctypeslib.ndpointer(np.uint32, flags="C")
+    L.mc_node_keys.argtypes = [dp, up, up, C.c_long]
     return L
 
 
@@ -402,3 +405,48 @@ def test_nonnegative_doubles_order_like_their_bit_patterns():
         best = idx[mine].min()
         order = np.lexsort((idx, w))                      # by value, ties by node index
         assert best == idx[order[0]]
+
+
+def test_astar_belief_probes_and_node_keys(mathlib):
+    """csrc/d2d_plan_math.cuh on the CPU.  (1) d2d_probe5_occ -- the five probes of Planner.is_free (traj_planner.py:35-47)
+    on an integer-valued sample, all loads issued together -- against OccupancyGridMap.get_grid (utils.py:545-548) restated
+    in Python, on samples inside the map, next to every border and outside it.  (2) The packed dict keys: the 32-bit-integer
+    form the small A* kernel uses equals the reference tuple (round(px)//10, round(py)//10, round(vx), round(vy)) field by
+    field and the 64-bit form, over the coordinate / velocity range a search can reach (halves round to even in both)."""
+    rng = np.random.RandomState(12)
+    bel = np.zeros(2560, np.uint8)
+    grid = rng.choice([0, 1, 2], (50, 50), p=[0.3, 0.25, 0.45]).astype(np.uint8)
+    bel[:2500] = grid.reshape(-1)
+    n = 200000
+    x = rng.randint(-40, 540, n).astype(np.int32)
+    y = rng.randint(-40, 540, n).astype(np.int32)
+    edge = rng.choice([0, 9, 10, 19, 20, 21, 479, 480, 489, 490, 499, 500], n // 4)
+    x[:n // 8], y[n // 8:n // 4] = edge[:n // 8], edge[n // 8:]
+    out = np.empty(n, np.int32)
+    mathlib.mc_probe5(bel, x, y, out, n, 20, 500, 500)
+
+    def get_grid(px, py):
+        outside = (px >= 500) | (px < 0) | (py >= 500) | (py < 0)
+        v = grid[np.clip(px // 10, 0, 49), np.clip(py // 10, 0, 49)]
+        return np.where(outside, 1, v)
+    ref = np.zeros(n, bool)
+    for ddx, ddy in ((-20, 0), (0, 0), (20, 0), (0, -20), (0, 20)):
+        ref |= get_grid(x + ddx, y + ddy) == 1
+    assert np.array_equal(out != 0, ref) and 0.2 < ref.mean() < 0.95
+    # (2) keys
+    m = 300000
+    pv = np.empty((m, 4))
+    pv[:, :2] = rng.uniform(-300, 900, (m, 2))
+    pv[:, 2:] = rng.uniform(-63.4, 63.4, (m, 2))
+    half = rng.rand(m) < 0.2
+    pv[half] = np.floor(pv[half]) + 0.5                                  # exact halves: round-half-even everywhere
+    pv[:, 2:] = np.clip(pv[:, 2:], -62.5, 62.5)                          # the packed key holds |round(v)| < 64 (drone_max_speed < 60)
+    pv[:1000, :2] = np.rint(pv[:1000, :2])                               # integer positions (every node but the start)
+    k32, k32i = np.empty(m, np.uint32), np.empty(m, np.uint32)
+    mathlib.mc_node_keys(np.ascontiguousarray(pv), k32, k32i, m)
+    assert np.array_equal(k32, k32i)
+    a = np.array([round(v) // 10 for v in pv[:20000, 0]]); b = np.array([round(v) // 10 for v in pv[:20000, 1]])
+    c = np.array([round(v) for v in pv[:20000, 2]]); d = np.array([round(v) for v in pv[:20000, 3]])
+    k = k32[:20000].astype(np.int64)
+    assert np.array_equal((k >> 21) & 127, a + 32) and np.array_equal((k >> 14) & 127, b + 32)
+    assert np.array_equal((k >> 7) & 127, c + 64) and np.array_equal(k & 127, d + 64)
