@@ -104,6 +104,9 @@ def run_batched_rows(params, num_envs, episodes=1, max_steps=100000, device="cud
         for k, i in enumerate(idx.cpu().numpy().tolist()):
             if played[i] >= episodes:
                 continue
+            # 'Agent tracked time': the reference sums len(ts) * 0.1 per archived tracker (experiment.py:74, 94) and the float sum
+            # depends on how the total splits over the trackers; the device keeps the count and the total only, so the column
+            # is the reference's value up to that rounding (<= a few ulp; compared at 1e-9 against reference rows in the tests)
             n = int(cnt[k])
             base, rem = divmod(int(tot[k]), n) if n else (0, 0)
             tracking_time = float(np.array([(base + (1 if j < rem else 0)) * 0.1 for j in range(n)]).sum())
