@@ -143,3 +143,43 @@ def test_jerk_primitive_live(kw, policy):
         assert np.array_equal(e.belief, r["belief"][t]) and e.c.done == int(r["done"][t]), t
         assert bool(e.c.plan_ok) == bool(r["plan_ok"][t]) and e.c.traj_len == r["traj_len"][t], t
     e.close()
+
+
+@pytest.mark.parametrize("blocker", ["belief_cell", "probe_cell", "tracker", "none"])
+def test_reference_search_from_blocked_start_expands_once(blocker):
+    """The rule d2d_step_prim_warp_kernel uses to decide a search without running it, on the reference's own Primitive.plan
+    (traj_planner.py:125-218): when is_free(start, 0) is False every primitive breaks at its first sample (the start position
+    at global time 0), nothing is added to the open set and plan() returns False after ONE expansion -- is_free is called once
+    per speed-feasible primitive and never again.  With a free start the same call explores further."""
+    ref_utils, ref_env, ref_traj, ref_yaw = ref_runner.import_reference()
+    env, params = ref_runner.make_env(planner="Primitive", map_id=7, agent_number=4)
+    drone, planner = env.drone, env.planner
+    planner.set_target(np.array([50, 460]))
+    x, y = drone.x, drone.y
+    assert np.linalg.norm(np.array([x, y]) - planner.target[:2]) > planner.search_threshold
+    scale = params.map_scale
+    if blocker == "belief_cell":
+        drone.map.grid_map[int(x // scale), int(y // scale)] = 1
+    elif blocker == "probe_cell":                         # one of the four probes at drone_radius + 10 (traj_planner.py:35-47)
+        drone.map.grid_map[int((x + params.drone_radius + 10) // scale), int(y // scale)] = 1
+    elif blocker == "tracker":
+        trk = drone.trackers[0]
+        trk.active = True
+        trk.mu_upds.append(np.array([[x + 3.0], [y - 2.0], [1.0], [1.0]]))       # estimate_pos reads mu_upds[-1] (utils.py:220-223)
+    calls = []
+    orig = planner.is_free
+
+    def spy(position, t, occupancy_map, trackers):
+        r = orig(position, t, occupancy_map, trackers)
+        calls.append((tuple(np.asarray(position, dtype=float)), float(t), bool(r)))
+        return r
+    planner.is_free = spy
+    planner.trajectory.clear()
+    ok = planner.plan(drone, params.dt)
+    n_prim = len(planner.u_space) ** 2
+    if blocker == "none":
+        assert len(calls) > n_prim                        # a free start: later samples and later expansions are tested
+        return
+    assert ok is False and len(planner.trajectory) == 0
+    assert 0 < len(calls) <= n_prim                       # one expansion, one (failed) sample per speed-feasible primitive
+    assert all(c == ((float(np.around(x)), float(np.around(y))), 0.0, False) for c in calls)
